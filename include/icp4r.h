@@ -1,0 +1,171 @@
+/* icp4r.h — C ABI of libicp4r_cuda: the B200 (sm_100a) drop-in for the registration hot path of
+ * invokermyself/ICP-4DRadar.
+ *
+ * The reference has no FFI of its own; its hot path sits behind two C++ call shapes:
+ *   - the ikd-Tree shape   KD_TREE<PointType>::{Build, Add_Points, Nearest_Search, Sector_Search, ...}
+ *                          (/root/reference/third_party/ikd-Tree/ikd_Tree.h:227-251, used at
+ *                          /root/reference/src/radar_odometry.cpp:92,347-348,390,396), and
+ *   - the PCL Registration shape  {setInputSource, setInputTarget, align, hasConverged, getFitnessScore,
+ *                          getFinalTransformation} (/root/reference/src/iterative_closest_point.cpp:510-521,
+ *                          /root/reference/src/radar_odometry.cpp:399-411).
+ * The header-only C++ adapters in icp-4dradar_b200/adapters/icp4r/ present those two shapes on top of
+ * the entry points below; INTEGRATION.md shows the two-line change at each reference call site.
+ *
+ * Conventions
+ *   - every function returns an icp4r_status (0 = ok); nothing throws or calls back across the boundary;
+ *     icp4r_last_error(h) describes the last failure on that handle.
+ *   - one handle = one CUDA device + one stream + one caller thread at a time; handles are independent.
+ *   - points are packed float rows  x, y, z, w  (w = intensity, carried not used); `mem` says whether the
+ *     caller's pointers (inputs AND outputs of that call) are host (ICP4R_HOST) or device (ICP4R_DEVICE).
+ *   - poses are row-major double[16]; the update convention is the left perturbation T <- exp(xi^) T with
+ *     xi = (omega, v), p' = R p + t.
+ *   - indices returned by the map are positions in insertion order (Build order, then every point ever
+ *     offered to Add_Points, kept or not); missing neighbour slots hold idx = -1, d2 = +inf.
+ *   - exact kNN: float d2 = (dx*dx + dy*dy) + dz*dz evaluated without FMA contraction
+ *     (calc_dist, ikd_Tree.cpp:1427-1431), kept iff (double)d2 <= max_dist^2 (ikd_Tree.cpp:880,895),
+ *     ordered by (d2, index) — ties go to the lowest index.
+ *   - there is no CPU fallback: without a usable CUDA device icp4r_create fails.
+ */
+#ifndef ICP4R_H
+#define ICP4R_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ICP4R_VERSION_MAJOR 0
+#define ICP4R_VERSION_MINOR 1
+#define ICP4R_MAX_K 16
+#define ICP4R_ACC_LEN 32
+
+typedef struct icp4r_ctx* icp4r_handle;
+
+typedef enum icp4r_status {
+    ICP4R_OK = 0,
+    ICP4R_ERR_INVALID = 1,     /* bad argument */
+    ICP4R_ERR_CUDA = 2,        /* CUDA runtime error (text in icp4r_last_error) */
+    ICP4R_ERR_NOMEM = 3,
+    ICP4R_ERR_STATE = 4,       /* e.g. map query before Build */
+    ICP4R_ERR_NCCL = 5,
+    ICP4R_ERR_UNSUPPORTED = 6
+} icp4r_status;
+
+typedef enum icp4r_mem { ICP4R_HOST = 0, ICP4R_DEVICE = 1 } icp4r_mem;
+
+/* residual kinds; definitions follow /root/reference/include/radarFactor.hpp */
+typedef enum icp4r_residual {
+    ICP4R_P2P_SVD = 0,     /* LidarDistanceFactor objective solved in closed form (Kabsch/Umeyama), what
+                              pcl::IterativeClosestPoint does at iterative_closest_point.cpp:510-514     */
+    ICP4R_P2P_GN = 1,      /* LidarDistanceFactor (radarFactor.hpp:140-171), Gauss-Newton 6x6           */
+    ICP4R_P2PLANE_KNN = 2, /* LidarPlaneNormFactor (radarFactor.hpp:105-137), plane from the k neighbours */
+    ICP4R_P2LINE = 3,      /* RadarEdgeFactor (radarFactor.hpp:11-54), line through the 2 nearest, s = 1  */
+    ICP4R_GICP = 4         /* fast_gicp cost (radar_odometry.cpp:399-405); next tier, ICP4R_ERR_UNSUPPORTED */
+} icp4r_residual;
+
+typedef struct icp4r_opts {
+    int32_t residual;        /* icp4r_residual */
+    int32_t k;               /* neighbours for P2PLANE_KNN (3..ICP4R_MAX_K, default 5); ignored otherwise */
+    int32_t max_iterations;  /* PCL default 10 */
+    int32_t early_exit;      /* 0: run exactly max_iterations */
+    double max_corr_dist;    /* <= 0 or +inf: ungated (PCL / fast_gicp defaults) */
+    double rot_eps;          /* early exit (GN kinds): |omega| < rot_eps && |v| < trans_eps */
+    double trans_eps;
+    double mse_abs_eps;      /* early exit (P2P_SVD): |mse_i - mse_{i-1}| < mse_abs_eps (PCL 1e-12) */
+    double plane_thresh;     /* P2PLANE_KNN: all k neighbours within this distance of the plane (0.2) */
+    double T0[16];           /* initial guess, row-major */
+} icp4r_opts;
+
+typedef struct icp4r_result {
+    int32_t converged;       /* PCL semantics: max_iterations reached or a criterion met */
+    int32_t iterations;
+    int32_t n_corr;          /* correspondences used by the last iteration */
+    int32_t n_fitness;
+    double fitness;          /* mean squared 1-NN distance after the final transform (getFitnessScore) */
+    double last_cost;
+} icp4r_result;
+
+/* Optional per-iteration debug dumps (caller-owned, same memory space as the call's `mem`; any may be NULL).
+ *   pose: [max_iterations][16]  pose BEFORE iteration i
+ *   acc : [max_iterations][ICP4R_ACC_LEN]
+ *         P2P_SVD -> n, sum p'(3), sum q(3), sum p' q^T (9, row-major), sum d2
+ *         GN kinds -> H upper triangle row-major (21), g = J^T r (6), cost, n
+ *   idx : [max_iterations][n][k] neighbour indices */
+typedef struct icp4r_dump {
+    double* pose;
+    double* acc;
+    int32_t* idx;
+} icp4r_dump;
+
+/* ---- lifecycle ------------------------------------------------------------------------------------ */
+int icp4r_create(int device, icp4r_handle* out);
+int icp4r_destroy(icp4r_handle h);
+const char* icp4r_last_error(icp4r_handle h);
+const char* icp4r_version(void);
+int icp4r_default_opts(icp4r_opts* o);
+/* run on an existing cudaStream_t (e.g. the harness' current stream) instead of the handle's own */
+int icp4r_set_stream(icp4r_handle h, void* cuda_stream);
+int icp4r_synchronize(icp4r_handle h);
+/* number of kernels this handle has launched so far (graph-replayed kernels included) */
+int icp4r_launch_count(icp4r_handle h, int64_t* out);
+
+/* ---- map: replaces KD_TREE<PointType> (ikd_Tree.h:227-251) ---------------------------------------- */
+/* Build (ikd_Tree.cpp:354-365): discards any previous map. cell_size <= 0 picks one from the density. */
+int icp4r_map_build(icp4r_handle h, const float* xyzw, int32_t n, int mem, float cell_size);
+/* set_downsample_param (ikd_Tree.h:232) */
+int icp4r_map_set_downsample(icp4r_handle h, float voxel);
+/* Add_Points (ikd_Tree.cpp:422-497). downsample_on = 0 appends; 1 keeps one point per voxel, the one
+ * nearest the voxel centre (new point wins ties). *n_replaced = the reference's return value. */
+int icp4r_map_add_points(icp4r_handle h, const float* xyzw, int32_t n, int mem, int downsample_on,
+                         int32_t* n_replaced);
+/* size() / validnum() (ikd_Tree.h:234-235) */
+int icp4r_map_size(icp4r_handle h, int32_t* size, int32_t* valid);
+/* tree_range() (ikd_Tree.h:248): min xyz, max xyz over valid points */
+int icp4r_map_range(icp4r_handle h, float out6[6]);
+/* Nearest_Search (ikd_Tree.cpp:368-398) for nq queries at once. idx/d2: [nq,k]; found: [nq] (may be NULL) */
+int icp4r_map_knn(icp4r_handle h, const float* q_xyzw, int32_t nq, int mem, int32_t k, double max_dist,
+                  int32_t* idx, float* d2, int32_t* found);
+/* same contract, forced through the exhaustive tiled kernel (no grid) — the on-device cross-check */
+int icp4r_map_knn_brute(icp4r_handle h, const float* q_xyzw, int32_t nq, int mem, int32_t k, double max_dist,
+                        int32_t* idx, float* d2, int32_t* found);
+/* Sector_Search (ikd_Tree.cpp:415-419,1098-1140): indices of matching points, unordered; *n_out may exceed cap */
+int icp4r_map_sector(icp4r_handle h, const float centre_xyz[3], float radius, float heading_deg, int mem,
+                     int32_t* idx_out, int32_t cap, int32_t* n_out);
+/* copy of the stored points in insertion order (valid flags optional) */
+int icp4r_map_points(icp4r_handle h, int mem, float* xyzw_out, uint8_t* valid_out, int32_t cap);
+
+/* ---- registration: replaces the PCL / fast_gicp align() calls -------------------------------------- */
+/* source vs an explicit target cloud (iterative_closest_point.cpp:510-521): builds a transient index */
+int icp4r_register(icp4r_handle h, const float* src_xyzw, int32_t n, const float* tgt_xyzw, int32_t m, int mem,
+                   const icp4r_opts* opts, double T_out[16], icp4r_result* res, const icp4r_dump* dump);
+/* source vs the handle's map (radar_odometry.cpp:390-411 with the ikd-Tree map as the target) */
+int icp4r_register_map(icp4r_handle h, const float* src_xyzw, int32_t n, int mem, const icp4r_opts* opts,
+                       double T_out[16], icp4r_result* res, const icp4r_dump* dump);
+/* n_pairs independent (source, target) pairs, CSR-style offsets ([n_pairs+1], in points), one CTA per pair
+ * with both clouds resident in shared memory. P2P_SVD and P2P_GN. T_out: [n_pairs][16]; res: [n_pairs].
+ * opts->T0 is the initial guess of every pair. Offsets and results follow `mem` too. */
+int icp4r_register_batch(icp4r_handle h, const float* src_xyzw, const int32_t* src_off, const float* tgt_xyzw,
+                         const int32_t* tgt_off, int32_t n_pairs, int mem, const icp4r_opts* opts, double* T_out,
+                         icp4r_result* res);
+
+/* ---- slab-sharded large maps (one process per GPU) -------------------------------------------------- */
+/* rank 0 makes an id, the host program broadcasts the 128 bytes (any transport), every rank joins */
+int icp4r_shard_unique_id(char id_out[128]);
+int icp4r_shard_init(icp4r_handle h, const char id[128], int rank, int world);
+/* registration against the union of all ranks' maps: every rank passes the same source; each source
+ * point is owned by the rank whose slab [slab_lo, slab_hi) along `axis` contains its transformed
+ * position; the 29 partial accumulators are summed across ranks every iteration; all ranks return the
+ * same pose. Requires a gated search and a halo >= max_corr_dist around each rank's map. */
+int icp4r_register_sharded(icp4r_handle h, const float* src_xyzw, int32_t n, int mem, const icp4r_opts* opts,
+                           int axis, float slab_lo, float slab_hi, double T_out[16], icp4r_result* res);
+
+/* ---- helpers on the path ----------------------------------------------------------------------------- */
+/* p' = R p + t in double, written back as float (pointAssociateToMap, radar_odometry.cpp:137-145) */
+int icp4r_transform_points(icp4r_handle h, const double T[16], const float* xyzw, int32_t n, int mem,
+                           float* xyzw_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ICP4R_H */

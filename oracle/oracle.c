@@ -1,0 +1,784 @@
+/* oracle.c — CPU ORACLE (TEST INFRASTRUCTURE, NOT PRODUCT CODE). See oracle.h for scope and pin status.
+ *
+ * Build: gcc -O3 -fopenmp -ffp-contract=off  (contraction MUST stay off: the reference is built with
+ * `-g` only, /root/reference/CMakeLists.txt:5-6, so its float/double expressions are evaluated with
+ * separate roundings; the CUDA library uses __fmul_rn/__fadd_rn/__dmul_rn/__dadd_rn to match).
+ */
+#include "oracle.h"
+
+#include <float.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+int orc_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+void orc_default_opts(orc_opts* o) {
+    memset(o, 0, sizeof(*o));
+    o->residual = ORC_P2P_SVD;
+    o->k = 1;
+    o->max_iterations = 10; /* PCL default; iterative_closest_point.cpp:513 leaves it */
+    o->early_exit = 0;
+    o->max_corr_dist = 0.0;
+    o->rot_eps = 2e-3;   /* fast_gicp defaults quoted in SURVEY.md §8 a11 */
+    o->trans_eps = 5e-4;
+    o->mse_abs_eps = 1e-12;
+    o->plane_thresh = 0.2;
+    for (int i = 0; i < 16; ++i) o->T0[i] = (i % 5 == 0) ? 1.0 : 0.0;
+}
+
+/* ------------------------------------------------------------------ kNN ---------------------------- */
+
+/* calc_dist, ikd_Tree.cpp:1427-1431: left-to-right float sum of squares */
+static inline float dist2f(const float* a, const float* b) {
+    float dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
+    return (dx * dx + dy * dy) + dz * dz;
+}
+
+static inline double gate2(double max_dist) {
+    if (!(max_dist > 0.0) || isinf(max_dist)) return INFINITY;
+    return max_dist * max_dist; /* ikd_Tree.cpp:880 */
+}
+
+void orc_knn(const float* tgt, const uint8_t* valid, int m, const float* q, int nq, int k, double max_dist,
+             int32_t* idx, float* d2, int32_t* found) {
+    const double g2 = gate2(max_dist);
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < nq; ++i) {
+        int32_t* bi = idx + (size_t)i * k;
+        float* bd = d2 + (size_t)i * k;
+        int cnt = 0;
+        for (int s = 0; s < k; ++s) {
+            bi[s] = -1;
+            bd[s] = INFINITY;
+        }
+        const float* qi = q + 4 * (size_t)i;
+        for (int j = 0; j < m; ++j) {
+            if (valid && !valid[j]) continue;
+            float d = dist2f(qi, tgt + 4 * (size_t)j);
+            if (!((double)d <= g2)) continue; /* ikd_Tree.cpp:895 gate (inclusive) */
+            /* ascending j => an equal distance never displaces an earlier (lower) index */
+            if (cnt == k && !(d < bd[k - 1])) continue;
+            int pos = (cnt < k) ? cnt : k - 1;
+            while (pos > 0 && d < bd[pos - 1]) {
+                bd[pos] = bd[pos - 1];
+                bi[pos] = bi[pos - 1];
+                --pos;
+            }
+            bd[pos] = d;
+            bi[pos] = j;
+            if (cnt < k) ++cnt;
+        }
+        if (found) found[i] = cnt;
+    }
+}
+
+void orc_knn_brute_cb(void* cloud, const float* q, int nq, int k, double max_dist, int32_t* idx, float* d2,
+                      int32_t* found) {
+    const orc_cloud* c = (const orc_cloud*)cloud;
+    orc_knn(c->xyzw, c->valid, c->m, q, nq, k, max_dist, idx, d2, found);
+}
+
+/* ------------------------------------------------------------------ transforms --------------------- */
+
+static inline void xform1(const double T[16], const float* p, double o[3]) {
+    const double x = p[0], y = p[1], z = p[2];
+    o[0] = ((T[0] * x + T[1] * y) + T[2] * z) + T[3];
+    o[1] = ((T[4] * x + T[5] * y) + T[6] * z) + T[7];
+    o[2] = ((T[8] * x + T[9] * y) + T[10] * z) + T[11];
+}
+
+void orc_transform(const double T[16], const float* xyzw, int n, float* out_f32, double* out_f64) {
+    for (int i = 0; i < n; ++i) {
+        double o[3];
+        xform1(T, xyzw + 4 * (size_t)i, o);
+        if (out_f32) {
+            out_f32[4 * (size_t)i + 0] = (float)o[0];
+            out_f32[4 * (size_t)i + 1] = (float)o[1];
+            out_f32[4 * (size_t)i + 2] = (float)o[2];
+            out_f32[4 * (size_t)i + 3] = xyzw[4 * (size_t)i + 3];
+        }
+        if (out_f64) {
+            out_f64[3 * (size_t)i + 0] = o[0];
+            out_f64[3 * (size_t)i + 1] = o[1];
+            out_f64[3 * (size_t)i + 2] = o[2];
+        }
+    }
+}
+
+void orc_mat4_mul(const double A[16], const double B[16], double C[16]) {
+    double R[16];
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            double s = 0.0;
+            for (int k = 0; k < 4; ++k) s += A[4 * i + k] * B[4 * k + j];
+            R[4 * i + j] = s;
+        }
+    memcpy(C, R, sizeof(R));
+}
+
+/* ------------------------------------------------------------------ residual functors -------------- */
+
+static inline void cross3(const double a[3], const double b[3], double c[3]) {
+    c[0] = a[1] * b[2] - a[2] * b[1];
+    c[1] = a[2] * b[0] - a[0] * b[2];
+    c[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+/* v' = q * v for a unit quaternion (x,y,z,w): v + w*(2 u x v) + u x (2 u x v) */
+static void quat_rotate(const double q[4], const double v[3], double o[3]) {
+    double uv[3], uuv[3];
+    cross3(q, v, uv);
+    uv[0] += uv[0];
+    uv[1] += uv[1];
+    uv[2] += uv[2];
+    cross3(q, uv, uuv);
+    o[0] = v[0] + q[3] * uv[0] + uuv[0];
+    o[1] = v[1] + q[3] * uv[1] + uuv[1];
+    o[2] = v[2] + q[3] * uv[2] + uuv[2];
+}
+
+/* identity.slerp(s, q) as the functors at radarFactor.hpp:26-28,78-80 use it */
+static void slerp_from_identity(double s, const double q[4], double o[4]) {
+    const double d = q[3]; /* dot(identity, q) */
+    const double ad = fabs(d);
+    double s0, s1;
+    if (ad >= 1.0 - DBL_EPSILON) {
+        s0 = 1.0 - s;
+        s1 = s;
+    } else {
+        const double th = acos(ad), sn = sin(th);
+        s0 = sin((1.0 - s) * th) / sn;
+        s1 = sin(s * th) / sn;
+    }
+    if (d < 0.0) s1 = -s1;
+    o[0] = s1 * q[0];
+    o[1] = s1 * q[1];
+    o[2] = s1 * q[2];
+    o[3] = s0 + s1 * q[3];
+}
+
+/* LidarDistanceFactor, radarFactor.hpp:147-160 */
+void orc_res_distance(const double q[4], const double t[3], const double p[3], const double c[3], double r[3]) {
+    double w[3];
+    quat_rotate(q, p, w);
+    r[0] = (w[0] + t[0]) - c[0];
+    r[1] = (w[1] + t[1]) - c[1];
+    r[2] = (w[2] + t[2]) - c[2];
+}
+
+/* LidarPlaneNormFactor, radarFactor.hpp:113-124 */
+void orc_res_plane_norm(const double q[4], const double t[3], const double p[3], const double n[3], double d,
+                        double r[1]) {
+    double w[3];
+    quat_rotate(q, p, w);
+    w[0] += t[0];
+    w[1] += t[1];
+    w[2] += t[2];
+    r[0] = (n[0] * w[0] + n[1] * w[1] + n[2] * w[2]) + d;
+}
+
+/* LidarPlaneFactor, radarFactor.hpp:63-64 (ctor normal) and :68-89 */
+void orc_res_plane(const double q[4], const double t[3], const double p[3], const double j[3],
+                   const double l[3], const double m[3], double s, double r[1]) {
+    double jl[3] = {j[0] - l[0], j[1] - l[1], j[2] - l[2]};
+    double jm[3] = {j[0] - m[0], j[1] - m[1], j[2] - m[2]};
+    double nrm[3];
+    cross3(jl, jm, nrm);
+    double len = sqrt(nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2]);
+    if (len > 0.0) {
+        nrm[0] /= len;
+        nrm[1] /= len;
+        nrm[2] /= len;
+    }
+    double qs[4], lp[3];
+    slerp_from_identity(s, q, qs);
+    quat_rotate(qs, p, lp);
+    lp[0] += s * t[0];
+    lp[1] += s * t[1];
+    lp[2] += s * t[2];
+    r[0] = (lp[0] - j[0]) * nrm[0] + (lp[1] - j[1]) * nrm[1] + (lp[2] - j[2]) * nrm[2];
+}
+
+/* RadarEdgeFactor, radarFactor.hpp:18-42 */
+void orc_res_edge(const double q[4], const double t[3], const double p[3], const double a[3],
+                  const double b[3], double s, double r[3]) {
+    double qs[4], lp[3];
+    slerp_from_identity(s, q, qs);
+    quat_rotate(qs, p, lp);
+    lp[0] += s * t[0];
+    lp[1] += s * t[1];
+    lp[2] += s * t[2];
+    double u[3] = {lp[0] - a[0], lp[1] - a[1], lp[2] - a[2]};
+    double v[3] = {lp[0] - b[0], lp[1] - b[1], lp[2] - b[2]};
+    double nu[3];
+    cross3(u, v, nu);
+    double de[3] = {a[0] - b[0], a[1] - b[1], a[2] - b[2]};
+    double dn = sqrt(de[0] * de[0] + de[1] * de[1] + de[2] * de[2]);
+    r[0] = nu[0] / dn;
+    r[1] = nu[1] / dn;
+    r[2] = nu[2] / dn;
+}
+
+/* ------------------------------------------------------------------ small dense algebra ------------ */
+
+/* One-sided (Hestenes) Jacobi SVD of a 3x3: A V = U S. Kabsch rotation R = V' U'^T with the column of
+ * the smallest singular value rebuilt by cross products so det(R) = +1 (Umeyama's reflection fix;
+ * PCL TransformationEstimationSVD -> pcl::umeyama). H = sum (p-pm)(q-qm)^T maps
+ * source to target: R = argmin sum |R p - q|^2. */
+void orc_svd3_rotation(const double H[9], double R[9]) {
+    double A[9], V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    memcpy(A, H, sizeof(A));
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        double off = 0.0;
+        for (int p = 0; p < 2; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                double al = 0, be = 0, ga = 0;
+                for (int i = 0; i < 3; ++i) {
+                    al += A[3 * i + p] * A[3 * i + p];
+                    be += A[3 * i + q] * A[3 * i + q];
+                    ga += A[3 * i + p] * A[3 * i + q];
+                }
+                if (ga == 0.0 || fabs(ga) <= 1e-300) continue;
+                double lim = 1e-16 * sqrt(al * be);
+                if (fabs(ga) <= lim) continue;
+                off += fabs(ga);
+                double zeta = (be - al) / (2.0 * ga);
+                double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+                for (int i = 0; i < 3; ++i) {
+                    double ap = A[3 * i + p], aq = A[3 * i + q];
+                    A[3 * i + p] = c * ap - s * aq;
+                    A[3 * i + q] = s * ap + c * aq;
+                    double vp = V[3 * i + p], vq = V[3 * i + q];
+                    V[3 * i + p] = c * vp - s * vq;
+                    V[3 * i + q] = s * vp + c * vq;
+                }
+            }
+        if (off == 0.0) break;
+    }
+    double sg[3];
+    for (int j = 0; j < 3; ++j)
+        sg[j] = sqrt(A[j] * A[j] + A[3 + j] * A[3 + j] + A[6 + j] * A[6 + j]);
+    /* indices of the two largest singular values (a,b) and the smallest (c), cyclic order a->b->c */
+    int c = 0;
+    if (sg[1] < sg[c]) c = 1;
+    if (sg[2] < sg[c]) c = 2;
+    int a = (c + 1) % 3, b = (c + 2) % 3;
+    double ua[3], ub[3], uc[3], va[3], vb[3], vc[3];
+    if (!(sg[a] > 0.0) || !(sg[b] > 0.0)) { /* rank < 2: rotation undefined, return identity */
+        for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+        return;
+    }
+    for (int i = 0; i < 3; ++i) {
+        ua[i] = A[3 * i + a] / sg[a];
+        ub[i] = A[3 * i + b] / sg[b];
+        va[i] = V[3 * i + a];
+        vb[i] = V[3 * i + b];
+    }
+    /* re-orthogonalise ub against ua (guards the nearly rank-1 case) */
+    double dab = ua[0] * ub[0] + ua[1] * ub[1] + ua[2] * ub[2];
+    double nb = 0;
+    for (int i = 0; i < 3; ++i) {
+        ub[i] -= dab * ua[i];
+        nb += ub[i] * ub[i];
+    }
+    nb = sqrt(nb);
+    for (int i = 0; i < 3; ++i) ub[i] /= nb;
+    cross3(ua, ub, uc);
+    cross3(va, vb, vc);
+    /* H = U S V^T (H V = U S); minimiser of sum |R p - q|^2 with H = sum p q^T is R = V U^T */
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) R[3 * i + j] = va[i] * ua[j] + vb[i] * ub[j] + vc[i] * uc[j];
+}
+
+static inline int tri(int i, int j) { /* upper-triangular row-major index, i<=j, 6x6 */
+    return i * 6 - i * (i - 1) / 2 + (j - i);
+}
+
+int orc_chol6_solve(const double H21[21], const double g[6], double x[6]) {
+    double L[36];
+    memset(L, 0, sizeof(L));
+    for (int j = 0; j < 6; ++j) {
+        double s = H21[tri(j, j)];
+        for (int k = 0; k < j; ++k) s -= L[6 * j + k] * L[6 * j + k];
+        if (!(s > 0.0)) return 1;
+        L[6 * j + j] = sqrt(s);
+        for (int i = j + 1; i < 6; ++i) {
+            double v = H21[tri(j, i)];
+            for (int k = 0; k < j; ++k) v -= L[6 * i + k] * L[6 * j + k];
+            L[6 * i + j] = v / L[6 * j + j];
+        }
+    }
+    double y[6];
+    for (int i = 0; i < 6; ++i) {
+        double s = -g[i];
+        for (int k = 0; k < i; ++k) s -= L[6 * i + k] * y[k];
+        y[i] = s / L[6 * i + i];
+    }
+    for (int i = 5; i >= 0; --i) {
+        double s = y[i];
+        for (int k = i + 1; k < 6; ++k) s -= L[6 * k + i] * x[k];
+        x[i] = s / L[6 * i + i];
+    }
+    return 0;
+}
+
+void orc_se3_exp(const double xi[6], double T[16]) {
+    const double wx = xi[0], wy = xi[1], wz = xi[2];
+    const double th2 = wx * wx + wy * wy + wz * wz, th = sqrt(th2);
+    double A, B, C; /* sin th/th, (1-cos th)/th^2, (th - sin th)/th^3 */
+    if (th < 1e-5) {
+        A = 1.0 - th2 / 6.0;
+        B = 0.5 - th2 / 24.0;
+        C = 1.0 / 6.0 - th2 / 120.0;
+    } else {
+        A = sin(th) / th;
+        B = (1.0 - cos(th)) / th2;
+        C = (th - sin(th)) / (th2 * th);
+    }
+    const double W[9] = {0, -wz, wy, wz, 0, -wx, -wy, wx, 0};
+    double W2[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double s = 0;
+            for (int k = 0; k < 3; ++k) s += W[3 * i + k] * W[3 * k + j];
+            W2[3 * i + j] = s;
+        }
+    double R[9], Vm[9];
+    for (int i = 0; i < 9; ++i) {
+        const double I = (i % 4 == 0) ? 1.0 : 0.0;
+        R[i] = I + A * W[i] + B * W2[i];
+        Vm[i] = I + B * W[i] + C * W2[i];
+    }
+    for (int i = 0; i < 3; ++i) {
+        T[4 * i + 0] = R[3 * i + 0];
+        T[4 * i + 1] = R[3 * i + 1];
+        T[4 * i + 2] = R[3 * i + 2];
+        T[4 * i + 3] = Vm[3 * i + 0] * xi[3] + Vm[3 * i + 1] * xi[4] + Vm[3 * i + 2] * xi[5];
+    }
+    T[12] = T[13] = T[14] = 0.0;
+    T[15] = 1.0;
+}
+
+int orc_plane_fit(const double* P, int k, double n[3], double* d) {
+    double m00 = 0, m01 = 0, m02 = 0, m11 = 0, m12 = 0, m22 = 0, v0 = 0, v1 = 0, v2 = 0;
+    for (int j = 0; j < k; ++j) {
+        const double x = P[3 * j], y = P[3 * j + 1], z = P[3 * j + 2];
+        m00 += x * x;
+        m01 += x * y;
+        m02 += x * z;
+        m11 += y * y;
+        m12 += y * z;
+        m22 += z * z;
+        v0 -= x;
+        v1 -= y;
+        v2 -= z;
+    }
+    const double c00 = m11 * m22 - m12 * m12, c01 = m02 * m12 - m01 * m22, c02 = m01 * m12 - m02 * m11;
+    const double c11 = m00 * m22 - m02 * m02, c12 = m01 * m02 - m00 * m12, c22 = m00 * m11 - m01 * m01;
+    const double det = (m00 * c00 + m01 * c01) + m02 * c02;
+    if (!(fabs(det) > 0.0) || !isfinite(det)) return 0;
+    double nx = ((c00 * v0 + c01 * v1) + c02 * v2) / det;
+    double ny = ((c01 * v0 + c11 * v1) + c12 * v2) / det;
+    double nz = ((c02 * v0 + c12 * v1) + c22 * v2) / det;
+    const double nn = sqrt((nx * nx + ny * ny) + nz * nz);
+    if (!(nn > 0.0) || !isfinite(nn)) return 0;
+    *d = 1.0 / nn;
+    n[0] = nx / nn;
+    n[1] = ny / nn;
+    n[2] = nz / nn;
+    return 1;
+}
+
+/* ------------------------------------------------------------------ accumulation ------------------- */
+
+static inline void acc_gn(double* acc, const double J[6], double r) {
+    int t = 0;
+    for (int i = 0; i < 6; ++i)
+        for (int j = i; j < 6; ++j) acc[t++] += J[i] * J[j];
+    for (int i = 0; i < 6; ++i) acc[21 + i] += J[i] * r;
+    acc[27] += r * r;
+}
+
+/* Accumulate one source point's contribution. pw = transformed point (double). Returns 1 if used. */
+static int contribute(int residual, int k, double plane_thresh, const double pw[3], const float* tgt,
+                      const int32_t* nn, const float* nd2, int found, double* acc) {
+    if (residual == ORC_P2P_SVD) {
+        if (found < 1) return 0;
+        const float* c = tgt + 4 * (size_t)nn[0];
+        const double q[3] = {c[0], c[1], c[2]};
+        acc[0] += 1.0;
+        for (int i = 0; i < 3; ++i) {
+            acc[1 + i] += pw[i];
+            acc[4 + i] += q[i];
+            for (int j = 0; j < 3; ++j) acc[7 + 3 * i + j] += pw[i] * q[j];
+        }
+        acc[16] += (double)nd2[0];
+        return 1;
+    }
+    if (residual == ORC_P2P_GN) {
+        if (found < 1) return 0;
+        const float* c = tgt + 4 * (size_t)nn[0];
+        /* r = p' - c, J = [-[p']x | I]  (LidarDistanceFactor, radarFactor.hpp:156-158) */
+        const double r[3] = {pw[0] - c[0], pw[1] - c[1], pw[2] - c[2]};
+        const double J0[6] = {0, pw[2], -pw[1], 1, 0, 0};
+        const double J1[6] = {-pw[2], 0, pw[0], 0, 1, 0};
+        const double J2[6] = {pw[1], -pw[0], 0, 0, 0, 1};
+        acc_gn(acc, J0, r[0]);
+        acc_gn(acc, J1, r[1]);
+        acc_gn(acc, J2, r[2]);
+        acc[28] += 1.0;
+        return 1;
+    }
+    if (residual == ORC_P2PLANE_KNN) {
+        if (found < k || k < 3) return 0;
+        double P[3 * 16];
+        for (int j = 0; j < k; ++j) {
+            const float* c = tgt + 4 * (size_t)nn[j];
+            P[3 * j] = c[0];
+            P[3 * j + 1] = c[1];
+            P[3 * j + 2] = c[2];
+        }
+        double n[3], d;
+        if (!orc_plane_fit(P, k, n, &d)) return 0;
+        for (int j = 0; j < k; ++j) {
+            double e = ((n[0] * P[3 * j] + n[1] * P[3 * j + 1]) + n[2] * P[3 * j + 2]) + d;
+            if (!(fabs(e) <= plane_thresh)) return 0;
+        }
+        /* r = n.p' + d (LidarPlaneNormFactor, radarFactor.hpp:122), J = [(p' x n)^T | n^T] */
+        const double r = ((n[0] * pw[0] + n[1] * pw[1]) + n[2] * pw[2]) + d;
+        double pxn[3];
+        cross3(pw, n, pxn);
+        const double J[6] = {pxn[0], pxn[1], pxn[2], n[0], n[1], n[2]};
+        acc_gn(acc, J, r);
+        acc[28] += 1.0;
+        return 1;
+    }
+    if (residual == ORC_P2LINE) {
+        if (found < 2) return 0;
+        const float* fa = tgt + 4 * (size_t)nn[0];
+        const float* fb = tgt + 4 * (size_t)nn[1];
+        const double a[3] = {fa[0], fa[1], fa[2]}, b[3] = {fb[0], fb[1], fb[2]};
+        const double ba[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
+        const double L = sqrt((ba[0] * ba[0] + ba[1] * ba[1]) + ba[2] * ba[2]);
+        if (!(L > 0.0)) return 0;
+        /* r = ((p'-a) x (p'-b)) / |a-b|  (RadarEdgeFactor, radarFactor.hpp:34-39) */
+        const double u[3] = {pw[0] - a[0], pw[1] - a[1], pw[2] - a[2]};
+        const double v[3] = {pw[0] - b[0], pw[1] - b[1], pw[2] - b[2]};
+        double nu[3];
+        cross3(u, v, nu);
+        /* dr/dp' = [b-a]x / L ; dp'/dxi = [-[p']x | I] */
+        const double e[3] = {ba[0] / L, ba[1] / L, ba[2] / L};
+        const double D[9] = {0, -e[2], e[1], e[2], 0, -e[0], -e[1], e[0], 0};
+        const double Px[9] = {0, pw[2], -pw[1], -pw[2], 0, pw[0], pw[1], -pw[0], 0}; /* -[p']x */
+        for (int i = 0; i < 3; ++i) {
+            double J[6];
+            for (int j = 0; j < 3; ++j) {
+                J[j] = (D[3 * i] * Px[j] + D[3 * i + 1] * Px[3 + j]) + D[3 * i + 2] * Px[6 + j];
+                J[3 + j] = D[3 * i + j];
+            }
+            acc_gn(acc, J, nu[i] / L);
+        }
+        acc[28] += 1.0;
+        return 1;
+    }
+    return 0;
+}
+
+static int knn_k_for(const orc_opts* o) {
+    switch (o->residual) {
+        case ORC_P2P_SVD:
+        case ORC_P2P_GN:
+            return 1;
+        case ORC_P2LINE:
+            return 2;
+        default:
+            return o->k > 0 ? o->k : 5;
+    }
+}
+
+int orc_accumulate(const float* src, int n, const float* tgt, int m, orc_knn_fn knn, void* ctx,
+                   const orc_opts* o, const double T[16], double acc[ORC_ACC_LEN], int32_t* idx_out) {
+    (void)m;
+    const int k = knn_k_for(o);
+    if (k > 16) return -1;
+    float* q = (float*)malloc(sizeof(float) * 4 * (size_t)n);
+    double* pw = (double*)malloc(sizeof(double) * 3 * (size_t)n);
+    int32_t* idx = (int32_t*)malloc(sizeof(int32_t) * (size_t)n * k);
+    float* d2 = (float*)malloc(sizeof(float) * (size_t)n * k);
+    int32_t* fnd = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
+    orc_transform(T, src, n, q, pw);
+    knn(ctx, q, n, k, o->max_corr_dist, idx, d2, fnd);
+    memset(acc, 0, sizeof(double) * ORC_ACC_LEN);
+    int used = 0;
+    for (int i = 0; i < n; ++i)
+        used += contribute(o->residual, k, o->plane_thresh, pw + 3 * (size_t)i, tgt, idx + (size_t)i * k,
+                           d2 + (size_t)i * k, fnd[i], acc);
+    if (idx_out) memcpy(idx_out, idx, sizeof(int32_t) * (size_t)n * k);
+    free(q);
+    free(pw);
+    free(idx);
+    free(d2);
+    free(fnd);
+    return used;
+}
+
+static void fitness_pass(const float* src, int n, orc_knn_fn knn, void* ctx, double max_dist, const double T[16],
+                         orc_result* res) {
+    float* q = (float*)malloc(sizeof(float) * 4 * (size_t)n);
+    int32_t* idx = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
+    float* d2 = (float*)malloc(sizeof(float) * (size_t)n);
+    int32_t* fnd = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
+    orc_transform(T, src, n, q, NULL);
+    knn(ctx, q, n, 1, max_dist, idx, d2, fnd);
+    double s = 0;
+    int c = 0;
+    for (int i = 0; i < n; ++i)
+        if (fnd[i] > 0) {
+            s += (double)d2[i];
+            ++c;
+        }
+    res->n_fitness = c;
+    res->fitness = c ? s / c : INFINITY;
+    free(q);
+    free(idx);
+    free(d2);
+    free(fnd);
+}
+
+int orc_register(const float* src, int n, const float* tgt, int m, orc_knn_fn knn, void* ctx, const orc_opts* o,
+                 double T_out[16], orc_result* res, double* dump_pose, double* dump_acc, int32_t* dump_idx) {
+    const int k = knn_k_for(o);
+    double T[16];
+    memcpy(T, o->T0, sizeof(T));
+    orc_result r;
+    memset(&r, 0, sizeof(r));
+    double mse_prev = INFINITY;
+    int it = 0;
+    r.converged = 0;
+    for (; it < o->max_iterations; ++it) {
+        double acc[ORC_ACC_LEN];
+        if (dump_pose) memcpy(dump_pose + 16 * (size_t)it, T, sizeof(T));
+        int used = orc_accumulate(src, n, tgt, m, knn, ctx, o, T, acc,
+                                  dump_idx ? dump_idx + (size_t)it * n * k : NULL);
+        if (used < 0) return -1;
+        if (dump_acc) memcpy(dump_acc + ORC_ACC_LEN * (size_t)it, acc, sizeof(acc));
+        r.n_corr = used;
+        double D[16];
+        if (o->residual == ORC_P2P_SVD) {
+            if (used < 3) break; /* PCL: fewer than 3 correspondences -> not converged */
+            const double cnt = acc[0];
+            double pm[3], qm[3], H[9], R[9];
+            for (int i = 0; i < 3; ++i) {
+                pm[i] = acc[1 + i] / cnt;
+                qm[i] = acc[4 + i] / cnt;
+            }
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) H[3 * i + j] = acc[7 + 3 * i + j] / cnt - pm[i] * qm[j];
+            orc_svd3_rotation(H, R);
+            for (int i = 0; i < 3; ++i) {
+                D[4 * i + 0] = R[3 * i + 0];
+                D[4 * i + 1] = R[3 * i + 1];
+                D[4 * i + 2] = R[3 * i + 2];
+                D[4 * i + 3] = qm[i] - ((R[3 * i] * pm[0] + R[3 * i + 1] * pm[1]) + R[3 * i + 2] * pm[2]);
+            }
+            D[12] = D[13] = D[14] = 0;
+            D[15] = 1;
+            r.last_cost = acc[16] / cnt;
+            orc_mat4_mul(D, T, T);
+            if (o->early_exit) {
+                if (fabs(r.last_cost - mse_prev) < o->mse_abs_eps) {
+                    r.converged = 1;
+                    ++it;
+                    break;
+                }
+                mse_prev = r.last_cost;
+            }
+        } else {
+            if (used < 6) break;
+            double xi[6];
+            if (orc_chol6_solve(acc, acc + 21, xi)) break;
+            orc_se3_exp(xi, D);
+            r.last_cost = acc[27];
+            orc_mat4_mul(D, T, T);
+            if (o->early_exit) {
+                const double wn = sqrt(xi[0] * xi[0] + xi[1] * xi[1] + xi[2] * xi[2]);
+                const double vn = sqrt(xi[3] * xi[3] + xi[4] * xi[4] + xi[5] * xi[5]);
+                if (wn < o->rot_eps && vn < o->trans_eps) {
+                    r.converged = 1;
+                    ++it;
+                    break;
+                }
+            }
+        }
+    }
+    if (it >= o->max_iterations) r.converged = 1; /* PCL: reaching max_iterations counts as converged */
+    r.iterations = it;
+    fitness_pass(src, n, knn, ctx, o->max_corr_dist, T, &r);
+    memcpy(T_out, T, sizeof(T));
+    if (res) *res = r;
+    return 0;
+}
+
+/* ------------------------------------------------------------------ fp32 PCL mirror ---------------- */
+
+int orc_icp_p2p_f32(const float* src, int n, const float* tgt, int m, orc_knn_fn knn, void* ctx,
+                    int max_iterations, float T_out[16]) {
+    (void)m;
+    float T[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    float* cur = (float*)malloc(sizeof(float) * 4 * (size_t)n);
+    int32_t* idx = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
+    float* d2 = (float*)malloc(sizeof(float) * (size_t)n);
+    int32_t* fnd = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
+    memcpy(cur, src, sizeof(float) * 4 * (size_t)n);
+    for (int it = 0; it < max_iterations; ++it) {
+        knn(ctx, cur, n, 1, 0.0, idx, d2, fnd);
+        float pm[3] = {0, 0, 0}, qm[3] = {0, 0, 0};
+        int c = 0;
+        for (int i = 0; i < n; ++i)
+            if (fnd[i] > 0) {
+                for (int a = 0; a < 3; ++a) {
+                    pm[a] += cur[4 * i + a];
+                    qm[a] += tgt[4 * (size_t)idx[i] + a];
+                }
+                ++c;
+            }
+        if (c < 3) break;
+        for (int a = 0; a < 3; ++a) {
+            pm[a] /= (float)c;
+            qm[a] /= (float)c;
+        }
+        float Hf[9] = {0};
+        for (int i = 0; i < n; ++i)
+            if (fnd[i] > 0)
+                for (int a = 0; a < 3; ++a)
+                    for (int b = 0; b < 3; ++b)
+                        Hf[3 * a + b] += (cur[4 * i + a] - pm[a]) * (tgt[4 * (size_t)idx[i] + b] - qm[b]);
+        double H[9], R[9];
+        for (int a = 0; a < 9; ++a) H[a] = (double)(Hf[a] / (float)c);
+        orc_svd3_rotation(H, R); /* the 3x3 factorisation itself is not the float-sensitive part */
+        float D[16] = {0};
+        for (int a = 0; a < 3; ++a) {
+            for (int b = 0; b < 3; ++b) D[4 * a + b] = (float)R[3 * a + b];
+            D[4 * a + 3] = qm[a] - (D[4 * a] * pm[0] + D[4 * a + 1] * pm[1] + D[4 * a + 2] * pm[2]);
+        }
+        D[15] = 1.f;
+        float Tn[16];
+        for (int a = 0; a < 4; ++a)
+            for (int b = 0; b < 4; ++b) {
+                float s = 0;
+                for (int e = 0; e < 4; ++e) s += D[4 * a + e] * T[4 * e + b];
+                Tn[4 * a + b] = s;
+            }
+        memcpy(T, Tn, sizeof(T));
+        for (int i = 0; i < n; ++i) { /* PCL transforms the already-transformed cloud by the increment */
+            float x = cur[4 * i], y = cur[4 * i + 1], z = cur[4 * i + 2];
+            for (int a = 0; a < 3; ++a) cur[4 * i + a] = D[4 * a] * x + D[4 * a + 1] * y + D[4 * a + 2] * z + D[4 * a + 3];
+        }
+    }
+    memcpy(T_out, T, sizeof(T));
+    free(cur);
+    free(idx);
+    free(d2);
+    free(fnd);
+    return 0;
+}
+
+/* ------------------------------------------------------------------ map maintenance ---------------- */
+
+static inline int in_box(const float* p, const float bmin[3], const float bmax[3]) {
+    /* Search_by_range / Delete_by_range point test, ikd_Tree.cpp:1034,678 */
+    return bmin[0] <= p[0] && bmax[0] > p[0] && bmin[1] <= p[1] && bmax[1] > p[1] && bmin[2] <= p[2] &&
+           bmax[2] > p[2];
+}
+
+int orc_map_add_points(float* pts, uint8_t* valid, int* m_io, const float* add, int n, int downsample_on,
+                       float ds) {
+    int m = *m_io;
+    int counter = 0;
+    for (int i = 0; i < n; ++i) {
+        const float* p = add + 4 * (size_t)i;
+        float* slot = pts + 4 * (size_t)m; /* every offered point takes the next index */
+        memcpy(slot, p, 4 * sizeof(float));
+        if (!downsample_on) {
+            valid[m++] = 1;
+            continue;
+        }
+        float bmin[3], bmax[3], mid[3];
+        for (int a = 0; a < 3; ++a) {
+            bmin[a] = floorf(p[a] / ds) * ds;                                    /* ikd_Tree.cpp:432-437 */
+            bmax[a] = bmin[a] + ds;
+            mid[a] = (float)((double)bmin[a] + (double)(bmax[a] - bmin[a]) / 2.0); /* :438-440 */
+        }
+        float min_dist = dist2f(p, mid);
+        int winner = -1; /* -1: the new point */
+        int in_cnt = 0;
+        for (int j = 0; j < m; ++j) {
+            if (!valid[j] || !in_box(pts + 4 * (size_t)j, bmin, bmax)) continue;
+            ++in_cnt;
+            float d = dist2f(pts + 4 * (size_t)j, mid);
+            if (d < min_dist) { /* strict: the new point wins ties, :447 */
+                min_dist = d;
+                winner = j;
+            }
+        }
+        int same = (winner < 0);
+        if (!same) {
+            const float* w = pts + 4 * (size_t)winner;
+            same = fabs(p[0] - w[0]) < 1e-6 && fabs(p[1] - w[1]) < 1e-6 && fabs(p[2] - w[2]) < 1e-6; /* :1422 */
+        }
+        valid[m] = 0;
+        if (in_cnt > 1 || same) { /* :453-457 */
+            for (int j = 0; j < m; ++j)
+                if (valid[j] && in_box(pts + 4 * (size_t)j, bmin, bmax)) valid[j] = 0;
+            if (winner < 0)
+                valid[m] = 1;
+            else
+                valid[winner] = 1;
+            ++counter;
+        }
+        ++m;
+    }
+    *m_io = m;
+    return counter;
+}
+
+static float heading_of(const float* a, const float* b) { /* calc_heading, ikd_Tree.cpp:1434-1448 */
+    float h;
+    const float s = sqrtf(dist2f(a, b));
+    const float as = asinf((a[0] - b[0]) / s);
+    if (a[1] - b[1] < 0)
+        h = (float)(180 + (double)(as * 180) / M_PI);
+    else
+        h = (float)((double)(-as * 180) / M_PI);
+    if (h > 180 && h < 360) h = h - 360;
+    return h;
+}
+
+int orc_map_sector(const float* pts, const uint8_t* valid, int m, const float c[3], float radius, float heading,
+                   int32_t* out, int cap) {
+    int cnt = 0;
+    for (int j = 0; j < m; ++j) {
+        const float* p = pts + 4 * (size_t)j;
+        const int alive = !valid || valid[j];
+        const float dh = fabsf(heading_of(p, c) - heading);
+        /* ikd_Tree.cpp:1114-1116: (alive && in radius && dh < 60) || dh > 300. The reference lets
+         * lazily-deleted nodes through the `dh > 300` arm until the next rebuild physically drops them
+         * (timing dependent); the restatement never returns a deleted point. */
+        if (alive && ((dist2f(p, c) <= radius * radius && dh < 60) || dh > 300)) {
+            if (cnt < cap) out[cnt] = j;
+            ++cnt;
+        }
+    }
+    return cnt;
+}
