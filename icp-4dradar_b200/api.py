@@ -1,0 +1,338 @@
+"""ctypes bindings over include/icp4r.h — the same boundary a reference maintainer would bind.
+
+No compute happens here and nothing falls back to the CPU: if ``libicp4r_cuda.so`` is missing the loader
+raises, and if there is no CUDA device ``icp4r_create`` fails with ICP4R_ERR_CUDA.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+HOST, DEVICE = 0, 1
+P2P_SVD, P2P_GN, P2PLANE_KNN, P2LINE, GICP = range(5)
+ACC_LEN = 32
+MAX_K = 16
+
+EXPORTS = [
+    "icp4r_create", "icp4r_destroy", "icp4r_last_error", "icp4r_version", "icp4r_default_opts", "icp4r_set_stream",
+    "icp4r_synchronize", "icp4r_launch_count", "icp4r_map_build", "icp4r_map_set_downsample", "icp4r_map_add_points",
+    "icp4r_map_size", "icp4r_map_range", "icp4r_map_knn", "icp4r_map_knn_brute", "icp4r_map_sector", "icp4r_map_points",
+    "icp4r_register", "icp4r_register_map", "icp4r_register_batch", "icp4r_shard_unique_id", "icp4r_shard_init",
+    "icp4r_register_sharded", "icp4r_transform_points",
+]
+
+
+class Opts(C.Structure):
+    _fields_ = [
+        ("residual", C.c_int32),
+        ("k", C.c_int32),
+        ("max_iterations", C.c_int32),
+        ("early_exit", C.c_int32),
+        ("max_corr_dist", C.c_double),
+        ("rot_eps", C.c_double),
+        ("trans_eps", C.c_double),
+        ("mse_abs_eps", C.c_double),
+        ("plane_thresh", C.c_double),
+        ("T0", C.c_double * 16),
+    ]
+
+
+class Result(C.Structure):
+    _fields_ = [
+        ("converged", C.c_int32),
+        ("iterations", C.c_int32),
+        ("n_corr", C.c_int32),
+        ("n_fitness", C.c_int32),
+        ("fitness", C.c_double),
+        ("last_cost", C.c_double),
+    ]
+
+
+class Dump(C.Structure):
+    _fields_ = [("pose", C.c_void_p), ("acc", C.c_void_p), ("idx", C.c_void_p)]
+
+
+RESULT_DTYPE = np.dtype([("converged", np.int32), ("iterations", np.int32), ("n_corr", np.int32), ("n_fitness", np.int32),
+                         ("fitness", np.float64), ("last_cost", np.float64)])
+assert RESULT_DTYPE.itemsize == C.sizeof(Result)
+
+
+class Icp4rError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"icp4r status {code}: {msg}")
+        self.code = code
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, "libicp4r_cuda.so")
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load libicp4r_cuda.so (fails loudly when it has not been built)."""
+    global _lib
+    if _lib is None:
+        p = lib_path()
+        if not os.path.exists(p):
+            raise FileNotFoundError(f"{p} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                    "(there is no CPU fallback)")
+        lib = C.CDLL(p)
+        lib.icp4r_last_error.restype = C.c_char_p
+        lib.icp4r_last_error.argtypes = [C.c_void_p]
+        lib.icp4r_version.restype = C.c_char_p
+        _lib = lib
+    return _lib
+
+
+def default_opts(**kw) -> Opts:
+    o = Opts()
+    load_library().icp4r_default_opts(C.byref(o))
+    for k, v in kw.items():
+        if k == "T0":
+            v = np.asarray(v, dtype=np.float64).reshape(16)
+            for i in range(16):
+                o.T0[i] = float(v[i])
+        else:
+            setattr(o, k, v)
+    return o
+
+
+def _ptr(a):
+    """(pointer, mem) for a numpy array, a torch tensor (cpu or cuda) or None."""
+    if a is None:
+        return None, None
+    if isinstance(a, np.ndarray):
+        return C.c_void_p(a.ctypes.data), HOST
+    # torch tensor
+    return C.c_void_p(a.data_ptr()), (DEVICE if a.is_cuda else HOST)
+
+
+def _f4(a):
+    if isinstance(a, np.ndarray):
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        assert a.ndim == 2 and a.shape[1] == 4, a.shape
+        return a
+    assert a.dim() == 2 and a.shape[1] == 4 and a.is_contiguous() and a.dtype.is_floating_point and a.element_size() == 4
+    return a
+
+
+def _knn_k(residual, k):
+    return 1 if residual in (P2P_SVD, P2P_GN) else (2 if residual == P2LINE else (k if k > 0 else 5))
+
+
+class Icp4r:
+    """One handle = one device + one stream. Methods take numpy arrays (host path, copies inside the call) or
+    torch CUDA tensors (device path, zero-copy)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.icp4r_create(C.c_int(device), C.byref(h))
+        if rc != 0:
+            raise Icp4rError(rc, self.lib.icp4r_last_error(None).decode())
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.icp4r_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise Icp4rError(rc, self.lib.icp4r_last_error(self.h).decode())
+
+    # ---- lifecycle
+    def set_stream(self, cuda_stream_ptr: int):
+        self._ck(self.lib.icp4r_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def synchronize(self):
+        self._ck(self.lib.icp4r_synchronize(self.h))
+
+    def launch_count(self) -> int:
+        v = C.c_int64(0)
+        self._ck(self.lib.icp4r_launch_count(self.h, C.byref(v)))
+        return v.value
+
+    # ---- map
+    def map_build(self, pts, cell_size: float = 0.0):
+        pts = _f4(pts)
+        p, mem = _ptr(pts)
+        self._ck(self.lib.icp4r_map_build(self.h, p, C.c_int32(pts.shape[0]), C.c_int(mem), C.c_float(cell_size)))
+
+    def map_set_downsample(self, voxel: float):
+        self._ck(self.lib.icp4r_map_set_downsample(self.h, C.c_float(voxel)))
+
+    def map_add_points(self, pts, downsample_on: bool = False) -> int:
+        pts = _f4(pts)
+        p, mem = _ptr(pts)
+        r = C.c_int32(0)
+        self._ck(self.lib.icp4r_map_add_points(self.h, p, C.c_int32(pts.shape[0]), C.c_int(mem), C.c_int(int(downsample_on)),
+                                               C.byref(r)))
+        return r.value
+
+    def map_size(self):
+        s, v = C.c_int32(0), C.c_int32(0)
+        self._ck(self.lib.icp4r_map_size(self.h, C.byref(s), C.byref(v)))
+        return s.value, v.value
+
+    def map_range(self):
+        out = np.zeros(6, np.float32)
+        self._ck(self.lib.icp4r_map_range(self.h, C.c_void_p(out.ctypes.data)))
+        return out
+
+    def _knn(self, fn, q, k, max_dist, out=None):
+        q = _f4(q)
+        p, mem = _ptr(q)
+        nq = q.shape[0]
+        if mem == HOST:
+            idx = np.empty((nq, k), np.int32)
+            d2 = np.empty((nq, k), np.float32)
+            found = np.empty(nq, np.int32)
+        else:
+            import torch
+            if out is not None:
+                idx, d2, found = out
+            else:
+                idx = torch.empty((nq, k), dtype=torch.int32, device=q.device)
+                d2 = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+                found = torch.empty(nq, dtype=torch.int32, device=q.device)
+        self._ck(fn(self.h, p, C.c_int32(nq), C.c_int(mem), C.c_int32(k), C.c_double(max_dist), _ptr(idx)[0], _ptr(d2)[0],
+                    _ptr(found)[0]))
+        return idx, d2, found
+
+    def map_knn(self, q, k, max_dist=0.0, out=None):
+        return self._knn(self.lib.icp4r_map_knn, q, k, max_dist, out)
+
+    def map_knn_brute(self, q, k, max_dist=0.0, out=None):
+        return self._knn(self.lib.icp4r_map_knn_brute, q, k, max_dist, out)
+
+    def map_points(self):
+        n, _ = self.map_size()
+        pts = np.zeros((n, 4), np.float32)
+        valid = np.zeros(n, np.uint8)
+        self._ck(self.lib.icp4r_map_points(self.h, C.c_int(HOST), C.c_void_p(pts.ctypes.data), C.c_void_p(valid.ctypes.data),
+                                           C.c_int32(n)))
+        return pts, valid
+
+    def map_sector(self, centre, radius, heading_deg):
+        n, _ = self.map_size()
+        c = np.asarray(centre, np.float32)
+        out = np.empty(max(n, 1), np.int32)
+        cnt = C.c_int32(0)
+        self._ck(self.lib.icp4r_map_sector(self.h, C.c_void_p(c.ctypes.data), C.c_float(radius), C.c_float(heading_deg),
+                                           C.c_int(HOST), C.c_void_p(out.ctypes.data), C.c_int32(out.shape[0]), C.byref(cnt)))
+        return out[:min(cnt.value, out.shape[0])].copy()
+
+    # ---- registration
+    def _dump_bufs(self, opts, n, dump, mem, device=None):
+        if not dump:
+            return None, None
+        it = max(opts.max_iterations, 0)
+        k = _knn_k(opts.residual, opts.k)
+        if mem == HOST:
+            dp = np.zeros((it, 16), np.float64)
+            da = np.zeros((it, ACC_LEN), np.float64)
+            di = np.full((it, n, k), -1, np.int32)
+        else:
+            import torch
+            dp = torch.zeros((it, 16), dtype=torch.float64, device=device)
+            da = torch.zeros((it, ACC_LEN), dtype=torch.float64, device=device)
+            di = torch.full((it, n, k), -1, dtype=torch.int32, device=device)
+        d = Dump(_ptr(dp)[0], _ptr(da)[0], _ptr(di)[0])
+        return d, (dp, da, di)
+
+    def register(self, src, tgt, opts: Opts, dump: bool = False):
+        src, tgt = _f4(src), _f4(tgt)
+        ps, mem = _ptr(src)
+        pt, mem2 = _ptr(tgt)
+        assert mem == mem2
+        T = np.zeros(16, np.float64)
+        res = Result()
+        d, bufs = self._dump_bufs(opts, src.shape[0], dump, mem, getattr(src, "device", None))
+        self._ck(self.lib.icp4r_register(self.h, ps, C.c_int32(src.shape[0]), pt, C.c_int32(tgt.shape[0]), C.c_int(mem),
+                                         C.byref(opts), C.c_void_p(T.ctypes.data), C.byref(res),
+                                         C.byref(d) if d is not None else None))
+        return T.reshape(4, 4), res, bufs
+
+    def register_map(self, src, opts: Opts, dump: bool = False):
+        src = _f4(src)
+        ps, mem = _ptr(src)
+        T = np.zeros(16, np.float64)
+        res = Result()
+        d, bufs = self._dump_bufs(opts, src.shape[0], dump, mem, getattr(src, "device", None))
+        self._ck(self.lib.icp4r_register_map(self.h, ps, C.c_int32(src.shape[0]), C.c_int(mem), C.byref(opts),
+                                             C.c_void_p(T.ctypes.data), C.byref(res), C.byref(d) if d is not None else None))
+        return T.reshape(4, 4), res, bufs
+
+    def register_batch(self, src, src_off, tgt, tgt_off, opts: Opts, out=None):
+        """src/tgt: concatenated clouds [sum n, 4]; *_off: int32 [n_pairs+1]. Returns (T [P,4,4], results)."""
+        src, tgt = _f4(src), _f4(tgt)
+        ps, mem = _ptr(src)
+        pt, _ = _ptr(tgt)
+        n_pairs = int(src_off.shape[0]) - 1
+        if mem == HOST:
+            src_off = np.ascontiguousarray(src_off, np.int32)
+            tgt_off = np.ascontiguousarray(tgt_off, np.int32)
+            T = np.zeros((n_pairs, 16), np.float64)
+            res = np.zeros(n_pairs, RESULT_DTYPE)
+        else:
+            import torch
+            if out is not None:
+                T, res = out
+            else:
+                T = torch.zeros((n_pairs, 16), dtype=torch.float64, device=src.device)
+                res = torch.zeros((n_pairs, RESULT_DTYPE.itemsize), dtype=torch.uint8, device=src.device)
+        self._ck(self.lib.icp4r_register_batch(self.h, ps, _ptr(src_off)[0], pt, _ptr(tgt_off)[0], C.c_int32(n_pairs), C.c_int(mem),
+                                               C.byref(opts), _ptr(T)[0], _ptr(res)[0]))
+        if mem == HOST:
+            return T.reshape(n_pairs, 4, 4), res
+        return T, res
+
+    # ---- sharding
+    @staticmethod
+    def shard_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        rc = load_library().icp4r_shard_unique_id(buf)
+        if rc != 0:
+            raise Icp4rError(rc, "icp4r_shard_unique_id failed (NCCL not loadable?)")
+        return buf.raw
+
+    def shard_init(self, uid: bytes, rank: int, world: int):
+        assert len(uid) == 128
+        self._ck(self.lib.icp4r_shard_init(self.h, C.c_char_p(uid), C.c_int(rank), C.c_int(world)))
+
+    def register_sharded(self, src, opts: Opts, axis: int, slab_lo: float, slab_hi: float):
+        src = _f4(src)
+        ps, mem = _ptr(src)
+        T = np.zeros(16, np.float64)
+        res = Result()
+        self._ck(self.lib.icp4r_register_sharded(self.h, ps, C.c_int32(src.shape[0]), C.c_int(mem), C.byref(opts), C.c_int(axis),
+                                                 C.c_float(slab_lo), C.c_float(slab_hi), C.c_void_p(T.ctypes.data), C.byref(res)))
+        return T.reshape(4, 4), res
+
+    # ---- helpers
+    def transform_points(self, T, pts):
+        pts = _f4(pts)
+        p, mem = _ptr(pts)
+        T = np.ascontiguousarray(T, np.float64).reshape(16)
+        if mem == HOST:
+            out = np.empty_like(pts)
+        else:
+            import torch
+            out = torch.empty_like(pts)
+        self._ck(self.lib.icp4r_transform_points(self.h, C.c_void_p(T.ctypes.data), p, C.c_int32(pts.shape[0]), C.c_int(mem),
+                                                 _ptr(out)[0]))
+        return out

@@ -1,0 +1,503 @@
+// api.cu — the extern "C" boundary of libicp4r_cuda (include/icp4r.h). Argument checking, host<->device
+// staging on the handle's stream, and dispatch into the kernels. There is no CPU fallback anywhere.
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+
+#include "ctx.h"
+
+namespace icp4r {
+
+static thread_local std::string g_create_err;
+
+int fail(Ctx* c, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    else g_create_err = buf;
+    return code;
+}
+
+int reserve(Ctx* c, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap && b.p) return ICP4R_OK;
+    if (b.p) {
+        cudaStreamSynchronize(c->stream);  // nobody may still be reading the old block
+        cudaFree(b.p);
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t want = bytes < 256 ? 256 : bytes;
+    const cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        b.p = nullptr;
+        return fail(c, ICP4R_ERR_NOMEM, "cudaMalloc(%zu): %s", want, cudaGetErrorString(e));
+    }
+    b.cap = want;
+    return ICP4R_OK;
+}
+
+void release(DevBuf& b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+int shard_unique_id(char id_out[128]);
+int shard_init(Ctx* c, const char id_in[128], int rank, int world);
+void shard_destroy(Ctx* c);
+
+static void free_map(Map& m) {
+    release(m.pts);
+    release(m.valid);
+    release(m.sorted);
+    release(m.cell_start);
+    release(m.keys_a);
+    release(m.keys_b);
+    release(m.vals_a);
+    release(m.vals_b);
+    m.m = m.m_valid = 0;
+    m.built = false;
+}
+
+static void drop_graphs(Ctx* c) {
+    for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+    c->graphs.clear();
+    c->graph_grid_owner = nullptr;
+}
+
+// copy a caller buffer onto the device (or alias it when it already lives there)
+static int stage_in(Ctx* c, DevBuf& b, const void* user, size_t bytes, int mem, const void** dev) {
+    if (bytes == 0) {
+        CKS(reserve(c, b, 256));
+        *dev = b.p;
+        return ICP4R_OK;
+    }
+    if (mem == ICP4R_DEVICE) {
+        *dev = user;
+        return ICP4R_OK;
+    }
+    CKS(reserve(c, b, bytes));
+    CK(cudaMemcpyAsync(b.p, user, bytes, cudaMemcpyHostToDevice, c->stream));
+    *dev = b.p;
+    return ICP4R_OK;
+}
+
+static int set_points(Ctx* c, Map& mp, const float* xyzw, int n, int mem, int offset) {
+    CKS(map_reserve(c, mp, offset + n));
+    if (n > 0) {
+        CK(cudaMemcpyAsync(mp.pts.as<float4>() + offset, xyzw, (size_t)n * sizeof(float4),
+                           mem == ICP4R_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemsetAsync(mp.valid.as<uint8_t>() + offset, 1, (size_t)n, c->stream));
+    }
+    return ICP4R_OK;
+}
+
+static bool bad_mem(int mem) { return mem != ICP4R_HOST && mem != ICP4R_DEVICE; }
+
+}  // namespace icp4r
+
+using namespace icp4r;
+
+#define HCHECK(h)                       \
+    if (!(h)) return ICP4R_ERR_INVALID; \
+    Ctx* c = (h);                       \
+    c->err.clear();                     \
+    if (cudaSetDevice(c->device) != cudaSuccess) return fail(c, ICP4R_ERR_CUDA, "cudaSetDevice(%d) failed", c->device)
+
+extern "C" {
+
+const char* icp4r_version(void) { return "libicp4r_cuda 0.1 (sm_100a)"; }
+
+int icp4r_default_opts(icp4r_opts* o) {
+    if (!o) return ICP4R_ERR_INVALID;
+    std::memset(o, 0, sizeof(*o));
+    o->residual = ICP4R_P2P_SVD;
+    o->k = 5;
+    o->max_iterations = 10;  // PCL default; iterative_closest_point.cpp:513 leaves it untouched
+    o->early_exit = 0;
+    o->max_corr_dist = 0.0;
+    o->rot_eps = 2e-3;  // fast_gicp defaults
+    o->trans_eps = 5e-4;
+    o->mse_abs_eps = 1e-12;
+    o->plane_thresh = 0.2;
+    for (int i = 0; i < 16; ++i) o->T0[i] = (i % 5 == 0) ? 1.0 : 0.0;
+    return ICP4R_OK;
+}
+
+int icp4r_create(int device, icp4r_handle* out) {
+    if (!out) return ICP4R_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0)
+        return fail(nullptr, ICP4R_ERR_CUDA, "no CUDA device (%s); libicp4r_cuda has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, ICP4R_ERR_INVALID, "device %d out of range (0..%d)", device, ndev - 1);
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(nullptr, ICP4R_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+        return fail(nullptr, ICP4R_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major < 10)
+        return fail(nullptr, ICP4R_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+                    prop.minor);
+    icp4r_ctx* c = new (std::nothrow) icp4r_ctx();
+    if (!c) return ICP4R_ERR_NOMEM;
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        delete c;
+        return fail(nullptr, ICP4R_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    }
+    c->stream = c->own_stream;
+    c->h_pinned_cap = 64 * 1024;
+    if ((e = cudaMallocHost(&c->h_pinned, c->h_pinned_cap)) != cudaSuccess) {
+        cudaStreamDestroy(c->own_stream);
+        delete c;
+        return fail(nullptr, ICP4R_ERR_NOMEM, "cudaMallocHost: %s", cudaGetErrorString(e));
+    }
+    const char* ng = std::getenv("ICP4R_NO_GRAPH");
+    c->use_graph = !(ng && ng[0] == '1');
+    *out = c;
+    return ICP4R_OK;
+}
+
+int icp4r_destroy(icp4r_handle h) {
+    if (!h) return ICP4R_ERR_INVALID;
+    Ctx* c = h;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->own_stream != c->stream) cudaStreamSynchronize(c->own_stream);
+    drop_graphs(c);
+    shard_destroy(c);
+    free_map(c->map);
+    free_map(c->tmp);
+    DevBuf* bufs[] = {&c->d_src, &c->d_q, &c->d_idx, &c->d_d2, &c->d_found, &c->d_scratch, &c->d_partials, &c->d_state, &c->d_params,
+                      &c->d_T, &c->d_res, &c->d_dump_pose, &c->d_dump_acc, &c->d_dump_idx, &c->b_src, &c->b_tgt, &c->b_soff,
+                      &c->b_toff, &c->b_T, &c->b_res};
+    for (DevBuf* b : bufs) release(*b);
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    cudaStreamDestroy(c->own_stream);
+    delete h;
+    return ICP4R_OK;
+}
+
+const char* icp4r_last_error(icp4r_handle h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int icp4r_set_stream(icp4r_handle h, void* s) {
+    HCHECK(h);
+    cudaStreamSynchronize(c->stream);
+    c->stream = s ? static_cast<cudaStream_t>(s) : c->own_stream;
+    return ICP4R_OK;
+}
+
+int icp4r_synchronize(icp4r_handle h) {
+    HCHECK(h);
+    CK(cudaStreamSynchronize(c->stream));
+    return ICP4R_OK;
+}
+
+int icp4r_launch_count(icp4r_handle h, int64_t* out) {
+    if (!h || !out) return ICP4R_ERR_INVALID;
+    *out = h->launches;
+    return ICP4R_OK;
+}
+
+// ---- map ------------------------------------------------------------------------------------------------
+
+int icp4r_map_build(icp4r_handle h, const float* xyzw, int32_t n, int mem, float cell_size) {
+    HCHECK(h);
+    if (n < 0 || (n > 0 && !xyzw) || bad_mem(mem)) return fail(c, ICP4R_ERR_INVALID, "icp4r_map_build: bad arguments");
+    Map& mp = c->map;
+    mp.m = 0;
+    mp.m_valid = 0;
+    mp.built = false;
+    mp.user_cell = cell_size;
+    CKS(set_points(c, mp, xyzw, n, mem, 0));
+    mp.m = n;
+    CKS(map_rebuild_grid(c, mp));
+    return ICP4R_OK;
+}
+
+int icp4r_map_set_downsample(icp4r_handle h, float voxel) {
+    HCHECK(h);
+    if (!(voxel > 0.f)) return fail(c, ICP4R_ERR_INVALID, "voxel must be positive");
+    c->map.ds_voxel = voxel;
+    return ICP4R_OK;
+}
+
+int icp4r_map_add_points(icp4r_handle h, const float* xyzw, int32_t n, int mem, int downsample_on, int32_t* n_replaced) {
+    HCHECK(h);
+    if (n < 0 || (n > 0 && !xyzw) || bad_mem(mem)) return fail(c, ICP4R_ERR_INVALID, "icp4r_map_add_points: bad arguments");
+    if (n_replaced) *n_replaced = 0;
+    Map& mp = c->map;
+    if (downsample_on) return fail(c, ICP4R_ERR_UNSUPPORTED, "Add_Points with down-sampling is not implemented yet");
+    if (n == 0) return ICP4R_OK;
+    CKS(set_points(c, mp, xyzw, n, mem, mp.m));
+    mp.m += n;
+    CKS(map_rebuild_grid(c, mp));
+    return ICP4R_OK;
+}
+
+int icp4r_map_size(icp4r_handle h, int32_t* size, int32_t* valid) {
+    HCHECK(h);
+    if (size) *size = c->map.m;
+    if (valid) *valid = c->map.m_valid;
+    return ICP4R_OK;
+}
+
+int icp4r_map_range(icp4r_handle h, float out6[6]) {
+    HCHECK(h);
+    if (!out6) return fail(c, ICP4R_ERR_INVALID, "null output");
+    if (!c->map.built) return fail(c, ICP4R_ERR_STATE, "map not built");
+    for (int a = 0; a < 3; ++a) {
+        out6[a] = c->map.bb_min[a];
+        out6[3 + a] = c->map.bb_max[a];
+    }
+    return ICP4R_OK;
+}
+
+static int map_knn_common(Ctx* c, bool brute, const float* q, int32_t nq, int mem, int32_t k, double max_dist, int32_t* idx, float* d2,
+                          int32_t* found) {
+    if (nq < 0 || k < 1 || k > ICP4R_MAX_K || bad_mem(mem) || (nq > 0 && (!q || !idx || !d2)))
+        return fail(c, ICP4R_ERR_INVALID, "icp4r_map_knn: bad arguments (nq=%d k=%d)", nq, k);
+    if (!c->map.built) return fail(c, ICP4R_ERR_STATE, "icp4r_map_knn before icp4r_map_build");
+    if (nq == 0) return ICP4R_OK;
+    const void* dq;
+    CKS(stage_in(c, c->d_q, q, (size_t)nq * sizeof(float4), mem, &dq));
+    int32_t* di = idx;
+    float* dd = d2;
+    int32_t* df = found;
+    if (mem == ICP4R_HOST) {
+        CKS(reserve(c, c->d_idx, (size_t)nq * k * 4));
+        CKS(reserve(c, c->d_d2, (size_t)nq * k * 4));
+        CKS(reserve(c, c->d_found, (size_t)nq * 4));
+        di = c->d_idx.as<int32_t>();
+        dd = c->d_d2.as<float>();
+        df = c->d_found.as<int32_t>();
+    }
+    if (brute) CKS(brute_knn(c, c->map, static_cast<const float4*>(dq), nq, k, max_dist, di, dd, df));
+    else CKS(grid_knn(c, c->map, static_cast<const float4*>(dq), nq, k, max_dist, di, dd, df));
+    if (mem == ICP4R_HOST) {
+        CK(cudaMemcpyAsync(idx, di, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(d2, dd, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (found) CK(cudaMemcpyAsync(found, df, (size_t)nq * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return ICP4R_OK;
+}
+
+int icp4r_map_knn(icp4r_handle h, const float* q, int32_t nq, int mem, int32_t k, double max_dist, int32_t* idx, float* d2,
+                  int32_t* found) {
+    HCHECK(h);
+    return map_knn_common(c, false, q, nq, mem, k, max_dist, idx, d2, found);
+}
+
+int icp4r_map_knn_brute(icp4r_handle h, const float* q, int32_t nq, int mem, int32_t k, double max_dist, int32_t* idx, float* d2,
+                        int32_t* found) {
+    HCHECK(h);
+    return map_knn_common(c, true, q, nq, mem, k, max_dist, idx, d2, found);
+}
+
+int icp4r_map_sector(icp4r_handle h, const float centre_xyz[3], float radius, float heading_deg, int mem, int32_t* idx_out,
+                     int32_t cap, int32_t* n_out) {
+    HCHECK(h);
+    (void)centre_xyz; (void)radius; (void)heading_deg; (void)mem; (void)idx_out; (void)cap; (void)n_out;
+    return fail(c, ICP4R_ERR_UNSUPPORTED, "icp4r_map_sector is not implemented yet");
+}
+
+int icp4r_map_points(icp4r_handle h, int mem, float* xyzw_out, uint8_t* valid_out, int32_t cap) {
+    HCHECK(h);
+    if (bad_mem(mem) || cap < 0) return fail(c, ICP4R_ERR_INVALID, "icp4r_map_points: bad arguments");
+    const int n = std::min(cap, c->map.m);
+    const cudaMemcpyKind kind = mem == ICP4R_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (n > 0 && xyzw_out) CK(cudaMemcpyAsync(xyzw_out, c->map.pts.p, (size_t)n * sizeof(float4), kind, c->stream));
+    if (n > 0 && valid_out) CK(cudaMemcpyAsync(valid_out, c->map.valid.p, (size_t)n, kind, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return ICP4R_OK;
+}
+
+// ---- registration -----------------------------------------------------------------------------------------
+
+static int k_of(const icp4r_opts* o) {
+    return (o->residual == ICP4R_P2P_SVD || o->residual == ICP4R_P2P_GN) ? 1 : (o->residual == ICP4R_P2LINE ? 2 : (o->k > 0 ? o->k : 5));
+}
+
+// dumps requested with host pointers are produced on the device and copied back afterwards
+struct DumpStage {
+    icp4r_dump dev{nullptr, nullptr, nullptr};
+    const icp4r_dump* user = nullptr;
+    size_t pose_b = 0, acc_b = 0, idx_b = 0;
+    bool host = false;
+};
+
+static int dump_prepare(Ctx* c, const icp4r_dump* dump, int mem, int n, const icp4r_opts* o, DumpStage& ds) {
+    ds.user = dump;
+    if (!dump) return ICP4R_OK;
+    const size_t it = (size_t)std::max(o->max_iterations, 0);
+    ds.pose_b = it * 16 * sizeof(double);
+    ds.acc_b = it * ICP4R_ACC_LEN * sizeof(double);
+    ds.idx_b = it * (size_t)n * k_of(o) * sizeof(int32_t);
+    if (mem == ICP4R_DEVICE) {
+        ds.dev = *dump;
+        return ICP4R_OK;
+    }
+    ds.host = true;
+    if (dump->pose) {
+        CKS(reserve(c, c->d_dump_pose, ds.pose_b));
+        ds.dev.pose = c->d_dump_pose.as<double>();
+    }
+    if (dump->acc) {
+        CKS(reserve(c, c->d_dump_acc, ds.acc_b));
+        ds.dev.acc = c->d_dump_acc.as<double>();
+    }
+    if (dump->idx) {
+        CKS(reserve(c, c->d_dump_idx, ds.idx_b));
+        ds.dev.idx = c->d_dump_idx.as<int32_t>();
+    }
+    if (ds.dev.pose && ds.pose_b) CK(cudaMemsetAsync(ds.dev.pose, 0, ds.pose_b, c->stream));
+    if (ds.dev.acc && ds.acc_b) CK(cudaMemsetAsync(ds.dev.acc, 0, ds.acc_b, c->stream));
+    if (ds.dev.idx && ds.idx_b) CK(cudaMemsetAsync(ds.dev.idx, 0xff, ds.idx_b, c->stream));
+    return ICP4R_OK;
+}
+
+static int dump_finish(Ctx* c, DumpStage& ds) {
+    if (!ds.user || !ds.host) return ICP4R_OK;
+    if (ds.dev.pose && ds.pose_b) CK(cudaMemcpyAsync(ds.user->pose, ds.dev.pose, ds.pose_b, cudaMemcpyDeviceToHost, c->stream));
+    if (ds.dev.acc && ds.acc_b) CK(cudaMemcpyAsync(ds.user->acc, ds.dev.acc, ds.acc_b, cudaMemcpyDeviceToHost, c->stream));
+    if (ds.dev.idx && ds.idx_b) CK(cudaMemcpyAsync(ds.user->idx, ds.dev.idx, ds.idx_b, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return ICP4R_OK;
+}
+
+int icp4r_register_map(icp4r_handle h, const float* src, int32_t n, int mem, const icp4r_opts* opts, double T_out[16],
+                       icp4r_result* res, const icp4r_dump* dump) {
+    HCHECK(h);
+    if (!opts || n < 0 || (n > 0 && !src) || bad_mem(mem)) return fail(c, ICP4R_ERR_INVALID, "icp4r_register_map: bad arguments");
+    const void* dsrc;
+    CKS(stage_in(c, c->d_src, src, (size_t)n * sizeof(float4), mem, &dsrc));
+    DumpStage ds;
+    CKS(dump_prepare(c, dump, mem, n, opts, ds));
+    CKS(register_against_map(c, c->map, static_cast<const float4*>(dsrc), n, opts, -1, 0.f, 0.f, T_out, res, dump ? &ds.dev : nullptr));
+    return dump_finish(c, ds);
+}
+
+int icp4r_register(icp4r_handle h, const float* src, int32_t n, const float* tgt, int32_t m, int mem, const icp4r_opts* opts,
+                   double T_out[16], icp4r_result* res, const icp4r_dump* dump) {
+    HCHECK(h);
+    if (!opts || n < 0 || m < 0 || (n > 0 && !src) || (m > 0 && !tgt) || bad_mem(mem))
+        return fail(c, ICP4R_ERR_INVALID, "icp4r_register: bad arguments");
+    // transient index over the target, rebuilt per call like PCL's setInputTarget kd-tree
+    Map& mp = c->tmp;
+    mp.m = 0;
+    mp.built = false;
+    mp.user_cell = 0.f;
+    CKS(set_points(c, mp, tgt, m, mem, 0));
+    mp.m = m;
+    CKS(map_rebuild_grid(c, mp));
+    const void* dsrc;
+    CKS(stage_in(c, c->d_src, src, (size_t)n * sizeof(float4), mem, &dsrc));
+    DumpStage ds;
+    CKS(dump_prepare(c, dump, mem, n, opts, ds));
+    CKS(register_against_map(c, mp, static_cast<const float4*>(dsrc), n, opts, -1, 0.f, 0.f, T_out, res, dump ? &ds.dev : nullptr));
+    return dump_finish(c, ds);
+}
+
+int icp4r_register_batch(icp4r_handle h, const float* src, const int32_t* src_off, const float* tgt, const int32_t* tgt_off,
+                         int32_t n_pairs, int mem, const icp4r_opts* opts, double* T_out, icp4r_result* res) {
+    HCHECK(h);
+    if (!opts || n_pairs < 0 || bad_mem(mem) || (n_pairs > 0 && (!src_off || !tgt_off || !T_out || !res)))
+        return fail(c, ICP4R_ERR_INVALID, "icp4r_register_batch: bad arguments");
+    if (n_pairs == 0) return ICP4R_OK;
+    // offsets are needed on the host to size shared memory
+    std::vector<int32_t> so(n_pairs + 1), to(n_pairs + 1);
+    if (mem == ICP4R_DEVICE) {
+        CK(cudaMemcpyAsync(so.data(), src_off, (size_t)(n_pairs + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(to.data(), tgt_off, (size_t)(n_pairs + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    } else {
+        std::memcpy(so.data(), src_off, (size_t)(n_pairs + 1) * 4);
+        std::memcpy(to.data(), tgt_off, (size_t)(n_pairs + 1) * 4);
+    }
+    int max_n = 0, max_m = 0;
+    for (int i = 0; i < n_pairs; ++i) {
+        const int a = so[i + 1] - so[i], b = to[i + 1] - to[i];
+        if (a < 0 || b < 0) return fail(c, ICP4R_ERR_INVALID, "offsets must be non-decreasing (pair %d)", i);
+        max_n = std::max(max_n, a);
+        max_m = std::max(max_m, b);
+    }
+    const size_t ns = (size_t)so[n_pairs], nt = (size_t)to[n_pairs];
+    if ((ns > 0 && !src) || (nt > 0 && !tgt)) return fail(c, ICP4R_ERR_INVALID, "null cloud pointer");
+    const void *dsrc, *dtgt, *dso, *dto;
+    CKS(stage_in(c, c->b_src, src, ns * sizeof(float4), mem, &dsrc));
+    CKS(stage_in(c, c->b_tgt, tgt, nt * sizeof(float4), mem, &dtgt));
+    CKS(stage_in(c, c->b_soff, src_off, (size_t)(n_pairs + 1) * 4, mem, &dso));
+    CKS(stage_in(c, c->b_toff, tgt_off, (size_t)(n_pairs + 1) * 4, mem, &dto));
+    double* dT = T_out;
+    icp4r_result* dR = res;
+    if (mem == ICP4R_HOST) {
+        CKS(reserve(c, c->b_T, (size_t)n_pairs * 16 * sizeof(double)));
+        CKS(reserve(c, c->b_res, (size_t)n_pairs * sizeof(icp4r_result)));
+        dT = c->b_T.as<double>();
+        dR = c->b_res.as<icp4r_result>();
+    }
+    CKS(register_batch(c, static_cast<const float4*>(dsrc), static_cast<const int32_t*>(dso), static_cast<const float4*>(dtgt),
+                       static_cast<const int32_t*>(dto), n_pairs, max_n, max_m, opts, dT, dR));
+    if (mem == ICP4R_HOST) {
+        CK(cudaMemcpyAsync(T_out, dT, (size_t)n_pairs * 16 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(res, dR, (size_t)n_pairs * sizeof(icp4r_result), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return ICP4R_OK;
+}
+
+// ---- sharding ---------------------------------------------------------------------------------------------
+
+int icp4r_shard_unique_id(char id_out[128]) {
+    if (!id_out) return ICP4R_ERR_INVALID;
+    return shard_unique_id(id_out);
+}
+
+int icp4r_shard_init(icp4r_handle h, const char id[128], int rank, int world) {
+    HCHECK(h);
+    if (!id) return fail(c, ICP4R_ERR_INVALID, "null id");
+    return shard_init(c, id, rank, world);
+}
+
+int icp4r_register_sharded(icp4r_handle h, const float* src, int32_t n, int mem, const icp4r_opts* opts, int axis, float slab_lo,
+                           float slab_hi, double T_out[16], icp4r_result* res) {
+    HCHECK(h);
+    if (!opts || n < 0 || (n > 0 && !src) || bad_mem(mem) || axis < 0 || axis > 2)
+        return fail(c, ICP4R_ERR_INVALID, "icp4r_register_sharded: bad arguments");
+    const void* dsrc;
+    CKS(stage_in(c, c->d_src, src, (size_t)n * sizeof(float4), mem, &dsrc));
+    return register_against_map(c, c->map, static_cast<const float4*>(dsrc), n, opts, axis, slab_lo, slab_hi, T_out, res, nullptr);
+}
+
+// ---- helpers ------------------------------------------------------------------------------------------------
+
+}  // extern "C"
+
+namespace icp4r {
+int transform_points(Ctx* c, const double* T_host, const float4* d_in, int n, float4* d_out);
+}
+
+extern "C" int icp4r_transform_points(icp4r_handle h, const double T[16], const float* xyzw, int32_t n, int mem, float* xyzw_out) {
+    HCHECK(h);
+    if (!T || n < 0 || (n > 0 && (!xyzw || !xyzw_out)) || bad_mem(mem)) return fail(c, ICP4R_ERR_INVALID, "icp4r_transform_points: bad arguments");
+    if (n == 0) return ICP4R_OK;
+    const void* din;
+    CKS(stage_in(c, c->d_q, xyzw, (size_t)n * sizeof(float4), mem, &din));
+    float4* dout = reinterpret_cast<float4*>(xyzw_out);
+    if (mem == ICP4R_HOST) {
+        CKS(reserve(c, c->d_src, (size_t)n * sizeof(float4)));
+        dout = c->d_src.as<float4>();
+    }
+    CKS(transform_points(c, T, static_cast<const float4*>(din), n, dout));
+    if (mem == ICP4R_HOST) {
+        CK(cudaMemcpyAsync(xyzw_out, dout, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return ICP4R_OK;
+}

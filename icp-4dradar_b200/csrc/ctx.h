@@ -1,0 +1,175 @@
+// ctx.h — host-side state behind an icp4r_handle and the internal entry points of each translation unit.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/icp4r.h"
+
+namespace icp4r {
+
+// ---- error plumbing -------------------------------------------------------------------------------
+struct Ctx;
+int fail(Ctx* c, int code, const char* fmt, ...);
+
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e__ = (call);                                                                     \
+        if (e__ != cudaSuccess)                                                                       \
+            return icp4r::fail(c, ICP4R_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call,       \
+                               cudaGetErrorString(e__));                                              \
+    } while (0)
+#define CKS(call)                       \
+    do {                                \
+        int s__ = (call);               \
+        if (s__ != ICP4R_OK) return s__; \
+    } while (0)
+
+// grow-only device buffer
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    template <typename T>
+    T* as() const { return static_cast<T*>(p); }
+};
+int reserve(Ctx* c, DevBuf& b, size_t bytes);
+void release(DevBuf& b);
+
+// ---- uniform voxel grid over a point set (replaces the k-d tree) ----------------------------------
+// Cells are keyed row-major with x fastest: key = (cz * ny + cy) * nx + cx, so the cells of one x-row are
+// contiguous in the sorted array and a (2R+1)^3 neighbourhood is (2R+1)^2 contiguous ranges.
+struct GridDesc {
+    float ox, oy, oz;     // origin (lower corner)
+    float cell, inv_cell;
+    int nx, ny, nz;
+    int ncells;
+    int m;                // points in the sorted array
+    float margin;         // absolute slack used by the termination bound (covers float rounding)
+    const float4* sorted; // x, y, z, bit-cast original index
+    const uint32_t* cell_start;  // [ncells + 1]
+};
+
+struct Map {
+    DevBuf pts;         // float4 [cap] insertion order (x, y, z, intensity)
+    DevBuf valid;       // uint8  [cap]
+    DevBuf sorted;      // float4 [m_sorted]
+    DevBuf cell_start;  // uint32 [ncells + 1]
+    DevBuf keys_a, keys_b, vals_a, vals_b;  // radix sort ping-pong
+    int m = 0;          // points ever offered (index space)
+    int m_valid = 0;
+    bool built = false;
+    float user_cell = 0.f;
+    float ds_voxel = 0.2f;  // KD_TREE default downsample_size, ikd_Tree.h:196
+    GridDesc grid{};
+    float bb_min[3] = {0, 0, 0}, bb_max[3] = {0, 0, 0};
+};
+
+// device-resident registration state (one per handle)
+struct RegState {
+    double T[16];
+    double acc[ICP4R_ACC_LEN];
+    double mse_prev;
+    double last_cost;
+    double fit_sum;
+    int fit_cnt;
+    int done;
+    int converged;
+    int iterations;
+    int n_corr;
+    unsigned ticket;
+    unsigned ticket_fit;
+    int pad;
+};
+
+struct RegParams {  // kernel parameters that change per call; lives in device memory so graphs stay valid
+    const float4* src;
+    int n;
+    int residual;
+    int k;
+    int max_iterations;
+    int early_exit;
+    float gate_f;        // largest float whose double is <= max_dist^2 (+inf when ungated)
+    float gate_r;        // search radius in metres incl. rounding slack (+inf when ungated)
+    double rot_eps, trans_eps, mse_abs_eps, plane_thresh;
+    double* dump_pose;
+    double* dump_acc;
+    int32_t* dump_idx;
+    // sharded registration
+    int shard_axis;      // -1: not sharded
+    float slab_lo, slab_hi;
+};
+
+struct GraphKey {
+    int kind, k, blocks, iters, flags;
+    bool operator<(const GraphKey& o) const {
+        if (kind != o.kind) return kind < o.kind;
+        if (k != o.k) return k < o.k;
+        if (blocks != o.blocks) return blocks < o.blocks;
+        if (iters != o.iters) return iters < o.iters;
+        return flags < o.flags;
+    }
+};
+
+struct Ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+
+    Map map;      // the handle's persistent map
+    Map tmp;      // transient target of icp4r_register
+
+    DevBuf d_src, d_q, d_idx, d_d2, d_found, d_scratch, d_partials, d_state, d_params, d_T, d_res;
+    DevBuf d_dump_pose, d_dump_acc, d_dump_idx;
+    DevBuf b_src, b_tgt, b_soff, b_toff, b_T, b_res;  // batched registration
+    void* h_pinned = nullptr;  // small pinned staging block
+    size_t h_pinned_cap = 0;
+
+    std::map<GraphKey, cudaGraphExec_t> graphs;
+    const GridDesc* graph_grid_owner = nullptr;  // graphs bake the grid by value: identity of what they baked
+    GridDesc graph_grid_copy{};
+    const void* graph_pts = nullptr;
+    bool use_graph = true;
+
+    // sharding (NCCL loaded lazily with dlopen)
+    void* nccl_comm = nullptr;
+    int rank = 0, world = 1;
+};
+
+inline int64_t& launches(Ctx* c) { return c->launches; }
+
+// ---- internal entry points --------------------------------------------------------------------------
+// radix_sort.cu: stable LSB radix sort of (key, value) pairs, `bits` significant key bits. Result in
+// keys_out/vals_out (which alias one of the two ping-pong pairs).
+int radix_sort_pairs(Ctx* c, uint32_t* keys_a, uint32_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, int n, int bits,
+                     DevBuf& scratch, uint32_t** keys_out, uint32_t** vals_out);
+
+// grid.cu
+int map_reserve(Ctx* c, Map& mp, int cap);
+int map_rebuild_grid(Ctx* c, Map& mp);  // (re)sort all valid points into the grid
+int grid_knn(Ctx* c, const Map& mp, const float4* q, int nq, int k, double max_dist, int32_t* idx, float* d2,
+             int32_t* found);
+int brute_knn(Ctx* c, const Map& mp, const float4* q, int nq, int k, double max_dist, int32_t* idx, float* d2,
+              int32_t* found);
+void gate_params(double max_dist, float* gate_f, float* gate_r);
+
+// register_map.cu
+int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4r_opts* o, int shard_axis,
+                         float slab_lo, float slab_hi, double* T_out_host, icp4r_result* res_host,
+                         const icp4r_dump* dump_dev);
+
+// register_batch.cu
+int register_batch(Ctx* c, const float4* d_src, const int32_t* d_soff, const float4* d_tgt, const int32_t* d_toff,
+                   int n_pairs, int max_n, int max_m, const icp4r_opts* o, double* d_T, icp4r_result* d_res);
+
+// shard.cu
+int shard_allreduce(Ctx* c, double* d_buf, int count);
+
+}  // namespace icp4r
+
+struct icp4r_ctx : icp4r::Ctx {};

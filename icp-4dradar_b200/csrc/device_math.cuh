@@ -1,0 +1,370 @@
+// device_math.cuh — scalar device helpers shared by every kernel of libicp4r_cuda (sm_100a).
+//
+// Everything that decides a correspondence is written with explicit round-to-nearest intrinsics so
+// nvcc cannot contract it into FMAs: the reference evaluates these expressions with separate roundings
+// (it is built with `-g` only, /root/reference/CMakeLists.txt:5-6) and the neighbour indices must be
+// bit-exact.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace icp4r {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr uint64_t KEY_EMPTY = ~0ull;
+
+// float squared distance, (dx*dx + dy*dy) + dz*dz — calc_dist, ikd_Tree.cpp:1427-1431
+__device__ __forceinline__ float dist2_exact(float qx, float qy, float qz, float px, float py, float pz) {
+    const float dx = __fsub_rn(qx, px), dy = __fsub_rn(qy, py), dz = __fsub_rn(qz, pz);
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// one row of p' = R p + t in double, left to right, unfused — pointAssociateToMap,
+// /root/reference/src/radar_odometry.cpp:137-145 (Eigen evaluates the 3x3 * 3x1 product coefficient-wise)
+__device__ __forceinline__ double xform_row(double a, double b, double c, double t, double x, double y, double z) {
+    return __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(a, x), __dmul_rn(b, y)), __dmul_rn(c, z)), t);
+}
+
+__device__ __forceinline__ void xform_point(const double* __restrict__ T, float px, float py, float pz, double pw[3]) {
+    const double x = (double)px, y = (double)py, z = (double)pz;
+    pw[0] = xform_row(T[0], T[1], T[2], T[3], x, y, z);
+    pw[1] = xform_row(T[4], T[5], T[6], T[7], x, y, z);
+    pw[2] = xform_row(T[8], T[9], T[10], T[11], x, y, z);
+}
+
+// (d2, index) packed so that unsigned comparison orders by distance first, lowest index on ties.
+// d2 >= 0 always, so its IEEE bit pattern is monotone as an unsigned integer.
+__device__ __forceinline__ uint64_t pack_key(float d2, int idx) {
+    return ((uint64_t)__float_as_uint(d2) << 32) | (uint32_t)idx;
+}
+__device__ __forceinline__ float key_d2(uint64_t k) { return __uint_as_float((uint32_t)(k >> 32)); }
+__device__ __forceinline__ int key_idx(uint64_t k) { return (int)(uint32_t)k; }
+
+// sorted (ascending) top-K of packed keys held in registers
+template <int K>
+struct TopK {
+    uint64_t key[K];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int i = 0; i < K; ++i) key[i] = KEY_EMPTY;
+    }
+    __device__ __forceinline__ uint64_t worst() const { return key[K - 1]; }
+    __device__ __forceinline__ void insert(uint64_t k) {
+        if (k < key[K - 1]) {
+            key[K - 1] = k;
+#pragma unroll
+            for (int j = K - 1; j > 0; --j) {
+                const uint64_t a = key[j - 1], b = key[j];
+                const bool sw = b < a;
+                key[j - 1] = sw ? b : a;
+                key[j] = sw ? a : b;
+            }
+        }
+    }
+    __device__ __forceinline__ void pop_front() {
+#pragma unroll
+        for (int j = 0; j < K - 1; ++j) key[j] = key[j + 1];
+        key[K - 1] = KEY_EMPTY;
+    }
+};
+
+__device__ __forceinline__ uint64_t warp_min_u64(uint64_t v) {
+    const uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;
+    const uint32_t mh = __reduce_min_sync(FULL, hi);
+    const uint32_t ml = __reduce_min_sync(FULL, hi == mh ? lo : 0xffffffffu);
+    return ((uint64_t)mh << 32) | ml;
+}
+
+// Merge the 32 per-lane sorted lists: afterwards lane r (< K) returns the r-th smallest key of the union,
+// other lanes return KEY_EMPTY. Destroys the lists.
+template <int K>
+__device__ __forceinline__ uint64_t warp_merge_topk(TopK<K>& t, int lane) {
+    uint64_t mine = KEY_EMPTY;
+#pragma unroll
+    for (int r = 0; r < K; ++r) {
+        const uint64_t m = warp_min_u64(t.key[0]);
+        if (m != KEY_EMPTY && t.key[0] == m) t.pop_front();  // keys are unique (index in the low word)
+        if (lane == r) mine = m;
+    }
+    return mine;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small dense algebra (fp64, one thread)
+
+__device__ __forceinline__ void cross3(const double a[3], const double b[3], double c[3]) {
+    c[0] = a[1] * b[2] - a[2] * b[1];
+    c[1] = a[2] * b[0] - a[0] * b[2];
+    c[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+__device__ inline void mat4_mul(const double A[16], const double B[16], double C[16]) {
+    double R[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s += A[4 * i + k] * B[4 * k + j];
+            R[4 * i + j] = s;
+        }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) C[i] = R[i];
+}
+
+// Kabsch rotation from the 3x3 cross-covariance H = sum (p - pm)(q - qm)^T by one-sided Jacobi SVD
+// (H V = U S), R = V U^T with the smallest-singular-value column rebuilt by cross products so that
+// det R = +1 (the Umeyama reflection fix of pcl::umeyama).
+__device__ inline void svd3_rotation(const double H[9], double R[9]) {
+    double A[9], V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    for (int i = 0; i < 9; ++i) A[i] = H[i];
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        double off = 0.0;
+        for (int p = 0; p < 2; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                double al = 0, be = 0, ga = 0;
+                for (int i = 0; i < 3; ++i) {
+                    al += A[3 * i + p] * A[3 * i + p];
+                    be += A[3 * i + q] * A[3 * i + q];
+                    ga += A[3 * i + p] * A[3 * i + q];
+                }
+                if (fabs(ga) <= 1e-300) continue;
+                if (fabs(ga) <= 1e-16 * sqrt(al * be)) continue;
+                off += fabs(ga);
+                const double zeta = (be - al) / (2.0 * ga);
+                const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+                for (int i = 0; i < 3; ++i) {
+                    const double ap = A[3 * i + p], aq = A[3 * i + q];
+                    A[3 * i + p] = c * ap - s * aq;
+                    A[3 * i + q] = s * ap + c * aq;
+                    const double vp = V[3 * i + p], vq = V[3 * i + q];
+                    V[3 * i + p] = c * vp - s * vq;
+                    V[3 * i + q] = s * vp + c * vq;
+                }
+            }
+        if (off == 0.0) break;
+    }
+    double sg[3];
+    for (int j = 0; j < 3; ++j) sg[j] = sqrt(A[j] * A[j] + A[3 + j] * A[3 + j] + A[6 + j] * A[6 + j]);
+    int c = 0;
+    if (sg[1] < sg[c]) c = 1;
+    if (sg[2] < sg[c]) c = 2;
+    const int a = (c + 1) % 3, b = (c + 2) % 3;
+    if (!(sg[a] > 0.0) || !(sg[b] > 0.0)) {
+        for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+        return;
+    }
+    double ua[3], ub[3], uc[3], va[3], vb[3], vc[3];
+    for (int i = 0; i < 3; ++i) {
+        ua[i] = A[3 * i + a] / sg[a];
+        ub[i] = A[3 * i + b] / sg[b];
+        va[i] = V[3 * i + a];
+        vb[i] = V[3 * i + b];
+    }
+    const double dab = ua[0] * ub[0] + ua[1] * ub[1] + ua[2] * ub[2];
+    double nb = 0;
+    for (int i = 0; i < 3; ++i) {
+        ub[i] -= dab * ua[i];
+        nb += ub[i] * ub[i];
+    }
+    nb = sqrt(nb);
+    for (int i = 0; i < 3; ++i) ub[i] /= nb;
+    cross3(ua, ub, uc);
+    cross3(va, vb, vc);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) R[3 * i + j] = va[i] * ua[j] + vb[i] * ub[j] + vc[i] * uc[j];
+}
+
+__device__ __forceinline__ int tri6(int i, int j) { return i * 6 - i * (i - 1) / 2 + (j - i); }
+
+// H x = -g, H symmetric positive definite given as its 21-entry upper triangle; returns 0 on success
+__device__ inline int chol6_solve(const double* H21, const double* g, double x[6]) {
+    double L[36];
+    for (int i = 0; i < 36; ++i) L[i] = 0.0;
+    for (int j = 0; j < 6; ++j) {
+        double s = H21[tri6(j, j)];
+        for (int k = 0; k < j; ++k) s -= L[6 * j + k] * L[6 * j + k];
+        if (!(s > 0.0)) return 1;
+        L[6 * j + j] = sqrt(s);
+        for (int i = j + 1; i < 6; ++i) {
+            double v = H21[tri6(j, i)];
+            for (int k = 0; k < j; ++k) v -= L[6 * i + k] * L[6 * j + k];
+            L[6 * i + j] = v / L[6 * j + j];
+        }
+    }
+    double y[6];
+    for (int i = 0; i < 6; ++i) {
+        double s = -g[i];
+        for (int k = 0; k < i; ++k) s -= L[6 * i + k] * y[k];
+        y[i] = s / L[6 * i + i];
+    }
+    for (int i = 5; i >= 0; --i) {
+        double s = y[i];
+        for (int k = i + 1; k < 6; ++k) s -= L[6 * k + i] * x[k];
+        x[i] = s / L[6 * i + i];
+    }
+    return 0;
+}
+
+// exp of xi = (omega, v) in SE(3), row-major 4x4
+__device__ inline void se3_exp(const double xi[6], double T[16]) {
+    const double wx = xi[0], wy = xi[1], wz = xi[2];
+    const double th2 = wx * wx + wy * wy + wz * wz, th = sqrt(th2);
+    double A, B, C;
+    if (th < 1e-5) {
+        A = 1.0 - th2 / 6.0;
+        B = 0.5 - th2 / 24.0;
+        C = 1.0 / 6.0 - th2 / 120.0;
+    } else {
+        A = sin(th) / th;
+        B = (1.0 - cos(th)) / th2;
+        C = (th - sin(th)) / (th2 * th);
+    }
+    const double W[9] = {0, -wz, wy, wz, 0, -wx, -wy, wx, 0};
+    double W2[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double s = 0;
+            for (int k = 0; k < 3; ++k) s += W[3 * i + k] * W[3 * k + j];
+            W2[3 * i + j] = s;
+        }
+    for (int i = 0; i < 3; ++i) {
+        double Vr[3];
+        for (int j = 0; j < 3; ++j) {
+            const double I = (i == j) ? 1.0 : 0.0;
+            T[4 * i + j] = I + A * W[3 * i + j] + B * W2[3 * i + j];
+            Vr[j] = I + B * W[3 * i + j] + C * W2[3 * i + j];
+        }
+        T[4 * i + 3] = Vr[0] * xi[3] + Vr[1] * xi[4] + Vr[2] * xi[5];
+    }
+    T[12] = T[13] = T[14] = 0.0;
+    T[15] = 1.0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-correspondence contributions. acc layout (ICP4R_ACC_LEN = 32 doubles):
+//   P2P_SVD : [0] n, [1..3] sum p', [4..6] sum q, [7..15] sum p' q^T, [16] sum d2
+//   GN kinds: [0..20] H upper triangle, [21..26] g = J^T r, [27] cost, [28] n
+
+__device__ __forceinline__ void acc_gn(double* acc, const double J[6], double r) {
+    int t = 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = i; j < 6; ++j) acc[t++] += J[i] * J[j];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) acc[21 + i] += J[i] * r;
+    acc[27] += r * r;
+}
+
+__device__ __forceinline__ void contrib_p2p_svd(double* acc, const double pw[3], float qx, float qy, float qz, float d2) {
+    const double q[3] = {(double)qx, (double)qy, (double)qz};
+    acc[0] += 1.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        acc[1 + i] += pw[i];
+        acc[4 + i] += q[i];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) acc[7 + 3 * i + j] += pw[i] * q[j];
+    }
+    acc[16] += (double)d2;
+}
+
+// LidarDistanceFactor (radarFactor.hpp:156-158): r = p' - c, J = [-[p']x | I]
+__device__ __forceinline__ void contrib_p2p_gn(double* acc, const double pw[3], float cx, float cy, float cz) {
+    const double r0 = pw[0] - (double)cx, r1 = pw[1] - (double)cy, r2 = pw[2] - (double)cz;
+    const double J0[6] = {0, pw[2], -pw[1], 1, 0, 0};
+    const double J1[6] = {-pw[2], 0, pw[0], 0, 1, 0};
+    const double J2[6] = {pw[1], -pw[0], 0, 0, 0, 1};
+    acc_gn(acc, J0, r0);
+    acc_gn(acc, J1, r1);
+    acc_gn(acc, J2, r2);
+    acc[28] += 1.0;
+}
+
+// LOAM plane through k points: A n = -1 by normal equations (adjugate), d = 1/|n|, n /= |n|
+template <int K>
+__device__ __forceinline__ bool plane_fit(const double (&P)[K][3], int k, double n[3], double& d) {
+    double m00 = 0, m01 = 0, m02 = 0, m11 = 0, m12 = 0, m22 = 0, v0 = 0, v1 = 0, v2 = 0;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        if (j < k) {
+            const double x = P[j][0], y = P[j][1], z = P[j][2];
+            m00 += x * x;
+            m01 += x * y;
+            m02 += x * z;
+            m11 += y * y;
+            m12 += y * z;
+            m22 += z * z;
+            v0 -= x;
+            v1 -= y;
+            v2 -= z;
+        }
+    }
+    const double c00 = m11 * m22 - m12 * m12, c01 = m02 * m12 - m01 * m22, c02 = m01 * m12 - m02 * m11;
+    const double c11 = m00 * m22 - m02 * m02, c12 = m01 * m02 - m00 * m12, c22 = m00 * m11 - m01 * m01;
+    const double det = (m00 * c00 + m01 * c01) + m02 * c02;
+    if (!(fabs(det) > 0.0) || !isfinite(det)) return false;
+    const double nx = ((c00 * v0 + c01 * v1) + c02 * v2) / det;
+    const double ny = ((c01 * v0 + c11 * v1) + c12 * v2) / det;
+    const double nz = ((c02 * v0 + c12 * v1) + c22 * v2) / det;
+    const double nn = sqrt((nx * nx + ny * ny) + nz * nz);
+    if (!(nn > 0.0) || !isfinite(nn)) return false;
+    d = 1.0 / nn;
+    n[0] = nx / nn;
+    n[1] = ny / nn;
+    n[2] = nz / nn;
+    return true;
+}
+
+// LidarPlaneNormFactor (radarFactor.hpp:122): r = n.p' + d, J = [(p' x n)^T | n^T]
+template <int K>
+__device__ __forceinline__ bool contrib_p2plane(double* acc, const double pw[3], const double (&P)[K][3], int k,
+                                                double plane_thresh) {
+    double n[3], d;
+    if (!plane_fit<K>(P, k, n, d)) return false;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        if (j < k) {
+            const double e = ((n[0] * P[j][0] + n[1] * P[j][1]) + n[2] * P[j][2]) + d;
+            if (!(fabs(e) <= plane_thresh)) return false;
+        }
+    }
+    const double r = ((n[0] * pw[0] + n[1] * pw[1]) + n[2] * pw[2]) + d;
+    double pxn[3];
+    cross3(pw, n, pxn);
+    const double J[6] = {pxn[0], pxn[1], pxn[2], n[0], n[1], n[2]};
+    acc_gn(acc, J, r);
+    acc[28] += 1.0;
+    return true;
+}
+
+// RadarEdgeFactor (radarFactor.hpp:34-39), s = 1: r = ((p'-a) x (p'-b)) / |a-b|
+__device__ __forceinline__ bool contrib_p2line(double* acc, const double pw[3], const double a[3], const double b[3]) {
+    const double ba[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
+    const double L = sqrt((ba[0] * ba[0] + ba[1] * ba[1]) + ba[2] * ba[2]);
+    if (!(L > 0.0)) return false;
+    const double u[3] = {pw[0] - a[0], pw[1] - a[1], pw[2] - a[2]};
+    const double v[3] = {pw[0] - b[0], pw[1] - b[1], pw[2] - b[2]};
+    double nu[3];
+    cross3(u, v, nu);
+    const double e[3] = {ba[0] / L, ba[1] / L, ba[2] / L};
+    const double D[9] = {0, -e[2], e[1], e[2], 0, -e[0], -e[1], e[0], 0};
+    const double Px[9] = {0, pw[2], -pw[1], -pw[2], 0, pw[0], pw[1], -pw[0], 0};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        double J[6];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            J[j] = (D[3 * i] * Px[j] + D[3 * i + 1] * Px[3 + j]) + D[3 * i + 2] * Px[6 + j];
+            J[3 + j] = D[3 * i + j];
+        }
+        acc_gn(acc, J, nu[i] / L);
+    }
+    acc[28] += 1.0;
+    return true;
+}
+
+}  // namespace icp4r

@@ -1,0 +1,401 @@
+// grid.cu — the device map: voxel-grid build (replaces KD_TREE::Build / BuildTree,
+// /root/reference/third_party/ikd-Tree/ikd_Tree.cpp:354-365,582-630) and the stand-alone kNN kernels behind
+// icp4r_map_knn / icp4r_map_knn_brute (replace Nearest_Search, ikd_Tree.cpp:368-398).
+#include <cmath>
+#include <cstring>
+
+#include "ctx.h"
+#include "device_math.cuh"
+#include "grid_knn.cuh"
+
+namespace icp4r {
+
+// ------------------------------------------------------------------------------------------------ bbox
+__device__ __forceinline__ int f2ord(float f) {  // order-preserving float -> int
+    const int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+static inline float ord2f(int i) {
+    const int j = i >= 0 ? i : i ^ 0x7fffffff;
+    float f;
+    std::memcpy(&f, &j, 4);
+    return f;
+}
+
+__global__ void bbox_init(int* bb) {
+    if (threadIdx.x < 3) bb[threadIdx.x] = 0x7fffffff;
+    else if (threadIdx.x < 6) bb[threadIdx.x] = (int)0x80000000;
+    else if (threadIdx.x == 6) bb[6] = 0;
+}
+
+__global__ void __launch_bounds__(256) bbox_kernel(const float4* __restrict__ pts, const uint8_t* __restrict__ valid, int m,
+                                                   int* __restrict__ bb) {
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    int cnt = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+        if (!valid[i]) continue;
+        const float4 p = pts[i];
+        if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) continue;
+        mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x);
+        mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
+        mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z);
+        ++cnt;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            mn[a] = fminf(mn[a], __shfl_xor_sync(FULL, mn[a], o));
+            mx[a] = fmaxf(mx[a], __shfl_xor_sync(FULL, mx[a], o));
+        }
+        cnt += __shfl_xor_sync(FULL, cnt, o);
+    }
+    if ((threadIdx.x & 31) == 0 && cnt > 0) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            atomicMin(bb + a, f2ord(mn[a]));
+            atomicMax(bb + 3 + a, f2ord(mx[a]));
+        }
+        atomicAdd(bb + 6, cnt);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ keys
+__global__ void __launch_bounds__(256) key_kernel(const float4* __restrict__ pts, const uint8_t* __restrict__ valid, int m,
+                                                  GridDesc g, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const float4 p = pts[i];
+    uint32_t key = (uint32_t)g.ncells;  // invalid / non-finite points sort behind every cell
+    if (valid[i] && isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+        const int cx = cell_of(p.x, g.ox, g.inv_cell, g.nx);
+        const int cy = cell_of(p.y, g.oy, g.inv_cell, g.ny);
+        const int cz = cell_of(p.z, g.oz, g.inv_cell, g.nz);
+        key = (uint32_t)(cz * g.ny + cy) * (uint32_t)g.nx + (uint32_t)cx;
+    }
+    keys[i] = key;
+    vals[i] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(256) gather_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ vals, int n,
+                                                     float4* __restrict__ sorted) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t j = vals[i];
+    const float4 p = pts[j];
+    sorted[i] = make_float4(p.x, p.y, p.z, __uint_as_float(j));
+}
+
+// cell_start[c] = first sorted position whose key >= c  (c in [0, ncells])
+__global__ void __launch_bounds__(256) cell_start_kernel(const uint32_t* __restrict__ keys, int n, int ncells,
+                                                         uint32_t* __restrict__ cell_start) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > ncells) return;
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(keys + mid) < (uint32_t)c) lo = mid + 1;
+        else hi = mid;
+    }
+    cell_start[c] = (uint32_t)lo;
+}
+
+int map_reserve(Ctx* c, Map& mp, int cap) {
+    if ((size_t)cap * sizeof(float4) <= mp.pts.cap) return ICP4R_OK;
+    // grow geometrically, keep contents
+    size_t want = (size_t)cap;
+    size_t have = mp.pts.cap / sizeof(float4);
+    if (want < have * 2) want = have * 2;
+    DevBuf np, nv;
+    CKS(reserve(c, np, want * sizeof(float4)));
+    CKS(reserve(c, nv, want));
+    if (mp.m > 0) {
+        CK(cudaMemcpyAsync(np.p, mp.pts.p, (size_t)mp.m * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
+        CK(cudaMemcpyAsync(nv.p, mp.valid.p, (size_t)mp.m, cudaMemcpyDeviceToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    release(mp.pts);
+    release(mp.valid);
+    mp.pts = np;
+    mp.valid = nv;
+    return ICP4R_OK;
+}
+
+int map_rebuild_grid(Ctx* c, Map& mp) {
+    const int m = mp.m;
+    mp.built = false;
+    mp.grid = GridDesc{};
+    if (m <= 0) {
+        mp.m_valid = 0;
+        CKS(reserve(c, mp.cell_start, 2 * sizeof(uint32_t)));
+        CK(cudaMemsetAsync(mp.cell_start.p, 0, 2 * sizeof(uint32_t), c->stream));
+        GridDesc g{};
+        g.nx = g.ny = g.nz = 1;
+        g.ncells = 1;
+        g.cell = g.inv_cell = 1.f;
+        g.m = 0;
+        g.sorted = mp.sorted.as<float4>();
+        g.cell_start = mp.cell_start.as<uint32_t>();
+        mp.grid = g;
+        mp.built = true;
+        return ICP4R_OK;
+    }
+    // 1. bounding box of the valid points
+    CKS(reserve(c, c->d_scratch, 4096));
+    int* d_bb = c->d_scratch.as<int>();
+    bbox_init<<<1, 32, 0, c->stream>>>(d_bb);
+    const int bblocks = std::min((m + 255) / 256, c->sm_count * 8);
+    bbox_kernel<<<bblocks, 256, 0, c->stream>>>(mp.pts.as<float4>(), mp.valid.as<uint8_t>(), m, d_bb);
+    c->launches += 2;
+    int h_bb[8];
+    CK(cudaMemcpyAsync(h_bb, d_bb, 7 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    const int nvalid = h_bb[6];
+    mp.m_valid = nvalid;
+    float mn[3], mx[3];
+    for (int a = 0; a < 3; ++a) {
+        mn[a] = nvalid ? ord2f(h_bb[a]) : 0.f;
+        mx[a] = nvalid ? ord2f(h_bb[3 + a]) : 0.f;
+        mp.bb_min[a] = mn[a];
+        mp.bb_max[a] = mx[a];
+    }
+    // 2. grid geometry: ~8 points per cell by volume unless the caller fixed the cell size
+    double ext[3];
+    double L = 1.0;
+    for (int a = 0; a < 3; ++a) {
+        ext[a] = (double)mx[a] - (double)mn[a];
+        L = std::max(L, std::max(std::fabs((double)mn[a]), std::fabs((double)mx[a])));
+    }
+    const double emax = std::max(ext[0], std::max(ext[1], ext[2]));
+    double cell = mp.user_cell > 0.f ? (double)mp.user_cell : 0.0;
+    if (!(cell > 0.0)) {
+        const double floor_e = std::max(emax * 1e-3, 1e-6);
+        const double vol = std::max(ext[0], floor_e) * std::max(ext[1], floor_e) * std::max(ext[2], floor_e);
+        cell = std::cbrt(vol / std::max(1.0, nvalid / 8.0));
+        cell = std::max(cell, std::max(emax * 1e-4, 1e-6));
+    }
+    const double max_cells = 64.0 * 1024 * 1024;
+    int nx, ny, nz;
+    for (;;) {
+        const double fx = std::floor(ext[0] / cell) + 1, fy = std::floor(ext[1] / cell) + 1, fz = std::floor(ext[2] / cell) + 1;
+        if (fx * fy * fz <= max_cells && fx < 2e6 && fy < 2e6 && fz < 2e6) {
+            nx = (int)fx;
+            ny = (int)fy;
+            nz = (int)fz;
+            break;
+        }
+        cell *= 1.26;  // coarsen: exactness does not depend on the cell size
+    }
+    GridDesc g{};
+    g.ox = mn[0];
+    g.oy = mn[1];
+    g.oz = mn[2];
+    g.cell = (float)cell;
+    g.inv_cell = 1.0f / g.cell;
+    g.nx = nx;
+    g.ny = ny;
+    g.nz = nz;
+    g.ncells = nx * ny * nz;
+    g.m = nvalid;
+    g.margin = (float)(L * 9.5367431640625e-7);
+    // 3. keys + stable radix sort by key
+    CKS(reserve(c, mp.keys_a, (size_t)m * 4));
+    CKS(reserve(c, mp.keys_b, (size_t)m * 4));
+    CKS(reserve(c, mp.vals_a, (size_t)m * 4));
+    CKS(reserve(c, mp.vals_b, (size_t)m * 4));
+    CKS(reserve(c, mp.sorted, (size_t)std::max(m, 1) * sizeof(float4)));
+    CKS(reserve(c, mp.cell_start, ((size_t)g.ncells + 2) * sizeof(uint32_t)));
+    key_kernel<<<(m + 255) / 256, 256, 0, c->stream>>>(mp.pts.as<float4>(), mp.valid.as<uint8_t>(), m, g,
+                                                         mp.keys_a.as<uint32_t>(), mp.vals_a.as<uint32_t>());
+    c->launches += 1;
+    int bits = 1;
+    while ((1ll << bits) <= (long long)g.ncells) ++bits;  // key == ncells must be representable
+    uint32_t *ks, *vs;
+    CKS(radix_sort_pairs(c, mp.keys_a.as<uint32_t>(), mp.keys_b.as<uint32_t>(), mp.vals_a.as<uint32_t>(),
+                         mp.vals_b.as<uint32_t>(), m, bits, c->d_scratch, &ks, &vs));
+    // 4. points into sorted order (valid ones come first), cell table by binary search over the sorted keys
+    if (nvalid > 0) {
+        gather_kernel<<<(nvalid + 255) / 256, 256, 0, c->stream>>>(mp.pts.as<float4>(), vs, nvalid, mp.sorted.as<float4>());
+        c->launches += 1;
+    }
+    cell_start_kernel<<<(g.ncells + 1 + 255) / 256, 256, 0, c->stream>>>(ks, m, g.ncells, mp.cell_start.as<uint32_t>());
+    c->launches += 1;
+    CK(cudaGetLastError());
+    g.sorted = mp.sorted.as<float4>();
+    g.cell_start = mp.cell_start.as<uint32_t>();
+    mp.grid = g;
+    mp.built = true;
+    return ICP4R_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ gate
+void gate_params(double max_dist, float* gate_f, float* gate_r) {
+    if (!(max_dist > 0.0) || std::isinf(max_dist)) {
+        *gate_f = INFINITY;
+        *gate_r = INFINITY;
+        return;
+    }
+    const double g2 = max_dist * max_dist;  // ikd_Tree.cpp:880
+    float f = (float)g2;
+    if ((double)f > g2) f = std::nextafterf(f, 0.0f);  // largest float with (double)f <= g2
+    *gate_f = f;
+    float r = (float)(max_dist * (1.0 + 1e-6));
+    if ((double)r < max_dist * (1.0 + 1e-6)) r = std::nextafterf(r, INFINITY);
+    *gate_r = r;
+}
+
+// ------------------------------------------------------------------------------------------------ grid kNN kernel
+template <int K>
+__global__ void __launch_bounds__(256) grid_knn_kernel(GridDesc g, const float4* __restrict__ q, int nq, int k, float gate_f,
+                                                       float gate_r, int32_t* __restrict__ idx, float* __restrict__ d2,
+                                                       int32_t* __restrict__ found) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = warp; i < nq; i += nwarps) {
+        const float4 p = __ldg(q + i);
+        const uint64_t mine = warp_grid_knn<K>(g, p.x, p.y, p.z, gate_f, gate_r, lane);
+        const bool have = (lane < k) && (mine != KEY_EMPTY);
+        if (lane < k) {
+            idx[(size_t)i * k + lane] = have ? key_idx(mine) : -1;
+            d2[(size_t)i * k + lane] = have ? key_d2(mine) : INFINITY;
+        }
+        const unsigned b = __ballot_sync(FULL, have);
+        if (found && lane == 0) found[i] = __popc(b);
+    }
+}
+
+template <int K>
+static int launch_grid_knn(Ctx* c, const GridDesc& g, const float4* q, int nq, int k, float gate_f, float gate_r, int32_t* idx,
+                           float* d2, int32_t* found) {
+    const int wpb = 8;
+    int blocks = (nq + wpb - 1) / wpb;
+    blocks = std::min(blocks, c->sm_count * 8);
+    grid_knn_kernel<K><<<blocks, wpb * 32, 0, c->stream>>>(g, q, nq, k, gate_f, gate_r, idx, d2, found);
+    c->launches += 1;
+    CK(cudaGetLastError());
+    return ICP4R_OK;
+}
+
+int grid_knn(Ctx* c, const Map& mp, const float4* q, int nq, int k, double max_dist, int32_t* idx, float* d2, int32_t* found) {
+    if (nq <= 0) return ICP4R_OK;
+    float gf, gr;
+    gate_params(max_dist, &gf, &gr);
+    const GridDesc& g = mp.grid;
+    if (k == 1) return launch_grid_knn<1>(c, g, q, nq, k, gf, gr, idx, d2, found);
+    if (k == 2) return launch_grid_knn<2>(c, g, q, nq, k, gf, gr, idx, d2, found);
+    if (k <= 5) return launch_grid_knn<5>(c, g, q, nq, k, gf, gr, idx, d2, found);
+    if (k <= 8) return launch_grid_knn<8>(c, g, q, nq, k, gf, gr, idx, d2, found);
+    return launch_grid_knn<16>(c, g, q, nq, k, gf, gr, idx, d2, found);
+}
+
+// ------------------------------------------------------------------------------------------------ exhaustive kNN
+// Thread per query, target tiles staged in shared memory (every thread reads the same candidate: broadcast),
+// the target range split across blockIdx.y so small query counts still fill the GPU; a second kernel merges.
+constexpr int BF_THREADS = 128;
+constexpr int BF_TILE = 1024;
+
+template <int K>
+__global__ void __launch_bounds__(BF_THREADS) brute_knn_kernel(const float4* __restrict__ sorted, int m, const float4* __restrict__ q,
+                                                               int nq, float gate_f, int splits, uint64_t* __restrict__ part) {
+    __shared__ float4 tile[BF_TILE];
+    const int qi = blockIdx.x * BF_THREADS + threadIdx.x;
+    const int sp = blockIdx.y;
+    const int chunk = (m + splits - 1) / splits;
+    const int lo = sp * chunk, hi = min(m, lo + chunk);
+    float4 p = make_float4(0, 0, 0, 0);
+    if (qi < nq) p = q[qi];
+    TopK<K> list;
+    list.clear();
+    for (int base = lo; base < hi; base += BF_TILE) {
+        const int cnt = min(BF_TILE, hi - base);
+        __syncthreads();
+        for (int t = threadIdx.x; t < cnt; t += BF_THREADS) tile[t] = sorted[base + t];
+        __syncthreads();
+        for (int t = 0; t < cnt; ++t) {
+            const float4 cpt = tile[t];
+            const float d = dist2_exact(p.x, p.y, p.z, cpt.x, cpt.y, cpt.z);
+            if (d <= gate_f) list.insert(pack_key(d, __float_as_int(cpt.w)));
+        }
+    }
+    if (qi < nq) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) part[((size_t)qi * splits + sp) * K + j] = list.key[j];
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(128) brute_merge_kernel(const uint64_t* __restrict__ part, int nq, int splits, int k,
+                                                          int32_t* __restrict__ idx, float* __restrict__ d2,
+                                                          int32_t* __restrict__ found) {
+    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
+    TopK<K> list;
+    list.clear();
+    for (int s = 0; s < splits; ++s)
+#pragma unroll
+        for (int j = 0; j < K; ++j) list.insert(part[((size_t)qi * splits + s) * K + j]);
+    int f = 0;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        if (j < k) {
+            const bool have = list.key[j] != KEY_EMPTY;
+            idx[(size_t)qi * k + j] = have ? key_idx(list.key[j]) : -1;
+            d2[(size_t)qi * k + j] = have ? key_d2(list.key[j]) : INFINITY;
+            f += have;
+        }
+    }
+    if (found) found[qi] = f;
+}
+
+template <int K>
+static int launch_brute(Ctx* c, const Map& mp, const float4* q, int nq, int k, float gate_f, int32_t* idx, float* d2,
+                        int32_t* found) {
+    const int m = mp.grid.m;
+    const int qblocks = (nq + BF_THREADS - 1) / BF_THREADS;
+    int splits = std::max(1, std::min((c->sm_count * 4 + qblocks - 1) / qblocks, (m + BF_TILE - 1) / BF_TILE));
+    splits = std::min(splits, 65535);
+    CKS(reserve(c, c->d_partials, (size_t)nq * splits * K * sizeof(uint64_t)));
+    uint64_t* part = c->d_partials.as<uint64_t>();
+    brute_knn_kernel<K><<<dim3(qblocks, splits), BF_THREADS, 0, c->stream>>>(mp.grid.sorted, m, q, nq, gate_f, splits, part);
+    brute_merge_kernel<K><<<(nq + 127) / 128, 128, 0, c->stream>>>(part, nq, splits, k, idx, d2, found);
+    c->launches += 2;
+    CK(cudaGetLastError());
+    return ICP4R_OK;
+}
+
+int brute_knn(Ctx* c, const Map& mp, const float4* q, int nq, int k, double max_dist, int32_t* idx, float* d2, int32_t* found) {
+    if (nq <= 0) return ICP4R_OK;
+    float gf, gr;
+    gate_params(max_dist, &gf, &gr);
+    if (k == 1) return launch_brute<1>(c, mp, q, nq, k, gf, idx, d2, found);
+    if (k == 2) return launch_brute<2>(c, mp, q, nq, k, gf, idx, d2, found);
+    if (k <= 5) return launch_brute<5>(c, mp, q, nq, k, gf, idx, d2, found);
+    if (k <= 8) return launch_brute<8>(c, mp, q, nq, k, gf, idx, d2, found);
+    return launch_brute<16>(c, mp, q, nq, k, gf, idx, d2, found);
+}
+
+// ------------------------------------------------------------------------------------------------ transform
+struct Pose12 {
+    double T[12];
+};
+// pointAssociateToMap (/root/reference/src/radar_odometry.cpp:137-145): p' = R p + t in double, stored as float
+__global__ void __launch_bounds__(256) transform_kernel(Pose12 P, const float4* __restrict__ in, int n, float4* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = in[i];
+    double pw[3];
+    xform_point(P.T, p.x, p.y, p.z, pw);
+    out[i] = make_float4((float)pw[0], (float)pw[1], (float)pw[2], p.w);
+}
+
+int transform_points(Ctx* c, const double* T_host, const float4* d_in, int n, float4* d_out) {
+    Pose12 P;
+    for (int i = 0; i < 12; ++i) P.T[i] = T_host[i];
+    transform_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(P, d_in, n, d_out);
+    c->launches += 1;
+    CK(cudaGetLastError());
+    return ICP4R_OK;
+}
+
+}  // namespace icp4r

@@ -1,0 +1,144 @@
+// grid_knn.cuh — exact k-nearest-neighbour search of one query by one warp over the voxel grid.
+//
+// Replaces KD_TREE::Search (/root/reference/third_party/ikd-Tree/ikd_Tree.cpp:877-1021) with the same
+// result set: the k valid points of smallest float d2 = (dx*dx+dy*dy)+dz*dz with (double)d2 <= max_dist^2,
+// ascending; the product's tie rule (lowest index first) replaces the reference's traversal order.
+//
+// Search = cube-shell expansion around the query's cell.  After the cube of radius R has been scanned,
+// every unscanned point lies beyond one of the cube faces that still has cells of interest behind it, so
+// its distance is at least `bound` = the smallest query-to-face distance (minus a rounding margin).  The
+// search stops as soon as the current k-th best d2 is strictly below bound^2 (nothing unscanned can enter,
+// not even on a tie) or the cube covers the whole gate box.
+//
+// Lanes stride over the candidates of one x-row range at a time (cells of an x-row are contiguous in the
+// sorted array, so each range is one coalesced float4 stream), keep a private sorted top-K in registers
+// and the 32 lists are merged with warp reductions.
+#pragma once
+#include "ctx.h"
+#include "device_math.cuh"
+
+namespace icp4r {
+
+constexpr int GRID_RING_CAP = 8;
+
+__device__ __forceinline__ int cell_of(float v, float o, float inv, int dim) {
+    float f = floorf(__fmul_rn(__fsub_rn(v, o), inv));
+    f = fminf(fmaxf(f, 0.0f), (float)(dim - 1));  // NaN -> 0
+    return (int)f;
+}
+
+template <int K>
+__device__ __forceinline__ void scan_range(const float4* __restrict__ sorted, uint32_t s, uint32_t e, int lane, float qx,
+                                           float qy, float qz, float gate_f, uint64_t kth, TopK<K>& list) {
+    for (uint32_t i = s + lane; i < e; i += 32) {
+        const float4 c = __ldg(sorted + i);
+        const float d = dist2_exact(qx, qy, qz, c.x, c.y, c.z);
+        if (d <= gate_f) {  // false for NaN
+            const uint64_t key = pack_key(d, __float_as_int(c.w));
+            if (key < kth) list.insert(key);
+        }
+    }
+}
+
+// Returns, in lane r < K, the r-th nearest neighbour's packed key (KEY_EMPTY if fewer exist).
+template <int K>
+__device__ __forceinline__ uint64_t warp_grid_knn(const GridDesc& g, float qx, float qy, float qz, float gate_f,
+                                                  float gate_r, int lane) {
+    const float4* __restrict__ sorted = g.sorted;
+    const uint32_t* __restrict__ cs = g.cell_start;
+    const float qmax = fmaxf(fabsf(qx), fmaxf(fabsf(qy), fabsf(qz)));
+    const float margin = fmaxf(g.margin, 9.5367431640625e-7f * qmax);  // 2^-20 * magnitude
+
+    const int cx = cell_of(qx, g.ox, g.inv_cell, g.nx);
+    const int cy = cell_of(qy, g.oy, g.inv_cell, g.ny);
+    const int cz = cell_of(qz, g.oz, g.inv_cell, g.nz);
+    int lox = 0, hix = g.nx - 1, loy = 0, hiy = g.ny - 1, loz = 0, hiz = g.nz - 1;
+    if (gate_r < 3.0e38f) {
+        const float gr = gate_r + margin;
+        lox = cell_of(qx - gr, g.ox, g.inv_cell, g.nx);
+        hix = cell_of(qx + gr, g.ox, g.inv_cell, g.nx);
+        loy = cell_of(qy - gr, g.oy, g.inv_cell, g.ny);
+        hiy = cell_of(qy + gr, g.oy, g.inv_cell, g.ny);
+        loz = cell_of(qz - gr, g.oz, g.inv_cell, g.nz);
+        hiz = cell_of(qz + gr, g.oz, g.inv_cell, g.nz);
+    }
+    const int rneed = max(max(max(cx - lox, hix - cx), max(cy - loy, hiy - cy)), max(cz - loz, hiz - cz));
+
+    TopK<K> list;
+    list.clear();
+    uint64_t mine = KEY_EMPTY, kth = KEY_EMPTY;
+    int prev = -1;  // radius already scanned
+    bool done = false;
+    for (int R = min(1, rneed); R <= rneed && R <= GRID_RING_CAP; ++R) {
+        // rows (dy, dz) of the shell, 32 at a time: each lane fetches the cell ranges of one row
+        const int side = 2 * R + 1, rows = side * side;
+        for (int rb = 0; rb < rows; rb += 32) {
+            const int r = rb + lane;
+            uint32_t s0 = 0, e0 = 0, s1 = 0, e1 = 0;
+            if (r < rows) {
+                const int dy = r % side - R, dz = r / side - R;
+                const int y = cy + dy, z = cz + dz;
+                if (y >= loy && y <= hiy && z >= loz && z <= hiz) {
+                    const uint32_t rowbase = (uint32_t)(z * g.ny + y) * (uint32_t)g.nx;
+                    const int xa = max(cx - R, lox), xb = min(cx + R, hix);
+                    if (max(abs(dy), abs(dz)) > prev) {  // new row: whole x range
+                        if (xa <= xb) {
+                            s0 = __ldg(cs + rowbase + xa);
+                            e0 = __ldg(cs + rowbase + xb + 1);
+                        }
+                    } else {  // row already scanned up to radius prev: only the two end caps
+                        const int xl = min(cx - prev - 1, hix), xr = max(cx + prev + 1, lox);
+                        if (xa <= xl) {
+                            s0 = __ldg(cs + rowbase + xa);
+                            e0 = __ldg(cs + rowbase + xl + 1);
+                        }
+                        if (xr <= xb) {
+                            s1 = __ldg(cs + rowbase + xr);
+                            e1 = __ldg(cs + rowbase + xb + 1);
+                        }
+                    }
+                }
+            }
+            unsigned live = __ballot_sync(FULL, (e0 > s0) || (e1 > s1));
+            while (live) {
+                const int src = __ffs(live) - 1;
+                live &= live - 1;
+                const uint32_t a0 = __shfl_sync(FULL, s0, src), b0 = __shfl_sync(FULL, e0, src);
+                const uint32_t a1 = __shfl_sync(FULL, s1, src), b1 = __shfl_sync(FULL, e1, src);
+                scan_range<K>(sorted, a0, b0, lane, qx, qy, qz, gate_f, kth, list);
+                scan_range<K>(sorted, a1, b1, lane, qx, qy, qz, gate_f, kth, list);
+            }
+        }
+        prev = R;
+        if (mine != KEY_EMPTY) list.insert(mine);  // carry the previous shells' winners (lanes < K)
+        mine = warp_merge_topk<K>(list, lane);
+        list.clear();
+        kth = __shfl_sync(FULL, mine, K - 1);
+
+        float bound = 3.4e38f;
+        if (cx - R > lox) bound = fminf(bound, qx - (g.ox + (float)(cx - R) * g.cell));
+        if (cx + R < hix) bound = fminf(bound, (g.ox + (float)(cx + R + 1) * g.cell) - qx);
+        if (cy - R > loy) bound = fminf(bound, qy - (g.oy + (float)(cy - R) * g.cell));
+        if (cy + R < hiy) bound = fminf(bound, (g.oy + (float)(cy + R + 1) * g.cell) - qy);
+        if (cz - R > loz) bound = fminf(bound, qz - (g.oz + (float)(cz - R) * g.cell));
+        if (cz + R < hiz) bound = fminf(bound, (g.oz + (float)(cz + R + 1) * g.cell) - qz);
+        if (bound > 3.0e38f) {
+            done = true;  // cube covers the gate box
+            break;
+        }
+        const float b = bound - margin;
+        if (b > 0.0f && kth != KEY_EMPTY && key_d2(kth) < b * b * 0.99999905f) {
+            done = true;
+            break;
+        }
+    }
+    if (!done && rneed > 0 && prev < rneed) {
+        // ring cap reached (far-away ungated query or a very wide gate): exhaustive scan, still exact
+        list.clear();
+        scan_range<K>(sorted, 0u, (uint32_t)g.m, lane, qx, qy, qz, gate_f, KEY_EMPTY, list);
+        mine = warp_merge_topk<K>(list, lane);
+    }
+    return mine;
+}
+
+}  // namespace icp4r

@@ -1,0 +1,461 @@
+// register_batch.cu — batched frame-pair registration: one CTA per (source, target) pair, both clouds and a
+// per-pair voxel grid resident in shared memory for every iteration of the loop, so a pair costs one read of
+// its two clouds from HBM and nothing else (16·(N+M)+64 bytes per registration).
+//
+// Replaces pcl::IterativeClosestPoint::align for scan-to-scan odometry
+// (/root/reference/src/iterative_closest_point.cpp:510-521): 1-NN (exact, ties to the lowest index) ->
+// Kabsch/Umeyama in fp64 (or the 6x6 Gauss-Newton form of LidarDistanceFactor, radarFactor.hpp:140-171).
+//
+// Per pair: (1) bounding box + cell geometry of the target, (2) counting sort of the target into cell order
+// inside shared memory, (3) max_iterations x { thread-per-point 1-NN by cube-shell expansion over the
+// shared-memory grid, fp64 accumulators in registers, shuffle + shared-memory reduction in a fixed order,
+// one thread solves and updates the pose }, (4) fitness pass.
+#include <cmath>
+#include <cstring>
+
+#include "ctx.h"
+#include "device_math.cuh"
+
+namespace icp4r {
+
+constexpr int RB_THREADS = 256;
+constexpr int RB_WARPS = RB_THREADS / 32;
+constexpr int RB_MAXC = 4096;  // cells per pair
+
+struct BatchParams {
+    const float4* src;
+    const int32_t* soff;
+    const float4* tgt;
+    const int32_t* toff;
+    int n_pairs, max_n, max_m;
+    int max_iterations, early_exit;
+    float gate_f, gate_r;
+    double rot_eps, trans_eps, mse_abs_eps;
+    double T0[16];
+};
+
+struct PairGrid {
+    float ox, oy, oz, cell, inv_cell, margin;
+    int nx, ny, nz, ncells;
+};
+
+__device__ __forceinline__ int cell_of_s(float v, float o, float inv, int dim) {
+    float f = floorf(__fmul_rn(__fsub_rn(v, o), inv));
+    f = fminf(fmaxf(f, 0.0f), (float)(dim - 1));
+    return (int)f;
+}
+
+// exact 1-NN of (qx,qy,qz) over the shared-memory grid; returns the packed key and the slot of the winner
+__device__ __forceinline__ uint64_t thread_grid_nn(const PairGrid& g, const float4* __restrict__ s_tgt,
+                                                   const uint32_t* __restrict__ cs, float qx, float qy, float qz, float gate_f,
+                                                   float gate_r, int& best_pos) {
+    const float qmax = fmaxf(fabsf(qx), fmaxf(fabsf(qy), fabsf(qz)));
+    const float margin = fmaxf(g.margin, 9.5367431640625e-7f * qmax);
+    const int cx = cell_of_s(qx, g.ox, g.inv_cell, g.nx);
+    const int cy = cell_of_s(qy, g.oy, g.inv_cell, g.ny);
+    const int cz = cell_of_s(qz, g.oz, g.inv_cell, g.nz);
+    int lox = 0, hix = g.nx - 1, loy = 0, hiy = g.ny - 1, loz = 0, hiz = g.nz - 1;
+    if (gate_r < 3.0e38f) {
+        const float gr = gate_r + margin;
+        lox = cell_of_s(qx - gr, g.ox, g.inv_cell, g.nx);
+        hix = cell_of_s(qx + gr, g.ox, g.inv_cell, g.nx);
+        loy = cell_of_s(qy - gr, g.oy, g.inv_cell, g.ny);
+        hiy = cell_of_s(qy + gr, g.oy, g.inv_cell, g.ny);
+        loz = cell_of_s(qz - gr, g.oz, g.inv_cell, g.nz);
+        hiz = cell_of_s(qz + gr, g.oz, g.inv_cell, g.nz);
+    }
+    const int rneed = max(max(max(cx - lox, hix - cx), max(cy - loy, hiy - cy)), max(cz - loz, hiz - cz));
+    uint64_t best = KEY_EMPTY;
+    best_pos = -1;
+    int prev = -1;
+    for (int R = min(1, rneed); R <= rneed; ++R) {
+        const int z0 = max(cz - R, loz), z1 = min(cz + R, hiz);
+        const int y0 = max(cy - R, loy), y1 = min(cy + R, hiy);
+        const int xa = max(cx - R, lox), xb = min(cx + R, hix);
+        for (int z = z0; z <= z1; ++z)
+            for (int y = y0; y <= y1; ++y) {
+                const int rowbase = (z * g.ny + y) * g.nx;
+                const bool fresh = max(abs(y - cy), abs(z - cz)) > prev;
+                // a fresh row is one range; an old row contributes its two end caps
+                const int nseg = fresh ? 1 : 2;
+                for (int sgi = 0; sgi < nseg; ++sgi) {
+                    int a, b;
+                    if (fresh) {
+                        a = xa;
+                        b = xb;
+                    } else if (sgi == 0) {
+                        a = xa;
+                        b = min(cx - prev - 1, hix);
+                    } else {
+                        a = max(cx + prev + 1, lox);
+                        b = xb;
+                    }
+                    if (a > b) continue;
+                    const uint32_t s = cs[rowbase + a], e = cs[rowbase + b + 1];
+                    for (uint32_t j = s; j < e; ++j) {
+                        const float4 c = s_tgt[j];
+                        const float d = dist2_exact(qx, qy, qz, c.x, c.y, c.z);
+                        if (d <= gate_f) {
+                            const uint64_t key = pack_key(d, __float_as_int(c.w));
+                            if (key < best) {
+                                best = key;
+                                best_pos = (int)j;
+                            }
+                        }
+                    }
+                }
+            }
+        prev = R;
+        float bound = 3.4e38f;
+        if (cx - R > lox) bound = fminf(bound, qx - (g.ox + (float)(cx - R) * g.cell));
+        if (cx + R < hix) bound = fminf(bound, (g.ox + (float)(cx + R + 1) * g.cell) - qx);
+        if (cy - R > loy) bound = fminf(bound, qy - (g.oy + (float)(cy - R) * g.cell));
+        if (cy + R < hiy) bound = fminf(bound, (g.oy + (float)(cy + R + 1) * g.cell) - qy);
+        if (cz - R > loz) bound = fminf(bound, qz - (g.oz + (float)(cz - R) * g.cell));
+        if (cz + R < hiz) bound = fminf(bound, (g.oz + (float)(cz + R + 1) * g.cell) - qz);
+        if (bound > 3.0e38f) break;
+        const float b = bound - margin;
+        if (b > 0.0f && best != KEY_EMPTY && key_d2(best) < b * b * 0.99999905f) break;
+    }
+    return best;
+}
+
+template <int NV>
+__device__ __forceinline__ void block_reduce(double (&acc)[NV], double* s_red /*[RB_WARPS][32]*/, double* s_tot, int tid) {
+    const int lane = tid & 31, w = tid >> 5;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        double x = acc[v];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+        if (lane == 0) s_red[w * 32 + v] = x;
+    }
+    __syncthreads();
+    if (tid < NV) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < RB_WARPS; ++j) s += s_red[j * 32 + tid];
+        s_tot[tid] = s;
+    }
+    __syncthreads();
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(RB_THREADS, 2) reg_batch_kernel(const __grid_constant__ BatchParams P, double* __restrict__ T_out,
+                                                                  icp4r_result* __restrict__ res) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* s_tgt = reinterpret_cast<float4*>(smem_raw);
+    float4* s_src = s_tgt + P.max_m;
+    uint32_t* s_cs = reinterpret_cast<uint32_t*>(s_src + P.max_n);  // [RB_MAXC + 2]
+    __shared__ double s_red[RB_WARPS * 32];
+    __shared__ double s_tot[32];
+    __shared__ double s_T[16];
+    __shared__ float s_bb[RB_WARPS][6];
+    __shared__ PairGrid s_g;
+    __shared__ uint32_t s_wsum[RB_WARPS];
+    __shared__ int s_flags[4];  // done, converged, iterations, n_corr
+    __shared__ double s_misc[2];  // mse_prev, last_cost
+
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    constexpr int NV = (KIND == ICP4R_P2P_SVD) ? 17 : 29;
+
+    for (int pair = blockIdx.x; pair < P.n_pairs; pair += gridDim.x) {
+        const int so = P.soff[pair], n = P.soff[pair + 1] - so;
+        const int to = P.toff[pair], m = P.toff[pair + 1] - to;
+        const float4* __restrict__ gsrc = P.src + so;
+        const float4* __restrict__ gtgt = P.tgt + to;
+        __syncthreads();  // previous pair fully consumed
+
+        // ---- stage the source; bounding box of the target --------------------------------------------
+        for (int i = tid; i < n; i += RB_THREADS) s_src[i] = __ldg(gsrc + i);
+        float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (int j = tid; j < m; j += RB_THREADS) {
+            const float4 p = __ldg(gtgt + j);
+            if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+                mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x);
+                mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
+                mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                mn[a] = fminf(mn[a], __shfl_xor_sync(FULL, mn[a], o));
+                mx[a] = fmaxf(mx[a], __shfl_xor_sync(FULL, mx[a], o));
+            }
+        if (lane == 0) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                s_bb[w][a] = mn[a];
+                s_bb[w][3 + a] = mx[a];
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            float lo[3], hi[3];
+            for (int a = 0; a < 3; ++a) {
+                lo[a] = s_bb[0][a];
+                hi[a] = s_bb[0][3 + a];
+                for (int j = 1; j < RB_WARPS; ++j) {
+                    lo[a] = fminf(lo[a], s_bb[j][a]);
+                    hi[a] = fmaxf(hi[a], s_bb[j][3 + a]);
+                }
+                if (!(lo[a] <= hi[a])) lo[a] = hi[a] = 0.f;  // empty / all non-finite
+            }
+            const float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
+            const float emax = fmaxf(ex, fmaxf(ey, ez));
+            const float fl = fmaxf(emax * 1e-3f, 1e-6f);
+            const float vol = fmaxf(ex, fl) * fmaxf(ey, fl) * fmaxf(ez, fl);
+            float cell = cbrtf(vol / fmaxf(1.0f, (float)m * 0.5f));  // ~2 points per cell by volume
+            cell = fmaxf(cell, fmaxf(emax * 1e-4f, 1e-6f));
+            int nx, ny, nz;
+            for (;;) {
+                const float fx = floorf(ex / cell) + 1.f, fy = floorf(ey / cell) + 1.f, fz = floorf(ez / cell) + 1.f;
+                if (fx * fy * fz <= (float)RB_MAXC) {
+                    nx = (int)fx;
+                    ny = (int)fy;
+                    nz = (int)fz;
+                    break;
+                }
+                cell *= 1.1f;
+            }
+            float L = 1.0f;
+            for (int a = 0; a < 3; ++a) L = fmaxf(L, fmaxf(fabsf(lo[a]), fabsf(hi[a])));
+            s_g.ox = lo[0];
+            s_g.oy = lo[1];
+            s_g.oz = lo[2];
+            s_g.cell = cell;
+            s_g.inv_cell = 1.0f / cell;
+            s_g.margin = L * 9.5367431640625e-7f;
+            s_g.nx = nx;
+            s_g.ny = ny;
+            s_g.nz = nz;
+            s_g.ncells = nx * ny * nz;
+            s_flags[0] = 0;
+            s_flags[1] = 0;
+            s_flags[2] = 0;
+            s_flags[3] = 0;
+            s_misc[0] = INFINITY;
+            s_misc[1] = 0.0;
+        }
+        if (tid < 16) s_T[tid] = P.T0[tid];
+        for (int c0 = tid; c0 < RB_MAXC + 2; c0 += RB_THREADS) s_cs[c0] = 0;
+        __syncthreads();
+        const PairGrid g = s_g;
+
+        // ---- counting sort of the target into cell order (shared memory) ----------------------------
+        for (int j = tid; j < m; j += RB_THREADS) {
+            const float4 p = __ldg(gtgt + j);
+            if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+                const int c0 = (cell_of_s(p.z, g.oz, g.inv_cell, g.nz) * g.ny + cell_of_s(p.y, g.oy, g.inv_cell, g.ny)) * g.nx +
+                               cell_of_s(p.x, g.ox, g.inv_cell, g.nx);
+                atomicAdd(&s_cs[c0 + 1], 1u);
+            }
+        }
+        __syncthreads();
+        {   // s_cs[c+1] <- exclusive prefix of the counts (becomes the running cursor of cell c)
+            constexpr int PER = (RB_MAXC + RB_THREADS - 1) / RB_THREADS;
+            uint32_t v[PER], sum = 0;
+#pragma unroll
+            for (int t = 0; t < PER; ++t) {
+                const int c0 = tid * PER + t;
+                v[t] = c0 < RB_MAXC ? s_cs[c0 + 1] : 0u;
+                sum += v[t];
+            }
+            uint32_t x = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(FULL, x, o);
+                if (lane >= o) x += y;
+            }
+            if (lane == 31) s_wsum[w] = x;
+            __syncthreads();
+            uint32_t base = x - sum;
+            for (int j = 0; j < w; ++j) base += s_wsum[j];
+#pragma unroll
+            for (int t = 0; t < PER; ++t) {
+                const int c0 = tid * PER + t;
+                if (c0 < RB_MAXC) s_cs[c0 + 1] = base;
+                base += v[t];
+            }
+        }
+        __syncthreads();
+        for (int j = tid; j < m; j += RB_THREADS) {
+            const float4 p = __ldg(gtgt + j);
+            if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+                const int c0 = (cell_of_s(p.z, g.oz, g.inv_cell, g.nz) * g.ny + cell_of_s(p.y, g.oy, g.inv_cell, g.ny)) * g.nx +
+                               cell_of_s(p.x, g.ox, g.inv_cell, g.nx);
+                const uint32_t pos = atomicAdd(&s_cs[c0 + 1], 1u);
+                s_tgt[pos] = make_float4(p.x, p.y, p.z, __int_as_float(j));
+            }
+        }
+        __syncthreads();  // now s_cs[c] = start of cell c, s_cs[c+1] = its end
+
+        // ---- iterations ---------------------------------------------------------------------------------
+        for (int it = 0; it < P.max_iterations; ++it) {
+            double T[12];
+#pragma unroll
+            for (int i = 0; i < 12; ++i) T[i] = s_T[i];
+            double acc[NV];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) acc[v] = 0.0;
+            for (int i = tid; i < n; i += RB_THREADS) {
+                const float4 p = s_src[i];
+                double pw[3];
+                xform_point(T, p.x, p.y, p.z, pw);
+                int pos;
+                const uint64_t key = thread_grid_nn(g, s_tgt, s_cs, (float)pw[0], (float)pw[1], (float)pw[2], P.gate_f, P.gate_r, pos);
+                if (key != KEY_EMPTY) {
+                    const float4 c = s_tgt[pos];
+                    if (KIND == ICP4R_P2P_SVD) contrib_p2p_svd(acc, pw, c.x, c.y, c.z, key_d2(key));
+                    else contrib_p2p_gn(acc, pw, c.x, c.y, c.z);
+                }
+            }
+            block_reduce<NV>(acc, s_red, s_tot, tid);
+            if (tid == 0) {
+                double Tc[16], D[16];
+                for (int i = 0; i < 16; ++i) Tc[i] = s_T[i];
+                const bool last = (it == P.max_iterations - 1);
+                if (KIND == ICP4R_P2P_SVD) {
+                    const double cnt = s_tot[0];
+                    s_flags[3] = (int)cnt;
+                    if (cnt < 3.0) {
+                        s_flags[0] = 1;
+                        s_flags[1] = 0;
+                        s_flags[2] = it;
+                    } else {
+                        double pm[3], qm[3], H[9], R[9];
+                        for (int i = 0; i < 3; ++i) {
+                            pm[i] = s_tot[1 + i] / cnt;
+                            qm[i] = s_tot[4 + i] / cnt;
+                        }
+                        for (int i = 0; i < 3; ++i)
+                            for (int j = 0; j < 3; ++j) H[3 * i + j] = s_tot[7 + 3 * i + j] / cnt - pm[i] * qm[j];
+                        svd3_rotation(H, R);
+                        for (int i = 0; i < 3; ++i) {
+                            D[4 * i + 0] = R[3 * i + 0];
+                            D[4 * i + 1] = R[3 * i + 1];
+                            D[4 * i + 2] = R[3 * i + 2];
+                            D[4 * i + 3] = qm[i] - ((R[3 * i] * pm[0] + R[3 * i + 1] * pm[1]) + R[3 * i + 2] * pm[2]);
+                        }
+                        D[12] = D[13] = D[14] = 0;
+                        D[15] = 1;
+                        const double mse = s_tot[16] / cnt;
+                        s_misc[1] = mse;
+                        mat4_mul(D, Tc, Tc);
+                        for (int i = 0; i < 16; ++i) s_T[i] = Tc[i];
+                        if (P.early_exit) {
+                            if (fabs(mse - s_misc[0]) < P.mse_abs_eps) {
+                                s_flags[0] = 1;
+                                s_flags[1] = 1;
+                                s_flags[2] = it + 1;
+                            }
+                            s_misc[0] = mse;
+                        }
+                    }
+                } else {
+                    const double cnt = s_tot[28];
+                    s_flags[3] = (int)cnt;
+                    double xi[6];
+                    if (cnt < 6.0 || chol6_solve(s_tot, s_tot + 21, xi)) {
+                        s_flags[0] = 1;
+                        s_flags[1] = 0;
+                        s_flags[2] = it;
+                    } else {
+                        se3_exp(xi, D);
+                        s_misc[1] = s_tot[27];
+                        mat4_mul(D, Tc, Tc);
+                        for (int i = 0; i < 16; ++i) s_T[i] = Tc[i];
+                        if (P.early_exit) {
+                            const double wn = sqrt(xi[0] * xi[0] + xi[1] * xi[1] + xi[2] * xi[2]);
+                            const double vn = sqrt(xi[3] * xi[3] + xi[4] * xi[4] + xi[5] * xi[5]);
+                            if (wn < P.rot_eps && vn < P.trans_eps) {
+                                s_flags[0] = 1;
+                                s_flags[1] = 1;
+                                s_flags[2] = it + 1;
+                            }
+                        }
+                    }
+                }
+                if (!s_flags[0] && last) {
+                    s_flags[0] = 1;
+                    s_flags[1] = 1;
+                    s_flags[2] = P.max_iterations;
+                }
+            }
+            __syncthreads();
+            if (s_flags[0]) break;
+        }
+
+        // ---- fitness pass: mean squared 1-NN distance under the final pose --------------------------
+        {
+            double T[12];
+#pragma unroll
+            for (int i = 0; i < 12; ++i) T[i] = s_T[i];
+            double fa[2] = {0.0, 0.0};
+            for (int i = tid; i < n; i += RB_THREADS) {
+                const float4 p = s_src[i];
+                double pw[3];
+                xform_point(T, p.x, p.y, p.z, pw);
+                int pos;
+                const uint64_t key = thread_grid_nn(g, s_tgt, s_cs, (float)pw[0], (float)pw[1], (float)pw[2], P.gate_f, P.gate_r, pos);
+                if (key != KEY_EMPTY) {
+                    fa[0] += 1.0;
+                    fa[1] += (double)key_d2(key);
+                }
+            }
+            block_reduce<2>(fa, s_red, s_tot, tid);
+        }
+        if (tid < 16) T_out[(size_t)pair * 16 + tid] = s_T[tid];
+        if (tid == 0) {
+            icp4r_result r;
+            r.converged = (P.max_iterations == 0) ? 1 : s_flags[1];
+            r.iterations = s_flags[2];
+            r.n_corr = s_flags[3];
+            r.n_fitness = (int)s_tot[0];
+            r.fitness = s_tot[0] > 0.0 ? s_tot[1] / s_tot[0] : INFINITY;
+            r.last_cost = s_misc[1];
+            res[pair] = r;
+        }
+    }
+}
+
+int register_batch(Ctx* c, const float4* d_src, const int32_t* d_soff, const float4* d_tgt, const int32_t* d_toff, int n_pairs,
+                   int max_n, int max_m, const icp4r_opts* o, double* d_T, icp4r_result* d_res) {
+    if (n_pairs <= 0) return ICP4R_OK;
+    if (o->residual != ICP4R_P2P_SVD && o->residual != ICP4R_P2P_GN)
+        return fail(c, ICP4R_ERR_UNSUPPORTED, "batched registration supports P2P_SVD and P2P_GN (got %d)", o->residual);
+    const size_t smem = (size_t)(std::max(max_m, 1) + std::max(max_n, 1)) * sizeof(float4) + (RB_MAXC + 2) * sizeof(uint32_t);
+    if (smem > 200 * 1024)
+        return fail(c, ICP4R_ERR_UNSUPPORTED, "pair too large for the shared-memory resident kernel (%zu B); use icp4r_register", smem);
+    BatchParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.src = d_src;
+    P.soff = d_soff;
+    P.tgt = d_tgt;
+    P.toff = d_toff;
+    P.n_pairs = n_pairs;
+    P.max_n = std::max(max_n, 1);
+    P.max_m = std::max(max_m, 1);
+    P.max_iterations = o->max_iterations;
+    P.early_exit = o->early_exit;
+    gate_params(o->max_corr_dist, &P.gate_f, &P.gate_r);
+    P.rot_eps = o->rot_eps;
+    P.trans_eps = o->trans_eps;
+    P.mse_abs_eps = o->mse_abs_eps;
+    std::memcpy(P.T0, o->T0, sizeof(P.T0));
+
+    auto kern = (o->residual == ICP4R_P2P_SVD) ? reg_batch_kernel<ICP4R_P2P_SVD> : reg_batch_kernel<ICP4R_P2P_GN>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RB_THREADS, smem));
+    per_sm = std::max(per_sm, 1);
+    const int blocks = std::min(n_pairs, c->sm_count * per_sm);
+    kern<<<blocks, RB_THREADS, smem, c->stream>>>(P, d_T, d_res);
+    c->launches += 1;
+    CK(cudaGetLastError());
+    return ICP4R_OK;
+}
+
+}  // namespace icp4r

@@ -1,0 +1,509 @@
+// register_map.cu — scan-to-map registration: the per-iteration hot path
+//   transform -> exact kNN over the voxel grid -> distance gate -> residual + Jacobian -> fp64 accumulators
+//   -> SE(3) solve -> pose update
+// as ONE kernel per iteration (the last block to finish reduces the block partials in a fixed order and does
+// the 3x3 Jacobi-SVD / 6x6 Cholesky update), the whole loop captured in a CUDA graph.
+//
+// Replaces pcl::IterativeClosestPoint::align (/root/reference/src/iterative_closest_point.cpp:510-514) and the
+// FastGICP align call (/root/reference/src/radar_odometry.cpp:399-405) on top of the map that replaces the
+// ikd-Tree (radar_odometry.cpp:390); residuals are those of /root/reference/include/radarFactor.hpp.
+#include <cmath>
+#include <cstddef>
+#include <cstdlib>
+#include <cstring>
+
+#include "ctx.h"
+#include "device_math.cuh"
+#include "grid_knn.cuh"
+
+namespace icp4r {
+
+constexpr int RM_WARPS = 8;
+constexpr int RM_THREADS = RM_WARPS * 32;
+
+enum { MODE_ITER = 0, MODE_ITER_NOSOLVE = 1, MODE_FITNESS = 2, MODE_FITNESS_NOFINAL = 3 };
+
+struct ResultBlock {  // what travels back to the host in one copy
+    double T[16];
+    icp4r_result res;
+};
+
+// pose update from the reduced accumulators; run by one thread.
+__device__ void solve_and_update(int residual, const RegParams& P, RegState* st, const double* tot, const double* Tin, int iter) {
+    double T[16];
+    for (int i = 0; i < 16; ++i) T[i] = Tin[i];
+    double D[16];
+    const bool last = (iter == P.max_iterations - 1);
+    if (residual == ICP4R_P2P_SVD) {
+        const double cnt = tot[0];
+        st->n_corr = (int)cnt;
+        if (cnt < 3.0) {  // PCL: fewer than 3 correspondences -> not converged
+            st->done = 1;
+            st->converged = 0;
+            st->iterations = iter;
+            return;
+        }
+        double pm[3], qm[3], H[9], R[9];
+        for (int i = 0; i < 3; ++i) {
+            pm[i] = tot[1 + i] / cnt;
+            qm[i] = tot[4 + i] / cnt;
+        }
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) H[3 * i + j] = tot[7 + 3 * i + j] / cnt - pm[i] * qm[j];
+        svd3_rotation(H, R);
+        for (int i = 0; i < 3; ++i) {
+            D[4 * i + 0] = R[3 * i + 0];
+            D[4 * i + 1] = R[3 * i + 1];
+            D[4 * i + 2] = R[3 * i + 2];
+            D[4 * i + 3] = qm[i] - ((R[3 * i] * pm[0] + R[3 * i + 1] * pm[1]) + R[3 * i + 2] * pm[2]);
+        }
+        D[12] = D[13] = D[14] = 0;
+        D[15] = 1;
+        const double mse = tot[16] / cnt;
+        st->last_cost = mse;
+        mat4_mul(D, T, T);
+        for (int i = 0; i < 16; ++i) st->T[i] = T[i];
+        if (P.early_exit) {
+            if (fabs(mse - st->mse_prev) < P.mse_abs_eps) {
+                st->done = 1;
+                st->converged = 1;
+                st->iterations = iter + 1;
+                return;
+            }
+            st->mse_prev = mse;
+        }
+    } else {
+        const double cnt = tot[28];
+        st->n_corr = (int)cnt;
+        double xi[6];
+        if (cnt < 6.0 || chol6_solve(tot, tot + 21, xi)) {
+            st->done = 1;
+            st->converged = 0;
+            st->iterations = iter;
+            return;
+        }
+        se3_exp(xi, D);
+        st->last_cost = tot[27];
+        mat4_mul(D, T, T);
+        for (int i = 0; i < 16; ++i) st->T[i] = T[i];
+        if (P.early_exit) {
+            const double wn = sqrt(xi[0] * xi[0] + xi[1] * xi[1] + xi[2] * xi[2]);
+            const double vn = sqrt(xi[3] * xi[3] + xi[4] * xi[4] + xi[5] * xi[5]);
+            if (wn < P.rot_eps && vn < P.trans_eps) {
+                st->done = 1;
+                st->converged = 1;
+                st->iterations = iter + 1;
+                return;
+            }
+        }
+    }
+    if (last) {
+        st->done = 1;
+        st->converged = 1;  // PCL: reaching max_iterations counts as converged
+        st->iterations = P.max_iterations;
+    }
+}
+
+__device__ void write_result(const RegState* st, ResultBlock* out) {
+    for (int i = 0; i < 16; ++i) out->T[i] = st->T[i];
+    out->res.converged = st->converged;
+    out->res.iterations = st->iterations;
+    out->res.n_corr = st->n_corr;
+    out->res.n_fitness = st->fit_cnt;
+    out->res.fitness = st->fit_cnt > 0 ? st->fit_sum / (double)st->fit_cnt : INFINITY;
+    out->res.last_cost = st->last_cost;
+}
+
+// One iteration (or the fitness pass). Block = 8 warps; each warp finds the neighbours of one source point at
+// a time and parks them in shared memory; then 8 lanes of warp 0 turn the 8 parked correspondences into
+// residual/Jacobian contributions (fp64) held in registers across the block's whole share of points.
+template <int KIND, int K, int MODE>
+__global__ void __launch_bounds__(RM_THREADS)
+    reg_iter_kernel(GridDesc g, const float4* __restrict__ pts, const RegParams* __restrict__ prm, RegState* __restrict__ st,
+                    double* __restrict__ partials, ResultBlock* __restrict__ out, int iter) {
+    constexpr bool FIT = (MODE == MODE_FITNESS || MODE == MODE_FITNESS_NOFINAL);
+    constexpr int KK = FIT ? 1 : K;
+    if (!FIT && st->done) return;
+
+    __shared__ int nb_idx[RM_WARPS][K];
+    __shared__ float nb_d2[RM_WARPS];
+    __shared__ int nb_src[RM_WARPS];
+    __shared__ double sacc[ICP4R_ACC_LEN * RM_WARPS];  // [value][lane 0..7]: running sums of the 8 contribution lanes
+    __shared__ double red[RM_WARPS][ICP4R_ACC_LEN];
+    __shared__ double tot[ICP4R_ACC_LEN];
+    __shared__ double Ts[16];
+    __shared__ bool is_last;
+
+    const RegParams P = *prm;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid < 16) Ts[tid] = st->T[tid];
+    __syncthreads();
+    double T[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) T[i] = Ts[i];
+
+    sacc[tid] = 0.0;  // RM_THREADS == ICP4R_ACC_LEN * RM_WARPS
+    static_assert(RM_THREADS == ICP4R_ACC_LEN * RM_WARPS, "sacc init");
+    __syncthreads();
+
+    const int n = P.n;
+    const int kq = FIT ? 1 : P.k;
+    const int groups = (n + RM_WARPS - 1) / RM_WARPS;
+    for (int grp = blockIdx.x; grp < groups; grp += gridDim.x) {
+        const int i = grp * RM_WARPS + w;
+        bool active = i < n;
+        double pw[3] = {0, 0, 0};
+        if (active) {
+            const float4 p = __ldg(P.src + i);
+            xform_point(T, p.x, p.y, p.z, pw);
+            const float qx = (float)pw[0], qy = (float)pw[1], qz = (float)pw[2];
+            if (P.shard_axis >= 0) {  // sharded map: the rank whose slab holds the transformed point owns it
+                const float v = P.shard_axis == 0 ? qx : (P.shard_axis == 1 ? qy : qz);
+                active = (v >= P.slab_lo) && (v < P.slab_hi);
+            }
+            if (active) {
+                const uint64_t mine = warp_grid_knn<KK>(g, qx, qy, qz, P.gate_f, P.gate_r, lane);
+                const bool have = (lane < kq) && (mine != KEY_EMPTY);
+                if (lane < KK) nb_idx[w][lane] = have ? key_idx(mine) : -1;
+                if (lane == 0) nb_d2[w] = have ? key_d2(mine) : INFINITY;
+                if (!FIT && P.dump_idx && lane < kq) P.dump_idx[((size_t)iter * n + i) * kq + lane] = have ? key_idx(mine) : -1;
+            } else if (!FIT && P.dump_idx && lane < kq) {
+                P.dump_idx[((size_t)iter * n + i) * kq + lane] = -1;
+            }
+        }
+        if (lane == 0) nb_src[w] = active ? i : -1;
+        __syncthreads();
+        if (tid < RM_WARPS && nb_src[tid] >= 0) {
+            const int si = nb_src[tid];
+            const float4 p = __ldg(P.src + si);
+            double pq[3];
+            xform_point(T, p.x, p.y, p.z, pq);
+            // contribution of this correspondence in registers (short-lived), then into the lane's running sums
+            double acc[ICP4R_ACC_LEN];
+#pragma unroll
+            for (int v = 0; v < ICP4R_ACC_LEN; ++v) acc[v] = 0.0;
+            if (FIT || KIND == ICP4R_P2P_SVD) {
+                const int j = nb_idx[tid][0];
+                if (j >= 0) {
+                    const float4 cpt = __ldg(pts + j);
+                    contrib_p2p_svd(acc, pq, cpt.x, cpt.y, cpt.z, nb_d2[tid]);
+                }
+            } else if (KIND == ICP4R_P2P_GN) {
+                const int j = nb_idx[tid][0];
+                if (j >= 0) {
+                    const float4 cpt = __ldg(pts + j);
+                    contrib_p2p_gn(acc, pq, cpt.x, cpt.y, cpt.z);
+                }
+            } else if (KIND == ICP4R_P2PLANE_KNN) {
+                double Pn[K][3];
+                bool all = true;
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    if (j < kq) {
+                        const int id = nb_idx[tid][j];
+                        if (id < 0) {
+                            all = false;
+                            Pn[j][0] = Pn[j][1] = Pn[j][2] = 0.0;
+                        } else {
+                            const float4 cpt = __ldg(pts + id);
+                            Pn[j][0] = (double)cpt.x;
+                            Pn[j][1] = (double)cpt.y;
+                            Pn[j][2] = (double)cpt.z;
+                        }
+                    }
+                }
+                if (all && kq >= 3) contrib_p2plane<K>(acc, pq, Pn, kq, P.plane_thresh);
+            } else if (KIND == ICP4R_P2LINE) {
+                const int ia = nb_idx[tid][0], ib = (K > 1) ? nb_idx[tid][K > 1 ? 1 : 0] : -1;
+                if (ia >= 0 && ib >= 0) {
+                    const float4 fa = __ldg(pts + ia), fb = __ldg(pts + ib);
+                    const double a[3] = {(double)fa.x, (double)fa.y, (double)fa.z};
+                    const double b[3] = {(double)fb.x, (double)fb.y, (double)fb.z};
+                    contrib_p2line(acc, pq, a, b);
+                }
+            }
+            constexpr int NV = (FIT || KIND == ICP4R_P2P_SVD) ? 17 : 29;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) sacc[v * RM_WARPS + tid] += acc[v];
+        }
+        __syncthreads();
+    }
+
+    // block partial: only lanes 0..7 of warp 0 hold non-zero accumulators; fixed-order shuffle tree
+    if (tid < ICP4R_ACC_LEN) {
+        double x = 0.0;
+#pragma unroll
+        for (int j = 0; j < RM_WARPS; ++j) x += sacc[tid * RM_WARPS + j];
+        partials[(size_t)blockIdx.x * ICP4R_ACC_LEN + tid] = x;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        unsigned* tk = FIT ? &st->ticket_fit : &st->ticket;
+        const unsigned t = atomicAdd(tk, 1u);
+        is_last = (t == gridDim.x - 1);
+        if (is_last) *tk = 0;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+
+    // last block: reduce the block partials in a fixed order (deterministic for a given grid size)
+    {
+        const int v = tid & 31, grp8 = tid >> 5;
+        double s = 0.0;
+        for (int b = grp8; b < (int)gridDim.x; b += RM_WARPS) s += __ldcg(partials + (size_t)b * ICP4R_ACC_LEN + v);
+        red[grp8][v] = s;
+    }
+    __syncthreads();
+    if (tid < ICP4R_ACC_LEN) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < RM_WARPS; ++j) s += red[j][tid];
+        tot[tid] = s;
+    }
+    __syncthreads();
+    if (FIT) {
+        if (tid == 0) {
+            if (MODE == MODE_FITNESS) {
+                st->fit_sum = tot[16];
+                st->fit_cnt = (int)tot[0];
+                write_result(st, out);
+            } else {
+                st->acc[0] = tot[0];
+                st->acc[1] = tot[16];
+            }
+        }
+        return;
+    }
+    if (tid < ICP4R_ACC_LEN) {
+        if (P.dump_acc) P.dump_acc[(size_t)iter * ICP4R_ACC_LEN + tid] = tot[tid];
+        if (MODE == MODE_ITER_NOSOLVE) st->acc[tid] = tot[tid];
+    }
+    if (tid < 16 && P.dump_pose) P.dump_pose[(size_t)iter * 16 + tid] = Ts[tid];
+    if (MODE == MODE_ITER && tid == 0) solve_and_update(KIND, P, st, tot, Ts, iter);
+}
+
+// sharded path: solve after the cross-rank sum of st->acc
+__global__ void solve_kernel(int residual, const RegParams* __restrict__ prm, RegState* __restrict__ st, int iter) {
+    if (st->done) return;
+    if (threadIdx.x == 0) {
+        const RegParams P = *prm;
+        double Tin[16], tot[ICP4R_ACC_LEN];
+        for (int i = 0; i < 16; ++i) Tin[i] = st->T[i];
+        for (int i = 0; i < ICP4R_ACC_LEN; ++i) tot[i] = st->acc[i];
+        solve_and_update(residual, P, st, tot, Tin, iter);
+    }
+}
+__global__ void fitness_final_kernel(RegState* __restrict__ st, ResultBlock* __restrict__ out) {
+    if (threadIdx.x == 0) {
+        st->fit_cnt = (int)st->acc[0];
+        st->fit_sum = st->acc[1];
+        write_result(st, out);
+    }
+}
+
+__global__ void init_state_kernel(RegState* st, const double* T0) {
+    const int t = threadIdx.x;
+    if (t < 16) st->T[t] = T0[t];
+    if (t < ICP4R_ACC_LEN) st->acc[t] = 0.0;
+    if (t == 0) {
+        st->mse_prev = INFINITY;
+        st->last_cost = 0.0;
+        st->fit_sum = 0.0;
+        st->fit_cnt = 0;
+        st->done = 0;
+        st->converged = 0;
+        st->iterations = 0;
+        st->n_corr = 0;
+        st->ticket = 0;
+        st->ticket_fit = 0;
+    }
+}
+
+template <int KIND, int K>
+static void launch_iter(Ctx* c, int mode, int blocks, const GridDesc& g, const float4* pts, const RegParams* prm, RegState* st,
+                        double* partials, ResultBlock* out, int iter) {
+    switch (mode) {
+        case MODE_ITER:
+            reg_iter_kernel<KIND, K, MODE_ITER><<<blocks, RM_THREADS, 0, c->stream>>>(g, pts, prm, st, partials, out, iter);
+            break;
+        case MODE_ITER_NOSOLVE:
+            reg_iter_kernel<KIND, K, MODE_ITER_NOSOLVE><<<blocks, RM_THREADS, 0, c->stream>>>(g, pts, prm, st, partials, out, iter);
+            break;
+        case MODE_FITNESS:
+            reg_iter_kernel<KIND, K, MODE_FITNESS><<<blocks, RM_THREADS, 0, c->stream>>>(g, pts, prm, st, partials, out, iter);
+            break;
+        default:
+            reg_iter_kernel<KIND, K, MODE_FITNESS_NOFINAL><<<blocks, RM_THREADS, 0, c->stream>>>(g, pts, prm, st, partials, out, iter);
+            break;
+    }
+    c->launches += 1;
+}
+
+static void dispatch_iter(Ctx* c, int kind, int K, int mode, int blocks, const GridDesc& g, const float4* pts,
+                          const RegParams* prm, RegState* st, double* partials, ResultBlock* out, int iter) {
+    switch (kind) {
+        case ICP4R_P2P_SVD:
+            launch_iter<ICP4R_P2P_SVD, 1>(c, mode, blocks, g, pts, prm, st, partials, out, iter);
+            break;
+        case ICP4R_P2P_GN:
+            launch_iter<ICP4R_P2P_GN, 1>(c, mode, blocks, g, pts, prm, st, partials, out, iter);
+            break;
+        case ICP4R_P2LINE:
+            launch_iter<ICP4R_P2LINE, 2>(c, mode, blocks, g, pts, prm, st, partials, out, iter);
+            break;
+        default:
+            if (K <= 5) launch_iter<ICP4R_P2PLANE_KNN, 5>(c, mode, blocks, g, pts, prm, st, partials, out, iter);
+            else if (K <= 8) launch_iter<ICP4R_P2PLANE_KNN, 8>(c, mode, blocks, g, pts, prm, st, partials, out, iter);
+            else launch_iter<ICP4R_P2PLANE_KNN, 16>(c, mode, blocks, g, pts, prm, st, partials, out, iter);
+            break;
+    }
+}
+
+static int knn_k_for(const icp4r_opts* o) {
+    switch (o->residual) {
+        case ICP4R_P2P_SVD:
+        case ICP4R_P2P_GN:
+            return 1;
+        case ICP4R_P2LINE:
+            return 2;
+        default:
+            return o->k > 0 ? o->k : 5;
+    }
+}
+
+int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4r_opts* o, int shard_axis, float slab_lo,
+                         float slab_hi, double* T_out_host, icp4r_result* res_host, const icp4r_dump* dump) {
+    if (!mp.built) return fail(c, ICP4R_ERR_STATE, "registration target has no built map");
+    if (o->residual == ICP4R_GICP) return fail(c, ICP4R_ERR_UNSUPPORTED, "ICP4R_GICP is not implemented yet");
+    if (o->residual < 0 || o->residual > ICP4R_GICP) return fail(c, ICP4R_ERR_INVALID, "bad residual kind %d", o->residual);
+    const int k = knn_k_for(o);
+    if (k > ICP4R_MAX_K) return fail(c, ICP4R_ERR_INVALID, "k=%d exceeds ICP4R_MAX_K", k);
+    if (o->residual == ICP4R_P2PLANE_KNN && k < 3) return fail(c, ICP4R_ERR_INVALID, "P2PLANE_KNN needs k >= 3");
+    if (o->max_iterations < 0 || n < 0) return fail(c, ICP4R_ERR_INVALID, "negative size");
+    const bool sharded = shard_axis >= 0;
+    if (sharded && !(o->max_corr_dist > 0.0 && std::isfinite(o->max_corr_dist)))
+        return fail(c, ICP4R_ERR_INVALID, "sharded registration needs a finite max_corr_dist (halo guarantee)");
+
+    // per-call parameters -> pinned staging -> device
+    CKS(reserve(c, c->d_params, sizeof(RegParams)));
+    CKS(reserve(c, c->d_state, sizeof(RegState)));
+    CKS(reserve(c, c->d_T, 16 * sizeof(double)));
+    CKS(reserve(c, c->d_res, sizeof(ResultBlock)));
+    const int groups = std::max(1, (n + RM_WARPS - 1) / RM_WARPS);
+    // block count: one group of 8 points per block up to 4 blocks per SM; rounded so graphs get reused
+    int blocks = std::min(groups, c->sm_count * 4);
+    // sized once for the largest grid so the pointer baked into captured graphs never moves
+    CKS(reserve(c, c->d_partials, (size_t)c->sm_count * 4 * ICP4R_ACC_LEN * sizeof(double) + 1024));
+
+    struct Stage {
+        RegParams prm;
+        double T0[16];
+        ResultBlock out;
+    };
+    Stage* hs = static_cast<Stage*>(c->h_pinned);
+    RegParams& P = hs->prm;
+    std::memset(&P, 0, sizeof(P));
+    P.src = d_src;
+    P.n = n;
+    P.residual = o->residual;
+    P.k = k;
+    P.max_iterations = o->max_iterations;
+    P.early_exit = o->early_exit;
+    gate_params(o->max_corr_dist, &P.gate_f, &P.gate_r);
+    P.rot_eps = o->rot_eps;
+    P.trans_eps = o->trans_eps;
+    P.mse_abs_eps = o->mse_abs_eps;
+    P.plane_thresh = o->plane_thresh;
+    P.dump_pose = dump ? dump->pose : nullptr;
+    P.dump_acc = dump ? dump->acc : nullptr;
+    P.dump_idx = dump ? dump->idx : nullptr;
+    P.shard_axis = sharded ? shard_axis : -1;
+    P.slab_lo = slab_lo;
+    P.slab_hi = slab_hi;
+    std::memcpy(hs->T0, o->T0, sizeof(hs->T0));
+
+    RegParams* d_prm = c->d_params.as<RegParams>();
+    RegState* d_st = c->d_state.as<RegState>();
+    ResultBlock* d_out = c->d_res.as<ResultBlock>();
+    double* d_part = c->d_partials.as<double>();
+    CK(cudaMemcpyAsync(d_prm, &hs->prm, sizeof(RegParams), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_T.p, hs->T0, sizeof(hs->T0), cudaMemcpyHostToDevice, c->stream));
+    init_state_kernel<<<1, 32, 0, c->stream>>>(d_st, c->d_T.as<double>());
+    c->launches += 1;
+
+    const GridDesc g = mp.grid;
+    const float4* pts = mp.pts.as<float4>();
+    const int iters = o->max_iterations;
+
+    if (!sharded) {
+        // The loop is a fixed sequence of launches whose arguments are all stable device pointers, so it is
+        // captured once per (kind, k, blocks, iterations, grid identity) and replayed as a CUDA graph.
+        const bool want_graph = c->use_graph && n > 0;
+        GraphKey key{o->residual, k, blocks, iters, 0};
+        cudaGraphExec_t exec = nullptr;
+        if (want_graph) {
+            // graphs bake the GridDesc by value: drop them when the map geometry or buffers changed
+            static_assert(sizeof(GridDesc) % 4 == 0, "GridDesc packing");
+            if (c->graph_grid_owner != &mp.grid || std::memcmp(&c->graph_grid_copy, &g, sizeof(GridDesc)) != 0 ||
+                c->graph_pts != (const void*)pts) {
+                for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+                c->graphs.clear();
+                c->graph_grid_owner = &mp.grid;
+                c->graph_grid_copy = g;
+                c->graph_pts = pts;
+            }
+            auto it = c->graphs.find(key);
+            if (it != c->graphs.end()) exec = it->second;
+        }
+        if (want_graph && !exec) {
+            cudaGraph_t graph = nullptr;
+            // capture on the handle's own stream (a caller-supplied stream may be the legacy default stream,
+            // which cannot be captured); the instantiated graph is then launched on c->stream
+            cudaStream_t run_stream = c->stream;
+            c->stream = c->own_stream;
+            CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+            const int64_t before = c->launches;
+            for (int it = 0; it < iters; ++it) dispatch_iter(c, o->residual, k, MODE_ITER, blocks, g, pts, d_prm, d_st, d_part, d_out, it);
+            dispatch_iter(c, o->residual, k, MODE_FITNESS, blocks, g, pts, d_prm, d_st, d_part, d_out, 0);
+            c->launches = before;  // counted at replay time below
+            cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+            c->stream = run_stream;
+            CK(ce);
+            CK(cudaGraphInstantiate(&exec, graph, 0));
+            cudaGraphDestroy(graph);
+            c->graphs[key] = exec;
+        }
+        if (exec) {
+            CK(cudaGraphLaunch(exec, c->stream));
+            c->launches += iters + 1;
+        } else {
+            for (int it = 0; it < iters; ++it) dispatch_iter(c, o->residual, k, MODE_ITER, blocks, g, pts, d_prm, d_st, d_part, d_out, it);
+            dispatch_iter(c, o->residual, k, MODE_FITNESS, blocks, g, pts, d_prm, d_st, d_part, d_out, 0);
+        }
+    } else {
+        for (int it = 0; it < iters; ++it) {
+            dispatch_iter(c, o->residual, k, MODE_ITER_NOSOLVE, blocks, g, pts, d_prm, d_st, d_part, d_out, it);
+            CKS(shard_allreduce(c, reinterpret_cast<double*>(reinterpret_cast<char*>(d_st) + offsetof(RegState, acc)), ICP4R_ACC_LEN));
+            solve_kernel<<<1, 32, 0, c->stream>>>(o->residual, d_prm, d_st, it);
+            c->launches += 1;
+        }
+        dispatch_iter(c, o->residual, k, MODE_FITNESS_NOFINAL, blocks, g, pts, d_prm, d_st, d_part, d_out, 0);
+        CKS(shard_allreduce(c, reinterpret_cast<double*>(reinterpret_cast<char*>(d_st) + offsetof(RegState, acc)), 2));
+        fitness_final_kernel<<<1, 32, 0, c->stream>>>(d_st, d_out);
+        c->launches += 1;
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(&hs->out, d_out, sizeof(ResultBlock), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (iters == 0) {  // no iteration ran: PCL reports convergence by max_iterations
+        hs->out.res.converged = 1;
+        hs->out.res.iterations = 0;
+    }
+    if (T_out_host) std::memcpy(T_out_host, hs->out.T, sizeof(hs->out.T));
+    if (res_host) *res_host = hs->out.res;
+    return ICP4R_OK;
+}
+
+}  // namespace icp4r

@@ -1,0 +1,165 @@
+"""GPU parity: registration loops vs the CPU oracle, through the C ABI.
+
+Bars (north_star): correspondence indices bit-exact; per-iteration J^T J / J^T r relative error <= 1e-5;
+final pose within 1e-4 m / 1e-4 rad after the fixed iteration count.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+POSE_TOL_T = 1e-4   # metres
+POSE_TOL_R = 1e-4   # radians
+ACC_RTOL = 1e-5
+
+
+def pose_err(A, B):
+    D = A @ np.linalg.inv(B)
+    ang = np.arccos(np.clip((np.trace(D[:3, :3]) - 1) / 2, -1, 1))
+    return np.linalg.norm(D[:3, 3]), ang
+
+
+def check_dumps(O, kind, k, src, tgt, oo, bufs, iterations):
+    """For each iteration the library ran: recompute correspondences and accumulators on the CPU from the
+    pose the GPU reports for that iteration. Indices must match exactly, accumulators to 1e-5."""
+    dp, da, di = bufs
+    for it in range(iterations):
+        acc, idx, used = O.accumulate(src, tgt, oo, dp[it].reshape(4, 4))
+        assert (idx == di[it]).all(), f"iteration {it}: {np.count_nonzero((idx != di[it]).any(axis=1))} correspondences differ"
+        nv = 17 if kind == O.P2P_SVD else 29
+        a, b = da[it][:nv], acc[:nv]
+        if kind == O.P2P_SVD:
+            assert np.linalg.norm(a - b) <= ACC_RTOL * np.linalg.norm(b)
+        else:
+            assert np.linalg.norm(a[:21] - b[:21]) <= ACC_RTOL * np.linalg.norm(b[:21]), f"JtJ it {it}"
+            assert np.linalg.norm(a[21:27] - b[21:27]) <= ACC_RTOL * max(np.linalg.norm(b[21:27]), 1e-12), f"Jtr it {it}"
+            assert a[28] == b[28]
+
+
+KINDS = [("P2P_SVD", 1, 0.0), ("P2P_GN", 1, 0.0), ("P2PLANE_KNN", 5, 2.0), ("P2LINE", 2, 3.0), ("P2P_SVD", 1, 2.5)]
+
+
+@pytest.mark.parametrize("name,k,gate", KINDS)
+def test_register_pair_matches_oracle(pkg, O, handle, name, k, gate):
+    kind = getattr(pkg, name)
+    src, tgt, _ = pkg.synth.frame_pair(1001, 1024, 4000, extent=40.0)
+    iters = 12
+    o = pkg.default_opts(residual=kind, k=k, max_iterations=iters, max_corr_dist=gate)
+    oo = O.default_opts(residual=kind, k=k, max_iterations=iters, max_corr_dist=gate)
+    T, res, bufs = handle.register(src, tgt, o, dump=True)
+    To, ro, _ = O.register(src, tgt, oo)
+    assert res.iterations == ro.iterations == iters and res.converged == ro.converged
+    check_dumps(O, kind, k, src, tgt, oo, bufs, res.iterations)
+    et, er = pose_err(T, To)
+    assert et <= POSE_TOL_T and er <= POSE_TOL_R, (et, er)
+    assert res.n_corr == ro.n_corr and res.n_fitness == ro.n_fitness
+    assert abs(res.fitness - ro.fitness) <= 1e-6 * max(ro.fitness, 1e-12)
+
+
+def test_c1_config(pkg, O, handle):
+    """BASELINE config 1: 1,024-pt frame pair, point-to-point, 30 iterations, ungated"""
+    src, tgt, _ = pkg.synth.frame_pair(1001, 1024)
+    o = pkg.default_opts(residual=pkg.P2P_SVD, max_iterations=30)
+    oo = O.default_opts(residual=O.P2P_SVD, max_iterations=30)
+    T, res, bufs = handle.register(src, tgt, o, dump=True)
+    To, ro, _ = O.register(src, tgt, oo)
+    check_dumps(O, O.P2P_SVD, 1, src, tgt, oo, bufs, 30)
+    et, er = pose_err(T, To)
+    assert et <= POSE_TOL_T and er <= POSE_TOL_R, (et, er)
+    # the batched (shared-memory resident) kernel must agree with the map kernel and the oracle
+    off = np.array([0, 1024], np.int32)
+    Tb, rb = handle.register_batch(src, off, tgt, off, o)
+    et, er = pose_err(Tb[0], To)
+    assert et <= POSE_TOL_T and er <= POSE_TOL_R, (et, er)
+    assert rb["iterations"][0] == 30 and rb["converged"][0] == 1 and rb["n_corr"][0] == ro.n_corr
+    assert abs(rb["fitness"][0] - ro.fitness) <= 1e-6 * ro.fitness
+
+
+def test_c2_config(pkg, O, handle):
+    """BASELINE config 2: 4,096-pt scan vs 200k-pt map, k=5 point-to-plane, 20 iterations, gate 2 m.
+    Oracle kNN comes from the reference's own ikd-Tree when the compiled reference travelled with the repo."""
+    scan, mp, _ = pkg.synth.scan_to_map(1002, 4096, 200000)
+    o = pkg.default_opts(residual=pkg.P2PLANE_KNN, k=5, max_iterations=20, max_corr_dist=2.0)
+    oo = O.default_opts(residual=O.P2PLANE_KNN, k=5, max_iterations=20, max_corr_dist=2.0)
+    handle.map_build(mp)
+    T, res, bufs = handle.register_map(scan, o, dump=True)
+    searcher = None
+    if O.have_ref():
+        searcher = O.IkdTree(nthreads=8)
+        searcher.build(mp)
+    To, ro, _ = O.register(scan, mp, oo, searcher=searcher)
+    et, er = pose_err(T, To)
+    assert et <= POSE_TOL_T and er <= POSE_TOL_R, (et, er)
+    assert res.n_corr == ro.n_corr
+    dp, da, di = bufs
+    for it in (0, 1, 7, 19):
+        acc, idx, used = O.accumulate(scan, mp, oo, dp[it].reshape(4, 4), searcher=searcher)
+        assert (idx == di[it]).all()
+        assert np.linalg.norm(da[it][:21] - acc[:21]) <= ACC_RTOL * np.linalg.norm(acc[:21])
+        assert np.linalg.norm(da[it][21:27] - acc[21:27]) <= ACC_RTOL * np.linalg.norm(acc[21:27])
+
+
+def test_early_exit_and_degenerate(pkg, O, handle):
+    src, tgt, _ = pkg.synth.frame_pair(77, 800, 3000, extent=30.0)
+    for kind, k, gate in ((pkg.P2P_SVD, 1, 0.0), (pkg.P2PLANE_KNN, 5, 2.0)):
+        o = pkg.default_opts(residual=kind, k=k, max_iterations=60, early_exit=1, max_corr_dist=gate, mse_abs_eps=1e-9)
+        oo = O.default_opts(residual=kind, k=k, max_iterations=60, early_exit=1, max_corr_dist=gate, mse_abs_eps=1e-9)
+        T, res, _ = handle.register(src, tgt, o)
+        To, ro, _ = O.register(src, tgt, oo)
+        assert (res.converged, res.iterations) == (ro.converged, ro.iterations)
+        if kind == pkg.P2P_SVD:
+            assert res.iterations < 60
+        et, er = pose_err(T, To)
+        assert et <= POSE_TOL_T and er <= POSE_TOL_R
+    # no correspondences at all: gate far smaller than the offset -> not converged, pose = initial guess
+    far = src.copy()
+    far[:, :3] += 1000.0
+    o = pkg.default_opts(residual=pkg.P2P_SVD, max_iterations=5, max_corr_dist=0.5)
+    T, res, _ = handle.register(far, tgt, o)
+    assert res.converged == 0 and res.iterations == 0 and res.n_corr == 0 and np.allclose(T, np.eye(4))
+    assert np.isinf(res.fitness) and res.n_fitness == 0
+    # empty source / empty target
+    T, res, _ = handle.register(src[:0], tgt, pkg.default_opts(max_iterations=3))
+    assert res.converged == 0 and np.allclose(T, np.eye(4))
+    T, res, _ = handle.register(src, tgt[:0], pkg.default_opts(max_iterations=3))
+    assert res.converged == 0 and np.allclose(T, np.eye(4))
+    # initial guess is honoured
+    T0 = pkg.synth.se3(0.02, 0, 0, (0.3, -0.2, 0.0))
+    o = pkg.default_opts(residual=pkg.P2P_SVD, max_iterations=4, T0=T0)
+    oo = O.default_opts(residual=O.P2P_SVD, max_iterations=4, T0=T0)
+    T, res, _ = handle.register(src, tgt, o)
+    To, ro, _ = O.register(src, tgt, oo)
+    et, er = pose_err(T, To)
+    assert et <= POSE_TOL_T and er <= POSE_TOL_R
+
+
+def test_batch_ragged(pkg, O, handle):
+    """batched registration over pairs of different sizes, both residual kinds, gated and ungated"""
+    rng = np.random.default_rng(9)
+    sizes = [(300, 500), (1024, 1024), (17, 2048), (2048, 33), (700, 700), (1, 5), (64, 0), (0, 64)]
+    srcs, tgts = [], []
+    for i, (n, m) in enumerate(sizes):
+        s, t, _ = pkg.synth.frame_pair(100 + i, max(n, 1), max(m, 1), extent=float(rng.choice([20.0, 80.0])))
+        srcs.append(s[:n])
+        tgts.append(t[:m])
+    soff = np.concatenate([[0], np.cumsum([len(s) for s in srcs])]).astype(np.int32)
+    toff = np.concatenate([[0], np.cumsum([len(t) for t in tgts])]).astype(np.int32)
+    S, Tg = np.concatenate(srcs), np.concatenate(tgts)
+    for kind, gate in ((pkg.P2P_SVD, 0.0), (pkg.P2P_GN, 0.0), (pkg.P2P_SVD, 4.0)):
+        o = pkg.default_opts(residual=kind, max_iterations=8, max_corr_dist=gate)
+        oo = O.default_opts(residual=kind, max_iterations=8, max_corr_dist=gate)
+        Tb, rb = handle.register_batch(S, soff, Tg, toff, o)
+        for i in range(len(sizes)):
+            To, ro, _ = O.register(srcs[i], tgts[i], oo)
+            assert (rb["converged"][i], rb["iterations"][i], rb["n_corr"][i]) == (ro.converged, ro.iterations, ro.n_corr), i
+            et, er = pose_err(Tb[i], To)
+            assert et <= POSE_TOL_T and er <= POSE_TOL_R, (i, et, er)
+            if ro.n_fitness:
+                assert abs(rb["fitness"][i] - ro.fitness) <= 1e-6 * ro.fitness
+
+
+def test_transform_points(pkg, O, handle):
+    src, _, Tgt = pkg.synth.frame_pair(5, 999)
+    got = handle.transform_points(Tgt, src)
+    want, _ = O.transform(Tgt, src)
+    assert (got.view(np.int32) == want.view(np.int32)).all()
