@@ -1,0 +1,56 @@
+// common.hpp — shared pieces of the header-only adapters over include/icp4r.h.
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+#include <utility>
+#include <vector>
+
+#include "icp4r.h"
+
+namespace icp4r {
+
+// intensity is carried through the map when the point type has one (pcl::PointXYZI), else 0
+template <typename P, typename = void>
+struct has_intensity : std::false_type {};
+template <typename P>
+struct has_intensity<P, decltype(void(std::declval<P>().intensity))> : std::true_type {};
+
+template <typename P>
+inline float intensity_of(const P& p, std::true_type) { return p.intensity; }
+template <typename P>
+inline float intensity_of(const P&, std::false_type) { return 0.f; }
+
+template <typename It>
+inline std::vector<float> pack_xyzw(It first, It last) {
+    std::vector<float> out;
+    out.reserve(4 * static_cast<std::size_t>(last - first));
+    for (; first != last; ++first) {
+        using P = typename std::decay<decltype(*first)>::type;
+        out.push_back(first->x);
+        out.push_back(first->y);
+        out.push_back(first->z);
+        out.push_back(intensity_of(*first, has_intensity<P>()));
+    }
+    return out;
+}
+
+// One process-wide handle per device for objects that the reference constructs per frame on the stack
+// (pcl::IterativeClosestPoint at iterative_closest_point.cpp:510, FastGICP at radar_odometry.cpp:399):
+// creating a CUDA stream and buffers per frame would be wasted work.
+inline icp4r_handle shared_handle(int device = 0) {
+    static icp4r_handle h[16] = {nullptr};
+    if (device < 0 || device >= 16) throw std::runtime_error("icp4r: bad device");
+    if (!h[device]) {
+        if (icp4r_create(device, &h[device]) != ICP4R_OK)
+            throw std::runtime_error(std::string("icp4r_create failed: ") + icp4r_last_error(nullptr));
+    }
+    return h[device];
+}
+
+inline void check(icp4r_handle h, int rc, const char* what) {
+    if (rc != ICP4R_OK) throw std::runtime_error(std::string(what) + ": " + icp4r_last_error(h));
+}
+
+}  // namespace icp4r

@@ -1,0 +1,139 @@
+// kd_tree.hpp — drop-in for the reference's KD_TREE<PointType> call shape on top of libicp4r_cuda.
+//
+// Mirrors the public interface of /root/reference/third_party/ikd-Tree/ikd_Tree.h:227-251 as used at
+// /root/reference/src/radar_odometry.cpp:92 (ctor), :347 (Build), :348 (set_downsample_param), :390 (Add_Points),
+// :396 (Sector_Search): same names, argument meaning, output-vector conventions (the callee clears them,
+// ikd_Tree.cpp:371,390-391) and return values.  The k-d tree itself is gone: points live in a device voxel
+// grid; there is no rebuild thread, so delete_param / balance_param are accepted and ignored.
+//
+// Differences a caller can observe:
+//   * exact ties in distance go to the lowest insertion index (the reference: traversal order);
+//   * Nearest_Search is also offered for a whole batch of queries (one launch instead of N calls).
+#pragma once
+#include <cmath>
+#include <memory>
+#include <vector>
+
+#include <pcl/point_types.h>
+
+#include "common.hpp"
+
+struct BoxPointType {  // same layout as ikd_Tree.h:32-35
+    float vertex_min[3];
+    float vertex_max[3];
+};
+
+namespace icp4r {
+
+template <typename PointType>
+class KD_TREE {
+   public:
+    using PointVector = std::vector<PointType, Eigen::aligned_allocator<PointType>>;
+    using Ptr = std::shared_ptr<KD_TREE<PointType>>;
+
+    explicit KD_TREE(float delete_param = 0.5f, float balance_param = 0.6f, float box_length = 0.2f, int device = 0)
+        : downsample_size_(box_length) {
+        (void)delete_param;
+        (void)balance_param;
+        check(nullptr, icp4r_create(device, &h_), "icp4r_create");
+    }
+    ~KD_TREE() {
+        if (h_) icp4r_destroy(h_);
+    }
+    KD_TREE(const KD_TREE&) = delete;
+    KD_TREE& operator=(const KD_TREE&) = delete;
+
+    void Set_delete_criterion_param(float) {}
+    void Set_balance_criterion_param(float) {}
+    void set_downsample_param(float box_length) {
+        downsample_size_ = box_length;
+        check(h_, icp4r_map_set_downsample(h_, box_length), "set_downsample_param");
+    }
+    void InitializeKDTree(float = 0.5f, float = 0.7f, float box_length = 0.2f) { set_downsample_param(box_length); }
+
+    int size() {
+        int32_t s = 0, v = 0;
+        check(h_, icp4r_map_size(h_, &s, &v), "size");
+        return s;
+    }
+    int validnum() {
+        int32_t s = 0, v = 0;
+        check(h_, icp4r_map_size(h_, &s, &v), "validnum");
+        return v;
+    }
+
+    void Build(PointVector point_cloud) {  // by value, like the reference
+        mirror_.assign(point_cloud.begin(), point_cloud.end());
+        const std::vector<float> xyzw = pack_xyzw(point_cloud.begin(), point_cloud.end());
+        check(h_, icp4r_map_build(h_, xyzw.data(), (int32_t)point_cloud.size(), ICP4R_HOST, 0.f), "Build");
+        check(h_, icp4r_map_set_downsample(h_, downsample_size_), "Build");
+    }
+
+    int Add_Points(PointVector& PointToAdd, bool downsample_on) {
+        const std::vector<float> xyzw = pack_xyzw(PointToAdd.begin(), PointToAdd.end());
+        int32_t replaced = 0;
+        check(h_, icp4r_map_add_points(h_, xyzw.data(), (int32_t)PointToAdd.size(), ICP4R_HOST, downsample_on ? 1 : 0, &replaced),
+              "Add_Points");
+        mirror_.insert(mirror_.end(), PointToAdd.begin(), PointToAdd.end());
+        return replaced;
+    }
+
+    void Nearest_Search(PointType point, int k_nearest, PointVector& Nearest_Points, std::vector<float>& Point_Distance,
+                        double max_dist = INFINITY) {
+        PointVector().swap(Nearest_Points);
+        std::vector<float>().swap(Point_Distance);
+        if (k_nearest <= 0) return;
+        const float q[4] = {point.x, point.y, point.z, 0.f};
+        std::vector<int32_t> idx(k_nearest);
+        std::vector<float> d2(k_nearest);
+        int32_t found = 0;
+        check(h_, icp4r_map_knn(h_, q, 1, ICP4R_HOST, k_nearest, std::isinf(max_dist) ? 0.0 : max_dist, idx.data(), d2.data(), &found),
+              "Nearest_Search");
+        for (int i = 0; i < found; ++i) {  // ascending, like ikd_Tree.cpp:392-396
+            Nearest_Points.push_back(mirror_[idx[i]]);
+            Point_Distance.push_back(d2[i]);
+        }
+    }
+
+    // batch form: rows of k indices into insertion order (-1 = none) and squared distances
+    void Nearest_Search_Batch(const PointVector& queries, int k_nearest, std::vector<int32_t>& indices, std::vector<float>& sq_dist,
+                              std::vector<int32_t>& found, double max_dist = INFINITY) {
+        const std::vector<float> q = pack_xyzw(queries.begin(), queries.end());
+        indices.assign(queries.size() * k_nearest, -1);
+        sq_dist.assign(queries.size() * k_nearest, INFINITY);
+        found.assign(queries.size(), 0);
+        check(h_, icp4r_map_knn(h_, q.data(), (int32_t)queries.size(), ICP4R_HOST, k_nearest, std::isinf(max_dist) ? 0.0 : max_dist,
+                               indices.data(), sq_dist.data(), found.data()),
+              "Nearest_Search_Batch");
+    }
+
+    void Sector_Search(PointType point, const float radius, const float heading, PointVector& Storage) {
+        Storage.clear();
+        const float c[3] = {point.x, point.y, point.z};
+        std::vector<int32_t> idx(mirror_.size() ? mirror_.size() : 1);
+        int32_t n = 0;
+        check(h_, icp4r_map_sector(h_, c, radius, heading, ICP4R_HOST, idx.data(), (int32_t)idx.size(), &n), "Sector_Search");
+        for (int i = 0; i < n && i < (int)idx.size(); ++i) Storage.push_back(mirror_[idx[i]]);
+    }
+
+    BoxPointType tree_range() {
+        float r[6];
+        check(h_, icp4r_map_range(h_, r), "tree_range");
+        BoxPointType b;
+        for (int a = 0; a < 3; ++a) {
+            b.vertex_min[a] = r[a];
+            b.vertex_max[a] = r[3 + a];
+        }
+        return b;
+    }
+
+    const PointType& point_at(int index) const { return mirror_[index]; }
+    icp4r_handle native_handle() { return h_; }
+
+   private:
+    icp4r_handle h_ = nullptr;
+    float downsample_size_;
+    std::vector<PointType, Eigen::aligned_allocator<PointType>> mirror_;  // host copies, returned by value like the reference
+};
+
+}  // namespace icp4r

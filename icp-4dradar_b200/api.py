@@ -19,7 +19,7 @@ MAX_K = 16
 
 EXPORTS = [
     "icp4r_create", "icp4r_destroy", "icp4r_last_error", "icp4r_version", "icp4r_default_opts", "icp4r_set_stream",
-    "icp4r_synchronize", "icp4r_launch_count", "icp4r_map_build", "icp4r_map_set_downsample", "icp4r_map_add_points",
+    "icp4r_synchronize", "icp4r_launch_count", "icp4r_set_profiling", "icp4r_last_profile", "icp4r_map_build", "icp4r_map_set_downsample", "icp4r_map_add_points",
     "icp4r_map_size", "icp4r_map_range", "icp4r_map_knn", "icp4r_map_knn_brute", "icp4r_map_sector", "icp4r_map_points",
     "icp4r_register", "icp4r_register_map", "icp4r_register_batch", "icp4r_shard_unique_id", "icp4r_shard_init",
     "icp4r_register_sharded", "icp4r_transform_points",
@@ -165,6 +165,15 @@ class Icp4r:
         v = C.c_int64(0)
         self._ck(self.lib.icp4r_launch_count(self.h, C.byref(v)))
         return v.value
+
+    def set_profiling(self, on: bool):
+        self._ck(self.lib.icp4r_set_profiling(self.h, C.c_int(int(on))))
+
+    def last_profile(self):
+        buf = np.zeros(4096, np.float32)
+        n = C.c_int32(0)
+        self._ck(self.lib.icp4r_last_profile(self.h, C.c_void_p(buf.ctypes.data), C.c_int32(buf.shape[0]), C.byref(n)))
+        return buf[:n.value].copy()
 
     # ---- map
     def map_build(self, pts, cell_size: float = 0.0):

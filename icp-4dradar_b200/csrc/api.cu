@@ -170,6 +170,7 @@ int icp4r_destroy(icp4r_handle h) {
     cudaStreamSynchronize(c->stream);
     if (c->own_stream != c->stream) cudaStreamSynchronize(c->own_stream);
     drop_graphs(c);
+    for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
     shard_destroy(c);
     free_map(c->map);
     free_map(c->tmp);
@@ -201,6 +202,20 @@ int icp4r_synchronize(icp4r_handle h) {
 int icp4r_launch_count(icp4r_handle h, int64_t* out) {
     if (!h || !out) return ICP4R_ERR_INVALID;
     *out = h->launches;
+    return ICP4R_OK;
+}
+
+int icp4r_set_profiling(icp4r_handle h, int on) {
+    HCHECK(h);
+    c->profiling = on != 0;
+    return ICP4R_OK;
+}
+
+int icp4r_last_profile(icp4r_handle h, float* ms_out, int32_t cap, int32_t* n_out) {
+    HCHECK(h);
+    if (!n_out || cap < 0 || (cap > 0 && !ms_out)) return fail(c, ICP4R_ERR_INVALID, "icp4r_last_profile: bad arguments");
+    *n_out = (int32_t)c->prof_ms.size();
+    for (int i = 0; i < cap && i < (int)c->prof_ms.size(); ++i) ms_out[i] = c->prof_ms[i];
     return ICP4R_OK;
 }
 

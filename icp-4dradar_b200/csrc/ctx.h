@@ -135,6 +135,9 @@ struct Ctx {
     GridDesc graph_grid_copy{};
     const void* graph_pts = nullptr;
     bool use_graph = true;
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;
+    std::vector<float> prof_ms;
 
     // sharding (NCCL loaded lazily with dlopen)
     void* nccl_comm = nullptr;

@@ -116,7 +116,7 @@ __device__ inline void mat4_mul(const double A[16], const double B[16], double C
 // Kabsch rotation from the 3x3 cross-covariance H = sum (p - pm)(q - qm)^T by one-sided Jacobi SVD
 // (H V = U S), R = V U^T with the smallest-singular-value column rebuilt by cross products so that
 // det R = +1 (the Umeyama reflection fix of pcl::umeyama).
-__device__ inline void svd3_rotation(const double H[9], double R[9]) {
+static __device__ __noinline__ void svd3_rotation(const double H[9], double R[9]) {
     double A[9], V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     for (int i = 0; i < 9; ++i) A[i] = H[i];
     for (int sweep = 0; sweep < 30; ++sweep) {
@@ -180,7 +180,7 @@ __device__ inline void svd3_rotation(const double H[9], double R[9]) {
 __device__ __forceinline__ int tri6(int i, int j) { return i * 6 - i * (i - 1) / 2 + (j - i); }
 
 // H x = -g, H symmetric positive definite given as its 21-entry upper triangle; returns 0 on success
-__device__ inline int chol6_solve(const double* H21, const double* g, double x[6]) {
+static __device__ __noinline__ int chol6_solve(const double* H21, const double* g, double x[6]) {
     double L[36];
     for (int i = 0; i < 36; ++i) L[i] = 0.0;
     for (int j = 0; j < 6; ++j) {
@@ -209,7 +209,7 @@ __device__ inline int chol6_solve(const double* H21, const double* g, double x[6
 }
 
 // exp of xi = (omega, v) in SE(3), row-major 4x4
-__device__ inline void se3_exp(const double xi[6], double T[16]) {
+static __device__ __noinline__ void se3_exp(const double xi[6], double T[16]) {
     const double wx = xi[0], wy = xi[1], wz = xi[2];
     const double th2 = wx * wx + wy * wy + wz * wz, th = sqrt(th2);
     double A, B, C;
@@ -285,13 +285,13 @@ __device__ __forceinline__ void contrib_p2p_gn(double* acc, const double pw[3], 
 }
 
 // LOAM plane through k points: A n = -1 by normal equations (adjugate), d = 1/|n|, n /= |n|
-template <int K>
-__device__ __forceinline__ bool plane_fit(const double (&P)[K][3], int k, double n[3], double& d) {
+template <int K, typename F>
+__device__ __forceinline__ bool plane_fit(const F (&P)[K][3], int k, double n[3], double& d) {
     double m00 = 0, m01 = 0, m02 = 0, m11 = 0, m12 = 0, m22 = 0, v0 = 0, v1 = 0, v2 = 0;
 #pragma unroll
     for (int j = 0; j < K; ++j) {
         if (j < k) {
-            const double x = P[j][0], y = P[j][1], z = P[j][2];
+            const double x = (double)P[j][0], y = (double)P[j][1], z = (double)P[j][2];
             m00 += x * x;
             m01 += x * y;
             m02 += x * z;
@@ -324,7 +324,7 @@ template <int K>
 __device__ __forceinline__ bool contrib_p2plane(double* acc, const double pw[3], const double (&P)[K][3], int k,
                                                 double plane_thresh) {
     double n[3], d;
-    if (!plane_fit<K>(P, k, n, d)) return false;
+    if (!plane_fit<K, double>(P, k, n, d)) return false;
 #pragma unroll
     for (int j = 0; j < K; ++j) {
         if (j < k) {

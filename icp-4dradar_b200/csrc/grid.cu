@@ -100,6 +100,15 @@ __global__ void __launch_bounds__(256) cell_start_kernel(const uint32_t* __restr
     cell_start[c] = (uint32_t)lo;
 }
 
+__global__ void __launch_bounds__(256) occupied_kernel(const uint32_t* __restrict__ cell_start, int ncells, int* __restrict__ out) {
+    int cnt = 0;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncells; c += gridDim.x * blockDim.x)
+        cnt += cell_start[c + 1] > cell_start[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(FULL, cnt, o);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(out, cnt);
+}
+
 int map_reserve(Ctx* c, Map& mp, int cap) {
     if ((size_t)cap * sizeof(float4) <= mp.pts.cap) return ICP4R_OK;
     // grow geometrically, keep contents
@@ -175,51 +184,82 @@ int map_rebuild_grid(Ctx* c, Map& mp) {
         cell = std::max(cell, std::max(emax * 1e-4, 1e-6));
     }
     const double max_cells = 64.0 * 1024 * 1024;
-    int nx, ny, nz;
-    for (;;) {
-        const double fx = std::floor(ext[0] / cell) + 1, fy = std::floor(ext[1] / cell) + 1, fz = std::floor(ext[2] / cell) + 1;
-        if (fx * fy * fz <= max_cells && fx < 2e6 && fy < 2e6 && fz < 2e6) {
-            nx = (int)fx;
-            ny = (int)fy;
-            nz = (int)fz;
-            break;
-        }
-        cell *= 1.26;  // coarsen: exactness does not depend on the cell size
-    }
     GridDesc g{};
-    g.ox = mn[0];
-    g.oy = mn[1];
-    g.oz = mn[2];
-    g.cell = (float)cell;
-    g.inv_cell = 1.0f / g.cell;
-    g.nx = nx;
-    g.ny = ny;
-    g.nz = nz;
-    g.ncells = nx * ny * nz;
-    g.m = nvalid;
-    g.margin = (float)(L * 9.5367431640625e-7);
-    // 3. keys + stable radix sort by key
-    CKS(reserve(c, mp.keys_a, (size_t)m * 4));
-    CKS(reserve(c, mp.keys_b, (size_t)m * 4));
-    CKS(reserve(c, mp.vals_a, (size_t)m * 4));
-    CKS(reserve(c, mp.vals_b, (size_t)m * 4));
-    CKS(reserve(c, mp.sorted, (size_t)std::max(m, 1) * sizeof(float4)));
-    CKS(reserve(c, mp.cell_start, ((size_t)g.ncells + 2) * sizeof(uint32_t)));
-    key_kernel<<<(m + 255) / 256, 256, 0, c->stream>>>(mp.pts.as<float4>(), mp.valid.as<uint8_t>(), m, g,
-                                                         mp.keys_a.as<uint32_t>(), mp.vals_a.as<uint32_t>());
-    c->launches += 1;
-    int bits = 1;
-    while ((1ll << bits) <= (long long)g.ncells) ++bits;  // key == ncells must be representable
-    uint32_t *ks, *vs;
-    CKS(radix_sort_pairs(c, mp.keys_a.as<uint32_t>(), mp.keys_b.as<uint32_t>(), mp.vals_a.as<uint32_t>(),
-                         mp.vals_b.as<uint32_t>(), m, bits, c->d_scratch, &ks, &vs));
-    // 4. points into sorted order (valid ones come first), cell table by binary search over the sorted keys
-    if (nvalid > 0) {
-        gather_kernel<<<(nvalid + 255) / 256, 256, 0, c->stream>>>(mp.pts.as<float4>(), vs, nvalid, mp.sorted.as<float4>());
+    // The volume estimate under-counts density when the points lie on surfaces (ground, walls). After the first
+    // build the number of occupied cells gives the real points-per-occupied-cell figure; if it is far from the
+    // target (~4: the 3x3x3 block around a query then holds a few dozen candidates and the 5th neighbour is
+    // still nearer than the block's faces) the cell is rescaled once or twice and the grid rebuilt.
+    for (int pass = 0; pass < 3; ++pass) {
+        int nx, ny, nz;
+        for (;;) {
+            const double fx = std::floor(ext[0] / cell) + 1, fy = std::floor(ext[1] / cell) + 1, fz = std::floor(ext[2] / cell) + 1;
+            if (fx * fy * fz <= max_cells && fx < 2e6 && fy < 2e6 && fz < 2e6) {
+                nx = (int)fx;
+                ny = (int)fy;
+                nz = (int)fz;
+                break;
+            }
+            cell *= 1.26;  // coarsen: exactness does not depend on the cell size
+        }
+        g = GridDesc{};
+        g.ox = mn[0];
+        g.oy = mn[1];
+        g.oz = mn[2];
+        g.cell = (float)cell;
+        g.inv_cell = 1.0f / g.cell;
+        g.nx = nx;
+        g.ny = ny;
+        g.nz = nz;
+        g.ncells = nx * ny * nz;
+        g.m = nvalid;
+        g.margin = (float)(L * 9.5367431640625e-7);
+        // 3. keys + stable radix sort by key
+        CKS(reserve(c, mp.keys_a, (size_t)m * 4));
+        CKS(reserve(c, mp.keys_b, (size_t)m * 4));
+        CKS(reserve(c, mp.vals_a, (size_t)m * 4));
+        CKS(reserve(c, mp.vals_b, (size_t)m * 4));
+        CKS(reserve(c, mp.sorted, (size_t)std::max(m, 1) * sizeof(float4)));
+        CKS(reserve(c, mp.cell_start, ((size_t)g.ncells + 2) * sizeof(uint32_t)));
+        key_kernel<<<(m + 255) / 256, 256, 0, c->stream>>>(mp.pts.as<float4>(), mp.valid.as<uint8_t>(), m, g,
+                                                             mp.keys_a.as<uint32_t>(), mp.vals_a.as<uint32_t>());
         c->launches += 1;
+        int bits = 1;
+        while ((1ll << bits) <= (long long)g.ncells) ++bits;  // key == ncells must be representable
+        uint32_t *ks, *vs;
+        CKS(radix_sort_pairs(c, mp.keys_a.as<uint32_t>(), mp.keys_b.as<uint32_t>(), mp.vals_a.as<uint32_t>(),
+                             mp.vals_b.as<uint32_t>(), m, bits, c->d_scratch, &ks, &vs));
+        // 4. cell table by binary search over the sorted keys
+        cell_start_kernel<<<(g.ncells + 1 + 255) / 256, 256, 0, c->stream>>>(ks, m, g.ncells, mp.cell_start.as<uint32_t>());
+        c->launches += 1;
+        bool again = false;
+        if (!(mp.user_cell > 0.f) && pass < 2 && nvalid >= 64) {
+            int* d_occ = c->d_scratch.as<int>();
+            CK(cudaMemsetAsync(d_occ, 0, sizeof(int), c->stream));
+            occupied_kernel<<<std::min((g.ncells + 255) / 256, c->sm_count * 8), 256, 0, c->stream>>>(mp.cell_start.as<uint32_t>(),
+                                                                                                    g.ncells, d_occ);
+            c->launches += 1;
+            int occ = 0;
+            CK(cudaMemcpyAsync(&occ, d_occ, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            const double per = (double)nvalid / std::max(occ, 1);
+            if (per > 8.0 || per < 2.0) {
+                // occupied cells scale between c^2 (surfaces) and c^3 (volumes): take the gentler exponent
+                const double f = std::sqrt(4.0 / per);
+                const double nc = std::max(cell * std::min(std::max(f, 0.25), 4.0), std::max(emax * 1e-4, 1e-6));
+                if (std::fabs(nc - cell) > 0.1 * cell) {
+                    cell = nc;
+                    again = true;
+                }
+            }
+        }
+        if (again) continue;
+        // 5. points into sorted order (valid ones come first)
+        if (nvalid > 0) {
+            gather_kernel<<<(nvalid + 255) / 256, 256, 0, c->stream>>>(mp.pts.as<float4>(), vs, nvalid, mp.sorted.as<float4>());
+            c->launches += 1;
+        }
+        break;
     }
-    cell_start_kernel<<<(g.ncells + 1 + 255) / 256, 256, 0, c->stream>>>(ks, m, g.ncells, mp.cell_start.as<uint32_t>());
-    c->launches += 1;
     CK(cudaGetLastError());
     g.sorted = mp.sorted.as<float4>();
     g.cell_start = mp.cell_start.as<uint32_t>();
@@ -246,15 +286,16 @@ void gate_params(double max_dist, float* gate_f, float* gate_r) {
 
 // ------------------------------------------------------------------------------------------------ grid kNN kernel
 template <int K>
-__global__ void __launch_bounds__(256) grid_knn_kernel(GridDesc g, const float4* __restrict__ q, int nq, int k, float gate_f,
+__global__ void __launch_bounds__(256, (K <= 5 ? 4 : 2)) grid_knn_kernel(GridDesc g, const float4* __restrict__ q, int nq, int k, float gate_f,
                                                        float gate_r, int32_t* __restrict__ idx, float* __restrict__ d2,
                                                        int32_t* __restrict__ found) {
+    __shared__ WarpSegs segs[8];
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     for (int i = warp; i < nq; i += nwarps) {
         const float4 p = __ldg(q + i);
-        const uint64_t mine = warp_grid_knn<K>(g, p.x, p.y, p.z, gate_f, gate_r, lane);
+        const uint64_t mine = warp_grid_knn<K>(g, segs[threadIdx.x >> 5], p.x, p.y, p.z, gate_f, gate_r, lane);
         const bool have = (lane < k) && (mine != KEY_EMPTY);
         if (lane < k) {
             idx[(size_t)i * k + lane] = have ? key_idx(mine) : -1;

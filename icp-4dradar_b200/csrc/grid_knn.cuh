@@ -10,9 +10,12 @@
 // search stops as soon as the current k-th best d2 is strictly below bound^2 (nothing unscanned can enter,
 // not even on a tie) or the cube covers the whole gate box.
 //
-// Lanes stride over the candidates of one x-row range at a time (cells of an x-row are contiguous in the
-// sorted array, so each range is one coalesced float4 stream), keep a private sorted top-K in registers
-// and the 32 lists are merged with warp reductions.
+// Memory access: the cells of one x-row are contiguous in the sorted array, so a shell is a few dozen
+// contiguous ranges.  Each lane fetches the bounds of one row (all rows' cell-table loads in flight at once),
+// a warp scan turns the range lengths into one virtual candidate index space kept in shared memory, and the
+// lanes then stride over that space four candidates at a time — coalesced float4 loads with 4 independent
+// requests in flight per lane instead of one dependent round trip per row.  Every lane keeps a private sorted
+// top-K in registers; the 32 lists are merged with warp reductions.
 #pragma once
 #include "ctx.h"
 #include "device_math.cuh"
@@ -20,6 +23,12 @@
 namespace icp4r {
 
 constexpr int GRID_RING_CAP = 8;
+constexpr int KNN_SEGS = 64;  // two ranges per lane
+
+struct WarpSegs {  // per-warp shared-memory scratch
+    uint32_t start[KNN_SEGS];
+    uint32_t pre[KNN_SEGS + 1];
+};
 
 __device__ __forceinline__ int cell_of(float v, float o, float inv, int dim) {
     float f = floorf(__fmul_rn(__fsub_rn(v, o), inv));
@@ -28,21 +37,67 @@ __device__ __forceinline__ int cell_of(float v, float o, float inv, int dim) {
 }
 
 template <int K>
-__device__ __forceinline__ void scan_range(const float4* __restrict__ sorted, uint32_t s, uint32_t e, int lane, float qx,
-                                           float qy, float qz, float gate_f, uint64_t kth, TopK<K>& list) {
-    for (uint32_t i = s + lane; i < e; i += 32) {
-        const float4 c = __ldg(sorted + i);
-        const float d = dist2_exact(qx, qy, qz, c.x, c.y, c.z);
-        if (d <= gate_f) {  // false for NaN
-            const uint64_t key = pack_key(d, __float_as_int(c.w));
-            if (key < kth) list.insert(key);
+__device__ __forceinline__ void consider(float qx, float qy, float qz, const float4& c, float gate_f, uint64_t kth, TopK<K>& list) {
+    const float d = dist2_exact(qx, qy, qz, c.x, c.y, c.z);
+    if (d <= gate_f) {  // false for NaN
+        const uint64_t key = pack_key(d, __float_as_int(c.w));
+        if (key < kth) list.insert(key);
+    }
+}
+
+// scan the ranges described by this lane's (s0,e0) and (s1,e1) together with the other 31 lanes' ranges
+template <int K>
+__device__ __forceinline__ void scan_segments(const float4* __restrict__ sorted, WarpSegs& sg, uint32_t s0, uint32_t e0, uint32_t s1,
+                                              uint32_t e1, int lane, float qx, float qy, float qz, float gate_f, uint64_t kth,
+                                              TopK<K>& list) {
+    const uint32_t l0 = e0 - s0, l1 = e1 - s1;
+    uint32_t inc = l0 + l1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += y;
+    }
+    const uint32_t total = __shfl_sync(FULL, inc, 31);
+    if (total == 0) return;
+    const uint32_t exc = inc - (l0 + l1);
+    // compact the non-empty ranges (in lane order) so the per-lane walk below only steps over real ones
+    const unsigned b0 = __ballot_sync(FULL, l0 > 0), b1 = __ballot_sync(FULL, l1 > 0);
+    const unsigned lt = (1u << lane) - 1u;
+    const int slot = __popc(b0 & lt) + __popc(b1 & lt);
+    const int nseg = __popc(b0) + __popc(b1);
+    __syncwarp();
+    if (l0 > 0) {
+        sg.start[slot] = s0;
+        sg.pre[slot] = exc;
+    }
+    if (l1 > 0) {
+        sg.start[slot + (l0 > 0)] = s1;
+        sg.pre[slot + (l0 > 0)] = exc + l0;
+    }
+    if (lane == 0) sg.pre[nseg] = total;
+    __syncwarp();
+    int r = 0;
+    for (uint32_t t0 = lane; t0 < total; t0 += 128) {
+        float4 c[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t t = t0 + 32u * u;
+            ok[u] = t < total;
+            if (ok[u]) {
+                while (t >= sg.pre[r + 1]) ++r;  // pre[nseg] == total > t terminates the walk
+                c[u] = __ldg(sorted + (sg.start[r] + (t - sg.pre[r])));
+            }
         }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (ok[u]) consider<K>(qx, qy, qz, c[u], gate_f, kth, list);
     }
 }
 
 // Returns, in lane r < K, the r-th nearest neighbour's packed key (KEY_EMPTY if fewer exist).
 template <int K>
-__device__ __forceinline__ uint64_t warp_grid_knn(const GridDesc& g, float qx, float qy, float qz, float gate_f,
+__device__ __forceinline__ uint64_t warp_grid_knn(const GridDesc& g, WarpSegs& sg, float qx, float qy, float qz, float gate_f,
                                                   float gate_r, int lane) {
     const float4* __restrict__ sorted = g.sorted;
     const uint32_t* __restrict__ cs = g.cell_start;
@@ -99,15 +154,7 @@ __device__ __forceinline__ uint64_t warp_grid_knn(const GridDesc& g, float qx, f
                     }
                 }
             }
-            unsigned live = __ballot_sync(FULL, (e0 > s0) || (e1 > s1));
-            while (live) {
-                const int src = __ffs(live) - 1;
-                live &= live - 1;
-                const uint32_t a0 = __shfl_sync(FULL, s0, src), b0 = __shfl_sync(FULL, e0, src);
-                const uint32_t a1 = __shfl_sync(FULL, s1, src), b1 = __shfl_sync(FULL, e1, src);
-                scan_range<K>(sorted, a0, b0, lane, qx, qy, qz, gate_f, kth, list);
-                scan_range<K>(sorted, a1, b1, lane, qx, qy, qz, gate_f, kth, list);
-            }
+            scan_segments<K>(sorted, sg, s0, e0, s1, e1, lane, qx, qy, qz, gate_f, kth, list);
         }
         prev = R;
         if (mine != KEY_EMPTY) list.insert(mine);  // carry the previous shells' winners (lanes < K)
@@ -135,7 +182,7 @@ __device__ __forceinline__ uint64_t warp_grid_knn(const GridDesc& g, float qx, f
     if (!done && rneed > 0 && prev < rneed) {
         // ring cap reached (far-away ungated query or a very wide gate): exhaustive scan, still exact
         list.clear();
-        scan_range<K>(sorted, 0u, (uint32_t)g.m, lane, qx, qy, qz, gate_f, KEY_EMPTY, list);
+        scan_segments<K>(sorted, sg, 0u, lane == 0 ? (uint32_t)g.m : 0u, 0u, 0u, lane, qx, qy, qz, gate_f, KEY_EMPTY, list);
         mine = warp_merge_topk<K>(list, lane);
     }
     return mine;

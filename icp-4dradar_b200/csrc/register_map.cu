@@ -29,7 +29,7 @@ struct ResultBlock {  // what travels back to the host in one copy
 };
 
 // pose update from the reduced accumulators; run by one thread.
-__device__ void solve_and_update(int residual, const RegParams& P, RegState* st, const double* tot, const double* Tin, int iter) {
+static __device__ __noinline__ void solve_and_update(int residual, const RegParams& P, RegState* st, const double* tot, const double* Tin, int iter) {
     double T[16];
     for (int i = 0; i < 16; ++i) T[i] = Tin[i];
     double D[16];
@@ -114,21 +114,24 @@ __device__ void write_result(const RegState* st, ResultBlock* out) {
     out->res.last_cost = st->last_cost;
 }
 
-// One iteration (or the fitness pass). Block = 8 warps; each warp finds the neighbours of one source point at
-// a time and parks them in shared memory; then 8 lanes of warp 0 turn the 8 parked correspondences into
-// residual/Jacobian contributions (fp64) held in registers across the block's whole share of points.
+// One iteration (or the fitness pass). One warp owns one source point at a time, start to finish:
+//   transform -> grid kNN (lanes stride the candidates) -> the k neighbours broadcast by shuffle ->
+//   residual and Jacobian row(s) (every lane computes the same few fp64 values) ->
+//   lane t adds ITS product J_i*J_j (or J_i*r, r*r, 1) to ITS accumulator: the 29 (or 17) running sums of
+//   the normal equations live one per lane, in one register, for the whole kernel.
+// No block barrier on the per-point path. At the end the 8 warps' lanes are summed in a fixed order into the
+// block partial, and the last block to finish sums the partials in a fixed order and solves.
 template <int KIND, int K, int MODE>
-__global__ void __launch_bounds__(RM_THREADS)
+__global__ void __launch_bounds__(RM_THREADS, (K <= 5 ? 4 : 2))
     reg_iter_kernel(GridDesc g, const float4* __restrict__ pts, const RegParams* __restrict__ prm, RegState* __restrict__ st,
                     double* __restrict__ partials, ResultBlock* __restrict__ out, int iter) {
     constexpr bool FIT = (MODE == MODE_FITNESS || MODE == MODE_FITNESS_NOFINAL);
     constexpr int KK = FIT ? 1 : K;
+    constexpr int RK = FIT ? ICP4R_P2P_SVD : KIND;  // residual actually accumulated
     if (!FIT && st->done) return;
 
-    __shared__ int nb_idx[RM_WARPS][K];
-    __shared__ float nb_d2[RM_WARPS];
-    __shared__ int nb_src[RM_WARPS];
-    __shared__ double sacc[ICP4R_ACC_LEN * RM_WARPS];  // [value][lane 0..7]: running sums of the 8 contribution lanes
+    __shared__ WarpSegs segs[RM_WARPS];
+    __shared__ double scr[RM_WARPS][3][12];  // per-warp operands of the lane products (up to 3 residual rows)
     __shared__ double red[RM_WARPS][ICP4R_ACC_LEN];
     __shared__ double tot[ICP4R_ACC_LEN];
     __shared__ double Ts[16];
@@ -138,102 +141,162 @@ __global__ void __launch_bounds__(RM_THREADS)
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     if (tid < 16) Ts[tid] = st->T[tid];
     __syncthreads();
-    double T[12];
-#pragma unroll
-    for (int i = 0; i < 12; ++i) T[i] = Ts[i];
 
-    sacc[tid] = 0.0;  // RM_THREADS == ICP4R_ACC_LEN * RM_WARPS
-    static_assert(RM_THREADS == ICP4R_ACC_LEN * RM_WARPS, "sacc init");
-    __syncthreads();
+    // which two operands this lane multiplies (indices into scr[w][row][*])
+    int ia = 8, ib = 8;  // scr[..][8] == 0
+    if (RK == ICP4R_P2P_SVD) {  // scr = {1, p'x,p'y,p'z, qx,qy,qz, d2, 0}
+        if (lane == 0) ia = 0, ib = 0;
+        else if (lane < 7) ia = 0, ib = lane;
+        else if (lane < 16) ia = 1 + (lane - 7) / 3, ib = 4 + (lane - 7) % 3;
+        else if (lane == 16) ia = 0, ib = 7;
+    } else {  // scr = {J0..J5, r, 1, 0}
+        if (lane < 21) {
+            int t = lane, i = 0;
+            while (t >= 6 - i) {
+                t -= 6 - i;
+                ++i;
+            }
+            ia = i;
+            ib = i + t;
+        } else if (lane < 27) ia = lane - 21, ib = 6;
+        else if (lane == 27) ia = 6, ib = 6;
+        else if (lane == 28) ia = 7, ib = 7;
+    }
+    double acc = 0.0;  // this lane's running sum
 
     const int n = P.n;
     const int kq = FIT ? 1 : P.k;
-    const int groups = (n + RM_WARPS - 1) / RM_WARPS;
-    for (int grp = blockIdx.x; grp < groups; grp += gridDim.x) {
-        const int i = grp * RM_WARPS + w;
-        bool active = i < n;
-        double pw[3] = {0, 0, 0};
-        if (active) {
-            const float4 p = __ldg(P.src + i);
-            xform_point(T, p.x, p.y, p.z, pw);
-            const float qx = (float)pw[0], qy = (float)pw[1], qz = (float)pw[2];
-            if (P.shard_axis >= 0) {  // sharded map: the rank whose slab holds the transformed point owns it
-                const float v = P.shard_axis == 0 ? qx : (P.shard_axis == 1 ? qy : qz);
-                active = (v >= P.slab_lo) && (v < P.slab_hi);
-            }
-            if (active) {
-                const uint64_t mine = warp_grid_knn<KK>(g, qx, qy, qz, P.gate_f, P.gate_r, lane);
-                const bool have = (lane < kq) && (mine != KEY_EMPTY);
-                if (lane < KK) nb_idx[w][lane] = have ? key_idx(mine) : -1;
-                if (lane == 0) nb_d2[w] = have ? key_d2(mine) : INFINITY;
-                if (!FIT && P.dump_idx && lane < kq) P.dump_idx[((size_t)iter * n + i) * kq + lane] = have ? key_idx(mine) : -1;
-            } else if (!FIT && P.dump_idx && lane < kq) {
-                P.dump_idx[((size_t)iter * n + i) * kq + lane] = -1;
-            }
+    const int gw = blockIdx.x * RM_WARPS + w, nw = gridDim.x * RM_WARPS;
+    for (int i = gw; i < n; i += nw) {
+        const float4 p = __ldg(P.src + i);
+        double pw[3];
+        xform_point(Ts, p.x, p.y, p.z, pw);
+        const float qx = (float)pw[0], qy = (float)pw[1], qz = (float)pw[2];
+        bool active = true;
+        if (P.shard_axis >= 0) {  // sharded map: the rank whose slab holds the transformed point owns it
+            const float v = P.shard_axis == 0 ? qx : (P.shard_axis == 1 ? qy : qz);
+            active = (v >= P.slab_lo) && (v < P.slab_hi);
         }
-        if (lane == 0) nb_src[w] = active ? i : -1;
-        __syncthreads();
-        if (tid < RM_WARPS && nb_src[tid] >= 0) {
-            const int si = nb_src[tid];
-            const float4 p = __ldg(P.src + si);
-            double pq[3];
-            xform_point(T, p.x, p.y, p.z, pq);
-            // contribution of this correspondence in registers (short-lived), then into the lane's running sums
-            double acc[ICP4R_ACC_LEN];
-#pragma unroll
-            for (int v = 0; v < ICP4R_ACC_LEN; ++v) acc[v] = 0.0;
-            if (FIT || KIND == ICP4R_P2P_SVD) {
-                const int j = nb_idx[tid][0];
-                if (j >= 0) {
-                    const float4 cpt = __ldg(pts + j);
-                    contrib_p2p_svd(acc, pq, cpt.x, cpt.y, cpt.z, nb_d2[tid]);
+        uint64_t mine = KEY_EMPTY;
+        if (active) mine = warp_grid_knn<KK>(g, segs[w], qx, qy, qz, P.gate_f, P.gate_r, lane);
+        const bool have = (lane < kq) && (mine != KEY_EMPTY);
+        if (!FIT && P.dump_idx && lane < kq) P.dump_idx[((size_t)iter * n + i) * kq + lane] = have ? key_idx(mine) : -1;
+        const int found = __popc(__ballot_sync(FULL, have));
+        float4 nb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (have) nb = __ldg(pts + key_idx(mine));  // lane j holds neighbour j
+
+        int rows = 0;  // residual rows written to scr[w]
+        if (RK == ICP4R_P2P_SVD) {
+            if (found >= 1) {
+                const float cx = __shfl_sync(FULL, nb.x, 0), cy = __shfl_sync(FULL, nb.y, 0), cz = __shfl_sync(FULL, nb.z, 0);
+                const float d2 = key_d2(__shfl_sync(FULL, mine, 0));
+                if (lane == 0) {
+                    double* s = scr[w][0];
+                    s[0] = 1.0; s[1] = pw[0]; s[2] = pw[1]; s[3] = pw[2];
+                    s[4] = (double)cx; s[5] = (double)cy; s[6] = (double)cz; s[7] = (double)d2; s[8] = 0.0;
                 }
-            } else if (KIND == ICP4R_P2P_GN) {
-                const int j = nb_idx[tid][0];
-                if (j >= 0) {
-                    const float4 cpt = __ldg(pts + j);
-                    contrib_p2p_gn(acc, pq, cpt.x, cpt.y, cpt.z);
+                rows = 1;
+            }
+        } else if (RK == ICP4R_P2P_GN) {
+            if (found >= 1) {
+                const float cx = __shfl_sync(FULL, nb.x, 0), cy = __shfl_sync(FULL, nb.y, 0), cz = __shfl_sync(FULL, nb.z, 0);
+                if (lane < 3) {  // LidarDistanceFactor (radarFactor.hpp:156-158): r = p' - c, J = [-[p']x | I]
+                    double* s = scr[w][lane];
+                    const double c3[3] = {(double)cx, (double)cy, (double)cz};
+                    s[0] = lane == 0 ? 0.0 : (lane == 1 ? -pw[2] : pw[1]);
+                    s[1] = lane == 0 ? pw[2] : (lane == 1 ? 0.0 : -pw[0]);
+                    s[2] = lane == 0 ? -pw[1] : (lane == 1 ? pw[0] : 0.0);
+                    s[3] = lane == 0 ? 1.0 : 0.0;
+                    s[4] = lane == 1 ? 1.0 : 0.0;
+                    s[5] = lane == 2 ? 1.0 : 0.0;
+                    s[6] = pw[lane] - c3[lane];
+                    s[7] = lane == 0 ? 1.0 : 0.0;  // the correspondence is counted once
+                    s[8] = 0.0;
                 }
-            } else if (KIND == ICP4R_P2PLANE_KNN) {
-                double Pn[K][3];
-                bool all = true;
+                rows = 3;
+            }
+        } else if (RK == ICP4R_P2PLANE_KNN) {
+            if (found == kq && kq >= 3) {
+                float Pn[K][3];  // kept as float (converted at use) to hold register pressure down
 #pragma unroll
                 for (int j = 0; j < K; ++j) {
-                    if (j < kq) {
-                        const int id = nb_idx[tid][j];
-                        if (id < 0) {
-                            all = false;
-                            Pn[j][0] = Pn[j][1] = Pn[j][2] = 0.0;
-                        } else {
-                            const float4 cpt = __ldg(pts + id);
-                            Pn[j][0] = (double)cpt.x;
-                            Pn[j][1] = (double)cpt.y;
-                            Pn[j][2] = (double)cpt.z;
+                    Pn[j][0] = __shfl_sync(FULL, nb.x, j);
+                    Pn[j][1] = __shfl_sync(FULL, nb.y, j);
+                    Pn[j][2] = __shfl_sync(FULL, nb.z, j);
+                }
+                double nrm[3], d;
+                bool ok = plane_fit<K, float>(Pn, kq, nrm, d);
+                if (ok) {
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        if (j < kq) {
+                            const double e = ((nrm[0] * (double)Pn[j][0] + nrm[1] * (double)Pn[j][1]) + nrm[2] * (double)Pn[j][2]) + d;
+                            if (!(fabs(e) <= P.plane_thresh)) ok = false;
                         }
                     }
                 }
-                if (all && kq >= 3) contrib_p2plane<K>(acc, pq, Pn, kq, P.plane_thresh);
-            } else if (KIND == ICP4R_P2LINE) {
-                const int ia = nb_idx[tid][0], ib = (K > 1) ? nb_idx[tid][K > 1 ? 1 : 0] : -1;
-                if (ia >= 0 && ib >= 0) {
-                    const float4 fa = __ldg(pts + ia), fb = __ldg(pts + ib);
-                    const double a[3] = {(double)fa.x, (double)fa.y, (double)fa.z};
-                    const double b[3] = {(double)fb.x, (double)fb.y, (double)fb.z};
-                    contrib_p2line(acc, pq, a, b);
+                if (ok) {  // LidarPlaneNormFactor (radarFactor.hpp:122): r = n.p' + d, J = [(p' x n)^T | n^T]
+                    if (lane == 0) {
+                        double* s = scr[w][0];
+                        double pxn[3];
+                        cross3(pw, nrm, pxn);
+                        s[0] = pxn[0]; s[1] = pxn[1]; s[2] = pxn[2];
+                        s[3] = nrm[0]; s[4] = nrm[1]; s[5] = nrm[2];
+                        s[6] = ((nrm[0] * pw[0] + nrm[1] * pw[1]) + nrm[2] * pw[2]) + d;
+                        s[7] = 1.0; s[8] = 0.0;
+                    }
+                    rows = 1;
                 }
             }
-            constexpr int NV = (FIT || KIND == ICP4R_P2P_SVD) ? 17 : 29;
+        } else if (RK == ICP4R_P2LINE) {
+            if (found >= 2) {
+                const double a[3] = {(double)__shfl_sync(FULL, nb.x, 0), (double)__shfl_sync(FULL, nb.y, 0), (double)__shfl_sync(FULL, nb.z, 0)};
+                const double b[3] = {(double)__shfl_sync(FULL, nb.x, 1), (double)__shfl_sync(FULL, nb.y, 1), (double)__shfl_sync(FULL, nb.z, 1)};
+                const double ba[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
+                const double L = sqrt((ba[0] * ba[0] + ba[1] * ba[1]) + ba[2] * ba[2]);
+                if (L > 0.0) {  // RadarEdgeFactor (radarFactor.hpp:34-39), s = 1
+                    if (lane < 3) {
+                        const double u[3] = {pw[0] - a[0], pw[1] - a[1], pw[2] - a[2]};
+                        const double v[3] = {pw[0] - b[0], pw[1] - b[1], pw[2] - b[2]};
+                        double nu[3];
+                        cross3(u, v, nu);
+                        const double e[3] = {ba[0] / L, ba[1] / L, ba[2] / L};
+                        const double D[9] = {0, -e[2], e[1], e[2], 0, -e[0], -e[1], e[0], 0};
+                        const double Px[9] = {0, pw[2], -pw[1], -pw[2], 0, pw[0], pw[1], -pw[0], 0};
+                        double* s = scr[w][lane];
 #pragma unroll
-            for (int v = 0; v < NV; ++v) sacc[v * RM_WARPS + tid] += acc[v];
+                        for (int j = 0; j < 3; ++j) {
+                            double Dr[3], nuj = 0.0;
+#pragma unroll
+                            for (int r3 = 0; r3 < 3; ++r3) {  // select row `lane` without dynamic register indexing
+                                Dr[r3] = lane == 0 ? D[r3] : (lane == 1 ? D[3 + r3] : D[6 + r3]);
+                            }
+                            nuj = lane == 0 ? nu[0] : (lane == 1 ? nu[1] : nu[2]);
+                            s[j] = (Dr[0] * Px[j] + Dr[1] * Px[3 + j]) + Dr[2] * Px[6 + j];
+                            s[3 + j] = Dr[j];
+                            s[6] = nuj / L;
+                        }
+                        s[7] = lane == 0 ? 1.0 : 0.0;
+                        s[8] = 0.0;
+                    }
+                    rows = 3;
+                }
+            }
         }
-        __syncthreads();
+        if (rows) {
+            __syncwarp();
+            for (int r3 = 0; r3 < rows; ++r3) acc += scr[w][r3][ia] * scr[w][r3][ib];
+            __syncwarp();
+        }
     }
 
-    // block partial: only lanes 0..7 of warp 0 hold non-zero accumulators; fixed-order shuffle tree
+    // block partial in a fixed order: value v = sum over warps 0..7 of lane v's accumulator
+    red[w][lane] = acc;
+    __syncthreads();
     if (tid < ICP4R_ACC_LEN) {
         double x = 0.0;
 #pragma unroll
-        for (int j = 0; j < RM_WARPS; ++j) x += sacc[tid * RM_WARPS + j];
+        for (int j = 0; j < RM_WARPS; ++j) x += red[j][tid];
         partials[(size_t)blockIdx.x * ICP4R_ACC_LEN + tid] = x;
     }
     __threadfence();
@@ -251,9 +314,17 @@ __global__ void __launch_bounds__(RM_THREADS)
     // last block: reduce the block partials in a fixed order (deterministic for a given grid size)
     {
         const int v = tid & 31, grp8 = tid >> 5;
-        double s = 0.0;
-        for (int b = grp8; b < (int)gridDim.x; b += RM_WARPS) s += __ldcg(partials + (size_t)b * ICP4R_ACC_LEN + v);
-        red[grp8][v] = s;
+        // 8 independent chains keep 8 loads in flight per thread; the summation order is still fixed
+        double s8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const int nb_ = (int)gridDim.x;
+        for (int b0 = grp8; b0 < nb_; b0 += RM_WARPS * 8) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int b = b0 + u * RM_WARPS;
+                if (b < nb_) s8[u] += __ldcg(partials + (size_t)b * ICP4R_ACC_LEN + v);
+            }
+        }
+        red[grp8][v] = ((s8[0] + s8[1]) + (s8[2] + s8[3])) + ((s8[4] + s8[5]) + (s8[6] + s8[7]));
     }
     __syncthreads();
     if (tid < ICP4R_ACC_LEN) {
@@ -440,7 +511,7 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
     if (!sharded) {
         // The loop is a fixed sequence of launches whose arguments are all stable device pointers, so it is
         // captured once per (kind, k, blocks, iterations, grid identity) and replayed as a CUDA graph.
-        const bool want_graph = c->use_graph && n > 0;
+        const bool want_graph = c->use_graph && n > 0 && !c->profiling;
         GraphKey key{o->residual, k, blocks, iters, 0};
         cudaGraphExec_t exec = nullptr;
         if (want_graph) {
@@ -479,8 +550,21 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
             CK(cudaGraphLaunch(exec, c->stream));
             c->launches += iters + 1;
         } else {
-            for (int it = 0; it < iters; ++it) dispatch_iter(c, o->residual, k, MODE_ITER, blocks, g, pts, d_prm, d_st, d_part, d_out, it);
+            const bool prof = c->profiling;
+            if (prof) {
+                while ((int)c->prof_events.size() < iters + 2) {
+                    cudaEvent_t e;
+                    CK(cudaEventCreate(&e));
+                    c->prof_events.push_back(e);
+                }
+                CK(cudaEventRecord(c->prof_events[0], c->stream));
+            }
+            for (int it = 0; it < iters; ++it) {
+                dispatch_iter(c, o->residual, k, MODE_ITER, blocks, g, pts, d_prm, d_st, d_part, d_out, it);
+                if (prof) CK(cudaEventRecord(c->prof_events[it + 1], c->stream));
+            }
             dispatch_iter(c, o->residual, k, MODE_FITNESS, blocks, g, pts, d_prm, d_st, d_part, d_out, 0);
+            if (prof) CK(cudaEventRecord(c->prof_events[iters + 1], c->stream));
         }
     } else {
         for (int it = 0; it < iters; ++it) {
@@ -497,6 +581,14 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(&hs->out, d_out, sizeof(ResultBlock), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    c->prof_ms.clear();
+    if (c->profiling && !sharded) {
+        for (int i = 0; i < iters + 1; ++i) {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, c->prof_events[i], c->prof_events[i + 1]));
+            c->prof_ms.push_back(ms);
+        }
+    }
     if (iters == 0) {  // no iteration ran: PCL reports convergence by max_iterations
         hs->out.res.converged = 1;
         hs->out.res.iterations = 0;

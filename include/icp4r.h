@@ -109,6 +109,11 @@ int icp4r_set_stream(icp4r_handle h, void* cuda_stream);
 int icp4r_synchronize(icp4r_handle h);
 /* number of kernels this handle has launched so far (graph-replayed kernels included) */
 int icp4r_launch_count(icp4r_handle h, int64_t* out);
+/* measurement aid: with profiling on, icp4r_register / icp4r_register_map launch their iteration kernels
+ * one by one (no graph) with a CUDA event between launches; icp4r_last_profile then returns the device
+ * time of each launch in milliseconds: max_iterations iteration kernels followed by the fitness pass. */
+int icp4r_set_profiling(icp4r_handle h, int on);
+int icp4r_last_profile(icp4r_handle h, float* ms_out, int32_t cap, int32_t* n_out);
 
 /* ---- map: replaces KD_TREE<PointType> (ikd_Tree.h:227-251) ---------------------------------------- */
 /* Build (ikd_Tree.cpp:354-365): discards any previous map. cell_size <= 0 picks one from the density. */

@@ -1,0 +1,19 @@
+"""GPU: the C++ adapters that mirror the reference's two call shapes (KD_TREE<PointType> and the PCL / fast_gicp
+Registration objects) run against libicp4r_cuda and check themselves against an exhaustive search."""
+import os
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cpp_adapters_selftest():
+    d = os.path.join(ROOT, "icp-4dradar_b200", "adapters")
+    exe = os.path.join(d, "test_adapters")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", d], check=True, capture_output=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "adapters ok" in r.stdout
