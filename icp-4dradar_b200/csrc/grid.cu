@@ -294,6 +294,9 @@ __global__ void __launch_bounds__(256, (K <= 5 ? 4 : 2)) grid_knn_kernel(GridDes
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     for (int i = warp; i < nq; i += nwarps) {
+#ifdef ICP4R_KNN_TIMING
+        const long long t_begin = clock64();
+#endif
         const float4 p = __ldg(q + i);
         const uint64_t mine = warp_grid_knn<K>(g, segs[threadIdx.x >> 5], p.x, p.y, p.z, gate_f, gate_r, lane);
         const bool have = (lane < k) && (mine != KEY_EMPTY);
@@ -303,6 +306,9 @@ __global__ void __launch_bounds__(256, (K <= 5 ? 4 : 2)) grid_knn_kernel(GridDes
         }
         const unsigned b = __ballot_sync(FULL, have);
         if (found && lane == 0) found[i] = __popc(b);
+#ifdef ICP4R_KNN_TIMING
+        if (found && lane == 0) found[i] = (int)(clock64() - t_begin);  // dev probe: cycles spent on this query
+#endif
     }
 }
 

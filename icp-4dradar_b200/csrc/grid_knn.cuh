@@ -124,9 +124,19 @@ __device__ __forceinline__ uint64_t warp_grid_knn(const GridDesc& g, WarpSegs& s
     uint64_t mine = KEY_EMPTY, kth = KEY_EMPTY;
     int prev = -1;  // radius already scanned
     bool done = false;
-    for (int R = min(1, rneed); R <= rneed && R <= GRID_RING_CAP; ++R) {
+    // Dense neighbourhoods (walls): look at the query's own cell first. Its k-th distance then prunes the rows and
+    // the x-extent of the next shells, so a 3x3x3 block that would hold hundreds of candidates shrinks to the few
+    // cells that can still contain a closer point.
+    int R0 = min(1, rneed);
+    if (rneed > 0) {
+        const uint32_t ci = (uint32_t)(cz * g.ny + cy) * (uint32_t)g.nx + (uint32_t)cx;
+        if (__ldg(cs + ci + 1) - __ldg(cs + ci) >= 2u * K) R0 = 0;
+    }
+    for (int R = R0; R <= rneed && R <= GRID_RING_CAP; ++R) {
         // rows (dy, dz) of the shell, 32 at a time: each lane fetches the cell ranges of one row
         const int side = 2 * R + 1, rows = side * side;
+        const bool prune = kth != KEY_EMPTY;
+        const float kd = key_d2(kth) * 1.000001f;  // inflated: a pruned cell can not even hold a tie
         for (int rb = 0; rb < rows; rb += 32) {
             const int r = rb + lane;
             uint32_t s0 = 0, e0 = 0, s1 = 0, e1 = 0;
@@ -134,22 +144,40 @@ __device__ __forceinline__ uint64_t warp_grid_knn(const GridDesc& g, WarpSegs& s
                 const int dy = r % side - R, dz = r / side - R;
                 const int y = cy + dy, z = cz + dz;
                 if (y >= loy && y <= hiy && z >= loz && z <= hiz) {
-                    const uint32_t rowbase = (uint32_t)(z * g.ny + y) * (uint32_t)g.nx;
-                    const int xa = max(cx - R, lox), xb = min(cx + R, hix);
-                    if (max(abs(dy), abs(dz)) > prev) {  // new row: whole x range
-                        if (xa <= xb) {
-                            s0 = __ldg(cs + rowbase + xa);
-                            e0 = __ldg(cs + rowbase + xb + 1);
+                    int xa = max(cx - R, lox), xb = min(cx + R, hix);
+                    bool skip = false;
+                    if (prune) {
+                        // lower bound of the distance from the query to this row's y/z slab (0 inside the slab)
+                        float ddy = dy > 0 ? (g.oy + (float)y * g.cell) - qy : (dy < 0 ? qy - (g.oy + (float)(y + 1) * g.cell) : 0.0f);
+                        float ddz = dz > 0 ? (g.oz + (float)z * g.cell) - qz : (dz < 0 ? qz - (g.oz + (float)(z + 1) * g.cell) : 0.0f);
+                        ddy = fmaxf(ddy - margin, 0.0f);
+                        ddz = fmaxf(ddz - margin, 0.0f);
+                        const float dyz2 = (ddy * ddy + ddz * ddz) * 0.999999f;
+                        if (dyz2 > kd) {
+                            skip = true;
+                        } else {
+                            const float xr = sqrtf(kd - dyz2) * 1.000001f + margin;
+                            xa = max(xa, cell_of(qx - xr, g.ox, g.inv_cell, g.nx));
+                            xb = min(xb, cell_of(qx + xr, g.ox, g.inv_cell, g.nx));
                         }
-                    } else {  // row already scanned up to radius prev: only the two end caps
-                        const int xl = min(cx - prev - 1, hix), xr = max(cx + prev + 1, lox);
-                        if (xa <= xl) {
-                            s0 = __ldg(cs + rowbase + xa);
-                            e0 = __ldg(cs + rowbase + xl + 1);
-                        }
-                        if (xr <= xb) {
-                            s1 = __ldg(cs + rowbase + xr);
-                            e1 = __ldg(cs + rowbase + xb + 1);
+                    }
+                    if (!skip) {
+                        const uint32_t rowbase = (uint32_t)(z * g.ny + y) * (uint32_t)g.nx;
+                        if (max(abs(dy), abs(dz)) > prev) {  // new row: whole x range
+                            if (xa <= xb) {
+                                s0 = __ldg(cs + rowbase + xa);
+                                e0 = __ldg(cs + rowbase + xb + 1);
+                            }
+                        } else {  // row already scanned up to radius prev: only the two end caps
+                            const int xl = min(cx - prev - 1, xb), xr2 = max(cx + prev + 1, xa);
+                            if (xa <= xl) {
+                                s0 = __ldg(cs + rowbase + xa);
+                                e0 = __ldg(cs + rowbase + xl + 1);
+                            }
+                            if (xr2 <= xb) {
+                                s1 = __ldg(cs + rowbase + xr2);
+                                e1 = __ldg(cs + rowbase + xb + 1);
+                            }
                         }
                     }
                 }
