@@ -15,10 +15,11 @@
 #include "ctx.h"
 #include "device_math.cuh"
 #include "grid_knn.cuh"
+#include "solve_warp.cuh"
 
 namespace icp4r {
 
-constexpr int RM_WARPS = 8;
+constexpr int RM_WARPS = 32;  // 1024-thread blocks, one per SM: few partials for the last block to sum
 constexpr int RM_THREADS = RM_WARPS * 32;
 
 enum { MODE_ITER = 0, MODE_ITER_NOSOLVE = 1, MODE_FITNESS = 2, MODE_FITNESS_NOFINAL = 3 };
@@ -28,79 +29,93 @@ struct ResultBlock {  // what travels back to the host in one copy
     icp4r_result res;
 };
 
-// pose update from the reduced accumulators; run by one thread.
-static __device__ __noinline__ void solve_and_update(int residual, const RegParams& P, RegState* st, const double* tot, const double* Tin, int iter) {
-    double T[16];
-    for (int i = 0; i < 16; ++i) T[i] = Tin[i];
-    double D[16];
+// Pose update from the reduced accumulators, run by one full warp (see solve_warp.cuh). `tot`, `Ts` and `ws`
+// (>= 32 doubles of scratch) are shared memory; every branch is warp-uniform.
+__device__ __forceinline__ void warp_solve_and_update(int residual, const RegParams& P, RegState* st, const double* tot, const double* Ts,
+                                                      double* ws, int iter, int lane) {
     const bool last = (iter == P.max_iterations - 1);
+    double* Ds = ws;        // [12] increment, 3x4 row-major
+    double* aux = ws + 16;  // [9] cross-covariance or [6] xi
+    bool stop = false, conv = false;
+    int its = iter + 1;
     if (residual == ICP4R_P2P_SVD) {
         const double cnt = tot[0];
-        st->n_corr = (int)cnt;
+        if (lane == 0) st->n_corr = (int)cnt;
         if (cnt < 3.0) {  // PCL: fewer than 3 correspondences -> not converged
-            st->done = 1;
-            st->converged = 0;
-            st->iterations = iter;
+            if (lane == 0) {
+                st->done = 1;
+                st->converged = 0;
+                st->iterations = iter;
+            }
             return;
         }
-        double pm[3], qm[3], H[9], R[9];
-        for (int i = 0; i < 3; ++i) {
-            pm[i] = tot[1 + i] / cnt;
-            qm[i] = tot[4 + i] / cnt;
+        const double pm0 = tot[1] / cnt, pm1 = tot[2] / cnt, pm2 = tot[3] / cnt;
+        if (lane < 9) {
+            const int r = lane / 3, c = lane % 3;
+            aux[lane] = tot[7 + lane] / cnt - (tot[1 + r] / cnt) * (tot[4 + c] / cnt);
         }
-        for (int i = 0; i < 3; ++i)
-            for (int j = 0; j < 3; ++j) H[3 * i + j] = tot[7 + 3 * i + j] / cnt - pm[i] * qm[j];
-        svd3_rotation(H, R);
-        for (int i = 0; i < 3; ++i) {
-            D[4 * i + 0] = R[3 * i + 0];
-            D[4 * i + 1] = R[3 * i + 1];
-            D[4 * i + 2] = R[3 * i + 2];
-            D[4 * i + 3] = qm[i] - ((R[3 * i] * pm[0] + R[3 * i + 1] * pm[1]) + R[3 * i + 2] * pm[2]);
+        __syncwarp();
+        double R0, R1, R2;
+        warp_kabsch(aux, lane, R0, R1, R2);
+        if (lane < 3) {
+            Ds[4 * lane + 0] = R0;
+            Ds[4 * lane + 1] = R1;
+            Ds[4 * lane + 2] = R2;
+            Ds[4 * lane + 3] = tot[4 + lane] / cnt - ((R0 * pm0 + R1 * pm1) + R2 * pm2);
         }
-        D[12] = D[13] = D[14] = 0;
-        D[15] = 1;
+        __syncwarp();
+        const double tn = warp_compose_entry(Ds, Ts, lane);
+        if (lane < 12) st->T[lane] = tn;
         const double mse = tot[16] / cnt;
-        st->last_cost = mse;
-        mat4_mul(D, T, T);
-        for (int i = 0; i < 16; ++i) st->T[i] = T[i];
+        if (lane == 0) st->last_cost = mse;
         if (P.early_exit) {
             if (fabs(mse - st->mse_prev) < P.mse_abs_eps) {
-                st->done = 1;
-                st->converged = 1;
-                st->iterations = iter + 1;
-                return;
+                stop = true;
+                conv = true;
+            } else if (lane == 0) {
+                st->mse_prev = mse;
             }
-            st->mse_prev = mse;
         }
     } else {
         const double cnt = tot[28];
-        st->n_corr = (int)cnt;
-        double xi[6];
-        if (cnt < 6.0 || chol6_solve(tot, tot + 21, xi)) {
-            st->done = 1;
-            st->converged = 0;
-            st->iterations = iter;
+        if (lane == 0) st->n_corr = (int)cnt;
+        double x = 0.0;
+        bool ok = cnt >= 6.0;
+        if (ok) ok = warp_chol6_solve(tot, tot + 21, lane, x);
+        if (!ok) {
+            if (lane == 0) {
+                st->done = 1;
+                st->converged = 0;
+                st->iterations = iter;
+            }
             return;
         }
-        se3_exp(xi, D);
-        st->last_cost = tot[27];
-        mat4_mul(D, T, T);
-        for (int i = 0; i < 16; ++i) st->T[i] = T[i];
+        if (lane < 6) aux[lane] = x;
+        __syncwarp();
+        const double de = warp_se3_exp_entry(aux, lane);
+        if (lane < 12) Ds[lane] = de;
+        __syncwarp();
+        const double tn = warp_compose_entry(Ds, Ts, lane);
+        if (lane < 12) st->T[lane] = tn;
+        if (lane == 0) st->last_cost = tot[27];
         if (P.early_exit) {
-            const double wn = sqrt(xi[0] * xi[0] + xi[1] * xi[1] + xi[2] * xi[2]);
-            const double vn = sqrt(xi[3] * xi[3] + xi[4] * xi[4] + xi[5] * xi[5]);
+            const double wn = sqrt(aux[0] * aux[0] + aux[1] * aux[1] + aux[2] * aux[2]);
+            const double vn = sqrt(aux[3] * aux[3] + aux[4] * aux[4] + aux[5] * aux[5]);
             if (wn < P.rot_eps && vn < P.trans_eps) {
-                st->done = 1;
-                st->converged = 1;
-                st->iterations = iter + 1;
-                return;
+                stop = true;
+                conv = true;
             }
         }
     }
-    if (last) {
+    if (!stop && last) {
+        stop = true;
+        conv = true;  // PCL: reaching max_iterations counts as converged
+        its = P.max_iterations;
+    }
+    if (stop && lane == 0) {
         st->done = 1;
-        st->converged = 1;  // PCL: reaching max_iterations counts as converged
-        st->iterations = P.max_iterations;
+        st->converged = conv ? 1 : 0;
+        st->iterations = its;
     }
 }
 
@@ -122,7 +137,7 @@ __device__ void write_result(const RegState* st, ResultBlock* out) {
 // No block barrier on the per-point path. At the end the 8 warps' lanes are summed in a fixed order into the
 // block partial, and the last block to finish sums the partials in a fixed order and solves.
 template <int KIND, int K, int MODE>
-__global__ void __launch_bounds__(RM_THREADS, (K <= 5 ? 4 : 2))
+__global__ void __launch_bounds__(RM_THREADS, 1)
     reg_iter_kernel(GridDesc g, const float4* __restrict__ pts, const RegParams* __restrict__ prm, RegState* __restrict__ st,
                     double* __restrict__ partials, ResultBlock* __restrict__ out, int iter) {
     constexpr bool FIT = (MODE == MODE_FITNESS || MODE == MODE_FITNESS_NOFINAL);
@@ -137,9 +152,10 @@ __global__ void __launch_bounds__(RM_THREADS, (K <= 5 ? 4 : 2))
     __shared__ double Ts[16];
     __shared__ bool is_last;
 
-    const RegParams P = *prm;
+    __shared__ RegParams P;  // per-call parameters: one copy per block instead of ~25 registers per thread
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     if (tid < 16) Ts[tid] = st->T[tid];
+    if (tid >= 32 && tid < 32 + (int)(sizeof(RegParams) / 4)) reinterpret_cast<uint32_t*>(&P)[tid - 32] = reinterpret_cast<const uint32_t*>(prm)[tid - 32];
     __syncthreads();
 
     // which two operands this lane multiplies (indices into scr[w][row][*])
@@ -163,6 +179,9 @@ __global__ void __launch_bounds__(RM_THREADS, (K <= 5 ? 4 : 2))
         else if (lane == 28) ia = 7, ib = 7;
     }
     double acc = 0.0;  // this lane's running sum
+#ifdef ICP4R_PHASE_TIMING
+    const long long tp0 = clock64();
+#endif
 
     const int n = P.n;
     const int kq = FIT ? 1 : P.k;
@@ -291,8 +310,16 @@ __global__ void __launch_bounds__(RM_THREADS, (K <= 5 ? 4 : 2))
     }
 
     // block partial in a fixed order: value v = sum over warps 0..7 of lane v's accumulator
+#ifdef ICP4R_PHASE_TIMING
+    const long long tp1 = clock64();
+#endif
     red[w][lane] = acc;
     __syncthreads();
+#ifdef ICP4R_PHASE_TIMING
+    const long long tp2 = clock64();
+    if (lane == 0) atomicMax((unsigned long long*)(partials + 160 * ICP4R_ACC_LEN) + blockIdx.x * 4 + 0, (unsigned long long)(tp1 - tp0));
+    if (tid == 0) ((unsigned long long*)(partials + 160 * ICP4R_ACC_LEN))[blockIdx.x * 4 + 1] = (unsigned long long)(tp2 - tp0);
+#endif
     if (tid < ICP4R_ACC_LEN) {
         double x = 0.0;
 #pragma unroll
@@ -310,6 +337,9 @@ __global__ void __launch_bounds__(RM_THREADS, (K <= 5 ? 4 : 2))
     __syncthreads();
     if (!is_last) return;
     __threadfence();
+#ifdef ICP4R_PHASE_TIMING
+    const long long tp3 = clock64();
+#endif
 
     // last block: reduce the block partials in a fixed order (deterministic for a given grid size)
     {
@@ -352,19 +382,30 @@ __global__ void __launch_bounds__(RM_THREADS, (K <= 5 ? 4 : 2))
         if (MODE == MODE_ITER_NOSOLVE) st->acc[tid] = tot[tid];
     }
     if (tid < 16 && P.dump_pose) P.dump_pose[(size_t)iter * 16 + tid] = Ts[tid];
-    if (MODE == MODE_ITER && tid == 0) solve_and_update(KIND, P, st, tot, Ts, iter);
+#ifdef ICP4R_PHASE_TIMING
+    const long long tp4 = clock64();
+#endif
+    if (MODE == MODE_ITER && w == 0) warp_solve_and_update(KIND, P, st, tot, Ts, &red[0][0], iter, lane);
+#ifdef ICP4R_PHASE_TIMING
+    if (tid == 0) {
+        unsigned long long* dbg = (unsigned long long*)(partials + 160 * ICP4R_ACC_LEN) + 4 * 160;
+        dbg[0] = (unsigned long long)(tp3 - tp0);   // last block: start of main loop -> start of final phase
+        dbg[1] = (unsigned long long)(tp4 - tp3);   // final reduce
+        dbg[2] = (unsigned long long)(clock64() - tp4);  // solve
+    }
+#endif
 }
 
 // sharded path: solve after the cross-rank sum of st->acc
-__global__ void solve_kernel(int residual, const RegParams* __restrict__ prm, RegState* __restrict__ st, int iter) {
+__global__ void __launch_bounds__(32) solve_kernel(int residual, const RegParams* __restrict__ prm, RegState* __restrict__ st, int iter) {
     if (st->done) return;
-    if (threadIdx.x == 0) {
-        const RegParams P = *prm;
-        double Tin[16], tot[ICP4R_ACC_LEN];
-        for (int i = 0; i < 16; ++i) Tin[i] = st->T[i];
-        for (int i = 0; i < ICP4R_ACC_LEN; ++i) tot[i] = st->acc[i];
-        solve_and_update(residual, P, st, tot, Tin, iter);
-    }
+    __shared__ double tot[ICP4R_ACC_LEN], Ts[16], ws[32];
+    const int lane = threadIdx.x;
+    const RegParams P = *prm;
+    tot[lane] = st->acc[lane];
+    if (lane < 16) Ts[lane] = st->T[lane];
+    __syncwarp();
+    warp_solve_and_update(residual, P, st, tot, Ts, ws, iter, lane);
 }
 __global__ void fitness_final_kernel(RegState* __restrict__ st, ResultBlock* __restrict__ out) {
     if (threadIdx.x == 0) {
@@ -464,7 +505,7 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
     CKS(reserve(c, c->d_res, sizeof(ResultBlock)));
     const int groups = std::max(1, (n + RM_WARPS - 1) / RM_WARPS);
     // block count: one group of 8 points per block up to 4 blocks per SM; rounded so graphs get reused
-    int blocks = std::min(groups, c->sm_count * 4);
+    int blocks = std::min(groups, c->sm_count);
     // sized once for the largest grid so the pointer baked into captured graphs never moves
     CKS(reserve(c, c->d_partials, (size_t)c->sm_count * 4 * ICP4R_ACC_LEN * sizeof(double) + 1024));
 
@@ -582,6 +623,17 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
     CK(cudaMemcpyAsync(&hs->out, d_out, sizeof(ResultBlock), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     c->prof_ms.clear();
+#ifdef ICP4R_PHASE_TIMING
+    if (c->profiling && !sharded) {
+        std::vector<unsigned long long> dbg(4 * 160 + 4);
+        cudaMemcpy(dbg.data(), d_part + 160 * ICP4R_ACC_LEN, dbg.size() * 8, cudaMemcpyDeviceToHost);
+        unsigned long long mx0 = 0, mx1 = 0, mn1 = ~0ull; double avg1 = 0;
+        for (int b = 0; b < blocks; ++b) { mx0 = std::max(mx0, dbg[4*b]); mx1 = std::max(mx1, dbg[4*b+1]); mn1 = std::min(mn1, dbg[4*b+1]); avg1 += dbg[4*b+1]; }
+        fprintf(stderr, "[phase] blocks %d  warp-loop max %llu  block(min/avg/max) %llu/%.0f/%llu  last: to-final %llu final-reduce %llu solve %llu cycles\n",
+                blocks, mx0, mn1, avg1 / blocks, mx1, dbg[4*160], dbg[4*160+1], dbg[4*160+2]);
+        cudaMemset(d_part + 160 * ICP4R_ACC_LEN, 0, dbg.size() * 8);
+    }
+#endif
     if (c->profiling && !sharded) {
         for (int i = 0; i < iters + 1; ++i) {
             float ms = 0.f;
