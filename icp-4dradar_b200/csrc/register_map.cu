@@ -19,7 +19,7 @@
 
 namespace icp4r {
 
-constexpr int RM_WARPS = 32;  // 1024-thread blocks, one per SM: few partials for the last block to sum
+constexpr int RM_WARPS = 32;  // upper bound; the launch picks warps per block so that every SM gets one block
 constexpr int RM_THREADS = RM_WARPS * 32;
 
 enum { MODE_ITER = 0, MODE_ITER_NOSOLVE = 1, MODE_FITNESS = 2, MODE_FITNESS_NOFINAL = 3 };
@@ -185,7 +185,8 @@ __global__ void __launch_bounds__(RM_THREADS, 1)
 
     const int n = P.n;
     const int kq = FIT ? 1 : P.k;
-    const int gw = blockIdx.x * RM_WARPS + w, nw = gridDim.x * RM_WARPS;
+    const int nwb = blockDim.x >> 5;  // warps in this block (<= RM_WARPS)
+    const int gw = blockIdx.x * nwb + w, nw = gridDim.x * nwb;
     for (int i = gw; i < n; i += nw) {
         const float4 p = __ldg(P.src + i);
         double pw[3];
@@ -323,7 +324,7 @@ __global__ void __launch_bounds__(RM_THREADS, 1)
     if (tid < ICP4R_ACC_LEN) {
         double x = 0.0;
 #pragma unroll
-        for (int j = 0; j < RM_WARPS; ++j) x += red[j][tid];
+        for (int j = 0; j < nwb; ++j) x += red[j][tid];
         partials[(size_t)blockIdx.x * ICP4R_ACC_LEN + tid] = x;
     }
     __threadfence();
@@ -347,10 +348,10 @@ __global__ void __launch_bounds__(RM_THREADS, 1)
         // 8 independent chains keep 8 loads in flight per thread; the summation order is still fixed
         double s8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         const int nb_ = (int)gridDim.x;
-        for (int b0 = grp8; b0 < nb_; b0 += RM_WARPS * 8) {
+        for (int b0 = grp8; b0 < nb_; b0 += nwb * 8) {
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const int b = b0 + u * RM_WARPS;
+                const int b = b0 + u * nwb;
                 if (b < nb_) s8[u] += __ldcg(partials + (size_t)b * ICP4R_ACC_LEN + v);
             }
         }
@@ -360,7 +361,7 @@ __global__ void __launch_bounds__(RM_THREADS, 1)
     if (tid < ICP4R_ACC_LEN) {
         double s = 0.0;
 #pragma unroll
-        for (int j = 0; j < RM_WARPS; ++j) s += red[j][tid];
+        for (int j = 0; j < nwb; ++j) s += red[j][tid];
         tot[tid] = s;
     }
     __syncthreads();
@@ -434,41 +435,41 @@ __global__ void init_state_kernel(RegState* st, const double* T0) {
 }
 
 template <int KIND, int K>
-static void launch_iter(Ctx* c, int mode, int blocks, const GridDesc& g, const float4* pts, const RegParams* prm, RegState* st,
+static void launch_iter(Ctx* c, int mode, int blocks, int threads, const GridDesc& g, const float4* pts, const RegParams* prm, RegState* st,
                         double* partials, ResultBlock* out, int iter) {
     switch (mode) {
         case MODE_ITER:
-            reg_iter_kernel<KIND, K, MODE_ITER><<<blocks, RM_THREADS, 0, c->stream>>>(g, pts, prm, st, partials, out, iter);
+            reg_iter_kernel<KIND, K, MODE_ITER><<<blocks, threads, 0, c->stream>>>(g, pts, prm, st, partials, out, iter);
             break;
         case MODE_ITER_NOSOLVE:
-            reg_iter_kernel<KIND, K, MODE_ITER_NOSOLVE><<<blocks, RM_THREADS, 0, c->stream>>>(g, pts, prm, st, partials, out, iter);
+            reg_iter_kernel<KIND, K, MODE_ITER_NOSOLVE><<<blocks, threads, 0, c->stream>>>(g, pts, prm, st, partials, out, iter);
             break;
         case MODE_FITNESS:
-            reg_iter_kernel<KIND, K, MODE_FITNESS><<<blocks, RM_THREADS, 0, c->stream>>>(g, pts, prm, st, partials, out, iter);
+            reg_iter_kernel<KIND, K, MODE_FITNESS><<<blocks, threads, 0, c->stream>>>(g, pts, prm, st, partials, out, iter);
             break;
         default:
-            reg_iter_kernel<KIND, K, MODE_FITNESS_NOFINAL><<<blocks, RM_THREADS, 0, c->stream>>>(g, pts, prm, st, partials, out, iter);
+            reg_iter_kernel<KIND, K, MODE_FITNESS_NOFINAL><<<blocks, threads, 0, c->stream>>>(g, pts, prm, st, partials, out, iter);
             break;
     }
     c->launches += 1;
 }
 
-static void dispatch_iter(Ctx* c, int kind, int K, int mode, int blocks, const GridDesc& g, const float4* pts,
+static void dispatch_iter(Ctx* c, int kind, int K, int mode, int blocks, int threads, const GridDesc& g, const float4* pts,
                           const RegParams* prm, RegState* st, double* partials, ResultBlock* out, int iter) {
     switch (kind) {
         case ICP4R_P2P_SVD:
-            launch_iter<ICP4R_P2P_SVD, 1>(c, mode, blocks, g, pts, prm, st, partials, out, iter);
+            launch_iter<ICP4R_P2P_SVD, 1>(c, mode, blocks, threads, g, pts, prm, st, partials, out, iter);
             break;
         case ICP4R_P2P_GN:
-            launch_iter<ICP4R_P2P_GN, 1>(c, mode, blocks, g, pts, prm, st, partials, out, iter);
+            launch_iter<ICP4R_P2P_GN, 1>(c, mode, blocks, threads, g, pts, prm, st, partials, out, iter);
             break;
         case ICP4R_P2LINE:
-            launch_iter<ICP4R_P2LINE, 2>(c, mode, blocks, g, pts, prm, st, partials, out, iter);
+            launch_iter<ICP4R_P2LINE, 2>(c, mode, blocks, threads, g, pts, prm, st, partials, out, iter);
             break;
         default:
-            if (K <= 5) launch_iter<ICP4R_P2PLANE_KNN, 5>(c, mode, blocks, g, pts, prm, st, partials, out, iter);
-            else if (K <= 8) launch_iter<ICP4R_P2PLANE_KNN, 8>(c, mode, blocks, g, pts, prm, st, partials, out, iter);
-            else launch_iter<ICP4R_P2PLANE_KNN, 16>(c, mode, blocks, g, pts, prm, st, partials, out, iter);
+            if (K <= 5) launch_iter<ICP4R_P2PLANE_KNN, 5>(c, mode, blocks, threads, g, pts, prm, st, partials, out, iter);
+            else if (K <= 8) launch_iter<ICP4R_P2PLANE_KNN, 8>(c, mode, blocks, threads, g, pts, prm, st, partials, out, iter);
+            else launch_iter<ICP4R_P2PLANE_KNN, 16>(c, mode, blocks, threads, g, pts, prm, st, partials, out, iter);
             break;
     }
 }
@@ -503,9 +504,12 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
     CKS(reserve(c, c->d_state, sizeof(RegState)));
     CKS(reserve(c, c->d_T, 16 * sizeof(double)));
     CKS(reserve(c, c->d_res, sizeof(ResultBlock)));
-    const int groups = std::max(1, (n + RM_WARPS - 1) / RM_WARPS);
-    // block count: one group of 8 points per block up to 4 blocks per SM; rounded so graphs get reused
-    int blocks = std::min(groups, c->sm_count);
+    // one source point per warp at a time; warps per block chosen so that the points spread over all SMs
+    // (one block per SM keeps the number of partials the last block has to sum at <= sm_count)
+    int wpb = (n + c->sm_count - 1) / c->sm_count;
+    wpb = std::min(std::max(wpb, 4), RM_WARPS);
+    const int threads = wpb * 32;
+    int blocks = std::min(std::max(1, (n + wpb - 1) / wpb), c->sm_count);
     // sized once for the largest grid so the pointer baked into captured graphs never moves
     CKS(reserve(c, c->d_partials, (size_t)c->sm_count * 4 * ICP4R_ACC_LEN * sizeof(double) + 1024));
 
@@ -553,7 +557,7 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
         // The loop is a fixed sequence of launches whose arguments are all stable device pointers, so it is
         // captured once per (kind, k, blocks, iterations, grid identity) and replayed as a CUDA graph.
         const bool want_graph = c->use_graph && n > 0 && !c->profiling;
-        GraphKey key{o->residual, k, blocks, iters, 0};
+        GraphKey key{o->residual, k, blocks, iters, threads};
         cudaGraphExec_t exec = nullptr;
         if (want_graph) {
             // graphs bake the GridDesc by value: drop them when the map geometry or buffers changed
@@ -577,8 +581,8 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
             c->stream = c->own_stream;
             CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
             const int64_t before = c->launches;
-            for (int it = 0; it < iters; ++it) dispatch_iter(c, o->residual, k, MODE_ITER, blocks, g, pts, d_prm, d_st, d_part, d_out, it);
-            dispatch_iter(c, o->residual, k, MODE_FITNESS, blocks, g, pts, d_prm, d_st, d_part, d_out, 0);
+            for (int it = 0; it < iters; ++it) dispatch_iter(c, o->residual, k, MODE_ITER, blocks, threads, g, pts, d_prm, d_st, d_part, d_out, it);
+            dispatch_iter(c, o->residual, k, MODE_FITNESS, blocks, threads, g, pts, d_prm, d_st, d_part, d_out, 0);
             c->launches = before;  // counted at replay time below
             cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
             c->stream = run_stream;
@@ -601,20 +605,20 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
                 CK(cudaEventRecord(c->prof_events[0], c->stream));
             }
             for (int it = 0; it < iters; ++it) {
-                dispatch_iter(c, o->residual, k, MODE_ITER, blocks, g, pts, d_prm, d_st, d_part, d_out, it);
+                dispatch_iter(c, o->residual, k, MODE_ITER, blocks, threads, g, pts, d_prm, d_st, d_part, d_out, it);
                 if (prof) CK(cudaEventRecord(c->prof_events[it + 1], c->stream));
             }
-            dispatch_iter(c, o->residual, k, MODE_FITNESS, blocks, g, pts, d_prm, d_st, d_part, d_out, 0);
+            dispatch_iter(c, o->residual, k, MODE_FITNESS, blocks, threads, g, pts, d_prm, d_st, d_part, d_out, 0);
             if (prof) CK(cudaEventRecord(c->prof_events[iters + 1], c->stream));
         }
     } else {
         for (int it = 0; it < iters; ++it) {
-            dispatch_iter(c, o->residual, k, MODE_ITER_NOSOLVE, blocks, g, pts, d_prm, d_st, d_part, d_out, it);
+            dispatch_iter(c, o->residual, k, MODE_ITER_NOSOLVE, blocks, threads, g, pts, d_prm, d_st, d_part, d_out, it);
             CKS(shard_allreduce(c, reinterpret_cast<double*>(reinterpret_cast<char*>(d_st) + offsetof(RegState, acc)), ICP4R_ACC_LEN));
             solve_kernel<<<1, 32, 0, c->stream>>>(o->residual, d_prm, d_st, it);
             c->launches += 1;
         }
-        dispatch_iter(c, o->residual, k, MODE_FITNESS_NOFINAL, blocks, g, pts, d_prm, d_st, d_part, d_out, 0);
+        dispatch_iter(c, o->residual, k, MODE_FITNESS_NOFINAL, blocks, threads, g, pts, d_prm, d_st, d_part, d_out, 0);
         CKS(shard_allreduce(c, reinterpret_cast<double*>(reinterpret_cast<char*>(d_st) + offsetof(RegState, acc)), 2));
         fitness_final_kernel<<<1, 32, 0, c->stream>>>(d_st, d_out);
         c->launches += 1;

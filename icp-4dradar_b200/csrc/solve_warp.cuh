@@ -136,9 +136,14 @@ __device__ __forceinline__ void warp_kabsch(const double* __restrict__ Hs, int l
             const double al = sum3(a[p] * a[p]), be = sum3(a[q] * a[q]), ga = sum3(a[p] * a[q]);
             if (fabs(ga) <= 1e-300 || fabs(ga) <= 1e-16 * sqrt(al * be)) continue;  // warp-uniform
             off += fabs(ga);
-            const double zeta = (be - al) / (2.0 * ga);
-            const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-            const double c = rsqrt(1.0 + t * t), s = c * t;
+            // rotation that zeroes a_p . a_q: tan 2t = 2 ga / (be - al), |t| <= pi/4, written with two rsqrt
+            // instead of a divide and two square roots (this loop is on the serial tail of every iteration)
+            const double dd = be - al, g2 = 2.0 * ga;
+            const double invh = rsqrt(dd * dd + g2 * g2);      // 1 / hypot(dd, g2)
+            const double c2 = 0.5 + 0.5 * fabs(dd) * invh;     // cos^2 t
+            const double invc = rsqrt(c2);
+            const double c = c2 * invc;
+            const double s = (dd >= 0 ? 0.5 : -0.5) * g2 * invh * invc;
             const double ap = a[p], aq = a[q], vp = v[p], vq = v[q];
             a[p] = c * ap - s * aq;
             a[q] = s * ap + c * aq;
