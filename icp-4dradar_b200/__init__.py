@@ -13,3 +13,4 @@ from .api import (  # noqa: F401
     lib_path, load_library, default_opts,
 )
 from . import synth  # noqa: F401
+from . import shard  # noqa: F401
