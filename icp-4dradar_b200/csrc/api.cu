@@ -247,11 +247,32 @@ int icp4r_map_add_points(icp4r_handle h, const float* xyzw, int32_t n, int mem, 
     if (n < 0 || (n > 0 && !xyzw) || bad_mem(mem)) return fail(c, ICP4R_ERR_INVALID, "icp4r_map_add_points: bad arguments");
     if (n_replaced) *n_replaced = 0;
     Map& mp = c->map;
-    if (downsample_on) return fail(c, ICP4R_ERR_UNSUPPORTED, "Add_Points with down-sampling is not implemented yet");
     if (n == 0) return ICP4R_OK;
-    CKS(set_points(c, mp, xyzw, n, mem, mp.m));
-    mp.m += n;
-    CKS(map_rebuild_grid(c, mp));
+    if (!downsample_on) {
+        CKS(set_points(c, mp, xyzw, n, mem, mp.m));
+        mp.m += n;
+        CKS(map_rebuild_grid(c, mp));
+        return ICP4R_OK;
+    }
+    // down-sampling: the reference inserts point by point, each seeing the effect of the previous ones. The device
+    // evaluates that rule voxel-parallel over chunks (the chunk bound keeps the leader search cheap); between
+    // chunks the grid is rebuilt so the next chunk sees the survivors.
+    if (!mp.built) CKS(map_rebuild_grid(c, mp));
+    const char* fs = std::getenv("ICP4R_DS_SEQUENTIAL");
+    const bool force_seq = fs && fs[0] == '1';
+    const int CH = 8192;
+    int total = 0;
+    for (int off = 0; off < n; off += CH) {
+        const int cn = std::min(CH, n - off);
+        CKS(set_points(c, mp, xyzw + 4 * (size_t)off, cn, mem, mp.m));
+        CK(cudaMemsetAsync(mp.valid.as<uint8_t>() + mp.m, 0, (size_t)cn, c->stream));  // not inserted yet
+        int rep = 0;
+        CKS(map_downsample_add(c, mp, cn, &rep, force_seq));
+        total += rep;
+        mp.m += cn;
+        CKS(map_rebuild_grid(c, mp));
+    }
+    if (n_replaced) *n_replaced = total;
     return ICP4R_OK;
 }
 
@@ -318,8 +339,21 @@ int icp4r_map_knn_brute(icp4r_handle h, const float* q, int32_t nq, int mem, int
 int icp4r_map_sector(icp4r_handle h, const float centre_xyz[3], float radius, float heading_deg, int mem, int32_t* idx_out,
                      int32_t cap, int32_t* n_out) {
     HCHECK(h);
-    (void)centre_xyz; (void)radius; (void)heading_deg; (void)mem; (void)idx_out; (void)cap; (void)n_out;
-    return fail(c, ICP4R_ERR_UNSUPPORTED, "icp4r_map_sector is not implemented yet");
+    if (!centre_xyz || !n_out || cap < 0 || (cap > 0 && !idx_out) || bad_mem(mem)) return fail(c, ICP4R_ERR_INVALID, "icp4r_map_sector: bad arguments");
+    if (!c->map.built) return fail(c, ICP4R_ERR_STATE, "icp4r_map_sector before icp4r_map_build");
+    int32_t* d_out = idx_out;
+    if (mem == ICP4R_HOST) {
+        CKS(reserve(c, c->d_idx, (size_t)std::max(cap, 1) * 4));
+        d_out = c->d_idx.as<int32_t>();
+    }
+    int cnt = 0;
+    CKS(map_sector(c, c->map, centre_xyz, radius, heading_deg, d_out, cap, &cnt));
+    if (mem == ICP4R_HOST && cap > 0 && cnt > 0) {
+        CK(cudaMemcpyAsync(idx_out, d_out, (size_t)std::min(cnt, cap) * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    *n_out = cnt;
+    return ICP4R_OK;
 }
 
 int icp4r_map_points(icp4r_handle h, int mem, float* xyzw_out, uint8_t* valid_out, int32_t cap) {

@@ -161,6 +161,10 @@ int brute_knn(Ctx* c, const Map& mp, const float4* q, int nq, int k, double max_
               int32_t* found);
 void gate_params(double max_dist, float* gate_f, float* gate_r);
 
+// map_ops.cu
+int map_downsample_add(Ctx* c, Map& mp, int n, int* n_replaced_host, bool force_sequential);
+int map_sector(Ctx* c, const Map& mp, const float centre[3], float radius, float heading, int32_t* d_out, int cap, int* n_out_host);
+
 // register_map.cu
 int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4r_opts* o, int shard_axis,
                          float slab_lo, float slab_hi, double* T_out_host, icp4r_result* res_host,

@@ -1,0 +1,110 @@
+"""GPU parity: map maintenance next to the kNN path — Add_Points with voxel down-sampling and Sector_Search —
+against golden vectors produced by the reference's own ikd-Tree and against the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.int32)
+
+
+def run_downsample(handle, base, batches, voxel):
+    handle.map_build(base)
+    handle.map_set_downsample(voxel)
+    rets, valids = [], []
+    for b in batches:
+        rets.append(handle.map_add_points(b, True))
+        valids.append(handle.map_size()[1])
+    pts, valid = handle.map_points()
+    return rets, valids, pts, valid
+
+
+@pytest.mark.parametrize("sequential", ["0", "1"])
+def test_downsample_golden(handle, O, sequential, monkeypatch):
+    """return values, survivor set and kNN over the survivors equal the reference's (both device paths)"""
+    monkeypatch.setenv("ICP4R_DS_SEQUENTIAL", sequential)
+    g = np.load(os.path.join(G, "downsample.npz"))
+    sizes = g["batch_sizes"]
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    batches = [g["batches"][offs[i]:offs[i + 1]] for i in range(len(sizes))]
+    rets, valids, pts, valid = run_downsample(handle, g["base"], batches, float(g["voxel"]))
+    assert rets == list(g["rets"]), (rets, list(g["rets"]))
+    assert valids == list(g["validnum"])
+    assert (np.nonzero(valid)[0] == g["alive"]).all()
+    idx, d2, found = handle.map_knn(g["q"], 5, 0.0)
+    assert (found == g["found"]).all() and (bits(d2) == bits(g["d2"])).all()
+    same = idx == g["idx"]
+    assert same.all() or (bits(d2)[~same] == bits(g["d2"])[~same]).all()  # exact duplicates were inserted on purpose
+
+
+@pytest.mark.parametrize("voxel", [0.3, 0.5, 0.77, 2.0])
+def test_downsample_matches_oracle(handle, O, voxel):
+    """voxel sizes that are not powers of two put voxel faces off the float grid (rounding hazards -> exact fallback)"""
+    rng = np.random.default_rng(int(voxel * 100))
+    base = np.zeros((3000, 4), np.float32)
+    base[:, :3] = rng.uniform(-9, 9, (3000, 3)) * np.array([1, 1, 0.2])
+    batches = []
+    for b in range(3):
+        a = np.zeros((1200, 4), np.float32)
+        a[:, :3] = rng.uniform(-10, 10, (1200, 3)) * np.array([1, 1, 0.2])
+        batches.append(a)
+    # points sitting exactly on voxel faces and exact duplicates of existing points
+    face = np.zeros((300, 4), np.float32)
+    face[:, :3] = (rng.integers(-20, 20, (300, 3)) * np.float32(voxel)).astype(np.float32)
+    batches.append(face)
+    batches.append(base[:100].copy())
+    rets, valids, pts, valid = run_downsample(handle, base, batches, voxel)
+    m = O.OracleMap(len(base) + sum(len(b) for b in batches))
+    m.add_points(base)
+    want = [m.add_points(b, True, voxel) for b in batches]
+    assert rets == want
+    assert (valid == m.valid[:m.m]).all(), np.nonzero(valid != m.valid[:m.m])[0][:10]
+    assert valids[-1] == int(m.valid[:m.m].sum())
+
+
+def test_downsample_into_empty_and_single_voxel(handle, O):
+    rng = np.random.default_rng(3)
+    ham = np.zeros((1000, 4), np.float32)
+    ham[:, :3] = rng.uniform(0.0, 0.5, (1000, 3)) + np.array([2.0, 2.0, 0.0])
+    handle.map_build(ham[:1])
+    handle.map_set_downsample(0.5)
+    r = handle.map_add_points(ham[1:], True)
+    m = O.OracleMap(1000)
+    m.add_points(ham[:1])
+    assert r == m.add_points(ham[1:], True, 0.5)
+    size, nvalid = handle.map_size()
+    assert size == 1000 and nvalid == 1 == int(m.valid[:m.m].sum())      # one survivor: the point nearest the voxel centre
+    _, valid = handle.map_points()
+    assert (valid == m.valid[:m.m]).all()
+
+
+def test_sector_golden(handle, O):
+    g = np.load(os.path.join(G, "sector.npz"))
+    handle.map_build(g["pts"])
+    for ci, c in enumerate(g["centres"]):
+        for hi, hd in enumerate(g["headings"]):
+            got = np.sort(handle.map_sector(c, float(g["radius"]), float(hd)))
+            want = g[f"s_{ci}_{hi}"]
+            assert got.shape == want.shape and (got == want).all(), (ci, hi, len(got), len(want))
+
+
+def test_sector_matches_oracle_after_downsample(handle, O):
+    """deleted points are never returned; centre on a map point (NaN heading) is excluded like in the reference"""
+    rng = np.random.default_rng(8)
+    pts = np.zeros((5000, 4), np.float32)
+    pts[:, :3] = rng.uniform(-60, 60, (5000, 3)) * np.array([1, 1, 0.05])
+    handle.map_build(pts[:4000])
+    handle.map_set_downsample(2.0)
+    handle.map_add_points(pts[4000:], True)
+    m = O.OracleMap(5000)
+    m.add_points(pts[:4000])
+    m.add_points(pts[4000:], True, 2.0)
+    for c, r, hd in ((pts[10, :3], 40.0, 30.0), (np.array([1.0, -2.0, 0.0], np.float32), 80.0, -100.0), (np.array([0, 0, 0], np.float32), 15.0, 179.0)):
+        got = np.sort(handle.map_sector(c, r, hd))
+        want = np.sort(m.sector(c, r, hd))
+        assert (got == want).all()
