@@ -332,7 +332,10 @@ def main():
             h.set_profiling(False)
             k_ms = float(np.mean(per[3:]))
             ach = alg / (k_ms * 1e-3) / 1e9
-            line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the ncu --set full capture summarised in
+            # profiles/r1_c2_reg_iter_kernel_ncu.txt (ncu flushes caches between replays: this is the COLD figure; warm
+            # launches of the same step are served from L2)
+            line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": 3608320,
                                 "kernel": "reg_iter_kernel<P2PLANE_KNN,5>", "kernel_ms": k_ms, "algorithmic_bytes": alg, "m_r": m_r,
                                 "peak_source": peak_src,
                                 "note": "working set (3.3 MB) is L2-resident: the kernel is latency-bound, see DESIGN.md"}
