@@ -21,6 +21,13 @@ int fail(Ctx* c, int code, const char* fmt, ...) {
     return code;
 }
 
+// like reserve, but over-allocates by 50 % so a buffer that grows a little on every call (the map's sort and
+// index arrays in an odometry loop) is not freed and re-allocated each time
+int reserve_grow(Ctx* c, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap && b.p) return ICP4R_OK;
+    return reserve(c, b, bytes + bytes / 2);
+}
+
 int reserve(Ctx* c, DevBuf& b, size_t bytes) {
     if (bytes <= b.cap && b.p) return ICP4R_OK;
     if (b.p) {
@@ -229,6 +236,7 @@ int icp4r_map_build(icp4r_handle h, const float* xyzw, int32_t n, int mem, float
     mp.m_valid = 0;
     mp.built = false;
     mp.user_cell = cell_size;
+    mp.hint_cell = 0.f;
     CKS(set_points(c, mp, xyzw, n, mem, 0));
     mp.m = n;
     CKS(map_rebuild_grid(c, mp));
@@ -442,6 +450,7 @@ int icp4r_register(icp4r_handle h, const float* src, int32_t n, const float* tgt
     mp.m = 0;
     mp.built = false;
     mp.user_cell = 0.f;
+    mp.hint_cell = 0.f;
     CKS(set_points(c, mp, tgt, m, mem, 0));
     mp.m = m;
     CKS(map_rebuild_grid(c, mp));

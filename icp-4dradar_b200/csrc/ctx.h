@@ -37,6 +37,7 @@ struct DevBuf {
     T* as() const { return static_cast<T*>(p); }
 };
 int reserve(Ctx* c, DevBuf& b, size_t bytes);
+int reserve_grow(Ctx* c, DevBuf& b, size_t bytes);
 void release(DevBuf& b);
 
 // ---- uniform voxel grid over a point set (replaces the k-d tree) ----------------------------------
@@ -63,6 +64,7 @@ struct Map {
     int m_valid = 0;
     bool built = false;
     float user_cell = 0.f;
+    float hint_cell = 0.f;  // refined cell size of the previous build of this map (Add_Points starts from it)
     float ds_voxel = 0.2f;  // KD_TREE default downsample_size, ikd_Tree.h:196
     GridDesc grid{};
     float bb_min[3] = {0, 0, 0}, bb_max[3] = {0, 0, 0};

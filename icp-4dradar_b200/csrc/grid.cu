@@ -1,7 +1,9 @@
 // grid.cu — the device map: voxel-grid build (replaces KD_TREE::Build / BuildTree,
 // /root/reference/third_party/ikd-Tree/ikd_Tree.cpp:354-365,582-630) and the stand-alone kNN kernels behind
 // icp4r_map_knn / icp4r_map_knn_brute (replace Nearest_Search, ikd_Tree.cpp:368-398).
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "ctx.h"
@@ -130,8 +132,29 @@ int map_reserve(Ctx* c, Map& mp, int cap) {
     return ICP4R_OK;
 }
 
+namespace {
+struct Trace {  // ICP4R_TRACE=1: wall time of the build stages (each stage is followed by a stream sync)
+    bool on;
+    cudaStream_t st;
+    std::chrono::steady_clock::time_point t0;
+    explicit Trace(cudaStream_t s) : st(s) {
+        const char* e = std::getenv("ICP4R_TRACE");
+        on = e && e[0] == '1';
+        t0 = std::chrono::steady_clock::now();
+    }
+    void mark(const char* what) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[icp4r trace] %-22s %8.1f us\n", what, std::chrono::duration<double, std::micro>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+}  // namespace
+
 int map_rebuild_grid(Ctx* c, Map& mp) {
     const int m = mp.m;
+    Trace tr(c->stream);
     mp.built = false;
     mp.grid = GridDesc{};
     if (m <= 0) {
@@ -161,6 +184,7 @@ int map_rebuild_grid(Ctx* c, Map& mp) {
     CK(cudaStreamSynchronize(c->stream));
     const int nvalid = h_bb[6];
     mp.m_valid = nvalid;
+    tr.mark("bbox");
     float mn[3], mx[3];
     for (int a = 0; a < 3; ++a) {
         mn[a] = nvalid ? ord2f(h_bb[a]) : 0.f;
@@ -176,7 +200,7 @@ int map_rebuild_grid(Ctx* c, Map& mp) {
         L = std::max(L, std::max(std::fabs((double)mn[a]), std::fabs((double)mx[a])));
     }
     const double emax = std::max(ext[0], std::max(ext[1], ext[2]));
-    double cell = mp.user_cell > 0.f ? (double)mp.user_cell : 0.0;
+    double cell = mp.user_cell > 0.f ? (double)mp.user_cell : (double)mp.hint_cell;
     if (!(cell > 0.0)) {
         const double floor_e = std::max(emax * 1e-3, 1e-6);
         const double vol = std::max(ext[0], floor_e) * std::max(ext[1], floor_e) * std::max(ext[2], floor_e);
@@ -214,23 +238,27 @@ int map_rebuild_grid(Ctx* c, Map& mp) {
         g.m = nvalid;
         g.margin = (float)(L * 9.5367431640625e-7);
         // 3. keys + stable radix sort by key
-        CKS(reserve(c, mp.keys_a, (size_t)m * 4));
-        CKS(reserve(c, mp.keys_b, (size_t)m * 4));
-        CKS(reserve(c, mp.vals_a, (size_t)m * 4));
-        CKS(reserve(c, mp.vals_b, (size_t)m * 4));
-        CKS(reserve(c, mp.sorted, (size_t)std::max(m, 1) * sizeof(float4)));
-        CKS(reserve(c, mp.cell_start, ((size_t)g.ncells + 2) * sizeof(uint32_t)));
+        CKS(reserve_grow(c, mp.keys_a, (size_t)m * 4));
+        CKS(reserve_grow(c, mp.keys_b, (size_t)m * 4));
+        CKS(reserve_grow(c, mp.vals_a, (size_t)m * 4));
+        CKS(reserve_grow(c, mp.vals_b, (size_t)m * 4));
+        CKS(reserve_grow(c, mp.sorted, (size_t)std::max(m, 1) * sizeof(float4)));
+        CKS(reserve_grow(c, mp.cell_start, ((size_t)g.ncells + 2) * sizeof(uint32_t)));
+        tr.mark("reserve");
         key_kernel<<<(m + 255) / 256, 256, 0, c->stream>>>(mp.pts.as<float4>(), mp.valid.as<uint8_t>(), m, g,
                                                              mp.keys_a.as<uint32_t>(), mp.vals_a.as<uint32_t>());
         c->launches += 1;
+        tr.mark("keys");
         int bits = 1;
         while ((1ll << bits) <= (long long)g.ncells) ++bits;  // key == ncells must be representable
         uint32_t *ks, *vs;
         CKS(radix_sort_pairs(c, mp.keys_a.as<uint32_t>(), mp.keys_b.as<uint32_t>(), mp.vals_a.as<uint32_t>(),
                              mp.vals_b.as<uint32_t>(), m, bits, c->d_scratch, &ks, &vs));
+        tr.mark("radix sort");
         // 4. cell table by binary search over the sorted keys
         cell_start_kernel<<<(g.ncells + 1 + 255) / 256, 256, 0, c->stream>>>(ks, m, g.ncells, mp.cell_start.as<uint32_t>());
         c->launches += 1;
+        tr.mark("cell table");
         bool again = false;
         if (!(mp.user_cell > 0.f) && pass < 2 && nvalid >= 64) {
             int* d_occ = c->d_scratch.as<int>();
@@ -241,6 +269,8 @@ int map_rebuild_grid(Ctx* c, Map& mp) {
             int occ = 0;
             CK(cudaMemcpyAsync(&occ, d_occ, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
             CK(cudaStreamSynchronize(c->stream));
+            tr.mark("occupancy");
+            if (tr.on) fprintf(stderr, "[icp4r trace] pass %d cell %.3f cells %d occupied %d\n", pass, cell, g.ncells, occ);
             const double per = (double)nvalid / std::max(occ, 1);
             if (per > 8.0 || per < 2.0) {
                 // occupied cells scale between c^2 (surfaces) and c^3 (volumes): take the gentler exponent
@@ -258,6 +288,7 @@ int map_rebuild_grid(Ctx* c, Map& mp) {
             gather_kernel<<<(nvalid + 255) / 256, 256, 0, c->stream>>>(mp.pts.as<float4>(), vs, nvalid, mp.sorted.as<float4>());
             c->launches += 1;
         }
+        tr.mark("gather");
         break;
     }
     CK(cudaGetLastError());
@@ -265,6 +296,7 @@ int map_rebuild_grid(Ctx* c, Map& mp) {
     g.cell_start = mp.cell_start.as<uint32_t>();
     mp.grid = g;
     mp.built = true;
+    mp.hint_cell = g.cell;
     return ICP4R_OK;
 }
 
