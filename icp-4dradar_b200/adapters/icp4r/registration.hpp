@@ -141,14 +141,14 @@ class IterativeClosestPoint : public RegistrationBase<PointSource, PointTarget> 
     }
 };
 
-// fast_gicp::FastGICPSingleThread shape. Until the GICP cost lands, the k-neighbour
-// plane residual (LidarPlaneNormFactor with the plane fitted to the k = CorrespondenceRandomness neighbours)
-// stands in: same 6x6 normal-equation solve, fast_gicp's stopping rule and 64-iteration cap.
+// fast_gicp::FastGICPSingleThread shape on the library's GICP cost (plane-regularised k-NN covariances of both
+// clouds, 1-NN Mahalanobis residual, Levenberg-Marquardt), with fast_gicp's defaults: k = 20 (capped at
+// ICP4R_MAX_K = 16), 64 iterations, rotation / translation epsilons 2e-3 / 5e-4, ungated.
 template <typename PointSource, typename PointTarget>
 class FastGICPSingleThread : public RegistrationBase<PointSource, PointTarget> {
    public:
     explicit FastGICPSingleThread(int device = 0) : RegistrationBase<PointSource, PointTarget>(device) {
-        this->opts_.residual = ICP4R_P2PLANE_KNN;
+        this->opts_.residual = ICP4R_GICP;
         this->opts_.k = 20;  // fast_gicp default k_correspondences
         if (this->opts_.k > ICP4R_MAX_K) this->opts_.k = ICP4R_MAX_K;
         this->opts_.max_iterations = 64;

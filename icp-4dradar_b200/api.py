@@ -123,7 +123,7 @@ def _f4(a):
 
 
 def _knn_k(residual, k):
-    return 1 if residual in (P2P_SVD, P2P_GN) else (2 if residual == P2LINE else (k if k > 0 else 5))
+    return 1 if residual in (P2P_SVD, P2P_GN, GICP) else (2 if residual == P2LINE else (k if k > 0 else 5))
 
 
 class Icp4r:

@@ -65,6 +65,7 @@ static void free_map(Map& m) {
     release(m.keys_b);
     release(m.vals_a);
     release(m.vals_b);
+    release(m.normals);
     m.m = m.m_valid = 0;
     m.built = false;
 }
@@ -181,6 +182,9 @@ int icp4r_destroy(icp4r_handle h) {
     shard_destroy(c);
     free_map(c->map);
     free_map(c->tmp);
+    free_map(c->srcmap);
+    release(c->d_src_normals);
+    release(c->d_gicp_corr);
     DevBuf* bufs[] = {&c->d_src, &c->d_q, &c->d_idx, &c->d_d2, &c->d_found, &c->d_scratch, &c->d_partials, &c->d_state, &c->d_params,
                       &c->d_T, &c->d_res, &c->d_dump_pose, &c->d_dump_acc, &c->d_dump_idx, &c->b_src, &c->b_tgt, &c->b_soff,
                       &c->b_toff, &c->b_T, &c->b_res};
@@ -378,7 +382,7 @@ int icp4r_map_points(icp4r_handle h, int mem, float* xyzw_out, uint8_t* valid_ou
 // ---- registration -----------------------------------------------------------------------------------------
 
 static int k_of(const icp4r_opts* o) {
-    return (o->residual == ICP4R_P2P_SVD || o->residual == ICP4R_P2P_GN) ? 1 : (o->residual == ICP4R_P2LINE ? 2 : (o->k > 0 ? o->k : 5));
+    return (o->residual == ICP4R_P2P_SVD || o->residual == ICP4R_P2P_GN || o->residual == ICP4R_GICP) ? 1 : (o->residual == ICP4R_P2LINE ? 2 : (o->k > 0 ? o->k : 5));
 }
 
 // dumps requested with host pointers are produced on the device and copied back afterwards

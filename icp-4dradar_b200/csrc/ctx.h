@@ -68,6 +68,14 @@ struct Map {
     float ds_voxel = 0.2f;  // KD_TREE default downsample_size, ikd_Tree.h:196
     GridDesc grid{};
     float bb_min[3] = {0, 0, 0}, bb_max[3] = {0, 0, 0};
+    DevBuf normals;     // double[3 * m]: GICP surface normals by insertion index (valid while normals_k != 0)
+    int normals_k = 0;  // neighbours they were estimated from; reset to 0 whenever the grid is rebuilt
+};
+
+struct GicpCorr {  // per source point, written by the linearisation, read by the LM error passes
+    int idx;       // target index or -1
+    int pad;
+    double li[6];  // L^-1 (lower triangle, row-major) with (C_B + R C_A R^T) = L L^T
 };
 
 // device-resident registration state (one per handle)
@@ -76,6 +84,9 @@ struct RegState {
     double acc[ICP4R_ACC_LEN];
     double mse_prev;
     double last_cost;
+    double lm_lambda;    // GICP Levenberg-Marquardt damping (< 0: not initialised)
+    int lm_last_conv;
+    int pad2;
     double fit_sum;
     int fit_cnt;
     int done;
@@ -103,6 +114,11 @@ struct RegParams {  // kernel parameters that change per call; lives in device m
     // sharded registration
     int shard_axis;      // -1: not sharded
     float slab_lo, slab_hi;
+    // GICP
+    const double* src_normals;
+    const double* tgt_normals;
+    const float4* tgt_pts;  // target points by insertion index
+    GicpCorr* corr;
 };
 
 struct GraphKey {
@@ -125,6 +141,8 @@ struct Ctx {
 
     Map map;      // the handle's persistent map
     Map tmp;      // transient target of icp4r_register
+    Map srcmap;   // transient index over the SOURCE cloud (GICP source covariances)
+    DevBuf d_src_normals, d_gicp_corr;
 
     DevBuf d_src, d_q, d_idx, d_d2, d_found, d_scratch, d_partials, d_state, d_params, d_T, d_res;
     DevBuf d_dump_pose, d_dump_acc, d_dump_idx;
@@ -175,6 +193,10 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
 // register_batch.cu
 int register_batch(Ctx* c, const float4* d_src, const int32_t* d_soff, const float4* d_tgt, const int32_t* d_toff,
                    int n_pairs, int max_n, int max_m, const icp4r_opts* o, double* d_T, icp4r_result* d_res);
+
+// gicp.cu
+int gicp_normals(Ctx* c, Map& mp, int k);  // fills mp.normals for every valid point of mp (cached per k)
+int gicp_lm_step(Ctx* c, const RegParams* d_prm, RegState* d_st, int iter);
 
 // shard.cu
 int shard_allreduce(Ctx* c, double* d_buf, int count);

@@ -1,0 +1,266 @@
+// gicp.cu — the pieces of the fast_gicp cost (call site /root/reference/src/radar_odometry.cpp:399-405)
+// that are not the fused iteration kernel:
+//   * per-point surface normals from each cloud's own k nearest neighbours (fast_gicp's calculate_covariances with
+//     the PLANE regularisation keeps only the eigenvector n of the smallest eigenvalue: C = I - (1 - 1e-3) n n^T);
+//   * the Levenberg-Marquardt step: damped 6x6 solve, candidate pose, error pass over the stored correspondences,
+//     gain ratio, accept / re-damp — one single-block kernel per outer iteration.
+// [UPSTREAM, unpinned]: fast_gicp is not vendored by the reference; restated from its published algorithm.
+#include <cmath>
+
+#include "ctx.h"
+#include "device_math.cuh"
+#include "grid_knn.cuh"
+#include "solve_warp.cuh"
+
+namespace icp4r {
+
+// eigenvector of the smallest eigenvalue of a symmetric 3x3 (cyclic Jacobi), same operation order as the oracle
+__device__ __forceinline__ void smallest_eigvec3(const double C[9], double n[3]) {
+    double A[9], V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+#pragma unroll
+    for (int i = 0; i < 9; ++i) A[i] = C[i];
+    for (int sweep = 0; sweep < 50; ++sweep) {
+        const double off = fabs(A[1]) + fabs(A[2]) + fabs(A[5]);
+        if (off < 1e-300) break;
+#pragma unroll
+        for (int pq = 0; pq < 3; ++pq) {
+            const int p = pq == 2 ? 1 : 0, q = pq == 0 ? 1 : 2;
+            const double apq = A[3 * p + q];
+            if (fabs(apq) < 1e-300) continue;
+            const double theta = (A[3 * q + q] - A[3 * p + p]) / (2.0 * apq);
+            const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+            const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double akp = A[3 * k + p], akq = A[3 * k + q];
+                A[3 * k + p] = c * akp - s * akq;
+                A[3 * k + q] = s * akp + c * akq;
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double apk = A[3 * p + k], aqk = A[3 * q + k];
+                A[3 * p + k] = c * apk - s * aqk;
+                A[3 * q + k] = s * apk + c * aqk;
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double vkp = V[3 * k + p], vkq = V[3 * k + q];
+                V[3 * k + p] = c * vkp - s * vkq;
+                V[3 * k + q] = s * vkp + c * vkq;
+            }
+        }
+    }
+    int m = 0;
+    if (A[4] < A[0]) m = 1;
+    if (A[8] < (m == 0 ? A[0] : A[4])) m = 2;
+    const double v0 = m == 0 ? V[0] : (m == 1 ? V[1] : V[2]);
+    const double v1 = m == 0 ? V[3] : (m == 1 ? V[4] : V[5]);
+    const double v2 = m == 0 ? V[6] : (m == 1 ? V[7] : V[8]);
+    const double len = sqrt(v0 * v0 + v1 * v1 + v2 * v2);
+    n[0] = v0 / len;
+    n[1] = v1 / len;
+    n[2] = v2 / len;
+}
+
+// one warp per point of the grid's own cloud: k-NN among the cloud (the point itself included), covariance about
+// the neighbours' mean divided by k, smallest eigenvector -> normals[3 * original_index]
+template <int K>
+__global__ void __launch_bounds__(256) normals_kernel(GridDesc g, const float4* __restrict__ pts, int k, double* __restrict__ normals) {
+    __shared__ WarpSegs segs[8];
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = warp; i < g.m; i += nwarps) {
+        const float4 p = __ldg(g.sorted + i);
+        const uint64_t mine = warp_grid_knn<K>(g, segs[threadIdx.x >> 5], p.x, p.y, p.z, INFINITY, INFINITY, lane);
+        const bool have = (lane < k) && (mine != KEY_EMPTY);
+        const int found = __popc(__ballot_sync(FULL, have));
+        float4 nb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (have) nb = __ldg(pts + key_idx(mine));
+        double mean[3] = {0, 0, 0}, C[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        float nx[K], ny[K], nz[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            nx[j] = __shfl_sync(FULL, nb.x, j);
+            ny[j] = __shfl_sync(FULL, nb.y, j);
+            nz[j] = __shfl_sync(FULL, nb.z, j);
+            if (j < found) {
+                mean[0] += (double)nx[j];
+                mean[1] += (double)ny[j];
+                mean[2] += (double)nz[j];
+            }
+        }
+        const double fdiv = (double)(found > 0 ? found : 1);
+        mean[0] /= fdiv;
+        mean[1] /= fdiv;
+        mean[2] /= fdiv;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            if (j < found) {
+                const double d[3] = {(double)nx[j] - mean[0], (double)ny[j] - mean[1], (double)nz[j] - mean[2]};
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) C[3 * a + b] += d[a] * d[b];
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 9; ++a) C[a] /= (double)k;  // fast_gicp divides by k_correspondences_
+        double n[3];
+        smallest_eigvec3(C, n);
+        if (lane == 0) {
+            const size_t o = 3 * (size_t)__float_as_int(p.w);
+            normals[o] = n[0];
+            normals[o + 1] = n[1];
+            normals[o + 2] = n[2];
+        }
+    }
+}
+
+int gicp_normals(Ctx* c, Map& mp, int k) {
+    if (mp.normals_k == k) return ICP4R_OK;
+    CKS(reserve_grow(c, mp.normals, (size_t)std::max(mp.m, 1) * 3 * sizeof(double)));
+    if (mp.grid.m > 0) {
+        const int blocks = std::min((mp.grid.m + 7) / 8, c->sm_count * 8);
+        double* out = mp.normals.as<double>();
+        if (k <= 5) normals_kernel<5><<<blocks, 256, 0, c->stream>>>(mp.grid, mp.pts.as<float4>(), k, out);
+        else if (k <= 8) normals_kernel<8><<<blocks, 256, 0, c->stream>>>(mp.grid, mp.pts.as<float4>(), k, out);
+        else normals_kernel<16><<<blocks, 256, 0, c->stream>>>(mp.grid, mp.pts.as<float4>(), k, out);
+        c->launches += 1;
+        CK(cudaGetLastError());
+    }
+    mp.normals_k = k;
+    return ICP4R_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ LM step
+constexpr int LM_THREADS = 1024;
+
+__device__ __forceinline__ bool delta_converged(const double* D /*3x4*/, double rot_eps, double trans_eps) {
+    double m = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) m = fmax(m, fabs(D[4 * i + j] - (i == j ? 1.0 : 0.0)) / rot_eps);
+        m = fmax(m, fabs(D[4 * i + 3]) / trans_eps);
+    }
+    return m < 1.0;
+}
+
+// fast_gicp LsqRegistration::step_lm for one outer iteration: st->acc holds H (21), g (6), y0, count of the
+// linearisation at st->T; P.corr holds each source point's correspondence and L^-1.
+__global__ void __launch_bounds__(LM_THREADS) gicp_lm_kernel(const RegParams* __restrict__ prm, RegState* __restrict__ st, int iter) {
+    if (st->done) return;
+    __shared__ double Hs[ICP4R_ACC_LEN], Hl[ICP4R_ACC_LEN], Ts[16], Xi[16], Ds[16], xi6[8], red[32];
+    __shared__ double s_lambda, s_nu, s_yi;
+    __shared__ int s_state;  // 0: keep trying, 1: step taken (x0 updated or converged without update), 2: failed
+    __shared__ RegParams P;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid < ICP4R_ACC_LEN) Hs[tid] = st->acc[tid];
+    if (tid < 16) Ts[tid] = st->T[tid];
+    if (tid >= 32 && tid < 32 + (int)(sizeof(RegParams) / 4)) reinterpret_cast<uint32_t*>(&P)[tid - 32] = reinterpret_cast<const uint32_t*>(prm)[tid - 32];
+    __syncthreads();
+    const double cnt = Hs[28], y0 = Hs[27];
+    const bool last = (iter == P.max_iterations - 1);
+    if (tid == 0) {
+        st->n_corr = (int)cnt;
+        st->last_cost = y0;
+        double lam = st->lm_lambda;
+        if (lam < 0.0) {
+            double mx = 0.0;
+            for (int i = 0; i < 6; ++i) mx = fmax(mx, fabs(Hs[i * 6 - i * (i - 1) / 2]));
+            lam = 1e-9 * mx;  // lm_init_lambda_factor_
+        }
+        s_lambda = lam;
+        s_nu = 2.0;
+        s_state = cnt < 6.0 ? 2 : 0;
+    }
+    __syncthreads();
+    for (int t = 0; t < 10 && s_state == 0; ++t) {  // lm_max_iterations_
+        if (w == 0) {
+            if (lane < 21) Hl[lane] = Hs[lane];
+            __syncwarp();
+            if (lane < 6) Hl[lane * 6 - lane * (lane - 1) / 2] += s_lambda;
+            __syncwarp();
+            double x = 0.0;
+            const bool ok = warp_chol6_solve(Hl, Hs + 21, lane, x);
+            if (lane < 6) xi6[lane] = x;
+            __syncwarp();
+            const double de = warp_se3_exp_entry(xi6, lane);
+            if (lane < 12) Ds[lane] = de;
+            __syncwarp();
+            const double tn = warp_compose_entry(Ds, Ts, lane);
+            if (lane < 12) Xi[lane] = tn;
+            if (lane == 0 && !ok) s_state = 2;
+        }
+        __syncthreads();
+        if (s_state != 0) break;
+        // y_i = sum |L^-1 (b - xi a)|^2 over the stored correspondences
+        double part = 0.0;
+        for (int i = tid; i < P.n; i += LM_THREADS) {
+            const GicpCorr cr = P.corr[i];
+            if (cr.idx < 0) continue;
+            const float4 a = __ldg(P.src + i);
+            double pa[3];
+            xform_point(Xi, a.x, a.y, a.z, pa);
+            const float4 b = __ldg(P.tgt_pts + cr.idx);
+            const double e0 = (double)b.x - pa[0], e1 = (double)b.y - pa[1], e2 = (double)b.z - pa[2];
+            const double f0 = cr.li[0] * e0, f1 = cr.li[1] * e0 + cr.li[2] * e1, f2 = (cr.li[3] * e0 + cr.li[4] * e1) + cr.li[5] * e2;
+            part += (f0 * f0 + f1 * f1) + f2 * f2;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
+        if (lane == 0) red[w] = part;
+        __syncthreads();
+        if (tid == 0) {
+            double yi = 0.0;
+            for (int k = 0; k < LM_THREADS / 32; ++k) yi += red[k];
+            s_yi = yi;
+            double den = 0.0;
+            for (int i = 0; i < 6; ++i) den += xi6[i] * (s_lambda * xi6[i] - Hs[21 + i]);
+            const double rho = (y0 - yi) / den;
+            if (rho < 0) {
+                if (delta_converged(Ds, P.rot_eps, P.trans_eps)) {
+                    s_state = 1;  // fast_gicp returns true here without moving x0
+                } else {
+                    s_lambda = s_nu * s_lambda;
+                    s_nu = 2.0 * s_nu;
+                }
+            } else {
+                for (int i = 0; i < 12; ++i) st->T[i] = Xi[i];
+                const double f = 2.0 * rho - 1.0;
+                s_lambda = s_lambda * fmax(1.0 / 3.0, 1.0 - f * f * f);
+                s_state = 1;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        st->lm_lambda = s_lambda;
+        if (s_state != 1) {  // "lm not converged!!" or too few correspondences
+            st->done = 1;
+            st->converged = 0;
+            st->iterations = iter;
+        } else {
+            const bool conv = delta_converged(Ds, P.rot_eps, P.trans_eps);
+            st->lm_last_conv = conv ? 1 : 0;
+            if (P.early_exit && conv) {
+                st->done = 1;
+                st->converged = 1;
+                st->iterations = iter + 1;
+            } else if (last) {
+                st->done = 1;
+                st->converged = P.early_exit ? 0 : (conv ? 1 : 0);
+                st->iterations = P.max_iterations;
+            }
+        }
+    }
+}
+
+int gicp_lm_step(Ctx* c, const RegParams* d_prm, RegState* d_st, int iter) {
+    gicp_lm_kernel<<<1, LM_THREADS, 0, c->stream>>>(d_prm, d_st, iter);
+    c->launches += 1;
+    return ICP4R_OK;
+}
+
+}  // namespace icp4r

@@ -156,6 +156,7 @@ int map_rebuild_grid(Ctx* c, Map& mp) {
     const int m = mp.m;
     Trace tr(c->stream);
     mp.built = false;
+    mp.normals_k = 0;  // any cached GICP normals belong to the previous point set
     mp.grid = GridDesc{};
     if (m <= 0) {
         mp.m_valid = 0;

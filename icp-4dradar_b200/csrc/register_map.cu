@@ -268,6 +268,59 @@ __global__ void __launch_bounds__(RM_THREADS, 1)
                     rows = 1;
                 }
             }
+        } else if (RK == ICP4R_GICP) {
+            // fast_gicp cost: e = b - T a, J = [skew(T a) | -I], weight M = (C_B + R C_A R^T)^-1 with C = I - 0.999 n n^T.
+            // With (C_B + R C_A R^T) = L L^T the three rows L^-1 J, L^-1 e feed the same lane-owned accumulators.
+            bool okc = false;
+            double li[6] = {0, 0, 0, 0, 0, 0};
+            const int j0 = found >= 1 ? key_idx(__shfl_sync(FULL, mine, 0)) : -1;
+            if (found >= 1) {
+                const float cx = __shfl_sync(FULL, nb.x, 0), cy = __shfl_sync(FULL, nb.y, 0), cz = __shfl_sync(FULL, nb.z, 0);
+                const double* na = P.src_normals + 3 * (size_t)i;
+                const double* nbn = P.tgt_normals + 3 * (size_t)j0;
+                const double a0 = na[0], a1 = na[1], a2 = na[2], b0 = nbn[0], b1 = nbn[1], b2 = nbn[2];
+                const double r0 = Ts[0] * a0 + Ts[1] * a1 + Ts[2] * a2, r1 = Ts[4] * a0 + Ts[5] * a1 + Ts[6] * a2,
+                             r2 = Ts[8] * a0 + Ts[9] * a1 + Ts[10] * a2;
+                const double al = 0.999;
+                const double s00 = 2.0 - al * (b0 * b0 + r0 * r0), s10 = -al * (b1 * b0 + r1 * r0), s11 = 2.0 - al * (b1 * b1 + r1 * r1);
+                const double s20 = -al * (b2 * b0 + r2 * r0), s21 = -al * (b2 * b1 + r2 * r1), s22 = 2.0 - al * (b2 * b2 + r2 * r2);
+                const double l00 = sqrt(s00), l10 = s10 / l00, l20 = s20 / l00;
+                const double d11 = s11 - l10 * l10;
+                const double l11 = sqrt(d11), l21 = (s21 - l20 * l10) / l11;
+                const double d22 = s22 - l20 * l20 - l21 * l21;
+                const double l22 = sqrt(d22);
+                okc = (s00 > 0.0) && (d11 > 0.0) && (d22 > 0.0);
+                if (okc) {
+                    li[0] = 1.0 / l00;
+                    li[2] = 1.0 / l11;
+                    li[5] = 1.0 / l22;
+                    li[1] = -l10 * li[0] * li[2];
+                    li[4] = -l21 * li[2] * li[5];
+                    li[3] = -(l20 * li[0] + l21 * li[1]) * li[5];
+                    if (lane < 3) {
+                        const double e[3] = {(double)cx - pw[0], (double)cy - pw[1], (double)cz - pw[2]};
+                        const double J[3][6] = {{0, -pw[2], pw[1], -1, 0, 0}, {pw[2], 0, -pw[0], 0, -1, 0}, {-pw[1], pw[0], 0, 0, 0, -1}};
+                        const double w0 = lane == 0 ? li[0] : (lane == 1 ? li[1] : li[3]);
+                        const double w1 = lane == 0 ? 0.0 : (lane == 1 ? li[2] : li[4]);
+                        const double w2 = lane == 2 ? li[5] : 0.0;
+                        double* s = scr[w][lane];
+#pragma unroll
+                        for (int cix = 0; cix < 6; ++cix) s[cix] = (w0 * J[0][cix] + w1 * J[1][cix]) + w2 * J[2][cix];
+                        s[6] = (w0 * e[0] + w1 * e[1]) + w2 * e[2];
+                        s[7] = lane == 0 ? 1.0 : 0.0;
+                        s[8] = 0.0;
+                    }
+                    rows = 3;
+                }
+            }
+            if (!FIT && lane == 0 && P.corr) {
+                GicpCorr cr;
+                cr.idx = okc ? j0 : -1;
+                cr.pad = 0;
+#pragma unroll
+                for (int t6 = 0; t6 < 6; ++t6) cr.li[t6] = li[t6];
+                P.corr[i] = cr;
+            }
         } else if (RK == ICP4R_P2LINE) {
             if (found >= 2) {
                 const double a[3] = {(double)__shfl_sync(FULL, nb.x, 0), (double)__shfl_sync(FULL, nb.y, 0), (double)__shfl_sync(FULL, nb.z, 0)};
@@ -423,6 +476,8 @@ __global__ void init_state_kernel(RegState* st, const double* T0) {
     if (t == 0) {
         st->mse_prev = INFINITY;
         st->last_cost = 0.0;
+        st->lm_lambda = -1.0;
+        st->lm_last_conv = 0;
         st->fit_sum = 0.0;
         st->fit_cnt = 0;
         st->done = 0;
@@ -466,6 +521,9 @@ static void dispatch_iter(Ctx* c, int kind, int K, int mode, int blocks, int thr
         case ICP4R_P2LINE:
             launch_iter<ICP4R_P2LINE, 2>(c, mode, blocks, threads, g, pts, prm, st, partials, out, iter);
             break;
+        case ICP4R_GICP:
+            launch_iter<ICP4R_GICP, 1>(c, mode, blocks, threads, g, pts, prm, st, partials, out, iter);
+            break;
         default:
             if (K <= 5) launch_iter<ICP4R_P2PLANE_KNN, 5>(c, mode, blocks, threads, g, pts, prm, st, partials, out, iter);
             else if (K <= 8) launch_iter<ICP4R_P2PLANE_KNN, 8>(c, mode, blocks, threads, g, pts, prm, st, partials, out, iter);
@@ -478,6 +536,7 @@ static int knn_k_for(const icp4r_opts* o) {
     switch (o->residual) {
         case ICP4R_P2P_SVD:
         case ICP4R_P2P_GN:
+        case ICP4R_GICP:
             return 1;
         case ICP4R_P2LINE:
             return 2;
@@ -489,7 +548,6 @@ static int knn_k_for(const icp4r_opts* o) {
 int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4r_opts* o, int shard_axis, float slab_lo,
                          float slab_hi, double* T_out_host, icp4r_result* res_host, const icp4r_dump* dump) {
     if (!mp.built) return fail(c, ICP4R_ERR_STATE, "registration target has no built map");
-    if (o->residual == ICP4R_GICP) return fail(c, ICP4R_ERR_UNSUPPORTED, "ICP4R_GICP is not implemented yet");
     if (o->residual < 0 || o->residual > ICP4R_GICP) return fail(c, ICP4R_ERR_INVALID, "bad residual kind %d", o->residual);
     const int k = knn_k_for(o);
     if (k > ICP4R_MAX_K) return fail(c, ICP4R_ERR_INVALID, "k=%d exceeds ICP4R_MAX_K", k);
@@ -538,6 +596,31 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
     P.shard_axis = sharded ? shard_axis : -1;
     P.slab_lo = slab_lo;
     P.slab_hi = slab_hi;
+    const bool gicp = o->residual == ICP4R_GICP;
+    if (gicp) {
+        if (sharded) return fail(c, ICP4R_ERR_UNSUPPORTED, "GICP is not available for sharded maps yet");
+        // covariances (normals) of both clouds from their own k nearest neighbours; the map's are cached per k
+        const int kc = std::min(std::max(o->k > 0 ? o->k : 20, 3), ICP4R_MAX_K);
+        CKS(gicp_normals(c, mp, kc));
+        Map& sm = c->srcmap;
+        sm.m = 0;
+        sm.built = false;
+        sm.user_cell = 0.f;
+        sm.hint_cell = 0.f;
+        CKS(map_reserve(c, sm, n));
+        if (n > 0) {
+            CK(cudaMemcpyAsync(sm.pts.p, d_src, (size_t)n * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
+            CK(cudaMemsetAsync(sm.valid.p, 1, (size_t)n, c->stream));
+        }
+        sm.m = n;
+        CKS(map_rebuild_grid(c, sm));
+        CKS(gicp_normals(c, sm, kc));
+        CKS(reserve_grow(c, c->d_gicp_corr, (size_t)std::max(n, 1) * sizeof(GicpCorr)));
+        P.src_normals = sm.normals.as<double>();
+        P.tgt_normals = mp.normals.as<double>();
+        P.tgt_pts = mp.pts.as<float4>();
+        P.corr = c->d_gicp_corr.as<GicpCorr>();
+    }
     std::memcpy(hs->T0, o->T0, sizeof(hs->T0));
 
     RegParams* d_prm = c->d_params.as<RegParams>();
@@ -553,7 +636,14 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
     const float4* pts = mp.pts.as<float4>();
     const int iters = o->max_iterations;
 
-    if (!sharded) {
+    if (gicp) {
+        // linearise (grid-wide, accumulators left in st->acc) then one single-block Levenberg-Marquardt step
+        for (int it = 0; it < iters; ++it) {
+            dispatch_iter(c, o->residual, k, MODE_ITER_NOSOLVE, blocks, threads, g, pts, d_prm, d_st, d_part, d_out, it);
+            CKS(gicp_lm_step(c, d_prm, d_st, it));
+        }
+        dispatch_iter(c, o->residual, k, MODE_FITNESS, blocks, threads, g, pts, d_prm, d_st, d_part, d_out, 0);
+    } else if (!sharded) {
         // The loop is a fixed sequence of launches whose arguments are all stable device pointers, so it is
         // captured once per (kind, k, blocks, iterations, grid identity) and replayed as a CUDA graph.
         const bool want_graph = c->use_graph && n > 0 && !c->profiling;

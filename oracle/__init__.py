@@ -235,7 +235,7 @@ class IkdTree:
 # ---------------------------------------------------------------------------------------- loops
 
 def knn_k_for(residual, k):
-    return 1 if residual in (P2P_SVD, P2P_GN) else (2 if residual == P2LINE else (k if k > 0 else 5))
+    return 1 if residual in (P2P_SVD, P2P_GN, GICP) else (2 if residual == P2LINE else (k if k > 0 else 5))
 
 
 def register(src, tgt, opts: OrcOpts, searcher=None, dump=False):
@@ -274,6 +274,45 @@ def icp_p2p_f32(src, tgt, iters, searcher=None):
     lib().orc_icp_p2p_f32(_p(src), C.c_int(src.shape[0]), _p(tgt), C.c_int(tgt.shape[0]), s.fn, s.ctx,
                           C.c_int(iters), _p(T))
     return T.reshape(4, 4)
+
+
+# ---------------------------------------------------------------------------------------- GICP
+
+def gicp_normals(pts, k, searcher=None):
+    pts = f4(pts)
+    s = searcher or BruteSearcher(pts)
+    out = np.zeros((pts.shape[0], 3), np.float64)
+    lib().orc_gicp_normals(_p(pts), C.c_int(pts.shape[0]), s.fn, s.ctx, C.c_int(k), _p(out))
+    return out
+
+
+def gicp_linearize(src, sn, tgt, tn, opts: OrcOpts, T, searcher=None):
+    src, tgt = f4(src), f4(tgt)
+    s = searcher or BruteSearcher(tgt)
+    T = np.ascontiguousarray(T, np.float64).reshape(16)
+    acc = np.zeros(ACC_LEN, np.float64)
+    idx = np.full(src.shape[0], -1, np.int32)
+    sn, tn = np.ascontiguousarray(sn, np.float64), np.ascontiguousarray(tn, np.float64)
+    used = lib().orc_gicp_linearize(_p(src), _p(sn), C.c_int(src.shape[0]), _p(tgt), _p(tn), s.fn, s.ctx, C.byref(opts), _p(T), _p(acc), _p(idx))
+    return acc, idx, used
+
+
+def gicp_register(src, tgt, opts: OrcOpts, searcher=None, normals=None, dump=False):
+    """(T, result, (dump_pose, dump_acc) or None). Normals come from each cloud's own opts.k nearest neighbours."""
+    src, tgt = f4(src), f4(tgt)
+    s = searcher or BruteSearcher(tgt)
+    k = opts.k if opts.k > 0 else 20
+    sn, tn = normals if normals is not None else (gicp_normals(src, k), gicp_normals(tgt, k, searcher))
+    T = np.zeros(16, np.float64)
+    res = OrcResult()
+    it = opts.max_iterations
+    dp = np.zeros((it, 16), np.float64) if dump else None
+    da = np.zeros((it, ACC_LEN), np.float64) if dump else None
+    lib().orc_gicp_register.restype = C.c_int
+    rc = lib().orc_gicp_register(_p(src), _p(sn), C.c_int(src.shape[0]), _p(tgt), _p(tn), C.c_int(tgt.shape[0]), s.fn, s.ctx,
+                                 C.byref(opts), _p(T), C.byref(res), _p(dp), _p(da))
+    assert rc == 0
+    return T.reshape(4, 4), res, ((dp, da) if dump else None)
 
 
 # ---------------------------------------------------------------------------------------- small algebra

@@ -782,3 +782,234 @@ int orc_map_sector(const float* pts, const uint8_t* valid, int m, const float c[
     }
     return cnt;
 }
+
+/* ------------------------------------------------------------------ GICP (fast_gicp restatement) --- */
+
+/* eigenvector of the smallest eigenvalue of a symmetric 3x3 (cyclic Jacobi) */
+static void smallest_eigvec3(const double C[9], double n[3]) {
+    double A[9], V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    memcpy(A, C, sizeof(A));
+    for (int sweep = 0; sweep < 50; ++sweep) {
+        double off = fabs(A[1]) + fabs(A[2]) + fabs(A[5]);
+        if (off < 1e-300) break;
+        for (int p = 0; p < 2; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                const double apq = A[3 * p + q];
+                if (fabs(apq) < 1e-300) continue;
+                const double theta = (A[3 * q + q] - A[3 * p + p]) / (2.0 * apq);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < 3; ++k) { /* A <- A J */
+                    const double akp = A[3 * k + p], akq = A[3 * k + q];
+                    A[3 * k + p] = c * akp - s * akq;
+                    A[3 * k + q] = s * akp + c * akq;
+                }
+                for (int k = 0; k < 3; ++k) { /* A <- J^T A */
+                    const double apk = A[3 * p + k], aqk = A[3 * q + k];
+                    A[3 * p + k] = c * apk - s * aqk;
+                    A[3 * q + k] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < 3; ++k) {
+                    const double vkp = V[3 * k + p], vkq = V[3 * k + q];
+                    V[3 * k + p] = c * vkp - s * vkq;
+                    V[3 * k + q] = s * vkp + c * vkq;
+                }
+            }
+    }
+    int m = 0;
+    if (A[4] < A[4 * m]) m = 1;
+    if (A[8] < A[4 * m]) m = 2;
+    const double len = sqrt(V[m] * V[m] + V[3 + m] * V[3 + m] + V[6 + m] * V[6 + m]);
+    n[0] = V[m] / len;
+    n[1] = V[3 + m] / len;
+    n[2] = V[6 + m] / len;
+}
+
+void orc_gicp_normals(const float* pts, int n, orc_knn_fn knn, void* ctx, int k, double* out) {
+    int32_t* idx = (int32_t*)malloc(sizeof(int32_t) * (size_t)n * k);
+    float* d2 = (float*)malloc(sizeof(float) * (size_t)n * k);
+    int32_t* fnd = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
+    knn(ctx, pts, n, k, 0.0, idx, d2, fnd);
+    for (int i = 0; i < n; ++i) {
+        const int f = fnd[i];
+        double mean[3] = {0, 0, 0}, C[9] = {0};
+        for (int j = 0; j < f; ++j)
+            for (int a = 0; a < 3; ++a) mean[a] += pts[4 * (size_t)idx[(size_t)i * k + j] + a];
+        for (int a = 0; a < 3; ++a) mean[a] /= (f > 0 ? f : 1);
+        for (int j = 0; j < f; ++j) {
+            double d[3];
+            for (int a = 0; a < 3; ++a) d[a] = (double)pts[4 * (size_t)idx[(size_t)i * k + j] + a] - mean[a];
+            for (int a = 0; a < 3; ++a)
+                for (int b = 0; b < 3; ++b) C[3 * a + b] += d[a] * d[b];
+        }
+        for (int a = 0; a < 9; ++a) C[a] /= k; /* fast_gicp divides by k_correspondences_ */
+        smallest_eigvec3(C, out + 3 * (size_t)i);
+    }
+    free(idx);
+    free(d2);
+    free(fnd);
+}
+
+static int inv3(const double A[9], double Ai[9]) {
+    const double c00 = A[4] * A[8] - A[5] * A[7], c01 = A[5] * A[6] - A[3] * A[8], c02 = A[3] * A[7] - A[4] * A[6];
+    const double det = A[0] * c00 + A[1] * c01 + A[2] * c02;
+    if (!(fabs(det) > 0.0)) return 0;
+    Ai[0] = c00 / det;
+    Ai[1] = (A[2] * A[7] - A[1] * A[8]) / det;
+    Ai[2] = (A[1] * A[5] - A[2] * A[4]) / det;
+    Ai[3] = c01 / det;
+    Ai[4] = (A[0] * A[8] - A[2] * A[6]) / det;
+    Ai[5] = (A[2] * A[3] - A[0] * A[5]) / det;
+    Ai[6] = c02 / det;
+    Ai[7] = (A[1] * A[6] - A[0] * A[7]) / det;
+    Ai[8] = (A[0] * A[4] - A[1] * A[3]) / det;
+    return 1;
+}
+
+#define GICP_ALPHA 0.999 /* 1 - 1e-3: C = I - alpha n n^T */
+
+/* Mahalanobis matrix of one correspondence under rotation R (row-major 3x3 inside T) */
+static int gicp_mahalanobis(const double T[16], const double na[3], const double nb[3], double M[9]) {
+    double ra[3];
+    for (int i = 0; i < 3; ++i) ra[i] = T[4 * i] * na[0] + T[4 * i + 1] * na[1] + T[4 * i + 2] * na[2];
+    double RCR[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) RCR[3 * i + j] = (i == j ? 2.0 : 0.0) - GICP_ALPHA * (nb[i] * nb[j] + ra[i] * ra[j]);
+    return inv3(RCR, M);
+}
+
+int orc_gicp_linearize(const float* src, const double* sn, int n, const float* tgt, const double* tn, orc_knn_fn knn, void* ctx,
+                       const orc_opts* o, const double T[16], double acc[ORC_ACC_LEN], int32_t* idx_out) {
+    float* q = (float*)malloc(sizeof(float) * 4 * (size_t)n);
+    double* pw = (double*)malloc(sizeof(double) * 3 * (size_t)n);
+    int32_t* idx = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
+    float* d2 = (float*)malloc(sizeof(float) * (size_t)n);
+    int32_t* fnd = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
+    orc_transform(T, src, n, q, pw);
+    knn(ctx, q, n, 1, o->max_corr_dist, idx, d2, fnd);
+    memset(acc, 0, sizeof(double) * ORC_ACC_LEN);
+    int used = 0;
+    for (int i = 0; i < n; ++i) {
+        if (idx_out) idx_out[i] = fnd[i] > 0 ? idx[i] : -1;
+        if (fnd[i] < 1) continue;
+        const int j = idx[i];
+        double M[9];
+        if (!gicp_mahalanobis(T, sn + 3 * (size_t)i, tn + 3 * (size_t)j, M)) continue;
+        const double* a = pw + 3 * (size_t)i;
+        const double e[3] = {(double)tgt[4 * (size_t)j] - a[0], (double)tgt[4 * (size_t)j + 1] - a[1], (double)tgt[4 * (size_t)j + 2] - a[2]};
+        /* J = [skew(Ta) | -I] */
+        const double J[18] = {0, -a[2], a[1], -1, 0, 0, a[2], 0, -a[0], 0, -1, 0, -a[1], a[0], 0, 0, 0, -1};
+        double MJ[18], Me[3];
+        for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 6; ++c) MJ[6 * r + c] = M[3 * r] * J[c] + M[3 * r + 1] * J[6 + c] + M[3 * r + 2] * J[12 + c];
+            Me[r] = M[3 * r] * e[0] + M[3 * r + 1] * e[1] + M[3 * r + 2] * e[2];
+        }
+        int t = 0;
+        for (int r = 0; r < 6; ++r)
+            for (int c = r; c < 6; ++c) acc[t++] += J[r] * MJ[c] + J[6 + r] * MJ[6 + c] + J[12 + r] * MJ[12 + c];
+        for (int r = 0; r < 6; ++r) acc[21 + r] += J[r] * Me[0] + J[6 + r] * Me[1] + J[12 + r] * Me[2];
+        acc[27] += e[0] * Me[0] + e[1] * Me[1] + e[2] * Me[2];
+        acc[28] += 1.0;
+        ++used;
+    }
+    free(q);
+    free(pw);
+    free(idx);
+    free(d2);
+    free(fnd);
+    return used;
+}
+
+/* sum e^T M e with the correspondences and Mahalanobis matrices of the linearisation pose T_lin, at pose T */
+static double gicp_error(const float* src, const double* sn, int n, const float* tgt, const double* tn, const int32_t* idx,
+                         const double T_lin[16], const double T[16]) {
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) {
+        if (idx[i] < 0) continue;
+        const int j = idx[i];
+        double M[9], a[3];
+        if (!gicp_mahalanobis(T_lin, sn + 3 * (size_t)i, tn + 3 * (size_t)j, M)) continue;
+        xform1(T, src + 4 * (size_t)i, a);
+        const double e[3] = {(double)tgt[4 * (size_t)j] - a[0], (double)tgt[4 * (size_t)j + 1] - a[1], (double)tgt[4 * (size_t)j + 2] - a[2]};
+        for (int r = 0; r < 3; ++r) s += e[r] * (M[3 * r] * e[0] + M[3 * r + 1] * e[1] + M[3 * r + 2] * e[2]);
+    }
+    return s;
+}
+
+static int gicp_delta_converged(const double D[16], double rot_eps, double trans_eps) {
+    double m = 0.0;
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) {
+            const double v = fabs(D[4 * i + j] - (i == j ? 1.0 : 0.0)) / rot_eps;
+            if (v > m) m = v;
+        }
+        const double v = fabs(D[4 * i + 3]) / trans_eps;
+        if (v > m) m = v;
+    }
+    return m < 1.0;
+}
+
+int orc_gicp_register(const float* src, const double* sn, int n, const float* tgt, const double* tn, int m, orc_knn_fn knn, void* ctx,
+                      const orc_opts* o, double T_out[16], orc_result* res, double* dump_pose, double* dump_acc) {
+    (void)m;
+    double x0[16];
+    memcpy(x0, o->T0, sizeof(x0));
+    orc_result r;
+    memset(&r, 0, sizeof(r));
+    double lambda = -1.0;
+    int32_t* idx = (int32_t*)malloc(sizeof(int32_t) * (size_t)(n > 0 ? n : 1));
+    int it = 0, converged = 0, last_conv = 0;
+    for (; it < o->max_iterations && !converged; ++it) {
+        double acc[ORC_ACC_LEN];
+        if (dump_pose) memcpy(dump_pose + 16 * (size_t)it, x0, sizeof(x0));
+        r.n_corr = orc_gicp_linearize(src, sn, n, tgt, tn, knn, ctx, o, x0, acc, idx);
+        if (dump_acc) memcpy(dump_acc + ORC_ACC_LEN * (size_t)it, acc, sizeof(acc));
+        if (r.n_corr < 6) break;
+        const double y0 = acc[27];
+        r.last_cost = y0;
+        if (lambda < 0.0) {
+            double mx = 0.0;
+            for (int i = 0; i < 6; ++i) mx = fmax(mx, fabs(acc[tri(i, i)]));
+            lambda = 1e-9 * mx;
+        }
+        double nu = 2.0, D[16];
+        int stepped = 0;
+        for (int t = 0; t < 10; ++t) {
+            double Hl[21], d[6];
+            memcpy(Hl, acc, sizeof(Hl));
+            for (int i = 0; i < 6; ++i) Hl[tri(i, i)] += lambda;
+            if (orc_chol6_solve(Hl, acc + 21, d)) break;
+            orc_se3_exp(d, D);
+            double xi[16];
+            orc_mat4_mul(D, x0, xi);
+            const double yi = gicp_error(src, sn, n, tgt, tn, idx, x0, xi);
+            double den = 0.0;
+            for (int i = 0; i < 6; ++i) den += d[i] * (lambda * d[i] - acc[21 + i]);
+            const double rho = (y0 - yi) / den;
+            if (rho < 0) {
+                if (gicp_delta_converged(D, o->rot_eps, o->trans_eps)) {
+                    stepped = 1;
+                    break;
+                }
+                lambda = nu * lambda;
+                nu = 2 * nu;
+                continue;
+            }
+            memcpy(x0, xi, sizeof(x0));
+            const double f = 2 * rho - 1;
+            lambda = lambda * fmax(1.0 / 3.0, 1 - f * f * f);
+            stepped = 1;
+            break;
+        }
+        if (!stepped) break; /* "lm not converged!!" */
+        last_conv = gicp_delta_converged(D, o->rot_eps, o->trans_eps);
+        if (o->early_exit) converged = last_conv; /* early_exit = 0: run every iteration, report the last verdict */
+    }
+    r.converged = o->early_exit ? converged : (it >= o->max_iterations ? last_conv : 0);
+    r.iterations = it;
+    fitness_pass(src, n, knn, ctx, o->max_corr_dist, x0, &r);
+    memcpy(T_out, x0, sizeof(x0));
+    if (res) *res = r;
+    free(idx);
+    return 0;
+}

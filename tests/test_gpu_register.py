@@ -163,3 +163,33 @@ def test_transform_points(pkg, O, handle):
     got = handle.transform_points(Tgt, src)
     want, _ = O.transform(Tgt, src)
     assert (got.view(np.int32) == want.view(np.int32)).all()
+
+
+def test_gicp_matches_oracle(pkg, O, handle):
+    """fast_gicp cost (what radar_odometry.cpp:399-405 runs, k = 5): per-iteration H / g / cost at the GPU's own poses
+    against the oracle's independent formulation (explicit Mahalanobis inverse), correspondences bit-exact, final
+    pose within tolerance, same Levenberg-Marquardt trajectory (iterations, convergence flag)."""
+    src, tgt, _ = pkg.synth.frame_pair(5, 1500, 6000, extent=25.0)
+    sn, tn = O.gicp_normals(src, 5), O.gicp_normals(tgt, 5)
+    for early, iters in ((0, 8), (1, 64)):
+        o = pkg.default_opts(residual=pkg.GICP, k=5, max_iterations=iters, early_exit=early)
+        oo = O.default_opts(residual=O.GICP, k=5, max_iterations=iters, early_exit=early)
+        T, res, bufs = handle.register(src, tgt, o, dump=True)
+        To, ro, _ = O.gicp_register(src, tgt, oo, normals=(sn, tn))
+        assert (res.converged, res.iterations, res.n_corr) == (ro.converged, ro.iterations, ro.n_corr)
+        dp, da, di = bufs
+        for it in range(res.iterations):
+            acc, idx, used = O.gicp_linearize(src, sn, tgt, tn, oo, dp[it].reshape(4, 4))
+            assert (idx == di[it][:, 0]).all(), it
+            assert np.linalg.norm(da[it][:21] - acc[:21]) <= ACC_RTOL * np.linalg.norm(acc[:21]), it
+            assert np.linalg.norm(da[it][21:27] - acc[21:27]) <= ACC_RTOL * max(np.linalg.norm(acc[21:27]), 1e-9), it
+            assert abs(da[it][27] - acc[27]) <= ACC_RTOL * acc[27] and da[it][28] == acc[28]
+        et, er = pose_err(T, To)
+        assert et <= POSE_TOL_T and er <= POSE_TOL_R, (et, er)
+        assert abs(res.fitness - ro.fitness) <= 1e-6 * ro.fitness
+    # against the resident map as well (the scan-to-map call shape), normals cached on the map
+    handle.map_build(tgt)
+    o = pkg.default_opts(residual=pkg.GICP, k=5, max_iterations=64, early_exit=1)
+    T2, r2, _ = handle.register_map(src, o)
+    T3, r3, _ = handle.register_map(src, o)
+    assert np.array_equal(T2, T3) and np.abs(T2 - T).max() < 1e-12
