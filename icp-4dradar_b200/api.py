@@ -22,7 +22,7 @@ EXPORTS = [
     "icp4r_synchronize", "icp4r_launch_count", "icp4r_set_profiling", "icp4r_last_profile", "icp4r_map_build", "icp4r_map_set_downsample", "icp4r_map_add_points",
     "icp4r_map_size", "icp4r_map_range", "icp4r_map_knn", "icp4r_map_knn_brute", "icp4r_map_sector", "icp4r_map_points",
     "icp4r_register", "icp4r_register_map", "icp4r_register_batch", "icp4r_shard_unique_id", "icp4r_shard_init",
-    "icp4r_register_sharded", "icp4r_transform_points",
+    "icp4r_register_sharded", "icp4r_transform_points", "icp4r_doppler_filter",
 ]
 
 
@@ -50,6 +50,15 @@ class Result(C.Structure):
         ("fitness", C.c_double),
         ("last_cost", C.c_double),
     ]
+
+
+class DopplerOpts(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("reserved", C.c_int32), ("seed", C.c_uint64), ("sigma", C.c_double), ("split", C.c_double)]
+
+
+class DopplerResult(C.Structure):
+    _fields_ = [("A", C.c_double), ("b", C.c_double), ("score", C.c_double), ("velocity", C.c_double * 3), ("n_static", C.c_int32),
+                ("best_iteration", C.c_int32)]
 
 
 class Dump(C.Structure):
@@ -331,6 +340,21 @@ class Icp4r:
         self._ck(self.lib.icp4r_register_sharded(self.h, ps, C.c_int32(src.shape[0]), C.c_int(mem), C.byref(opts), C.c_int(axis),
                                                  C.c_float(slab_lo), C.c_float(slab_hi), C.c_void_p(T.ctypes.data), C.byref(res)))
         return T.reshape(4, 4), res
+
+    # ---- Doppler filter
+    def doppler_filter(self, records, iterations: int = 0, seed: int = 1, sigma: float = 0.5, split: float = 0.2):
+        """records: [n,5] x,y,z,intensity,v_r (numpy or CUDA tensor). Returns (static_mask uint8 [n], DopplerResult)."""
+        if isinstance(records, np.ndarray):
+            records = np.ascontiguousarray(records, np.float32)
+            mask = np.zeros(records.shape[0], np.uint8)
+        else:
+            import torch
+            mask = torch.zeros(records.shape[0], dtype=torch.uint8, device=records.device)
+        p, mem = _ptr(records)
+        o = DopplerOpts(iterations, 0, seed, sigma, split)
+        r = DopplerResult()
+        self._ck(self.lib.icp4r_doppler_filter(self.h, p, C.c_int32(records.shape[0]), C.c_int(mem), C.byref(o), _ptr(mask)[0], C.byref(r)))
+        return mask, r
 
     # ---- helpers
     def transform_points(self, T, pts):

@@ -537,6 +537,29 @@ int icp4r_register_sharded(icp4r_handle h, const float* src, int32_t n, int mem,
     return register_against_map(c, c->map, static_cast<const float4*>(dsrc), n, opts, axis, slab_lo, slab_hi, T_out, res, nullptr);
 }
 
+// ---- Doppler filter ---------------------------------------------------------------------------------------------
+
+int icp4r_doppler_filter(icp4r_handle h, const float* xyziv, int32_t n, int mem, const icp4r_doppler_opts* opts, uint8_t* static_mask,
+                         icp4r_doppler_result* res) {
+    HCHECK(h);
+    if (!opts || !res || n < 0 || (n > 0 && !xyziv) || bad_mem(mem)) return fail(c, ICP4R_ERR_INVALID, "icp4r_doppler_filter: bad arguments");
+    const void* drec;
+    CKS(stage_in(c, c->d_src, xyziv, (size_t)n * 5 * sizeof(float), mem, &drec));
+    uint8_t* dmask = static_mask;
+    if (mem == ICP4R_HOST && static_mask) {
+        CKS(reserve(c, c->d_found, (size_t)std::max(n, 1)));
+        dmask = c->d_found.as<uint8_t>();
+    }
+    static_assert(sizeof(icp4r_doppler_result) == 56, "icp4r_doppler_result layout");
+    CKS(doppler_filter(c, static_cast<const float*>(drec), n, opts->iterations, opts->seed, opts->sigma, opts->split, dmask, c->h_pinned));
+    std::memcpy(res, c->h_pinned, sizeof(icp4r_doppler_result));
+    if (mem == ICP4R_HOST && static_mask && n > 0) {
+        CK(cudaMemcpyAsync(static_mask, dmask, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return ICP4R_OK;
+}
+
 // ---- helpers ------------------------------------------------------------------------------------------------
 
 }  // extern "C"

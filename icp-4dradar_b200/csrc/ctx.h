@@ -198,6 +198,10 @@ int register_batch(Ctx* c, const float4* d_src, const int32_t* d_soff, const flo
 int gicp_normals(Ctx* c, Map& mp, int k);  // fills mp.normals for every valid point of mp (cached per k)
 int gicp_lm_step(Ctx* c, const RegParams* d_prm, RegState* d_st, int iter);
 
+// doppler.cu
+int doppler_filter(Ctx* c, const float* d_rec, int n, int iterations, uint64_t seed, double sigma, double split, uint8_t* d_mask,
+                   void* out_host);
+
 // shard.cu
 int shard_allreduce(Ctx* c, double* d_buf, int count);
 

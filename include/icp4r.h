@@ -166,6 +166,26 @@ int icp4r_shard_init(icp4r_handle h, const char id[128], int rank, int world);
 int icp4r_register_sharded(icp4r_handle h, const float* src_xyzw, int32_t n, int mem, const icp4r_opts* opts,
                            int axis, float slab_lo, float slab_hi, double T_out[16], icp4r_result* res);
 
+/* ---- Doppler static-point filter (next to the path: the step before registration in icp4radar) -------------------- */
+/* records: n x 5 floats x, y, z, intensity, v_r (the reference's .bin layout, iterative_closest_point.cpp:373-377).
+ * Two-point sine-model RANSAC (fitSineRansac, :85-128), static/dynamic split by the signed residual (:392-403) and
+ * least-squares ego velocity over the static points (:412-427). iterations <= 0 -> 0.2 * n (:389). */
+typedef struct icp4r_doppler_opts {
+    int32_t iterations;
+    int32_t reserved;
+    uint64_t seed;     /* sample indices come from a counter-based generator (the reference: unseeded random_device) */
+    double sigma;      /* inlier band of the RANSAC score, reference default 0.5 */
+    double split;      /* dynamic if residual > split, reference 0.2 */
+} icp4r_doppler_opts;
+typedef struct icp4r_doppler_result {
+    double A, b, score;   /* best model v_r cos(beta) = A cos(alpha + b) and its inlier count */
+    double velocity[3];
+    int32_t n_static;
+    int32_t best_iteration;
+} icp4r_doppler_result;
+int icp4r_doppler_filter(icp4r_handle h, const float* xyziv, int32_t n, int mem, const icp4r_doppler_opts* opts,
+                         uint8_t* static_mask, icp4r_doppler_result* res);
+
 /* ---- helpers on the path ----------------------------------------------------------------------------- */
 /* p' = R p + t in double, written back as float (pointAssociateToMap, radar_odometry.cpp:137-145) */
 int icp4r_transform_points(icp4r_handle h, const double T[16], const float* xyzw, int32_t n, int mem,

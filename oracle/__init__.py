@@ -315,6 +315,23 @@ def gicp_register(src, tgt, opts: OrcOpts, searcher=None, normals=None, dump=Fal
     return T.reshape(4, 4), res, ((dp, da) if dump else None)
 
 
+# ---------------------------------------------------------------------------------------- Doppler filter
+
+class OrcDopplerOut(C.Structure):
+    _fields_ = [("A", C.c_double), ("b", C.c_double), ("score", C.c_double), ("v", C.c_double * 3), ("n_static", C.c_int),
+                ("best_iteration", C.c_int)]
+
+
+def doppler_filter(records, iterations=0, seed=1, sigma=0.5, split=0.2):
+    rec = np.ascontiguousarray(records, np.float32)
+    assert rec.ndim == 2 and rec.shape[1] == 5
+    mask = np.zeros(rec.shape[0], np.uint8)
+    out = OrcDopplerOut()
+    lib().orc_doppler_filter(_p(rec), C.c_int(rec.shape[0]), C.c_int(iterations), C.c_uint64(seed), C.c_double(sigma), C.c_double(split),
+                             _p(mask), C.byref(out))
+    return mask, out
+
+
 # ---------------------------------------------------------------------------------------- small algebra
 
 def svd3_rotation(H):

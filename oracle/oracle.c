@@ -1013,3 +1013,88 @@ int orc_gicp_register(const float* src, const double* sn, int n, const float* tg
     free(idx);
     return 0;
 }
+
+/* ------------------------------------------------------------------ Doppler filter ----------------- */
+
+static inline uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+#define ORC_DEG2RAD(x) ((x) * 0.017453293) /* pcl_macros.h, as used at iterative_closest_point.cpp:106-108 */
+
+int orc_doppler_filter(const float* rec, int n, int iterations, uint64_t seed, double sigma, double split, uint8_t* mask,
+                       orc_doppler_out* out) {
+    memset(out, 0, sizeof(*out));
+    out->best_iteration = -1;
+    if (n <= 0) return 0;
+    if (iterations <= 0) iterations = (int)(n * 0.2); /* fitSineRansac(..., PointsNum * 0.2), :389 */
+    float* arfa = (float*)malloc(sizeof(float) * (size_t)n);
+    float* beta = (float*)malloc(sizeof(float) * (size_t)n);
+    for (int i = 0; i < n; ++i) {
+        const float x = rec[5 * (size_t)i], y = rec[5 * (size_t)i + 1], z = rec[5 * (size_t)i + 2];
+        const float dist = sqrtf(x * x + y * y + z * z);                              /* :378-379 */
+        arfa[i] = (float)((double)((float)atan2((double)y, (double)x) * 180) / M_PI);  /* :382 */
+        beta[i] = (float)((double)((float)asin((double)(z / dist)) * 180) / M_PI);     /* :383 */
+    }
+    int* scores = (int*)malloc(sizeof(int) * (size_t)iterations);
+    double* As = (double*)malloc(sizeof(double) * (size_t)iterations);
+    double* bs = (double*)malloc(sizeof(double) * (size_t)iterations);
+#pragma omp parallel for schedule(dynamic, 8)
+    for (int it = 0; it < iterations; ++it) {
+        const int i1 = (int)(splitmix64(seed + 2ull * (uint64_t)it) % (uint64_t)n);
+        const int i2 = (int)(splitmix64(seed + 2ull * (uint64_t)it + 1ull) % (uint64_t)n);
+        const double v1 = rec[5 * (size_t)i1 + 4], v2 = rec[5 * (size_t)i2 + 4];
+        const double k = (v1 * cos(ORC_DEG2RAD(beta[i1]))) / (v2 * cos(ORC_DEG2RAD(beta[i2])));
+        const double b = atan((cos(ORC_DEG2RAD(arfa[i1])) - k * cos(ORC_DEG2RAD(arfa[i2]))) /
+                              (sin(ORC_DEG2RAD(arfa[i1])) - k * sin(ORC_DEG2RAD(arfa[i2]))));
+        const double A = cos(ORC_DEG2RAD(beta[i1])) * v1 / cos((ORC_DEG2RAD(arfa[i1])) + b);
+        int sc = 0;
+        for (int j = 0; j < n; ++j) {
+            const double delta = (cos(ORC_DEG2RAD(beta[j])) * (double)rec[5 * (size_t)j + 4]) - (A * cos(ORC_DEG2RAD(arfa[j]) + b));
+            if (fabs(delta) < sigma) ++sc;
+        }
+        scores[it] = sc;
+        As[it] = A;
+        bs[it] = b;
+    }
+    int best = -1, best_sc = 0;
+    for (int it = 0; it < iterations; ++it)
+        if (scores[it] > best_sc) { /* strict: the first maximum wins, :120 */
+            best_sc = scores[it];
+            best = it;
+        }
+    const double A = best >= 0 ? As[best] : 0.0, b = best >= 0 ? bs[best] : 0.0; /* reference leaves A = b = 0 when nothing scores */
+    out->A = A;
+    out->b = b;
+    out->score = best_sc;
+    out->best_iteration = best;
+    double KK[6] = {0, 0, 0, 0, 0, 0}, Kv[3] = {0, 0, 0};
+    int ns = 0;
+    for (int j = 0; j < n; ++j) {
+        const double vr = rec[5 * (size_t)j + 4];
+        const double delta = (cos(ORC_DEG2RAD(beta[j])) * vr) - (A * cos(ORC_DEG2RAD(arfa[j]) + b));
+        const int is_static = !(delta > split); /* :394-403 */
+        if (mask) mask[j] = (uint8_t)is_static;
+        if (!is_static) continue;
+        ++ns;
+        const double k0 = cos(ORC_DEG2RAD(arfa[j])) * cos(ORC_DEG2RAD(beta[j]));
+        const double k1 = sin(ORC_DEG2RAD(arfa[j])) * cos(ORC_DEG2RAD(beta[j]));
+        const double k2 = sin(ORC_DEG2RAD(beta[j]));
+        KK[0] += k0 * k0; KK[1] += k0 * k1; KK[2] += k0 * k2; KK[3] += k1 * k1; KK[4] += k1 * k2; KK[5] += k2 * k2;
+        Kv[0] += k0 * vr; Kv[1] += k1 * vr; Kv[2] += k2 * vr;
+    }
+    out->n_static = ns;
+    const double M[9] = {KK[0], KK[1], KK[2], KK[1], KK[3], KK[4], KK[2], KK[4], KK[5]};
+    double Mi[9];
+    if (ns >= 3 && inv3(M, Mi))
+        for (int a = 0; a < 3; ++a) out->v[a] = Mi[3 * a] * Kv[0] + Mi[3 * a + 1] * Kv[1] + Mi[3 * a + 2] * Kv[2];
+    free(arfa);
+    free(beta);
+    free(scores);
+    free(As);
+    free(bs);
+    return 0;
+}
