@@ -65,19 +65,34 @@ __device__ __forceinline__ uint64_t thread_grid_nn(const PairGrid& g, const floa
         hiz = cell_of_s(qz + gr, g.oz, g.inv_cell, g.nz);
     }
     const int rneed = max(max(max(cx - lox, hix - cx), max(cy - loy, hiy - cy)), max(cz - loz, hiz - cz));
-    uint64_t best = KEY_EMPTY;
+    float best_d = INFINITY;   // running best (d2, index): compared as floats first, the packed key is built at the end
+    int best_i = 0x7fffffff;
     best_pos = -1;
     int prev = -1;
     for (int R = min(1, rneed); R <= rneed; ++R) {
         const int z0 = max(cz - R, loz), z1 = min(cz + R, hiz);
         const int y0 = max(cy - R, loy), y1 = min(cy + R, hiy);
-        const int xa = max(cx - R, lox), xb = min(cx + R, hix);
         for (int z = z0; z <= z1; ++z)
             for (int y = y0; y <= y1; ++y) {
+                int xa = max(cx - R, lox), xb = min(cx + R, hix);
+                if (best_pos >= 0) {
+                    // the running best prunes whole rows and the x-extent of the others (strictly farther cells only,
+                    // so a tie with a lower index can never be skipped)
+                    const int dy = y - cy, dz = z - cz;
+                    float ddy = dy > 0 ? (g.oy + (float)y * g.cell) - qy : (dy < 0 ? qy - (g.oy + (float)(y + 1) * g.cell) : 0.0f);
+                    float ddz = dz > 0 ? (g.oz + (float)z * g.cell) - qz : (dz < 0 ? qz - (g.oz + (float)(z + 1) * g.cell) : 0.0f);
+                    ddy = fmaxf(ddy - margin, 0.0f);
+                    ddz = fmaxf(ddz - margin, 0.0f);
+                    const float dyz2 = (ddy * ddy + ddz * ddz) * 0.999999f;
+                    const float kd = best_d * 1.000001f;
+                    if (dyz2 > kd) continue;
+                    const float xr = sqrtf(kd - dyz2) * 1.000001f + margin;
+                    xa = max(xa, cell_of_s(qx - xr, g.ox, g.inv_cell, g.nx));
+                    xb = min(xb, cell_of_s(qx + xr, g.ox, g.inv_cell, g.nx));
+                }
                 const int rowbase = (z * g.ny + y) * g.nx;
                 const bool fresh = max(abs(y - cy), abs(z - cz)) > prev;
-                // a fresh row is one range; an old row contributes its two end caps
-                const int nseg = fresh ? 1 : 2;
+                const int nseg = fresh ? 1 : 2;  // a fresh row is one range; an old row contributes its two end caps
                 for (int sgi = 0; sgi < nseg; ++sgi) {
                     int a, b;
                     if (fresh) {
@@ -85,9 +100,9 @@ __device__ __forceinline__ uint64_t thread_grid_nn(const PairGrid& g, const floa
                         b = xb;
                     } else if (sgi == 0) {
                         a = xa;
-                        b = min(cx - prev - 1, hix);
+                        b = min(cx - prev - 1, xb);
                     } else {
-                        a = max(cx + prev + 1, lox);
+                        a = max(cx + prev + 1, xa);
                         b = xb;
                     }
                     if (a > b) continue;
@@ -95,10 +110,11 @@ __device__ __forceinline__ uint64_t thread_grid_nn(const PairGrid& g, const floa
                     for (uint32_t j = s; j < e; ++j) {
                         const float4 c = s_tgt[j];
                         const float d = dist2_exact(qx, qy, qz, c.x, c.y, c.z);
-                        if (d <= gate_f) {
-                            const uint64_t key = pack_key(d, __float_as_int(c.w));
-                            if (key < best) {
-                                best = key;
+                        if (d <= best_d && d <= gate_f) {  // false for NaN
+                            const int ci = __float_as_int(c.w);
+                            if (d < best_d || ci < best_i) {
+                                best_d = d;
+                                best_i = ci;
                                 best_pos = (int)j;
                             }
                         }
@@ -115,8 +131,9 @@ __device__ __forceinline__ uint64_t thread_grid_nn(const PairGrid& g, const floa
         if (cz + R < hiz) bound = fminf(bound, (g.oz + (float)(cz + R + 1) * g.cell) - qz);
         if (bound > 3.0e38f) break;
         const float b = bound - margin;
-        if (b > 0.0f && best != KEY_EMPTY && key_d2(best) < b * b * 0.99999905f) break;
+        if (b > 0.0f && best_pos >= 0 && best_d < b * b * 0.99999905f) break;
     }
+    const uint64_t best = best_pos >= 0 ? pack_key(best_d, best_i) : KEY_EMPTY;
     return best;
 }
 
@@ -146,7 +163,8 @@ __global__ void __launch_bounds__(RB_THREADS, 2) reg_batch_kernel(const __grid_c
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* s_tgt = reinterpret_cast<float4*>(smem_raw);
     float4* s_src = s_tgt + P.max_m;
-    uint32_t* s_cs = reinterpret_cast<uint32_t*>(s_src + P.max_n);  // [RB_MAXC + 2]
+    uint32_t* s_cs = reinterpret_cast<uint32_t*>(s_src + P.max_n);  // [RB_MAXC + 2] target cell table
+    uint32_t* s_cq = s_cs + (RB_MAXC + 2);                          // [RB_MAXC + 2] source cell cursors (spatial sort)
     __shared__ double s_red[RB_WARPS * 32];
     __shared__ double s_tot[32];
     __shared__ double s_T[16];
@@ -166,8 +184,7 @@ __global__ void __launch_bounds__(RB_THREADS, 2) reg_batch_kernel(const __grid_c
         const float4* __restrict__ gtgt = P.tgt + to;
         __syncthreads();  // previous pair fully consumed
 
-        // ---- stage the source; bounding box of the target --------------------------------------------
-        for (int i = tid; i < n; i += RB_THREADS) s_src[i] = __ldg(gsrc + i);
+        // ---- bounding box of the target ------------------------------------------------------------------
         float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
         for (int j = tid; j < m; j += RB_THREADS) {
             const float4 p = __ldg(gtgt + j);
@@ -240,27 +257,37 @@ __global__ void __launch_bounds__(RB_THREADS, 2) reg_batch_kernel(const __grid_c
             s_misc[1] = 0.0;
         }
         if (tid < 16) s_T[tid] = P.T0[tid];
-        for (int c0 = tid; c0 < RB_MAXC + 2; c0 += RB_THREADS) s_cs[c0] = 0;
+        for (int c0 = tid; c0 < 2 * (RB_MAXC + 2); c0 += RB_THREADS) s_cs[c0] = 0;  // both tables
         __syncthreads();
         const PairGrid g = s_g;
 
-        // ---- counting sort of the target into cell order (shared memory) ----------------------------
+        // ---- counting sorts into cell order (shared memory): the target (this IS the search structure) and the
+        //      source, by the cell its initially-transformed position falls in, so that the 32 queries of a warp
+        //      are spatial neighbours: same rows, similar trip counts, broadcast shared-memory reads
+        auto tgt_cell = [&](const float4& p) {
+            return (cell_of_s(p.z, g.oz, g.inv_cell, g.nz) * g.ny + cell_of_s(p.y, g.oy, g.inv_cell, g.ny)) * g.nx +
+                   cell_of_s(p.x, g.ox, g.inv_cell, g.nx);
+        };
+        auto src_cell = [&](const float4& p) {
+            double pw[3];
+            xform_point(s_T, p.x, p.y, p.z, pw);
+            return (cell_of_s((float)pw[2], g.oz, g.inv_cell, g.nz) * g.ny + cell_of_s((float)pw[1], g.oy, g.inv_cell, g.ny)) * g.nx +
+                   cell_of_s((float)pw[0], g.ox, g.inv_cell, g.nx);
+        };
         for (int j = tid; j < m; j += RB_THREADS) {
             const float4 p = __ldg(gtgt + j);
-            if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
-                const int c0 = (cell_of_s(p.z, g.oz, g.inv_cell, g.nz) * g.ny + cell_of_s(p.y, g.oy, g.inv_cell, g.ny)) * g.nx +
-                               cell_of_s(p.x, g.ox, g.inv_cell, g.nx);
-                atomicAdd(&s_cs[c0 + 1], 1u);
-            }
+            if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) atomicAdd(&s_cs[tgt_cell(p) + 1], 1u);
         }
+        for (int i = tid; i < n; i += RB_THREADS) atomicAdd(&s_cq[src_cell(__ldg(gsrc + i)) + 1], 1u);
         __syncthreads();
-        {   // s_cs[c+1] <- exclusive prefix of the counts (becomes the running cursor of cell c)
+        for (int which = 0; which < 2; ++which) {  // table[c+1] <- exclusive prefix of the counts (the running cursor of cell c)
+            uint32_t* tab = which ? s_cq : s_cs;
             constexpr int PER = (RB_MAXC + RB_THREADS - 1) / RB_THREADS;
             uint32_t v[PER], sum = 0;
 #pragma unroll
             for (int t = 0; t < PER; ++t) {
                 const int c0 = tid * PER + t;
-                v[t] = c0 < RB_MAXC ? s_cs[c0 + 1] : 0u;
+                v[t] = c0 < RB_MAXC ? tab[c0 + 1] : 0u;
                 sum += v[t];
             }
             uint32_t x = sum;
@@ -276,21 +303,24 @@ __global__ void __launch_bounds__(RB_THREADS, 2) reg_batch_kernel(const __grid_c
 #pragma unroll
             for (int t = 0; t < PER; ++t) {
                 const int c0 = tid * PER + t;
-                if (c0 < RB_MAXC) s_cs[c0 + 1] = base;
+                if (c0 < RB_MAXC) tab[c0 + 1] = base;
                 base += v[t];
             }
+            __syncthreads();
         }
-        __syncthreads();
         for (int j = tid; j < m; j += RB_THREADS) {
             const float4 p = __ldg(gtgt + j);
             if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
-                const int c0 = (cell_of_s(p.z, g.oz, g.inv_cell, g.nz) * g.ny + cell_of_s(p.y, g.oy, g.inv_cell, g.ny)) * g.nx +
-                               cell_of_s(p.x, g.ox, g.inv_cell, g.nx);
-                const uint32_t pos = atomicAdd(&s_cs[c0 + 1], 1u);
+                const uint32_t pos = atomicAdd(&s_cs[tgt_cell(p) + 1], 1u);
                 s_tgt[pos] = make_float4(p.x, p.y, p.z, __int_as_float(j));
             }
         }
-        __syncthreads();  // now s_cs[c] = start of cell c, s_cs[c+1] = its end
+        for (int i = tid; i < n; i += RB_THREADS) {
+            const float4 p = __ldg(gsrc + i);
+            const uint32_t pos = atomicAdd(&s_cq[src_cell(p) + 1], 1u);
+            s_src[pos] = p;
+        }
+        __syncthreads();  // now s_cs[c] = start of target cell c, s_cs[c+1] = its end
 
         // ---- iterations ---------------------------------------------------------------------------------
         for (int it = 0; it < P.max_iterations; ++it) {
@@ -426,7 +456,7 @@ int register_batch(Ctx* c, const float4* d_src, const int32_t* d_soff, const flo
     if (n_pairs <= 0) return ICP4R_OK;
     if (o->residual != ICP4R_P2P_SVD && o->residual != ICP4R_P2P_GN)
         return fail(c, ICP4R_ERR_UNSUPPORTED, "batched registration supports P2P_SVD and P2P_GN (got %d)", o->residual);
-    const size_t smem = (size_t)(std::max(max_m, 1) + std::max(max_n, 1)) * sizeof(float4) + (RB_MAXC + 2) * sizeof(uint32_t);
+    const size_t smem = (size_t)(std::max(max_m, 1) + std::max(max_n, 1)) * sizeof(float4) + 2 * (RB_MAXC + 2) * sizeof(uint32_t);
     if (smem > 200 * 1024)
         return fail(c, ICP4R_ERR_UNSUPPORTED, "pair too large for the shared-memory resident kernel (%zu B); use icp4r_register", smem);
     BatchParams P;
