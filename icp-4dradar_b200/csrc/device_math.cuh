@@ -307,15 +307,20 @@ __device__ __forceinline__ bool plane_fit(const F (&P)[K][3], int k, double n[3]
     const double c11 = m00 * m22 - m02 * m02, c12 = m01 * m02 - m00 * m12, c22 = m00 * m11 - m01 * m01;
     const double det = (m00 * c00 + m01 * c01) + m02 * c02;
     if (!(fabs(det) > 0.0) || !isfinite(det)) return false;
-    const double nx = ((c00 * v0 + c01 * v1) + c02 * v2) / det;
-    const double ny = ((c01 * v0 + c11 * v1) + c12 * v2) / det;
-    const double nz = ((c02 * v0 + c12 * v1) + c22 * v2) / det;
-    const double nn = sqrt((nx * nx + ny * ny) + nz * nz);
-    if (!(nn > 0.0) || !isfinite(nn)) return false;
-    d = 1.0 / nn;
-    n[0] = nx / nn;
-    n[1] = ny / nn;
-    n[2] = nz / nn;
+    // n = adj(M) v / det, then n /= |n|, d = 1 / |n|. The common factor 1/det cancels in the direction, so the
+    // three divisions by det and the three by |n| collapse into one reciprocal square root and one reciprocal
+    // (this runs once per source point per iteration, redundantly on every lane of the warp).
+    const double ux = (c00 * v0 + c01 * v1) + c02 * v2;
+    const double uy = (c01 * v0 + c11 * v1) + c12 * v2;
+    const double uz = (c02 * v0 + c12 * v1) + c22 * v2;
+    const double uu = (ux * ux + uy * uy) + uz * uz;
+    if (!(uu > 0.0) || !isfinite(uu)) return false;
+    const double iu = rsqrt(uu);                 // 1 / |u|
+    const double sgn = det > 0.0 ? 1.0 : -1.0;   // n = u / det / |u / det| = sign(det) u / |u|
+    n[0] = sgn * ux * iu;
+    n[1] = sgn * uy * iu;
+    n[2] = sgn * uz * iu;
+    d = fabs(det) * iu;                          // 1 / |u / det|
     return true;
 }
 

@@ -135,13 +135,15 @@ __device__ __forceinline__ uint64_t warp_grid_knn(const GridDesc& g, WarpSegs& s
     for (int R = R0; R <= rneed && R <= GRID_RING_CAP; ++R) {
         // rows (dy, dz) of the shell, 32 at a time: each lane fetches the cell ranges of one row
         const int side = 2 * R + 1, rows = side * side;
+        const float inv_side = 1.0f / (float)side;  // r / side without an integer division (exact for these small r)
         const bool prune = kth != KEY_EMPTY;
         const float kd = key_d2(kth) * 1.000001f;  // inflated: a pruned cell can not even hold a tie
         for (int rb = 0; rb < rows; rb += 32) {
             const int r = rb + lane;
             uint32_t s0 = 0, e0 = 0, s1 = 0, e1 = 0;
             if (r < rows) {
-                const int dy = r % side - R, dz = r / side - R;
+                const int rz = (int)(((float)r + 0.5f) * inv_side);
+                const int dy = r - rz * side - R, dz = rz - R;
                 const int y = cy + dy, z = cz + dz;
                 if (y >= loy && y <= hiy && z >= loz && z <= hiz) {
                     int xa = max(cx - R, lox), xb = min(cx + R, hix);
