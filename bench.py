@@ -57,6 +57,25 @@ def make_c2(seed=1002):
     return mp, scans
 
 
+C5_N, C5_ITERS = 16384, 20
+
+
+def make_c5(m, seed=1005):
+    """C5: dense map, uniform volume density over 400 x 400 x 20 m (6.25 pts/m^3 at 20 M), and a 16,384-pt scan drawn
+    from the map's own surfaces (a random subset + 2 cm noise) moved by a small rigid transform."""
+    from icp4r_loader import pkg
+    s = pkg.synth
+    mp = s.dense_map(seed, m)
+    rng = np.random.default_rng(seed + 1)
+    scans = []
+    for i in range(4):
+        sel = rng.choice(m, C5_N, replace=False)
+        w = mp[sel].copy()
+        w[:, :3] += rng.normal(0, 0.02, (C5_N, 3)).astype(np.float32)
+        scans.append(np.ascontiguousarray(s.apply(np.linalg.inv(s.random_small_se3(rng, 0.3, 1.0)), w)))
+    return mp, scans
+
+
 def make_c4(n_pairs, seed=1004):
     """n_pairs frame pairs of 2,048 points: 64 distinct scenes, each re-used with a different rigid offset of the
     source (generating 65,536 scenes on the host would dominate the run)."""
@@ -200,7 +219,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c4"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"])
+    ap.add_argument("--map-points", type=int, default=20_000_000, help="c5: points of the dense map (whole job)")
     ap.add_argument("--pairs", type=int, default=65536, help="c4: frame pairs per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -262,6 +282,34 @@ def main():
         cfg = {"workload": "C2 scan-to-map: 4096-pt scan vs resident 200000-pt map, P2PLANE k=5, 20 iters, gate 2.0 m",
                "n": N_SCAN, "m": N_MAP, "k": K_NN, "iterations": ITERS, "max_corr_dist": GATE, "scan_pool": POOL,
                "l2": "flushed before every timed step (256 MiB fill, untimed)", "replicas": world}
+    elif args.workload == "c5":
+        # one map split in spatial slabs along x (halo = gate) across the ranks; every rank gets the same scan; the 29
+        # accumulators are all-reduced (NCCL inside libicp4r_cuda) every iteration. N = 1: the whole map on one GPU.
+        mp, scans = make_c5(args.map_points)
+        o = pkg.default_opts(residual=pkg.P2PLANE_KNN, k=K_NN, max_iterations=C5_ITERS, max_corr_dist=GATE)
+        if world > 1:
+            bounds = pkg.shard.slab_bounds(mp[:, 0], world)
+            mine, lo, hi, _ = pkg.shard.slab_of_rank(mp, rank, world, axis=0, halo=GATE, bounds=bounds)
+            uid = [pkg.Icp4r.shard_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            h.shard_init(uid[0], rank, world)
+            h.map_build(torch.from_numpy(mine).to(dev))
+            step_dev = lambda i: h.register_sharded(d_scans[i % 4], o, 0, lo, hi)
+            step_e2e = lambda i: h.register_sharded(h_scans[i % 4], o, 0, lo, hi)
+        else:
+            h.map_build(torch.from_numpy(mp).to(dev))
+            step_dev = lambda i: h.register_map(d_scans[i % 4], o)
+            step_e2e = lambda i: h.register_map(h_scans[i % 4], o)
+        d_scans = [torch.from_numpy(s).to(dev) for s in scans]
+        pinned = [torch.from_numpy(s).pin_memory() for s in scans]
+        h_scans = [p.numpy() for p in pinned]
+        units_per_step = 1.0 / world   # ONE registration per step for the whole job (strong scaling)
+        queries_per_unit = C5_ITERS * C5_N
+        h2d, d2h = C5_N * 16, 16 * 8 + 32
+        cfg = {"workload": f"C5 large-map registration: 16384-pt scan vs {args.map_points}-pt dense map in {world} x-slab(s), P2PLANE k=5, 20 iters, gate 2.0 m",
+               "n": C5_N, "m": args.map_points, "k": K_NN, "iterations": C5_ITERS, "max_corr_dist": GATE, "slabs": world,
+               "collective": "29-double NCCL all-reduce per iteration" if world > 1 else "none",
+               "l2": "flushed before every timed step (256 MiB fill, untimed)"}
     else:
         src, tgt, off = make_c4(args.pairs)
         o = pkg.default_opts(residual=pkg.P2P_SVD, max_iterations=C4_ITERS)
@@ -306,7 +354,8 @@ def main():
     if rank == 0:
         line = {
             "metric": "registrations/s", "value": value, "unit": "registrations/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if args.workload == "c5" else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
             "nn_queries_per_s": value * queries_per_unit,
             "e2e": {"value": e2e_value, "unit": "registrations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -339,6 +388,8 @@ def main():
                                 "kernel": "reg_iter_kernel<P2PLANE_KNN,5>", "kernel_ms": k_ms, "algorithmic_bytes": alg, "m_r": m_r,
                                 "peak_source": peak_src,
                                 "note": "working set (3.3 MB) is L2-resident: the kernel is latency-bound, see DESIGN.md"}
+        elif args.workload == "c5":
+            line["roofline"] = None
         else:
             alg = args.pairs * (16 * 2 * C4_N + 64 + 160)
             k_ms = total_ms / args.steps
@@ -354,7 +405,7 @@ def main():
             v = len(times) / float(np.sum(times))
             line["cpu_baseline"] = {"value": v, "unit": "registrations/s", "cores": threads, "kind": kind,
                                     "sample": f"{len(times)} registrations of the same workload (~15 s); ikd-Tree Build excluded"}
-        elif world == 1 and not args.no_cpu_baseline:
+        elif world == 1 and not args.no_cpu_baseline and args.workload == "c4":
             import oracle as O
             oo = O.default_opts(residual=O.P2P_SVD, max_iterations=C4_ITERS)
             t0 = time.perf_counter()

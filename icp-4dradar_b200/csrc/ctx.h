@@ -151,6 +151,9 @@ struct Ctx {
     size_t h_pinned_cap = 0;
 
     std::map<GraphKey, cudaGraphExec_t> graphs;
+    std::map<GraphKey, int64_t> graph_launch_counts;
+    int64_t graph_launches = 0;
+    bool no_graph_sharded = false;
     const GridDesc* graph_grid_owner = nullptr;  // graphs bake the grid by value: identity of what they baked
     GridDesc graph_grid_copy{};
     const void* graph_pts = nullptr;

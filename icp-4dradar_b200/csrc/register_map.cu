@@ -636,82 +636,97 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
     const float4* pts = mp.pts.as<float4>();
     const int iters = o->max_iterations;
 
-    if (gicp) {
-        // linearise (grid-wide, accumulators left in st->acc) then one single-block Levenberg-Marquardt step
-        for (int it = 0; it < iters; ++it) {
-            dispatch_iter(c, o->residual, k, MODE_ITER_NOSOLVE, blocks, threads, g, pts, d_prm, d_st, d_part, d_out, it);
-            CKS(gicp_lm_step(c, d_prm, d_st, it));
-        }
-        dispatch_iter(c, o->residual, k, MODE_FITNESS, blocks, threads, g, pts, d_prm, d_st, d_part, d_out, 0);
-    } else if (!sharded) {
-        // The loop is a fixed sequence of launches whose arguments are all stable device pointers, so it is
-        // captured once per (kind, k, blocks, iterations, grid identity) and replayed as a CUDA graph.
-        const bool want_graph = c->use_graph && n > 0 && !c->profiling;
-        GraphKey key{o->residual, k, blocks, iters, threads};
-        cudaGraphExec_t exec = nullptr;
-        if (want_graph) {
-            // graphs bake the GridDesc by value: drop them when the map geometry or buffers changed
-            static_assert(sizeof(GridDesc) % 4 == 0, "GridDesc packing");
-            if (c->graph_grid_owner != &mp.grid || std::memcmp(&c->graph_grid_copy, &g, sizeof(GridDesc)) != 0 ||
-                c->graph_pts != (const void*)pts) {
-                for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
-                c->graphs.clear();
-                c->graph_grid_owner = &mp.grid;
-                c->graph_grid_copy = g;
-                c->graph_pts = pts;
+    // The loop is a fixed sequence of launches whose arguments are all stable device pointers (per-call values
+    // travel through RegParams in device memory), so it is captured once per (kind, k, grid size, iterations,
+    // flavour, map identity) and replayed as a CUDA graph. Early exit is a device flag that turns the remaining
+    // launches into no-ops. The NCCL all-reduce of the sharded flavour is captured like any other stream operation.
+    const bool prof = c->profiling && !sharded && !gicp;
+    int enqueue_status = ICP4R_OK;
+    auto enqueue_loop = [&]() {
+        double* acc_ptr = reinterpret_cast<double*>(reinterpret_cast<char*>(d_st) + offsetof(RegState, acc));
+        if (gicp) {
+            // linearise (grid-wide, accumulators left in st->acc) then one single-block Levenberg-Marquardt step
+            for (int it = 0; it < iters; ++it) {
+                dispatch_iter(c, o->residual, k, MODE_ITER_NOSOLVE, blocks, threads, g, pts, d_prm, d_st, d_part, d_out, it);
+                gicp_lm_step(c, d_prm, d_st, it);
             }
-            auto it = c->graphs.find(key);
-            if (it != c->graphs.end()) exec = it->second;
-        }
-        if (want_graph && !exec) {
-            cudaGraph_t graph = nullptr;
-            // capture on the handle's own stream (a caller-supplied stream may be the legacy default stream,
-            // which cannot be captured); the instantiated graph is then launched on c->stream
-            cudaStream_t run_stream = c->stream;
-            c->stream = c->own_stream;
-            CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-            const int64_t before = c->launches;
-            for (int it = 0; it < iters; ++it) dispatch_iter(c, o->residual, k, MODE_ITER, blocks, threads, g, pts, d_prm, d_st, d_part, d_out, it);
             dispatch_iter(c, o->residual, k, MODE_FITNESS, blocks, threads, g, pts, d_prm, d_st, d_part, d_out, 0);
-            c->launches = before;  // counted at replay time below
-            cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
-            c->stream = run_stream;
-            CK(ce);
-            CK(cudaGraphInstantiate(&exec, graph, 0));
-            cudaGraphDestroy(graph);
-            c->graphs[key] = exec;
-        }
-        if (exec) {
-            CK(cudaGraphLaunch(exec, c->stream));
-            c->launches += iters + 1;
-        } else {
-            const bool prof = c->profiling;
-            if (prof) {
-                while ((int)c->prof_events.size() < iters + 2) {
-                    cudaEvent_t e;
-                    CK(cudaEventCreate(&e));
-                    c->prof_events.push_back(e);
-                }
-                CK(cudaEventRecord(c->prof_events[0], c->stream));
+        } else if (sharded) {
+            for (int it = 0; it < iters; ++it) {
+                dispatch_iter(c, o->residual, k, MODE_ITER_NOSOLVE, blocks, threads, g, pts, d_prm, d_st, d_part, d_out, it);
+                if (shard_allreduce(c, acc_ptr, ICP4R_ACC_LEN) != ICP4R_OK) enqueue_status = ICP4R_ERR_NCCL;
+                solve_kernel<<<1, 32, 0, c->stream>>>(o->residual, d_prm, d_st, it);
+                c->launches += 1;
             }
+            dispatch_iter(c, o->residual, k, MODE_FITNESS_NOFINAL, blocks, threads, g, pts, d_prm, d_st, d_part, d_out, 0);
+            if (shard_allreduce(c, acc_ptr, 2) != ICP4R_OK) enqueue_status = ICP4R_ERR_NCCL;
+            fitness_final_kernel<<<1, 32, 0, c->stream>>>(d_st, d_out);
+            c->launches += 1;
+        } else {
+            if (prof) cudaEventRecord(c->prof_events[0], c->stream);
             for (int it = 0; it < iters; ++it) {
                 dispatch_iter(c, o->residual, k, MODE_ITER, blocks, threads, g, pts, d_prm, d_st, d_part, d_out, it);
-                if (prof) CK(cudaEventRecord(c->prof_events[it + 1], c->stream));
+                if (prof) cudaEventRecord(c->prof_events[it + 1], c->stream);
             }
             dispatch_iter(c, o->residual, k, MODE_FITNESS, blocks, threads, g, pts, d_prm, d_st, d_part, d_out, 0);
-            if (prof) CK(cudaEventRecord(c->prof_events[iters + 1], c->stream));
+            if (prof) cudaEventRecord(c->prof_events[iters + 1], c->stream);
         }
+    };
+    if (prof) {
+        while ((int)c->prof_events.size() < iters + 2) {
+            cudaEvent_t e;
+            CK(cudaEventCreate(&e));
+            c->prof_events.push_back(e);
+        }
+    }
+    const bool want_graph = c->use_graph && n > 0 && !c->profiling && !(sharded && c->no_graph_sharded);
+    GraphKey key{o->residual, k, blocks, iters, threads | (sharded ? 1 << 16 : 0) | (gicp ? 1 << 17 : 0)};
+    cudaGraphExec_t exec = nullptr;
+    if (want_graph) {
+        // graphs bake the GridDesc by value: drop them when the map geometry or buffers changed
+        if (c->graph_grid_owner != &mp.grid || std::memcmp(&c->graph_grid_copy, &g, sizeof(GridDesc)) != 0 ||
+            c->graph_pts != (const void*)pts) {
+            for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+            c->graphs.clear();
+            c->graph_grid_owner = &mp.grid;
+            c->graph_grid_copy = g;
+            c->graph_pts = pts;
+        }
+        auto it = c->graphs.find(key);
+        if (it != c->graphs.end()) exec = it->second;
+    }
+    if (want_graph && !exec) {
+        cudaGraph_t graph = nullptr;
+        // capture on the handle's own stream (a caller-supplied stream may be the legacy default stream, which
+        // cannot be captured); the instantiated graph is then launched on c->stream
+        cudaStream_t run_stream = c->stream;
+        c->stream = c->own_stream;
+        CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        const int64_t before = c->launches;
+        enqueue_loop();
+        c->graph_launches = c->launches - before;
+        c->launches = before;  // counted at replay time below
+        cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+        c->stream = run_stream;
+        if (ce == cudaSuccess && enqueue_status == ICP4R_OK) ce = cudaGraphInstantiate(&exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (ce != cudaSuccess || enqueue_status != ICP4R_OK) {
+            cudaGetLastError();
+            exec = nullptr;
+            enqueue_status = ICP4R_OK;
+            if (sharded) c->no_graph_sharded = true;  // this NCCL build can not be captured: launch directly from now on
+            else return fail(c, ICP4R_ERR_CUDA, "graph capture of the registration loop failed: %s", cudaGetErrorString(ce));
+        } else {
+            c->graphs[key] = exec;
+            c->graph_launch_counts[key] = c->graph_launches;
+        }
+    }
+    if (exec) {
+        CK(cudaGraphLaunch(exec, c->stream));
+        c->launches += c->graph_launch_counts[key];
     } else {
-        for (int it = 0; it < iters; ++it) {
-            dispatch_iter(c, o->residual, k, MODE_ITER_NOSOLVE, blocks, threads, g, pts, d_prm, d_st, d_part, d_out, it);
-            CKS(shard_allreduce(c, reinterpret_cast<double*>(reinterpret_cast<char*>(d_st) + offsetof(RegState, acc)), ICP4R_ACC_LEN));
-            solve_kernel<<<1, 32, 0, c->stream>>>(o->residual, d_prm, d_st, it);
-            c->launches += 1;
-        }
-        dispatch_iter(c, o->residual, k, MODE_FITNESS_NOFINAL, blocks, threads, g, pts, d_prm, d_st, d_part, d_out, 0);
-        CKS(shard_allreduce(c, reinterpret_cast<double*>(reinterpret_cast<char*>(d_st) + offsetof(RegState, acc)), 2));
-        fitness_final_kernel<<<1, 32, 0, c->stream>>>(d_st, d_out);
-        c->launches += 1;
+        enqueue_loop();
+        if (enqueue_status != ICP4R_OK) return enqueue_status;
     }
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(&hs->out, d_out, sizeof(ResultBlock), cudaMemcpyDeviceToHost, c->stream));
