@@ -9,7 +9,7 @@ The directory name carries a hyphen, so import it through the loader at the repo
     from icp4r_loader import pkg      # -> this package, registered as ``icp4dradar_b200``
 """
 from .api import (  # noqa: F401
-    DEVICE, HOST, P2LINE, P2PLANE_KNN, P2P_GN, P2P_SVD, GICP, ACC_LEN, Icp4r, Icp4rError, Opts, Result,
+    DEVICE, HOST, P2LINE, P2PLANE_KNN, P2PLANE_3PT, P2P_GN, P2P_SVD, GICP, ACC_LEN, Icp4r, Icp4rError, Opts, Result,
     lib_path, load_library, default_opts,
 )
 from . import synth  # noqa: F401

@@ -13,7 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 HOST, DEVICE = 0, 1
-P2P_SVD, P2P_GN, P2PLANE_KNN, P2LINE, GICP = range(5)
+P2P_SVD, P2P_GN, P2PLANE_KNN, P2LINE, GICP, P2PLANE_3PT = range(6)
 ACC_LEN = 32
 MAX_K = 16
 
@@ -132,7 +132,7 @@ def _f4(a):
 
 
 def _knn_k(residual, k):
-    return 1 if residual in (P2P_SVD, P2P_GN, GICP) else (2 if residual == P2LINE else (k if k > 0 else 5))
+    return 1 if residual in (P2P_SVD, P2P_GN, GICP) else (2 if residual == P2LINE else (3 if residual == P2PLANE_3PT else (k if k > 0 else 5)))
 
 
 class Icp4r:

@@ -382,7 +382,7 @@ int icp4r_map_points(icp4r_handle h, int mem, float* xyzw_out, uint8_t* valid_ou
 // ---- registration -----------------------------------------------------------------------------------------
 
 static int k_of(const icp4r_opts* o) {
-    return (o->residual == ICP4R_P2P_SVD || o->residual == ICP4R_P2P_GN || o->residual == ICP4R_GICP) ? 1 : (o->residual == ICP4R_P2LINE ? 2 : (o->k > 0 ? o->k : 5));
+    return (o->residual == ICP4R_P2P_SVD || o->residual == ICP4R_P2P_GN || o->residual == ICP4R_GICP) ? 1 : (o->residual == ICP4R_P2LINE ? 2 : (o->residual == ICP4R_P2PLANE_3PT ? 3 : (o->k > 0 ? o->k : 5)));
 }
 
 // dumps requested with host pointers are produced on the device and copied back afterwards

@@ -19,7 +19,7 @@
 
 namespace icp4r {
 
-constexpr int RM_WARPS = 32;  // upper bound; the launch picks warps per block so that every SM gets one block
+constexpr int RM_WARPS = 28;  // upper bound (28 x 32 threads x 72 registers fill one SM); the launch picks warps per block so that every SM gets one block
 constexpr int RM_THREADS = RM_WARPS * 32;
 
 enum { MODE_ITER = 0, MODE_ITER_NOSOLVE = 1, MODE_FITNESS = 2, MODE_FITNESS_NOFINAL = 3 };
@@ -321,6 +321,32 @@ __global__ void __launch_bounds__(RM_THREADS, 1)
                 for (int t6 = 0; t6 < 6; ++t6) cr.li[t6] = li[t6];
                 P.corr[i] = cr;
             }
+        } else if (RK == ICP4R_P2PLANE_3PT) {
+            if (found >= 3) {  // LidarPlaneFactor (radarFactor.hpp:63-64,86), s = 1: plane through the 3 nearest points
+                const double j3[3] = {(double)__shfl_sync(FULL, nb.x, 0), (double)__shfl_sync(FULL, nb.y, 0), (double)__shfl_sync(FULL, nb.z, 0)};
+                const double l3[3] = {(double)__shfl_sync(FULL, nb.x, 1), (double)__shfl_sync(FULL, nb.y, 1), (double)__shfl_sync(FULL, nb.z, 1)};
+                const double m3[3] = {(double)__shfl_sync(FULL, nb.x, 2), (double)__shfl_sync(FULL, nb.y, 2), (double)__shfl_sync(FULL, nb.z, 2)};
+                const double jl[3] = {j3[0] - l3[0], j3[1] - l3[1], j3[2] - l3[2]};
+                const double jm[3] = {j3[0] - m3[0], j3[1] - m3[1], j3[2] - m3[2]};
+                double nrm[3];
+                cross3(jl, jm, nrm);
+                const double len = sqrt((nrm[0] * nrm[0] + nrm[1] * nrm[1]) + nrm[2] * nrm[2]);
+                if (len > 0.0) {
+                    nrm[0] /= len;
+                    nrm[1] /= len;
+                    nrm[2] /= len;
+                    if (lane == 0) {
+                        double* s = scr[w][0];
+                        double pxn[3];
+                        cross3(pw, nrm, pxn);
+                        s[0] = pxn[0]; s[1] = pxn[1]; s[2] = pxn[2];
+                        s[3] = nrm[0]; s[4] = nrm[1]; s[5] = nrm[2];
+                        s[6] = ((pw[0] - j3[0]) * nrm[0] + (pw[1] - j3[1]) * nrm[1]) + (pw[2] - j3[2]) * nrm[2];
+                        s[7] = 1.0; s[8] = 0.0;
+                    }
+                    rows = 1;
+                }
+            }
         } else if (RK == ICP4R_P2LINE) {
             if (found >= 2) {
                 const double a[3] = {(double)__shfl_sync(FULL, nb.x, 0), (double)__shfl_sync(FULL, nb.y, 0), (double)__shfl_sync(FULL, nb.z, 0)};
@@ -524,6 +550,9 @@ static void dispatch_iter(Ctx* c, int kind, int K, int mode, int blocks, int thr
         case ICP4R_GICP:
             launch_iter<ICP4R_GICP, 1>(c, mode, blocks, threads, g, pts, prm, st, partials, out, iter);
             break;
+        case ICP4R_P2PLANE_3PT:
+            launch_iter<ICP4R_P2PLANE_3PT, 5>(c, mode, blocks, threads, g, pts, prm, st, partials, out, iter);
+            break;
         default:
             if (K <= 5) launch_iter<ICP4R_P2PLANE_KNN, 5>(c, mode, blocks, threads, g, pts, prm, st, partials, out, iter);
             else if (K <= 8) launch_iter<ICP4R_P2PLANE_KNN, 8>(c, mode, blocks, threads, g, pts, prm, st, partials, out, iter);
@@ -540,6 +569,8 @@ static int knn_k_for(const icp4r_opts* o) {
             return 1;
         case ICP4R_P2LINE:
             return 2;
+        case ICP4R_P2PLANE_3PT:
+            return 3;
         default:
             return o->k > 0 ? o->k : 5;
     }
@@ -548,7 +579,7 @@ static int knn_k_for(const icp4r_opts* o) {
 int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4r_opts* o, int shard_axis, float slab_lo,
                          float slab_hi, double* T_out_host, icp4r_result* res_host, const icp4r_dump* dump) {
     if (!mp.built) return fail(c, ICP4R_ERR_STATE, "registration target has no built map");
-    if (o->residual < 0 || o->residual > ICP4R_GICP) return fail(c, ICP4R_ERR_INVALID, "bad residual kind %d", o->residual);
+    if (o->residual < 0 || o->residual > ICP4R_P2PLANE_3PT) return fail(c, ICP4R_ERR_INVALID, "bad residual kind %d", o->residual);
     const int k = knn_k_for(o);
     if (k > ICP4R_MAX_K) return fail(c, ICP4R_ERR_INVALID, "k=%d exceeds ICP4R_MAX_K", k);
     if (o->residual == ICP4R_P2PLANE_KNN && k < 3) return fail(c, ICP4R_ERR_INVALID, "P2PLANE_KNN needs k >= 3");

@@ -61,6 +61,7 @@ typedef enum icp4r_residual {
     ICP4R_P2P_GN = 1,      /* LidarDistanceFactor (radarFactor.hpp:140-171), Gauss-Newton 6x6           */
     ICP4R_P2PLANE_KNN = 2, /* LidarPlaneNormFactor (radarFactor.hpp:105-137), plane from the k neighbours */
     ICP4R_P2LINE = 3,      /* RadarEdgeFactor (radarFactor.hpp:11-54), line through the 2 nearest, s = 1  */
+    ICP4R_P2PLANE_3PT = 5, /* LidarPlaneFactor (radarFactor.hpp:56-103), plane through the 3 nearest points, s = 1 */
     ICP4R_GICP = 4         /* fast_gicp cost (radar_odometry.cpp:399-405): k-NN plane-regularised covariances of both
                               clouds, 1-NN Mahalanobis residual, Levenberg-Marquardt; opts.k = CorrespondenceRandomness */
 } icp4r_residual;

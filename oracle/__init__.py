@@ -16,7 +16,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ACC_LEN = 32
 
-P2P_SVD, P2P_GN, P2PLANE_KNN, P2LINE, GICP = range(5)
+P2P_SVD, P2P_GN, P2PLANE_KNN, P2LINE, GICP, P2PLANE_3PT = range(6)
 
 
 class OrcOpts(C.Structure):
@@ -235,7 +235,7 @@ class IkdTree:
 # ---------------------------------------------------------------------------------------- loops
 
 def knn_k_for(residual, k):
-    return 1 if residual in (P2P_SVD, P2P_GN, GICP) else (2 if residual == P2LINE else (k if k > 0 else 5))
+    return 1 if residual in (P2P_SVD, P2P_GN, GICP) else (2 if residual == P2LINE else (3 if residual == P2PLANE_3PT else (k if k > 0 else 5)))
 
 
 def register(src, tgt, opts: OrcOpts, searcher=None, dump=False):

@@ -464,6 +464,30 @@ static int contribute(int residual, int k, double plane_thresh, const double pw[
         acc[28] += 1.0;
         return 1;
     }
+    if (residual == ORC_P2PLANE_3PT) {
+        if (found < 3) return 0;
+        /* LidarPlaneFactor (radarFactor.hpp:63-64,86), s = 1: plane through the three nearest points j, l, m with
+         * unit normal (j-l) x (j-m); r = (p' - j) . n ; J = [(p' x n)^T | n^T] */
+        const float* fj = tgt + 4 * (size_t)nn[0];
+        const float* fl = tgt + 4 * (size_t)nn[1];
+        const float* fm = tgt + 4 * (size_t)nn[2];
+        const double jl[3] = {(double)fj[0] - fl[0], (double)fj[1] - fl[1], (double)fj[2] - fl[2]};
+        const double jm[3] = {(double)fj[0] - fm[0], (double)fj[1] - fm[1], (double)fj[2] - fm[2]};
+        double n[3];
+        cross3(jl, jm, n);
+        const double len = sqrt((n[0] * n[0] + n[1] * n[1]) + n[2] * n[2]);
+        if (!(len > 0.0)) return 0;
+        n[0] /= len;
+        n[1] /= len;
+        n[2] /= len;
+        const double r = ((pw[0] - fj[0]) * n[0] + (pw[1] - fj[1]) * n[1]) + (pw[2] - fj[2]) * n[2];
+        double pxn[3];
+        cross3(pw, n, pxn);
+        const double J[6] = {pxn[0], pxn[1], pxn[2], n[0], n[1], n[2]};
+        acc_gn(acc, J, r);
+        acc[28] += 1.0;
+        return 1;
+    }
     if (residual == ORC_P2LINE) {
         if (found < 2) return 0;
         const float* fa = tgt + 4 * (size_t)nn[0];
@@ -502,6 +526,8 @@ static int knn_k_for(const orc_opts* o) {
             return 1;
         case ORC_P2LINE:
             return 2;
+        case ORC_P2PLANE_3PT:
+            return 3;
         default:
             return o->k > 0 ? o->k : 5;
     }

@@ -32,11 +32,16 @@ def check_dumps(O, kind, k, src, tgt, oo, bufs, iterations):
             assert np.linalg.norm(a - b) <= ACC_RTOL * np.linalg.norm(b)
         else:
             assert np.linalg.norm(a[:21] - b[:21]) <= ACC_RTOL * np.linalg.norm(b[:21]), f"JtJ it {it}"
-            assert np.linalg.norm(a[21:27] - b[21:27]) <= ACC_RTOL * max(np.linalg.norm(b[21:27]), 1e-12), f"Jtr it {it}"
+            # J^T r vanishes at the optimum (a sum of cancelling terms): measure its error against the natural scale of
+            # those terms, |J^T r| <= sqrt(tr(J^T J) * sum r^2), not against the vanishing net value
+            diag = [0, 6, 11, 15, 18, 20]
+            g_scale = max(np.linalg.norm(b[21:27]), np.sqrt(b[diag].sum() * b[27]))
+            assert np.linalg.norm(a[21:27] - b[21:27]) <= ACC_RTOL * max(g_scale, 1e-12), f"Jtr it {it}"
             assert a[28] == b[28]
 
 
-KINDS = [("P2P_SVD", 1, 0.0), ("P2P_GN", 1, 0.0), ("P2PLANE_KNN", 5, 2.0), ("P2LINE", 2, 3.0), ("P2P_SVD", 1, 2.5)]
+KINDS = [("P2P_SVD", 1, 0.0), ("P2P_GN", 1, 0.0), ("P2PLANE_KNN", 5, 2.0), ("P2LINE", 2, 3.0), ("P2P_SVD", 1, 2.5),
+         ("P2PLANE_3PT", 3, 2.0), ("P2PLANE_KNN", 8, 3.0)]
 
 
 @pytest.mark.parametrize("name,k,gate", KINDS)

@@ -91,7 +91,7 @@ def test_plane_fit_loam_convention(O):
     assert np.allclose(n, x / np.linalg.norm(x), atol=1e-8) and np.isclose(d, 1 / np.linalg.norm(x), rtol=1e-8)
 
 
-@pytest.mark.parametrize("kind,k,gate", [("P2P_GN", 1, 0.0), ("P2PLANE_KNN", 5, 2.0), ("P2LINE", 2, 3.0)])
+@pytest.mark.parametrize("kind,k,gate", [("P2P_GN", 1, 0.0), ("P2PLANE_KNN", 5, 2.0), ("P2LINE", 2, 3.0), ("P2PLANE_3PT", 3, 3.0)])
 def test_analytic_jacobians_vs_finite_differences(O, pkg, kind, k, gate):
     """J^T r accumulated with the analytic Jacobians == gradient of 0.5*sum r^2 under T <- exp(xi) T with the
     correspondences (and fitted planes/lines) frozen — checked by central differences of the restated functors."""
@@ -117,6 +117,10 @@ def test_analytic_jacobians_vs_finite_differences(O, pkg, kind, k, gate):
                 if not ok or (np.abs(Pn @ n + d) > 0.2).any():
                     continue
                 r = np.array([n @ pw[i] + d])
+            elif kind == O.P2PLANE_3PT:
+                j, l, m = (tgt[nn[t], :3].astype(np.float64) for t in range(3))
+                nv = np.cross(j - l, j - m)
+                r = np.array([(pw[i] - j) @ (nv / np.linalg.norm(nv))])
             else:
                 a, b = tgt[nn[0], :3].astype(np.float64), tgt[nn[1], :3].astype(np.float64)
                 r = np.cross(pw[i] - a, pw[i] - b) / np.linalg.norm(a - b)
