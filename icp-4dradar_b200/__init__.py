@@ -15,3 +15,4 @@ from .api import (  # noqa: F401
 from . import synth  # noqa: F401
 from . import shard  # noqa: F401
 from . import pipeline  # noqa: F401
+from . import io  # noqa: F401
