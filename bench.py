@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 
 N_SCAN, N_MAP, K_NN, ITERS, GATE = 4096, 200000, 5, 20, 2.0
 C4_N, C4_ITERS = 2048, 30
-POOL = 8
+POOL = 16   # distinct scans; one C2 step registers all of them against the resident map in ONE call
 
 
 def peaks():
@@ -57,6 +57,7 @@ def make_c2(seed=1002):
     return mp, scans
 
 
+NCU_TRAFFIC_BYTES = None  # filled from profiles/ once the batched launch has been captured
 C5_N, C5_ITERS = 16384, 20
 
 
@@ -195,17 +196,21 @@ def run_reference(args, rank, world):
     except Exception:
         pass
     # warm-up + timed steps, bounded to a few minutes in total
+    # one step = POOL registrations (the scans of one batch of our arm), run one after the other on all host threads;
+    # warm-up + timed steps bounded to a few minutes in total
     kind, threads, _ = cpu_reference_c2(mp, scans, 30.0, max(args.warmup, 1), threads)
-    kind, threads, times = cpu_reference_c2(mp, scans, 150.0, args.steps, threads)
+    kind, threads, times = cpu_reference_c2(mp, scans, 150.0, args.steps * POOL, threads)
     total = float(np.sum(times))
     v = len(times) / total
+    nsteps = max(len(times) // POOL, 1)
     line = {
         "impl": "reference", "metric": "registrations/s", "value": v, "unit": "registrations/s", "n_gpus": args.gpus,
-        "steps": len(times), "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
+        "steps": nsteps, "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * total / len(times) * POOL, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "nn_queries_per_s": v * ITERS * N_SCAN,
-        "config": {"workload": "C2 scan-to-map: 4096-pt scan vs resident 200000-pt map, P2PLANE k=5, 20 iters, gate 2.0 m",
-                   "n": N_SCAN, "m": N_MAP, "k": K_NN, "iterations": ITERS, "max_corr_dist": GATE},
+        "config": {"workload": "C2 scan-to-map: 4096-pt scans vs resident 200000-pt map, P2PLANE k=5, 20 iters, gate 2.0 m",
+                   "n": N_SCAN, "m": N_MAP, "k": K_NN, "iterations": ITERS, "max_corr_dist": GATE, "batch_scans": POOL,
+                   "step": f"{POOL} registrations, one after the other, each on all host threads"},
         "cpu_baseline": {"value": v, "unit": "registrations/s", "cores": threads, "kind": kind,
                          "sample": f"{len(times)} registrations; ikd-Tree Build excluded (resident map); PCL/fast_gicp absent from the image"},
         "e2e": {"value": v, "unit": "registrations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -219,7 +224,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--frames", type=int, default=2000, help="c3: frames of the odometry sequence (one step = the whole sequence)")
     ap.add_argument("--map-points", type=int, default=20_000_000, help="c5: points of the dense map (whole job)")
     ap.add_argument("--pairs", type=int, default=65536, help="c4: frame pairs per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -271,17 +277,38 @@ def main():
         mp, scans = make_c2(1002 + rank * 0)
         h.map_build(mp)
         o = pkg.default_opts(residual=pkg.P2PLANE_KNN, k=K_NN, max_iterations=ITERS, max_corr_dist=GATE)
+        off = (np.arange(POOL + 1) * N_SCAN).astype(np.int32)
+        cat = np.ascontiguousarray(np.concatenate(scans))
+        d_cat = torch.from_numpy(cat).to(dev)
+        pin_cat = torch.from_numpy(cat).pin_memory()
+        h_cat = pin_cat.numpy()
         d_scans = [torch.from_numpy(s).to(dev) for s in scans]
-        pinned = [torch.from_numpy(s).pin_memory() for s in scans]
-        h_scans = [p.numpy() for p in pinned]
-        units_per_step = 1
+        units_per_step = POOL
         queries_per_unit = ITERS * N_SCAN
-        step_dev = lambda i: h.register_map(d_scans[i % POOL], o)
-        step_e2e = lambda i: h.register_map(h_scans[i % POOL], o)
-        h2d, d2h = N_SCAN * 16, 16 * 8 + 32
-        cfg = {"workload": "C2 scan-to-map: 4096-pt scan vs resident 200000-pt map, P2PLANE k=5, 20 iters, gate 2.0 m",
-               "n": N_SCAN, "m": N_MAP, "k": K_NN, "iterations": ITERS, "max_corr_dist": GATE, "scan_pool": POOL,
+        step_dev = lambda i: h.register_map_batch(d_cat, off, o)
+        step_e2e = lambda i: h.register_map_batch(h_cat, off, o)
+        h2d, d2h = POOL * N_SCAN * 16, POOL * (16 * 8 + 32)
+        cfg = {"workload": "C2 scan-to-map: 4096-pt scans vs resident 200000-pt map, P2PLANE k=5, 20 iters, gate 2.0 m",
+               "n": N_SCAN, "m": N_MAP, "k": K_NN, "iterations": ITERS, "max_corr_dist": GATE,
+               "batch_scans": POOL, "step": f"{POOL} independent scans registered in one icp4r_register_map_batch call "
+               "(one scan alone is latency-bound and leaves most SMs idle; single-scan latency is in latency_ms_single)",
                "l2": "flushed before every timed step (256 MiB fill, untimed)", "replicas": world}
+    elif args.workload == "c3":
+        # one step = the whole odometry sequence: Build on frame 0, then per frame register against the growing map,
+        # transform with the estimated pose, Add_Points(false). value = frames/s (each frame is one registration).
+        seq, _gt = pkg.pipeline.synth_sequence(1003 + rank, args.frames)
+        o = pkg.default_opts(residual=pkg.P2PLANE_KNN, k=K_NN, max_iterations=ITERS, max_corr_dist=GATE)
+        d_seq = [torch.from_numpy(s).to(dev) for s in seq]
+        pin_seq = [torch.from_numpy(s).pin_memory() for s in seq]
+        h_seq = [p.numpy() for p in pin_seq]
+        units_per_step = args.frames
+        queries_per_unit = ITERS * int(np.mean([len(s) for s in seq]))
+        step_dev = lambda i: pkg.pipeline.run_odometry(h, d_seq, o)
+        step_e2e = lambda i: pkg.pipeline.run_odometry(h, h_seq, o)
+        h2d, d2h = int(sum(len(s) for s in seq)) * 16 * 2, args.frames * (16 * 8 + 32)
+        cfg = {"workload": f"C3 odometry sequence: {args.frames} frames (~3000 static pts each), register vs growing map (P2PLANE k=5, 20 iters, gate 2.0 m) + transform + Add_Points(false) per frame",
+               "frames": args.frames, "k": K_NN, "iterations": ITERS, "max_corr_dist": GATE,
+               "final_map_points": int(sum(len(s) for s in seq)), "l2": "flushed before every timed step; the map outgrows L2 during the sequence"}
     elif args.workload == "c5":
         # one map split in spatial slabs along x (halo = gate) across the ranks; every rank gets the same scan; the 29
         # accumulators are all-reduced (NCCL inside libicp4r_cuda) every iteration. N = 1: the whole map on one GPU.
@@ -366,29 +393,29 @@ def main():
         # ---- roofline of the dominant kernel -------------------------------------------------------------------
         if args.workload == "c2":
             from scipy.spatial import cKDTree
-            # algorithmic bytes of one fused iteration launch (kNN row without the index output,
-            # which the fused kernel never writes): 16*(N + M_r) + 232, M_r = map points within the gate of >= 1 query
-            d, _ = cKDTree(scans[0][:, :3]).query(mp[:, :3], distance_upper_bound=GATE)
+            # single-scan latency through icp4r_register_map (what a sequential odometry loop sees)
+            ms1 = timed(lambda i: h.register_map(d_scans[i % POOL], o), max(args.steps // 2, 10))
+            line["latency_ms_single"] = float(np.median(ms1))
+            line["single_scan_registrations_per_s"] = 1e3 / float(np.mean(ms1))
+            # algorithmic bytes of one fused iteration launch over the whole batch (kNN row without the
+            # index output the fused kernel never writes): 16*(B*N + M_r) + 232*B, M_r = map points within the gate of
+            # >= 1 query of any scan of the batch
+            d, _ = cKDTree(cat[:, :3]).query(mp[:, :3], distance_upper_bound=GATE)
             m_r = int(np.isfinite(d).sum())
-            alg = 16 * (N_SCAN + m_r) + 232
-            h.set_profiling(True)
-            per = []
-            with torch.cuda.stream(stream):
-                for i in range(10):
-                    flush.fill_(i)
-                    h.register_map(d_scans[i % POOL], o)
-                    per.append(h.last_profile()[:ITERS])
-            h.set_profiling(False)
-            k_ms = float(np.mean(per[3:]))
+            alg = 16 * (POOL * N_SCAN + m_r) + 232 * POOL
+            # device time of one iteration launch = (t(20 iterations) - t(10 iterations)) / 10, CUDA events, L2 flushed
+            o10 = pkg.default_opts(residual=pkg.P2PLANE_KNN, k=K_NN, max_iterations=ITERS // 2, max_corr_dist=GATE)
+            t20 = np.mean(timed(step_dev, 10))
+            t10 = np.mean(timed(lambda i: h.register_map_batch(d_cat, off, o10), 10))
+            k_ms = float(t20 - t10) / (ITERS - ITERS // 2)
             ach = alg / (k_ms * 1e-3) / 1e9
-            # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the ncu --set full capture summarised in
-            # profiles/r1_c2_reg_iter_kernel_ncu.txt (ncu flushes caches between replays: this is the COLD figure; warm
-            # launches of the same step are served from L2)
-            line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": 3608320,
-                                "kernel": "reg_iter_kernel<P2PLANE_KNN,5>", "kernel_ms": k_ms, "algorithmic_bytes": alg, "m_r": m_r,
+            # traffic: dram__bytes_read.sum + dram__bytes_write.sum of one launch from the ncu --set full capture summarised
+            # in profiles/ (ncu flushes caches between replays: the COLD figure; warm launches are served from L2)
+            line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": NCU_TRAFFIC_BYTES,
+                                "kernel": "reg_iter_kernel<P2PLANE_KNN,5> (gridDim.y = 16 scans)", "kernel_ms": k_ms, "algorithmic_bytes": alg, "m_r": m_r,
                                 "peak_source": peak_src,
-                                "note": "working set (3.3 MB) is L2-resident: the kernel is latency-bound, see DESIGN.md"}
-        elif args.workload == "c5":
+                                "note": "working set (3.3 MB map + 1 MB scans) is L2-resident: issue/latency-bound, see DESIGN.md"}
+        elif args.workload in ("c5", "c3"):
             line["roofline"] = None
         else:
             alg = args.pairs * (16 * 2 * C4_N + 64 + 160)

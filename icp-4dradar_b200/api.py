@@ -21,7 +21,7 @@ EXPORTS = [
     "icp4r_create", "icp4r_destroy", "icp4r_last_error", "icp4r_version", "icp4r_default_opts", "icp4r_set_stream",
     "icp4r_synchronize", "icp4r_launch_count", "icp4r_set_profiling", "icp4r_last_profile", "icp4r_map_build", "icp4r_map_set_downsample", "icp4r_map_add_points",
     "icp4r_map_size", "icp4r_map_range", "icp4r_map_knn", "icp4r_map_knn_brute", "icp4r_map_sector", "icp4r_map_points",
-    "icp4r_register", "icp4r_register_map", "icp4r_register_batch", "icp4r_shard_unique_id", "icp4r_shard_init",
+    "icp4r_register", "icp4r_register_map", "icp4r_register_map_batch", "icp4r_register_batch", "icp4r_shard_unique_id", "icp4r_shard_init",
     "icp4r_register_sharded", "icp4r_transform_points", "icp4r_doppler_filter",
 ]
 
@@ -294,6 +294,21 @@ class Icp4r:
         self._ck(self.lib.icp4r_register_map(self.h, ps, C.c_int32(src.shape[0]), C.c_int(mem), C.byref(opts),
                                              C.c_void_p(T.ctypes.data), C.byref(res), C.byref(d) if d is not None else None))
         return T.reshape(4, 4), res, bufs
+
+    def register_map_batch(self, src, off, opts: Opts, T0s=None):
+        """several scans (concatenated [sum n, 4], numpy or CUDA tensor; off int32 [B+1]) against the map at once.
+        Returns (T [B,4,4], results structured array)."""
+        src = _f4(src)
+        ps, mem = _ptr(src)
+        off = np.ascontiguousarray(off, np.int32)
+        B = off.shape[0] - 1
+        T = np.zeros((B, 16), np.float64)
+        res = np.zeros(B, RESULT_DTYPE)
+        t0 = None if T0s is None else np.ascontiguousarray(T0s, np.float64).reshape(B, 16)
+        self._ck(self.lib.icp4r_register_map_batch(self.h, ps, C.c_void_p(off.ctypes.data), C.c_int32(B), C.c_int(mem), C.byref(opts),
+                                                   None if t0 is None else C.c_void_p(t0.ctypes.data), C.c_void_p(T.ctypes.data),
+                                                   C.c_void_p(res.ctypes.data)))
+        return T.reshape(B, 4, 4), res
 
     def register_batch(self, src, src_off, tgt, tgt_off, opts: Opts, out=None):
         """src/tgt: concatenated clouds [sum n, 4]; *_off: int32 [n_pairs+1]. Returns (T [P,4,4], results)."""

@@ -187,7 +187,7 @@ int icp4r_destroy(icp4r_handle h) {
     release(c->d_gicp_corr);
     DevBuf* bufs[] = {&c->d_src, &c->d_q, &c->d_idx, &c->d_d2, &c->d_found, &c->d_scratch, &c->d_partials, &c->d_state, &c->d_params,
                       &c->d_T, &c->d_res, &c->d_dump_pose, &c->d_dump_acc, &c->d_dump_idx, &c->b_src, &c->b_tgt, &c->b_soff,
-                      &c->b_toff, &c->b_T, &c->b_res};
+                      &c->b_toff, &c->b_T, &c->b_res, &c->bm_params, &c->bm_state, &c->bm_T0, &c->bm_res, &c->bm_partials};
     for (DevBuf* b : bufs) release(*b);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     cudaStreamDestroy(c->own_stream);
@@ -442,6 +442,22 @@ int icp4r_register_map(icp4r_handle h, const float* src, int32_t n, int mem, con
     CKS(dump_prepare(c, dump, mem, n, opts, ds));
     CKS(register_against_map(c, c->map, static_cast<const float4*>(dsrc), n, opts, -1, 0.f, 0.f, T_out, res, dump ? &ds.dev : nullptr));
     return dump_finish(c, ds);
+}
+
+int icp4r_register_map_batch(icp4r_handle h, const float* src, const int32_t* off, int32_t n_scans, int mem, const icp4r_opts* opts,
+                             const double* T0s, double* T_out, icp4r_result* res) {
+    HCHECK(h);
+    if (!opts || n_scans < 0 || bad_mem(mem) || (n_scans > 0 && (!off || !T_out || !res)))
+        return fail(c, ICP4R_ERR_INVALID, "icp4r_register_map_batch: bad arguments");
+    if (n_scans == 0) return ICP4R_OK;
+    // offsets, initial guesses, poses and results are small and always host memory; only the points follow `mem`
+    for (int i = 0; i < n_scans; ++i)
+        if (off[i + 1] < off[i]) return fail(c, ICP4R_ERR_INVALID, "offsets must be non-decreasing (scan %d)", i);
+    const size_t total = (size_t)(off[n_scans] - off[0]);
+    if (total > 0 && !src) return fail(c, ICP4R_ERR_INVALID, "null cloud pointer");
+    const void* dsrc;
+    CKS(stage_in(c, c->d_src, src, (size_t)off[n_scans] * sizeof(float4), mem, &dsrc));
+    return register_scans_against_map(c, c->map, static_cast<const float4*>(dsrc), off, n_scans, opts, T0s, T_out, res);
 }
 
 int icp4r_register(icp4r_handle h, const float* src, int32_t n, const float* tgt, int32_t m, int mem, const icp4r_opts* opts,

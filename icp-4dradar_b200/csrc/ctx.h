@@ -147,6 +147,7 @@ struct Ctx {
     DevBuf d_src, d_q, d_idx, d_d2, d_found, d_scratch, d_partials, d_state, d_params, d_T, d_res;
     DevBuf d_dump_pose, d_dump_acc, d_dump_idx;
     DevBuf b_src, b_tgt, b_soff, b_toff, b_T, b_res;  // batched registration
+    DevBuf bm_params, bm_state, bm_T0, bm_res, bm_partials;  // batched scans against the map
     void* h_pinned = nullptr;  // small pinned staging block
     size_t h_pinned_cap = 0;
 
@@ -192,6 +193,9 @@ int map_sector(Ctx* c, const Map& mp, const float centre[3], float radius, float
 int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4r_opts* o, int shard_axis,
                          float slab_lo, float slab_hi, double* T_out_host, icp4r_result* res_host,
                          const icp4r_dump* dump_dev);
+
+int register_scans_against_map(Ctx* c, Map& mp, const float4* d_src, const int32_t* off_host, int nscan, const icp4r_opts* o,
+                               const double* T0s_host, double* T_out_host, icp4r_result* res_host);
 
 // register_batch.cu
 int register_batch(Ctx* c, const float4* d_src, const int32_t* d_soff, const float4* d_tgt, const int32_t* d_toff,

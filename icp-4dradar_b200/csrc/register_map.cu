@@ -143,6 +143,12 @@ __global__ void __launch_bounds__(RM_THREADS, 1)
     constexpr bool FIT = (MODE == MODE_FITNESS || MODE == MODE_FITNESS_NOFINAL);
     constexpr int KK = FIT ? 1 : K;
     constexpr int RK = FIT ? ICP4R_P2P_SVD : KIND;  // residual actually accumulated
+    // blockIdx.y selects one of the independent scans of a batched call (each has its own parameters, state,
+    // partials and result); single registrations launch with gridDim.y == 1
+    prm += blockIdx.y;
+    st += blockIdx.y;
+    partials += (size_t)blockIdx.y * gridDim.x * ICP4R_ACC_LEN;
+    out += blockIdx.y;
     if (!FIT && st->done) return;
 
     __shared__ WarpSegs segs[RM_WARPS];
@@ -496,6 +502,8 @@ __global__ void fitness_final_kernel(RegState* __restrict__ st, ResultBlock* __r
 }
 
 __global__ void init_state_kernel(RegState* st, const double* T0) {
+    st += blockIdx.x;   // one block per scan of a batched call
+    T0 += 16 * blockIdx.x;
     const int t = threadIdx.x;
     if (t < 16) st->T[t] = T0[t];
     if (t < ICP4R_ACC_LEN) st->acc[t] = 0.0;
@@ -516,47 +524,47 @@ __global__ void init_state_kernel(RegState* st, const double* T0) {
 }
 
 template <int KIND, int K>
-static void launch_iter(Ctx* c, int mode, int blocks, int threads, const GridDesc& g, const float4* pts, const RegParams* prm, RegState* st,
+static void launch_iter(Ctx* c, int mode, int blocks, int threads, int nscan, const GridDesc& g, const float4* pts, const RegParams* prm, RegState* st,
                         double* partials, ResultBlock* out, int iter) {
     switch (mode) {
         case MODE_ITER:
-            reg_iter_kernel<KIND, K, MODE_ITER><<<blocks, threads, 0, c->stream>>>(g, pts, prm, st, partials, out, iter);
+            reg_iter_kernel<KIND, K, MODE_ITER><<<dim3(blocks, nscan), threads, 0, c->stream>>>(g, pts, prm, st, partials, out, iter);
             break;
         case MODE_ITER_NOSOLVE:
-            reg_iter_kernel<KIND, K, MODE_ITER_NOSOLVE><<<blocks, threads, 0, c->stream>>>(g, pts, prm, st, partials, out, iter);
+            reg_iter_kernel<KIND, K, MODE_ITER_NOSOLVE><<<dim3(blocks, nscan), threads, 0, c->stream>>>(g, pts, prm, st, partials, out, iter);
             break;
         case MODE_FITNESS:
-            reg_iter_kernel<KIND, K, MODE_FITNESS><<<blocks, threads, 0, c->stream>>>(g, pts, prm, st, partials, out, iter);
+            reg_iter_kernel<KIND, K, MODE_FITNESS><<<dim3(blocks, nscan), threads, 0, c->stream>>>(g, pts, prm, st, partials, out, iter);
             break;
         default:
-            reg_iter_kernel<KIND, K, MODE_FITNESS_NOFINAL><<<blocks, threads, 0, c->stream>>>(g, pts, prm, st, partials, out, iter);
+            reg_iter_kernel<KIND, K, MODE_FITNESS_NOFINAL><<<dim3(blocks, nscan), threads, 0, c->stream>>>(g, pts, prm, st, partials, out, iter);
             break;
     }
     c->launches += 1;
 }
 
-static void dispatch_iter(Ctx* c, int kind, int K, int mode, int blocks, int threads, const GridDesc& g, const float4* pts,
+static void dispatch_iter(Ctx* c, int kind, int K, int mode, int blocks, int threads, int nscan, const GridDesc& g, const float4* pts,
                           const RegParams* prm, RegState* st, double* partials, ResultBlock* out, int iter) {
     switch (kind) {
         case ICP4R_P2P_SVD:
-            launch_iter<ICP4R_P2P_SVD, 1>(c, mode, blocks, threads, g, pts, prm, st, partials, out, iter);
+            launch_iter<ICP4R_P2P_SVD, 1>(c, mode, blocks, threads, nscan, g, pts, prm, st, partials, out, iter);
             break;
         case ICP4R_P2P_GN:
-            launch_iter<ICP4R_P2P_GN, 1>(c, mode, blocks, threads, g, pts, prm, st, partials, out, iter);
+            launch_iter<ICP4R_P2P_GN, 1>(c, mode, blocks, threads, nscan, g, pts, prm, st, partials, out, iter);
             break;
         case ICP4R_P2LINE:
-            launch_iter<ICP4R_P2LINE, 2>(c, mode, blocks, threads, g, pts, prm, st, partials, out, iter);
+            launch_iter<ICP4R_P2LINE, 2>(c, mode, blocks, threads, nscan, g, pts, prm, st, partials, out, iter);
             break;
         case ICP4R_GICP:
-            launch_iter<ICP4R_GICP, 1>(c, mode, blocks, threads, g, pts, prm, st, partials, out, iter);
+            launch_iter<ICP4R_GICP, 1>(c, mode, blocks, threads, nscan, g, pts, prm, st, partials, out, iter);
             break;
         case ICP4R_P2PLANE_3PT:
-            launch_iter<ICP4R_P2PLANE_3PT, 5>(c, mode, blocks, threads, g, pts, prm, st, partials, out, iter);
+            launch_iter<ICP4R_P2PLANE_3PT, 5>(c, mode, blocks, threads, nscan, g, pts, prm, st, partials, out, iter);
             break;
         default:
-            if (K <= 5) launch_iter<ICP4R_P2PLANE_KNN, 5>(c, mode, blocks, threads, g, pts, prm, st, partials, out, iter);
-            else if (K <= 8) launch_iter<ICP4R_P2PLANE_KNN, 8>(c, mode, blocks, threads, g, pts, prm, st, partials, out, iter);
-            else launch_iter<ICP4R_P2PLANE_KNN, 16>(c, mode, blocks, threads, g, pts, prm, st, partials, out, iter);
+            if (K <= 5) launch_iter<ICP4R_P2PLANE_KNN, 5>(c, mode, blocks, threads, nscan, g, pts, prm, st, partials, out, iter);
+            else if (K <= 8) launch_iter<ICP4R_P2PLANE_KNN, 8>(c, mode, blocks, threads, nscan, g, pts, prm, st, partials, out, iter);
+            else launch_iter<ICP4R_P2PLANE_KNN, 16>(c, mode, blocks, threads, nscan, g, pts, prm, st, partials, out, iter);
             break;
     }
 }
@@ -678,28 +686,28 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
         if (gicp) {
             // linearise (grid-wide, accumulators left in st->acc) then one single-block Levenberg-Marquardt step
             for (int it = 0; it < iters; ++it) {
-                dispatch_iter(c, o->residual, k, MODE_ITER_NOSOLVE, blocks, threads, g, pts, d_prm, d_st, d_part, d_out, it);
+                dispatch_iter(c, o->residual, k, MODE_ITER_NOSOLVE, blocks, threads, 1, g, pts, d_prm, d_st, d_part, d_out, it);
                 gicp_lm_step(c, d_prm, d_st, it);
             }
-            dispatch_iter(c, o->residual, k, MODE_FITNESS, blocks, threads, g, pts, d_prm, d_st, d_part, d_out, 0);
+            dispatch_iter(c, o->residual, k, MODE_FITNESS, blocks, threads, 1, g, pts, d_prm, d_st, d_part, d_out, 0);
         } else if (sharded) {
             for (int it = 0; it < iters; ++it) {
-                dispatch_iter(c, o->residual, k, MODE_ITER_NOSOLVE, blocks, threads, g, pts, d_prm, d_st, d_part, d_out, it);
+                dispatch_iter(c, o->residual, k, MODE_ITER_NOSOLVE, blocks, threads, 1, g, pts, d_prm, d_st, d_part, d_out, it);
                 if (shard_allreduce(c, acc_ptr, ICP4R_ACC_LEN) != ICP4R_OK) enqueue_status = ICP4R_ERR_NCCL;
                 solve_kernel<<<1, 32, 0, c->stream>>>(o->residual, d_prm, d_st, it);
                 c->launches += 1;
             }
-            dispatch_iter(c, o->residual, k, MODE_FITNESS_NOFINAL, blocks, threads, g, pts, d_prm, d_st, d_part, d_out, 0);
+            dispatch_iter(c, o->residual, k, MODE_FITNESS_NOFINAL, blocks, threads, 1, g, pts, d_prm, d_st, d_part, d_out, 0);
             if (shard_allreduce(c, acc_ptr, 2) != ICP4R_OK) enqueue_status = ICP4R_ERR_NCCL;
             fitness_final_kernel<<<1, 32, 0, c->stream>>>(d_st, d_out);
             c->launches += 1;
         } else {
             if (prof) cudaEventRecord(c->prof_events[0], c->stream);
             for (int it = 0; it < iters; ++it) {
-                dispatch_iter(c, o->residual, k, MODE_ITER, blocks, threads, g, pts, d_prm, d_st, d_part, d_out, it);
+                dispatch_iter(c, o->residual, k, MODE_ITER, blocks, threads, 1, g, pts, d_prm, d_st, d_part, d_out, it);
                 if (prof) cudaEventRecord(c->prof_events[it + 1], c->stream);
             }
-            dispatch_iter(c, o->residual, k, MODE_FITNESS, blocks, threads, g, pts, d_prm, d_st, d_part, d_out, 0);
+            dispatch_iter(c, o->residual, k, MODE_FITNESS, blocks, threads, 1, g, pts, d_prm, d_st, d_part, d_out, 0);
             if (prof) cudaEventRecord(c->prof_events[iters + 1], c->stream);
         }
     };
@@ -787,6 +795,128 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
     }
     if (T_out_host) std::memcpy(T_out_host, hs->out.T, sizeof(hs->out.T));
     if (res_host) *res_host = hs->out.res;
+    return ICP4R_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ batched scans
+// nscan independent scans against the same map in ONE sequence of launches (gridDim.y = scan): a single scan of a
+// few thousand points cannot fill the GPU (the iteration kernel is latency-bound, profiles/), several can.
+int register_scans_against_map(Ctx* c, Map& mp, const float4* d_src, const int32_t* off_host, int nscan, const icp4r_opts* o,
+                               const double* T0s_host, double* T_out_host, icp4r_result* res_host) {
+    if (!mp.built) return fail(c, ICP4R_ERR_STATE, "registration target has no built map");
+    if (o->residual == ICP4R_GICP) return fail(c, ICP4R_ERR_UNSUPPORTED, "batched scans do not support ICP4R_GICP (per-scan covariances)");
+    if (o->residual < 0 || o->residual > ICP4R_P2PLANE_3PT) return fail(c, ICP4R_ERR_INVALID, "bad residual kind %d", o->residual);
+    const int k = knn_k_for(o);
+    if (k > ICP4R_MAX_K) return fail(c, ICP4R_ERR_INVALID, "k=%d exceeds ICP4R_MAX_K", k);
+    if (o->residual == ICP4R_P2PLANE_KNN && k < 3) return fail(c, ICP4R_ERR_INVALID, "P2PLANE_KNN needs k >= 3");
+    if (o->max_iterations < 0) return fail(c, ICP4R_ERR_INVALID, "negative iteration count");
+    struct Stage {
+        RegParams prm;
+        double T0[16];
+        ResultBlock out;
+    };
+    const int CH = (int)std::min<size_t>(64, c->h_pinned_cap / sizeof(Stage));  // scans per launch sequence
+    const GridDesc g = mp.grid;
+    const float4* pts = mp.pts.as<float4>();
+    const int iters = o->max_iterations;
+    for (int s0 = 0; s0 < nscan; s0 += CH) {
+        const int B = std::min(CH, nscan - s0);
+        int nmax = 0;
+        for (int b = 0; b < B; ++b) nmax = std::max(nmax, off_host[s0 + b + 1] - off_host[s0 + b]);
+        const int bps = std::max(1, c->sm_count / B);  // blocks per scan: the whole batch is one wave
+        int wpb = (nmax + bps - 1) / std::max(bps, 1);
+        wpb = std::min(std::max(wpb, 4), RM_WARPS);
+        const int threads = wpb * 32;
+        const int blocks = std::min(std::max(1, (nmax + wpb - 1) / wpb), bps);
+        const void* old_ptrs[4] = {c->bm_params.p, c->bm_state.p, c->bm_res.p, c->bm_partials.p};
+        CKS(reserve_grow(c, c->bm_params, (size_t)B * sizeof(RegParams)));
+        CKS(reserve_grow(c, c->bm_state, (size_t)B * sizeof(RegState)));
+        CKS(reserve_grow(c, c->bm_T0, (size_t)B * 16 * sizeof(double)));
+        CKS(reserve_grow(c, c->bm_res, (size_t)B * sizeof(ResultBlock)));
+        CKS(reserve_grow(c, c->bm_partials, (size_t)B * blocks * ICP4R_ACC_LEN * sizeof(double)));
+        const bool moved = old_ptrs[0] != c->bm_params.p || old_ptrs[1] != c->bm_state.p || old_ptrs[2] != c->bm_res.p ||
+                           old_ptrs[3] != c->bm_partials.p;
+        Stage* hs = static_cast<Stage*>(c->h_pinned);
+        for (int b = 0; b < B; ++b) {
+            RegParams& P = hs[b].prm;
+            std::memset(&P, 0, sizeof(P));
+            P.src = d_src + off_host[s0 + b];
+            P.n = off_host[s0 + b + 1] - off_host[s0 + b];
+            P.residual = o->residual;
+            P.k = k;
+            P.max_iterations = o->max_iterations;
+            P.early_exit = o->early_exit;
+            gate_params(o->max_corr_dist, &P.gate_f, &P.gate_r);
+            P.rot_eps = o->rot_eps;
+            P.trans_eps = o->trans_eps;
+            P.mse_abs_eps = o->mse_abs_eps;
+            P.plane_thresh = o->plane_thresh;
+            P.shard_axis = -1;
+            std::memcpy(hs[b].T0, T0s_host ? T0s_host + 16 * (size_t)(s0 + b) : o->T0, sizeof(hs[b].T0));
+        }
+        RegParams* d_prm = c->bm_params.as<RegParams>();
+        RegState* d_st = c->bm_state.as<RegState>();
+        ResultBlock* d_out = c->bm_res.as<ResultBlock>();
+        double* d_part = c->bm_partials.as<double>();
+        // the staging block interleaves params / T0 / out per scan: two strided copies
+        CK(cudaMemcpy2DAsync(d_prm, sizeof(RegParams), &hs[0].prm, sizeof(Stage), sizeof(RegParams), B, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpy2DAsync(c->bm_T0.p, 16 * sizeof(double), hs[0].T0, sizeof(Stage), 16 * sizeof(double), B, cudaMemcpyHostToDevice, c->stream));
+        init_state_kernel<<<B, 32, 0, c->stream>>>(d_st, c->bm_T0.as<double>());
+        c->launches += 1;
+        auto enqueue = [&]() {
+            for (int it = 0; it < iters; ++it) dispatch_iter(c, o->residual, k, MODE_ITER, blocks, threads, B, g, pts, d_prm, d_st, d_part, d_out, it);
+            dispatch_iter(c, o->residual, k, MODE_FITNESS, blocks, threads, B, g, pts, d_prm, d_st, d_part, d_out, 0);
+        };
+        const bool want_graph = c->use_graph && !c->profiling;
+        GraphKey key{o->residual, k, blocks, iters, threads | (1 << 18) | (B << 20)};
+        cudaGraphExec_t exec = nullptr;
+        if (want_graph) {
+            if (moved || c->graph_grid_owner != &mp.grid || std::memcmp(&c->graph_grid_copy, &g, sizeof(GridDesc)) != 0 ||
+                c->graph_pts != (const void*)pts) {
+                for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+                c->graphs.clear();
+                c->graph_grid_owner = &mp.grid;
+                c->graph_grid_copy = g;
+                c->graph_pts = pts;
+            }
+            auto itg = c->graphs.find(key);
+            if (itg != c->graphs.end()) exec = itg->second;
+            if (!exec) {
+                cudaGraph_t graph = nullptr;
+                cudaStream_t run_stream = c->stream;
+                c->stream = c->own_stream;
+                CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+                const int64_t before = c->launches;
+                enqueue();
+                c->graph_launches = c->launches - before;
+                c->launches = before;
+                cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+                c->stream = run_stream;
+                CK(ce);
+                CK(cudaGraphInstantiate(&exec, graph, 0));
+                cudaGraphDestroy(graph);
+                c->graphs[key] = exec;
+                c->graph_launch_counts[key] = c->graph_launches;
+            }
+        }
+        if (exec) {
+            CK(cudaGraphLaunch(exec, c->stream));
+            c->launches += c->graph_launch_counts[key];
+        } else {
+            enqueue();
+        }
+        CK(cudaGetLastError());
+        CK(cudaMemcpy2DAsync(&hs[0].out, sizeof(Stage), d_out, sizeof(ResultBlock), sizeof(ResultBlock), B, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        for (int b = 0; b < B; ++b) {
+            if (iters == 0) {
+                hs[b].out.res.converged = 1;
+                hs[b].out.res.iterations = 0;
+            }
+            if (T_out_host) std::memcpy(T_out_host + 16 * (size_t)(s0 + b), hs[b].out.T, sizeof(hs[b].out.T));
+            if (res_host) res_host[s0 + b] = hs[b].out.res;
+        }
+    }
     return ICP4R_OK;
 }
 

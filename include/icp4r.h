@@ -149,6 +149,12 @@ int icp4r_register(icp4r_handle h, const float* src_xyzw, int32_t n, const float
 /* source vs the handle's map (radar_odometry.cpp:390-411 with the ikd-Tree map as the target) */
 int icp4r_register_map(icp4r_handle h, const float* src_xyzw, int32_t n, int mem, const icp4r_opts* opts,
                        double T_out[16], icp4r_result* res, const icp4r_dump* dump);
+/* n_scans independent scans against the handle's map in ONE sequence of launches (throughput mode: one scan of a
+ * few thousand points leaves most of the GPU idle). src_xyzw holds the scans back to back (memory space `mem`);
+ * off [n_scans+1] (points), T0s ([n_scans][16] initial guesses, or NULL = opts->T0 for all), T_out [n_scans][16]
+ * and res [n_scans] are HOST memory. All residual kinds except ICP4R_GICP. */
+int icp4r_register_map_batch(icp4r_handle h, const float* src_xyzw, const int32_t* off, int32_t n_scans, int mem,
+                             const icp4r_opts* opts, const double* T0s, double* T_out, icp4r_result* res);
 /* n_pairs independent (source, target) pairs, CSR-style offsets ([n_pairs+1], in points), one CTA per pair
  * with both clouds resident in shared memory. P2P_SVD and P2P_GN. T_out: [n_pairs][16]; res: [n_pairs].
  * opts->T0 is the initial guess of every pair. Offsets and results follow `mem` too. */

@@ -198,3 +198,31 @@ def test_gicp_matches_oracle(pkg, O, handle):
     T2, r2, _ = handle.register_map(src, o)
     T3, r3, _ = handle.register_map(src, o)
     assert np.array_equal(T2, T3) and np.abs(T2 - T).max() < 1e-12
+
+
+def test_register_map_batch(pkg, O, handle):
+    """several scans against the same map in one launch sequence == each scan registered alone"""
+    import bench
+    mp, scans = bench.make_c2()
+    scans = [s[: 1500 + 300 * i] for i, s in enumerate(scans[:5])] + [scans[5][:0], scans[6][:7]]   # ragged, empty, tiny
+    off = np.concatenate([[0], np.cumsum([len(s) for s in scans])]).astype(np.int32)
+    S = np.concatenate(scans)
+    handle.map_build(mp)
+    for kind, k, gate in ((pkg.P2PLANE_KNN, 5, 2.0), (pkg.P2P_SVD, 1, 2.0)):
+        o = pkg.default_opts(residual=kind, k=k, max_iterations=6, max_corr_dist=gate)
+        T0s = np.stack([pkg.synth.se3(0.002 * i, 0, 0, (0.01 * i, 0, 0)) for i in range(len(scans))])
+        Tb, rb = handle.register_map_batch(S, off, o, T0s)
+        for i, s in enumerate(scans):
+            oi = pkg.default_opts(residual=kind, k=k, max_iterations=6, max_corr_dist=gate, T0=T0s[i])
+            Ti, ri, _ = handle.register_map(s, oi)
+            assert np.abs(Tb[i] - Ti).max() < 1e-9, (i, np.abs(Tb[i] - Ti).max())
+            assert (rb["converged"][i], rb["iterations"][i], rb["n_corr"][i], rb["n_fitness"][i]) == (ri.converged, ri.iterations, ri.n_corr, ri.n_fitness)
+        # one of them against the oracle too
+        oo = O.default_opts(residual=kind, k=k, max_iterations=6, max_corr_dist=gate, T0=T0s[2])
+        To, ro, _ = O.register(scans[2], mp, oo)
+        et, er = pose_err(Tb[2], To)
+        assert et <= POSE_TOL_T and er <= POSE_TOL_R
+    # device-resident scans
+    import torch
+    Tb2, rb2 = handle.register_map_batch(torch.from_numpy(S).cuda(), off, o, T0s)
+    assert np.array_equal(Tb2, Tb)
