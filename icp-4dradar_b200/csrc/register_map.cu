@@ -153,6 +153,9 @@ __global__ void __launch_bounds__(RM_THREADS, 1)
 
     __shared__ WarpSegs segs[RM_WARPS];
     __shared__ double scr[RM_WARPS][3][12];  // per-warp operands of the lane products (up to 3 residual rows)
+    constexpr bool PARKED = (!FIT && KIND == ICP4R_P2PLANE_KNN && K <= 8);  // plane fits done 8 points at a time, one per lane
+    constexpr int PARK = 8;
+    __shared__ double scrq[PARKED ? RM_WARPS : 1][PARK][8];
     __shared__ double red[RM_WARPS][ICP4R_ACC_LEN];
     __shared__ double tot[ICP4R_ACC_LEN];
     __shared__ double Ts[16];
@@ -188,6 +191,62 @@ __global__ void __launch_bounds__(RM_THREADS, 1)
 #ifdef ICP4R_PHASE_TIMING
     const long long tp0 = clock64();
 #endif
+
+    // P2PLANE_KNN: a warp finds the neighbours of its points one after the other but fits the planes of up to PARK
+    // points at once, one point per lane (the fit is ~400 fp64 instructions that every lane would otherwise execute
+    // redundantly for every single point); lane q keeps point q's neighbour indices until the flush
+    int parked = 0, my_src = -1;
+    int my_nb[PARKED ? K : 1];
+    auto flush_parked = [&]() {
+        if (PARKED) {
+            if (lane < parked) {
+                const float4 p = __ldg(P.src + my_src);
+                double pw[3];
+                xform_point(Ts, p.x, p.y, p.z, pw);
+                float Pn[K][3];
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    if (j < P.k) {
+                        const float4 cpt = __ldg(pts + my_nb[j]);
+                        Pn[j][0] = cpt.x;
+                        Pn[j][1] = cpt.y;
+                        Pn[j][2] = cpt.z;
+                    } else {
+                        Pn[j][0] = Pn[j][1] = Pn[j][2] = 0.f;
+                    }
+                }
+                double nrm[3], d;
+                bool ok = plane_fit<K, float>(Pn, P.k, nrm, d);
+                if (ok) {
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        if (j < P.k) {
+                            const double e = ((nrm[0] * (double)Pn[j][0] + nrm[1] * (double)Pn[j][1]) + nrm[2] * (double)Pn[j][2]) + d;
+                            if (!(fabs(e) <= P.plane_thresh)) ok = false;
+                        }
+                    }
+                }
+                double* s = scrq[w][lane];
+                if (ok) {  // LidarPlaneNormFactor (radarFactor.hpp:122): r = n.p' + d, J = [(p' x n)^T | n^T]
+                    double pxn[3];
+                    cross3(pw, nrm, pxn);
+                    s[0] = pxn[0]; s[1] = pxn[1]; s[2] = pxn[2];
+                    s[3] = nrm[0]; s[4] = nrm[1]; s[5] = nrm[2];
+                    s[6] = ((nrm[0] * pw[0] + nrm[1] * pw[1]) + nrm[2] * pw[2]) + d;
+                    s[7] = 1.0;
+                } else {
+#pragma unroll
+                    for (int t8 = 0; t8 < 8; ++t8) s[t8] = 0.0;
+                }
+            }
+            __syncwarp();
+            if (ia < 8) {
+                for (int q = 0; q < parked; ++q) acc += scrq[w][q][ia] * scrq[w][q][ib];  // fixed order
+            }
+            __syncwarp();
+            parked = 0;
+        }
+    };
 
     const int n = P.n;
     const int kq = FIT ? 1 : P.k;
@@ -240,6 +299,16 @@ __global__ void __launch_bounds__(RM_THREADS, 1)
                     s[8] = 0.0;
                 }
                 rows = 3;
+            }
+        } else if (RK == ICP4R_P2PLANE_KNN && PARKED) {
+            if (found == kq && kq >= 3) {  // park the neighbours in lane `parked`; the fit happens in flush_parked()
+#pragma unroll
+                for (int r = 0; r < K; ++r) {
+                    const int v = key_idx(__shfl_sync(FULL, mine, r));
+                    if (lane == parked) my_nb[PARKED ? r : 0] = v;
+                }
+                if (lane == parked) my_src = i;
+                if (++parked == PARK) flush_parked();
             }
         } else if (RK == ICP4R_P2PLANE_KNN) {
             if (found == kq && kq >= 3) {
@@ -395,6 +464,7 @@ __global__ void __launch_bounds__(RM_THREADS, 1)
         }
     }
 
+    flush_parked();
     // block partial in a fixed order: value v = sum over warps 0..7 of lane v's accumulator
 #ifdef ICP4R_PHASE_TIMING
     const long long tp1 = clock64();
