@@ -228,6 +228,8 @@ def main():
     ap.add_argument("--frames", type=int, default=2000, help="c3: frames of the odometry sequence (one step = the whole sequence)")
     ap.add_argument("--map-points", type=int, default=20_000_000, help="c5: points of the dense map (whole job)")
     ap.add_argument("--pairs", type=int, default=65536, help="c4: frame pairs per GPU per step")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="c5, N > 1: cross-rank sum inside the iteration kernel over NVLink peer memory, or one NCCL all-reduce per iteration")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -311,7 +313,7 @@ def main():
                "final_map_points": int(sum(len(s) for s in seq)), "l2": "flushed before every timed step; the map outgrows L2 during the sequence"}
     elif args.workload == "c5":
         # one map split in spatial slabs along x (halo = gate) across the ranks; every rank gets the same scan; the 29
-        # accumulators are all-reduced (NCCL inside libicp4r_cuda) every iteration. N = 1: the whole map on one GPU.
+        # accumulators are summed across ranks every iteration (in-kernel over peer memory, or NCCL). N = 1: the whole map on one GPU.
         mp, scans = make_c5(args.map_points)
         o = pkg.default_opts(residual=pkg.P2PLANE_KNN, k=K_NN, max_iterations=C5_ITERS, max_corr_dist=GATE)
         if world > 1:
@@ -320,6 +322,10 @@ def main():
             uid = [pkg.Icp4r.shard_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(uid, src=0)
             h.shard_init(uid[0], rank, world)
+            if args.exchange == "peer":
+                hs = [None] * world
+                dist.all_gather_object(hs, h.shard_ipc_export())
+                h.shard_ipc_import(hs, rank, world)
             h.map_build(torch.from_numpy(mine).to(dev))
             step_dev = lambda i: h.register_sharded(d_scans[i % 4], o, 0, lo, hi)
             step_e2e = lambda i: h.register_sharded(h_scans[i % 4], o, 0, lo, hi)
@@ -335,7 +341,8 @@ def main():
         h2d, d2h = C5_N * 16, 16 * 8 + 32
         cfg = {"workload": f"C5 large-map registration: 16384-pt scan vs {args.map_points}-pt dense map in {world} x-slab(s), P2PLANE k=5, 20 iters, gate 2.0 m",
                "n": C5_N, "m": args.map_points, "k": K_NN, "iterations": C5_ITERS, "max_corr_dist": GATE, "slabs": world,
-               "collective": "29-double NCCL all-reduce per iteration" if world > 1 else "none",
+               "collective": ("none" if world == 1 else "29 fp64 sums exchanged inside the iteration kernel over NVLink peer memory" if args.exchange == "peer"
+                              else "29-double NCCL all-reduce per iteration"),
                "l2": "flushed before every timed step (256 MiB fill, untimed)"}
     else:
         src, tgt, off = make_c4(args.pairs)

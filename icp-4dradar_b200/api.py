@@ -21,7 +21,7 @@ EXPORTS = [
     "icp4r_create", "icp4r_destroy", "icp4r_last_error", "icp4r_version", "icp4r_default_opts", "icp4r_set_stream",
     "icp4r_synchronize", "icp4r_launch_count", "icp4r_set_profiling", "icp4r_last_profile", "icp4r_map_build", "icp4r_map_set_downsample", "icp4r_map_add_points",
     "icp4r_map_size", "icp4r_map_range", "icp4r_map_knn", "icp4r_map_knn_brute", "icp4r_map_sector", "icp4r_map_points",
-    "icp4r_register", "icp4r_register_map", "icp4r_register_map_batch", "icp4r_register_batch", "icp4r_shard_unique_id", "icp4r_shard_init",
+    "icp4r_register", "icp4r_register_map", "icp4r_register_map_batch", "icp4r_register_batch", "icp4r_shard_unique_id", "icp4r_shard_init", "icp4r_shard_ipc_export", "icp4r_shard_ipc_import",
     "icp4r_register_sharded", "icp4r_transform_points", "icp4r_doppler_filter",
 ]
 
@@ -346,6 +346,16 @@ class Icp4r:
     def shard_init(self, uid: bytes, rank: int, world: int):
         assert len(uid) == 128
         self._ck(self.lib.icp4r_shard_init(self.h, C.c_char_p(uid), C.c_int(rank), C.c_int(world)))
+
+    def shard_ipc_export(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._ck(self.lib.icp4r_shard_ipc_export(self.h, buf))
+        return buf.raw
+
+    def shard_ipc_import(self, handles, rank: int, world: int):
+        blob = b"".join(handles)
+        assert len(blob) == 64 * world
+        self._ck(self.lib.icp4r_shard_ipc_import(self.h, C.c_char_p(blob), C.c_int(rank), C.c_int(world)))
 
     def register_sharded(self, src, opts: Opts, axis: int, slab_lo: float, slab_hi: float):
         src = _f4(src)

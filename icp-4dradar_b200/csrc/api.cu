@@ -55,6 +55,9 @@ void release(DevBuf& b) {
 int shard_unique_id(char id_out[128]);
 int shard_init(Ctx* c, const char id_in[128], int rank, int world);
 void shard_destroy(Ctx* c);
+int shard_ipc_export(Ctx* c, unsigned char out[64]);
+int shard_ipc_import(Ctx* c, const unsigned char* handles, int rank, int world);
+void shard_ipc_close(Ctx* c);
 
 static void free_map(Map& m) {
     release(m.pts);
@@ -180,6 +183,9 @@ int icp4r_destroy(icp4r_handle h) {
     drop_graphs(c);
     for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
     shard_destroy(c);
+    shard_ipc_close(c);
+    release(c->d_xch);
+    release(c->d_xt);
     free_map(c->map);
     free_map(c->tmp);
     free_map(c->srcmap);
@@ -541,6 +547,18 @@ int icp4r_shard_init(icp4r_handle h, const char id[128], int rank, int world) {
     HCHECK(h);
     if (!id) return fail(c, ICP4R_ERR_INVALID, "null id");
     return shard_init(c, id, rank, world);
+}
+
+int icp4r_shard_ipc_export(icp4r_handle h, unsigned char handle_out[64]) {
+    HCHECK(h);
+    if (!handle_out) return fail(c, ICP4R_ERR_INVALID, "null output");
+    return shard_ipc_export(c, handle_out);
+}
+
+int icp4r_shard_ipc_import(icp4r_handle h, const unsigned char* handles, int rank, int world) {
+    HCHECK(h);
+    if (!handles) return fail(c, ICP4R_ERR_INVALID, "null handles");
+    return shard_ipc_import(c, handles, rank, world);
 }
 
 int icp4r_register_sharded(icp4r_handle h, const float* src, int32_t n, int mem, const icp4r_opts* opts, int axis, float slab_lo,

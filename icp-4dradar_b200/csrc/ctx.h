@@ -72,6 +72,18 @@ struct Map {
     int normals_k = 0;  // neighbours they were estimated from; reset to 0 whenever the grid is rebuilt
 };
 
+// ---- peer-memory exchange for slab-sharded registration (one process per GPU, NVLink P2P) --------------------
+constexpr int XCH_MAXW = 8;
+struct Xch {  // lives on every rank; peers write their partial sums straight into it
+    double vals[2][XCH_MAXW][ICP4R_ACC_LEN];     // [parity][writer rank][accumulator]
+    unsigned long long flag[2][XCH_MAXW];        // epoch the writer has published for that parity
+    unsigned long long seq;                      // exchanges this rank has completed (identical on all ranks)
+};
+struct XchTable {  // device-resident view of the communicator
+    Xch* peer[XCH_MAXW];  // peer[r] = rank r's Xch mapped into this process (own rank: the local buffer)
+    int rank, world;
+};
+
 struct GicpCorr {  // per source point, written by the linearisation, read by the LM error passes
     int idx;       // target index or -1
     int pad;
@@ -89,6 +101,7 @@ struct RegState {
     int pad2;
     double fit_sum;
     int fit_cnt;
+    int xch_timeout;     // set when a peer never published (fused sharded flavour)
     int done;
     int converged;
     int iterations;
@@ -119,6 +132,8 @@ struct RegParams {  // kernel parameters that change per call; lives in device m
     const double* tgt_normals;
     const float4* tgt_pts;  // target points by insertion index
     GicpCorr* corr;
+    // fused cross-rank sum over peer memory (NULL: single rank or the NCCL flavour)
+    const XchTable* xt;
 };
 
 struct GraphKey {
@@ -166,6 +181,9 @@ struct Ctx {
     // sharding (NCCL loaded lazily with dlopen)
     void* nccl_comm = nullptr;
     int rank = 0, world = 1;
+    DevBuf d_xch, d_xt;            // local exchange buffer and the peer table
+    void* xch_peers[XCH_MAXW] = {nullptr};  // peer mappings opened with cudaIpcOpenMemHandle
+    bool xch_ready = false;
 };
 
 inline int64_t& launches(Ctx* c) { return c->launches; }

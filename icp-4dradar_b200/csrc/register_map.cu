@@ -27,6 +27,8 @@ enum { MODE_ITER = 0, MODE_ITER_NOSOLVE = 1, MODE_FITNESS = 2, MODE_FITNESS_NOFI
 struct ResultBlock {  // what travels back to the host in one copy
     double T[16];
     icp4r_result res;
+    int xch_timeout;
+    int pad;
 };
 
 // Pose update from the reduced accumulators, run by one full warp (see solve_warp.cuh). `tot`, `Ts` and `ws`
@@ -127,6 +129,7 @@ __device__ void write_result(const RegState* st, ResultBlock* out) {
     out->res.n_fitness = st->fit_cnt;
     out->res.fitness = st->fit_cnt > 0 ? st->fit_sum / (double)st->fit_cnt : INFINITY;
     out->res.last_cost = st->last_cost;
+    out->xch_timeout = st->xch_timeout;
 }
 
 // One iteration (or the fitness pass). One warp owns one source point at a time, start to finish:
@@ -160,6 +163,7 @@ __global__ void __launch_bounds__(RM_THREADS, 1)
     __shared__ double tot[ICP4R_ACC_LEN];
     __shared__ double Ts[16];
     __shared__ bool is_last;
+    __shared__ int own_list[RM_THREADS], own_cnt[RM_WARPS], own_n;  // sharded maps: this block's owned source points
 
     __shared__ RegParams P;  // per-call parameters: one copy per block instead of ~25 registers per thread
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -252,18 +256,53 @@ __global__ void __launch_bounds__(RM_THREADS, 1)
     const int kq = FIT ? 1 : P.k;
     const int nwb = blockDim.x >> 5;  // warps in this block (<= RM_WARPS)
     const int gw = blockIdx.x * nwb + w, nw = gridDim.x * nwb;
-    for (int i = gw; i < n; i += nw) {
+    // Sharded map: the rank whose slab holds the transformed point owns it. Ownership changes with the pose, and a
+    // warp that strides over ALL points would find a random share of its points owned (the slowest warp sets the
+    // kernel time), so each block first compacts the owned points of its contiguous chunk into an ordered list
+    // (ballot + prefix: deterministic) and its warps stride over that list.
+    const bool sharded = P.shard_axis >= 0;
+    const int per = sharded ? (n + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int cbeg = sharded ? min(n, (int)blockIdx.x * per) : 0, cend = sharded ? min(n, cbeg + per) : 1;
+    for (int c0 = cbeg; c0 < cend; c0 += (int)blockDim.x) {
+    if (sharded) {
+        const int i = c0 + tid;
+        bool own = false;
+        if (i < cend) {
+            const float4 p = __ldg(P.src + i);
+            double pw[3];
+            xform_point(Ts, p.x, p.y, p.z, pw);
+            const float v = P.shard_axis == 0 ? (float)pw[0] : (P.shard_axis == 1 ? (float)pw[1] : (float)pw[2]);
+            own = (v >= P.slab_lo) && (v < P.slab_hi);
+        }
+        const unsigned bal = __ballot_sync(FULL, own);
+        __syncthreads();  // the previous chunk's list is no longer read
+        if (lane == 0) own_cnt[w] = __popc(bal);
+        __syncthreads();
+        int before = 0;
+        for (int j = 0; j < w; ++j) before += own_cnt[j];
+        if (own) own_list[before + __popc(bal & ((1u << lane) - 1u))] = i;
+        if (tid == 0) {
+            int t = 0;
+            for (int j = 0; j < nwb; ++j) t += own_cnt[j];
+            own_n = t;
+        }
+        __syncthreads();
+    }
+    for (int jj = 0;; ++jj) {
+        int i;
+        if (sharded) {
+            const int sl = w + jj * nwb;
+            if (sl >= own_n) break;
+            i = own_list[sl];
+        } else {
+            i = gw + jj * nw;
+            if (i >= n) break;
+        }
         const float4 p = __ldg(P.src + i);
         double pw[3];
         xform_point(Ts, p.x, p.y, p.z, pw);
         const float qx = (float)pw[0], qy = (float)pw[1], qz = (float)pw[2];
-        bool active = true;
-        if (P.shard_axis >= 0) {  // sharded map: the rank whose slab holds the transformed point owns it
-            const float v = P.shard_axis == 0 ? qx : (P.shard_axis == 1 ? qy : qz);
-            active = (v >= P.slab_lo) && (v < P.slab_hi);
-        }
-        uint64_t mine = KEY_EMPTY;
-        if (active) mine = warp_grid_knn<KK>(g, segs[w], qx, qy, qz, P.gate_f, P.gate_r, lane);
+        uint64_t mine = warp_grid_knn<KK>(g, segs[w], qx, qy, qz, P.gate_f, P.gate_r, lane);
         const bool have = (lane < kq) && (mine != KEY_EMPTY);
         if (!FIT && P.dump_idx && lane < kq) P.dump_idx[((size_t)iter * n + i) * kq + lane] = have ? key_idx(mine) : -1;
         const int found = __popc(__ballot_sync(FULL, have));
@@ -463,6 +502,7 @@ __global__ void __launch_bounds__(RM_THREADS, 1)
             __syncwarp();
         }
     }
+    }
 
     flush_parked();
     // block partial in a fixed order: value v = sum over warps 0..7 of lane v's accumulator
@@ -520,6 +560,45 @@ __global__ void __launch_bounds__(RM_THREADS, 1)
         tot[tid] = s;
     }
     __syncthreads();
+    if ((MODE == MODE_ITER || MODE == MODE_FITNESS) && P.xt != nullptr) {
+        // Slab-sharded map, fused flavour: the sum over ranks happens HERE, over NVLink peer memory, instead of a
+        // separate collective launch. Every rank's last block stores its 32 partial sums into every peer's
+        // exchange buffer, publishes an epoch flag, waits for all peers' flags and adds the contributions in rank
+        // order — so all ranks hold bit-identical totals, take the same decisions and therefore run the same
+        // number of exchanges. The epoch is that count (kept on the device), so consecutive exchanges alternate
+        // between the two buffers: a rank can only overwrite buffer p after every peer has published the epoch
+        // in between, i.e. after every peer finished reading p.
+        const XchTable xt = *P.xt;
+        Xch* mine = xt.peer[xt.rank];
+        const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long*>(&mine->seq) + 1ull;
+        const int par = (int)(epoch & 1ull);
+        if (tid < ICP4R_ACC_LEN)
+            for (int r = 0; r < xt.world; ++r) xt.peer[r]->vals[par][xt.rank][tid] = tot[tid];
+        __threadfence_system();
+        __syncthreads();
+        if (tid < xt.world) {
+            *reinterpret_cast<volatile unsigned long long*>(&xt.peer[tid]->flag[par][xt.rank]) = epoch;
+            volatile unsigned long long* f = &mine->flag[par][tid];
+            unsigned long long t0, t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            while (*f < epoch) {
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 10000000000ull) {  // 10 s: a peer never arrived; report instead of hanging the GPU
+                    st->xch_timeout = 1;
+                    break;
+                }
+            }
+        }
+        __syncthreads();
+        __threadfence_system();
+        if (tid < ICP4R_ACC_LEN) {
+            double sum = 0.0;
+            for (int r = 0; r < xt.world; ++r) sum += *reinterpret_cast<volatile double*>(&mine->vals[par][r][tid]);
+            tot[tid] = sum;
+        }
+        if (tid == 0) mine->seq = epoch;
+        __syncthreads();
+    }
     if (FIT) {
         if (tid == 0) {
             if (MODE == MODE_FITNESS) {
@@ -584,6 +663,7 @@ __global__ void init_state_kernel(RegState* st, const double* T0) {
         st->lm_last_conv = 0;
         st->fit_sum = 0.0;
         st->fit_cnt = 0;
+        st->xch_timeout = 0;
         st->done = 0;
         st->converged = 0;
         st->iterations = 0;
@@ -705,6 +785,10 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
     P.shard_axis = sharded ? shard_axis : -1;
     P.slab_lo = slab_lo;
     P.slab_hi = slab_hi;
+    const bool fused_shard = sharded && c->xch_ready && c->world > 1;
+    if (fused_shard) {
+        P.xt = c->d_xt.as<XchTable>();
+    }
     const bool gicp = o->residual == ICP4R_GICP;
     if (gicp) {
         if (sharded) return fail(c, ICP4R_ERR_UNSUPPORTED, "GICP is not available for sharded maps yet");
@@ -760,7 +844,7 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
                 gicp_lm_step(c, d_prm, d_st, it);
             }
             dispatch_iter(c, o->residual, k, MODE_FITNESS, blocks, threads, 1, g, pts, d_prm, d_st, d_part, d_out, 0);
-        } else if (sharded) {
+        } else if (sharded && !fused_shard) {
             for (int it = 0; it < iters; ++it) {
                 dispatch_iter(c, o->residual, k, MODE_ITER_NOSOLVE, blocks, threads, 1, g, pts, d_prm, d_st, d_part, d_out, it);
                 if (shard_allreduce(c, acc_ptr, ICP4R_ACC_LEN) != ICP4R_OK) enqueue_status = ICP4R_ERR_NCCL;
@@ -789,7 +873,7 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
         }
     }
     const bool want_graph = c->use_graph && n > 0 && !c->profiling && !(sharded && c->no_graph_sharded);
-    GraphKey key{o->residual, k, blocks, iters, threads | (sharded ? 1 << 16 : 0) | (gicp ? 1 << 17 : 0)};
+    GraphKey key{o->residual, k, blocks, iters, threads | (sharded ? 1 << 16 : 0) | (gicp ? 1 << 17 : 0) | (fused_shard ? 1 << 19 : 0)};
     cudaGraphExec_t exec = nullptr;
     if (want_graph) {
         // graphs bake the GridDesc by value: drop them when the map geometry or buffers changed
@@ -859,6 +943,7 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
             c->prof_ms.push_back(ms);
         }
     }
+    if (hs->out.xch_timeout) return fail(c, ICP4R_ERR_NCCL, "sharded registration: a peer rank never published its partial sums (timeout)");
     if (iters == 0) {  // no iteration ran: PCL reports convergence by max_iterations
         hs->out.res.converged = 1;
         hs->out.res.iterations = 0;

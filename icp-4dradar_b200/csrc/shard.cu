@@ -74,6 +74,57 @@ void shard_destroy(Ctx* c) {
     c->nccl_comm = nullptr;
 }
 
+// ---- peer-memory flavour: exchange buffers mapped across processes with CUDA IPC ------------------------------------
+int shard_ipc_export(Ctx* c, unsigned char out[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+    CKS(reserve(c, c->d_xch, sizeof(Xch)));
+    CK(cudaMemsetAsync(c->d_xch.p, 0, sizeof(Xch), c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    cudaIpcMemHandle_t hnd;
+    CK(cudaIpcGetMemHandle(&hnd, c->d_xch.p));
+    std::memcpy(out, &hnd, 64);
+    return ICP4R_OK;
+}
+
+int shard_ipc_import(Ctx* c, const unsigned char* handles, int rank, int world) {
+    if (world < 1 || world > XCH_MAXW || rank < 0 || rank >= world)
+        return fail(c, ICP4R_ERR_INVALID, "peer exchange supports 1..%d ranks (got rank %d of %d)", XCH_MAXW, rank, world);
+    if (!c->d_xch.p) return fail(c, ICP4R_ERR_STATE, "icp4r_shard_ipc_export has not been called on this handle");
+    XchTable t;
+    std::memset(&t, 0, sizeof(t));
+    t.rank = rank;
+    t.world = world;
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) {
+            t.peer[r] = c->d_xch.as<Xch>();
+            continue;
+        }
+        cudaIpcMemHandle_t hnd;
+        std::memcpy(&hnd, handles + 64 * (size_t)r, 64);
+        void* p = nullptr;
+        const cudaError_t e = cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return fail(c, ICP4R_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+        c->xch_peers[r] = p;
+        t.peer[r] = static_cast<Xch*>(p);
+    }
+    CKS(reserve(c, c->d_xt, sizeof(XchTable)));
+    CK(cudaMemcpyAsync(c->d_xt.p, &t, sizeof(t), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->rank = rank;
+    c->world = world;
+    c->xch_ready = true;
+    return ICP4R_OK;
+}
+
+void shard_ipc_close(Ctx* c) {
+    for (int r = 0; r < XCH_MAXW; ++r)
+        if (c->xch_peers[r]) {
+            cudaIpcCloseMemHandle(c->xch_peers[r]);
+            c->xch_peers[r] = nullptr;
+        }
+    c->xch_ready = false;
+}
+
 int shard_allreduce(Ctx* c, double* d_buf, int count) {
     if (c->world <= 1 && !c->nccl_comm) return ICP4R_OK;  // single rank: the sum is the local value
     NcclApi& a = api();

@@ -166,6 +166,13 @@ int icp4r_register_batch(icp4r_handle h, const float* src_xyzw, const int32_t* s
 /* rank 0 makes an id, the host program broadcasts the 128 bytes (any transport), every rank joins */
 int icp4r_shard_unique_id(char id_out[128]);
 int icp4r_shard_init(icp4r_handle h, const char id[128], int rank, int world);
+/* Optional faster cross-rank sum: instead of an NCCL call per iteration, each rank's iteration kernel writes its
+ * partial sums straight into every peer's exchange buffer over NVLink (CUDA IPC mapping) and adds the peers'
+ * contributions itself, so a sharded iteration stays ONE kernel. Every rank exports a 64-byte handle, the host
+ * program gathers them (any transport), every rank imports the full list (handles = world x 64 bytes, rank order).
+ * One process per GPU, at most 8 ranks; once imported, icp4r_register_sharded uses this path. */
+int icp4r_shard_ipc_export(icp4r_handle h, unsigned char handle_out[64]);
+int icp4r_shard_ipc_import(icp4r_handle h, const unsigned char* handles, int rank, int world);
 /* registration against the union of all ranks' maps: every rank passes the same source; each source
  * point is owned by the rank whose slab [slab_lo, slab_hi) along `axis` contains its transformed
  * position; the 29 partial accumulators are summed across ranks every iteration; all ranks return the

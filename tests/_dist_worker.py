@@ -3,8 +3,8 @@
 mode cpu : gloo, no GPU. Checks the sharding math with the ORACLE standing in for the device kernel:
            sum over ranks of (accumulators of the source points a rank owns, searched in its slab+halo)
            == accumulators over the whole map, and the per-rank pair ranges tile the batch.
-mode gpu : one rank per GPU, NCCL inside libicp4r_cuda (icp4r_register_sharded); the sharded pose must equal the
-           single-GPU pose on the whole map and the oracle's.
+mode gpu : one rank per GPU, icp4r_register_sharded first with the NCCL all-reduce, then with the in-kernel peer-memory
+           exchange (icp4r_shard_ipc_*); the sharded pose must equal the single-GPU pose on the whole map and the oracle's.
 """
 import os
 import sys
@@ -79,6 +79,26 @@ def main():
             assert res.n_corr == r1.n_corr == ro.n_corr and res.n_fitness == r1.n_fitness
             assert abs(res.fitness - r1.fitness) < 1e-9 * max(r1.fitness, 1)
             print("DIST-GPU-OK", res.n_corr)
+        # fused flavour: the cross-rank sum runs inside the iteration kernel over peer memory (CUDA IPC), no NCCL call
+        mine_h = h.shard_ipc_export()
+        hs = [None] * world
+        dist.all_gather_object(hs, mine_h)
+        h.shard_ipc_import(hs, rank, world)
+        for rep, oe in enumerate([o, o, pkg.default_opts(residual=pkg.P2P_SVD, k=1, max_iterations=40, max_corr_dist=gate, early_exit=1), o]):
+            dist.barrier()
+            Tf, rf = h.register_sharded(scan, oe, 0, lo, hi)
+            Ts = [None] * world
+            dist.all_gather_object(Ts, (Tf, rf.iterations, rf.n_corr))
+            for other in Ts:
+                assert np.array_equal(other[0], Tf) and other[1:] == (rf.iterations, rf.n_corr), "ranks disagree (fused exchange)"
+            if oe is o:
+                assert np.abs(Tf - T).max() < 1e-10, (rep, np.abs(Tf - T).max())
+                assert rf.n_corr == res.n_corr and rf.n_fitness == res.n_fitness
+            elif rank == 0:
+                T1e, r1e, _ = h2.register_map(scan, oe)
+                assert np.abs(Tf - T1e).max() < 1e-9 and rf.iterations == r1e.iterations < 40, (rf.iterations, r1e.iterations)
+        if rank == 0:
+            print("DIST-GPU-FUSED-OK")
         h.close()
     dist.barrier()
     dist.destroy_process_group()

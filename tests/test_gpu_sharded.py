@@ -20,4 +20,4 @@ def test_register_sharded_two_ranks():
                         "--master-port", "29613", os.path.join(ROOT, "tests", "_dist_worker.py"), "gpu"],
                        capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert "DIST-GPU-OK" in r.stdout
+    assert "DIST-GPU-OK" in r.stdout and "DIST-GPU-FUSED-OK" in r.stdout, r.stdout[-2000:]
