@@ -170,6 +170,8 @@ int icp4r_create(int device, icp4r_handle* out) {
     }
     const char* ng = std::getenv("ICP4R_NO_GRAPH");
     c->use_graph = !(ng && ng[0] == '1');
+    const char* nh = std::getenv("ICP4R_NO_HINTS");
+    c->use_hints = !(nh && nh[0] == '1');
     *out = c;
     return ICP4R_OK;
 }
@@ -186,6 +188,7 @@ int icp4r_destroy(icp4r_handle h) {
     shard_ipc_close(c);
     release(c->d_xch);
     release(c->d_xt);
+    release(c->d_nbprev);
     free_map(c->map);
     free_map(c->tmp);
     free_map(c->srcmap);

@@ -134,6 +134,8 @@ struct RegParams {  // kernel parameters that change per call; lives in device m
     GicpCorr* corr;
     // fused cross-rank sum over peer memory (NULL: single rank or the NCCL flavour)
     const XchTable* xt;
+    // neighbours found at the previous iteration, K per source point (NULL: no hints — sharded maps, GICP)
+    int32_t* nb_prev;
 };
 
 struct GraphKey {
@@ -181,7 +183,8 @@ struct Ctx {
     // sharding (NCCL loaded lazily with dlopen)
     void* nccl_comm = nullptr;
     int rank = 0, world = 1;
-    DevBuf d_xch, d_xt;            // local exchange buffer and the peer table
+    DevBuf d_xch, d_xt, d_nbprev;
+    bool use_hints = true;  // ICP4R_NO_HINTS=1 turns the previous-iteration search bound off (A/B measurements)            // local exchange buffer and the peer table
     void* xch_peers[XCH_MAXW] = {nullptr};  // peer mappings opened with cudaIpcOpenMemHandle
     bool xch_ready = false;
 };

@@ -31,9 +31,8 @@ struct WarpSegs {  // per-warp shared-memory scratch
 };
 
 __device__ __forceinline__ int cell_of(float v, float o, float inv, int dim) {
-    float f = floorf(__fmul_rn(__fsub_rn(v, o), inv));
-    f = fminf(fmaxf(f, 0.0f), (float)(dim - 1));  // NaN -> 0
-    return (int)f;
+    const int c = __float2int_rd(__fmul_rn(__fsub_rn(v, o), inv));  // floor; NaN -> 0, +-inf saturate
+    return min(max(c, 0), dim - 1);
 }
 
 template <int K>
@@ -96,9 +95,14 @@ __device__ __forceinline__ void scan_segments(const float4* __restrict__ sorted,
 }
 
 // Returns, in lane r < K, the r-th nearest neighbour's packed key (KEY_EMPTY if fewer exist).
+//
+// `hint` >= 0: the caller knows K distinct valid points with d2 <= hint (the neighbours found for this source point at
+// the previous pose). The k-th distance can then not exceed `hint`, so ONE pass over the cells that intersect the ball
+// of that radius (clipped to the gate box) sees every point that can be part of the answer: no own-cell probe, no
+// shell-by-shell proof, one merge. The result is the same set, the hint only removes work.
 template <int K>
 __device__ __forceinline__ uint64_t warp_grid_knn(const GridDesc& g, WarpSegs& sg, float qx, float qy, float qz, float gate_f,
-                                                  float gate_r, int lane) {
+                                                  float gate_r, int lane, float hint = -1.0f) {
     const float4* __restrict__ sorted = g.sorted;
     const uint32_t* __restrict__ cs = g.cell_start;
     const float qmax = fmaxf(fabsf(qx), fmaxf(fabsf(qy), fabsf(qz)));
@@ -108,16 +112,29 @@ __device__ __forceinline__ uint64_t warp_grid_knn(const GridDesc& g, WarpSegs& s
     const int cy = cell_of(qy, g.oy, g.inv_cell, g.ny);
     const int cz = cell_of(qz, g.oz, g.inv_cell, g.nz);
     int lox = 0, hix = g.nx - 1, loy = 0, hiy = g.ny - 1, loz = 0, hiz = g.nz - 1;
-    if (gate_r < 3.0e38f) {
-        const float gr = gate_r + margin;
-        lox = cell_of(qx - gr, g.ox, g.inv_cell, g.nx);
-        hix = cell_of(qx + gr, g.ox, g.inv_cell, g.nx);
-        loy = cell_of(qy - gr, g.oy, g.inv_cell, g.ny);
-        hiy = cell_of(qy + gr, g.oy, g.inv_cell, g.ny);
-        loz = cell_of(qz - gr, g.oz, g.inv_cell, g.nz);
-        hiz = cell_of(qz + gr, g.oz, g.inv_cell, g.nz);
+    const float gr = gate_r < 3.0e38f ? gate_r + margin : 3.4e38f;
+    bool hinted = (hint >= 0.0f) && (hint < 3.0e38f);
+    // cells that can hold part of the answer: the gate box, or the (smaller) box around the hint ball
+    float br = hinted ? fminf(gr, sqrtf(hint) * 1.000001f + margin) : gr;
+    int rneed;
+    for (;;) {
+        if (br < 3.0e38f) {
+            lox = cell_of(qx - br, g.ox, g.inv_cell, g.nx);
+            hix = cell_of(qx + br, g.ox, g.inv_cell, g.nx);
+            loy = cell_of(qy - br, g.oy, g.inv_cell, g.ny);
+            hiy = cell_of(qy + br, g.oy, g.inv_cell, g.ny);
+            loz = cell_of(qz - br, g.oz, g.inv_cell, g.nz);
+            hiz = cell_of(qz + br, g.oz, g.inv_cell, g.nz);
+        } else {
+            lox = 0, hix = g.nx - 1, loy = 0, hiy = g.ny - 1, loz = 0, hiz = g.nz - 1;
+        }
+        rneed = max(max(max(cx - lox, hix - cx), max(cy - loy, hiy - cy)), max(cz - loz, hiz - cz));
+        if (!hinted || rneed <= GRID_RING_CAP) break;
+        hinted = false;  // a hint ball wider than the ring cap: search without it
+        br = gr;
     }
-    const int rneed = max(max(max(cx - lox, hix - cx), max(cy - loy, hiy - cy)), max(cz - loz, hiz - cz));
+    // candidates farther than the hint can not be part of the answer (an equal distance still can)
+    const uint64_t hint_key = ((uint64_t)__float_as_uint(hint) << 32) | 0xFFFFFFFFull;
 
     TopK<K> list;
     list.clear();
@@ -127,8 +144,8 @@ __device__ __forceinline__ uint64_t warp_grid_knn(const GridDesc& g, WarpSegs& s
     // Dense neighbourhoods (walls): look at the query's own cell first. Its k-th distance then prunes the rows and
     // the x-extent of the next shells, so a 3x3x3 block that would hold hundreds of candidates shrinks to the few
     // cells that can still contain a closer point.
-    int R0 = min(1, rneed);
-    if (rneed > 0) {
+    int R0 = hinted ? rneed : min(1, rneed);
+    if (rneed > 0 && !hinted) {
         const uint32_t ci = (uint32_t)(cz * g.ny + cy) * (uint32_t)g.nx + (uint32_t)cx;
         if (__ldg(cs + ci + 1) - __ldg(cs + ci) >= 2u * K) R0 = 0;
     }
@@ -136,8 +153,8 @@ __device__ __forceinline__ uint64_t warp_grid_knn(const GridDesc& g, WarpSegs& s
         // rows (dy, dz) of the shell, 32 at a time: each lane fetches the cell ranges of one row
         const int side = 2 * R + 1, rows = side * side;
         const float inv_side = 1.0f / (float)side;  // r / side without an integer division (exact for these small r)
-        const bool prune = kth != KEY_EMPTY;
-        const float kd = key_d2(kth) * 1.000001f;  // inflated: a pruned cell can not even hold a tie
+        const bool prune = hinted || kth != KEY_EMPTY;
+        const float kd = (hinted ? hint : key_d2(kth)) * 1.000001f;  // inflated: a pruned cell can not even hold a tie
         for (int rb = 0; rb < rows; rb += 32) {
             const int r = rb + lane;
             uint32_t s0 = 0, e0 = 0, s1 = 0, e1 = 0;
@@ -184,13 +201,17 @@ __device__ __forceinline__ uint64_t warp_grid_knn(const GridDesc& g, WarpSegs& s
                     }
                 }
             }
-            scan_segments<K>(sorted, sg, s0, e0, s1, e1, lane, qx, qy, qz, gate_f, kth, list);
+            scan_segments<K>(sorted, sg, s0, e0, s1, e1, lane, qx, qy, qz, gate_f, hinted ? hint_key : kth, list);
         }
         prev = R;
         if (mine != KEY_EMPTY) list.insert(mine);  // carry the previous shells' winners (lanes < K)
         mine = warp_merge_topk<K>(list, lane);
         list.clear();
         kth = __shfl_sync(FULL, mine, K - 1);
+        if (hinted) {  // the pass covered the whole hint box
+            done = true;
+            break;
+        }
 
         float bound = 3.4e38f;
         if (cx - R > lox) bound = fminf(bound, qx - (g.ox + (float)(cx - R) * g.cell));

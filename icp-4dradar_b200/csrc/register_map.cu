@@ -199,12 +199,14 @@ __global__ void __launch_bounds__(RM_THREADS, 1)
     // P2PLANE_KNN: a warp finds the neighbours of its points one after the other but fits the planes of up to PARK
     // points at once, one point per lane (the fit is ~400 fp64 instructions that every lane would otherwise execute
     // redundantly for every single point); lane q keeps point q's neighbour indices until the flush
-    int parked = 0, my_src = -1;
-    int my_nb[PARKED ? K : 1];
+    int parked = 0;
+    __shared__ int nbq[PARKED ? RM_WARPS : 1][PARK][K + 1];  // parked neighbour indices (+ the source index in slot K)
     auto flush_parked = [&]() {
         if (PARKED) {
+            __syncwarp();  // the parked indices were written by other lanes
             if (lane < parked) {
-                const float4 p = __ldg(P.src + my_src);
+                const int* my_nb = nbq[w][lane];
+                const float4 p = __ldg(P.src + my_nb[K]);
                 double pw[3];
                 xform_point(Ts, p.x, p.y, p.z, pw);
                 float Pn[K][3];
@@ -302,8 +304,22 @@ __global__ void __launch_bounds__(RM_THREADS, 1)
         double pw[3];
         xform_point(Ts, p.x, p.y, p.z, pw);
         const float qx = (float)pw[0], qy = (float)pw[1], qz = (float)pw[2];
-        uint64_t mine = warp_grid_knn<KK>(g, segs[w], qx, qy, qz, P.gate_f, P.gate_r, lane);
+        // the neighbours of the previous iteration bound this iteration's k-th distance (see warp_grid_knn)
+        float hint = -1.0f;
+        int32_t* nbp = P.nb_prev ? P.nb_prev + (size_t)i * K : nullptr;
+        if (nbp != nullptr && (FIT ? P.max_iterations > 0 : iter > 0)) {
+            const int pj = lane < kq ? __ldcg(nbp + lane) : 0;
+            float dh = 0.0f;
+            if (lane < kq && pj >= 0) {
+                const float4 c = __ldg(pts + pj);
+                dh = dist2_exact(qx, qy, qz, c.x, c.y, c.z);
+            }
+            const unsigned hb = __reduce_max_sync(FULL, __float_as_uint(dh));  // d2 >= 0: bit order == value order; NaN sorts last
+            if (!__any_sync(FULL, pj < 0) && hb < 0x7f800000u) hint = __uint_as_float(hb);
+        }
+        uint64_t mine = warp_grid_knn<KK>(g, segs[w], qx, qy, qz, P.gate_f, P.gate_r, lane, hint);
         const bool have = (lane < kq) && (mine != KEY_EMPTY);
+        if (!FIT && nbp != nullptr && lane < kq) nbp[lane] = have ? key_idx(mine) : -1;
         if (!FIT && P.dump_idx && lane < kq) P.dump_idx[((size_t)iter * n + i) * kq + lane] = have ? key_idx(mine) : -1;
         const int found = __popc(__ballot_sync(FULL, have));
         float4 nb = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -341,12 +357,8 @@ __global__ void __launch_bounds__(RM_THREADS, 1)
             }
         } else if (RK == ICP4R_P2PLANE_KNN && PARKED) {
             if (found == kq && kq >= 3) {  // park the neighbours in lane `parked`; the fit happens in flush_parked()
-#pragma unroll
-                for (int r = 0; r < K; ++r) {
-                    const int v = key_idx(__shfl_sync(FULL, mine, r));
-                    if (lane == parked) my_nb[PARKED ? r : 0] = v;
-                }
-                if (lane == parked) my_src = i;
+                if (lane < kq) nbq[PARKED ? w : 0][parked][lane] = key_idx(mine);
+                if (lane == K) nbq[PARKED ? w : 0][parked][K] = i;
                 if (++parked == PARK) flush_parked();
             }
         } else if (RK == ICP4R_P2PLANE_KNN) {
@@ -790,6 +802,10 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
         P.xt = c->d_xt.as<XchTable>();
     }
     const bool gicp = o->residual == ICP4R_GICP;
+    if (!sharded && !gicp && c->use_hints) {
+        CKS(reserve_grow(c, c->d_nbprev, (size_t)n * ICP4R_MAX_K * sizeof(int32_t)));
+        P.nb_prev = c->d_nbprev.as<int32_t>();
+    }
     if (gicp) {
         if (sharded) return fail(c, ICP4R_ERR_UNSUPPORTED, "GICP is not available for sharded maps yet");
         // covariances (normals) of both clouds from their own k nearest neighbours; the map's are cached per k
@@ -989,6 +1005,7 @@ int register_scans_against_map(Ctx* c, Map& mp, const float4* d_src, const int32
         CKS(reserve_grow(c, c->bm_T0, (size_t)B * 16 * sizeof(double)));
         CKS(reserve_grow(c, c->bm_res, (size_t)B * sizeof(ResultBlock)));
         CKS(reserve_grow(c, c->bm_partials, (size_t)B * blocks * ICP4R_ACC_LEN * sizeof(double)));
+        CKS(reserve_grow(c, c->d_nbprev, (size_t)off_host[s0 + B] * ICP4R_MAX_K * sizeof(int32_t)));
         const bool moved = old_ptrs[0] != c->bm_params.p || old_ptrs[1] != c->bm_state.p || old_ptrs[2] != c->bm_res.p ||
                            old_ptrs[3] != c->bm_partials.p;
         Stage* hs = static_cast<Stage*>(c->h_pinned);
@@ -1007,6 +1024,7 @@ int register_scans_against_map(Ctx* c, Map& mp, const float4* d_src, const int32
             P.mse_abs_eps = o->mse_abs_eps;
             P.plane_thresh = o->plane_thresh;
             P.shard_axis = -1;
+            P.nb_prev = c->use_hints ? c->d_nbprev.as<int32_t>() + (size_t)off_host[s0 + b] * ICP4R_MAX_K : nullptr;
             std::memcpy(hs[b].T0, T0s_host ? T0s_host + 16 * (size_t)(s0 + b) : o->T0, sizeof(hs[b].T0));
         }
         RegParams* d_prm = c->bm_params.as<RegParams>();
