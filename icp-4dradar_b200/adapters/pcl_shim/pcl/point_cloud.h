@@ -1,5 +1,6 @@
 // Minimal pcl::PointCloud stand-in (see point_types.h in this directory for when it is used).
 #pragma once
+#include <cstdint>
 #include <memory>
 #include <vector>
 
@@ -12,6 +13,8 @@ class PointCloud {
     using Ptr = std::shared_ptr<PointCloud<PointT>>;
     using ConstPtr = std::shared_ptr<const PointCloud<PointT>>;
     std::vector<PointT, Eigen::aligned_allocator<PointT>> points;
+    std::uint32_t width = 0, height = 0;
+    bool is_dense = true;
     std::size_t size() const { return points.size(); }
     bool empty() const { return points.empty(); }
     void clear() { points.clear(); }

@@ -8,6 +8,7 @@
 
 #include "icp4r/kd_tree.hpp"
 #include "icp4r/registration.hpp"
+#include "icp4r/voxel_grid.hpp"
 
 using PointType = pcl::PointXYZI;
 
@@ -110,6 +111,26 @@ int main() {
     icp2.setInputTarget(empty);
     icp2.align(*Final);
     REQUIRE(!icp2.hasConverged());
+    // ---- the pcl::VoxelGrid shape, as radar_odometry.cpp:426-429 uses it
+    {
+        icp4r::VoxelGrid<PointType> sor;
+        pcl::PointCloud<PointType>::Ptr downSizeFilterMap(new pcl::PointCloud<PointType>);
+        sor.setInputCloud(cloud_tar_in);
+        sor.setLeafSize(0.5f, 0.5f, 0.5f);
+        sor.filter(*downSizeFilterMap);
+        REQUIRE(!downSizeFilterMap->empty() && downSizeFilterMap->size() <= cloud_tar_in->size());
+        // every input point's leaf holds exactly one output point: count-weighted means reproduce the cloud's mean
+        std::vector<long long> keys_in, keys_out;
+        auto leaf_key = [](const PointType& p) {
+            return ((long long)std::floor(p.x * 2.f) + 100000) + ((long long)std::floor(p.y * 2.f) + 100000) * 1000000LL +
+                   ((long long)std::floor(p.z * 2.f) + 100000) * 1000000000000LL;
+        };
+        for (const auto& p : cloud_tar_in->points) keys_in.push_back(leaf_key(p));
+        std::sort(keys_in.begin(), keys_in.end());
+        keys_in.erase(std::unique(keys_in.begin(), keys_in.end()), keys_in.end());
+        REQUIRE(keys_in.size() == downSizeFilterMap->size());
+        std::printf("voxel-grid-shape: %zu -> %zu points\n", cloud_tar_in->size(), downSizeFilterMap->size());
+    }
     std::printf("adapters ok\n");
     return 0;
 }

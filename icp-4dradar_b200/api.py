@@ -22,7 +22,7 @@ EXPORTS = [
     "icp4r_synchronize", "icp4r_launch_count", "icp4r_set_profiling", "icp4r_last_profile", "icp4r_map_build", "icp4r_map_set_downsample", "icp4r_map_add_points",
     "icp4r_map_size", "icp4r_map_range", "icp4r_map_knn", "icp4r_map_knn_brute", "icp4r_map_sector", "icp4r_map_points",
     "icp4r_register", "icp4r_register_map", "icp4r_register_map_batch", "icp4r_register_batch", "icp4r_shard_unique_id", "icp4r_shard_init", "icp4r_shard_ipc_export", "icp4r_shard_ipc_import",
-    "icp4r_register_sharded", "icp4r_transform_points", "icp4r_doppler_filter",
+    "icp4r_register_sharded", "icp4r_transform_points", "icp4r_voxel_grid", "icp4r_doppler_filter",
 ]
 
 
@@ -382,6 +382,26 @@ class Icp4r:
         return mask, r
 
     # ---- helpers
+    def voxel_grid(self, pts, leaf: float):
+        """pcl::VoxelGrid centroid filter. pts None: the handle's map (returns numpy); numpy -> numpy; torch CUDA -> torch."""
+        cnt = C.c_int32(0)
+        if pts is None:
+            n, _ = self.map_size()
+            out = np.empty((max(n, 1), 4), np.float32)
+            self._ck(self.lib.icp4r_voxel_grid(self.h, None, C.c_int32(0), C.c_int(HOST), C.c_float(leaf), C.c_void_p(out.ctypes.data),
+                                               C.c_int32(out.shape[0]), C.byref(cnt)))
+            return out[:cnt.value].copy()
+        pts = _f4(pts)
+        p, mem = _ptr(pts)
+        if mem == HOST:
+            out = np.empty((max(pts.shape[0], 1), 4), np.float32)
+        else:
+            import torch
+            out = torch.empty((max(pts.shape[0], 1), 4), dtype=torch.float32, device=pts.device)
+        self._ck(self.lib.icp4r_voxel_grid(self.h, p, C.c_int32(pts.shape[0]), C.c_int(mem), C.c_float(leaf), _ptr(out)[0],
+                                           C.c_int32(out.shape[0]), C.byref(cnt)))
+        return out[:cnt.value].copy() if mem == HOST else out[:cnt.value]
+
     def transform_points(self, T, pts):
         pts = _f4(pts)
         p, mem = _ptr(pts)

@@ -189,6 +189,11 @@ int icp4r_destroy(icp4r_handle h) {
     release(c->d_xch);
     release(c->d_xt);
     release(c->d_nbprev);
+    release(c->vg_keys);
+    release(c->vg_vals);
+    release(c->vg_sort);
+    release(c->vg_tiles);
+    release(c->vg_out);
     free_map(c->map);
     free_map(c->tmp);
     free_map(c->srcmap);
@@ -621,5 +626,35 @@ extern "C" int icp4r_transform_points(icp4r_handle h, const double T[16], const 
         CK(cudaMemcpyAsync(xyzw_out, dout, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
     }
+    return ICP4R_OK;
+}
+
+extern "C" int icp4r_voxel_grid(icp4r_handle h, const float* xyzw, int32_t n, int mem, float leaf, float* xyzw_out, int32_t cap, int32_t* n_out) {
+    HCHECK(h);
+    if (!n_out || n < 0 || cap < 0 || (cap > 0 && !xyzw_out) || bad_mem(mem)) return fail(c, ICP4R_ERR_INVALID, "icp4r_voxel_grid: bad arguments");
+    const float4* din = nullptr;
+    const uint8_t* dvalid = nullptr;
+    if (xyzw) {
+        const void* p;
+        CKS(stage_in(c, c->d_q, xyzw, (size_t)n * sizeof(float4), mem, &p));
+        din = static_cast<const float4*>(p);
+    } else {  // the handle's own map (deleted points skipped)
+        if (!c->map.built) return fail(c, ICP4R_ERR_STATE, "icp4r_voxel_grid(NULL) before icp4r_map_build");
+        din = c->map.pts.as<float4>();
+        dvalid = c->map.valid.as<uint8_t>();
+        n = c->map.m;
+    }
+    float4* dout = reinterpret_cast<float4*>(xyzw_out);
+    if (mem == ICP4R_HOST) {
+        CKS(reserve(c, c->vg_out, (size_t)std::max(cap, 1) * sizeof(float4)));
+        dout = c->vg_out.as<float4>();
+    }
+    int cnt = 0;
+    CKS(voxel_grid(c, din, dvalid, n, leaf, dout, cap, &cnt));
+    if (mem == ICP4R_HOST && cap > 0 && cnt > 0) {
+        CK(cudaMemcpyAsync(xyzw_out, dout, (size_t)std::min(cnt, cap) * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    *n_out = cnt;
     return ICP4R_OK;
 }

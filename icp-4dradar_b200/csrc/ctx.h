@@ -184,6 +184,7 @@ struct Ctx {
     void* nccl_comm = nullptr;
     int rank = 0, world = 1;
     DevBuf d_xch, d_xt, d_nbprev;
+    DevBuf vg_keys, vg_vals, vg_sort, vg_tiles, vg_out;  // voxel-grid centroid filter
     bool use_hints = true;  // ICP4R_NO_HINTS=1 turns the previous-iteration search bound off (A/B measurements)            // local exchange buffer and the peer table
     void* xch_peers[XCH_MAXW] = {nullptr};  // peer mappings opened with cudaIpcOpenMemHandle
     bool xch_ready = false;
@@ -208,6 +209,7 @@ void gate_params(double max_dist, float* gate_f, float* gate_r);
 
 // map_ops.cu
 int map_downsample_add(Ctx* c, Map& mp, int n, int* n_replaced_host, bool force_sequential);
+int voxel_grid(Ctx* c, const float4* d_pts, const uint8_t* d_valid, int n, float leaf, float4* d_out, int cap, int* n_out_host);
 int map_sector(Ctx* c, const Map& mp, const float centre[3], float radius, float heading, int32_t* d_out, int cap, int* n_out_host);
 
 // register_map.cu

@@ -315,7 +315,13 @@ __global__ void __launch_bounds__(RM_THREADS, 1)
                 dh = dist2_exact(qx, qy, qz, c.x, c.y, c.z);
             }
             const unsigned hb = __reduce_max_sync(FULL, __float_as_uint(dh));  // d2 >= 0: bit order == value order; NaN sorts last
-            if (!__any_sync(FULL, pj < 0) && hb < 0x7f800000u) hint = __uint_as_float(hb);
+            if (!__any_sync(FULL, pj < 0)) {
+                if (hb < 0x7f800000u) hint = __uint_as_float(hb);
+            } else if (P.gate_r < 3.0e38f) {
+                // fewer than k neighbours inside the gate last time: most likely still so. The gate itself is the
+                // bound then: one pass over the gate ball instead of growing shell by shell up to it.
+                hint = P.gate_f;
+            }
         }
         uint64_t mine = warp_grid_knn<KK>(g, segs[w], qx, qy, qz, P.gate_f, P.gate_r, lane, hint);
         const bool have = (lane < kq) && (mine != KEY_EMPTY);

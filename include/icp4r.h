@@ -205,6 +205,15 @@ int icp4r_doppler_filter(icp4r_handle h, const float* xyziv, int32_t n, int mem,
 int icp4r_transform_points(icp4r_handle h, const double T[16], const float* xyzw, int32_t n, int mem,
                            float* xyzw_out);
 
+/* Centroid-per-leaf down-sampling: pcl::VoxelGrid<PointXYZI>::filter with setLeafSize(leaf, leaf, leaf) as the
+ * scan-to-map node runs it over the accumulated map every frame (radar_odometry.cpp:426-429). One output point per
+ * occupied leaf (float mean of x, y, z, intensity), ascending leaf index (x fastest). Non-finite points are
+ * skipped. xyzw == NULL: filter the handle's map (deleted points skipped, n ignored). At most `cap` points are
+ * written; *n_out receives the number of occupied leaves (call again with a larger buffer if it exceeds cap).
+ * A leaf so small that the leaf index would overflow 31 bits is an error (PCL passes the cloud through instead). */
+int icp4r_voxel_grid(icp4r_handle h, const float* xyzw, int32_t n, int mem, float leaf, float* xyzw_out,
+                     int32_t cap, int32_t* n_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -88,6 +88,7 @@ def lib() -> C.CDLL:
         _lib.orc_plane_fit.restype = C.c_int
         _lib.orc_map_add_points.restype = C.c_int
         _lib.orc_map_sector.restype = C.c_int
+        _lib.orc_voxel_grid.restype = C.c_int
         _lib.orc_num_threads.restype = C.c_int
         _lib.orc_icp_p2p_f32.restype = C.c_int
     return _lib
@@ -422,6 +423,17 @@ class OracleMap:
         n = lib().orc_map_sector(_p(self.pts), _p(self.valid), C.c_int(self.m), _p(c), C.c_float(radius),
                                  C.c_float(heading), _p(out), C.c_int(out.shape[0]))
         return out[:n].copy()
+
+
+def voxel_grid(pts, leaf, valid=None):
+    """pcl::VoxelGrid centroid filter restated (oracle.c: orc_voxel_grid). Returns [L,4] float32, ascending leaf index."""
+    pts = f4(pts)
+    out = np.zeros((max(pts.shape[0], 1), 4), np.float32)
+    v = None if valid is None else np.ascontiguousarray(valid, np.uint8)
+    n = lib().orc_voxel_grid(_p(pts), _p(v) if v is not None else None, C.c_int(pts.shape[0]), C.c_float(leaf), _p(out), C.c_int(out.shape[0]))
+    if n < 0:
+        raise ValueError("leaf size too small for the extent of the cloud")
+    return out[:n].copy()
 
 
 def num_threads() -> int:

@@ -809,6 +809,77 @@ int orc_map_sector(const float* pts, const uint8_t* valid, int m, const float c[
     return cnt;
 }
 
+/* ------------------------------------------------------------------ VoxelGrid (PCL 1.8 restatement) --- */
+/* pcl::VoxelGrid<PointXYZI>::applyFilter with the defaults the reference uses (src/radar_odometry.cpp:426-429:
+ * setLeafSize(0.5, 0.5, 0.5), downsample_all_data, min_points_per_voxel 0, no field filter). PCL (1.8, the ROS
+ * Melodic version the reference builds against) is not part of /root/reference; this restates its published
+ * algorithm: min/max over finite points, min_b = floor(min * inv_leaf), leaf index
+ * (floor(x*inv) - min_b.x) + (floor(y*inv) - min_b.y) * div.x + (floor(z*inv) - min_b.z) * div.x * div.y in float
+ * arithmetic, points grouped by leaf index ascending, centroid = float sums / count (CentroidPoint accumulators).
+ * PCL orders the points of a leaf with an unstable std::sort; this restatement fixes the order to ascending input
+ * index. Parity unpinned: the reference has no test vector for this step and PCL cannot be built here. */
+typedef struct { uint32_t key; int32_t idx; } vg_pair;
+static int vg_cmp(const void* a, const void* b) {
+    const vg_pair *x = (const vg_pair*)a, *y = (const vg_pair*)b;
+    if (x->key != y->key) return x->key < y->key ? -1 : 1;
+    return x->idx < y->idx ? -1 : (x->idx > y->idx ? 1 : 0);
+}
+
+int orc_voxel_grid(const float* pts, const uint8_t* valid, int n, float leaf, float* out, int cap) {
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    int nf = 0;
+    for (int i = 0; i < n; ++i) {
+        const float* p = pts + 4 * (size_t)i;
+        if ((valid && !valid[i]) || !isfinite(p[0]) || !isfinite(p[1]) || !isfinite(p[2])) continue;
+        for (int a = 0; a < 3; ++a) {
+            if (p[a] < mn[a]) mn[a] = p[a];
+            if (p[a] > mx[a]) mx[a] = p[a];
+        }
+        ++nf;
+    }
+    if (nf == 0) return 0;
+    const float inv = 1.0f / leaf;
+    int min_b[3];
+    long long div[3];
+    for (int a = 0; a < 3; ++a) {
+        min_b[a] = (int)floorf(mn[a] * inv);
+        div[a] = (long long)(int)floorf(mx[a] * inv) - min_b[a] + 1;
+    }
+    if ((double)div[0] * (double)div[1] * (double)div[2] > 2147483647.0) return -1;
+    const int mul1 = (int)div[0], mul2 = (int)(div[0] * div[1]);
+    vg_pair* pr = (vg_pair*)malloc(sizeof(vg_pair) * (size_t)nf);
+    int k = 0;
+    for (int i = 0; i < n; ++i) {
+        const float* p = pts + 4 * (size_t)i;
+        if ((valid && !valid[i]) || !isfinite(p[0]) || !isfinite(p[1]) || !isfinite(p[2])) continue;
+        const int i0 = (int)(floorf(p[0] * inv) - (float)min_b[0]);
+        const int i1 = (int)(floorf(p[1] * inv) - (float)min_b[1]);
+        const int i2 = (int)(floorf(p[2] * inv) - (float)min_b[2]);
+        pr[k].key = (uint32_t)(i0 + i1 * mul1 + i2 * mul2);
+        pr[k].idx = i;
+        ++k;
+    }
+    qsort(pr, (size_t)nf, sizeof(vg_pair), vg_cmp);
+    int cnt = 0;
+    for (int s = 0; s < nf;) {
+        int e = s;
+        float sum[4] = {0.f, 0.f, 0.f, 0.f};
+        while (e < nf && pr[e].key == pr[s].key) {
+            const float* p = pts + 4 * (size_t)pr[e].idx;
+            for (int a = 0; a < 4; ++a) sum[a] = sum[a] + p[a];
+            ++e;
+        }
+        if (cnt < cap) {
+            const float fn = (float)(e - s);
+            for (int a = 0; a < 4; ++a) out[4 * (size_t)cnt + a] = sum[a] / fn;
+        }
+        ++cnt;
+        s = e;
+    }
+    free(pr);
+    return cnt;
+}
+
 /* ------------------------------------------------------------------ GICP (fast_gicp restatement) --- */
 
 /* eigenvector of the smallest eigenvalue of a symmetric 3x3 (cyclic Jacobi) */

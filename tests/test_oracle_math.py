@@ -157,3 +157,40 @@ def test_icp_loop_vs_scipy(O, pkg):
     # fp32 mirror of PCL's Scalar=float loop stays close to the fp64 loop
     Tf = O.icp_p2p_f32(src, tgt, 8)
     assert np.allclose(Tf, To, atol=5e-3)
+
+
+def test_voxel_grid_restatement_small_cases():
+    """pcl::VoxelGrid restated: hand-checkable cases (leaf order x fastest, float means, NaN skipped)"""
+    import oracle as O
+    p = np.array([[0.1, 0.1, 0.1, 1.0], [0.4, 0.2, 0.3, 3.0],      # leaf (0,0,0)
+                  [0.6, 0.1, 0.1, 5.0],                             # leaf (1,0,0)
+                  [0.1, 0.7, 0.1, 7.0],                             # leaf (0,1,0)
+                  [-0.2, 0.1, 0.1, 9.0],                            # leaf (-1,0,0): becomes the first column
+                  [np.nan, 0.0, 0.0, 11.0]], np.float32)
+    out = O.voxel_grid(p, 0.5)
+    assert out.shape == (4, 4)
+    want = np.array([[-0.2, 0.1, 0.1, 9.0], [0.25, 0.15, 0.2, 2.0], [0.6, 0.1, 0.1, 5.0], [0.1, 0.7, 0.1, 7.0]], np.float32)
+    assert np.allclose(out, want, atol=1e-6), out
+    # float accumulation in input order: the mean of the two points of leaf (0,0,0) is (fl(0.1+0.4))/2 exactly
+    assert out[1, 0] == (np.float32(0.1) + np.float32(0.4)) / np.float32(2)
+    assert O.voxel_grid(np.zeros((0, 4), np.float32), 0.5).shape == (0, 4)
+    # deleted points are skipped when a validity mask is given
+    v = np.array([1, 0, 1, 1, 1, 1], np.uint8)
+    out2 = O.voxel_grid(p, 0.5, valid=v)
+    assert out2.shape == (4, 4) and out2[1, 3] == 1.0
+    # numpy cross-check on a random cloud: same leaf count, same per-leaf means to float tolerance
+    rng = np.random.default_rng(0)
+    q = np.zeros((5000, 4), np.float32)
+    q[:, :3] = rng.uniform(-10, 10, (5000, 3))
+    q[:, 3] = rng.uniform(0, 1, 5000)
+    o = O.voxel_grid(q, 0.5)
+    inv = np.float32(1) / np.float32(0.5)
+    ijk = np.floor(q[:, :3] * inv).astype(np.int64)
+    mn = ijk.min(0); div = ijk.max(0) - mn + 1
+    key = (ijk[:, 0] - mn[0]) + (ijk[:, 1] - mn[1]) * div[0] + (ijk[:, 2] - mn[2]) * div[0] * div[1]
+    uk, inv_ix, cnt = np.unique(key, return_inverse=True, return_counts=True)
+    assert o.shape[0] == len(uk)
+    means = np.zeros((len(uk), 4))
+    np.add.at(means, inv_ix, q.astype(np.float64))
+    means /= cnt[:, None]
+    assert np.allclose(o, means, atol=1e-5)
