@@ -29,6 +29,7 @@ struct BatchParams {
     const int32_t* toff;
     int n_pairs, max_n, max_m;
     int max_iterations, early_exit;
+    int use_hints;  // previous-iteration neighbour kept per source point (16-bit slot: needs max_m < 65535)
     float gate_f, gate_r;
     double rot_eps, trans_eps, mse_abs_eps;
     double T0[16];
@@ -48,9 +49,52 @@ __device__ __forceinline__ int cell_of_s(float v, float o, float inv, int dim) {
 // exact 1-NN of (qx,qy,qz) over the shared-memory grid; returns the packed key and the slot of the winner
 __device__ __forceinline__ uint64_t thread_grid_nn(const PairGrid& g, const float4* __restrict__ s_tgt,
                                                    const uint32_t* __restrict__ cs, float qx, float qy, float qz, float gate_f,
-                                                   float gate_r, int& best_pos) {
+                                                   float gate_r, int& best_pos, int hint_pos = -1) {
     const float qmax = fmaxf(fabsf(qx), fmaxf(fabsf(qy), fabsf(qz)));
     const float margin = fmaxf(g.margin, 9.5367431640625e-7f * qmax);
+    if (hint_pos >= 0) {
+        // The point that was nearest at the previous pose bounds the distance of the nearest one now: start from it
+        // and look only at the cells the ball of that radius touches (rows and x-extents shrink with the running
+        // best). Same answer as the shell search below — every point at most that far away is visited.
+        const float4 h = s_tgt[hint_pos];
+        const float hd = dist2_exact(qx, qy, qz, h.x, h.y, h.z);
+        if (hd <= gate_f) {  // false for NaN; a hint outside the gate falls through to the plain search
+            float best_d = hd;
+            int best_i = __float_as_int(h.w);
+            best_pos = hint_pos;
+            const float r = sqrtf(hd) * 1.000001f + margin;
+            const int y0 = cell_of_s(qy - r, g.oy, g.inv_cell, g.ny), y1 = cell_of_s(qy + r, g.oy, g.inv_cell, g.ny);
+            const int z0 = cell_of_s(qz - r, g.oz, g.inv_cell, g.nz), z1 = cell_of_s(qz + r, g.oz, g.inv_cell, g.nz);
+            for (int z = z0; z <= z1; ++z)
+                for (int y = y0; y <= y1; ++y) {
+                    const float ylo = g.oy + (float)y * g.cell, zlo = g.oz + (float)z * g.cell;
+                    float ddy = fmaxf(fmaxf(ylo - qy, qy - (ylo + g.cell)), 0.0f);  // distance to the row's y / z slab
+                    float ddz = fmaxf(fmaxf(zlo - qz, qz - (zlo + g.cell)), 0.0f);
+                    ddy = fmaxf(ddy - margin, 0.0f);
+                    ddz = fmaxf(ddz - margin, 0.0f);
+                    const float dyz2 = (ddy * ddy + ddz * ddz) * 0.999999f;
+                    const float kd = best_d * 1.000001f;
+                    if (dyz2 > kd) continue;
+                    const float xr = sqrtf(kd - dyz2) * 1.000001f + margin;
+                    const int xa = cell_of_s(qx - xr, g.ox, g.inv_cell, g.nx), xb = cell_of_s(qx + xr, g.ox, g.inv_cell, g.nx);
+                    const int rowbase = (z * g.ny + y) * g.nx;
+                    const uint32_t s = cs[rowbase + xa], e = cs[rowbase + xb + 1];
+                    for (uint32_t j = s; j < e; ++j) {
+                        const float4 c = s_tgt[j];
+                        const float d = dist2_exact(qx, qy, qz, c.x, c.y, c.z);
+                        if (d <= best_d) {
+                            const int ci = __float_as_int(c.w);
+                            if (d < best_d || ci < best_i) {
+                                best_d = d;
+                                best_i = ci;
+                                best_pos = (int)j;
+                            }
+                        }
+                    }
+                }
+            return pack_key(best_d, best_i);
+        }
+    }
     const int cx = cell_of_s(qx, g.ox, g.inv_cell, g.nx);
     const int cy = cell_of_s(qy, g.oy, g.inv_cell, g.ny);
     const int cz = cell_of_s(qz, g.oz, g.inv_cell, g.nz);
@@ -165,6 +209,7 @@ __global__ void __launch_bounds__(RB_THREADS, 2) reg_batch_kernel(const __grid_c
     float4* s_src = s_tgt + P.max_m;
     uint32_t* s_cs = reinterpret_cast<uint32_t*>(s_src + P.max_n);  // [RB_MAXC + 2] target cell table
     uint32_t* s_cq = s_cs + (RB_MAXC + 2);                          // [RB_MAXC + 2] source cell cursors (spatial sort)
+    unsigned short* s_prev = reinterpret_cast<unsigned short*>(s_cq + (RB_MAXC + 2));  // [max_n] slot of the last neighbour
     __shared__ double s_red[RB_WARPS * 32];
     __shared__ double s_tot[32];
     __shared__ double s_T[16];
@@ -335,7 +380,9 @@ __global__ void __launch_bounds__(RB_THREADS, 2) reg_batch_kernel(const __grid_c
                 double pw[3];
                 xform_point(T, p.x, p.y, p.z, pw);
                 int pos;
-                const uint64_t key = thread_grid_nn(g, s_tgt, s_cs, (float)pw[0], (float)pw[1], (float)pw[2], P.gate_f, P.gate_r, pos);
+                const int hint = (P.use_hints && it > 0 && s_prev[i] != 0xFFFFu) ? (int)s_prev[i] : -1;
+                const uint64_t key = thread_grid_nn(g, s_tgt, s_cs, (float)pw[0], (float)pw[1], (float)pw[2], P.gate_f, P.gate_r, pos, hint);
+                if (P.use_hints) s_prev[i] = pos >= 0 ? (unsigned short)pos : (unsigned short)0xFFFFu;
                 if (key != KEY_EMPTY) {
                     const float4 c = s_tgt[pos];
                     if (KIND == ICP4R_P2P_SVD) contrib_p2p_svd(acc, pw, c.x, c.y, c.z, key_d2(key));
@@ -429,7 +476,8 @@ __global__ void __launch_bounds__(RB_THREADS, 2) reg_batch_kernel(const __grid_c
                 double pw[3];
                 xform_point(T, p.x, p.y, p.z, pw);
                 int pos;
-                const uint64_t key = thread_grid_nn(g, s_tgt, s_cs, (float)pw[0], (float)pw[1], (float)pw[2], P.gate_f, P.gate_r, pos);
+                const int hint = (P.use_hints && P.max_iterations > 0 && s_prev[i] != 0xFFFFu) ? (int)s_prev[i] : -1;
+                const uint64_t key = thread_grid_nn(g, s_tgt, s_cs, (float)pw[0], (float)pw[1], (float)pw[2], P.gate_f, P.gate_r, pos, hint);
                 if (key != KEY_EMPTY) {
                     fa[0] += 1.0;
                     fa[1] += (double)key_d2(key);
@@ -456,7 +504,8 @@ int register_batch(Ctx* c, const float4* d_src, const int32_t* d_soff, const flo
     if (n_pairs <= 0) return ICP4R_OK;
     if (o->residual != ICP4R_P2P_SVD && o->residual != ICP4R_P2P_GN)
         return fail(c, ICP4R_ERR_UNSUPPORTED, "batched registration supports P2P_SVD and P2P_GN (got %d)", o->residual);
-    const size_t smem = (size_t)(std::max(max_m, 1) + std::max(max_n, 1)) * sizeof(float4) + 2 * (RB_MAXC + 2) * sizeof(uint32_t);
+    const size_t smem = (size_t)(std::max(max_m, 1) + std::max(max_n, 1)) * sizeof(float4) + 2 * (RB_MAXC + 2) * sizeof(uint32_t) +
+                        (((size_t)std::max(max_n, 1) * sizeof(unsigned short) + 15) & ~(size_t)15);
     if (smem > 200 * 1024)
         return fail(c, ICP4R_ERR_UNSUPPORTED, "pair too large for the shared-memory resident kernel (%zu B); use icp4r_register", smem);
     BatchParams P;
@@ -470,6 +519,7 @@ int register_batch(Ctx* c, const float4* d_src, const int32_t* d_soff, const flo
     P.max_m = std::max(max_m, 1);
     P.max_iterations = o->max_iterations;
     P.early_exit = o->early_exit;
+    P.use_hints = (c->use_hints && max_m < 65535) ? 1 : 0;
     gate_params(o->max_corr_dist, &P.gate_f, &P.gate_r);
     P.rot_eps = o->rot_eps;
     P.trans_eps = o->trans_eps;
