@@ -276,8 +276,10 @@ int icp4r_map_add_points(icp4r_handle h, const float* xyzw, int32_t n, int mem, 
     if (n == 0) return ICP4R_OK;
     if (!downsample_on) {
         CKS(set_points(c, mp, xyzw, n, mem, mp.m));
+        bool merged = false;
+        CKS(map_append_incremental(c, mp, n, &merged));  // merge into the existing grid when the batch fits
         mp.m += n;
-        CKS(map_rebuild_grid(c, mp));
+        if (!merged) CKS(map_rebuild_grid(c, mp));
         return ICP4R_OK;
     }
     // down-sampling: the reference inserts point by point, each seeing the effect of the previous ones. The device

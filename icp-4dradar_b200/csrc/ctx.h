@@ -70,6 +70,11 @@ struct Map {
     float bb_min[3] = {0, 0, 0}, bb_max[3] = {0, 0, 0};
     DevBuf normals;     // double[3 * m]: GICP surface normals by insertion index (valid while normals_k != 0)
     int normals_k = 0;  // neighbours they were estimated from; reset to 0 whenever the grid is rebuilt
+    // incremental Add_Points (no down-sampling): new points are merged into the sorted array instead of re-sorting
+    DevBuf sorted_alt;               // the other half of the sorted ping-pong
+    DevBuf ik_a, ik_b, iv_a, iv_b;   // keys / indices of the batch being merged
+    int valid_at_build = 0;          // valid points at the last full build (density drift -> full rebuild)
+    bool padded = false;             // grid built with slack around the bounding box (set once an append fell outside)
 };
 
 // ---- peer-memory exchange for slab-sharded registration (one process per GPU, NVLink P2P) --------------------
@@ -134,6 +139,11 @@ struct RegParams {  // kernel parameters that change per call; lives in device m
     GicpCorr* corr;
     // fused cross-rank sum over peer memory (NULL: single rank or the NCCL flavour)
     const XchTable* xt;
+    // the map's buffers: read from here (not from the by-value GridDesc) so that captured loops survive Add_Points
+    const float4* map_sorted;
+    const uint32_t* map_cell_start;
+    const float4* map_pts;
+    int map_m;
     // neighbours found at the previous iteration, K per source point (NULL: no hints — sharded maps, GICP)
     int32_t* nb_prev;
 };
@@ -201,6 +211,7 @@ int radix_sort_pairs(Ctx* c, uint32_t* keys_a, uint32_t* keys_b, uint32_t* vals_
 // grid.cu
 int map_reserve(Ctx* c, Map& mp, int cap);
 int map_rebuild_grid(Ctx* c, Map& mp);  // (re)sort all valid points into the grid
+int map_append_incremental(Ctx* c, Map& mp, int n_new, bool* merged);  // merge pts[m, m+n_new) into the grid if it fits
 int grid_knn(Ctx* c, const Map& mp, const float4* q, int nq, int k, double max_dist, int32_t* idx, float* d2,
              int32_t* found);
 int brute_knn(Ctx* c, const Map& mp, const float4* q, int nq, int k, double max_dist, int32_t* idx, float* d2,

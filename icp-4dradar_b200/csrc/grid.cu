@@ -200,11 +200,24 @@ int map_rebuild_grid(Ctx* c, Map& mp) {
         ext[a] = (double)mx[a] - (double)mn[a];
         L = std::max(L, std::max(std::fabs((double)mn[a]), std::fabs((double)mx[a])));
     }
+    const double ext_tight[3] = {ext[0], ext[1], ext[2]};
+    if (mp.padded) {
+        // a growing map (odometry): leave room around the bounding box so that the next batches merge into this
+        // grid instead of forcing a new sort; exactness never depends on the geometry
+        const double emax_t = std::max(ext[0], std::max(ext[1], ext[2]));
+        for (int a = 0; a < 3; ++a) {
+            const double pad = std::max(0.15 * ext[a], 0.02 * emax_t);
+            mn[a] = (float)((double)mn[a] - pad);
+            mx[a] = (float)((double)mx[a] + pad);
+            ext[a] = (double)mx[a] - (double)mn[a];
+            L = std::max(L, std::max(std::fabs((double)mn[a]), std::fabs((double)mx[a])));
+        }
+    }
     const double emax = std::max(ext[0], std::max(ext[1], ext[2]));
     double cell = mp.user_cell > 0.f ? (double)mp.user_cell : (double)mp.hint_cell;
     if (!(cell > 0.0)) {
         const double floor_e = std::max(emax * 1e-3, 1e-6);
-        const double vol = std::max(ext[0], floor_e) * std::max(ext[1], floor_e) * std::max(ext[2], floor_e);
+        const double vol = std::max(ext_tight[0], floor_e) * std::max(ext_tight[1], floor_e) * std::max(ext_tight[2], floor_e);
         cell = std::cbrt(vol / std::max(1.0, nvalid / 8.0));
         cell = std::max(cell, std::max(emax * 1e-4, 1e-6));
     }
@@ -298,6 +311,165 @@ int map_rebuild_grid(Ctx* c, Map& mp) {
     mp.grid = g;
     mp.built = true;
     mp.hint_cell = g.cell;
+    mp.valid_at_build = nvalid;
+    return ICP4R_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ incremental append
+// Add_Points(.., false) of a batch that lies inside the current grid: instead of sorting all M + n points again
+// (about ten passes over the map), sort the n new keys and MERGE: every old point moves up by the number of new
+// points in lower cells, every new point lands behind the old points of its cell (stable: insertion order inside a
+// cell is kept, which is what the full sort produces), and the cell table is shifted by the same counts. One read
+// and one write of the sorted array (32 B per map point) — the HBM floor for keeping the array contiguous.
+namespace {
+__device__ __forceinline__ int lower_bound_u32(const uint32_t* __restrict__ a, int lo, int hi, uint32_t v) {
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(a + mid) < v) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// keys of the new points; info = {outside flag, finite count, ordered min xyz, ordered max xyz}
+__global__ void __launch_bounds__(256) inc_key_kernel(const float4* __restrict__ pts, int base, int n, GridDesc g, uint32_t* __restrict__ keys,
+                                                      uint32_t* __restrict__ vals, int* __restrict__ info) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = pts[base + i];
+    uint32_t key = (uint32_t)g.ncells;
+    if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+        const int cx = __float2int_rd(__fmul_rn(__fsub_rn(p.x, g.ox), g.inv_cell));
+        const int cy = __float2int_rd(__fmul_rn(__fsub_rn(p.y, g.oy), g.inv_cell));
+        const int cz = __float2int_rd(__fmul_rn(__fsub_rn(p.z, g.oz), g.inv_cell));
+        if (cx < 0 || cx >= g.nx || cy < 0 || cy >= g.ny || cz < 0 || cz >= g.nz) {
+            atomicOr(info, 1);
+        } else {
+            key = (uint32_t)(cz * g.ny + cy) * (uint32_t)g.nx + (uint32_t)cx;  // == cell_of() for an inside point
+        }
+        atomicAdd(info + 1, 1);
+        atomicMin(info + 2, f2ord(p.x)); atomicMax(info + 5, f2ord(p.x));
+        atomicMin(info + 3, f2ord(p.y)); atomicMax(info + 6, f2ord(p.y));
+        atomicMin(info + 4, f2ord(p.z)); atomicMax(info + 7, f2ord(p.z));
+    }
+    keys[i] = key;
+    vals[i] = (uint32_t)(base + i);
+}
+
+__global__ void inc_info_init(int* info) {
+    const int t = threadIdx.x;
+    if (t < 2) info[t] = 0;
+    else if (t < 5) info[t] = 0x7fffffff;
+    else if (t < 8) info[t] = (int)0x80000000;
+}
+
+constexpr int INC_THREADS = 256;
+// old sorted point j moves to j + (new points in lower cells)
+__global__ void __launch_bounds__(INC_THREADS) inc_merge_old_kernel(const float4* __restrict__ sorted_old, int m_old, GridDesc g,
+                                                                   const uint32_t* __restrict__ nkeys, int nf, float4* __restrict__ sorted_new) {
+    __shared__ int s_lo, s_hi;
+    const int j0 = blockIdx.x * INC_THREADS, j = j0 + threadIdx.x;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t key = 0;
+    if (j < m_old) {
+        p = sorted_old[j];
+        key = (uint32_t)(cell_of(p.z, g.oz, g.inv_cell, g.nz) * g.ny + cell_of(p.y, g.oy, g.inv_cell, g.ny)) * (uint32_t)g.nx +
+              (uint32_t)cell_of(p.x, g.ox, g.inv_cell, g.nx);
+    }
+    // the block's points are consecutive in cell order: narrow the search range once per block
+    const int jl = min(j0 + INC_THREADS, m_old) - 1;
+    if (threadIdx.x == 0) s_lo = lower_bound_u32(nkeys, 0, nf, key);
+    if (j == jl) s_hi = lower_bound_u32(nkeys, 0, nf, key + 1u);
+    __syncthreads();
+    if (j < m_old) sorted_new[j + lower_bound_u32(nkeys, s_lo, s_hi, key)] = p;
+}
+
+// new point i (i-th in key order) lands behind the old points of its cell and the new ones before it
+__global__ void __launch_bounds__(256) inc_merge_new_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ nkeys,
+                                                           const uint32_t* __restrict__ nvals, int nf, const uint32_t* __restrict__ cs_old,
+                                                           float4* __restrict__ sorted_new) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nf) return;
+    const uint32_t k = nkeys[i], idx = nvals[i];
+    const float4 p = pts[idx];
+    sorted_new[(uint32_t)i + cs_old[k + 1]] = make_float4(p.x, p.y, p.z, __uint_as_float(idx));
+}
+
+// cell_start[c] += new points in cells < c (in place; runs after inc_merge_new_kernel has read the old table)
+__global__ void __launch_bounds__(INC_THREADS) inc_cell_kernel(uint32_t* __restrict__ cs, int ncells, const uint32_t* __restrict__ nkeys, int nf) {
+    __shared__ int s_lo, s_hi;
+    const int c0 = blockIdx.x * INC_THREADS, c = c0 + threadIdx.x;
+    if (threadIdx.x == 0) {
+        s_lo = lower_bound_u32(nkeys, 0, nf, (uint32_t)c0);
+        s_hi = lower_bound_u32(nkeys, 0, nf, (uint32_t)min(c0 + INC_THREADS, ncells + 1));
+    }
+    __syncthreads();
+    if (c <= ncells && s_hi > 0) {
+        const int add = lower_bound_u32(nkeys, s_lo, s_hi, (uint32_t)c);
+        if (add) cs[c] += (uint32_t)add;
+    }
+}
+}  // namespace
+
+int map_append_incremental(Ctx* c, Map& mp, int n_new, bool* merged) {
+    *merged = false;
+    const char* off = std::getenv("ICP4R_NO_INCREMENTAL");
+    if (off && off[0] == '1') return ICP4R_OK;
+    if (!mp.built || n_new <= 0 || mp.grid.m <= 0 || mp.grid.m != mp.m_valid) return ICP4R_OK;
+    // density drift: the cell size was chosen for the point count of the last full build
+    if ((long long)mp.m_valid + n_new > (long long)mp.valid_at_build * 3 / 2 + 4096) return ICP4R_OK;
+    Trace tr(c->stream);
+    const GridDesc g = mp.grid;
+    CKS(reserve_grow(c, mp.ik_a, (size_t)n_new * 4));
+    CKS(reserve_grow(c, mp.ik_b, (size_t)n_new * 4));
+    CKS(reserve_grow(c, mp.iv_a, (size_t)n_new * 4));
+    CKS(reserve_grow(c, mp.iv_b, (size_t)n_new * 4));
+    CKS(reserve(c, c->d_scratch, 4096));
+    int* d_info = c->d_scratch.as<int>();
+    inc_info_init<<<1, 32, 0, c->stream>>>(d_info);
+    inc_key_kernel<<<(n_new + 255) / 256, 256, 0, c->stream>>>(mp.pts.as<float4>(), mp.m, n_new, g, mp.ik_a.as<uint32_t>(),
+                                                               mp.iv_a.as<uint32_t>(), d_info);
+    c->launches += 2;
+    int info[8];
+    CK(cudaMemcpyAsync(info, d_info, sizeof(info), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (info[0] != 0) {  // a point outside the grid: rebuild with slack so that the following batches fit
+        mp.padded = true;
+        return ICP4R_OK;
+    }
+    const int nf = info[1];
+    tr.mark("inc keys");
+    if (nf > 0) {
+        int bits = 1;
+        while ((1ll << bits) <= (long long)g.ncells) ++bits;
+        uint32_t *ks, *vs;
+        CKS(radix_sort_pairs(c, mp.ik_a.as<uint32_t>(), mp.ik_b.as<uint32_t>(), mp.iv_a.as<uint32_t>(), mp.iv_b.as<uint32_t>(), n_new, bits,
+                             c->d_scratch, &ks, &vs));
+        tr.mark("inc sort");
+        const int m_old = g.m, m_new = m_old + nf;
+        if (mp.sorted_alt.cap < (size_t)m_new * sizeof(float4)) CKS(reserve(c, mp.sorted_alt, ((size_t)m_new + (size_t)m_new / 4) * sizeof(float4)));
+        float4* s_new = mp.sorted_alt.as<float4>();
+        inc_merge_old_kernel<<<(m_old + INC_THREADS - 1) / INC_THREADS, INC_THREADS, 0, c->stream>>>(g.sorted, m_old, g, ks, nf, s_new);
+        inc_merge_new_kernel<<<(nf + 255) / 256, 256, 0, c->stream>>>(mp.pts.as<float4>(), ks, vs, nf, g.cell_start, s_new);
+        inc_cell_kernel<<<(g.ncells + 1 + INC_THREADS - 1) / INC_THREADS, INC_THREADS, 0, c->stream>>>(mp.cell_start.as<uint32_t>(), g.ncells, ks, nf);
+        c->launches += 3;
+        CK(cudaGetLastError());
+        tr.mark("inc merge");
+        std::swap(mp.sorted, mp.sorted_alt);
+        mp.grid.sorted = mp.sorted.as<float4>();
+        mp.grid.m = m_new;
+        mp.m_valid = m_new;
+        for (int a = 0; a < 3; ++a) {
+            mp.bb_min[a] = std::min(mp.bb_min[a], ord2f(info[2 + a]));
+            mp.bb_max[a] = std::max(mp.bb_max[a], ord2f(info[5 + a]));
+        }
+        const float Lnew = std::max(std::max(std::fabs(ord2f(info[2])), std::fabs(ord2f(info[5]))),
+                                    std::max(std::max(std::fabs(ord2f(info[3])), std::fabs(ord2f(info[6]))),
+                                             std::max(std::fabs(ord2f(info[4])), std::fabs(ord2f(info[7])))));
+        mp.grid.margin = std::max(mp.grid.margin, Lnew * 9.5367431640625e-7f);
+    }
+    mp.normals_k = 0;
+    *merged = true;
     return ICP4R_OK;
 }
 

@@ -95,16 +95,17 @@ __device__ __forceinline__ void scan_segments(const float4* __restrict__ sorted,
 }
 
 // Returns, in lane r < K, the r-th nearest neighbour's packed key (KEY_EMPTY if fewer exist).
+// `g` carries the geometry only; the sorted points, the cell table and their length are passed next to it so that a
+// captured launch (whose GridDesc is baked in by value) can pick them up from device memory at run time.
 //
 // `hint` >= 0: the caller knows K distinct valid points with d2 <= hint (the neighbours found for this source point at
 // the previous pose). The k-th distance can then not exceed `hint`, so ONE pass over the cells that intersect the ball
 // of that radius (clipped to the gate box) sees every point that can be part of the answer: no own-cell probe, no
 // shell-by-shell proof, one merge. The result is the same set, the hint only removes work.
 template <int K>
-__device__ __forceinline__ uint64_t warp_grid_knn(const GridDesc& g, WarpSegs& sg, float qx, float qy, float qz, float gate_f,
-                                                  float gate_r, int lane, float hint = -1.0f) {
-    const float4* __restrict__ sorted = g.sorted;
-    const uint32_t* __restrict__ cs = g.cell_start;
+__device__ __forceinline__ uint64_t warp_grid_knn(const GridDesc& g, const float4* __restrict__ sorted, const uint32_t* __restrict__ cs,
+                                                  int m_sorted, WarpSegs& sg, float qx, float qy, float qz, float gate_f, float gate_r,
+                                                  int lane, float hint = -1.0f) {
     const float qmax = fmaxf(fabsf(qx), fmaxf(fabsf(qy), fabsf(qz)));
     const float margin = fmaxf(g.margin, 9.5367431640625e-7f * qmax);  // 2^-20 * magnitude
 
@@ -233,10 +234,18 @@ __device__ __forceinline__ uint64_t warp_grid_knn(const GridDesc& g, WarpSegs& s
     if (!done && rneed > 0 && prev < rneed) {
         // ring cap reached (far-away ungated query or a very wide gate): exhaustive scan, still exact
         list.clear();
-        scan_segments<K>(sorted, sg, 0u, lane == 0 ? (uint32_t)g.m : 0u, 0u, 0u, lane, qx, qy, qz, gate_f, KEY_EMPTY, list);
+        scan_segments<K>(sorted, sg, 0u, lane == 0 ? (uint32_t)m_sorted : 0u, 0u, 0u, lane, qx, qy, qz, gate_f, KEY_EMPTY, list);
         mine = warp_merge_topk<K>(list, lane);
     }
     return mine;
 }
 
+}  // namespace icp4r
+
+namespace icp4r {
+template <int K>
+__device__ __forceinline__ uint64_t warp_grid_knn(const GridDesc& g, WarpSegs& sg, float qx, float qy, float qz, float gate_f,
+                                                  float gate_r, int lane) {
+    return warp_grid_knn<K>(g, g.sorted, g.cell_start, g.m, sg, qx, qy, qz, gate_f, gate_r, lane);
+}
 }  // namespace icp4r

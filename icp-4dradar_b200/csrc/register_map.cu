@@ -141,7 +141,7 @@ __device__ void write_result(const RegState* st, ResultBlock* out) {
 // block partial, and the last block to finish sums the partials in a fixed order and solves.
 template <int KIND, int K, int MODE>
 __global__ void __launch_bounds__(RM_THREADS, 1)
-    reg_iter_kernel(GridDesc g, const float4* __restrict__ pts, const RegParams* __restrict__ prm, RegState* __restrict__ st,
+    reg_iter_kernel(GridDesc g, const RegParams* __restrict__ prm, RegState* __restrict__ st,
                     double* __restrict__ partials, ResultBlock* __restrict__ out, int iter) {
     constexpr bool FIT = (MODE == MODE_FITNESS || MODE == MODE_FITNESS_NOFINAL);
     constexpr int KK = FIT ? 1 : K;
@@ -171,6 +171,7 @@ __global__ void __launch_bounds__(RM_THREADS, 1)
     if (tid >= 32 && tid < 32 + (int)(sizeof(RegParams) / 4)) reinterpret_cast<uint32_t*>(&P)[tid - 32] = reinterpret_cast<const uint32_t*>(prm)[tid - 32];
     __syncthreads();
 
+    const float4* __restrict__ pts = P.map_pts;  // map points by insertion index
     // which two operands this lane multiplies (indices into scr[w][row][*])
     int ia = 8, ib = 8;  // scr[..][8] == 0
     if (RK == ICP4R_P2P_SVD) {  // scr = {1, p'x,p'y,p'z, qx,qy,qz, d2, 0}
@@ -323,7 +324,7 @@ __global__ void __launch_bounds__(RM_THREADS, 1)
                 hint = P.gate_f;
             }
         }
-        uint64_t mine = warp_grid_knn<KK>(g, segs[w], qx, qy, qz, P.gate_f, P.gate_r, lane, hint);
+        uint64_t mine = warp_grid_knn<KK>(g, P.map_sorted, P.map_cell_start, P.map_m, segs[w], qx, qy, qz, P.gate_f, P.gate_r, lane, hint);
         const bool have = (lane < kq) && (mine != KEY_EMPTY);
         if (!FIT && nbp != nullptr && lane < kq) nbp[lane] = have ? key_idx(mine) : -1;
         if (!FIT && P.dump_idx && lane < kq) P.dump_idx[((size_t)iter * n + i) * kq + lane] = have ? key_idx(mine) : -1;
@@ -692,47 +693,47 @@ __global__ void init_state_kernel(RegState* st, const double* T0) {
 }
 
 template <int KIND, int K>
-static void launch_iter(Ctx* c, int mode, int blocks, int threads, int nscan, const GridDesc& g, const float4* pts, const RegParams* prm, RegState* st,
+static void launch_iter(Ctx* c, int mode, int blocks, int threads, int nscan, const GridDesc& g, const RegParams* prm, RegState* st,
                         double* partials, ResultBlock* out, int iter) {
     switch (mode) {
         case MODE_ITER:
-            reg_iter_kernel<KIND, K, MODE_ITER><<<dim3(blocks, nscan), threads, 0, c->stream>>>(g, pts, prm, st, partials, out, iter);
+            reg_iter_kernel<KIND, K, MODE_ITER><<<dim3(blocks, nscan), threads, 0, c->stream>>>(g, prm, st, partials, out, iter);
             break;
         case MODE_ITER_NOSOLVE:
-            reg_iter_kernel<KIND, K, MODE_ITER_NOSOLVE><<<dim3(blocks, nscan), threads, 0, c->stream>>>(g, pts, prm, st, partials, out, iter);
+            reg_iter_kernel<KIND, K, MODE_ITER_NOSOLVE><<<dim3(blocks, nscan), threads, 0, c->stream>>>(g, prm, st, partials, out, iter);
             break;
         case MODE_FITNESS:
-            reg_iter_kernel<KIND, K, MODE_FITNESS><<<dim3(blocks, nscan), threads, 0, c->stream>>>(g, pts, prm, st, partials, out, iter);
+            reg_iter_kernel<KIND, K, MODE_FITNESS><<<dim3(blocks, nscan), threads, 0, c->stream>>>(g, prm, st, partials, out, iter);
             break;
         default:
-            reg_iter_kernel<KIND, K, MODE_FITNESS_NOFINAL><<<dim3(blocks, nscan), threads, 0, c->stream>>>(g, pts, prm, st, partials, out, iter);
+            reg_iter_kernel<KIND, K, MODE_FITNESS_NOFINAL><<<dim3(blocks, nscan), threads, 0, c->stream>>>(g, prm, st, partials, out, iter);
             break;
     }
     c->launches += 1;
 }
 
-static void dispatch_iter(Ctx* c, int kind, int K, int mode, int blocks, int threads, int nscan, const GridDesc& g, const float4* pts,
+static void dispatch_iter(Ctx* c, int kind, int K, int mode, int blocks, int threads, int nscan, const GridDesc& g,
                           const RegParams* prm, RegState* st, double* partials, ResultBlock* out, int iter) {
     switch (kind) {
         case ICP4R_P2P_SVD:
-            launch_iter<ICP4R_P2P_SVD, 1>(c, mode, blocks, threads, nscan, g, pts, prm, st, partials, out, iter);
+            launch_iter<ICP4R_P2P_SVD, 1>(c, mode, blocks, threads, nscan, g, prm, st, partials, out, iter);
             break;
         case ICP4R_P2P_GN:
-            launch_iter<ICP4R_P2P_GN, 1>(c, mode, blocks, threads, nscan, g, pts, prm, st, partials, out, iter);
+            launch_iter<ICP4R_P2P_GN, 1>(c, mode, blocks, threads, nscan, g, prm, st, partials, out, iter);
             break;
         case ICP4R_P2LINE:
-            launch_iter<ICP4R_P2LINE, 2>(c, mode, blocks, threads, nscan, g, pts, prm, st, partials, out, iter);
+            launch_iter<ICP4R_P2LINE, 2>(c, mode, blocks, threads, nscan, g, prm, st, partials, out, iter);
             break;
         case ICP4R_GICP:
-            launch_iter<ICP4R_GICP, 1>(c, mode, blocks, threads, nscan, g, pts, prm, st, partials, out, iter);
+            launch_iter<ICP4R_GICP, 1>(c, mode, blocks, threads, nscan, g, prm, st, partials, out, iter);
             break;
         case ICP4R_P2PLANE_3PT:
-            launch_iter<ICP4R_P2PLANE_3PT, 5>(c, mode, blocks, threads, nscan, g, pts, prm, st, partials, out, iter);
+            launch_iter<ICP4R_P2PLANE_3PT, 5>(c, mode, blocks, threads, nscan, g, prm, st, partials, out, iter);
             break;
         default:
-            if (K <= 5) launch_iter<ICP4R_P2PLANE_KNN, 5>(c, mode, blocks, threads, nscan, g, pts, prm, st, partials, out, iter);
-            else if (K <= 8) launch_iter<ICP4R_P2PLANE_KNN, 8>(c, mode, blocks, threads, nscan, g, pts, prm, st, partials, out, iter);
-            else launch_iter<ICP4R_P2PLANE_KNN, 16>(c, mode, blocks, threads, nscan, g, pts, prm, st, partials, out, iter);
+            if (K <= 5) launch_iter<ICP4R_P2PLANE_KNN, 5>(c, mode, blocks, threads, nscan, g, prm, st, partials, out, iter);
+            else if (K <= 8) launch_iter<ICP4R_P2PLANE_KNN, 8>(c, mode, blocks, threads, nscan, g, prm, st, partials, out, iter);
+            else launch_iter<ICP4R_P2PLANE_KNN, 16>(c, mode, blocks, threads, nscan, g, prm, st, partials, out, iter);
             break;
     }
 }
@@ -800,6 +801,10 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
     P.dump_pose = dump ? dump->pose : nullptr;
     P.dump_acc = dump ? dump->acc : nullptr;
     P.dump_idx = dump ? dump->idx : nullptr;
+    P.map_sorted = mp.grid.sorted;
+    P.map_cell_start = mp.grid.cell_start;
+    P.map_pts = mp.pts.as<float4>();
+    P.map_m = mp.grid.m;
     P.shard_axis = sharded ? shard_axis : -1;
     P.slab_lo = slab_lo;
     P.slab_hi = slab_hi;
@@ -847,8 +852,12 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
     init_state_kernel<<<1, 32, 0, c->stream>>>(d_st, c->d_T.as<double>());
     c->launches += 1;
 
-    const GridDesc g = mp.grid;
-    const float4* pts = mp.pts.as<float4>();
+    // geometry only by value: buffers and their length travel in RegParams (see ctx.h), so Add_Points between two
+    // registrations does not invalidate the captured loop as long as the cell geometry stays
+    GridDesc g = mp.grid;
+    g.sorted = nullptr;
+    g.cell_start = nullptr;
+    g.m = 0;
     const int iters = o->max_iterations;
 
     // The loop is a fixed sequence of launches whose arguments are all stable device pointers (per-call values
@@ -862,28 +871,28 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
         if (gicp) {
             // linearise (grid-wide, accumulators left in st->acc) then one single-block Levenberg-Marquardt step
             for (int it = 0; it < iters; ++it) {
-                dispatch_iter(c, o->residual, k, MODE_ITER_NOSOLVE, blocks, threads, 1, g, pts, d_prm, d_st, d_part, d_out, it);
+                dispatch_iter(c, o->residual, k, MODE_ITER_NOSOLVE, blocks, threads, 1, g, d_prm, d_st, d_part, d_out, it);
                 gicp_lm_step(c, d_prm, d_st, it);
             }
-            dispatch_iter(c, o->residual, k, MODE_FITNESS, blocks, threads, 1, g, pts, d_prm, d_st, d_part, d_out, 0);
+            dispatch_iter(c, o->residual, k, MODE_FITNESS, blocks, threads, 1, g, d_prm, d_st, d_part, d_out, 0);
         } else if (sharded && !fused_shard) {
             for (int it = 0; it < iters; ++it) {
-                dispatch_iter(c, o->residual, k, MODE_ITER_NOSOLVE, blocks, threads, 1, g, pts, d_prm, d_st, d_part, d_out, it);
+                dispatch_iter(c, o->residual, k, MODE_ITER_NOSOLVE, blocks, threads, 1, g, d_prm, d_st, d_part, d_out, it);
                 if (shard_allreduce(c, acc_ptr, ICP4R_ACC_LEN) != ICP4R_OK) enqueue_status = ICP4R_ERR_NCCL;
                 solve_kernel<<<1, 32, 0, c->stream>>>(o->residual, d_prm, d_st, it);
                 c->launches += 1;
             }
-            dispatch_iter(c, o->residual, k, MODE_FITNESS_NOFINAL, blocks, threads, 1, g, pts, d_prm, d_st, d_part, d_out, 0);
+            dispatch_iter(c, o->residual, k, MODE_FITNESS_NOFINAL, blocks, threads, 1, g, d_prm, d_st, d_part, d_out, 0);
             if (shard_allreduce(c, acc_ptr, 2) != ICP4R_OK) enqueue_status = ICP4R_ERR_NCCL;
             fitness_final_kernel<<<1, 32, 0, c->stream>>>(d_st, d_out);
             c->launches += 1;
         } else {
             if (prof) cudaEventRecord(c->prof_events[0], c->stream);
             for (int it = 0; it < iters; ++it) {
-                dispatch_iter(c, o->residual, k, MODE_ITER, blocks, threads, 1, g, pts, d_prm, d_st, d_part, d_out, it);
+                dispatch_iter(c, o->residual, k, MODE_ITER, blocks, threads, 1, g, d_prm, d_st, d_part, d_out, it);
                 if (prof) cudaEventRecord(c->prof_events[it + 1], c->stream);
             }
-            dispatch_iter(c, o->residual, k, MODE_FITNESS, blocks, threads, 1, g, pts, d_prm, d_st, d_part, d_out, 0);
+            dispatch_iter(c, o->residual, k, MODE_FITNESS, blocks, threads, 1, g, d_prm, d_st, d_part, d_out, 0);
             if (prof) cudaEventRecord(c->prof_events[iters + 1], c->stream);
         }
     };
@@ -899,13 +908,11 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
     cudaGraphExec_t exec = nullptr;
     if (want_graph) {
         // graphs bake the GridDesc by value: drop them when the map geometry or buffers changed
-        if (c->graph_grid_owner != &mp.grid || std::memcmp(&c->graph_grid_copy, &g, sizeof(GridDesc)) != 0 ||
-            c->graph_pts != (const void*)pts) {
+        if (c->graph_grid_owner != &mp.grid || std::memcmp(&c->graph_grid_copy, &g, sizeof(GridDesc)) != 0) {
             for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
             c->graphs.clear();
             c->graph_grid_owner = &mp.grid;
             c->graph_grid_copy = g;
-            c->graph_pts = pts;
         }
         auto it = c->graphs.find(key);
         if (it != c->graphs.end()) exec = it->second;
@@ -993,8 +1000,10 @@ int register_scans_against_map(Ctx* c, Map& mp, const float4* d_src, const int32
         ResultBlock out;
     };
     const int CH = (int)std::min<size_t>(64, c->h_pinned_cap / sizeof(Stage));  // scans per launch sequence
-    const GridDesc g = mp.grid;
-    const float4* pts = mp.pts.as<float4>();
+    GridDesc g = mp.grid;  // geometry only (see register_against_map)
+    g.sorted = nullptr;
+    g.cell_start = nullptr;
+    g.m = 0;
     const int iters = o->max_iterations;
     for (int s0 = 0; s0 < nscan; s0 += CH) {
         const int B = std::min(CH, nscan - s0);
@@ -1029,6 +1038,10 @@ int register_scans_against_map(Ctx* c, Map& mp, const float4* d_src, const int32
             P.trans_eps = o->trans_eps;
             P.mse_abs_eps = o->mse_abs_eps;
             P.plane_thresh = o->plane_thresh;
+            P.map_sorted = mp.grid.sorted;
+            P.map_cell_start = mp.grid.cell_start;
+            P.map_pts = mp.pts.as<float4>();
+            P.map_m = mp.grid.m;
             P.shard_axis = -1;
             P.nb_prev = c->use_hints ? c->d_nbprev.as<int32_t>() + (size_t)off_host[s0 + b] * ICP4R_MAX_K : nullptr;
             std::memcpy(hs[b].T0, T0s_host ? T0s_host + 16 * (size_t)(s0 + b) : o->T0, sizeof(hs[b].T0));
@@ -1043,20 +1056,18 @@ int register_scans_against_map(Ctx* c, Map& mp, const float4* d_src, const int32
         init_state_kernel<<<B, 32, 0, c->stream>>>(d_st, c->bm_T0.as<double>());
         c->launches += 1;
         auto enqueue = [&]() {
-            for (int it = 0; it < iters; ++it) dispatch_iter(c, o->residual, k, MODE_ITER, blocks, threads, B, g, pts, d_prm, d_st, d_part, d_out, it);
-            dispatch_iter(c, o->residual, k, MODE_FITNESS, blocks, threads, B, g, pts, d_prm, d_st, d_part, d_out, 0);
+            for (int it = 0; it < iters; ++it) dispatch_iter(c, o->residual, k, MODE_ITER, blocks, threads, B, g, d_prm, d_st, d_part, d_out, it);
+            dispatch_iter(c, o->residual, k, MODE_FITNESS, blocks, threads, B, g, d_prm, d_st, d_part, d_out, 0);
         };
         const bool want_graph = c->use_graph && !c->profiling;
         GraphKey key{o->residual, k, blocks, iters, threads | (1 << 18) | (B << 20)};
         cudaGraphExec_t exec = nullptr;
         if (want_graph) {
-            if (moved || c->graph_grid_owner != &mp.grid || std::memcmp(&c->graph_grid_copy, &g, sizeof(GridDesc)) != 0 ||
-                c->graph_pts != (const void*)pts) {
+            if (moved || c->graph_grid_owner != &mp.grid || std::memcmp(&c->graph_grid_copy, &g, sizeof(GridDesc)) != 0) {
                 for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
                 c->graphs.clear();
                 c->graph_grid_owner = &mp.grid;
                 c->graph_grid_copy = g;
-                c->graph_pts = pts;
             }
             auto itg = c->graphs.find(key);
             if (itg != c->graphs.end()) exec = itg->second;

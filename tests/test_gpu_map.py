@@ -108,3 +108,47 @@ def test_sector_matches_oracle_after_downsample(handle, O):
         got = np.sort(handle.map_sector(c, r, hd))
         want = np.sort(m.sector(c, r, hd))
         assert (got == want).all()
+
+
+def test_incremental_append_equals_fresh_build(handle, pkg):
+    """Add_Points(false) of batches that fit the grid are merged instead of re-sorted: searches over the merged map
+    must equal searches over a map built from scratch with the same points (indices, distances, counts — bit for bit),
+    through out-of-bounds batches (padded rebuild), density drift (full rebuild) and non-finite points"""
+    rng = np.random.default_rng(77)
+
+    def batch(n, cx):
+        p = np.zeros((n, 4), np.float32)
+        p[:, 0] = rng.uniform(cx - 40, cx + 40, n)
+        p[:, 1] = rng.uniform(-40, 40, n)
+        p[:, 2] = rng.uniform(-2, 2, n)
+        p[:, 3] = rng.uniform(0, 1, n)
+        return p
+
+    allp = batch(20000, 0.0)
+    handle.map_build(allp)
+    fresh = pkg.Icp4r(0)
+    try:
+        for b in range(36):
+            nb = batch(1500, 1.5 * b)            # the window drifts along +x like a moving sensor
+            if b == 7:
+                nb[::50, 1] = np.nan               # skipped points keep their index
+            if b == 20:
+                nb = np.concatenate([nb, batch(30000, 1.5 * b)])   # a big batch: density drift
+            handle.map_add_points(nb, False)
+            allp = np.concatenate([allp, nb])
+            if b % 5 == 2 or b in (7, 8, 20, 21, 35):
+                q = batch(700, 1.5 * b)
+                got = handle.map_knn(q, 5, 2.0)
+                fresh.map_build(allp)
+                want = fresh.map_knn(q, 5, 2.0)
+                assert handle.map_size() == fresh.map_size()
+                for a, w in zip(got, want):
+                    assert (bits(a) == bits(w)).all(), b
+                o = pkg.default_opts(residual=pkg.P2PLANE_KNN, k=5, max_iterations=4, max_corr_dist=2.0)
+                T1, r1, _ = handle.register_map(q, o)
+                T2, r2, _ = fresh.register_map(q, o)
+                assert np.array_equal(T1, T2) and r1.n_corr == r2.n_corr
+        pts, valid = handle.map_points()
+        assert (bits(pts) == bits(allp)).all() and valid.all()
+    finally:
+        fresh.close()
