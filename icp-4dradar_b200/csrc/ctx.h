@@ -73,6 +73,7 @@ struct Map {
     // incremental Add_Points (no down-sampling): new points are merged into the sorted array instead of re-sorting
     DevBuf sorted_alt;               // the other half of the sorted ping-pong
     DevBuf ik_a, ik_b, iv_a, iv_b;   // keys / indices of the batch being merged
+    DevBuf inc_bnd;                  // per-block search bounds of the merge passes
     int valid_at_build = 0;          // valid points at the last full build (density drift -> full rebuild)
     bool padded = false;             // grid built with slack around the bounding box (set once an append fell outside)
 };

@@ -363,25 +363,78 @@ __global__ void inc_info_init(int* info) {
     else if (t < 8) info[t] = (int)0x80000000;
 }
 
+// small batches (a radar / lidar frame): one block sorts the (key, index) pairs in shared memory. The pairs are
+// unique, so sorting the packed 64-bit words gives the stable order (ascending index inside a cell).
+constexpr int SB_MAX = 4096;
+__global__ void __launch_bounds__(1024) small_sort_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, int n,
+                                                         uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
+    __shared__ unsigned long long s[SB_MAX];
+    int np2 = 32;
+    while (np2 < n) np2 <<= 1;
+    for (int i = threadIdx.x; i < np2; i += 1024)
+        s[i] = i < n ? ((unsigned long long)keys[i] << 32) | vals[i] : ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= np2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < np2; i += 1024) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const unsigned long long a = s[i], b = s[l];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) {
+                        s[i] = b;
+                        s[l] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    for (int i = threadIdx.x; i < n; i += 1024) {
+        keys_out[i] = (uint32_t)(s[i] >> 32);
+        vals_out[i] = (uint32_t)s[i];
+    }
+}
+
 constexpr int INC_THREADS = 256;
+// search bounds of every block of the two merge passes below, so that the passes themselves start with a
+// (usually empty) range instead of a chain of dependent loads: bnd[b] = lower_bound(first key of block b); the entry
+// behind the last block is nf
+__global__ void __launch_bounds__(256) inc_bounds_old_kernel(const float4* __restrict__ sorted_old, int m_old, GridDesc g,
+                                                            const uint32_t* __restrict__ nkeys, int nf, int nblocks, int* __restrict__ bnd) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > nblocks) return;
+    if (b == nblocks) {
+        bnd[b] = nf;
+        return;
+    }
+    const float4 p = sorted_old[(size_t)b * INC_THREADS];
+    const uint32_t key = (uint32_t)(cell_of(p.z, g.oz, g.inv_cell, g.nz) * g.ny + cell_of(p.y, g.oy, g.inv_cell, g.ny)) * (uint32_t)g.nx +
+                         (uint32_t)cell_of(p.x, g.ox, g.inv_cell, g.nx);
+    bnd[b] = lower_bound_u32(nkeys, 0, nf, key);
+}
+__global__ void __launch_bounds__(256) inc_bounds_cell_kernel(int ncells, const uint32_t* __restrict__ nkeys, int nf, int nblocks,
+                                                             int* __restrict__ bnd) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > nblocks) return;
+    bnd[b] = b == nblocks ? nf : lower_bound_u32(nkeys, 0, nf, (uint32_t)b * INC_THREADS);
+}
 // old sorted point j moves to j + (new points in lower cells)
 __global__ void __launch_bounds__(INC_THREADS) inc_merge_old_kernel(const float4* __restrict__ sorted_old, int m_old, GridDesc g,
-                                                                   const uint32_t* __restrict__ nkeys, int nf, float4* __restrict__ sorted_new) {
-    __shared__ int s_lo, s_hi;
-    const int j0 = blockIdx.x * INC_THREADS, j = j0 + threadIdx.x;
-    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-    uint32_t key = 0;
-    if (j < m_old) {
-        p = sorted_old[j];
-        key = (uint32_t)(cell_of(p.z, g.oz, g.inv_cell, g.nz) * g.ny + cell_of(p.y, g.oy, g.inv_cell, g.ny)) * (uint32_t)g.nx +
-              (uint32_t)cell_of(p.x, g.ox, g.inv_cell, g.nx);
+                                                                   const uint32_t* __restrict__ nkeys, const int* __restrict__ bnd,
+                                                                   float4* __restrict__ sorted_new) {
+    const int j = blockIdx.x * INC_THREADS + threadIdx.x;
+    if (j >= m_old) return;
+    const float4 p = sorted_old[j];
+    // the block's points are consecutive in cell order: its keys lie between the first key of this block and the
+    // first key of the next one, so the answer lies in [bnd[b], bnd[b+1]] — an empty range for most blocks
+    const int lo = __ldg(bnd + blockIdx.x), hi = __ldg(bnd + blockIdx.x + 1);
+    int sh = lo;
+    if (lo < hi) {
+        const uint32_t key = (uint32_t)(cell_of(p.z, g.oz, g.inv_cell, g.nz) * g.ny + cell_of(p.y, g.oy, g.inv_cell, g.ny)) * (uint32_t)g.nx +
+                             (uint32_t)cell_of(p.x, g.ox, g.inv_cell, g.nx);
+        sh = lower_bound_u32(nkeys, lo, hi, key);
     }
-    // the block's points are consecutive in cell order: narrow the search range once per block
-    const int jl = min(j0 + INC_THREADS, m_old) - 1;
-    if (threadIdx.x == 0) s_lo = lower_bound_u32(nkeys, 0, nf, key);
-    if (j == jl) s_hi = lower_bound_u32(nkeys, 0, nf, key + 1u);
-    __syncthreads();
-    if (j < m_old) sorted_new[j + lower_bound_u32(nkeys, s_lo, s_hi, key)] = p;
+    sorted_new[j + sh] = p;
 }
 
 // new point i (i-th in key order) lands behind the old points of its cell and the new ones before it
@@ -396,18 +449,13 @@ __global__ void __launch_bounds__(256) inc_merge_new_kernel(const float4* __rest
 }
 
 // cell_start[c] += new points in cells < c (in place; runs after inc_merge_new_kernel has read the old table)
-__global__ void __launch_bounds__(INC_THREADS) inc_cell_kernel(uint32_t* __restrict__ cs, int ncells, const uint32_t* __restrict__ nkeys, int nf) {
-    __shared__ int s_lo, s_hi;
-    const int c0 = blockIdx.x * INC_THREADS, c = c0 + threadIdx.x;
-    if (threadIdx.x == 0) {
-        s_lo = lower_bound_u32(nkeys, 0, nf, (uint32_t)c0);
-        s_hi = lower_bound_u32(nkeys, 0, nf, (uint32_t)min(c0 + INC_THREADS, ncells + 1));
-    }
-    __syncthreads();
-    if (c <= ncells && s_hi > 0) {
-        const int add = lower_bound_u32(nkeys, s_lo, s_hi, (uint32_t)c);
-        if (add) cs[c] += (uint32_t)add;
-    }
+__global__ void __launch_bounds__(INC_THREADS) inc_cell_kernel(uint32_t* __restrict__ cs, int ncells, const uint32_t* __restrict__ nkeys,
+                                                              const int* __restrict__ bnd) {
+    const int c = blockIdx.x * INC_THREADS + threadIdx.x;
+    if (c > ncells) return;
+    const int lo = __ldg(bnd + blockIdx.x), hi = __ldg(bnd + blockIdx.x + 1);
+    const int add = lo < hi ? lower_bound_u32(nkeys, lo, hi, (uint32_t)c) : lo;
+    if (add) cs[c] += (uint32_t)add;
 }
 }  // namespace
 
@@ -443,16 +491,29 @@ int map_append_incremental(Ctx* c, Map& mp, int n_new, bool* merged) {
         int bits = 1;
         while ((1ll << bits) <= (long long)g.ncells) ++bits;
         uint32_t *ks, *vs;
-        CKS(radix_sort_pairs(c, mp.ik_a.as<uint32_t>(), mp.ik_b.as<uint32_t>(), mp.iv_a.as<uint32_t>(), mp.iv_b.as<uint32_t>(), n_new, bits,
-                             c->d_scratch, &ks, &vs));
+        if (n_new <= SB_MAX) {
+            ks = mp.ik_b.as<uint32_t>();
+            vs = mp.iv_b.as<uint32_t>();
+            small_sort_kernel<<<1, 1024, 0, c->stream>>>(mp.ik_a.as<uint32_t>(), mp.iv_a.as<uint32_t>(), n_new, ks, vs);
+            c->launches += 1;
+        } else {
+            CKS(radix_sort_pairs(c, mp.ik_a.as<uint32_t>(), mp.ik_b.as<uint32_t>(), mp.iv_a.as<uint32_t>(), mp.iv_b.as<uint32_t>(), n_new, bits,
+                                 c->d_scratch, &ks, &vs));
+        }
         tr.mark("inc sort");
         const int m_old = g.m, m_new = m_old + nf;
         if (mp.sorted_alt.cap < (size_t)m_new * sizeof(float4)) CKS(reserve(c, mp.sorted_alt, ((size_t)m_new + (size_t)m_new / 4) * sizeof(float4)));
         float4* s_new = mp.sorted_alt.as<float4>();
-        inc_merge_old_kernel<<<(m_old + INC_THREADS - 1) / INC_THREADS, INC_THREADS, 0, c->stream>>>(g.sorted, m_old, g, ks, nf, s_new);
+        const int ob = (m_old + INC_THREADS - 1) / INC_THREADS, cb = (g.ncells + 1 + INC_THREADS - 1) / INC_THREADS;
+        CKS(reserve_grow(c, mp.inc_bnd, ((size_t)(ob + 1) + (size_t)(cb + 1)) * sizeof(int)));
+        int* bnd_old = mp.inc_bnd.as<int>();
+        int* bnd_cell = bnd_old + (ob + 1);
+        inc_bounds_old_kernel<<<(ob + 1 + 255) / 256, 256, 0, c->stream>>>(g.sorted, m_old, g, ks, nf, ob, bnd_old);
+        inc_bounds_cell_kernel<<<(cb + 1 + 255) / 256, 256, 0, c->stream>>>(g.ncells, ks, nf, cb, bnd_cell);
+        inc_merge_old_kernel<<<ob, INC_THREADS, 0, c->stream>>>(g.sorted, m_old, g, ks, bnd_old, s_new);
         inc_merge_new_kernel<<<(nf + 255) / 256, 256, 0, c->stream>>>(mp.pts.as<float4>(), ks, vs, nf, g.cell_start, s_new);
-        inc_cell_kernel<<<(g.ncells + 1 + INC_THREADS - 1) / INC_THREADS, INC_THREADS, 0, c->stream>>>(mp.cell_start.as<uint32_t>(), g.ncells, ks, nf);
-        c->launches += 3;
+        inc_cell_kernel<<<cb, INC_THREADS, 0, c->stream>>>(mp.cell_start.as<uint32_t>(), g.ncells, ks, bnd_cell);
+        c->launches += 5;
         CK(cudaGetLastError());
         tr.mark("inc merge");
         std::swap(mp.sorted, mp.sorted_alt);
