@@ -29,6 +29,7 @@ struct BatchParams {
     const int32_t* toff;
     int n_pairs, max_n, max_m;
     int max_iterations, early_exit;
+    float cell_pts;  // target points per cell (by volume) of the per-pair grid
     int use_hints;  // previous-iteration neighbour kept per source point (16-bit slot: needs max_m < 65535)
     float gate_f, gate_r;
     double rot_eps, trans_eps, mse_abs_eps;
@@ -269,7 +270,7 @@ __global__ void __launch_bounds__(RB_THREADS, 2) reg_batch_kernel(const __grid_c
             const float emax = fmaxf(ex, fmaxf(ey, ez));
             const float fl = fmaxf(emax * 1e-3f, 1e-6f);
             const float vol = fmaxf(ex, fl) * fmaxf(ey, fl) * fmaxf(ez, fl);
-            float cell = cbrtf(vol / fmaxf(1.0f, (float)m * 0.5f));  // ~2 points per cell by volume
+            float cell = cbrtf(vol / fmaxf(1.0f, (float)m / P.cell_pts));  // cell_pts points per cell by volume
             cell = fmaxf(cell, fmaxf(emax * 1e-4f, 1e-6f));
             int nx, ny, nz;
             for (;;) {
@@ -520,6 +521,8 @@ int register_batch(Ctx* c, const float4* d_src, const int32_t* d_soff, const flo
     P.max_iterations = o->max_iterations;
     P.early_exit = o->early_exit;
     P.use_hints = (c->use_hints && max_m < 65535) ? 1 : 0;
+    P.cell_pts = 2.0f;
+    if (const char* e = std::getenv("ICP4R_RB_CELL_PTS")) P.cell_pts = std::max(0.05f, (float)std::atof(e));
     gate_params(o->max_corr_dist, &P.gate_f, &P.gate_r);
     P.rot_eps = o->rot_eps;
     P.trans_eps = o->trans_eps;

@@ -813,9 +813,13 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
         P.xt = c->d_xt.as<XchTable>();
     }
     const bool gicp = o->residual == ICP4R_GICP;
-    if (!sharded && !gicp && c->use_hints) {
+    if (!gicp && c->use_hints) {
         CKS(reserve_grow(c, c->d_nbprev, (size_t)n * ICP4R_MAX_K * sizeof(int32_t)));
         P.nb_prev = c->d_nbprev.as<int32_t>();
+        // Sharded maps: a rank only refreshes the entries of the points it owns, so a point that changes owner finds
+        // an older entry — still k valid points of this rank's slab, hence still a bound — or none (-1). Entries of
+        // an earlier CALL must not survive (the map may have changed since): clear them.
+        if (sharded && n > 0) CK(cudaMemsetAsync(c->d_nbprev.p, 0xFF, (size_t)n * ICP4R_MAX_K * sizeof(int32_t), c->stream));
     }
     if (gicp) {
         if (sharded) return fail(c, ICP4R_ERR_UNSUPPORTED, "GICP is not available for sharded maps yet");
