@@ -69,6 +69,13 @@ static void free_map(Map& m) {
     release(m.vals_a);
     release(m.vals_b);
     release(m.normals);
+    release(m.coarse);
+    release(m.sorted_alt);
+    release(m.ik_a);
+    release(m.ik_b);
+    release(m.iv_a);
+    release(m.iv_b);
+    release(m.inc_bnd);
     m.m = m.m_valid = 0;
     m.built = false;
 }

@@ -52,6 +52,7 @@ struct GridDesc {
     float margin;         // absolute slack used by the termination bound (covers float rounding)
     const float4* sorted; // x, y, z, bit-cast original index
     const uint32_t* cell_start;  // [ncells + 1]
+    const uint32_t* coarse;      // points per block of 8 x 8 x 8 cells, dims ceil(n / 8) (bound for far queries)
 };
 
 struct Map {
@@ -59,6 +60,7 @@ struct Map {
     DevBuf valid;       // uint8  [cap]
     DevBuf sorted;      // float4 [m_sorted]
     DevBuf cell_start;  // uint32 [ncells + 1]
+    DevBuf coarse;      // uint32 [ceil(nx/8) * ceil(ny/8) * ceil(nz/8)]
     DevBuf keys_a, keys_b, vals_a, vals_b;  // radix sort ping-pong
     int m = 0;          // points ever offered (index space)
     int m_valid = 0;
@@ -75,6 +77,7 @@ struct Map {
     DevBuf ik_a, ik_b, iv_a, iv_b;   // keys / indices of the batch being merged
     DevBuf inc_bnd;                  // per-block search bounds of the merge passes
     int valid_at_build = 0;          // valid points at the last full build (density drift -> full rebuild)
+    bool quick_build = false;        // skip the occupancy-based cell refinement (short-lived clouds: GICP source)
     bool padded = false;             // grid built with slack around the bounding box (set once an append fell outside)
 };
 
@@ -143,6 +146,7 @@ struct RegParams {  // kernel parameters that change per call; lives in device m
     // the map's buffers: read from here (not from the by-value GridDesc) so that captured loops survive Add_Points
     const float4* map_sorted;
     const uint32_t* map_cell_start;
+    const uint32_t* map_coarse;
     const float4* map_pts;
     int map_m;
     // neighbours found at the previous iteration, K per source point (NULL: no hints — sharded maps, GICP)

@@ -62,58 +62,75 @@ __device__ __forceinline__ void smallest_eigvec3(const double C[9], double n[3])
     n[2] = v2 / len;
 }
 
-// one warp per point of the grid's own cloud: k-NN among the cloud (the point itself included), covariance about
-// the neighbours' mean divided by k, smallest eigenvector -> normals[3 * original_index]
+// k-NN among the grid's own cloud (the point itself included), covariance about the neighbours' mean divided by k,
+// smallest eigenvector -> normals[3 * original_index]. A warp searches the neighbours of PARK consecutive points one
+// after the other (all lanes cooperate on one query) and parks their coordinates in shared memory; the covariance
+// and the Jacobi eigen-solver (a few thousand fp64 instructions) then run with ONE POINT PER LANE instead of
+// redundantly on all 32 lanes for every single point.
 template <int K>
-__global__ void __launch_bounds__(256) normals_kernel(GridDesc g, const float4* __restrict__ pts, int k, double* __restrict__ normals) {
+__global__ void __launch_bounds__(256) normals_kernel(GridDesc g, const float4* __restrict__ pts, int k, int chunk, double* __restrict__ normals) {
+    constexpr int PARK = K <= 5 ? 32 : (K <= 8 ? 16 : 8);  // upper bound of `chunk` (points a warp parks per round)
     __shared__ WarpSegs segs[8];
-    const int lane = threadIdx.x & 31;
+    __shared__ float nbuf[8][PARK][K][3];
+    __shared__ int nfound[8][PARK], nidx[8][PARK];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int i = warp; i < g.m; i += nwarps) {
-        const float4 p = __ldg(g.sorted + i);
-        const uint64_t mine = warp_grid_knn<K>(g, segs[threadIdx.x >> 5], p.x, p.y, p.z, INFINITY, INFINITY, lane);
-        const bool have = (lane < k) && (mine != KEY_EMPTY);
-        const int found = __popc(__ballot_sync(FULL, have));
-        float4 nb = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (have) nb = __ldg(pts + key_idx(mine));
-        double mean[3] = {0, 0, 0}, C[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        float nx[K], ny[K], nz[K];
-#pragma unroll
-        for (int j = 0; j < K; ++j) {
-            nx[j] = __shfl_sync(FULL, nb.x, j);
-            ny[j] = __shfl_sync(FULL, nb.y, j);
-            nz[j] = __shfl_sync(FULL, nb.z, j);
-            if (j < found) {
-                mean[0] += (double)nx[j];
-                mean[1] += (double)ny[j];
-                mean[2] += (double)nz[j];
+    for (int base = warp * chunk; base < g.m; base += nwarps * chunk) {
+        const int cnt = min(chunk, g.m - base);
+        for (int j = 0; j < cnt; ++j) {
+            const float4 p = __ldg(g.sorted + base + j);
+            const uint64_t mine = warp_grid_knn<K>(g, segs[w], p.x, p.y, p.z, INFINITY, INFINITY, lane);
+            const bool have = (lane < k) && (mine != KEY_EMPTY);
+            const int found = __popc(__ballot_sync(FULL, have));
+            if (have) {
+                const float4 nb = __ldg(pts + key_idx(mine));
+                nbuf[w][j][lane][0] = nb.x;
+                nbuf[w][j][lane][1] = nb.y;
+                nbuf[w][j][lane][2] = nb.z;
+            }
+            if (lane == 0) {
+                nfound[w][j] = found;
+                nidx[w][j] = __float_as_int(p.w);
             }
         }
-        const double fdiv = (double)(found > 0 ? found : 1);
-        mean[0] /= fdiv;
-        mean[1] /= fdiv;
-        mean[2] /= fdiv;
+        __syncwarp();
+        if (lane < cnt) {
+            const int found = nfound[w][lane];
+            double mean[3] = {0, 0, 0}, C[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-        for (int j = 0; j < K; ++j) {
-            if (j < found) {
-                const double d[3] = {(double)nx[j] - mean[0], (double)ny[j] - mean[1], (double)nz[j] - mean[2]};
-#pragma unroll
-                for (int a = 0; a < 3; ++a)
-#pragma unroll
-                    for (int b = 0; b < 3; ++b) C[3 * a + b] += d[a] * d[b];
+            for (int j = 0; j < K; ++j) {
+                if (j < found) {
+                    mean[0] += (double)nbuf[w][lane][j][0];
+                    mean[1] += (double)nbuf[w][lane][j][1];
+                    mean[2] += (double)nbuf[w][lane][j][2];
+                }
             }
-        }
+            const double fdiv = (double)(found > 0 ? found : 1);
+            mean[0] /= fdiv;
+            mean[1] /= fdiv;
+            mean[2] /= fdiv;
 #pragma unroll
-        for (int a = 0; a < 9; ++a) C[a] /= (double)k;  // fast_gicp divides by k_correspondences_
-        double n[3];
-        smallest_eigvec3(C, n);
-        if (lane == 0) {
-            const size_t o = 3 * (size_t)__float_as_int(p.w);
+            for (int j = 0; j < K; ++j) {
+                if (j < found) {
+                    const double d[3] = {(double)nbuf[w][lane][j][0] - mean[0], (double)nbuf[w][lane][j][1] - mean[1],
+                                         (double)nbuf[w][lane][j][2] - mean[2]};
+#pragma unroll
+                    for (int a = 0; a < 3; ++a)
+#pragma unroll
+                        for (int b = 0; b < 3; ++b) C[3 * a + b] += d[a] * d[b];
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < 9; ++a) C[a] /= (double)k;  // fast_gicp divides by k_correspondences_
+            double n[3];
+            smallest_eigvec3(C, n);
+            const size_t o = 3 * (size_t)nidx[w][lane];
             normals[o] = n[0];
             normals[o + 1] = n[1];
             normals[o + 2] = n[2];
         }
+        __syncwarp();
     }
 }
 
@@ -121,11 +138,15 @@ int gicp_normals(Ctx* c, Map& mp, int k) {
     if (mp.normals_k == k) return ICP4R_OK;
     CKS(reserve_grow(c, mp.normals, (size_t)std::max(mp.m, 1) * 3 * sizeof(double)));
     if (mp.grid.m > 0) {
-        const int blocks = std::min((mp.grid.m + 7) / 8, c->sm_count * 8);
+        // points per warp and round: as many as fit the parking buffers, but a small cloud is spread over all warps
+        const int park = k <= 5 ? 32 : (k <= 8 ? 16 : 8);
+        const int warps_avail = c->sm_count * 8 * 8;
+        const int chunk = std::min(park, std::max(1, (mp.grid.m + warps_avail - 1) / warps_avail));
+        const int blocks = std::min((mp.grid.m + 8 * chunk - 1) / (8 * chunk), c->sm_count * 8);
         double* out = mp.normals.as<double>();
-        if (k <= 5) normals_kernel<5><<<blocks, 256, 0, c->stream>>>(mp.grid, mp.pts.as<float4>(), k, out);
-        else if (k <= 8) normals_kernel<8><<<blocks, 256, 0, c->stream>>>(mp.grid, mp.pts.as<float4>(), k, out);
-        else normals_kernel<16><<<blocks, 256, 0, c->stream>>>(mp.grid, mp.pts.as<float4>(), k, out);
+        if (k <= 5) normals_kernel<5><<<blocks, 256, 0, c->stream>>>(mp.grid, mp.pts.as<float4>(), k, chunk, out);
+        else if (k <= 8) normals_kernel<8><<<blocks, 256, 0, c->stream>>>(mp.grid, mp.pts.as<float4>(), k, chunk, out);
+        else normals_kernel<16><<<blocks, 256, 0, c->stream>>>(mp.grid, mp.pts.as<float4>(), k, chunk, out);
         c->launches += 1;
         CK(cudaGetLastError());
     }

@@ -111,6 +111,31 @@ __global__ void __launch_bounds__(256) occupied_kernel(const uint32_t* __restric
     if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(out, cnt);
 }
 
+// coarse occupancy: one thread per block of 8 x 8 x 8 cells sums the lengths of its 64 x-row segments
+__global__ void __launch_bounds__(256) coarse_count_kernel(const uint32_t* __restrict__ cs, GridDesc g, uint32_t* __restrict__ coarse) {
+    const int cnx = (g.nx + 7) >> 3, cny = (g.ny + 7) >> 3, cnz = (g.nz + 7) >> 3;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cnx * cny * cnz) return;
+    const int Z = t / (cnx * cny), rem = t - Z * (cnx * cny), Y = rem / cnx, X = rem - Y * cnx;
+    const int xa = X << 3, xb = min(xa + 8, g.nx);
+    uint32_t cnt = 0;
+    for (int z = Z << 3; z < min((Z << 3) + 8, g.nz); ++z)
+        for (int y = Y << 3; y < min((Y << 3) + 8, g.ny); ++y) {
+            const uint32_t rowbase = (uint32_t)(z * g.ny + y) * (uint32_t)g.nx;
+            cnt += __ldg(cs + rowbase + xb) - __ldg(cs + rowbase + xa);
+        }
+    coarse[t] = cnt;
+}
+
+static int build_coarse(Ctx* c, Map& mp, GridDesc& g) {
+    const size_t nc = (size_t)((g.nx + 7) >> 3) * (size_t)((g.ny + 7) >> 3) * (size_t)((g.nz + 7) >> 3);
+    CKS(reserve_grow(c, mp.coarse, nc * sizeof(uint32_t)));
+    coarse_count_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, c->stream>>>(mp.cell_start.as<uint32_t>(), g, mp.coarse.as<uint32_t>());
+    c->launches += 1;
+    g.coarse = mp.coarse.as<uint32_t>();
+    return ICP4R_OK;
+}
+
 int map_reserve(Ctx* c, Map& mp, int cap) {
     if ((size_t)cap * sizeof(float4) <= mp.pts.cap) return ICP4R_OK;
     // grow geometrically, keep contents
@@ -169,6 +194,7 @@ int map_rebuild_grid(Ctx* c, Map& mp) {
         g.m = 0;
         g.sorted = mp.sorted.as<float4>();
         g.cell_start = mp.cell_start.as<uint32_t>();
+        CKS(build_coarse(c, mp, g));
         mp.grid = g;
         mp.built = true;
         return ICP4R_OK;
@@ -274,7 +300,7 @@ int map_rebuild_grid(Ctx* c, Map& mp) {
         c->launches += 1;
         tr.mark("cell table");
         bool again = false;
-        if (!(mp.user_cell > 0.f) && pass < 2 && nvalid >= 64) {
+        if (!(mp.user_cell > 0.f) && !mp.quick_build && pass < 2 && nvalid >= 64) {
             int* d_occ = c->d_scratch.as<int>();
             CK(cudaMemsetAsync(d_occ, 0, sizeof(int), c->stream));
             occupied_kernel<<<std::min((g.ncells + 255) / 256, c->sm_count * 8), 256, 0, c->stream>>>(mp.cell_start.as<uint32_t>(),
@@ -305,9 +331,11 @@ int map_rebuild_grid(Ctx* c, Map& mp) {
         tr.mark("gather");
         break;
     }
-    CK(cudaGetLastError());
     g.sorted = mp.sorted.as<float4>();
     g.cell_start = mp.cell_start.as<uint32_t>();
+    CKS(build_coarse(c, mp, g));
+    tr.mark("coarse table");
+    CK(cudaGetLastError());
     mp.grid = g;
     mp.built = true;
     mp.hint_cell = g.cell;
@@ -514,6 +542,7 @@ int map_append_incremental(Ctx* c, Map& mp, int n_new, bool* merged) {
         inc_merge_new_kernel<<<(nf + 255) / 256, 256, 0, c->stream>>>(mp.pts.as<float4>(), ks, vs, nf, g.cell_start, s_new);
         inc_cell_kernel<<<cb, INC_THREADS, 0, c->stream>>>(mp.cell_start.as<uint32_t>(), g.ncells, ks, bnd_cell);
         c->launches += 5;
+        CKS(build_coarse(c, mp, mp.grid));
         CK(cudaGetLastError());
         tr.mark("inc merge");
         std::swap(mp.sorted, mp.sorted_alt);

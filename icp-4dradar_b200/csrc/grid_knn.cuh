@@ -94,7 +94,93 @@ __device__ __forceinline__ void scan_segments(const float4* __restrict__ sorted,
     }
 }
 
+// Coarse occupancy: entry (X, Y, Z) counts the points of the 8 x 8 x 8 cells [8X, 8X+8) x ... ; dims ceil(n / 8).
+constexpr int COARSE_SHIFT = 3;
+constexpr int COARSE_MAX_R = 24;
+// Squared distance within which at least K points are guaranteed to lie (-1: not found within COARSE_MAX_R coarse cells).
+template <int K>
+__device__ __forceinline__ float coarse_bound(const GridDesc& g, const uint32_t* __restrict__ coarse, int cx, int cy, int cz, float qx,
+                                              float qy, float qz, float margin, int lane) {
+    const int cnx = (g.nx + 7) >> COARSE_SHIFT, cny = (g.ny + 7) >> COARSE_SHIFT, cnz = (g.nz + 7) >> COARSE_SHIFT;
+    const int X = cx >> COARSE_SHIFT, Y = cy >> COARSE_SHIFT, Z = cz >> COARSE_SHIFT;
+    int Rc = 0;
+    for (;;) {
+        const int x0 = max(X - Rc, 0), x1 = min(X + Rc, cnx - 1), y0 = max(Y - Rc, 0), y1 = min(Y + Rc, cny - 1);
+        const int z0 = max(Z - Rc, 0), z1 = min(Z + Rc, cnz - 1);
+        const int sx = x1 - x0 + 1, sy = y1 - y0 + 1, sz = z1 - z0 + 1;
+        const int ncube = sx * sy * sz;
+        uint32_t part = 0;
+        for (int t = lane; t < ncube; t += 32) {
+            const int tz = t / (sx * sy), rem = t - tz * (sx * sy), ty = rem / sx, tx = rem - ty * sx;
+            part += __ldg(coarse + ((size_t)(z0 + tz) * cny + (y0 + ty)) * cnx + (x0 + tx));
+        }
+        part = __reduce_add_sync(FULL, part);
+        if (part >= (uint32_t)K) {
+            const float cw = g.cell * (float)(1 << COARSE_SHIFT);
+            const float lo[3] = {g.ox + (float)x0 * cw, g.oy + (float)y0 * cw, g.oz + (float)z0 * cw};
+            const float hi[3] = {fminf(g.ox + (float)(x1 + 1) * cw, g.ox + (float)g.nx * g.cell),
+                                 fminf(g.oy + (float)(y1 + 1) * cw, g.oy + (float)g.ny * g.cell),
+                                 fminf(g.oz + (float)(z1 + 1) * cw, g.oz + (float)g.nz * g.cell)};
+            const float q[3] = {qx, qy, qz};
+            float d2 = 0.0f;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const float b = fmaxf(fabsf(q[a] - lo[a]), fabsf(hi[a] - q[a])) + 2.0f * margin;
+                d2 += b * b;
+            }
+            return d2 * 1.00001f;
+        }
+        if (sx == cnx && sy == cny && sz == cnz) return -1.0f;  // the whole map holds fewer than K points
+        if (Rc >= COARSE_MAX_R) return -1.0f;
+        Rc = Rc < 4 ? Rc + 1 : Rc + (Rc >> 1);  // 0 1 2 3 4 6 9 13 19 28
+    }
+}
+
+// One pruned pass over the cells that the ball of squared radius `bound2` (clipped to the gate box) touches: the
+// fallback for queries whose shell search hit the ring cap. Kept out of line — it is rare and must not cost the
+// common path registers or instructions. `bound2` must bound the K-th distance (>= K valid points within it).
+template <int K>
+static __device__ __noinline__ uint64_t wide_ball_knn(const GridDesc& g, const float4* __restrict__ sorted, const uint32_t* __restrict__ cs,
+                                                      WarpSegs& sg, float qx, float qy, float qz, float gate_f, float br, float bound2,
+                                                      float margin, int lane) {
+    const int cx = cell_of(qx, g.ox, g.inv_cell, g.nx), cy = cell_of(qy, g.oy, g.inv_cell, g.ny), cz = cell_of(qz, g.oz, g.inv_cell, g.nz);
+    const int lox = cell_of(qx - br, g.ox, g.inv_cell, g.nx), hix = cell_of(qx + br, g.ox, g.inv_cell, g.nx);
+    const int loy = cell_of(qy - br, g.oy, g.inv_cell, g.ny), hiy = cell_of(qy + br, g.oy, g.inv_cell, g.ny);
+    const int loz = cell_of(qz - br, g.oz, g.inv_cell, g.nz), hiz = cell_of(qz + br, g.oz, g.inv_cell, g.nz);
+    const int sy = hiy - loy + 1, sz = hiz - loz + 1, rows = sy * sz;
+    const float kd = bound2 * 1.000001f;
+    const uint64_t bound_key = ((uint64_t)__float_as_uint(bound2) << 32) | 0xFFFFFFFFull;
+    TopK<K> list;
+    list.clear();
+    for (int rb = 0; rb < rows; rb += 32) {
+        const int r = rb + lane;
+        uint32_t s0 = 0, e0 = 0;
+        if (r < rows) {
+            const int rz = r / sy, y = loy + (r - rz * sy), z = loz + rz;
+            const int dy = y - cy, dz = z - cz;
+            float ddy = dy > 0 ? (g.oy + (float)y * g.cell) - qy : (dy < 0 ? qy - (g.oy + (float)(y + 1) * g.cell) : 0.0f);
+            float ddz = dz > 0 ? (g.oz + (float)z * g.cell) - qz : (dz < 0 ? qz - (g.oz + (float)(z + 1) * g.cell) : 0.0f);
+            ddy = fmaxf(ddy - margin, 0.0f);
+            ddz = fmaxf(ddz - margin, 0.0f);
+            const float dyz2 = (ddy * ddy + ddz * ddz) * 0.999999f;
+            if (!(dyz2 > kd)) {
+                const float xr = sqrtf(kd - dyz2) * 1.000001f + margin;
+                const int xa = max(lox, cell_of(qx - xr, g.ox, g.inv_cell, g.nx)), xb = min(hix, cell_of(qx + xr, g.ox, g.inv_cell, g.nx));
+                if (xa <= xb) {
+                    const uint32_t rowbase = (uint32_t)(z * g.ny + y) * (uint32_t)g.nx;
+                    s0 = __ldg(cs + rowbase + xa);
+                    e0 = __ldg(cs + rowbase + xb + 1);
+                }
+            }
+        }
+        if (__any_sync(FULL, e0 > s0)) scan_segments<K>(sorted, sg, s0, e0, 0u, 0u, lane, qx, qy, qz, gate_f, bound_key, list);
+    }
+    return warp_merge_topk<K>(list, lane);
+}
+
 // Returns, in lane r < K, the r-th nearest neighbour's packed key (KEY_EMPTY if fewer exist).
+// WIDE = false leaves the coarse-table fallback out (the fused iteration kernel: its register and instruction budget
+// is tuned for the common path, and its queries are gated scan points near the map).
 // `g` carries the geometry only; the sorted points, the cell table and their length are passed next to it so that a
 // captured launch (whose GridDesc is baked in by value) can pick them up from device memory at run time.
 //
@@ -102,10 +188,10 @@ __device__ __forceinline__ void scan_segments(const float4* __restrict__ sorted,
 // the previous pose). The k-th distance can then not exceed `hint`, so ONE pass over the cells that intersect the ball
 // of that radius (clipped to the gate box) sees every point that can be part of the answer: no own-cell probe, no
 // shell-by-shell proof, one merge. The result is the same set, the hint only removes work.
-template <int K>
+template <int K, bool WIDE = true>
 __device__ __forceinline__ uint64_t warp_grid_knn(const GridDesc& g, const float4* __restrict__ sorted, const uint32_t* __restrict__ cs,
-                                                  int m_sorted, WarpSegs& sg, float qx, float qy, float qz, float gate_f, float gate_r,
-                                                  int lane, float hint = -1.0f) {
+                                                  const uint32_t* __restrict__ coarse, int m_sorted, WarpSegs& sg, float qx, float qy,
+                                                  float qz, float gate_f, float gate_r, int lane, float hint = -1.0f) {
     const float qmax = fmaxf(fabsf(qx), fmaxf(fabsf(qy), fabsf(qz)));
     const float margin = fmaxf(g.margin, 9.5367431640625e-7f * qmax);  // 2^-20 * magnitude
 
@@ -231,8 +317,23 @@ __device__ __forceinline__ uint64_t warp_grid_knn(const GridDesc& g, const float
             break;
         }
     }
+    if (WIDE && !done && rneed > 0 && prev < rneed && coarse != nullptr) {
+        // Ring cap reached (a query far from the map's points, or a gate much wider than the cells). The coarse
+        // occupancy table tells how far one has to go to be SURE of K points: that distance bounds the K-th distance
+        // like the previous-iteration hint does, and one pruned pass over the ball settles the query. The pass may be
+        // wide, but an empty row costs two loads — far less than scanning the whole map.
+        const float cb = coarse_bound<K>(g, coarse, cx, cy, cz, qx, qy, qz, margin, lane);
+        if (cb >= 0.0f) {
+            const float brw = fminf(gr, sqrtf(cb) * 1.000001f + margin);
+            // rows the pass would touch (clipped to the grid) against the points an exhaustive scan would read
+            const float wy = (float)(cell_of(qy + brw, g.oy, g.inv_cell, g.ny) - cell_of(qy - brw, g.oy, g.inv_cell, g.ny) + 1);
+            const float wz = (float)(cell_of(qz + brw, g.oz, g.inv_cell, g.nz) - cell_of(qz - brw, g.oz, g.inv_cell, g.nz) + 1);
+            if (wy * wz * 3.0f < (float)m_sorted)
+                return wide_ball_knn<K>(g, sorted, cs, sg, qx, qy, qz, gate_f, brw, fminf(cb, gate_f), margin, lane);
+        }
+    }
     if (!done && rneed > 0 && prev < rneed) {
-        // ring cap reached (far-away ungated query or a very wide gate): exhaustive scan, still exact
+        // no usable bound (tiny map, fewer than K points, or a ball that would cover most of the map): exhaustive scan
         list.clear();
         scan_segments<K>(sorted, sg, 0u, lane == 0 ? (uint32_t)m_sorted : 0u, 0u, 0u, lane, qx, qy, qz, gate_f, KEY_EMPTY, list);
         mine = warp_merge_topk<K>(list, lane);
@@ -246,6 +347,6 @@ namespace icp4r {
 template <int K>
 __device__ __forceinline__ uint64_t warp_grid_knn(const GridDesc& g, WarpSegs& sg, float qx, float qy, float qz, float gate_f,
                                                   float gate_r, int lane) {
-    return warp_grid_knn<K>(g, g.sorted, g.cell_start, g.m, sg, qx, qy, qz, gate_f, gate_r, lane);
+    return warp_grid_knn<K>(g, g.sorted, g.cell_start, g.coarse, g.m, sg, qx, qy, qz, gate_f, gate_r, lane);
 }
 }  // namespace icp4r

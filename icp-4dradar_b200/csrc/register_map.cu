@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(RM_THREADS, 1)
                 hint = P.gate_f;
             }
         }
-        uint64_t mine = warp_grid_knn<KK>(g, P.map_sorted, P.map_cell_start, P.map_m, segs[w], qx, qy, qz, P.gate_f, P.gate_r, lane, hint);
+        uint64_t mine = warp_grid_knn<KK, false>(g, P.map_sorted, P.map_cell_start, nullptr, P.map_m, segs[w], qx, qy, qz, P.gate_f, P.gate_r, lane, hint);
         const bool have = (lane < kq) && (mine != KEY_EMPTY);
         if (!FIT && nbp != nullptr && lane < kq) nbp[lane] = have ? key_idx(mine) : -1;
         if (!FIT && P.dump_idx && lane < kq) P.dump_idx[((size_t)iter * n + i) * kq + lane] = have ? key_idx(mine) : -1;
@@ -783,6 +783,7 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
         RegParams prm;
         double T0[16];
         ResultBlock out;
+        int done_flag;
     };
     Stage* hs = static_cast<Stage*>(c->h_pinned);
     RegParams& P = hs->prm;
@@ -803,6 +804,7 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
     P.dump_idx = dump ? dump->idx : nullptr;
     P.map_sorted = mp.grid.sorted;
     P.map_cell_start = mp.grid.cell_start;
+    P.map_coarse = mp.grid.coarse;
     P.map_pts = mp.pts.as<float4>();
     P.map_m = mp.grid.m;
     P.shard_axis = sharded ? shard_axis : -1;
@@ -829,6 +831,7 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
         Map& sm = c->srcmap;
         sm.m = 0;
         sm.built = false;
+        sm.quick_build = true;  // only its own 5-NN is searched, once: a volume-estimated cell is good enough
         sm.user_cell = 0.f;
         sm.hint_cell = 0.f;
         CKS(map_reserve(c, sm, n));
@@ -861,6 +864,7 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
     GridDesc g = mp.grid;
     g.sorted = nullptr;
     g.cell_start = nullptr;
+    g.coarse = nullptr;
     g.m = 0;
     const int iters = o->max_iterations;
 
@@ -870,15 +874,16 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
     // launches into no-ops. The NCCL all-reduce of the sharded flavour is captured like any other stream operation.
     const bool prof = c->profiling && !sharded && !gicp;
     int enqueue_status = ICP4R_OK;
-    auto enqueue_loop = [&]() {
+    // iterations [it0, it1) and, if `fit`, the fitness pass
+    auto enqueue_loop = [&](int it0, int it1, bool fit) {
         double* acc_ptr = reinterpret_cast<double*>(reinterpret_cast<char*>(d_st) + offsetof(RegState, acc));
         if (gicp) {
             // linearise (grid-wide, accumulators left in st->acc) then one single-block Levenberg-Marquardt step
-            for (int it = 0; it < iters; ++it) {
+            for (int it = it0; it < it1; ++it) {
                 dispatch_iter(c, o->residual, k, MODE_ITER_NOSOLVE, blocks, threads, 1, g, d_prm, d_st, d_part, d_out, it);
                 gicp_lm_step(c, d_prm, d_st, it);
             }
-            dispatch_iter(c, o->residual, k, MODE_FITNESS, blocks, threads, 1, g, d_prm, d_st, d_part, d_out, 0);
+            if (fit) dispatch_iter(c, o->residual, k, MODE_FITNESS, blocks, threads, 1, g, d_prm, d_st, d_part, d_out, 0);
         } else if (sharded && !fused_shard) {
             for (int it = 0; it < iters; ++it) {
                 dispatch_iter(c, o->residual, k, MODE_ITER_NOSOLVE, blocks, threads, 1, g, d_prm, d_st, d_part, d_out, it);
@@ -892,11 +897,11 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
             c->launches += 1;
         } else {
             if (prof) cudaEventRecord(c->prof_events[0], c->stream);
-            for (int it = 0; it < iters; ++it) {
+            for (int it = it0; it < it1; ++it) {
                 dispatch_iter(c, o->residual, k, MODE_ITER, blocks, threads, 1, g, d_prm, d_st, d_part, d_out, it);
                 if (prof) cudaEventRecord(c->prof_events[it + 1], c->stream);
             }
-            dispatch_iter(c, o->residual, k, MODE_FITNESS, blocks, threads, 1, g, d_prm, d_st, d_part, d_out, 0);
+            if (fit) dispatch_iter(c, o->residual, k, MODE_FITNESS, blocks, threads, 1, g, d_prm, d_st, d_part, d_out, 0);
             if (prof) cudaEventRecord(c->prof_events[iters + 1], c->stream);
         }
     };
@@ -907,52 +912,75 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
             c->prof_events.push_back(e);
         }
     }
-    const bool want_graph = c->use_graph && n > 0 && !c->profiling && !(sharded && c->no_graph_sharded);
-    GraphKey key{o->residual, k, blocks, iters, threads | (sharded ? 1 << 16 : 0) | (gicp ? 1 << 17 : 0) | (fused_shard ? 1 << 19 : 0)};
-    cudaGraphExec_t exec = nullptr;
+    const bool want_graph = c->use_graph && n > 0 && !c->profiling && !(sharded && c->no_graph_sharded) && iters < 4096;
     if (want_graph) {
-        // graphs bake the GridDesc by value: drop them when the map geometry or buffers changed
+        // graphs bake the grid geometry by value: drop them when it changed
         if (c->graph_grid_owner != &mp.grid || std::memcmp(&c->graph_grid_copy, &g, sizeof(GridDesc)) != 0) {
             for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
             c->graphs.clear();
             c->graph_grid_owner = &mp.grid;
             c->graph_grid_copy = g;
         }
-        auto it = c->graphs.find(key);
-        if (it != c->graphs.end()) exec = it->second;
     }
-    if (want_graph && !exec) {
-        cudaGraph_t graph = nullptr;
-        // capture on the handle's own stream (a caller-supplied stream may be the legacy default stream, which
-        // cannot be captured); the instantiated graph is then launched on c->stream
-        cudaStream_t run_stream = c->stream;
-        c->stream = c->own_stream;
-        CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-        const int64_t before = c->launches;
-        enqueue_loop();
-        c->graph_launches = c->launches - before;
-        c->launches = before;  // counted at replay time below
-        cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
-        c->stream = run_stream;
-        if (ce == cudaSuccess && enqueue_status == ICP4R_OK) ce = cudaGraphInstantiate(&exec, graph, 0);
-        if (graph) cudaGraphDestroy(graph);
-        if (ce != cudaSuccess || enqueue_status != ICP4R_OK) {
-            cudaGetLastError();
-            exec = nullptr;
-            enqueue_status = ICP4R_OK;
-            if (sharded) c->no_graph_sharded = true;  // this NCCL build can not be captured: launch directly from now on
-            else return fail(c, ICP4R_ERR_CUDA, "graph capture of the registration loop failed: %s", cudaGetErrorString(ce));
-        } else {
-            c->graphs[key] = exec;
-            c->graph_launch_counts[key] = c->graph_launches;
+    auto run_range = [&](int it0, int it1, bool fit) -> int {
+        GraphKey key{o->residual, k, blocks, it0 + 4096 * it1,
+                     threads | (sharded ? 1 << 16 : 0) | (gicp ? 1 << 17 : 0) | (fused_shard ? 1 << 19 : 0) | (fit ? 1 << 21 : 0)};
+        cudaGraphExec_t exec = nullptr;
+        if (want_graph) {
+            auto it = c->graphs.find(key);
+            if (it != c->graphs.end()) exec = it->second;
         }
-    }
-    if (exec) {
-        CK(cudaGraphLaunch(exec, c->stream));
-        c->launches += c->graph_launch_counts[key];
+        if (want_graph && !exec) {
+            cudaGraph_t graph = nullptr;
+            // capture on the handle's own stream (a caller-supplied stream may be the legacy default stream, which
+            // cannot be captured); the instantiated graph is then launched on c->stream
+            cudaStream_t run_stream = c->stream;
+            c->stream = c->own_stream;
+            CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+            const int64_t before = c->launches;
+            enqueue_loop(it0, it1, fit);
+            c->graph_launches = c->launches - before;
+            c->launches = before;  // counted at replay time below
+            cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+            c->stream = run_stream;
+            if (ce == cudaSuccess && enqueue_status == ICP4R_OK) ce = cudaGraphInstantiate(&exec, graph, 0);
+            if (graph) cudaGraphDestroy(graph);
+            if (ce != cudaSuccess || enqueue_status != ICP4R_OK) {
+                cudaGetLastError();
+                exec = nullptr;
+                enqueue_status = ICP4R_OK;
+                if (sharded) c->no_graph_sharded = true;  // this NCCL build can not be captured: launch directly from now on
+                else return fail(c, ICP4R_ERR_CUDA, "graph capture of the registration loop failed: %s", cudaGetErrorString(ce));
+            } else {
+                c->graphs[key] = exec;
+                c->graph_launch_counts[key] = c->graph_launches;
+            }
+        }
+        if (exec) {
+            CK(cudaGraphLaunch(exec, c->stream));
+            c->launches += c->graph_launch_counts[key];
+        } else {
+            enqueue_loop(it0, it1, fit);
+            if (enqueue_status != ICP4R_OK) return enqueue_status;
+        }
+        return ICP4R_OK;
+    };
+    // With early exit the iterations after convergence are no-op launches (~2 us each): a 64-iteration budget that
+    // converges after 8 would spend more time skipping than iterating. Run such loops in chunks and look at the
+    // device's `done` flag in between (one 4-byte copy + sync per chunk).
+    constexpr int CHUNK = 8;
+    const bool chunked = o->early_exit && iters > CHUNK + CHUNK / 2 && !sharded && !prof;
+    if (!chunked) {
+        CKS(run_range(0, iters, true));
     } else {
-        enqueue_loop();
-        if (enqueue_status != ICP4R_OK) return enqueue_status;
+        for (int it0 = 0; it0 < iters; it0 += CHUNK) {
+            CKS(run_range(it0, std::min(it0 + CHUNK, iters), false));
+            CK(cudaMemcpyAsync(&hs->done_flag, reinterpret_cast<const char*>(d_st) + offsetof(RegState, done), sizeof(int),
+                               cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            if (hs->done_flag) break;
+        }
+        CKS(run_range(0, 0, true));
     }
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(&hs->out, d_out, sizeof(ResultBlock), cudaMemcpyDeviceToHost, c->stream));
@@ -969,7 +997,7 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
         cudaMemset(d_part + 160 * ICP4R_ACC_LEN, 0, dbg.size() * 8);
     }
 #endif
-    if (c->profiling && !sharded) {
+    if (prof) {
         for (int i = 0; i < iters + 1; ++i) {
             float ms = 0.f;
             CK(cudaEventElapsedTime(&ms, c->prof_events[i], c->prof_events[i + 1]));
@@ -1007,6 +1035,7 @@ int register_scans_against_map(Ctx* c, Map& mp, const float4* d_src, const int32
     GridDesc g = mp.grid;  // geometry only (see register_against_map)
     g.sorted = nullptr;
     g.cell_start = nullptr;
+    g.coarse = nullptr;
     g.m = 0;
     const int iters = o->max_iterations;
     for (int s0 = 0; s0 < nscan; s0 += CH) {
@@ -1044,6 +1073,7 @@ int register_scans_against_map(Ctx* c, Map& mp, const float4* d_src, const int32
             P.plane_thresh = o->plane_thresh;
             P.map_sorted = mp.grid.sorted;
             P.map_cell_start = mp.grid.cell_start;
+            P.map_coarse = mp.grid.coarse;
             P.map_pts = mp.pts.as<float4>();
             P.map_m = mp.grid.m;
             P.shard_axis = -1;

@@ -68,3 +68,20 @@ def test_launch_counter_and_determinism(pkg):
     assert np.array_equal(T1, T2) and r1.fitness == r2.fitness
     assert n1 - n0 == 1 + 7 + 1 and h.launch_count() - n1 == 9    # state init + 7 iterations + fitness pass
     h.close()
+
+
+def test_profiling_mode_with_gicp_does_not_crash(handle, pkg):
+    """per-launch profiling is only produced for the plain iteration loop; GICP must simply return an empty profile"""
+    import numpy as np
+    scan, mp, _ = pkg.synth.scan_to_map(5, 800, 20000, extent=40.0, scan_radius=30.0)
+    handle.map_build(mp)
+    handle.set_profiling(True)
+    try:
+        o = pkg.default_opts(residual=pkg.GICP, k=5, max_iterations=5, max_corr_dist=2.0)
+        T, res, _ = handle.register_map(scan, o)
+        assert np.isfinite(T).all() and len(handle.last_profile()) == 0
+        o = pkg.default_opts(residual=pkg.P2P_GN, max_iterations=5, max_corr_dist=2.0)
+        handle.register_map(scan, o)
+        assert len(handle.last_profile()) == 6
+    finally:
+        handle.set_profiling(False)
