@@ -21,7 +21,9 @@ __device__ __forceinline__ void smallest_eigvec3(const double C[9], double n[3])
     for (int i = 0; i < 9; ++i) A[i] = C[i];
     for (int sweep = 0; sweep < 50; ++sweep) {
         const double off = fabs(A[1]) + fabs(A[2]) + fabs(A[5]);
-        if (off < 1e-300) break;
+        // converged: rotations by angles below 1e-20 change nothing in double precision (was: 50 sweeps, ~40 of them no-ops
+        // that still cost their divisions and square roots)
+        if (off <= 1e-20 * (fabs(A[0]) + fabs(A[4]) + fabs(A[8])) || off < 1e-300) break;
 #pragma unroll
         for (int pq = 0; pq < 3; ++pq) {
             const int p = pq == 2 ? 1 : 0, q = pq == 0 ? 1 : 2;

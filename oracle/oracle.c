@@ -888,7 +888,7 @@ static void smallest_eigvec3(const double C[9], double n[3]) {
     memcpy(A, C, sizeof(A));
     for (int sweep = 0; sweep < 50; ++sweep) {
         double off = fabs(A[1]) + fabs(A[2]) + fabs(A[5]);
-        if (off < 1e-300) break;
+        if (off <= 1e-20 * (fabs(A[0]) + fabs(A[4]) + fabs(A[8])) || off < 1e-300) break;
         for (int p = 0; p < 2; ++p)
             for (int q = p + 1; q < 3; ++q) {
                 const double apq = A[3 * p + q];
