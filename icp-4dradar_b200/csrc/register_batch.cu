@@ -15,6 +15,7 @@
 
 #include "ctx.h"
 #include "device_math.cuh"
+#include "solve_warp.cuh"
 
 namespace icp4r {
 
@@ -391,10 +392,60 @@ __global__ void __launch_bounds__(RB_THREADS, 2) reg_batch_kernel(const __grid_c
                 }
             }
             block_reduce<NV>(acc, s_red, s_tot, tid);
-            if (tid == 0) {
-                double Tc[16], D[16];
-                for (int i = 0; i < 16; ++i) Tc[i] = s_T[i];
+            if (KIND == ICP4R_P2P_SVD && w == 0) {
+                // Kabsch step by one WARP (one matrix row per lane, solve_warp.cuh) instead of one thread: the other
+                // seven warps wait at the barrier below for this, every iteration
                 const bool last = (it == P.max_iterations - 1);
+                const double cnt = s_tot[0];
+                double* aux = s_red;       // [9] cross-covariance
+                double* Ds = s_red + 16;   // [12] increment, 3x4 row-major
+                if (cnt < 3.0) {
+                    if (lane == 0) {
+                        s_flags[3] = (int)cnt;
+                        s_flags[0] = 1;
+                        s_flags[1] = 0;
+                        s_flags[2] = it;
+                    }
+                } else {
+                    const double pm0 = s_tot[1] / cnt, pm1 = s_tot[2] / cnt, pm2 = s_tot[3] / cnt;
+                    if (lane < 9) aux[lane] = s_tot[7 + lane] / cnt - (s_tot[1 + lane / 3] / cnt) * (s_tot[4 + lane % 3] / cnt);
+                    __syncwarp();
+                    double R0, R1, R2;
+                    warp_kabsch(aux, lane, R0, R1, R2);
+                    if (lane < 3) {
+                        Ds[4 * lane + 0] = R0;
+                        Ds[4 * lane + 1] = R1;
+                        Ds[4 * lane + 2] = R2;
+                        Ds[4 * lane + 3] = s_tot[4 + lane] / cnt - ((R0 * pm0 + R1 * pm1) + R2 * pm2);
+                    }
+                    __syncwarp();
+                    const double tn = warp_compose_entry(Ds, s_T, lane);
+                    __syncwarp();
+                    if (lane < 12) s_T[lane] = tn;
+                    if (lane == 0) {
+                        s_flags[3] = (int)cnt;
+                        const double mse = s_tot[16] / cnt;
+                        s_misc[1] = mse;
+                        if (P.early_exit) {
+                            if (fabs(mse - s_misc[0]) < P.mse_abs_eps) {
+                                s_flags[0] = 1;
+                                s_flags[1] = 1;
+                                s_flags[2] = it + 1;
+                            }
+                            s_misc[0] = mse;
+                        }
+                        if (!s_flags[0] && last) {
+                            s_flags[0] = 1;
+                            s_flags[1] = 1;
+                            s_flags[2] = P.max_iterations;
+                        }
+                    }
+                }
+            }
+            if (KIND != ICP4R_P2P_SVD && tid == 0) {
+                double Tc[16], D[16];
+                const bool last = (it == P.max_iterations - 1);
+                for (int i = 0; i < 16; ++i) Tc[i] = s_T[i];
                 if (KIND == ICP4R_P2P_SVD) {
                     const double cnt = s_tot[0];
                     s_flags[3] = (int)cnt;
