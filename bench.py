@@ -307,8 +307,8 @@ def main():
         queries_per_unit = ITERS * int(np.mean([len(s) for s in seq]))
         step_dev = lambda i: pkg.pipeline.run_odometry(h, d_seq, o)
         step_e2e = lambda i: pkg.pipeline.run_odometry(h, h_seq, o)
-        h2d, d2h = int(sum(len(s) for s in seq)) * 16 * 2, args.frames * (16 * 8 + 32)
-        cfg = {"workload": f"C3 odometry sequence: {args.frames} frames (~3000 static pts each), register vs growing map (P2PLANE k=5, 20 iters, gate 2.0 m) + transform + Add_Points(false) per frame",
+        h2d, d2h = int(sum(len(s) for s in seq)) * 16, args.frames * (16 * 8 + 32)  # one icp4r_odometry_step per frame: the scan crosses once
+        cfg = {"workload": f"C3 odometry sequence: {args.frames} frames (~3000 static pts each), register vs growing map (P2PLANE k=5, 20 iters, gate 2.0 m) + transform + Add_Points(false) per frame (one icp4r_odometry_step call)",
                "frames": args.frames, "k": K_NN, "iterations": ITERS, "max_corr_dist": GATE,
                "final_map_points": int(sum(len(s) for s in seq)), "l2": "flushed before every timed step; the map outgrows L2 during the sequence"}
     elif args.workload == "c5":

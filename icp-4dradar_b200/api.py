@@ -22,7 +22,7 @@ EXPORTS = [
     "icp4r_synchronize", "icp4r_launch_count", "icp4r_set_profiling", "icp4r_last_profile", "icp4r_map_build", "icp4r_map_set_downsample", "icp4r_map_add_points",
     "icp4r_map_size", "icp4r_map_range", "icp4r_map_knn", "icp4r_map_knn_brute", "icp4r_map_sector", "icp4r_map_points",
     "icp4r_register", "icp4r_register_map", "icp4r_register_map_batch", "icp4r_register_batch", "icp4r_shard_unique_id", "icp4r_shard_init", "icp4r_shard_ipc_export", "icp4r_shard_ipc_import",
-    "icp4r_register_sharded", "icp4r_transform_points", "icp4r_voxel_grid", "icp4r_doppler_filter",
+    "icp4r_register_sharded", "icp4r_transform_points", "icp4r_voxel_grid", "icp4r_odometry_step", "icp4r_doppler_filter",
 ]
 
 
@@ -382,6 +382,16 @@ class Icp4r:
         return mask, r
 
     # ---- helpers
+    def odometry_step(self, scan, opts: Opts, T_prior):
+        """register against the map from T_prior, then insert the scan at the estimated pose; returns (T, result)"""
+        scan = _f4(scan)
+        p, mem = _ptr(scan)
+        T = np.ascontiguousarray(T_prior, np.float64).reshape(16).copy()
+        res = Result()
+        self._ck(self.lib.icp4r_odometry_step(self.h, p, C.c_int32(scan.shape[0]), C.c_int(mem), C.byref(opts), C.c_int(0),
+                                              C.c_void_p(T.ctypes.data), C.byref(res)))
+        return T.reshape(4, 4), res
+
     def voxel_grid(self, pts, leaf: float):
         """pcl::VoxelGrid centroid filter. pts None: the handle's map (returns numpy); numpy -> numpy; torch CUDA -> torch."""
         cnt = C.c_int32(0)

@@ -58,6 +58,7 @@ void shard_destroy(Ctx* c);
 int shard_ipc_export(Ctx* c, unsigned char out[64]);
 int shard_ipc_import(Ctx* c, const unsigned char* handles, int rank, int world);
 void shard_ipc_close(Ctx* c);
+int transform_points(Ctx* c, const double* T_host, const float4* d_in, int n, float4* d_out);
 
 static void free_map(Map& m) {
     release(m.pts);
@@ -465,6 +466,38 @@ int icp4r_register_map(icp4r_handle h, const float* src, int32_t n, int mem, con
     CKS(dump_prepare(c, dump, mem, n, opts, ds));
     CKS(register_against_map(c, c->map, static_cast<const float4*>(dsrc), n, opts, -1, 0.f, 0.f, T_out, res, dump ? &ds.dev : nullptr));
     return dump_finish(c, ds);
+}
+
+// One frame of scan-to-map odometry in one call: register against the map, move the scan with the estimated pose,
+// append it. The scan crosses the bus once and the transformed points never leave the device.
+int icp4r_odometry_step(icp4r_handle h, const float* scan, int32_t n, int mem, const icp4r_opts* opts, int downsample_on, double T_io[16],
+                        icp4r_result* res) {
+    HCHECK(h);
+    if (!opts || !T_io || n < 0 || (n > 0 && !scan) || bad_mem(mem)) return fail(c, ICP4R_ERR_INVALID, "icp4r_odometry_step: bad arguments");
+    if (downsample_on) return fail(c, ICP4R_ERR_UNSUPPORTED, "icp4r_odometry_step: use icp4r_map_add_points for down-sampled insertion");
+    Map& mp = c->map;
+    const void* dsrc;
+    CKS(stage_in(c, c->d_src, scan, (size_t)n * sizeof(float4), mem, &dsrc));
+    icp4r_result r;
+    std::memset(&r, 0, sizeof(r));
+    if (mp.built && mp.m > 0) {
+        icp4r_opts o = *opts;
+        std::memcpy(o.T0, T_io, sizeof(o.T0));
+        CKS(register_against_map(c, mp, static_cast<const float4*>(dsrc), n, &o, -1, 0.f, 0.f, T_io, &r, nullptr));
+    } else {
+        r.converged = 1;  // first frame: nothing to register against, the prior pose stands
+    }
+    if (res) *res = r;
+    if (n == 0) return ICP4R_OK;
+    // p_w = R p + t straight into the map's point array (pointAssociateToMap + Add_Points(.., false))
+    CKS(map_reserve(c, mp, mp.m + n));
+    CKS(transform_points(c, T_io, static_cast<const float4*>(dsrc), n, mp.pts.as<float4>() + mp.m));
+    CK(cudaMemsetAsync(mp.valid.as<uint8_t>() + mp.m, 1, (size_t)n, c->stream));
+    bool merged = false;
+    CKS(map_append_incremental(c, mp, n, &merged));
+    mp.m += n;
+    if (!merged) CKS(map_rebuild_grid(c, mp));
+    return ICP4R_OK;
 }
 
 int icp4r_register_map_batch(icp4r_handle h, const float* src, const int32_t* off, int32_t n_scans, int mem, const icp4r_opts* opts,

@@ -33,10 +33,18 @@ def synth_sequence(seed: int, frames: int, pts_per_scan: int = 3000, raw_per_sca
     return scans, poses
 
 
-def run_odometry(h: api.Icp4r, scans, opts: api.Opts, T_first=None):
-    """Returns the list of estimated poses T_w_s (float64 4x4)."""
+def run_odometry(h: api.Icp4r, scans, opts: api.Opts, T_first=None, fused: bool = True):
+    """Returns the list of estimated poses T_w_s (float64 4x4). fused: one icp4r_odometry_step call per frame
+    (register + transform + Add_Points on the device); otherwise the three separate calls."""
     T = np.eye(4) if T_first is None else np.asarray(T_first, np.float64)
     poses = [T.copy()]
+    if fused:
+        h.map_build(np.zeros((0, 4), np.float32))
+        h.odometry_step(scans[0], opts, T)
+        for scan in scans[1:]:
+            T, _res = h.odometry_step(scan, opts, T)
+            poses.append(T.copy())
+        return poses
     h.map_build(h.transform_points(T, scans[0]))
     for scan in scans[1:]:
         for i in range(16):

@@ -205,6 +205,14 @@ int icp4r_doppler_filter(icp4r_handle h, const float* xyziv, int32_t n, int mem,
 int icp4r_transform_points(icp4r_handle h, const double T[16], const float* xyzw, int32_t n, int mem,
                            float* xyzw_out);
 
+/* One frame of scan-to-map odometry (the loop body of radar_odometry.cpp:380-421 with registration before insertion):
+ * register the scan against the handle's map starting from T_io, write the estimated pose back to T_io, transform the
+ * scan with it (pointAssociateToMap) and append it to the map (Add_Points(.., false)) — one host-to-device copy of
+ * the scan, nothing else crosses the bus. With an empty map the scan is inserted at T_io (first frame).
+ * downsample_on must be 0 (use icp4r_map_add_points for down-sampled insertion). */
+int icp4r_odometry_step(icp4r_handle h, const float* scan_xyzw, int32_t n, int mem, const icp4r_opts* opts,
+                        int downsample_on, double T_io[16], icp4r_result* res);
+
 /* Centroid-per-leaf down-sampling: pcl::VoxelGrid<PointXYZI>::filter with setLeafSize(leaf, leaf, leaf) as the
  * scan-to-map node runs it over the accumulated map every frame (radar_odometry.cpp:426-429). One output point per
  * occupied leaf (float mean of x, y, z, intensity), ascending leaf index (x fastest). Non-finite points are

@@ -44,3 +44,21 @@ def test_odometry_sequence_matches_oracle(pkg, O, handle):
     # and the loop really tracks the trajectory (sanity of the synthetic sequence, not a parity bar)
     drift = np.linalg.norm(got[-1][:3, 3] - (np.linalg.inv(gt[0]) @ gt[-1])[:3, 3])
     assert drift < 3.0, drift  # ~5.6 m travelled; the ground plane constrains x, y only through sparse walls
+
+
+def test_fused_odometry_step_equals_separate_calls(pkg, handle):
+    """icp4r_odometry_step (register + transform + Add_Points in one call, device-side) gives the poses and the map of
+    the three separate C-ABI calls, bit for bit; host and device inputs alike"""
+    import torch
+    scans, _ = pkg.pipeline.synth_sequence(77, 10, pts_per_scan=800, raw_per_scan=1000, extent=100.0, scan_radius=40.0)
+    o = pkg.default_opts(residual=pkg.P2PLANE_KNN, k=5, max_iterations=8, max_corr_dist=2.0)
+    sep = pkg.pipeline.run_odometry(handle, scans, o, fused=False)
+    pts_sep, valid_sep = handle.map_points()
+    fused = pkg.pipeline.run_odometry(handle, scans, o, fused=True)
+    pts_fused, valid_fused = handle.map_points()
+    for a, b in zip(sep, fused):
+        assert np.array_equal(a, b)
+    assert np.array_equal(pts_sep.view(np.int32), pts_fused.view(np.int32)) and np.array_equal(valid_sep, valid_fused)
+    dev = pkg.pipeline.run_odometry(handle, [torch.from_numpy(s).cuda() for s in scans], o, fused=True)
+    for a, b in zip(sep, dev):
+        assert np.array_equal(a, b)
