@@ -404,15 +404,13 @@ __global__ void __launch_bounds__(1024) small_sort_kernel(const uint32_t* __rest
     __syncthreads();
     for (int k = 2; k <= np2; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < np2; i += 1024) {
-                const int l = i ^ j;
-                if (l > i) {
-                    const unsigned long long a = s[i], b = s[l];
-                    const bool up = (i & k) == 0;
-                    if ((a > b) == up) {
-                        s[i] = b;
-                        s[l] = a;
-                    }
+            for (int t = threadIdx.x; t < (np2 >> 1); t += 1024) {  // one compare-exchange per thread and trip
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
+                const unsigned long long a = s[i], b = s[l];
+                const bool up = (i & k) == 0;
+                if ((a > b) == up) {
+                    s[i] = b;
+                    s[l] = a;
                 }
             }
             __syncthreads();
