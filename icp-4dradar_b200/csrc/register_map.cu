@@ -324,10 +324,23 @@ __global__ void __launch_bounds__(RM_THREADS, 1)
                 hint = P.gate_f;
             }
         }
+#ifdef ICP4R_KNN_TIMING
+        const long long tq0 = clock64();
+#endif
         uint64_t mine = warp_grid_knn<KK, false>(g, P.map_sorted, P.map_cell_start, nullptr, P.map_m, segs[w], qx, qy, qz, P.gate_f, P.gate_r, lane, hint);
+#ifdef ICP4R_KNN_TIMING
+        const int tq_cycles = (int)(clock64() - tq0);
+#endif
         const bool have = (lane < kq) && (mine != KEY_EMPTY);
         if (!FIT && nbp != nullptr && lane < kq) nbp[lane] = have ? key_idx(mine) : -1;
         if (!FIT && P.dump_idx && lane < kq) P.dump_idx[((size_t)iter * n + i) * kq + lane] = have ? key_idx(mine) : -1;
+#ifdef ICP4R_KNN_TIMING
+        // dev probe: the last two slots of the index dump carry the search's cycle count and the kind of bound it had
+        if (!FIT && P.dump_idx && kq >= 3 && lane == 0) {
+            P.dump_idx[((size_t)iter * n + i) * kq + kq - 1] = tq_cycles;
+            P.dump_idx[((size_t)iter * n + i) * kq + kq - 2] = hint < 0.0f ? 0 : (hint == P.gate_f ? 2 : 1);
+        }
+#endif
         const int found = __popc(__ballot_sync(FULL, have));
         float4 nb = make_float4(0.f, 0.f, 0.f, 0.f);
         if (have) nb = __ldg(pts + key_idx(mine));  // lane j holds neighbour j
