@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(256) normals_kernel(GridDesc g, const float4* 
         const int cnt = min(chunk, g.m - base);
         for (int j = 0; j < cnt; ++j) {
             const float4 p = __ldg(g.sorted + base + j);
-            const uint64_t mine = warp_grid_knn<K>(g, segs[w], p.x, p.y, p.z, INFINITY, INFINITY, lane);
+            const uint64_t mine = warp_grid_knn<K>(g, seg_addr(&segs[w]), p.x, p.y, p.z, INFINITY, INFINITY, lane);
             const bool have = (lane < k) && (mine != KEY_EMPTY);
             const int found = __popc(__ballot_sync(FULL, have));
             if (have) {

@@ -591,7 +591,7 @@ __global__ void __launch_bounds__(256, (K <= 5 ? 4 : 2)) grid_knn_kernel(GridDes
         const long long t_begin = clock64();
 #endif
         const float4 p = __ldg(q + i);
-        const uint64_t mine = warp_grid_knn<K>(g, segs[threadIdx.x >> 5], p.x, p.y, p.z, gate_f, gate_r, lane);
+        const uint64_t mine = warp_grid_knn<K>(g, seg_addr(&segs[threadIdx.x >> 5]), p.x, p.y, p.z, gate_f, gate_r, lane);
         const bool have = (lane < k) && (mine != KEY_EMPTY);
         if (lane < k) {
             idx[(size_t)i * k + lane] = have ? key_idx(mine) : -1;

@@ -29,6 +29,23 @@ struct WarpSegs {  // per-warp shared-memory scratch
     uint32_t start[KNN_SEGS];
     uint32_t pre[KNN_SEGS + 1];
 };
+// The scratch is addressed through its 32-bit shared-space address with explicit ld.shared / st.shared: handing a C++
+// reference to shared memory through the (inlined) search functions made the compiler rebuild the shared-window base
+// (S2R SR_CgaCtaId + LEA) and the warp index at every access — 7 % of the executed instructions of the fused kernel.
+using SegAddr = uint32_t;
+__device__ __forceinline__ SegAddr seg_addr(WarpSegs* sg) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(sg);
+    uint32_t pinned;  // an opaque move: the compiler keeps the value in a register instead of re-deriving it at every use
+    asm volatile("mov.u32 %0, %1;" : "=r"(pinned) : "r"(a));
+    return pinned;
+}
+__device__ __forceinline__ uint32_t lds_u32(SegAddr a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_u32(SegAddr a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+constexpr uint32_t SEG_PRE = KNN_SEGS * 4;  // byte offset of pre[] inside WarpSegs
 
 __device__ __forceinline__ int cell_of(float v, float o, float inv, int dim) {
     const int c = __float2int_rd(__fmul_rn(__fsub_rn(v, o), inv));  // floor; NaN -> 0, +-inf saturate
@@ -46,7 +63,7 @@ __device__ __forceinline__ void consider(float qx, float qy, float qz, const flo
 
 // scan the ranges described by this lane's (s0,e0) and (s1,e1) together with the other 31 lanes' ranges
 template <int K>
-__device__ __forceinline__ void scan_segments(const float4* __restrict__ sorted, WarpSegs& sg, uint32_t s0, uint32_t e0, uint32_t s1,
+__device__ __forceinline__ void scan_segments(const float4* __restrict__ sorted, SegAddr sg, uint32_t s0, uint32_t e0, uint32_t s1,
                                               uint32_t e1, int lane, float qx, float qy, float qz, float gate_f, uint64_t kth,
                                               TopK<K>& list) {
     const uint32_t l0 = e0 - s0, l1 = e1 - s1;
@@ -66,14 +83,14 @@ __device__ __forceinline__ void scan_segments(const float4* __restrict__ sorted,
     const int nseg = __popc(b0) + __popc(b1);
     __syncwarp();
     if (l0 > 0) {
-        sg.start[slot] = s0;
-        sg.pre[slot] = exc;
+        sts_u32(sg + 4u * slot, s0);
+        sts_u32(sg + SEG_PRE + 4u * slot, exc);
     }
     if (l1 > 0) {
-        sg.start[slot + (l0 > 0)] = s1;
-        sg.pre[slot + (l0 > 0)] = exc + l0;
+        sts_u32(sg + 4u * (slot + (l0 > 0)), s1);
+        sts_u32(sg + SEG_PRE + 4u * (slot + (l0 > 0)), exc + l0);
     }
-    if (lane == 0) sg.pre[nseg] = total;
+    if (lane == 0) sts_u32(sg + SEG_PRE + 4u * nseg, total);
     __syncwarp();
     int r = 0;
     for (uint32_t t0 = lane; t0 < total; t0 += 128) {
@@ -84,8 +101,8 @@ __device__ __forceinline__ void scan_segments(const float4* __restrict__ sorted,
             const uint32_t t = t0 + 32u * u;
             ok[u] = t < total;
             if (ok[u]) {
-                while (t >= sg.pre[r + 1]) ++r;  // pre[nseg] == total > t terminates the walk
-                c[u] = __ldg(sorted + (sg.start[r] + (t - sg.pre[r])));
+                while (t >= lds_u32(sg + SEG_PRE + 4u * (r + 1))) ++r;  // pre[nseg] == total > t terminates the walk
+                c[u] = __ldg(sorted + (lds_u32(sg + 4u * r) + (t - lds_u32(sg + SEG_PRE + 4u * r))));
             }
         }
 #pragma unroll
@@ -141,7 +158,7 @@ __device__ __forceinline__ float coarse_bound(const GridDesc& g, const uint32_t*
 // common path registers or instructions. `bound2` must bound the K-th distance (>= K valid points within it).
 template <int K>
 static __device__ __noinline__ uint64_t wide_ball_knn(const GridDesc& g, const float4* __restrict__ sorted, const uint32_t* __restrict__ cs,
-                                                      WarpSegs& sg, float qx, float qy, float qz, float gate_f, float br, float bound2,
+                                                      SegAddr sg, float qx, float qy, float qz, float gate_f, float br, float bound2,
                                                       float margin, int lane) {
     const int cx = cell_of(qx, g.ox, g.inv_cell, g.nx), cy = cell_of(qy, g.oy, g.inv_cell, g.ny), cz = cell_of(qz, g.oz, g.inv_cell, g.nz);
     const int lox = cell_of(qx - br, g.ox, g.inv_cell, g.nx), hix = cell_of(qx + br, g.ox, g.inv_cell, g.nx);
@@ -190,7 +207,7 @@ static __device__ __noinline__ uint64_t wide_ball_knn(const GridDesc& g, const f
 // shell-by-shell proof, one merge. The result is the same set, the hint only removes work.
 template <int K, bool WIDE = true>
 __device__ __forceinline__ uint64_t warp_grid_knn(const GridDesc& g, const float4* __restrict__ sorted, const uint32_t* __restrict__ cs,
-                                                  const uint32_t* __restrict__ coarse, int m_sorted, WarpSegs& sg, float qx, float qy,
+                                                  const uint32_t* __restrict__ coarse, int m_sorted, SegAddr sg, float qx, float qy,
                                                   float qz, float gate_f, float gate_r, int lane, float hint = -1.0f) {
     const float qmax = fmaxf(fabsf(qx), fmaxf(fabsf(qy), fabsf(qz)));
     const float margin = fmaxf(g.margin, 9.5367431640625e-7f * qmax);  // 2^-20 * magnitude
@@ -345,7 +362,7 @@ __device__ __forceinline__ uint64_t warp_grid_knn(const GridDesc& g, const float
 
 namespace icp4r {
 template <int K>
-__device__ __forceinline__ uint64_t warp_grid_knn(const GridDesc& g, WarpSegs& sg, float qx, float qy, float qz, float gate_f,
+__device__ __forceinline__ uint64_t warp_grid_knn(const GridDesc& g, SegAddr sg, float qx, float qy, float qz, float gate_f,
                                                   float gate_r, int lane) {
     return warp_grid_knn<K>(g, g.sorted, g.cell_start, g.coarse, g.m, sg, qx, qy, qz, gate_f, gate_r, lane);
 }

@@ -172,6 +172,7 @@ __global__ void __launch_bounds__(RM_THREADS, 1)
     __syncthreads();
 
     const float4* __restrict__ pts = P.map_pts;  // map points by insertion index
+    const SegAddr sgaddr = seg_addr(&segs[w]);
     // which two operands this lane multiplies (indices into scr[w][row][*])
     int ia = 8, ib = 8;  // scr[..][8] == 0
     if (RK == ICP4R_P2P_SVD) {  // scr = {1, p'x,p'y,p'z, qx,qy,qz, d2, 0}
@@ -327,7 +328,7 @@ __global__ void __launch_bounds__(RM_THREADS, 1)
 #ifdef ICP4R_KNN_TIMING
         const long long tq0 = clock64();
 #endif
-        uint64_t mine = warp_grid_knn<KK, false>(g, P.map_sorted, P.map_cell_start, nullptr, P.map_m, segs[w], qx, qy, qz, P.gate_f, P.gate_r, lane, hint);
+        uint64_t mine = warp_grid_knn<KK, false>(g, P.map_sorted, P.map_cell_start, nullptr, P.map_m, sgaddr, qx, qy, qz, P.gate_f, P.gate_r, lane, hint);
 #ifdef ICP4R_KNN_TIMING
         const int tq_cycles = (int)(clock64() - tq0);
 #endif

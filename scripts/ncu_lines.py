@@ -60,3 +60,10 @@ smp = sum(a[1] for a in agg.values()) or 1
 print(f"total warp-instructions {tot}, samples {smp}")
 for loc, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
     print(f"{a[0]:9d} {100*a[0]/tot:5.1f}%  samples {a[1]:5d} {100*a[1]/smp:5.1f}%  sass {a[2]:4d}  {loc[0]}:{loc[1]}")
+# optional 5th argument file:line — list that line's SASS with execution counts
+if len(sys.argv) > 5:
+    f, ln = sys.argv[5].rsplit(":", 1)
+    print(f"--- SASS attributed to {f}:{ln}")
+    for r, (loc, txt) in zip(uniq[:n], ins[:n]):
+        if loc == (f, int(ln)):
+            print(f"{I(r, 'Instructions Executed'):9d}  smp {I(r, '# Samples'):4d}  {txt}")
