@@ -22,6 +22,7 @@ struct BoxPointType {  // same layout as ikd_Tree.h:32-35
     float vertex_min[3];
     float vertex_max[3];
 };
+static_assert(sizeof(BoxPointType) == 6 * sizeof(float), "a vector<BoxPointType> is passed to the C ABI as n x 6 floats");
 
 namespace icp4r {
 
@@ -114,6 +115,43 @@ class KD_TREE {
         int32_t n = 0;
         check(h_, icp4r_map_sector(h_, c, radius, heading, ICP4R_HOST, idx.data(), (int32_t)idx.size(), &n), "Sector_Search");
         for (int i = 0; i < n && i < (int)idx.size(); ++i) Storage.push_back(mirror_[idx[i]]);
+    }
+
+    // ikd_Tree.h:243-249 — the searches return point copies like the reference, in unspecified order
+    void Box_Search(const BoxPointType& Box_of_Point, PointVector& Storage) {
+        Storage.clear();
+        std::vector<int32_t> idx(mirror_.size() ? mirror_.size() : 1);
+        int32_t n = 0;
+        check(h_, icp4r_map_box_search(h_, Box_of_Point.vertex_min, Box_of_Point.vertex_max, ICP4R_HOST, idx.data(), (int32_t)idx.size(), &n),
+              "Box_Search");
+        for (int i = 0; i < n && i < (int)idx.size(); ++i) Storage.push_back(mirror_[idx[i]]);
+    }
+
+    void Radius_Search(PointType point, const float radius, PointVector& Storage) {
+        Storage.clear();
+        const float c[3] = {point.x, point.y, point.z};
+        std::vector<int32_t> idx(mirror_.size() ? mirror_.size() : 1);
+        int32_t n = 0;
+        check(h_, icp4r_map_radius_search(h_, c, radius, ICP4R_HOST, idx.data(), (int32_t)idx.size(), &n), "Radius_Search");
+        for (int i = 0; i < n && i < (int)idx.size(); ++i) Storage.push_back(mirror_[idx[i]]);
+    }
+
+    int Delete_Point_Boxes(std::vector<BoxPointType>& BoxPoints) {
+        int32_t n = 0;
+        check(h_, icp4r_map_delete_boxes(h_, BoxPoints.empty() ? nullptr : BoxPoints[0].vertex_min, (int32_t)BoxPoints.size(), &n),
+              "Delete_Point_Boxes");
+        return n;
+    }
+
+    void Add_Point_Boxes(std::vector<BoxPointType>& BoxPoints) {
+        check(h_, icp4r_map_add_boxes(h_, BoxPoints.empty() ? nullptr : BoxPoints[0].vertex_min, (int32_t)BoxPoints.size(), nullptr),
+              "Add_Point_Boxes");
+    }
+
+    void Delete_Points(PointVector& PointToDel) {
+        if (PointToDel.empty()) return;
+        const std::vector<float> v = pack_xyzw(PointToDel.begin(), PointToDel.end());
+        check(h_, icp4r_map_delete_points(h_, v.data(), (int32_t)PointToDel.size(), ICP4R_HOST, nullptr), "Delete_Points");
     }
 
     BoxPointType tree_range() {

@@ -111,6 +111,36 @@ int main() {
     icp2.setInputTarget(empty);
     icp2.align(*Final);
     REQUIRE(!icp2.hasConverged());
+    // ---- the rest of the KD_TREE surface (ikd_Tree.h:243-249)
+    {
+        BoxPointType box;
+        for (int a = 0; a < 3; ++a) {
+            box.vertex_min[a] = -5.f;
+            box.vertex_max[a] = 5.f;
+        }
+        icp4r::KD_TREE<PointType>::PointVector in_box, in_ball;
+        ikd_Tree.Box_Search(box, in_box);
+        size_t want = 0;
+        for (const auto& p : all) want += (p.x >= -5.f && p.x < 5.f && p.y >= -5.f && p.y < 5.f && p.z >= -5.f && p.z < 5.f);
+        REQUIRE(in_box.size() == want && want > 0);
+        PointType c0 = rnd(0.f);
+        ikd_Tree.Radius_Search(c0, 4.f, in_ball);
+        want = 0;
+        for (const auto& p : all) want += d2f(c0, p) <= 16.f;
+        REQUIRE(in_ball.size() == want);
+        std::vector<BoxPointType> boxes(1, box);
+        const int before = ikd_Tree.validnum();
+        const int deleted = ikd_Tree.Delete_Point_Boxes(boxes);
+        REQUIRE(deleted == (int)in_box.size() && ikd_Tree.validnum() == before - deleted && ikd_Tree.size() == before);
+        ikd_Tree.Box_Search(box, in_ball);
+        REQUIRE(in_ball.empty());
+        ikd_Tree.Add_Point_Boxes(boxes);
+        REQUIRE(ikd_Tree.validnum() == before);
+        icp4r::KD_TREE<PointType>::PointVector victims(all.begin(), all.begin() + 7);
+        ikd_Tree.Delete_Points(victims);
+        REQUIRE(ikd_Tree.validnum() == before - 7);
+        std::printf("box/radius/delete shapes: %zu in box, %d deleted and restored, 7 points deleted\n", in_box.size(), deleted);
+    }
     // ---- the pcl::VoxelGrid shape, as radar_odometry.cpp:426-429 uses it
     {
         icp4r::VoxelGrid<PointType> sor;

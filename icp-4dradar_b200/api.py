@@ -22,7 +22,8 @@ EXPORTS = [
     "icp4r_synchronize", "icp4r_launch_count", "icp4r_set_profiling", "icp4r_last_profile", "icp4r_map_build", "icp4r_map_set_downsample", "icp4r_map_add_points",
     "icp4r_map_size", "icp4r_map_range", "icp4r_map_knn", "icp4r_map_knn_brute", "icp4r_map_sector", "icp4r_map_points",
     "icp4r_register", "icp4r_register_map", "icp4r_register_map_batch", "icp4r_register_batch", "icp4r_shard_unique_id", "icp4r_shard_init", "icp4r_shard_ipc_export", "icp4r_shard_ipc_import",
-    "icp4r_register_sharded", "icp4r_transform_points", "icp4r_voxel_grid", "icp4r_odometry_step", "icp4r_doppler_filter",
+    "icp4r_register_sharded", "icp4r_transform_points", "icp4r_voxel_grid", "icp4r_odometry_step", "icp4r_map_box_search",
+    "icp4r_map_radius_search", "icp4r_map_delete_boxes", "icp4r_map_add_boxes", "icp4r_map_delete_points", "icp4r_doppler_filter",
 ]
 
 
@@ -253,6 +254,43 @@ class Icp4r:
         self._ck(self.lib.icp4r_map_sector(self.h, C.c_void_p(c.ctypes.data), C.c_float(radius), C.c_float(heading_deg),
                                            C.c_int(HOST), C.c_void_p(out.ctypes.data), C.c_int32(out.shape[0]), C.byref(cnt)))
         return out[:min(cnt.value, out.shape[0])].copy()
+
+    def map_box_search(self, bmin, bmax):
+        n, _ = self.map_size()
+        lo, hi = np.ascontiguousarray(bmin, np.float32), np.ascontiguousarray(bmax, np.float32)
+        out = np.empty(max(n, 1), np.int32)
+        cnt = C.c_int32(0)
+        self._ck(self.lib.icp4r_map_box_search(self.h, C.c_void_p(lo.ctypes.data), C.c_void_p(hi.ctypes.data), C.c_int(HOST),
+                                               C.c_void_p(out.ctypes.data), C.c_int32(out.shape[0]), C.byref(cnt)))
+        return out[:min(cnt.value, out.shape[0])].copy()
+
+    def map_radius_search(self, centre, radius):
+        n, _ = self.map_size()
+        c = np.ascontiguousarray(centre, np.float32)
+        out = np.empty(max(n, 1), np.int32)
+        cnt = C.c_int32(0)
+        self._ck(self.lib.icp4r_map_radius_search(self.h, C.c_void_p(c.ctypes.data), C.c_float(radius), C.c_int(HOST),
+                                                  C.c_void_p(out.ctypes.data), C.c_int32(out.shape[0]), C.byref(cnt)))
+        return out[:min(cnt.value, out.shape[0])].copy()
+
+    def map_delete_boxes(self, boxes) -> int:
+        b = np.ascontiguousarray(boxes, np.float32).reshape(-1, 6)
+        cnt = C.c_int32(0)
+        self._ck(self.lib.icp4r_map_delete_boxes(self.h, C.c_void_p(b.ctypes.data), C.c_int32(b.shape[0]), C.byref(cnt)))
+        return cnt.value
+
+    def map_add_boxes(self, boxes) -> int:
+        b = np.ascontiguousarray(boxes, np.float32).reshape(-1, 6)
+        cnt = C.c_int32(0)
+        self._ck(self.lib.icp4r_map_add_boxes(self.h, C.c_void_p(b.ctypes.data), C.c_int32(b.shape[0]), C.byref(cnt)))
+        return cnt.value
+
+    def map_delete_points(self, pts) -> int:
+        pts = _f4(pts)
+        p, mem = _ptr(pts)
+        cnt = C.c_int32(0)
+        self._ck(self.lib.icp4r_map_delete_points(self.h, p, C.c_int32(pts.shape[0]), C.c_int(mem), C.byref(cnt)))
+        return cnt.value
 
     # ---- registration
     def _dump_bufs(self, opts, n, dump, mem, device=None):

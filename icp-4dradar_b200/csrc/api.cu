@@ -63,6 +63,7 @@ int transform_points(Ctx* c, const double* T_host, const float4* d_in, int n, fl
 static void free_map(Map& m) {
     release(m.pts);
     release(m.valid);
+    release(m.userdel);
     release(m.sorted);
     release(m.cell_start);
     release(m.keys_a);
@@ -110,6 +111,7 @@ static int set_points(Ctx* c, Map& mp, const float* xyzw, int n, int mem, int of
         CK(cudaMemcpyAsync(mp.pts.as<float4>() + offset, xyzw, (size_t)n * sizeof(float4),
                            mem == ICP4R_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
         CK(cudaMemsetAsync(mp.valid.as<uint8_t>() + offset, 1, (size_t)n, c->stream));
+        CK(cudaMemsetAsync(mp.userdel.as<uint8_t>() + offset, 0, (size_t)n, c->stream));
     }
     return ICP4R_OK;
 }
@@ -392,6 +394,79 @@ int icp4r_map_sector(icp4r_handle h, const float centre_xyz[3], float radius, fl
     return ICP4R_OK;
 }
 
+static int region_search(Ctx* c, int kind, const float a[3], const float b[3], int mem, int32_t* idx_out, int32_t cap, int32_t* n_out) {
+    if (!c->map.built) return fail(c, ICP4R_ERR_STATE, "search before icp4r_map_build");
+    int32_t* d_out = idx_out;
+    if (mem == ICP4R_HOST) {
+        CKS(reserve(c, c->d_idx, (size_t)std::max(cap, 1) * 4));
+        d_out = c->d_idx.as<int32_t>();
+    }
+    int cnt = 0;
+    CKS(map_region_search(c, c->map, kind, a, b, d_out, cap, &cnt));
+    if (mem == ICP4R_HOST && cap > 0 && cnt > 0) {
+        CK(cudaMemcpyAsync(idx_out, d_out, (size_t)std::min(cnt, cap) * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    *n_out = cnt;
+    return ICP4R_OK;
+}
+
+int icp4r_map_box_search(icp4r_handle h, const float box_min[3], const float box_max[3], int mem, int32_t* idx_out, int32_t cap, int32_t* n_out) {
+    HCHECK(h);
+    if (!box_min || !box_max || !n_out || cap < 0 || (cap > 0 && !idx_out) || bad_mem(mem))
+        return fail(c, ICP4R_ERR_INVALID, "icp4r_map_box_search: bad arguments");
+    return region_search(c, 0, box_min, box_max, mem, idx_out, cap, n_out);
+}
+
+int icp4r_map_radius_search(icp4r_handle h, const float centre_xyz[3], float radius, int mem, int32_t* idx_out, int32_t cap, int32_t* n_out) {
+    HCHECK(h);
+    if (!centre_xyz || !n_out || cap < 0 || (cap > 0 && !idx_out) || bad_mem(mem))
+        return fail(c, ICP4R_ERR_INVALID, "icp4r_map_radius_search: bad arguments");
+    const float b[3] = {radius * radius, 0.f, 0.f};  // ikd_Tree.cpp:1070: calc_dist(...) <= radius * radius
+    return region_search(c, 1, centre_xyz, b, mem, idx_out, cap, n_out);
+}
+
+static int box_flags(Ctx* c, const float* boxes6, int32_t n_boxes, bool revive, int32_t* n_changed) {
+    if (n_changed) *n_changed = 0;
+    if (n_boxes < 0 || (n_boxes > 0 && !boxes6)) return fail(c, ICP4R_ERR_INVALID, "bad box list");
+    Map& mp = c->map;
+    if (!mp.built) return fail(c, ICP4R_ERR_STATE, "box operation before icp4r_map_build");
+    if (n_boxes == 0 || mp.m == 0) return ICP4R_OK;
+    const void* dboxes;
+    CKS(stage_in(c, c->d_q, boxes6, (size_t)n_boxes * 6 * sizeof(float), ICP4R_HOST, &dboxes));
+    int changed = 0;
+    CKS(map_box_flags(c, mp, static_cast<const float*>(dboxes), n_boxes, revive, &changed));
+    if (changed > 0) CKS(map_rebuild_grid(c, mp));
+    if (n_changed) *n_changed = changed;
+    return ICP4R_OK;
+}
+
+int icp4r_map_delete_boxes(icp4r_handle h, const float* boxes6, int32_t n_boxes, int32_t* n_deleted) {
+    HCHECK(h);
+    return box_flags(c, boxes6, n_boxes, false, n_deleted);
+}
+
+int icp4r_map_add_boxes(icp4r_handle h, const float* boxes6, int32_t n_boxes, int32_t* n_restored) {
+    HCHECK(h);
+    return box_flags(c, boxes6, n_boxes, true, n_restored);
+}
+
+int icp4r_map_delete_points(icp4r_handle h, const float* xyzw, int32_t n, int mem, int32_t* n_deleted) {
+    HCHECK(h);
+    if (n_deleted) *n_deleted = 0;
+    if (n < 0 || (n > 0 && !xyzw) || bad_mem(mem)) return fail(c, ICP4R_ERR_INVALID, "icp4r_map_delete_points: bad arguments");
+    Map& mp = c->map;
+    if (!mp.built) return fail(c, ICP4R_ERR_STATE, "icp4r_map_delete_points before icp4r_map_build");
+    if (n == 0) return ICP4R_OK;
+    const void* dreq;
+    CKS(stage_in(c, c->d_q, xyzw, (size_t)n * sizeof(float4), mem, &dreq));
+    int deleted = 0;
+    CKS(map_delete_points(c, mp, static_cast<const float4*>(dreq), n, &deleted));
+    if (deleted > 0) CKS(map_rebuild_grid(c, mp));
+    if (n_deleted) *n_deleted = deleted;
+    return ICP4R_OK;
+}
+
 int icp4r_map_points(icp4r_handle h, int mem, float* xyzw_out, uint8_t* valid_out, int32_t cap) {
     HCHECK(h);
     if (bad_mem(mem) || cap < 0) return fail(c, ICP4R_ERR_INVALID, "icp4r_map_points: bad arguments");
@@ -493,6 +568,7 @@ int icp4r_odometry_step(icp4r_handle h, const float* scan, int32_t n, int mem, c
     CKS(map_reserve(c, mp, mp.m + n));
     CKS(transform_points(c, T_io, static_cast<const float4*>(dsrc), n, mp.pts.as<float4>() + mp.m));
     CK(cudaMemsetAsync(mp.valid.as<uint8_t>() + mp.m, 1, (size_t)n, c->stream));
+    CK(cudaMemsetAsync(mp.userdel.as<uint8_t>() + mp.m, 0, (size_t)n, c->stream));
     bool merged = false;
     CKS(map_append_incremental(c, mp, n, &merged));
     mp.m += n;

@@ -58,6 +58,7 @@ struct GridDesc {
 struct Map {
     DevBuf pts;         // float4 [cap] insertion order (x, y, z, intensity)
     DevBuf valid;       // uint8  [cap]
+    DevBuf userdel;     // uint8  [cap]: removed by Delete_Points / Delete_Point_Boxes (Add_Point_Boxes can bring it back)
     DevBuf sorted;      // float4 [m_sorted]
     DevBuf cell_start;  // uint32 [ncells + 1]
     DevBuf coarse;      // uint32 [ceil(nx/8) * ceil(ny/8) * ceil(nz/8)]
@@ -226,6 +227,9 @@ void gate_params(double max_dist, float* gate_f, float* gate_r);
 // map_ops.cu
 int map_downsample_add(Ctx* c, Map& mp, int n, int* n_replaced_host, bool force_sequential);
 int voxel_grid(Ctx* c, const float4* d_pts, const uint8_t* d_valid, int n, float leaf, float4* d_out, int cap, int* n_out_host);
+int map_region_search(Ctx* c, const Map& mp, int kind, const float a[3], const float b[3], int32_t* d_out, int cap, int* n_out_host);
+int map_box_flags(Ctx* c, Map& mp, const float* d_boxes6, int nb, bool revive, int* n_changed_host);
+int map_delete_points(Ctx* c, Map& mp, const float4* d_req, int n, int* n_deleted_host);
 int map_sector(Ctx* c, const Map& mp, const float centre[3], float radius, float heading, int32_t* d_out, int cap, int* n_out_host);
 
 // register_map.cu

@@ -142,18 +142,23 @@ int map_reserve(Ctx* c, Map& mp, int cap) {
     size_t want = (size_t)cap;
     size_t have = mp.pts.cap / sizeof(float4);
     if (want < have * 2) want = have * 2;
-    DevBuf np, nv;
+    DevBuf np, nv, nu;
     CKS(reserve(c, np, want * sizeof(float4)));
     CKS(reserve(c, nv, want));
+    CKS(reserve(c, nu, want));
+    CK(cudaMemsetAsync(nu.p, 0, want, c->stream));
     if (mp.m > 0) {
         CK(cudaMemcpyAsync(np.p, mp.pts.p, (size_t)mp.m * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
         CK(cudaMemcpyAsync(nv.p, mp.valid.p, (size_t)mp.m, cudaMemcpyDeviceToDevice, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
+        if (mp.userdel.p) CK(cudaMemcpyAsync(nu.p, mp.userdel.p, (size_t)mp.m, cudaMemcpyDeviceToDevice, c->stream));
     }
+    CK(cudaStreamSynchronize(c->stream));
     release(mp.pts);
     release(mp.valid);
+    release(mp.userdel);
     mp.pts = np;
     mp.valid = nv;
+    mp.userdel = nu;
     return ICP4R_OK;
 }
 

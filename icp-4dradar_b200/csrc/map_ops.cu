@@ -311,6 +311,156 @@ __global__ void __launch_bounds__(256) sector_kernel(const float4* __restrict__ 
     }
 }
 
+// ---- Box_Search / Radius_Search: the same one-pass filter + warp-aggregated compaction over the sorted map -----------
+// (ikd_Tree.cpp:401-412,1024-1095; half-open box test `min <= p < max`, sphere test d2 <= radius * radius in float)
+struct RegionQuery {
+    int kind;  // 0 box, 1 sphere
+    float a[3], b[3];  // box min / max, or centre (a) and radius^2 (b[0])
+};
+__device__ __forceinline__ bool in_region(const RegionQuery& q, const float4& p) {
+    if (q.kind == 0) return q.a[0] <= p.x && q.b[0] > p.x && q.a[1] <= p.y && q.b[1] > p.y && q.a[2] <= p.z && q.b[2] > p.z;
+    return dist2_exact(p.x, p.y, p.z, q.a[0], q.a[1], q.a[2]) <= q.b[0];
+}
+__global__ void __launch_bounds__(256) region_kernel(const float4* __restrict__ sorted, int m, RegionQuery q, int32_t* __restrict__ out, int cap,
+                                                     int* __restrict__ count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool hit = false;
+    int id = -1;
+    if (i < m) {
+        const float4 p = sorted[i];
+        id = __float_as_int(p.w);
+        hit = in_region(q, p);
+    }
+    const unsigned b = __ballot_sync(FULL, hit);
+    if (b == 0) return;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == __ffs(b) - 1) base = atomicAdd(count, __popc(b));
+    base = __shfl_sync(FULL, base, __ffs(b) - 1);
+    if (hit) {
+        const int slot = base + __popc(b & ((1u << lane) - 1u));
+        if (slot < cap) out[slot] = id;
+    }
+}
+
+int map_region_search(Ctx* c, const Map& mp, int kind, const float a[3], const float b[3], int32_t* d_out, int cap, int* n_out_host) {
+    CKS(reserve(c, c->d_scratch, 64));
+    int* d_cnt = c->d_scratch.as<int>();
+    CK(cudaMemsetAsync(d_cnt, 0, sizeof(int), c->stream));
+    RegionQuery q;
+    q.kind = kind;
+    for (int i = 0; i < 3; ++i) {
+        q.a[i] = a[i];
+        q.b[i] = b[i];
+    }
+    const int m = mp.grid.m;
+    if (m > 0) {
+        region_kernel<<<(m + 255) / 256, 256, 0, c->stream>>>(mp.grid.sorted, m, q, d_out, cap, d_cnt);
+        c->launches += 1;
+    }
+    CK(cudaGetLastError());
+    int h = 0;
+    CK(cudaMemcpyAsync(&h, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    *n_out_host = h;
+    return ICP4R_OK;
+}
+
+// ---- Delete_Point_Boxes / Add_Point_Boxes / Delete_Points (ikd_Tree.cpp:500-565,656-824) ------------------------------
+// valid[] is the alive flag; userdel[] remembers that a point was removed by a delete call (and may come back with
+// Add_Point_Boxes) as opposed to down-sampling (point_downsample_deleted: never comes back).
+__global__ void __launch_bounds__(256) box_flag_kernel(const float4* __restrict__ pts, uint8_t* __restrict__ valid, uint8_t* __restrict__ userdel,
+                                                       int m, const float* __restrict__ boxes6, int nb, int revive, int* __restrict__ count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool change = false;
+    if (i < m) {
+        const bool candidate = revive ? (!valid[i] && userdel[i]) : (valid[i] != 0);
+        if (candidate) {
+            const float4 p = pts[i];
+            for (int b = 0; b < nb && !change; ++b) {
+                const float* q = boxes6 + 6 * b;
+                change = q[0] <= p.x && q[3] > p.x && q[1] <= p.y && q[4] > p.y && q[2] <= p.z && q[5] > p.z;
+            }
+            if (change) {
+                valid[i] = revive ? 1 : 0;
+                userdel[i] = revive ? 0 : 1;
+            }
+        }
+    }
+    const unsigned bal = __ballot_sync(FULL, change);
+    if (bal && (threadIdx.x & 31) == 0) atomicAdd(count, __popc(bal));
+}
+
+// one warp walks the requests in order (each sees the deletions of the previous ones, like the reference's loop);
+// for a request the lanes scan the cells within EPSS of the point and the lowest insertion index that matches wins
+__global__ void __launch_bounds__(32) delete_points_kernel(GridDesc g, const float4* __restrict__ req, int n, uint8_t* __restrict__ valid,
+                                                          uint8_t* __restrict__ userdel, int* __restrict__ count) {
+    const int lane = threadIdx.x;
+    int deleted = 0;
+    for (int r = 0; r < n; ++r) {
+        const float4 t = req[r];
+        int best = 0x7fffffff;
+        if (isfinite(t.x) && isfinite(t.y) && isfinite(t.z)) {
+            const float e = 2e-6f + g.margin;
+            const int x0 = cell_of(t.x - e, g.ox, g.inv_cell, g.nx), x1 = cell_of(t.x + e, g.ox, g.inv_cell, g.nx);
+            const int y0 = cell_of(t.y - e, g.oy, g.inv_cell, g.ny), y1 = cell_of(t.y + e, g.oy, g.inv_cell, g.ny);
+            const int z0 = cell_of(t.z - e, g.oz, g.inv_cell, g.nz), z1 = cell_of(t.z + e, g.oz, g.inv_cell, g.nz);
+            for (int z = z0; z <= z1; ++z)
+                for (int y = y0; y <= y1; ++y) {
+                    const uint32_t rowbase = (uint32_t)(z * g.ny + y) * (uint32_t)g.nx;
+                    const uint32_t s = g.cell_start[rowbase + x0], eidx = g.cell_start[rowbase + x1 + 1];
+                    for (uint32_t j = s + lane; j < eidx; j += 32) {
+                        const float4 p = g.sorted[j];
+                        const int id = __float_as_int(p.w);
+                        // same_point (ikd_Tree.cpp:1422-1424): float differences, compared with EPSS in double
+                        if (valid[id] && (double)fabsf(__fsub_rn(p.x, t.x)) < 1e-6 && (double)fabsf(__fsub_rn(p.y, t.y)) < 1e-6 &&
+                            (double)fabsf(__fsub_rn(p.z, t.z)) < 1e-6)
+                            best = min(best, id);
+                    }
+                }
+        }
+        best = __reduce_min_sync(FULL, best);
+        if (best != 0x7fffffff) {
+            if (lane == 0) {
+                valid[best] = 0;
+                userdel[best] = 1;
+            }
+            ++deleted;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) *count = deleted;
+}
+
+int map_box_flags(Ctx* c, Map& mp, const float* d_boxes6, int nb, bool revive, int* n_changed_host) {
+    *n_changed_host = 0;
+    if (nb <= 0 || mp.m <= 0) return ICP4R_OK;
+    CKS(reserve(c, c->d_scratch, 64));
+    int* d_cnt = c->d_scratch.as<int>();
+    CK(cudaMemsetAsync(d_cnt, 0, sizeof(int), c->stream));
+    box_flag_kernel<<<(mp.m + 255) / 256, 256, 0, c->stream>>>(mp.pts.as<float4>(), mp.valid.as<uint8_t>(), mp.userdel.as<uint8_t>(), mp.m, d_boxes6, nb,
+                                                               revive ? 1 : 0, d_cnt);
+    c->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(n_changed_host, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return ICP4R_OK;
+}
+
+int map_delete_points(Ctx* c, Map& mp, const float4* d_req, int n, int* n_deleted_host) {
+    *n_deleted_host = 0;
+    if (n <= 0 || mp.grid.m <= 0) return ICP4R_OK;
+    CKS(reserve(c, c->d_scratch, 64));
+    int* d_cnt = c->d_scratch.as<int>();
+    CK(cudaMemsetAsync(d_cnt, 0, sizeof(int), c->stream));
+    delete_points_kernel<<<1, 32, 0, c->stream>>>(mp.grid, d_req, n, mp.valid.as<uint8_t>(), mp.userdel.as<uint8_t>(), d_cnt);
+    c->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(n_deleted_host, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return ICP4R_OK;
+}
+
 int map_sector(Ctx* c, const Map& mp, const float centre[3], float radius, float heading, int32_t* d_out, int cap, int* n_out_host) {
     CKS(reserve(c, c->d_scratch, 64));
     int* d_cnt = c->d_scratch.as<int>();

@@ -205,6 +205,26 @@ int icp4r_doppler_filter(icp4r_handle h, const float* xyziv, int32_t n, int mem,
 int icp4r_transform_points(icp4r_handle h, const double T[16], const float* xyzw, int32_t n, int mem,
                            float* xyzw_out);
 
+/* ---- the rest of the KD_TREE surface (ikd_Tree.h:243-249) ----------------------------------------------- */
+/* KD_TREE::Box_Search (ikd_Tree.cpp:401-405,1024-1051): indices of the valid points with min <= p < max on every
+ * axis. Output order is unspecified (the reference: tree order); *n_out = number of hits, at most cap written. */
+int icp4r_map_box_search(icp4r_handle h, const float box_min[3], const float box_max[3], int mem, int32_t* idx_out,
+                         int32_t cap, int32_t* n_out);
+/* KD_TREE::Radius_Search (ikd_Tree.cpp:408-412,1054-1095): valid points with float d2 <= radius * radius. */
+int icp4r_map_radius_search(icp4r_handle h, const float centre_xyz[3], float radius, int mem, int32_t* idx_out,
+                            int32_t cap, int32_t* n_out);
+/* KD_TREE::Delete_Point_Boxes (ikd_Tree.cpp:544-565): deletes every valid point inside any of the boxes
+ * (boxes6 = n_boxes x {min xyz, max xyz}, host memory, half-open like Box_Search); *n_deleted = how many. */
+int icp4r_map_delete_boxes(icp4r_handle h, const float* boxes6, int32_t n_boxes, int32_t* n_deleted);
+/* KD_TREE::Add_Point_Boxes (ikd_Tree.cpp:500-519): points inside the boxes that Delete_Points / Delete_Point_Boxes
+ * removed come back (points removed by down-sampling do not). The reference can only revive points that no
+ * re-balancing rebuild has purged yet — which ones depends on its tree shape; here every such point is restorable. */
+int icp4r_map_add_boxes(icp4r_handle h, const float* boxes6, int32_t n_boxes, int32_t* n_restored);
+/* KD_TREE::Delete_Points (ikd_Tree.cpp:522-541): for each requested point, in order, ONE valid point with
+ * |dx|, |dy|, |dz| < 1e-6 (same_point, :1422) is deleted — the one with the lowest index (the reference: the first on
+ * its descent path, which can miss a copy when coordinates tie on a split axis). */
+int icp4r_map_delete_points(icp4r_handle h, const float* xyzw, int32_t n, int mem, int32_t* n_deleted);
+
 /* One frame of scan-to-map odometry (the loop body of radar_odometry.cpp:380-421 with registration before insertion):
  * register the scan against the handle's map starting from T_io, write the estimated pose back to T_io, transform the
  * scan with it (pointAssociateToMap) and append it to the map (Add_Points(.., false)) — one host-to-device copy of

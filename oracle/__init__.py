@@ -226,6 +226,37 @@ class IkdTree:
         n = ref().ikdref_sector(self.h, _p(c), C.c_float(radius), C.c_float(heading), _p(out), C.c_int(cap))
         return out[:min(n, cap)].copy()
 
+    def radius(self, centre, radius):
+        c = np.ascontiguousarray(centre, np.float32)
+        cap = max(self.n, 1)
+        out = np.empty(cap, np.int32)
+        ref().ikdref_radius.restype = C.c_int
+        n = ref().ikdref_radius(self.h, _p(c), C.c_float(radius), _p(out), C.c_int(cap))
+        return out[:n].copy()
+
+    def box(self, bmin, bmax):
+        lo, hi = np.ascontiguousarray(bmin, np.float32), np.ascontiguousarray(bmax, np.float32)
+        cap = max(self.n, 1)
+        out = np.empty(cap, np.int32)
+        ref().ikdref_box.restype = C.c_int
+        n = ref().ikdref_box(self.h, _p(lo), _p(hi), _p(out), C.c_int(cap))
+        return out[:n].copy()
+
+    def delete_boxes(self, boxes):
+        b = np.ascontiguousarray(boxes, np.float32).reshape(-1, 6)
+        ref().ikdref_delete_boxes.restype = C.c_int
+        return ref().ikdref_delete_boxes(self.h, _p(b), C.c_int(b.shape[0]))
+
+    def add_boxes(self, boxes):
+        b = np.ascontiguousarray(boxes, np.float32).reshape(-1, 6)
+        ref().ikdref_add_boxes.restype = None
+        ref().ikdref_add_boxes(self.h, _p(b), C.c_int(b.shape[0]))
+
+    def delete_points(self, pts):
+        pts = f4(pts)
+        ref().ikdref_delete_points.restype = None
+        ref().ikdref_delete_points(self.h, _p(pts), C.c_int(pts.shape[0]))
+
     def flatten(self):
         cap = max(self.n, 1)
         out = np.empty(cap, np.int32)
@@ -423,6 +454,45 @@ class OracleMap:
         n = lib().orc_map_sector(_p(self.pts), _p(self.valid), C.c_int(self.m), _p(c), C.c_float(radius),
                                  C.c_float(heading), _p(out), C.c_int(out.shape[0]))
         return out[:n].copy()
+
+
+def map_box_search(pts, valid, bmin, bmax):
+    pts = f4(pts)
+    v = np.ascontiguousarray(valid, np.uint8)
+    out = np.empty(max(pts.shape[0], 1), np.int32)
+    lib().orc_map_box_search.restype = C.c_int
+    n = lib().orc_map_box_search(_p(pts), _p(v), C.c_int(pts.shape[0]), _p(np.ascontiguousarray(bmin, np.float32)),
+                                 _p(np.ascontiguousarray(bmax, np.float32)), _p(out), C.c_int(out.shape[0]))
+    return out[:n].copy()
+
+
+def map_radius_search(pts, valid, centre, radius):
+    pts = f4(pts)
+    v = np.ascontiguousarray(valid, np.uint8)
+    out = np.empty(max(pts.shape[0], 1), np.int32)
+    lib().orc_map_radius_search.restype = C.c_int
+    n = lib().orc_map_radius_search(_p(pts), _p(v), C.c_int(pts.shape[0]), _p(np.ascontiguousarray(centre, np.float32)),
+                                    C.c_float(radius), _p(out), C.c_int(out.shape[0]))
+    return out[:n].copy()
+
+
+def map_delete_boxes(pts, valid, userdel, boxes):
+    """in place on valid / userdel; returns the number of points deleted"""
+    b = np.ascontiguousarray(boxes, np.float32).reshape(-1, 6)
+    lib().orc_map_delete_boxes.restype = C.c_int
+    return lib().orc_map_delete_boxes(_p(f4(pts)), _p(valid), _p(userdel), C.c_int(pts.shape[0]), _p(b), C.c_int(b.shape[0]))
+
+
+def map_add_boxes(pts, valid, userdel, boxes):
+    b = np.ascontiguousarray(boxes, np.float32).reshape(-1, 6)
+    lib().orc_map_add_boxes.restype = C.c_int
+    return lib().orc_map_add_boxes(_p(f4(pts)), _p(valid), _p(userdel), C.c_int(pts.shape[0]), _p(b), C.c_int(b.shape[0]))
+
+
+def map_delete_points(pts, valid, userdel, targets):
+    t = f4(targets)
+    lib().orc_map_delete_points.restype = C.c_int
+    return lib().orc_map_delete_points(_p(f4(pts)), _p(valid), _p(userdel), C.c_int(pts.shape[0]), _p(t), C.c_int(t.shape[0]))
 
 
 def voxel_grid(pts, leaf, valid=None):

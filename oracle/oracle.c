@@ -809,6 +809,88 @@ int orc_map_sector(const float* pts, const uint8_t* valid, int m, const float c[
     return cnt;
 }
 
+/* ------------------------------------------------------------------ box / radius search, deletes --- */
+/* KD_TREE::Box_Search -> Search_by_range (ikd_Tree.cpp:401-405,1024-1051): non-deleted points with
+ * min <= p < max on every axis (half-open, float compares). Output order in the reference is tree order;
+ * here ascending index — compare as sets. */
+static int in_box6(const float* p, const float* b6) { /* half-open box, b6 = min xyz, max xyz */
+    return b6[0] <= p[0] && b6[3] > p[0] && b6[1] <= p[1] && b6[4] > p[1] && b6[2] <= p[2] && b6[5] > p[2];
+}
+int orc_map_box_search(const float* pts, const uint8_t* valid, int m, const float bmin[3], const float bmax[3], int32_t* out, int cap) {
+    const float b6[6] = {bmin[0], bmin[1], bmin[2], bmax[0], bmax[1], bmax[2]};
+    int cnt = 0;
+    for (int j = 0; j < m; ++j)
+        if ((!valid || valid[j]) && in_box6(pts + 4 * (size_t)j, b6)) {
+            if (cnt < cap) out[cnt] = j;
+            ++cnt;
+        }
+    return cnt;
+}
+
+/* KD_TREE::Radius_Search -> Search_by_radius (ikd_Tree.cpp:408-412,1054-1095): non-deleted points with
+ * calc_dist(p, centre) <= radius * radius (float). The reference also takes whole subtrees whose bounding
+ * sphere lies inside the query sphere, which is the same set up to float rounding exactly on the boundary. */
+int orc_map_radius_search(const float* pts, const uint8_t* valid, int m, const float c[3], float radius, int32_t* out, int cap) {
+    int cnt = 0;
+    const float r2 = radius * radius;
+    for (int j = 0; j < m; ++j)
+        if ((!valid || valid[j]) && dist2f(pts + 4 * (size_t)j, c) <= r2) {
+            if (cnt < cap) out[cnt] = j;
+            ++cnt;
+        }
+    return cnt;
+}
+
+/* KD_TREE::Delete_Point_Boxes -> Delete_by_range(.., is_downsample = false) (ikd_Tree.cpp:544-565,656-719):
+ * every non-deleted point inside a box is deleted; returns how many. `userdel` remembers that the deletion can be
+ * undone by Add_Point_Boxes (points removed by down-sampling can not: point_downsample_deleted, :782,789). */
+int orc_map_delete_boxes(const float* pts, uint8_t* valid, uint8_t* userdel, int m, const float* boxes6, int nb) {
+    int cnt = 0;
+    for (int b = 0; b < nb; ++b)
+        for (int j = 0; j < m; ++j)
+            if (valid[j] && in_box6(pts + 4 * (size_t)j, boxes6 + 6 * (size_t)b)) {
+                valid[j] = 0;
+                userdel[j] = 1;
+                ++cnt;
+            }
+    return cnt;
+}
+
+/* KD_TREE::Add_Point_Boxes -> Add_by_range (ikd_Tree.cpp:500-519,771-824): points inside a box that were deleted by
+ * Delete_Points / Delete_Point_Boxes come back. Returns how many (the reference returns nothing). */
+int orc_map_add_boxes(const float* pts, uint8_t* valid, uint8_t* userdel, int m, const float* boxes6, int nb) {
+    int cnt = 0;
+    for (int b = 0; b < nb; ++b)
+        for (int j = 0; j < m; ++j)
+            if (!valid[j] && userdel[j] && in_box6(pts + 4 * (size_t)j, boxes6 + 6 * (size_t)b)) {
+                valid[j] = 1;
+                userdel[j] = 0;
+                ++cnt;
+            }
+    return cnt;
+}
+
+/* KD_TREE::Delete_Points -> Delete_by_point (ikd_Tree.cpp:522-541,721-768): for every requested point, in order,
+ * ONE non-deleted point with |dx|, |dy|, |dz| < EPSS = 1e-6 (same_point, :1422-1424) is deleted. The reference
+ * finds it by descending the tree along the split comparisons (with coordinates equal on the split axis it can
+ * miss an existing copy); the restatement deletes the lowest-index match. Returns how many were deleted. */
+int orc_map_delete_points(const float* pts, uint8_t* valid, uint8_t* userdel, int m, const float* targets, int n) {
+    int cnt = 0;
+    for (int i = 0; i < n; ++i) {
+        const float* t = targets + 4 * (size_t)i;
+        for (int j = 0; j < m; ++j) {
+            const float* p = pts + 4 * (size_t)j;
+            if (valid[j] && (double)fabsf(p[0] - t[0]) < 1e-6 && (double)fabsf(p[1] - t[1]) < 1e-6 && (double)fabsf(p[2] - t[2]) < 1e-6) {
+                valid[j] = 0;
+                userdel[j] = 1;
+                ++cnt;
+                break;
+            }
+        }
+    }
+    return cnt;
+}
+
 /* ------------------------------------------------------------------ VoxelGrid (PCL 1.8 restatement) --- */
 /* pcl::VoxelGrid<PointXYZI>::applyFilter with the defaults the reference uses (src/radar_odometry.cpp:426-429:
  * setLeafSize(0.5, 0.5, 0.5), downsample_all_data, min_points_per_voxel 0, no field filter). PCL (1.8, the ROS

@@ -145,6 +145,23 @@ int ikdref_delete_boxes(void* h, const float* boxes6, int nb) {
     return static_cast<Tree*>(h)->Delete_Point_Boxes(v);
 }
 
+void ikdref_add_boxes(void* h, const float* boxes6, int nb) {
+    std::vector<BoxPointType> v(nb);
+    for (int i = 0; i < nb; ++i)
+        for (int a = 0; a < 3; ++a) {
+            v[i].vertex_min[a] = boxes6[6 * i + a];
+            v[i].vertex_max[a] = boxes6[6 * i + 3 + a];
+        }
+    static_cast<Tree*>(h)->Add_Point_Boxes(v);
+}
+
+void ikdref_delete_points(void* h, const float* xyzw, int n) {
+    PV v;
+    v.reserve(n);
+    for (int i = 0; i < n; ++i) v.push_back(mk(xyzw + 4 * (size_t)i, 0));
+    static_cast<Tree*>(h)->Delete_Points(v);
+}
+
 /* indices of all valid points currently in the tree */
 int ikdref_flatten(void* h, int32_t* idx_out, int cap) {
     Tree* t = static_cast<Tree*>(h);

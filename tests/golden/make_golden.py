@@ -11,6 +11,8 @@ Files written next to this script:
     knn_incr.npz     Build(3000) + 3 x Add_Points(2000, false) + Nearest_Search k=5, as radar_odometry.cpp does
     downsample.npz   Build + Add_Points(..., true) with a 0.5 m voxel: return values and surviving index set
     sector.npz       Sector_Search index sets for several headings (80 m, as radar_odometry.cpp:396)
+    boxops.npz       Box_Search / Radius_Search sets, Delete_Point_Boxes counts, Delete_Points, Add_Point_Boxes: the
+                     surviving index set and a k-NN over it after every step
 """
 import os
 import sys
@@ -95,6 +97,46 @@ def main():
         for hi, hd in enumerate(headings):
             out[f"s_{ci}_{hi}"] = np.sort(t.sector(c, 80.0, float(hd)))
     np.savez_compressed(os.path.join(HERE, "sector.npz"), pts=pts, centres=centres, headings=headings, radius=80.0, **out)
+    t.close()
+    # --- box / radius search and the deletes (ikd_Tree.h:243-249)
+    rng = np.random.default_rng(61)
+    pts = np.zeros((5000, 4), np.float32)
+    pts[:, :3] = rng.uniform(-20, 20, (5000, 3)) * np.array([1, 1, 0.15])
+    t = O.IkdTree()
+    t.build(pts)
+    boxes = np.array([[-5, -5, -1, 5, 5, 1], [3, 3, -3, 12, 9, 3], [-19.5, 10, -0.5, -12, 19, 0.5], [100, 100, 100, 101, 101, 101]], np.float32)
+    centres = np.array([[0, 0, 0], [10.5, -12.25, 0.5], [-18, 18, -1]], np.float32)
+    radii = np.array([3.0, 7.5, 0.8], np.float32)
+    out = {}
+    for bi, b in enumerate(boxes):
+        out[f"box_{bi}"] = np.sort(t.box(b[:3], b[3:]))
+    for ci, c in enumerate(centres):
+        for ri, r in enumerate(radii):
+            out[f"rad_{ci}_{ri}"] = np.sort(t.radius(c, float(r)))
+    steps = []
+    q = np.zeros((400, 4), np.float32)
+    q[:, :3] = rng.uniform(-20, 20, (400, 3)) * np.array([1, 1, 0.15])
+
+    def snap(tag):
+        alive = np.sort(t.flatten())
+        ik, dk, fk = t.knn(q, 5, 0.0)
+        out[f"alive_{tag}"] = alive
+        out[f"knn_idx_{tag}"], out[f"knn_d2_{tag}"], out[f"knn_found_{tag}"] = ik, dk, fk
+        steps.append(tag)
+
+    del_boxes = np.array([[-4, -4, -2, 4, 4, 2], [8, -15, -3, 15, -8, 3]], np.float32)
+    out["del_count"] = np.int32(t.delete_boxes(del_boxes))
+    snap("after_delete_boxes")
+    victims = pts[np.array([11, 222, 3333, 4444, 4999])].copy()
+    victims[2, 0] += np.float32(5e-7)       # inside EPSS: still the same point
+    victims[4, 1] += np.float32(1e-3)       # outside EPSS: nothing to delete
+    t.delete_points(victims)
+    snap("after_delete_points")
+    add_boxes = np.array([[-2, -2, -2, 2, 2, 2]], np.float32)
+    t.add_boxes(add_boxes)
+    snap("after_add_boxes")
+    np.savez_compressed(os.path.join(HERE, "boxops.npz"), pts=pts, boxes=boxes, centres=centres, radii=radii, q=q, del_boxes=del_boxes,
+                        victims=victims, add_boxes=add_boxes, **out)
     t.close()
     print("golden vectors written to", HERE)
 

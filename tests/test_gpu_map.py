@@ -152,3 +152,60 @@ def test_incremental_append_equals_fresh_build(handle, pkg):
         assert (bits(pts) == bits(allp)).all() and valid.all()
     finally:
         fresh.close()
+
+
+def test_box_radius_delete_golden(handle, O):
+    """Box_Search / Radius_Search / Delete_Point_Boxes / Delete_Points / Add_Point_Boxes through the C ABI against the
+    reference's ikd-Tree (golden vectors) — index sets, counts, and the k-NN over the survivors after every step"""
+    g = np.load(os.path.join(G, "boxops.npz"))
+    pts = g["pts"]
+    handle.map_build(pts)
+    for bi, b in enumerate(g["boxes"]):
+        assert (np.sort(handle.map_box_search(b[:3], b[3:])) == g[f"box_{bi}"]).all()
+    for ci, c in enumerate(g["centres"]):
+        for ri, r in enumerate(g["radii"]):
+            assert (np.sort(handle.map_radius_search(c, float(r))) == g[f"rad_{ci}_{ri}"]).all()
+
+    def check(tag):
+        _, valid = handle.map_points()
+        assert (np.nonzero(valid)[0] == g[f"alive_{tag}"]).all(), tag
+        idx, d2, found = handle.map_knn(g["q"], 5, 0.0)
+        assert (found == g[f"knn_found_{tag}"]).all() and (bits(d2) == bits(g[f"knn_d2_{tag}"])).all() and (idx == g[f"knn_idx_{tag}"]).all()
+
+    assert handle.map_delete_boxes(g["del_boxes"]) == int(g["del_count"])
+    check("after_delete_boxes")
+    assert handle.map_delete_points(g["victims"]) == 4
+    check("after_delete_points")
+    # Add_Point_Boxes: superset of the reference (see tests/test_oracle_golden.py), equal to the oracle
+    valid_o = np.ones(len(pts), np.uint8)
+    userdel_o = np.zeros(len(pts), np.uint8)
+    O.map_delete_boxes(pts, valid_o, userdel_o, g["del_boxes"])
+    O.map_delete_points(pts, valid_o, userdel_o, g["victims"])
+    want = O.map_add_boxes(pts, valid_o, userdel_o, g["add_boxes"])
+    assert handle.map_add_boxes(g["add_boxes"]) == want
+    _, valid = handle.map_points()
+    assert (valid == valid_o).all() and set(g["alive_after_add_boxes"]) <= set(np.nonzero(valid)[0])
+    # points removed by down-sampling never come back; searches on an empty region return nothing
+    handle.map_build(pts[:2000])
+    handle.map_set_downsample(0.5)
+    handle.map_add_points(pts[2000:3000], True)
+    _, v0 = handle.map_points()
+    assert handle.map_add_boxes(np.array([[-100, -100, -100, 100, 100, 100]], np.float32)) == 0
+    _, v1 = handle.map_points()
+    assert (v0 == v1).all()
+    assert len(handle.map_box_search([500, 500, 500], [501, 501, 501])) == 0
+
+
+def test_region_search_matches_oracle_large(handle, O):
+    rng = np.random.default_rng(9)
+    pts = np.zeros((300000, 4), np.float32)
+    pts[:, :3] = rng.uniform(-60, 60, (300000, 3)) * np.array([1, 1, 0.1])
+    handle.map_build(pts)
+    valid = np.ones(len(pts), np.uint8)
+    for _ in range(5):
+        c = rng.uniform(-50, 50, 3).astype(np.float32) * np.array([1, 1, 0.1], np.float32)
+        r = float(rng.uniform(1, 25))
+        assert (np.sort(handle.map_radius_search(c, r)) == O.map_radius_search(pts, valid, c, r)).all()
+        lo = c - rng.uniform(0.5, 20, 3).astype(np.float32)
+        hi = c + rng.uniform(0.5, 20, 3).astype(np.float32)
+        assert (np.sort(handle.map_box_search(lo, hi)) == O.map_box_search(pts, valid, lo, hi)).all()

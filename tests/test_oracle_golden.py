@@ -81,3 +81,40 @@ def test_oracle_vs_live_reference(O, pkg):
         got = O.knn(tgt, src, k, gate)
         assert (got[0] == want[0]).all() and (bits(got[1]) == bits(want[1])).all() and (got[2] == want[2]).all()
         t.close()
+
+
+def test_box_radius_delete_golden(O):
+    """Box_Search, Radius_Search, Delete_Point_Boxes, Delete_Points, Add_Point_Boxes restated over flat arrays ==
+    the reference's ikd-Tree (index sets, delete count, k-NN over the survivors after every step)"""
+    g = np.load(os.path.join(G, "boxops.npz"))
+    pts = g["pts"]
+    valid = np.ones(len(pts), np.uint8)
+    userdel = np.zeros(len(pts), np.uint8)
+    for bi, b in enumerate(g["boxes"]):
+        assert (O.map_box_search(pts, valid, b[:3], b[3:]) == g[f"box_{bi}"]).all()
+    for ci, c in enumerate(g["centres"]):
+        for ri, r in enumerate(g["radii"]):
+            assert (O.map_radius_search(pts, valid, c, float(r)) == g[f"rad_{ci}_{ri}"]).all()
+
+    def check(tag):
+        assert (np.nonzero(valid)[0] == g[f"alive_{tag}"]).all(), tag
+        ik, dk, fk = O.knn(pts, g["q"], 5, 0.0, valid=valid)
+        assert (fk == g[f"knn_found_{tag}"]).all() and (dk.view(np.int32) == g[f"knn_d2_{tag}"].view(np.int32)).all()
+        assert (ik == g[f"knn_idx_{tag}"]).all()
+
+    assert O.map_delete_boxes(pts, valid, userdel, g["del_boxes"]) == int(g["del_count"])
+    check("after_delete_boxes")
+    assert O.map_delete_points(pts, valid, userdel, g["victims"]) == 4   # the fifth victim is 1 mm off: not the same point
+    check("after_delete_points")
+    before = valid.copy()
+    O.map_add_boxes(pts, valid, userdel, g["add_boxes"])
+    # Add_Point_Boxes: the reference can only revive deleted points that no re-balancing rebuild has purged from the
+    # tree yet (Rebuild flattens without the deleted points, ikd_Tree.cpp:633-653,1379-1404) — which ones depends on
+    # the tree's shape. The restatement revives every point deleted by Delete_*: a superset, and the extra points
+    # are exactly deleted points inside the box.
+    mine, ref = set(np.nonzero(valid)[0]), set(g["alive_after_add_boxes"])
+    assert ref <= mine
+    b = g["add_boxes"][0]
+    for j in mine - ref:
+        assert not before[j] and (b[:3] <= pts[j, :3]).all() and (b[3:] > pts[j, :3]).all()
+    assert len(mine) > int(before.sum())
