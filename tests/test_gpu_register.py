@@ -226,3 +226,28 @@ def test_register_map_batch(pkg, O, handle):
     import torch
     Tb2, rb2 = handle.register_map_batch(torch.from_numpy(S).cuda(), off, o, T0s)
     assert np.array_equal(Tb2, Tb)
+
+
+def test_non_finite_points_are_ignored(pkg, O, handle):
+    """NaN / inf coordinates in the scan or in the map never match anything: the result equals the registration of the
+    clouds with those points removed (indices keep referring to the original arrays)"""
+    src, tgt, _ = pkg.synth.frame_pair(91, 900, 4000, extent=30.0)
+    src_bad, tgt_bad = src.copy(), tgt.copy()
+    src_bad[::37, 0] = np.nan
+    src_bad[5::53, 2] = np.inf
+    tgt_bad[::29, 1] = np.nan
+    tgt_bad[7::61, 0] = -np.inf
+    keep_s = np.isfinite(src_bad[:, :3]).all(1)
+    keep_t = np.isfinite(tgt_bad[:, :3]).all(1)
+    for kind, k in ((pkg.P2P_SVD, 1), (pkg.P2PLANE_KNN, 5)):
+        o = pkg.default_opts(residual=kind, k=k, max_iterations=8, max_corr_dist=2.0)
+        T_bad, r_bad, _ = handle.register(src_bad, tgt_bad, o)
+        T_ok, r_ok, _ = handle.register(src_bad[keep_s], tgt_bad[keep_t], o)
+        assert np.isfinite(T_bad).all()
+        assert r_bad.n_corr == r_ok.n_corr and r_bad.n_fitness == r_ok.n_fitness
+        et, er = pose_err(T_bad, T_ok)
+        assert et <= 1e-9 and er <= 1e-9
+        handle.map_build(tgt_bad)
+        T_map, r_map, _ = handle.register_map(src_bad, o)
+        et, er = pose_err(T_map, T_ok)
+        assert et <= 1e-9 and er <= 1e-9 and r_map.n_corr == r_ok.n_corr
