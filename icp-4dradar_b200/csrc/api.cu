@@ -338,7 +338,7 @@ static int map_knn_common(Ctx* c, bool brute, const float* q, int32_t nq, int me
         return fail(c, ICP4R_ERR_INVALID, "icp4r_map_knn: bad arguments (nq=%d k=%d)", nq, k);
     if (!c->map.built) return fail(c, ICP4R_ERR_STATE, "icp4r_map_knn before icp4r_map_build");
     if (nq == 0) return ICP4R_OK;
-    const void* dq;
+    const void* dq = nullptr;
     CKS(stage_in(c, c->d_q, q, (size_t)nq * sizeof(float4), mem, &dq));
     int32_t* di = idx;
     float* dd = d2;
@@ -432,7 +432,7 @@ static int box_flags(Ctx* c, const float* boxes6, int32_t n_boxes, bool revive, 
     Map& mp = c->map;
     if (!mp.built) return fail(c, ICP4R_ERR_STATE, "box operation before icp4r_map_build");
     if (n_boxes == 0 || mp.m == 0) return ICP4R_OK;
-    const void* dboxes;
+    const void* dboxes = nullptr;
     CKS(stage_in(c, c->d_q, boxes6, (size_t)n_boxes * 6 * sizeof(float), ICP4R_HOST, &dboxes));
     int changed = 0;
     CKS(map_box_flags(c, mp, static_cast<const float*>(dboxes), n_boxes, revive, &changed));
@@ -458,7 +458,7 @@ int icp4r_map_delete_points(icp4r_handle h, const float* xyzw, int32_t n, int me
     Map& mp = c->map;
     if (!mp.built) return fail(c, ICP4R_ERR_STATE, "icp4r_map_delete_points before icp4r_map_build");
     if (n == 0) return ICP4R_OK;
-    const void* dreq;
+    const void* dreq = nullptr;
     CKS(stage_in(c, c->d_q, xyzw, (size_t)n * sizeof(float4), mem, &dreq));
     int deleted = 0;
     CKS(map_delete_points(c, mp, static_cast<const float4*>(dreq), n, &deleted));
@@ -535,7 +535,7 @@ int icp4r_register_map(icp4r_handle h, const float* src, int32_t n, int mem, con
                        icp4r_result* res, const icp4r_dump* dump) {
     HCHECK(h);
     if (!opts || n < 0 || (n > 0 && !src) || bad_mem(mem)) return fail(c, ICP4R_ERR_INVALID, "icp4r_register_map: bad arguments");
-    const void* dsrc;
+    const void* dsrc = nullptr;
     CKS(stage_in(c, c->d_src, src, (size_t)n * sizeof(float4), mem, &dsrc));
     DumpStage ds;
     CKS(dump_prepare(c, dump, mem, n, opts, ds));
@@ -551,7 +551,7 @@ int icp4r_odometry_step(icp4r_handle h, const float* scan, int32_t n, int mem, c
     if (!opts || !T_io || n < 0 || (n > 0 && !scan) || bad_mem(mem)) return fail(c, ICP4R_ERR_INVALID, "icp4r_odometry_step: bad arguments");
     if (downsample_on) return fail(c, ICP4R_ERR_UNSUPPORTED, "icp4r_odometry_step: use icp4r_map_add_points for down-sampled insertion");
     Map& mp = c->map;
-    const void* dsrc;
+    const void* dsrc = nullptr;
     CKS(stage_in(c, c->d_src, scan, (size_t)n * sizeof(float4), mem, &dsrc));
     icp4r_result r;
     std::memset(&r, 0, sizeof(r));
@@ -587,7 +587,7 @@ int icp4r_register_map_batch(icp4r_handle h, const float* src, const int32_t* of
         if (off[i + 1] < off[i]) return fail(c, ICP4R_ERR_INVALID, "offsets must be non-decreasing (scan %d)", i);
     const size_t total = (size_t)(off[n_scans] - off[0]);
     if (total > 0 && !src) return fail(c, ICP4R_ERR_INVALID, "null cloud pointer");
-    const void* dsrc;
+    const void* dsrc = nullptr;
     CKS(stage_in(c, c->d_src, src, (size_t)off[n_scans] * sizeof(float4), mem, &dsrc));
     return register_scans_against_map(c, c->map, static_cast<const float4*>(dsrc), off, n_scans, opts, T0s, T_out, res);
 }
@@ -606,7 +606,7 @@ int icp4r_register(icp4r_handle h, const float* src, int32_t n, const float* tgt
     CKS(set_points(c, mp, tgt, m, mem, 0));
     mp.m = m;
     CKS(map_rebuild_grid(c, mp));
-    const void* dsrc;
+    const void* dsrc = nullptr;
     CKS(stage_in(c, c->d_src, src, (size_t)n * sizeof(float4), mem, &dsrc));
     DumpStage ds;
     CKS(dump_prepare(c, dump, mem, n, opts, ds));
@@ -692,7 +692,7 @@ int icp4r_register_sharded(icp4r_handle h, const float* src, int32_t n, int mem,
     HCHECK(h);
     if (!opts || n < 0 || (n > 0 && !src) || bad_mem(mem) || axis < 0 || axis > 2)
         return fail(c, ICP4R_ERR_INVALID, "icp4r_register_sharded: bad arguments");
-    const void* dsrc;
+    const void* dsrc = nullptr;
     CKS(stage_in(c, c->d_src, src, (size_t)n * sizeof(float4), mem, &dsrc));
     return register_against_map(c, c->map, static_cast<const float4*>(dsrc), n, opts, axis, slab_lo, slab_hi, T_out, res, nullptr);
 }
@@ -703,7 +703,7 @@ int icp4r_doppler_filter(icp4r_handle h, const float* xyziv, int32_t n, int mem,
                          icp4r_doppler_result* res) {
     HCHECK(h);
     if (!opts || !res || n < 0 || (n > 0 && !xyziv) || bad_mem(mem)) return fail(c, ICP4R_ERR_INVALID, "icp4r_doppler_filter: bad arguments");
-    const void* drec;
+    const void* drec = nullptr;
     CKS(stage_in(c, c->d_src, xyziv, (size_t)n * 5 * sizeof(float), mem, &drec));
     uint8_t* dmask = static_mask;
     if (mem == ICP4R_HOST && static_mask) {
@@ -732,7 +732,7 @@ extern "C" int icp4r_transform_points(icp4r_handle h, const double T[16], const 
     HCHECK(h);
     if (!T || n < 0 || (n > 0 && (!xyzw || !xyzw_out)) || bad_mem(mem)) return fail(c, ICP4R_ERR_INVALID, "icp4r_transform_points: bad arguments");
     if (n == 0) return ICP4R_OK;
-    const void* din;
+    const void* din = nullptr;
     CKS(stage_in(c, c->d_q, xyzw, (size_t)n * sizeof(float4), mem, &din));
     float4* dout = reinterpret_cast<float4*>(xyzw_out);
     if (mem == ICP4R_HOST) {

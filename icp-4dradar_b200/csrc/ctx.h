@@ -190,7 +190,6 @@ struct Ctx {
     bool no_graph_sharded = false;
     const GridDesc* graph_grid_owner = nullptr;  // graphs bake the grid by value: identity of what they baked
     GridDesc graph_grid_copy{};
-    const void* graph_pts = nullptr;
     bool use_graph = true;
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;

@@ -90,7 +90,6 @@ __global__ void __launch_bounds__(1024) doppler_final_kernel(const float* __rest
     __shared__ unsigned long long s_best[32];
     __shared__ double s_sum[32][10];
     __shared__ double s_model[2];
-    __shared__ int s_it;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     // best = max score, lowest iteration: key = (score << 32) | (0xffffffff - it), maximised
     unsigned long long best = 0ull;
@@ -113,7 +112,6 @@ __global__ void __launch_bounds__(1024) doppler_final_kernel(const float* __rest
         for (int k = 0; k < 32; ++k) bb = s_best[k] > bb ? s_best[k] : bb;
         const int sc = (int)(bb >> 32);
         const int it = sc > 0 ? (int)(0xffffffffu - (unsigned)(bb & 0xffffffffull)) : -1;
-        s_it = it;
         s_model[0] = it >= 0 ? As[it] : 0.0;  // the reference leaves A = b = 0 when no hypothesis scores
         s_model[1] = it >= 0 ? bs[it] : 0.0;
         out->A = s_model[0];

@@ -175,7 +175,7 @@ __device__ __forceinline__ bool delta_converged(const double* D /*3x4*/, double 
 __global__ void __launch_bounds__(LM_THREADS) gicp_lm_kernel(const RegParams* __restrict__ prm, RegState* __restrict__ st, int iter) {
     if (st->done) return;
     __shared__ double Hs[ICP4R_ACC_LEN], Hl[ICP4R_ACC_LEN], Ts[16], Xi[16], Ds[16], xi6[8], red[32];
-    __shared__ double s_lambda, s_nu, s_yi;
+    __shared__ double s_lambda, s_nu;
     __shared__ int s_state;  // 0: keep trying, 1: step taken (x0 updated or converged without update), 2: failed
     __shared__ RegParams P;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -238,7 +238,6 @@ __global__ void __launch_bounds__(LM_THREADS) gicp_lm_kernel(const RegParams* __
         if (tid == 0) {
             double yi = 0.0;
             for (int k = 0; k < LM_THREADS / 32; ++k) yi += red[k];
-            s_yi = yi;
             double den = 0.0;
             for (int i = 0; i < 6; ++i) den += xi6[i] * (s_lambda * xi6[i] - Hs[21 + i]);
             const double rho = (y0 - yi) / den;
