@@ -85,9 +85,10 @@ struct Map {
 // ---- peer-memory exchange for slab-sharded registration (one process per GPU, NVLink P2P) --------------------
 constexpr int XCH_MAXW = 8;
 struct Xch {  // lives on every rank; peers write their partial sums straight into it
-    double vals[2][XCH_MAXW][ICP4R_ACC_LEN];     // [parity][writer rank][accumulator]
-    unsigned long long flag[2][XCH_MAXW];        // epoch the writer has published for that parity
-    unsigned long long seq;                      // exchanges this rank has completed (identical on all ranks)
+    // [parity][writer rank][2 words per accumulator]: every 8-byte word carries 32 bits of a double and the 32-bit epoch
+    // it belongs to, so a word is valid the moment it is seen with the expected epoch — no flag, no fence
+    unsigned long long ll[2][XCH_MAXW][2 * ICP4R_ACC_LEN];
+    unsigned long long seq;  // exchanges this rank has completed (identical on all ranks)
 };
 struct XchTable {  // device-resident view of the communicator
     Xch* peer[XCH_MAXW];  // peer[r] = rank r's Xch mapped into this process (own rank: the local buffer)

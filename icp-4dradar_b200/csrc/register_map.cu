@@ -595,41 +595,51 @@ __global__ void __launch_bounds__(RM_THREADS, 1)
     __syncthreads();
     if ((MODE == MODE_ITER || MODE == MODE_FITNESS) && P.xt != nullptr) {
         // Slab-sharded map, fused flavour: the sum over ranks happens HERE, over NVLink peer memory, instead of a
-        // separate collective launch. Every rank's last block stores its 32 partial sums into every peer's
-        // exchange buffer, publishes an epoch flag, waits for all peers' flags and adds the contributions in rank
-        // order — so all ranks hold bit-identical totals, take the same decisions and therefore run the same
-        // number of exchanges. The epoch is that count (kept on the device), so consecutive exchanges alternate
-        // between the two buffers: a rank can only overwrite buffer p after every peer has published the epoch
-        // in between, i.e. after every peer finished reading p.
-        const XchTable xt = *P.xt;
-        Xch* mine = xt.peer[xt.rank];
-        const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long*>(&mine->seq) + 1ull;
-        const int par = (int)(epoch & 1ull);
-        if (tid < ICP4R_ACC_LEN)
-            for (int r = 0; r < xt.world; ++r) xt.peer[r]->vals[par][xt.rank][tid] = tot[tid];
-        __threadfence_system();
-        __syncthreads();
-        if (tid < xt.world) {
-            *reinterpret_cast<volatile unsigned long long*>(&xt.peer[tid]->flag[par][xt.rank]) = epoch;
-            volatile unsigned long long* f = &mine->flag[par][tid];
-            unsigned long long t0, t1;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-            while (*f < epoch) {
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-                if (t1 - t0 > 10000000000ull) {  // 10 s: a peer never arrived; report instead of hanging the GPU
-                    st->xch_timeout = 1;
-                    break;
-                }
+        // separate collective launch. Warp 0 of every rank's last block stores its 32 partial sums into every peer's
+        // exchange buffer and collects the peers' sums from its own, adding them in rank order — so all ranks hold
+        // bit-identical totals, take the same decisions and therefore run the same number of exchanges.
+        // Transport: every double travels as two 8-byte words {32 data bits, 32-bit epoch}; an aligned 8-byte store is
+        // one transaction, so a word seen with the expected epoch is complete — no flag word, no system-scope fence
+        // (two block-wide fences cost 9 us per iteration before). The epoch is the count of exchanges (kept on the
+        // device), consecutive exchanges alternate between two buffers: a rank can only overwrite buffer p after every
+        // peer has published the epoch in between, i.e. after every peer finished reading p.
+        if (w == 0) {
+            const XchTable xt = *P.xt;
+            Xch* mine = xt.peer[xt.rank];
+            const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long*>(&mine->seq) + 1ull;
+            const int par = (int)(epoch & 1ull);
+            const unsigned long long tag = (epoch & 0xFFFFFFFFull) << 32;
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(tot[lane]);
+            const unsigned long long w0 = tag | (bits & 0xFFFFFFFFull), w1 = tag | (bits >> 32);
+            for (int r = 0; r < xt.world; ++r) {
+                volatile unsigned long long* dst = &xt.peer[r]->ll[par][xt.rank][2 * lane];
+                dst[0] = w0;
+                dst[1] = w1;
             }
-        }
-        __syncthreads();
-        __threadfence_system();
-        if (tid < ICP4R_ACC_LEN) {
+            unsigned long long t0;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
             double sum = 0.0;
-            for (int r = 0; r < xt.world; ++r) sum += *reinterpret_cast<volatile double*>(&mine->vals[par][r][tid]);
-            tot[tid] = sum;
+            bool late = false;
+            for (int r = 0; r < xt.world; ++r) {
+                volatile unsigned long long* src = &mine->ll[par][r][2 * lane];
+                unsigned long long a, b;
+                for (;;) {
+                    a = src[0];
+                    b = src[1];
+                    if ((a & 0xFFFFFFFF00000000ull) == tag && (b & 0xFFFFFFFF00000000ull) == tag) break;
+                    unsigned long long t1;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                    if (t1 - t0 > 10000000000ull) {  // 10 s: a peer never arrived; report instead of hanging the GPU
+                        late = true;
+                        break;
+                    }
+                }
+                sum += __longlong_as_double((long long)((a & 0xFFFFFFFFull) | (b << 32)));
+            }
+            if (late) st->xch_timeout = 1;
+            tot[lane] = sum;
+            if (lane == 0) mine->seq = epoch;
         }
-        if (tid == 0) mine->seq = epoch;
         __syncthreads();
     }
     if (FIT) {
@@ -824,7 +834,7 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
     P.shard_axis = sharded ? shard_axis : -1;
     P.slab_lo = slab_lo;
     P.slab_hi = slab_hi;
-    const bool fused_shard = sharded && c->xch_ready && c->world > 1;
+    const bool fused_shard = sharded && c->xch_ready && c->world >= 1;
     if (fused_shard) {
         P.xt = c->d_xt.as<XchTable>();
     }
