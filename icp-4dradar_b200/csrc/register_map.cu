@@ -549,23 +549,26 @@ __global__ void __launch_bounds__(RM_THREADS, 1)
     if (lane == 0) atomicMax((unsigned long long*)(partials + 160 * ICP4R_ACC_LEN) + blockIdx.x * 4 + 0, (unsigned long long)(tp1 - tp0));
     if (tid == 0) ((unsigned long long*)(partials + 160 * ICP4R_ACC_LEN))[blockIdx.x * 4 + 1] = (unsigned long long)(tp2 - tp0);
 #endif
-    if (tid < ICP4R_ACC_LEN) {
+    // warp 0 publishes the block partial and takes the ticket: the fence that orders the two is needed only in the
+    // lanes that wrote (a block-wide fence made all 28 warps wait for it), the acquire side only in the lane that
+    // read the ticket — the barrier below hands the ordering on to the other threads, which read with ld.cg
+    if (w == 0) {
         double x = 0.0;
 #pragma unroll
-        for (int j = 0; j < nwb; ++j) x += red[j][tid];
-        partials[(size_t)blockIdx.x * ICP4R_ACC_LEN + tid] = x;
-    }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        unsigned* tk = FIT ? &st->ticket_fit : &st->ticket;
-        const unsigned t = atomicAdd(tk, 1u);
-        is_last = (t == gridDim.x - 1);
-        if (is_last) *tk = 0;
+        for (int j = 0; j < nwb; ++j) x += red[j][lane];
+        partials[(size_t)blockIdx.x * ICP4R_ACC_LEN + lane] = x;
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) {
+            unsigned* tk = FIT ? &st->ticket_fit : &st->ticket;
+            const unsigned t = atomicAdd(tk, 1u);
+            is_last = (t == gridDim.x - 1);
+            if (is_last) *tk = 0;
+            __threadfence();
+        }
     }
     __syncthreads();
     if (!is_last) return;
-    __threadfence();
 #ifdef ICP4R_PHASE_TIMING
     const long long tp3 = clock64();
 #endif
