@@ -57,7 +57,7 @@ def make_c2(seed=1002):
     return mp, scans
 
 
-NCU_TRAFFIC_BYTES = 7_580_928 + 637_184  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r1_c2_reg_iter_kernel_ncu.txt (cold-cache replay)
+NCU_TRAFFIC_BYTES = 7_582_208 + 537_600  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r1_c2_reg_iter_kernel_ncu.txt (cold-cache replay)
 C5_N, C5_ITERS = 16384, 20
 
 
