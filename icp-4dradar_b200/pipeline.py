@@ -53,3 +53,58 @@ def run_odometry(h: api.Icp4r, scans, opts: api.Opts, T_first=None, fused: bool 
         poses.append(T.copy())
         h.map_add_points(h.transform_points(T, scan), False)
     return poses
+
+
+# ---- scan-to-scan node ---------------------------------------------------------------------------------------------
+def synth_radar_sequence(seed: int, frames: int, pts_per_frame: int = 1200, extent: float = 120.0, scan_radius: float = 50.0,
+                         dynamic_frac: float = 0.1):
+    """(list of raw radar frames [n,5] x,y,z,intensity,doppler in the sensor frame, list of ground-truth poses)."""
+    rng = np.random.default_rng(seed)
+    scene = synth.Scene(seed, extent=extent, n_walls=int(12 * (extent / 80.0) ** 2))
+    poses = synth.trajectory(seed, frames)
+    out = []
+    for f, T in enumerate(poses):
+        w = scene.sample(rng, pts_per_frame, centre=(T[0, 3], T[1, 3]), radius=scan_radius)
+        s = synth.apply(np.linalg.inv(T), w)
+        nxt = poses[min(f + 1, frames - 1)]
+        prv = poses[max(f - 1, 0)]
+        v_world = (nxt[:3, 3] - prv[:3, 3]) / (0.1 * max(1, min(f + 1, frames - 1) - max(f - 1, 0)))   # 10 Hz frames
+        v_sensor = T[:3, :3].T @ v_world
+        vr, _dyn = synth.doppler(rng, s, v_sensor, dynamic_frac)
+        out.append(synth.radar_frame_bin(s, vr))
+    return out, poses
+
+
+def run_scan_to_scan(h: api.Icp4r, frames, opts: api.Opts, batched: bool = True, seed: int = 1):
+    """The scan-to-scan node over the C ABI (what /root/reference/src/iterative_closest_point.cpp:300-560 does per
+    frame): Doppler static-point filter on every frame (fitSineRansac + split, :387-403), ICP of the current static
+    points (source) against the previous frame's (target) (:510-514), pose chained by RIGHT multiplication
+    `currOdom = currOdom * icp_result` (:552). batched: all frame pairs of the recording in one
+    icp4r_register_batch call (replay); otherwise one icp4r_register per frame (live).
+    Returns (poses [frames][4,4], ego velocities [frames][3], per-frame results)."""
+    statics, vel = [], []
+    for f, rec in enumerate(frames):
+        mask, dr = h.doppler_filter(rec, 0, seed=seed + f)
+        m = np.asarray(mask.cpu() if hasattr(mask, "cpu") else mask).astype(bool)
+        r = np.asarray(rec.cpu() if hasattr(rec, "cpu") else rec)
+        statics.append(np.ascontiguousarray(r[m][:, :4], np.float32))
+        vel.append(np.array(list(dr.velocity)))
+    n = len(frames)
+    if batched and n > 1:
+        src = np.concatenate(statics[1:])
+        tgt = np.concatenate(statics[:-1])
+        so = np.concatenate([[0], np.cumsum([len(s) for s in statics[1:]])]).astype(np.int32)
+        to = np.concatenate([[0], np.cumsum([len(s) for s in statics[:-1]])]).astype(np.int32)
+        Ts, res = h.register_batch(src, so, tgt, to, opts)
+    else:
+        Ts, res = [], []
+        for f in range(1, n):
+            T, r, _ = h.register(statics[f], statics[f - 1], opts)
+            Ts.append(T)
+            res.append(r)
+    cur = np.eye(4)
+    poses = [cur.copy()]
+    for T in Ts:
+        cur = cur @ np.asarray(T, np.float64).reshape(4, 4)
+        poses.append(cur.copy())
+    return poses, vel, res
