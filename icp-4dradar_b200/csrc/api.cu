@@ -194,6 +194,11 @@ int icp4r_destroy(icp4r_handle h) {
     if (c->own_stream != c->stream) cudaStreamSynchronize(c->own_stream);
     drop_graphs(c);
     for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
+    if (c->copy_stream) {
+        for (auto& e : c->copy_events)
+            if (e) cudaEventDestroy(e);
+        cudaStreamDestroy(c->copy_stream);
+    }
     shard_destroy(c);
     shard_ipc_close(c);
     release(c->d_xch);
@@ -639,7 +644,48 @@ int icp4r_register_batch(icp4r_handle h, const float* src, const int32_t* src_of
     }
     const size_t ns = (size_t)so[n_pairs], nt = (size_t)to[n_pairs];
     if ((ns > 0 && !src) || (nt > 0 && !tgt)) return fail(c, ICP4R_ERR_INVALID, "null cloud pointer");
-    const void *dsrc, *dtgt, *dso, *dto;
+    // Large host-resident batches: copy the clouds in chunks on a second stream that runs ahead of the kernels, so the
+    // bus transfer of chunk k+1 overlaps the registration of chunk k (the clouds of a pair range are contiguous).
+    constexpr int NCHUNK = 8;
+    if (mem == ICP4R_HOST && n_pairs >= 64 * NCHUNK && (ns + nt) * sizeof(float4) >= ((size_t)32 << 20)) {
+        if (!c->copy_stream) {
+            CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+            for (auto& e : c->copy_events) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+        CKS(reserve(c, c->b_src, std::max<size_t>(ns, 1) * sizeof(float4)));
+        CKS(reserve(c, c->b_tgt, std::max<size_t>(nt, 1) * sizeof(float4)));
+        CKS(reserve(c, c->b_soff, (size_t)(n_pairs + 1) * 4));
+        CKS(reserve(c, c->b_toff, (size_t)(n_pairs + 1) * 4));
+        CKS(reserve(c, c->b_T, (size_t)n_pairs * 16 * sizeof(double)));
+        CKS(reserve(c, c->b_res, (size_t)n_pairs * sizeof(icp4r_result)));
+        CK(cudaMemcpyAsync(c->b_soff.p, src_off, (size_t)(n_pairs + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->b_toff.p, tgt_off, (size_t)(n_pairs + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+        // the staging buffers may still be read by earlier work of this handle: the copies start after it
+        CK(cudaEventRecord(c->copy_events[NCHUNK], c->stream));
+        CK(cudaStreamWaitEvent(c->copy_stream, c->copy_events[NCHUNK], 0));
+        const int per = (n_pairs + NCHUNK - 1) / NCHUNK;
+        for (int k = 0; k < NCHUNK; ++k) {
+            const int p0 = std::min(k * per, n_pairs), p1 = std::min(p0 + per, n_pairs);
+            if (p1 > p0) {
+                const size_t s0 = (size_t)so[p0], s1 = (size_t)so[p1], t0 = (size_t)to[p0], t1 = (size_t)to[p1];
+                if (s1 > s0) CK(cudaMemcpyAsync(c->b_src.as<float4>() + s0, src + 4 * s0, (s1 - s0) * sizeof(float4), cudaMemcpyHostToDevice, c->copy_stream));
+                if (t1 > t0) CK(cudaMemcpyAsync(c->b_tgt.as<float4>() + t0, tgt + 4 * t0, (t1 - t0) * sizeof(float4), cudaMemcpyHostToDevice, c->copy_stream));
+            }
+            CK(cudaEventRecord(c->copy_events[k], c->copy_stream));
+        }
+        for (int k = 0; k < NCHUNK; ++k) {
+            const int p0 = std::min(k * per, n_pairs), p1 = std::min(p0 + per, n_pairs);
+            CK(cudaStreamWaitEvent(c->stream, c->copy_events[k], 0));
+            if (p1 > p0)
+                CKS(register_batch(c, c->b_src.as<float4>(), c->b_soff.as<int32_t>() + p0, c->b_tgt.as<float4>(), c->b_toff.as<int32_t>() + p0, p1 - p0,
+                                   max_n, max_m, opts, c->b_T.as<double>() + (size_t)p0 * 16, c->b_res.as<icp4r_result>() + p0));
+        }
+        CK(cudaMemcpyAsync(T_out, c->b_T.p, (size_t)n_pairs * 16 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(res, c->b_res.p, (size_t)n_pairs * sizeof(icp4r_result), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        return ICP4R_OK;
+    }
+    const void *dsrc = nullptr, *dtgt = nullptr, *dso = nullptr, *dto = nullptr;
     CKS(stage_in(c, c->b_src, src, ns * sizeof(float4), mem, &dsrc));
     CKS(stage_in(c, c->b_tgt, tgt, nt * sizeof(float4), mem, &dtgt));
     CKS(stage_in(c, c->b_soff, src_off, (size_t)(n_pairs + 1) * 4, mem, &dso));

@@ -170,6 +170,8 @@ struct Ctx {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr, own_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // host->device copies of large batched calls run ahead of the compute stream
+    cudaEvent_t copy_events[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     std::string err;
     int64_t launches = 0;
 

@@ -251,3 +251,30 @@ def test_non_finite_points_are_ignored(pkg, O, handle):
         T_map, r_map, _ = handle.register_map(src_bad, o)
         et, er = pose_err(T_map, T_ok)
         assert et <= 1e-9 and er <= 1e-9 and r_map.n_corr == r_ok.n_corr
+
+
+def test_large_host_batch_is_pipelined_and_equal(pkg, handle):
+    """host-resident batches above 32 MB are copied in chunks on a second stream while earlier chunks are registered;
+    the poses must equal the device-resident (single launch) path (to summation-order rounding: the per-pair counting
+    sort places points with shared-memory atomics), ragged pair sizes included"""
+    import torch
+    rng = np.random.default_rng(5)
+    base = [pkg.synth.frame_pair(300 + i, 2048) for i in range(8)]
+    n_pairs = 700
+    srcs, tgts = [], []
+    for p in range(n_pairs):
+        s, t, _ = base[p % 8]
+        cut_s, cut_t = 2048 - int(rng.integers(0, 64)), 2048 - int(rng.integers(0, 64))
+        srcs.append(s[:cut_s])
+        tgts.append(t[:cut_t])
+    so = np.concatenate([[0], np.cumsum([len(s) for s in srcs])]).astype(np.int32)
+    to = np.concatenate([[0], np.cumsum([len(t) for t in tgts])]).astype(np.int32)
+    S, T = np.concatenate(srcs), np.concatenate(tgts)
+    assert (S.nbytes + T.nbytes) > (32 << 20)
+    o = pkg.default_opts(residual=pkg.P2P_SVD, max_iterations=6)
+    Th, rh = handle.register_batch(S, so, T, to, o)
+    Td, rd = handle.register_batch(torch.from_numpy(S).cuda(), torch.from_numpy(so).cuda(), torch.from_numpy(T).cuda(), torch.from_numpy(to).cuda(), o)
+    handle.synchronize()  # device-resident calls are asynchronous on the handle's stream
+    assert np.allclose(Th.reshape(n_pairs, 16), Td.cpu().numpy(), rtol=0, atol=1e-10)
+    rdn = rd.cpu().numpy().view(pkg.api.RESULT_DTYPE).reshape(-1)
+    assert (rh["n_corr"] == rdn["n_corr"]).all() and (rh["iterations"] == rdn["iterations"]).all()
