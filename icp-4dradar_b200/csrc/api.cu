@@ -182,6 +182,8 @@ int icp4r_create(int device, icp4r_handle* out) {
     c->use_graph = !(ng && ng[0] == '1');
     const char* nh = std::getenv("ICP4R_NO_HINTS");
     c->use_hints = !(nh && nh[0] == '1');
+    const char* br = std::getenv("ICP4R_BATCH_REPRODUCIBLE");
+    c->batch_reproducible = br && br[0] == '1';
     *out = c;
     return ICP4R_OK;
 }

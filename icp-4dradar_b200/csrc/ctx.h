@@ -203,6 +203,7 @@ struct Ctx {
     int rank = 0, world = 1;
     DevBuf d_xch, d_xt, d_nbprev;
     DevBuf vg_keys, vg_vals, vg_sort, vg_tiles, vg_out;  // voxel-grid centroid filter
+    bool batch_reproducible = false;  // ICP4R_BATCH_REPRODUCIBLE=1 (see register_batch.cu)
     bool use_hints = true;  // ICP4R_NO_HINTS=1 turns the previous-iteration search bound off (A/B measurements)            // local exchange buffer and the peer table
     void* xch_peers[XCH_MAXW] = {nullptr};  // peer mappings opened with cudaIpcOpenMemHandle
     bool xch_ready = false;

@@ -253,11 +253,16 @@ def test_non_finite_points_are_ignored(pkg, O, handle):
         assert et <= 1e-9 and er <= 1e-9 and r_map.n_corr == r_ok.n_corr
 
 
-def test_large_host_batch_is_pipelined_and_equal(pkg, handle):
+def test_large_host_batch_is_pipelined_and_equal(pkg, monkeypatch):
     """host-resident batches above 32 MB are copied in chunks on a second stream while earlier chunks are registered;
-    the poses must equal the device-resident (single launch) path (to summation-order rounding: the per-pair counting
-    sort places points with shared-memory atomics), ragged pair sizes included"""
+    the poses must equal the device-resident (single launch) path — bit for bit with ICP4R_BATCH_REPRODUCIBLE=1 (the
+    source cloud is placed into its cells in index order), to summation-order rounding otherwise — ragged pair sizes
+    included"""
     import torch
+    monkeypatch.setenv("ICP4R_BATCH_REPRODUCIBLE", "1")
+    handle = pkg.Icp4r(0)
+    monkeypatch.delenv("ICP4R_BATCH_REPRODUCIBLE")
+    fast = pkg.Icp4r(0)
     rng = np.random.default_rng(5)
     base = [pkg.synth.frame_pair(300 + i, 2048) for i in range(8)]
     n_pairs = 700
@@ -275,6 +280,12 @@ def test_large_host_batch_is_pipelined_and_equal(pkg, handle):
     Th, rh = handle.register_batch(S, so, T, to, o)
     Td, rd = handle.register_batch(torch.from_numpy(S).cuda(), torch.from_numpy(so).cuda(), torch.from_numpy(T).cuda(), torch.from_numpy(to).cuda(), o)
     handle.synchronize()  # device-resident calls are asynchronous on the handle's stream
-    assert np.allclose(Th.reshape(n_pairs, 16), Td.cpu().numpy(), rtol=0, atol=1e-10)
+    assert np.array_equal(Th.reshape(n_pairs, 16), Td.cpu().numpy())
+    Th2, _ = handle.register_batch(S, so, T, to, o)
+    assert np.array_equal(Th, Th2)
+    Tf, _ = fast.register_batch(S, so, T, to, o)          # default placement: same poses up to summation order
+    assert np.allclose(Tf, Th, rtol=0, atol=1e-10)
+    handle.close()
+    fast.close()
     rdn = rd.cpu().numpy().view(pkg.api.RESULT_DTYPE).reshape(-1)
     assert (rh["n_corr"] == rdn["n_corr"]).all() and (rh["iterations"] == rdn["iterations"]).all()
