@@ -206,6 +206,11 @@ int icp4r_destroy(icp4r_handle h) {
     release(c->d_xch);
     release(c->d_xt);
     release(c->d_nbprev);
+    release(c->bf_part);
+    release(c->gs_pts);
+    release(c->gs_idx);
+    release(c->gs_d2);
+    release(c->gs_found);
     release(c->vg_keys);
     release(c->vg_vals);
     release(c->vg_sort);

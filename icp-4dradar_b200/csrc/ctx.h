@@ -202,6 +202,8 @@ struct Ctx {
     void* nccl_comm = nullptr;
     int rank = 0, world = 1;
     DevBuf d_xch, d_xt, d_nbprev;
+    DevBuf bf_part;                           // exhaustive k-NN: per-split partial lists
+    DevBuf gs_pts, gs_idx, gs_d2, gs_found;  // GICP: exhaustive k-NN scratch for the scan's own normals
     DevBuf vg_keys, vg_vals, vg_sort, vg_tiles, vg_out;  // voxel-grid centroid filter
     bool batch_reproducible = false;  // ICP4R_BATCH_REPRODUCIBLE=1 (see register_batch.cu)
     bool use_hints = true;  // ICP4R_NO_HINTS=1 turns the previous-iteration search bound off (A/B measurements)            // local exchange buffer and the peer table
@@ -223,6 +225,9 @@ int map_rebuild_grid(Ctx* c, Map& mp);  // (re)sort all valid points into the gr
 int map_append_incremental(Ctx* c, Map& mp, int n_new, bool* merged);  // merge pts[m, m+n_new) into the grid if it fits
 int grid_knn(Ctx* c, const Map& mp, const float4* q, int nq, int k, double max_dist, int32_t* idx, float* d2,
              int32_t* found);
+int brute_knn_cloud(Ctx* c, const float4* cloud_xyzi, int m, const float4* q, int nq, int k, double max_dist, int32_t* idx, float* d2,
+                    int32_t* found);
+int gicp_normals_small(Ctx* c, const float4* d_pts, int n, int k, DevBuf& normals);  // own-cloud k-NN normals without a grid
 int brute_knn(Ctx* c, const Map& mp, const float4* q, int nq, int k, double max_dist, int32_t* idx, float* d2,
               int32_t* found);
 void gate_params(double max_dist, float* gate_f, float* gate_r);

@@ -136,6 +136,85 @@ __global__ void __launch_bounds__(256) normals_kernel(GridDesc g, const float4* 
     }
 }
 
+// ---- small clouds (a scan): exhaustive k-NN instead of building a grid that is searched once ------------------------------
+__global__ void __launch_bounds__(256) stamp_index_kernel(const float4* __restrict__ pts, int n, float4* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = pts[i];
+    out[i] = make_float4(p.x, p.y, p.z, __int_as_float(i));
+}
+
+// same arithmetic, in the same order, as the parked part of normals_kernel: one thread per point
+template <int K>
+__global__ void __launch_bounds__(128) normals_from_idx_kernel(const float4* __restrict__ pts, const int32_t* __restrict__ idx,
+                                                               const int32_t* __restrict__ found_n, int n, int k, double* __restrict__ normals) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int found = found_n[i];
+    float nb[K][3];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        if (j < found) {
+            const float4 q = __ldg(pts + idx[(size_t)i * k + j]);
+            nb[j][0] = q.x;
+            nb[j][1] = q.y;
+            nb[j][2] = q.z;
+        } else {
+            nb[j][0] = nb[j][1] = nb[j][2] = 0.f;
+        }
+    }
+    double mean[3] = {0, 0, 0}, C[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        if (j < found) {
+            mean[0] += (double)nb[j][0];
+            mean[1] += (double)nb[j][1];
+            mean[2] += (double)nb[j][2];
+        }
+    }
+    const double fdiv = (double)(found > 0 ? found : 1);
+    mean[0] /= fdiv;
+    mean[1] /= fdiv;
+    mean[2] /= fdiv;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        if (j < found) {
+            const double d[3] = {(double)nb[j][0] - mean[0], (double)nb[j][1] - mean[1], (double)nb[j][2] - mean[2]};
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = 0; b < 3; ++b) C[3 * a + b] += d[a] * d[b];
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 9; ++a) C[a] /= (double)k;
+    double nrm[3];
+    smallest_eigvec3(C, nrm);
+    normals[3 * (size_t)i] = nrm[0];
+    normals[3 * (size_t)i + 1] = nrm[1];
+    normals[3 * (size_t)i + 2] = nrm[2];
+}
+
+int gicp_normals_small(Ctx* c, const float4* d_pts, int n, int k, DevBuf& normals) {
+    CKS(reserve_grow(c, normals, (size_t)std::max(n, 1) * 3 * sizeof(double)));
+    if (n <= 0) return ICP4R_OK;
+    CKS(reserve_grow(c, c->gs_pts, (size_t)n * sizeof(float4)));
+    CKS(reserve_grow(c, c->gs_idx, (size_t)n * k * sizeof(int32_t)));
+    CKS(reserve_grow(c, c->gs_d2, (size_t)n * k * sizeof(float)));
+    CKS(reserve_grow(c, c->gs_found, (size_t)n * sizeof(int32_t)));
+    stamp_index_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(d_pts, n, c->gs_pts.as<float4>());
+    c->launches += 1;
+    CKS(brute_knn_cloud(c, c->gs_pts.as<float4>(), n, d_pts, n, k, 0.0, c->gs_idx.as<int32_t>(), c->gs_d2.as<float>(), c->gs_found.as<int32_t>()));
+    double* out = normals.as<double>();
+    const int blocks = (n + 127) / 128;
+    if (k <= 5) normals_from_idx_kernel<5><<<blocks, 128, 0, c->stream>>>(d_pts, c->gs_idx.as<int32_t>(), c->gs_found.as<int32_t>(), n, k, out);
+    else if (k <= 8) normals_from_idx_kernel<8><<<blocks, 128, 0, c->stream>>>(d_pts, c->gs_idx.as<int32_t>(), c->gs_found.as<int32_t>(), n, k, out);
+    else normals_from_idx_kernel<16><<<blocks, 128, 0, c->stream>>>(d_pts, c->gs_idx.as<int32_t>(), c->gs_found.as<int32_t>(), n, k, out);
+    c->launches += 1;
+    CK(cudaGetLastError());
+    return ICP4R_OK;
+}
+
 int gicp_normals(Ctx* c, Map& mp, int k) {
     if (mp.normals_k == k) return ICP4R_OK;
     CKS(reserve_grow(c, mp.normals, (size_t)std::max(mp.m, 1) * 3 * sizeof(double)));

@@ -694,30 +694,36 @@ __global__ void __launch_bounds__(128) brute_merge_kernel(const uint64_t* __rest
 }
 
 template <int K>
-static int launch_brute(Ctx* c, const Map& mp, const float4* q, int nq, int k, float gate_f, int32_t* idx, float* d2,
+static int launch_brute(Ctx* c, const float4* sorted, int m, const float4* q, int nq, int k, float gate_f, int32_t* idx, float* d2,
                         int32_t* found) {
-    const int m = mp.grid.m;
     const int qblocks = (nq + BF_THREADS - 1) / BF_THREADS;
     int splits = std::max(1, std::min((c->sm_count * 4 + qblocks - 1) / qblocks, (m + BF_TILE - 1) / BF_TILE));
     splits = std::min(splits, 65535);
-    CKS(reserve(c, c->d_partials, (size_t)nq * splits * K * sizeof(uint64_t)));
-    uint64_t* part = c->d_partials.as<uint64_t>();
-    brute_knn_kernel<K><<<dim3(qblocks, splits), BF_THREADS, 0, c->stream>>>(mp.grid.sorted, m, q, nq, gate_f, splits, part);
+    // own scratch: d_partials is baked into captured registration loops and must never move
+    CKS(reserve_grow(c, c->bf_part, (size_t)nq * splits * K * sizeof(uint64_t)));
+    uint64_t* part = c->bf_part.as<uint64_t>();
+    brute_knn_kernel<K><<<dim3(qblocks, splits), BF_THREADS, 0, c->stream>>>(sorted, m, q, nq, gate_f, splits, part);
     brute_merge_kernel<K><<<(nq + 127) / 128, 128, 0, c->stream>>>(part, nq, splits, k, idx, d2, found);
     c->launches += 2;
     CK(cudaGetLastError());
     return ICP4R_OK;
 }
 
-int brute_knn(Ctx* c, const Map& mp, const float4* q, int nq, int k, double max_dist, int32_t* idx, float* d2, int32_t* found) {
+// exhaustive kNN of q over an arbitrary cloud whose w lanes carry the indices to report
+int brute_knn_cloud(Ctx* c, const float4* cloud_xyzi, int m, const float4* q, int nq, int k, double max_dist, int32_t* idx, float* d2,
+                    int32_t* found) {
     if (nq <= 0) return ICP4R_OK;
     float gf, gr;
     gate_params(max_dist, &gf, &gr);
-    if (k == 1) return launch_brute<1>(c, mp, q, nq, k, gf, idx, d2, found);
-    if (k == 2) return launch_brute<2>(c, mp, q, nq, k, gf, idx, d2, found);
-    if (k <= 5) return launch_brute<5>(c, mp, q, nq, k, gf, idx, d2, found);
-    if (k <= 8) return launch_brute<8>(c, mp, q, nq, k, gf, idx, d2, found);
-    return launch_brute<16>(c, mp, q, nq, k, gf, idx, d2, found);
+    if (k == 1) return launch_brute<1>(c, cloud_xyzi, m, q, nq, k, gf, idx, d2, found);
+    if (k == 2) return launch_brute<2>(c, cloud_xyzi, m, q, nq, k, gf, idx, d2, found);
+    if (k <= 5) return launch_brute<5>(c, cloud_xyzi, m, q, nq, k, gf, idx, d2, found);
+    if (k <= 8) return launch_brute<8>(c, cloud_xyzi, m, q, nq, k, gf, idx, d2, found);
+    return launch_brute<16>(c, cloud_xyzi, m, q, nq, k, gf, idx, d2, found);
+}
+
+int brute_knn(Ctx* c, const Map& mp, const float4* q, int nq, int k, double max_dist, int32_t* idx, float* d2, int32_t* found) {
+    return brute_knn_cloud(c, mp.grid.sorted, mp.grid.m, q, nq, k, max_dist, idx, d2, found);
 }
 
 // ------------------------------------------------------------------------------------------------ transform

@@ -856,19 +856,22 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
         const int kc = std::min(std::max(o->k > 0 ? o->k : 20, 3), ICP4R_MAX_K);
         CKS(gicp_normals(c, mp, kc));
         Map& sm = c->srcmap;
-        sm.m = 0;
-        sm.built = false;
-        sm.quick_build = true;  // only its own 5-NN is searched, once: a volume-estimated cell is good enough
-        sm.user_cell = 0.f;
-        sm.hint_cell = 0.f;
-        CKS(map_reserve(c, sm, n));
-        if (n > 0) {
+        if (n <= 8192) {
+            // a scan: exhaustive k-NN (n^2 distances, tens of microseconds) beats building a grid that is searched once
+            CKS(gicp_normals_small(c, d_src, n, kc, sm.normals));
+        } else {
+            sm.m = 0;
+            sm.built = false;
+            sm.quick_build = true;  // only its own 5-NN is searched, once: a volume-estimated cell is good enough
+            sm.user_cell = 0.f;
+            sm.hint_cell = 0.f;
+            CKS(map_reserve(c, sm, n));
             CK(cudaMemcpyAsync(sm.pts.p, d_src, (size_t)n * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
             CK(cudaMemsetAsync(sm.valid.p, 1, (size_t)n, c->stream));
+            sm.m = n;
+            CKS(map_rebuild_grid(c, sm));
+            CKS(gicp_normals(c, sm, kc));
         }
-        sm.m = n;
-        CKS(map_rebuild_grid(c, sm));
-        CKS(gicp_normals(c, sm, kc));
         CKS(reserve_grow(c, c->d_gicp_corr, (size_t)std::max(n, 1) * sizeof(GicpCorr)));
         P.src_normals = sm.normals.as<double>();
         P.tgt_normals = mp.normals.as<double>();
