@@ -108,6 +108,10 @@ const char* icp4r_version(void);
 int icp4r_default_opts(icp4r_opts* o);
 /* run on an existing cudaStream_t (e.g. the harness' current stream) instead of the handle's own */
 int icp4r_set_stream(icp4r_handle h, void* cuda_stream);
+/* Completion: every call that returns something in HOST memory (poses, results, counts, host output arrays) has
+ * finished when it returns. Outputs the caller asked for in DEVICE memory (mem = ICP4R_DEVICE: neighbour tables,
+ * transformed points, batched poses/results, dumps, filtered clouds) are ordered on the handle's stream: use them on
+ * that stream, or call icp4r_synchronize first. */
 int icp4r_synchronize(icp4r_handle h);
 /* number of kernels this handle has launched so far (graph-replayed kernels included) */
 int icp4r_launch_count(icp4r_handle h, int64_t* out);
