@@ -236,8 +236,10 @@ int map_rebuild_grid(Ctx* c, Map& mp) {
         // a growing map (odometry): leave room around the bounding box so that the next batches merge into this
         // grid instead of forcing a new sort; exactness never depends on the geometry
         const double emax_t = std::max(ext[0], std::max(ext[1], ext[2]));
+        const double cell_guess = mp.user_cell > 0.f ? (double)mp.user_cell : (mp.hint_cell > 0.f ? (double)mp.hint_cell : 0.005 * emax_t);
         for (int a = 0; a < 3; ++a) {
-            const double pad = std::max(0.15 * ext[a], 0.02 * emax_t);
+            // proportional to the axis' own extent (a ground vehicle's map grows in x and y, hardly in z), a few cells at least
+            const double pad = std::max(0.15 * ext[a], 4.0 * cell_guess);
             mn[a] = (float)((double)mn[a] - pad);
             mx[a] = (float)((double)mx[a] + pad);
             ext[a] = (double)mx[a] - (double)mn[a];
@@ -471,12 +473,16 @@ __global__ void __launch_bounds__(INC_THREADS) inc_merge_old_kernel(const float4
 // new point i (i-th in key order) lands behind the old points of its cell and the new ones before it
 __global__ void __launch_bounds__(256) inc_merge_new_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ nkeys,
                                                            const uint32_t* __restrict__ nvals, int nf, const uint32_t* __restrict__ cs_old,
-                                                           float4* __restrict__ sorted_new) {
+                                                           float4* __restrict__ sorted_new, GridDesc g, uint32_t* __restrict__ coarse) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nf) return;
     const uint32_t k = nkeys[i], idx = nvals[i];
     const float4 p = pts[idx];
     sorted_new[(uint32_t)i + cs_old[k + 1]] = make_float4(p.x, p.y, p.z, __uint_as_float(idx));
+    // the coarse occupancy table counts this point too (cheaper than recounting the whole table)
+    const uint32_t row = k / (uint32_t)g.nx, cx = k - row * (uint32_t)g.nx, cz = row / (uint32_t)g.ny, cy = row - cz * (uint32_t)g.ny;
+    const uint32_t cnx = (uint32_t)(g.nx + 7) >> 3, cny = (uint32_t)(g.ny + 7) >> 3;
+    atomicAdd(coarse + ((size_t)(cz >> 3) * cny + (cy >> 3)) * cnx + (cx >> 3), 1u);
 }
 
 // cell_start[c] += new points in cells < c (in place; runs after inc_merge_new_kernel has read the old table)
@@ -542,10 +548,9 @@ int map_append_incremental(Ctx* c, Map& mp, int n_new, bool* merged) {
         inc_bounds_old_kernel<<<(ob + 1 + 255) / 256, 256, 0, c->stream>>>(g.sorted, m_old, g, ks, nf, ob, bnd_old);
         inc_bounds_cell_kernel<<<(cb + 1 + 255) / 256, 256, 0, c->stream>>>(g.ncells, ks, nf, cb, bnd_cell);
         inc_merge_old_kernel<<<ob, INC_THREADS, 0, c->stream>>>(g.sorted, m_old, g, ks, bnd_old, s_new);
-        inc_merge_new_kernel<<<(nf + 255) / 256, 256, 0, c->stream>>>(mp.pts.as<float4>(), ks, vs, nf, g.cell_start, s_new);
+        inc_merge_new_kernel<<<(nf + 255) / 256, 256, 0, c->stream>>>(mp.pts.as<float4>(), ks, vs, nf, g.cell_start, s_new, g, mp.coarse.as<uint32_t>());
         inc_cell_kernel<<<cb, INC_THREADS, 0, c->stream>>>(mp.cell_start.as<uint32_t>(), g.ncells, ks, bnd_cell);
         c->launches += 5;
-        CKS(build_coarse(c, mp, mp.grid));
         CK(cudaGetLastError());
         tr.mark("inc merge");
         std::swap(mp.sorted, mp.sorted_alt);

@@ -144,6 +144,11 @@ def test_incremental_append_equals_fresh_build(handle, pkg):
                 assert handle.map_size() == fresh.map_size()
                 for a, w in zip(got, want):
                     assert (bits(a) == bits(w)).all(), b
+                # far, ungated queries go through the coarse occupancy table, which the merge updates in place
+                qf = q[:64].copy()
+                qf[:, 0] += 400.0
+                for a, w in zip(handle.map_knn(qf, 5, 0.0), fresh.map_knn(qf, 5, 0.0)):
+                    assert (bits(a) == bits(w)).all(), b
                 o = pkg.default_opts(residual=pkg.P2PLANE_KNN, k=5, max_iterations=4, max_corr_dist=2.0)
                 T1, r1, _ = handle.register_map(q, o)
                 T2, r2, _ = fresh.register_map(q, o)
