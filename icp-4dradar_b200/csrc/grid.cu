@@ -401,30 +401,68 @@ __global__ void inc_info_init(int* info) {
 // small batches (a radar / lidar frame): one block sorts the (key, index) pairs in shared memory. The pairs are
 // unique, so sorting the packed 64-bit words gives the stable order (ascending index inside a cell).
 constexpr int SB_MAX = 4096;
+// Bitonic network over 4096 packed words, 4 consecutive words per thread: strides 1 and 2 stay inside a thread, strides
+// 4..64 are lane exchanges (shuffles), only strides >= 128 go through shared memory (15 of the 78 steps).
+__device__ __forceinline__ unsigned long long cmpx(unsigned long long a, unsigned long long b, bool keep_min) {
+    return (a < b) == keep_min ? a : b;
+}
 __global__ void __launch_bounds__(1024) small_sort_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, int n,
                                                          uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
     __shared__ unsigned long long s[SB_MAX];
-    int np2 = 32;
-    while (np2 < n) np2 <<= 1;
-    for (int i = threadIdx.x; i < np2; i += 1024)
-        s[i] = i < n ? ((unsigned long long)keys[i] << 32) | vals[i] : ~0ull;
-    __syncthreads();
-    for (int k = 2; k <= np2; k <<= 1)
+    const int t = threadIdx.x;
+    unsigned long long e[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int i = 4 * t + r;
+        e[r] = i < n ? ((unsigned long long)keys[i] << 32) | vals[i] : ~0ull;
+    }
+    for (int k = 2; k <= SB_MAX; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = threadIdx.x; t < (np2 >> 1); t += 1024) {  // one compare-exchange per thread and trip
-                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
-                const unsigned long long a = s[i], b = s[l];
-                const bool up = (i & k) == 0;
-                if ((a > b) == up) {
-                    s[i] = b;
-                    s[l] = a;
+            if (j >= 128) {  // partner lives in another warp
+#pragma unroll
+                for (int r = 0; r < 4; ++r) s[4 * t + r] = e[r];
+                __syncthreads();
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int i = 4 * t + r;
+                    const unsigned long long o = s[i ^ j];
+                    e[r] = cmpx(e[r], o, ((i & j) == 0) == ((i & k) == 0));
+                }
+                __syncthreads();
+            } else if (j >= 4) {  // partner lane, same slot
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int i = 4 * t + r;
+                    const unsigned long long o = __shfl_xor_sync(FULL, e[r], j >> 2);
+                    e[r] = cmpx(e[r], o, ((i & j) == 0) == ((i & k) == 0));
+                }
+            } else {  // inside the thread
+                const bool asc = ((4 * t) & k) == 0;  // k >= 4 here or the 4-group shares the direction bit... see below
+                if (j == 2) {
+                    const bool a0 = k == 2 ? true : asc;  // k == 2 never has j == 2
+                    const unsigned long long x0 = e[0], x1 = e[1], x2 = e[2], x3 = e[3];
+                    e[0] = cmpx(x0, x2, a0);
+                    e[2] = cmpx(x2, x0, !a0);
+                    e[1] = cmpx(x1, x3, a0);
+                    e[3] = cmpx(x3, x1, !a0);
+                } else {  // j == 1: direction bit k may split the thread's four words when k == 2
+                    const bool a01 = ((4 * t + 0) & k) == 0, a23 = ((4 * t + 2) & k) == 0;
+                    const unsigned long long x0 = e[0], x1 = e[1], x2 = e[2], x3 = e[3];
+                    e[0] = cmpx(x0, x1, a01);
+                    e[1] = cmpx(x1, x0, !a01);
+                    e[2] = cmpx(x2, x3, a23);
+                    e[3] = cmpx(x3, x2, !a23);
                 }
             }
-            __syncthreads();
         }
-    for (int i = threadIdx.x; i < n; i += 1024) {
-        keys_out[i] = (uint32_t)(s[i] >> 32);
-        vals_out[i] = (uint32_t)s[i];
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int i = 4 * t + r;
+        if (i < n) {
+            keys_out[i] = (uint32_t)(e[r] >> 32);
+            vals_out[i] = (uint32_t)e[r];
+        }
     }
 }
 
