@@ -151,7 +151,7 @@ struct RegParams {  // kernel parameters that change per call; lives in device m
     const uint32_t* map_coarse;
     const float4* map_pts;
     int map_m;
-    // neighbours found at the previous iteration, K per source point (NULL: no hints — sharded maps, GICP)
+    // neighbours found at the previous iteration, K per source point (NULL: hints switched off)
     int32_t* nb_prev;
 };
 

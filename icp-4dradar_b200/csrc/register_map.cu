@@ -842,7 +842,7 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
         P.xt = c->d_xt.as<XchTable>();
     }
     const bool gicp = o->residual == ICP4R_GICP;
-    if (!gicp && c->use_hints) {
+    if (c->use_hints) {
         CKS(reserve_grow(c, c->d_nbprev, (size_t)n * ICP4R_MAX_K * sizeof(int32_t)));
         P.nb_prev = c->d_nbprev.as<int32_t>();
         // Sharded maps: a rank only refreshes the entries of the points it owns, so a point that changes owner finds
