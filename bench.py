@@ -224,7 +224,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5", "gicp"])
     ap.add_argument("--frames", type=int, default=2000, help="c3: frames of the odometry sequence (one step = the whole sequence)")
     ap.add_argument("--map-points", type=int, default=20_000_000, help="c5: points of the dense map (whole job)")
     ap.add_argument("--pairs", type=int, default=65536, help="c4: frame pairs per GPU per step")
@@ -295,6 +295,22 @@ def main():
                "batch_scans": POOL, "step": f"{POOL} independent scans registered in one icp4r_register_map_batch call "
                "(one scan alone is latency-bound and leaves most SMs idle; single-scan latency is in latency_ms_single)",
                "l2": "flushed before every timed step (256 MiB fill, untimed)", "replicas": world}
+    elif args.workload == "gicp":
+        # what radar_odometry.cpp:399-411 runs per frame: fast_gicp's cost (k = 5 covariances, LM, early exit, <= 64 iterations)
+        # for one 4,096-pt scan against the resident 200 k-pt map (target normals cached in the handle)
+        mp, scans = make_c2(1002)
+        h.map_build(mp)
+        o = pkg.default_opts(residual=pkg.GICP, k=K_NN, max_iterations=64, early_exit=1, max_corr_dist=0.0)
+        d_scans = [torch.from_numpy(s).to(dev) for s in scans]
+        pinned = [torch.from_numpy(s).pin_memory() for s in scans]
+        h_scans = [p.numpy() for p in pinned]
+        units_per_step = 1
+        queries_per_unit = 8 * N_SCAN   # ~8 outer iterations until the reference's convergence test fires
+        step_dev = lambda i: h.register_map(d_scans[i % POOL], o)
+        step_e2e = lambda i: h.register_map(h_scans[i % POOL], o)
+        h2d, d2h = N_SCAN * 16, 16 * 8 + 32
+        cfg = {"workload": "GICP scan-to-map: 4096-pt scan vs resident 200000-pt map, fast_gicp cost (k=5 covariances, LM), early exit, ungated",
+               "n": N_SCAN, "m": N_MAP, "k": K_NN, "max_iterations": 64, "l2": "flushed before every timed step (256 MiB fill, untimed)"}
     elif args.workload == "c3":
         # one step = the whole odometry sequence: Build on frame 0, then per frame register against the growing map,
         # transform with the estimated pose, Add_Points(false). value = frames/s (each frame is one registration).
@@ -422,7 +438,7 @@ def main():
                                 "kernel": "reg_iter_kernel<P2PLANE_KNN,5> (gridDim.y = 16 scans)", "kernel_ms": k_ms, "algorithmic_bytes": alg, "m_r": m_r,
                                 "peak_source": peak_src,
                                 "note": "working set (3.3 MB map + 1 MB scans) is L2-resident: issue/latency-bound, see DESIGN.md"}
-        elif args.workload in ("c5", "c3"):
+        elif args.workload in ("c5", "c3", "gicp"):
             line["roofline"] = None
         else:
             alg = args.pairs * (16 * 2 * C4_N + 64 + 160)
