@@ -111,23 +111,52 @@ __global__ void __launch_bounds__(RS_THREADS)
         rank[r] = prior + __popc(mask & lt);
     }
     __syncthreads();
-    {   // thread d: turn per-warp counts into per-warp global bases for digit d
-        uint32_t run = dbase[tid];
+    // Stage the tile in digit order through shared memory, then write it out: consecutive threads then hold
+    // consecutive elements of the same digit and their global writes are contiguous runs instead of a 32-way scatter.
+    __shared__ uint32_t toff[256];               // first tile-local slot of every digit
+    __shared__ uint32_t stage_k[RS_TILE], stage_v[RS_TILE];
+    {   // thread d: per-warp counts -> per-warp offsets inside digit d's run; the digit's tile count -> toff by a block scan
+        uint32_t run = 0;
 #pragma unroll
         for (int j = 0; j < RS_THREADS / 32; ++j) {
             const uint32_t t = whist[j][tid];
             whist[j][tid] = run;
             run += t;
         }
+        uint32_t x = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(FULL, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) wsum[w] = x;
+        __syncthreads();
+        uint32_t woff = 0;
+        for (int j = 0; j < w; ++j) woff += wsum[j];
+        toff[tid] = woff + x - run;
     }
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; ++r) {
         const int g = wbase + r * 32 + lane;
         if (g < n) {
-            const uint32_t pos = whist[w][(key[r] >> shift) & 255u] + rank[r];
-            keys_out[pos] = key[r];
-            vals_out[pos] = val[r];
+            const uint32_t dg = (key[r] >> shift) & 255u;
+            const uint32_t slot = toff[dg] + whist[w][dg] + rank[r];
+            stage_k[slot] = key[r];
+            stage_v[slot] = val[r];
+        }
+    }
+    __syncthreads();
+    const int tile_n = min(RS_TILE, n - tile * RS_TILE);
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        const int i = r * RS_THREADS + tid;
+        if (i < tile_n) {
+            const uint32_t k = stage_k[i];
+            const uint32_t dg = (k >> shift) & 255u;
+            const uint32_t pos = dbase[dg] + ((uint32_t)i - toff[dg]);
+            keys_out[pos] = k;
+            vals_out[pos] = stage_v[i];
         }
     }
 }
