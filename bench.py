@@ -475,6 +475,40 @@ def main():
             line["cpu_baseline"] = {"value": cnt / (time.perf_counter() - t0), "unit": "registrations/s", "cores": 1,
                                     "kind": "reference" if O.have_ref() else "port",
                                     "sample": f"{cnt} pairs, ikd-Tree Build + 30 x 1-NN + Kabsch each, one thread"}
+        elif world == 1 and not args.no_cpu_baseline and args.workload == "c3":
+            # the same loop on the host: the reference's ikd-Tree (Build, Add_Points(.., false), Nearest_Search on all
+            # threads) + the restated Gauss-Newton loop, on the first frames of the sequence (~20 s)
+            import oracle as O
+            threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+            oo = O.default_opts(residual=O.P2PLANE_KNN, k=K_NN, max_iterations=ITERS, max_corr_dist=GATE)
+            with quiet_c_stdout():
+                use_ref = O.have_ref()
+                T = np.eye(4)
+                w0, _ = O.transform(T, seq[0])
+                pts = [w0]
+                tree = None
+                if use_ref:
+                    tree = O.IkdTree(nthreads=threads)
+                    tree.build(w0)
+                t0 = time.perf_counter()
+                cnt = 0
+                for scan in seq[1:]:
+                    for i in range(16):
+                        oo.T0[i] = float(T.reshape(16)[i])
+                    T, _r, _ = O.register(scan, np.concatenate(pts), oo, searcher=tree)
+                    wv, _ = O.transform(T, scan)
+                    pts.append(wv)
+                    if tree is not None:
+                        tree.add_points(wv, False)
+                    cnt += 1
+                    if time.perf_counter() - t0 > 20.0:
+                        break
+                dt = time.perf_counter() - t0
+                if tree is not None:
+                    tree.close()
+            line["cpu_baseline"] = {"value": cnt / dt, "unit": "registrations/s", "cores": threads if use_ref else 1,
+                                    "kind": "reference" if use_ref else "port",
+                                    "sample": f"first {cnt} frames of the sequence (map still small: the reference slows down as the tree grows)"}
         print(json.dumps(line), flush=True)
     h.close()
     if world > 1:
