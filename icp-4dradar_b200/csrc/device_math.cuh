@@ -113,70 +113,6 @@ __device__ inline void mat4_mul(const double A[16], const double B[16], double C
     for (int i = 0; i < 16; ++i) C[i] = R[i];
 }
 
-// Kabsch rotation from the 3x3 cross-covariance H = sum (p - pm)(q - qm)^T by one-sided Jacobi SVD
-// (H V = U S), R = V U^T with the smallest-singular-value column rebuilt by cross products so that
-// det R = +1 (the Umeyama reflection fix of pcl::umeyama).
-static __device__ __noinline__ void svd3_rotation(const double H[9], double R[9]) {
-    double A[9], V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-    for (int i = 0; i < 9; ++i) A[i] = H[i];
-    for (int sweep = 0; sweep < 30; ++sweep) {
-        double off = 0.0;
-        for (int p = 0; p < 2; ++p)
-            for (int q = p + 1; q < 3; ++q) {
-                double al = 0, be = 0, ga = 0;
-                for (int i = 0; i < 3; ++i) {
-                    al += A[3 * i + p] * A[3 * i + p];
-                    be += A[3 * i + q] * A[3 * i + q];
-                    ga += A[3 * i + p] * A[3 * i + q];
-                }
-                if (fabs(ga) <= 1e-300) continue;
-                if (fabs(ga) <= 1e-16 * sqrt(al * be)) continue;
-                off += fabs(ga);
-                const double zeta = (be - al) / (2.0 * ga);
-                const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
-                for (int i = 0; i < 3; ++i) {
-                    const double ap = A[3 * i + p], aq = A[3 * i + q];
-                    A[3 * i + p] = c * ap - s * aq;
-                    A[3 * i + q] = s * ap + c * aq;
-                    const double vp = V[3 * i + p], vq = V[3 * i + q];
-                    V[3 * i + p] = c * vp - s * vq;
-                    V[3 * i + q] = s * vp + c * vq;
-                }
-            }
-        if (off == 0.0) break;
-    }
-    double sg[3];
-    for (int j = 0; j < 3; ++j) sg[j] = sqrt(A[j] * A[j] + A[3 + j] * A[3 + j] + A[6 + j] * A[6 + j]);
-    int c = 0;
-    if (sg[1] < sg[c]) c = 1;
-    if (sg[2] < sg[c]) c = 2;
-    const int a = (c + 1) % 3, b = (c + 2) % 3;
-    if (!(sg[a] > 0.0) || !(sg[b] > 0.0)) {
-        for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
-        return;
-    }
-    double ua[3], ub[3], uc[3], va[3], vb[3], vc[3];
-    for (int i = 0; i < 3; ++i) {
-        ua[i] = A[3 * i + a] / sg[a];
-        ub[i] = A[3 * i + b] / sg[b];
-        va[i] = V[3 * i + a];
-        vb[i] = V[3 * i + b];
-    }
-    const double dab = ua[0] * ub[0] + ua[1] * ub[1] + ua[2] * ub[2];
-    double nb = 0;
-    for (int i = 0; i < 3; ++i) {
-        ub[i] -= dab * ua[i];
-        nb += ub[i] * ub[i];
-    }
-    nb = sqrt(nb);
-    for (int i = 0; i < 3; ++i) ub[i] /= nb;
-    cross3(ua, ub, uc);
-    cross3(va, vb, vc);
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) R[3 * i + j] = va[i] * ua[j] + vb[i] * ub[j] + vc[i] * uc[j];
-}
-
 __device__ __forceinline__ int tri6(int i, int j) { return i * 6 - i * (i - 1) / 2 + (j - i); }
 
 // H x = -g, H symmetric positive definite given as its 21-entry upper triangle; returns 0 on success
@@ -321,54 +257,6 @@ __device__ __forceinline__ bool plane_fit(const F (&P)[K][3], int k, double n[3]
     n[1] = sgn * uy * iu;
     n[2] = sgn * uz * iu;
     d = fabs(det) * iu;                          // 1 / |u / det|
-    return true;
-}
-
-// LidarPlaneNormFactor (radarFactor.hpp:122): r = n.p' + d, J = [(p' x n)^T | n^T]
-template <int K>
-__device__ __forceinline__ bool contrib_p2plane(double* acc, const double pw[3], const double (&P)[K][3], int k,
-                                                double plane_thresh) {
-    double n[3], d;
-    if (!plane_fit<K, double>(P, k, n, d)) return false;
-#pragma unroll
-    for (int j = 0; j < K; ++j) {
-        if (j < k) {
-            const double e = ((n[0] * P[j][0] + n[1] * P[j][1]) + n[2] * P[j][2]) + d;
-            if (!(fabs(e) <= plane_thresh)) return false;
-        }
-    }
-    const double r = ((n[0] * pw[0] + n[1] * pw[1]) + n[2] * pw[2]) + d;
-    double pxn[3];
-    cross3(pw, n, pxn);
-    const double J[6] = {pxn[0], pxn[1], pxn[2], n[0], n[1], n[2]};
-    acc_gn(acc, J, r);
-    acc[28] += 1.0;
-    return true;
-}
-
-// RadarEdgeFactor (radarFactor.hpp:34-39), s = 1: r = ((p'-a) x (p'-b)) / |a-b|
-__device__ __forceinline__ bool contrib_p2line(double* acc, const double pw[3], const double a[3], const double b[3]) {
-    const double ba[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
-    const double L = sqrt((ba[0] * ba[0] + ba[1] * ba[1]) + ba[2] * ba[2]);
-    if (!(L > 0.0)) return false;
-    const double u[3] = {pw[0] - a[0], pw[1] - a[1], pw[2] - a[2]};
-    const double v[3] = {pw[0] - b[0], pw[1] - b[1], pw[2] - b[2]};
-    double nu[3];
-    cross3(u, v, nu);
-    const double e[3] = {ba[0] / L, ba[1] / L, ba[2] / L};
-    const double D[9] = {0, -e[2], e[1], e[2], 0, -e[0], -e[1], e[0], 0};
-    const double Px[9] = {0, pw[2], -pw[1], -pw[2], 0, pw[0], pw[1], -pw[0], 0};
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        double J[6];
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            J[j] = (D[3 * i] * Px[j] + D[3 * i + 1] * Px[3 + j]) + D[3 * i + 2] * Px[6 + j];
-            J[3 + j] = D[3 * i + j];
-        }
-        acc_gn(acc, J, nu[i] / L);
-    }
-    acc[28] += 1.0;
     return true;
 }
 

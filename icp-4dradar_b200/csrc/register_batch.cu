@@ -476,44 +476,7 @@ __global__ void __launch_bounds__(RB_THREADS, 2) reg_batch_kernel(const __grid_c
                 double Tc[16], D[16];
                 const bool last = (it == P.max_iterations - 1);
                 for (int i = 0; i < 16; ++i) Tc[i] = s_T[i];
-                if (KIND == ICP4R_P2P_SVD) {
-                    const double cnt = s_tot[0];
-                    s_flags[3] = (int)cnt;
-                    if (cnt < 3.0) {
-                        s_flags[0] = 1;
-                        s_flags[1] = 0;
-                        s_flags[2] = it;
-                    } else {
-                        double pm[3], qm[3], H[9], R[9];
-                        for (int i = 0; i < 3; ++i) {
-                            pm[i] = s_tot[1 + i] / cnt;
-                            qm[i] = s_tot[4 + i] / cnt;
-                        }
-                        for (int i = 0; i < 3; ++i)
-                            for (int j = 0; j < 3; ++j) H[3 * i + j] = s_tot[7 + 3 * i + j] / cnt - pm[i] * qm[j];
-                        svd3_rotation(H, R);
-                        for (int i = 0; i < 3; ++i) {
-                            D[4 * i + 0] = R[3 * i + 0];
-                            D[4 * i + 1] = R[3 * i + 1];
-                            D[4 * i + 2] = R[3 * i + 2];
-                            D[4 * i + 3] = qm[i] - ((R[3 * i] * pm[0] + R[3 * i + 1] * pm[1]) + R[3 * i + 2] * pm[2]);
-                        }
-                        D[12] = D[13] = D[14] = 0;
-                        D[15] = 1;
-                        const double mse = s_tot[16] / cnt;
-                        s_misc[1] = mse;
-                        mat4_mul(D, Tc, Tc);
-                        for (int i = 0; i < 16; ++i) s_T[i] = Tc[i];
-                        if (P.early_exit) {
-                            if (fabs(mse - s_misc[0]) < P.mse_abs_eps) {
-                                s_flags[0] = 1;
-                                s_flags[1] = 1;
-                                s_flags[2] = it + 1;
-                            }
-                            s_misc[0] = mse;
-                        }
-                    }
-                } else {
+                {  // Gauss-Newton form: 6x6 Cholesky + SE(3) exponential by one thread (the headline kind is P2P_SVD, above)
                     const double cnt = s_tot[28];
                     s_flags[3] = (int)cnt;
                     double xi[6];
