@@ -615,6 +615,11 @@ int icp4r_register(icp4r_handle h, const float* src, int32_t n, const float* tgt
     mp.built = false;
     mp.user_cell = 0.f;
     mp.hint_cell = 0.f;
+    {   // a small target that serves one registration: the volume-estimated cell is good enough, the occupancy-based
+        // refinement (a device round trip and up to two more sorts) costs more than it saves
+        const char* e = std::getenv("ICP4R_TMP_REFINE");
+        mp.quick_build = m <= 16384 && !(e && e[0] == '1');
+    }
     CKS(set_points(c, mp, tgt, m, mem, 0));
     mp.m = m;
     CKS(map_rebuild_grid(c, mp));
