@@ -77,21 +77,29 @@ def make_c5(m, seed=1005):
     return mp, scans
 
 
-def make_c4(n_pairs, seed=1004):
+def make_c4(n_pairs, seed=1004, with_offsets=False):
     """n_pairs frame pairs of 2,048 points: 64 distinct scenes, each re-used with a different rigid offset of the
-    source (generating 65,536 scenes on the host would dominate the run)."""
+    source (generating 65,536 scenes on the host would dominate the run). with_offsets: also return those offsets
+    [n_pairs,4,4] (identity for the first 64 pairs)."""
     from icp4r_loader import pkg
     s = pkg.synth
     base = [s.frame_pair(seed + i, C4_N) for i in range(64)]
     rng = np.random.default_rng(seed)
     src = np.empty((n_pairs * C4_N, 4), np.float32)
     tgt = np.empty((n_pairs * C4_N, 4), np.float32)
+    D = np.tile(np.eye(4), (n_pairs, 1, 1)) if with_offsets else None
     for p in range(n_pairs):
         a, b, _ = base[p % 64]
-        src[p * C4_N:(p + 1) * C4_N] = s.apply(s.random_small_se3(rng, 0.3, 2.0), a) if p >= 64 else a
+        if p >= 64:
+            Dp = s.random_small_se3(rng, 0.3, 2.0)
+            src[p * C4_N:(p + 1) * C4_N] = s.apply(Dp, a)
+            if with_offsets:
+                D[p] = Dp
+        else:
+            src[p * C4_N:(p + 1) * C4_N] = a
         tgt[p * C4_N:(p + 1) * C4_N] = b
     off = (np.arange(n_pairs + 1) * C4_N).astype(np.int32)
-    return src, tgt, off
+    return (src, tgt, off, D) if with_offsets else (src, tgt, off)
 
 
 class ClockSampler:
