@@ -63,3 +63,18 @@ def test_product_never_touches_oracle():
                 if re.search(r"\bimport oracle\b|from oracle\b|oracle/|liboracle|libikd_ref|orc_", s):
                     bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_header_is_plain_c_and_cxx(tmp_path):
+    """include/icp4r.h must be consumable from C (the boundary is a C ABI) and from the C++ adapters"""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc", path="/usr/bin") or shutil.which("gcc")
+    gxx = shutil.which("g++", path="/usr/bin") or shutil.which("g++")
+    if not gcc or not gxx:
+        pytest.skip("no host compiler")
+    src = tmp_path / "use_header.c"
+    src.write_text('#include "icp4r.h"\nint main(void) { icp4r_opts o; icp4r_result r; (void)o; (void)r; return (int)sizeof(icp4r_dump) * 0; }\n')
+    inc = os.path.join(ROOT, "include")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc, str(src)], check=True)
+    subprocess.run([gxx, "-std=c++11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc, "-x", "c++", str(src)], check=True)
