@@ -7,10 +7,25 @@
 // Kabsch/Umeyama in fp64 (or the 6x6 Gauss-Newton form of LidarDistanceFactor, radarFactor.hpp:140-171).
 //
 // Per pair: (1) bounding box + cell geometry of the target, (2) counting sort of the target into cell order
-// inside shared memory, (3) max_iterations x { thread-per-point 1-NN by cube-shell expansion over the
-// shared-memory grid, fp64 accumulators in registers, shuffle + shared-memory reduction in a fixed order,
-// one thread solves and updates the pose }, (4) fitness pass.
+// inside shared memory (and of the source, by the target cell it starts in), (3) max_iterations x { the exact 1-NN of
+// every source point, fp64 accumulators in registers, shuffle + shared-memory reduction in a fixed order, one warp
+// solves and updates the pose }, (4) fitness pass.
+//
+// How the exact 1-NN is kept cheap over the 30 iterations (all of it exact: the answer is always the one an exhaustive
+// search with the (d2, index) order would give):
+//   * every source point remembers its previous neighbour h and a lower bound LB on its distance to every OTHER target
+//     point. A pose update moves the point by delta, so the other points are now at least LB - delta away, and if
+//     |q - h| < LB - delta the old neighbour is still the unique nearest one: no search at all. One uniform pass over
+//     the cloud (32 of 32 lanes active, no loops) settles most points this way once the pose increments get small.
+//   * the points that fail the test are compacted, in order, into a per-warp list and searched: all cells that the box
+//     [q - |q - h|, q + |q - h|] touches (it contains the ball in which a better neighbour would have to lie). The same
+//     pass yields the new LB = min(distance of the runner-up, distance from q to the nearest face of that cell box that
+//     has unvisited cells behind it).
+//   * without a previous neighbour (first iteration, or nothing inside the gate last time): cube-shell expansion around
+//     the query's cell with the running best pruning rows and x-extents.
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "ctx.h"
@@ -19,8 +34,6 @@
 
 namespace icp4r {
 
-constexpr int RB_THREADS = 256;
-constexpr int RB_WARPS = RB_THREADS / 32;
 constexpr int RB_MAXC = 4096;  // cells per pair
 
 struct BatchParams {
@@ -31,6 +44,7 @@ struct BatchParams {
     int n_pairs, max_n, max_m;
     int max_iterations, early_exit;
     float cell_pts;  // target points per cell (by volume) of the per-pair grid
+    float slack;     // extra radius of the bounded search, in cells (a wider box costs candidates and buys a larger LB)
     int reproducible;  // place the source in index order (bit-reproducible sums) instead of with atomics (2.4 % faster)
     int use_hints;  // previous-iteration neighbour kept per source point (16-bit slot: needs max_m < 65535)
     float gate_f, gate_r;
@@ -49,55 +63,69 @@ __device__ __forceinline__ int cell_of_s(float v, float o, float inv, int dim) {
     return (int)f;
 }
 
-// exact 1-NN of (qx,qy,qz) over the shared-memory grid; returns the packed key and the slot of the winner
-__device__ __forceinline__ uint64_t thread_grid_nn(const PairGrid& g, const float4* __restrict__ s_tgt,
-                                                   const uint32_t* __restrict__ cs, float qx, float qy, float qz, float gate_f,
-                                                   float gate_r, int& best_pos, int hint_pos = -1) {
-    const float qmax = fmaxf(fabsf(qx), fmaxf(fabsf(qy), fabsf(qz)));
-    const float margin = fmaxf(g.margin, 9.5367431640625e-7f * qmax);
-    if (hint_pos >= 0) {
-        // The point that was nearest at the previous pose bounds the distance of the nearest one now: start from it
-        // and look only at the cells the ball of that radius touches (rows and x-extents shrink with the running
-        // best). Same answer as the shell search below — every point at most that far away is visited.
-        const float4 h = s_tgt[hint_pos];
-        const float hd = dist2_exact(qx, qy, qz, h.x, h.y, h.z);
-        if (hd <= gate_f) {  // false for NaN; a hint outside the gate falls through to the plain search
-            float best_d = hd;
-            int best_i = __float_as_int(h.w);
-            best_pos = hint_pos;
-            const float r = sqrtf(hd) * 1.000001f + margin;
-            const int y0 = cell_of_s(qy - r, g.oy, g.inv_cell, g.ny), y1 = cell_of_s(qy + r, g.oy, g.inv_cell, g.ny);
-            const int z0 = cell_of_s(qz - r, g.oz, g.inv_cell, g.nz), z1 = cell_of_s(qz + r, g.oz, g.inv_cell, g.nz);
-            for (int z = z0; z <= z1; ++z)
-                for (int y = y0; y <= y1; ++y) {
-                    const float ylo = g.oy + (float)y * g.cell, zlo = g.oz + (float)z * g.cell;
-                    float ddy = fmaxf(fmaxf(ylo - qy, qy - (ylo + g.cell)), 0.0f);  // distance to the row's y / z slab
-                    float ddz = fmaxf(fmaxf(zlo - qz, qz - (zlo + g.cell)), 0.0f);
-                    ddy = fmaxf(ddy - margin, 0.0f);
-                    ddz = fmaxf(ddz - margin, 0.0f);
-                    const float dyz2 = (ddy * ddy + ddz * ddz) * 0.999999f;
-                    const float kd = best_d * 1.000001f;
-                    if (dyz2 > kd) continue;
-                    const float xr = sqrtf(kd - dyz2) * 1.000001f + margin;
-                    const int xa = cell_of_s(qx - xr, g.ox, g.inv_cell, g.nx), xb = cell_of_s(qx + xr, g.ox, g.inv_cell, g.nx);
-                    const int rowbase = (z * g.ny + y) * g.nx;
-                    const uint32_t s = cs[rowbase + xa], e = cs[rowbase + xb + 1];
-                    for (uint32_t j = s; j < e; ++j) {
-                        const float4 c = s_tgt[j];
-                        const float d = dist2_exact(qx, qy, qz, c.x, c.y, c.z);
-                        if (d <= best_d) {
-                            const int ci = __float_as_int(c.w);
-                            if (d < best_d || ci < best_i) {
-                                best_d = d;
-                                best_i = ci;
-                                best_pos = (int)j;
-                            }
-                        }
-                    }
-                }
-            return pack_key(best_d, best_i);
+// Bounded exact 1-NN: `hd` = squared distance of a known target point (the previous neighbour, at slot hint_pos), so
+// the nearest point lies in the closed ball of that radius. Every point of every cell the enclosing box touches is
+// looked at — no pruning, the loop body is load / distance / compare — and the second smallest distance seen plus the
+// distance to the faces of the visited cell box bound every other target point from below (`lb`, metres).
+__device__ __forceinline__ uint64_t thread_box_nn(const PairGrid& g, const float4* __restrict__ s_tgt, const uint32_t* __restrict__ cs,
+                                                  float qx, float qy, float qz, float gate_f, float margin, float hd, float slack,
+                                                  int& best_pos, float& lb) {
+    const float r = sqrtf(hd) * 1.000001f + margin + slack;
+    const int xa = cell_of_s(qx - r, g.ox, g.inv_cell, g.nx), xb = cell_of_s(qx + r, g.ox, g.inv_cell, g.nx);
+    const int y0 = cell_of_s(qy - r, g.oy, g.inv_cell, g.ny), y1 = cell_of_s(qy + r, g.oy, g.inv_cell, g.ny);
+    const int z0 = cell_of_s(qz - r, g.oz, g.inv_cell, g.nz), z1 = cell_of_s(qz + r, g.oz, g.inv_cell, g.nz);
+    float best_d = INFINITY, second = INFINITY;
+    int best_i = 0x7fffffff;
+    best_pos = -1;
+    for (int z = z0; z <= z1; ++z) {
+        int rowbase = (z * g.ny + y0) * g.nx;
+        for (int y = y0; y <= y1; ++y, rowbase += g.nx) {
+            const uint32_t s = cs[rowbase + xa], e = cs[rowbase + xb + 1];
+            for (uint32_t j = s; j < e; ++j) {
+                const float4 c = s_tgt[j];
+                const float d = dist2_exact(qx, qy, qz, c.x, c.y, c.z);
+                const int ci = __float_as_int(c.w);
+                // the loser of (running best, candidate) competes for second place; fminf drops a NaN
+                const bool better = d <= gate_f && (d < best_d || (d == best_d && ci < best_i));  // false for NaN
+                second = fminf(second, better ? best_d : d);
+                best_d = better ? d : best_d;
+                best_i = better ? ci : best_i;
+                best_pos = better ? (int)j : best_pos;
+            }
         }
     }
+    // faces of the visited cell box with cells behind them (the grid spans the target's bounding box: nothing lies outside)
+    float bd = 3.4e38f;
+    if (xa > 0) bd = fminf(bd, qx - (g.ox + (float)xa * g.cell));
+    if (xb < g.nx - 1) bd = fminf(bd, (g.ox + (float)(xb + 1) * g.cell) - qx);
+    if (y0 > 0) bd = fminf(bd, qy - (g.oy + (float)y0 * g.cell));
+    if (y1 < g.ny - 1) bd = fminf(bd, (g.oy + (float)(y1 + 1) * g.cell) - qy);
+    if (z0 > 0) bd = fminf(bd, qz - (g.oz + (float)z0 * g.cell));
+    if (z1 < g.nz - 1) bd = fminf(bd, (g.oz + (float)(z1 + 1) * g.cell) - qz);
+    lb = fmaxf(fminf(sqrtf(second) * 0.999999f, bd - 2.0f * margin), 0.0f);
+#ifdef ICP4R_RB_VERIFY
+    {
+        float sd = INFINITY;
+        int sp = -1;
+        const int mv = (int)cs[g.ncells];
+        for (int j = 0; j < mv; ++j) {
+            if (j == best_pos) continue;
+            const float4 c = s_tgt[j];
+            const float d = dist2_exact(qx, qy, qz, c.x, c.y, c.z);
+            if (d < sd) sd = d, sp = j;
+        }
+        if (lb > sqrtf(sd))
+            printf("RB_BOX block=%d best=%d second=%g bd=%g lb=%g true2=%g at %d | hd=%g r=%g box x %d..%d y %d..%d z %d..%d | dims %d %d %d cell %g o %g %g %g | cs[row y0]=%u..%u\n",
+                   blockIdx.x, best_pos, second, bd, lb, sd, sp, hd, r, xa, xb, y0, y1, z0, z1, g.nx, g.ny, g.nz, g.cell, g.ox, g.oy, g.oz,
+                   cs[(z0 * g.ny + y0) * g.nx + xa], cs[(z0 * g.ny + y0) * g.nx + xb + 1]);
+    }
+#endif
+    return best_pos >= 0 ? pack_key(best_d, best_i) : KEY_EMPTY;
+}
+
+// exact 1-NN of (qx,qy,qz) over the shared-memory grid without prior knowledge; returns the packed key and the slot
+__device__ __forceinline__ uint64_t thread_shell_nn(const PairGrid& g, const float4* __restrict__ s_tgt, const uint32_t* __restrict__ cs,
+                                                    float qx, float qy, float qz, float gate_f, float gate_r, float margin, int& best_pos) {
     const int cx = cell_of_s(qx, g.ox, g.inv_cell, g.nx);
     const int cy = cell_of_s(qy, g.oy, g.inv_cell, g.ny);
     const int cz = cell_of_s(qz, g.oz, g.inv_cell, g.nz);
@@ -180,12 +208,42 @@ __device__ __forceinline__ uint64_t thread_grid_nn(const PairGrid& g, const floa
         const float b = bound - margin;
         if (b > 0.0f && best_pos >= 0 && best_d < b * b * 0.99999905f) break;
     }
-    const uint64_t best = best_pos >= 0 ? pack_key(best_d, best_i) : KEY_EMPTY;
-    return best;
+    return best_pos >= 0 ? pack_key(best_d, best_i) : KEY_EMPTY;
 }
 
-template <int NV>
-__device__ __forceinline__ void block_reduce(double (&acc)[NV], double* s_red /*[RB_WARPS][32]*/, double* s_tot, int tid) {
+#ifdef ICP4R_RB_VERIFY
+// debug build only: exhaustive check of one answer
+__device__ __noinline__ void rb_verify(const float4* s_tgt, int max_m, int mvalid, float qx, float qy, float qz, float gate_f, int pos, int how,
+                                       int i, float lb, float delta) {
+    float bd = INFINITY;
+    int bi = 0x7fffffff, bp = -1;
+    for (int j = 0; j < mvalid; ++j) {
+        const float4 c = s_tgt[j];
+        const float d = dist2_exact(qx, qy, qz, c.x, c.y, c.z);
+        const int ci = __float_as_int(c.w);
+        if (d <= gate_f && (d < bd || (d == bd && ci < bi))) {
+            bd = d;
+            bi = ci;
+            bp = j;
+        }
+    }
+    if (how == 2) {  // is lb really a lower bound on every other point?
+        float sd = INFINITY;
+        int sp = -1;
+        for (int j = 0; j < mvalid; ++j) {
+            if (j == bp) continue;
+            const float4 c = s_tgt[j];
+            const float d = dist2_exact(qx, qy, qz, c.x, c.y, c.z);
+            if (d < sd) sd = d, sp = j;
+        }
+        if (lb > sqrtf(sd)) printf("RB_VERIFY bad lb block=%d i=%d best=%d (r %g) runner-up=%d at %g but lb=%g q=(%g %g %g)\n", blockIdx.x, i, bp, sqrtf(bd), sp, sqrtf(sd), lb, qx, qy, qz);
+    }
+    if (bp != pos) printf("RB_VERIFY mismatch how=%d block=%d i=%d got=%d want=%d (d2 want %g) lb=%g delta=%g\n", how, blockIdx.x, i, pos, bp, bd, lb, delta);
+}
+#endif
+
+template <int NV, int NW>
+__device__ __forceinline__ void block_reduce(double (&acc)[NV], double* s_red /*[NW][32]*/, double* s_tot, int tid) {
     const int lane = tid & 31, w = tid >> 5;
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
@@ -198,27 +256,141 @@ __device__ __forceinline__ void block_reduce(double (&acc)[NV], double* s_red /*
     if (tid < NV) {
         double s = 0.0;
 #pragma unroll
-        for (int j = 0; j < RB_WARPS; ++j) s += s_red[j * 32 + tid];
+        for (int j = 0; j < NW; ++j) s += s_red[j * 32 + tid];
         s_tot[tid] = s;
     }
     __syncthreads();
 }
 
-template <int KIND>
-__global__ void __launch_bounds__(RB_THREADS, 2) reg_batch_kernel(const __grid_constant__ BatchParams P, double* __restrict__ T_out,
-                                                                  icp4r_result* __restrict__ res) {
+// contribution of one correspondence; FIT: {count, sum d2}
+template <int KIND, bool FIT, int NV>
+__device__ __forceinline__ void add_corr(double (&acc)[NV], int& cnt, const double pw[3], const float4& c, float d2) {
+    ++cnt;
+    if (FIT) {
+        acc[1] += (double)d2;
+    } else if (KIND == ICP4R_P2P_SVD) {
+        const double q[3] = {(double)c.x, (double)c.y, (double)c.z};
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            acc[1 + i] += pw[i];
+            acc[4 + i] += q[i];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) acc[7 + 3 * i + j] = fma(pw[i], q[j], acc[7 + 3 * i + j]);
+        }
+        acc[16] += (double)d2;
+    } else {
+        contrib_p2p_gn(acc, pw, c.x, c.y, c.z);  // counts in acc[28] itself
+    }
+}
+
+// One pass over the source cloud of the pair (an iteration, or the fitness pass): warp w owns the contiguous slice
+// [w * chunk, (w + 1) * chunk) of the cell-sorted source, so there is no block barrier between the two phases.
+template <int KIND, bool FIT, int NV>
+__device__ __forceinline__ void pair_pass(const PairGrid& g, const float4* __restrict__ s_tgt, float4* __restrict__ s_src,
+                                          const uint32_t* __restrict__ s_cs, unsigned short* __restrict__ s_prev,
+                                          unsigned short* __restrict__ s_list, const double* __restrict__ s_T, const float* __restrict__ s_dA,
+                                          const BatchParams& P, int n, int chunk, bool have_prev, double (&acc)[NV], int lane, int w) {
+    const int beg = min(n, w * chunk), end = min(n, beg + chunk);
+    unsigned short* list = s_list + beg;
+    int nl = 0, cnt = 0;
+    double T[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) T[i] = s_T[i];
+    const unsigned lt = (1u << lane) - 1u;
+    const float slack = P.slack * g.cell;
+    // ---- phase 1: is the previous neighbour provably still the nearest one? ------------------------------------
+    for (int i0 = beg; i0 < end; i0 += 32) {
+        const int i = i0 + lane;
+        bool need = i < end;
+        if (need && have_prev) {
+            const int hp = (int)s_prev[i];
+            if (hp != 0xFFFF) {
+                const float4 p = s_src[i];
+                double pw[3];
+                xform_point(T, p.x, p.y, p.z, pw);
+                const float qx = (float)pw[0], qy = (float)pw[1], qz = (float)pw[2];
+                const float margin = fmaxf(g.margin, 9.5367431640625e-7f * fmaxf(fabsf(qx), fmaxf(fabsf(qy), fabsf(qz))));
+                const float4 h = s_tgt[hp];
+                const float d = dist2_exact(qx, qy, qz, h.x, h.y, h.z);
+                // how far the last pose increment D moved this point: q - D^-1 q = (I - R^T) q + R^T t
+                const float ex = __fmaf_rn(s_dA[0], qx, __fmaf_rn(s_dA[1], qy, __fmaf_rn(s_dA[2], qz, s_dA[3])));
+                const float ey = __fmaf_rn(s_dA[4], qx, __fmaf_rn(s_dA[5], qy, __fmaf_rn(s_dA[6], qz, s_dA[7])));
+                const float ez = __fmaf_rn(s_dA[8], qx, __fmaf_rn(s_dA[9], qy, __fmaf_rn(s_dA[10], qz, s_dA[11])));
+                const float delta = sqrtf(__fmaf_rn(ex, ex, __fmaf_rn(ey, ey, ez * ez))) * 1.0001f + 2.0f * margin;
+                const float lb = p.w - delta;  // every other target point is at least this far away now
+                s_src[i].w = lb;
+                if (d <= P.gate_f && sqrtf(d) * 1.000001f + margin < lb) {  // false for NaN
+                    need = false;
+                    add_corr<KIND, FIT, NV>(acc, cnt, pw, h, d);
+#ifdef ICP4R_RB_VERIFY
+                    rb_verify(s_tgt, P.max_m, s_cs[g.ncells], qx, qy, qz, P.gate_f, hp, 1, i, lb, delta);
+#endif
+                }
+            }
+        }
+        const unsigned mask = __ballot_sync(FULL, need);
+        if (need) list[nl + __popc(mask & lt)] = (unsigned short)i;
+        nl += __popc(mask);
+    }
+    __syncwarp();
+    // ---- phase 2: search the rest --------------------------------------------------------------------------------
+    for (int j0 = 0; j0 < nl; j0 += 32) {
+        const int j = j0 + lane;
+        if (j < nl) {
+            const int i = (int)list[j];
+            const float4 p = s_src[i];
+            double pw[3];
+            xform_point(T, p.x, p.y, p.z, pw);
+            const float qx = (float)pw[0], qy = (float)pw[1], qz = (float)pw[2];
+            const float margin = fmaxf(g.margin, 9.5367431640625e-7f * fmaxf(fabsf(qx), fmaxf(fabsf(qy), fabsf(qz))));
+            int pos = -1;
+            float lb = 0.0f;
+            uint64_t key = KEY_EMPTY;
+            bool bounded = false;
+            if (have_prev) {
+                const int hp = (int)s_prev[i];
+                if (hp != 0xFFFF) {
+                    const float4 h = s_tgt[hp];
+                    const float hd = dist2_exact(qx, qy, qz, h.x, h.y, h.z);
+                    if (hd <= P.gate_f) {  // false for NaN; a previous neighbour outside the gate is no bound
+                        key = thread_box_nn(g, s_tgt, s_cs, qx, qy, qz, P.gate_f, margin, hd, slack, pos, lb);
+                        bounded = true;
+                    }
+                }
+            }
+            if (!bounded) key = thread_shell_nn(g, s_tgt, s_cs, qx, qy, qz, P.gate_f, P.gate_r, margin, pos);
+#ifdef ICP4R_RB_VERIFY
+            rb_verify(s_tgt, P.max_m, s_cs[g.ncells], qx, qy, qz, P.gate_f, pos, bounded ? 2 : 3, i, lb, 0.f);
+#endif
+            if (P.use_hints) {
+                s_prev[i] = pos >= 0 ? (unsigned short)pos : (unsigned short)0xFFFFu;
+                s_src[i].w = lb;
+            }
+            if (key != KEY_EMPTY) add_corr<KIND, FIT, NV>(acc, cnt, pw, s_tgt[pos], key_d2(key));
+        }
+    }
+    if (FIT || KIND == ICP4R_P2P_SVD) acc[0] = (double)cnt;
+}
+
+template <int KIND, int NT>
+__global__ void __launch_bounds__(NT, 2) reg_batch_kernel(const __grid_constant__ BatchParams P, double* __restrict__ T_out,
+                                                          icp4r_result* __restrict__ res) {
+    constexpr int NW = NT / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* s_tgt = reinterpret_cast<float4*>(smem_raw);
-    float4* s_src = s_tgt + P.max_m;
+    float4* s_src = s_tgt + P.max_m;                                // .w = LB (metres) once the loop runs
     uint32_t* s_cs = reinterpret_cast<uint32_t*>(s_src + P.max_n);  // [RB_MAXC + 2] target cell table
-    uint32_t* s_cq = s_cs + (RB_MAXC + 2);                          // [RB_MAXC + 2] source cell cursors (spatial sort)
-    unsigned short* s_prev = reinterpret_cast<unsigned short*>(s_cq + (RB_MAXC + 2));  // [max_n] slot of the last neighbour
-    __shared__ double s_red[RB_WARPS * 32];
+    uint32_t* s_cq = s_cs + (RB_MAXC + 2);                          // [RB_MAXC + 2] source cell cursors (spatial sort) ...
+    unsigned short* s_list = reinterpret_cast<unsigned short*>(s_cq);  // ... later the per-warp lists of points to search
+    const size_t cq_bytes = max((size_t)(RB_MAXC + 2) * 4, ((size_t)(P.max_n + NT) * 2 + 15) & ~(size_t)15);
+    unsigned short* s_prev = reinterpret_cast<unsigned short*>(reinterpret_cast<unsigned char*>(s_cq) + cq_bytes);  // [max_n] slot of the last neighbour
+    __shared__ double s_red[NW * 32];
     __shared__ double s_tot[32];
     __shared__ double s_T[16];
-    __shared__ float s_bb[RB_WARPS][6];
+    __shared__ float s_dA[12];  // last pose increment as the point displacement map q -> (I - R^T) q + R^T t
+    __shared__ float s_bb[NW][6];
     __shared__ PairGrid s_g;
-    __shared__ uint32_t s_wsum[RB_WARPS];
+    __shared__ uint32_t s_wsum[NW];
     __shared__ int s_flags[4];  // done, converged, iterations, n_corr
     __shared__ double s_misc[2];  // mse_prev, last_cost
 
@@ -234,7 +406,7 @@ __global__ void __launch_bounds__(RB_THREADS, 2) reg_batch_kernel(const __grid_c
 
         // ---- bounding box of the target ------------------------------------------------------------------
         float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-        for (int j = tid; j < m; j += RB_THREADS) {
+        for (int j = tid; j < m; j += NT) {
             const float4 p = __ldg(gtgt + j);
             if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
                 mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x);
@@ -262,7 +434,7 @@ __global__ void __launch_bounds__(RB_THREADS, 2) reg_batch_kernel(const __grid_c
             for (int a = 0; a < 3; ++a) {
                 lo[a] = s_bb[0][a];
                 hi[a] = s_bb[0][3 + a];
-                for (int j = 1; j < RB_WARPS; ++j) {
+                for (int j = 1; j < NW; ++j) {
                     lo[a] = fminf(lo[a], s_bb[j][a]);
                     hi[a] = fmaxf(hi[a], s_bb[j][3 + a]);
                 }
@@ -305,7 +477,8 @@ __global__ void __launch_bounds__(RB_THREADS, 2) reg_batch_kernel(const __grid_c
             s_misc[1] = 0.0;
         }
         if (tid < 16) s_T[tid] = P.T0[tid];
-        for (int c0 = tid; c0 < 2 * (RB_MAXC + 2); c0 += RB_THREADS) s_cs[c0] = 0;  // both tables
+        if (tid < 12) s_dA[tid] = 0.0f;
+        for (int c0 = tid; c0 < 2 * (RB_MAXC + 2); c0 += NT) s_cs[c0] = 0;  // both tables
         __syncthreads();
         const PairGrid g = s_g;
 
@@ -322,11 +495,11 @@ __global__ void __launch_bounds__(RB_THREADS, 2) reg_batch_kernel(const __grid_c
             return (cell_of_s((float)pw[2], g.oz, g.inv_cell, g.nz) * g.ny + cell_of_s((float)pw[1], g.oy, g.inv_cell, g.ny)) * g.nx +
                    cell_of_s((float)pw[0], g.ox, g.inv_cell, g.nx);
         };
-        for (int j = tid; j < m; j += RB_THREADS) {
+        for (int j = tid; j < m; j += NT) {
             const float4 p = __ldg(gtgt + j);
             if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) atomicAdd(&s_cs[tgt_cell(p) + 1], 1u);
         }
-        for (int i = tid; i < n; i += RB_THREADS) {  // the cell of every source point is kept for the placement below
+        for (int i = tid; i < n; i += NT) {  // the cell of every source point is kept for the placement below
             const int cell = src_cell(__ldg(gsrc + i));
             s_prev[i] = (unsigned short)cell;
             atomicAdd(&s_cq[cell + 1], 1u);
@@ -334,7 +507,7 @@ __global__ void __launch_bounds__(RB_THREADS, 2) reg_batch_kernel(const __grid_c
         __syncthreads();
         for (int which = 0; which < 2; ++which) {  // table[c+1] <- exclusive prefix of the counts (the running cursor of cell c)
             uint32_t* tab = which ? s_cq : s_cs;
-            constexpr int PER = (RB_MAXC + RB_THREADS - 1) / RB_THREADS;
+            constexpr int PER = (RB_MAXC + NT - 1) / NT;
             uint32_t v[PER], sum = 0;
 #pragma unroll
             for (int t = 0; t < PER; ++t) {
@@ -360,7 +533,7 @@ __global__ void __launch_bounds__(RB_THREADS, 2) reg_batch_kernel(const __grid_c
             }
             __syncthreads();
         }
-        for (int j = tid; j < m; j += RB_THREADS) {
+        for (int j = tid; j < m; j += NT) {
             const float4 p = __ldg(gtgt + j);
             if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
                 const uint32_t pos = atomicAdd(&s_cs[tgt_cell(p) + 1], 1u);
@@ -369,14 +542,14 @@ __global__ void __launch_bounds__(RB_THREADS, 2) reg_batch_kernel(const __grid_c
         }
         // Which thread sums which source points decides the rounding of the fp64 sums. Default: atomic placement (order
         // inside a cell varies run to run, poses agree to ~1e-14). ICP4R_BATCH_REPRODUCIBLE=1: ascending original index
-        // inside a cell — every warp owns a contiguous slice of the cloud, the warps take turns (8 barriers per pair) to
-        // hand out positions, lanes that share a cell rank themselves with match_any — bit-reproducible, 2.4 % slower.
+        // inside a cell — every warp owns a contiguous slice of the cloud, the warps take turns (one barrier per warp and
+        // pair) to hand out positions, lanes that share a cell rank themselves with match_any — bit-reproducible.
         if (!P.reproducible) {
-            for (int i = tid; i < n; i += RB_THREADS) s_prev[i] = (unsigned short)atomicAdd(&s_cq[(int)s_prev[i] + 1], 1u);
+            for (int i = tid; i < n; i += NT) s_prev[i] = (unsigned short)atomicAdd(&s_cq[(int)s_prev[i] + 1], 1u);
         } else {
-            const int slice = (n + RB_WARPS - 1) / RB_WARPS;
+            const int slice = (n + NW - 1) / NW;
             const int beg = w * slice, end = min(n, beg + slice);
-            for (int turn = 0; turn < RB_WARPS; ++turn) {
+            for (int turn = 0; turn < NW; ++turn) {
                 if (w == turn) {
                     for (int i0 = beg; i0 < end; i0 += 32) {
                         const int i = i0 + lane;
@@ -395,36 +568,21 @@ __global__ void __launch_bounds__(RB_THREADS, 2) reg_batch_kernel(const __grid_c
             }
         }
         __syncthreads();
-        for (int i = tid; i < n; i += RB_THREADS) s_src[s_prev[i]] = __ldg(gsrc + i);
+        for (int i = tid; i < n; i += NT) s_src[s_prev[i]] = __ldg(gsrc + i);
         __syncthreads();
-        // now s_cs[c] = start of target cell c, s_cs[c+1] = its end
+        // now s_cs[c] = start of target cell c, s_cs[c+1] = its end; s_cq is free: it holds the search lists from here on
+        const int chunk = ((n + NT - 1) / NT) * 32;  // source points per warp
 
         // ---- iterations ---------------------------------------------------------------------------------
         for (int it = 0; it < P.max_iterations; ++it) {
-            double T[12];
-#pragma unroll
-            for (int i = 0; i < 12; ++i) T[i] = s_T[i];
             double acc[NV];
 #pragma unroll
             for (int v = 0; v < NV; ++v) acc[v] = 0.0;
-            for (int i = tid; i < n; i += RB_THREADS) {
-                const float4 p = s_src[i];
-                double pw[3];
-                xform_point(T, p.x, p.y, p.z, pw);
-                int pos;
-                const int hint = (P.use_hints && it > 0 && s_prev[i] != 0xFFFFu) ? (int)s_prev[i] : -1;
-                const uint64_t key = thread_grid_nn(g, s_tgt, s_cs, (float)pw[0], (float)pw[1], (float)pw[2], P.gate_f, P.gate_r, pos, hint);
-                if (P.use_hints) s_prev[i] = pos >= 0 ? (unsigned short)pos : (unsigned short)0xFFFFu;
-                if (key != KEY_EMPTY) {
-                    const float4 c = s_tgt[pos];
-                    if (KIND == ICP4R_P2P_SVD) contrib_p2p_svd(acc, pw, c.x, c.y, c.z, key_d2(key));
-                    else contrib_p2p_gn(acc, pw, c.x, c.y, c.z);
-                }
-            }
-            block_reduce<NV>(acc, s_red, s_tot, tid);
+            pair_pass<KIND, false, NV>(g, s_tgt, s_src, s_cs, s_prev, s_list, s_T, s_dA, P, n, chunk, P.use_hints && it > 0, acc, lane, w);
+            block_reduce<NV, NW>(acc, s_red, s_tot, tid);
             if (KIND == ICP4R_P2P_SVD && w == 0) {
                 // Kabsch step by one WARP (one matrix row per lane, solve_warp.cuh) instead of one thread: the other
-                // seven warps wait at the barrier below for this, every iteration
+                // warps wait at the barrier below for this, every iteration
                 const bool last = (it == P.max_iterations - 1);
                 const double cnt = s_tot[0];
                 double* aux = s_red;       // [9] cross-covariance
@@ -451,7 +609,12 @@ __global__ void __launch_bounds__(RB_THREADS, 2) reg_batch_kernel(const __grid_c
                     __syncwarp();
                     const double tn = warp_compose_entry(Ds, s_T, lane);
                     __syncwarp();
-                    if (lane < 12) s_T[lane] = tn;
+                    if (lane < 12) {
+                        s_T[lane] = tn;
+                        const int r = lane >> 2, cc = lane & 3;  // displacement map of this increment (see pair_pass)
+                        s_dA[lane] = cc < 3 ? (float)((r == cc ? 1.0 : 0.0) - Ds[4 * cc + r])
+                                            : (float)((Ds[r] * Ds[3] + Ds[4 + r] * Ds[7]) + Ds[8 + r] * Ds[11]);
+                    }
                     if (lane == 0) {
                         s_flags[3] = (int)cnt;
                         const double mse = s_tot[16] / cnt;
@@ -489,6 +652,10 @@ __global__ void __launch_bounds__(RB_THREADS, 2) reg_batch_kernel(const __grid_c
                         s_misc[1] = s_tot[27];
                         mat4_mul(D, Tc, Tc);
                         for (int i = 0; i < 16; ++i) s_T[i] = Tc[i];
+                        for (int r = 0; r < 3; ++r) {
+                            for (int cc = 0; cc < 3; ++cc) s_dA[4 * r + cc] = (float)((r == cc ? 1.0 : 0.0) - D[4 * cc + r]);
+                            s_dA[4 * r + 3] = (float)((D[r] * D[3] + D[4 + r] * D[7]) + D[8 + r] * D[11]);
+                        }
                         if (P.early_exit) {
                             const double wn = sqrt(xi[0] * xi[0] + xi[1] * xi[1] + xi[2] * xi[2]);
                             const double vn = sqrt(xi[3] * xi[3] + xi[4] * xi[4] + xi[5] * xi[5]);
@@ -512,23 +679,9 @@ __global__ void __launch_bounds__(RB_THREADS, 2) reg_batch_kernel(const __grid_c
 
         // ---- fitness pass: mean squared 1-NN distance under the final pose --------------------------
         {
-            double T[12];
-#pragma unroll
-            for (int i = 0; i < 12; ++i) T[i] = s_T[i];
             double fa[2] = {0.0, 0.0};
-            for (int i = tid; i < n; i += RB_THREADS) {
-                const float4 p = s_src[i];
-                double pw[3];
-                xform_point(T, p.x, p.y, p.z, pw);
-                int pos;
-                const int hint = (P.use_hints && P.max_iterations > 0 && s_prev[i] != 0xFFFFu) ? (int)s_prev[i] : -1;
-                const uint64_t key = thread_grid_nn(g, s_tgt, s_cs, (float)pw[0], (float)pw[1], (float)pw[2], P.gate_f, P.gate_r, pos, hint);
-                if (key != KEY_EMPTY) {
-                    fa[0] += 1.0;
-                    fa[1] += (double)key_d2(key);
-                }
-            }
-            block_reduce<2>(fa, s_red, s_tot, tid);
+            pair_pass<KIND, true, 2>(g, s_tgt, s_src, s_cs, s_prev, s_list, s_T, s_dA, P, n, chunk, P.use_hints && P.max_iterations > 0, fa, lane, w);
+            block_reduce<2, NW>(fa, s_red, s_tot, tid);
         }
         if (tid < 16) T_out[(size_t)pair * 16 + tid] = s_T[tid];
         if (tid == 0) {
@@ -544,12 +697,30 @@ __global__ void __launch_bounds__(RB_THREADS, 2) reg_batch_kernel(const __grid_c
     }
 }
 
+template <int KIND, int NT>
+static int launch_batch(Ctx* c, const BatchParams& P, size_t smem, double* d_T, icp4r_result* d_res) {
+    auto kern = reg_batch_kernel<KIND, NT>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
+    per_sm = std::max(per_sm, 1);
+    const int blocks = std::min(P.n_pairs, c->sm_count * per_sm);
+    kern<<<blocks, NT, smem, c->stream>>>(P, d_T, d_res);
+    c->launches += 1;
+    CK(cudaGetLastError());
+    return ICP4R_OK;
+}
+
 int register_batch(Ctx* c, const float4* d_src, const int32_t* d_soff, const float4* d_tgt, const int32_t* d_toff, int n_pairs,
                    int max_n, int max_m, const icp4r_opts* o, double* d_T, icp4r_result* d_res) {
     if (n_pairs <= 0) return ICP4R_OK;
     if (o->residual != ICP4R_P2P_SVD && o->residual != ICP4R_P2P_GN)
         return fail(c, ICP4R_ERR_UNSUPPORTED, "batched registration supports P2P_SVD and P2P_GN (got %d)", o->residual);
-    const size_t smem = (size_t)(std::max(max_m, 1) + std::max(max_n, 1)) * sizeof(float4) + 2 * (RB_MAXC + 2) * sizeof(uint32_t) +
+    int nt = 256;
+    if (const char* e = std::getenv("ICP4R_RB_THREADS")) nt = std::atoi(e);
+    if (nt != 256 && nt != 384 && nt != 512) nt = 256;
+    const size_t cq_bytes = std::max((size_t)(RB_MAXC + 2) * 4, ((size_t)(std::max(max_n, 1) + nt) * 2 + 15) & ~(size_t)15);
+    const size_t smem = (size_t)(std::max(max_m, 1) + std::max(max_n, 1)) * sizeof(float4) + (RB_MAXC + 2) * sizeof(uint32_t) + cq_bytes +
                         (((size_t)std::max(max_n, 1) * sizeof(unsigned short) + 15) & ~(size_t)15);
     if (smem > 200 * 1024)
         return fail(c, ICP4R_ERR_UNSUPPORTED, "pair too large for the shared-memory resident kernel (%zu B); use icp4r_register", smem);
@@ -564,26 +735,22 @@ int register_batch(Ctx* c, const float4* d_src, const int32_t* d_soff, const flo
     P.max_m = std::max(max_m, 1);
     P.max_iterations = o->max_iterations;
     P.early_exit = o->early_exit;
-    P.use_hints = (c->use_hints && max_m < 65535) ? 1 : 0;
+    P.use_hints = (c->use_hints && max_m < 65535 && max_n < 65535) ? 1 : 0;
     P.reproducible = c->batch_reproducible ? 1 : 0;
     P.cell_pts = 2.0f;
     if (const char* e = std::getenv("ICP4R_RB_CELL_PTS")) P.cell_pts = std::max(0.05f, (float)std::atof(e));
+    P.slack = 0.0f;
+    if (const char* e = std::getenv("ICP4R_RB_SLACK")) P.slack = std::min(std::max(0.0f, (float)std::atof(e)), 4.0f);
     gate_params(o->max_corr_dist, &P.gate_f, &P.gate_r);
     P.rot_eps = o->rot_eps;
     P.trans_eps = o->trans_eps;
     P.mse_abs_eps = o->mse_abs_eps;
     std::memcpy(P.T0, o->T0, sizeof(P.T0));
 
-    auto kern = (o->residual == ICP4R_P2P_SVD) ? reg_batch_kernel<ICP4R_P2P_SVD> : reg_batch_kernel<ICP4R_P2P_GN>;
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 1;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RB_THREADS, smem));
-    per_sm = std::max(per_sm, 1);
-    const int blocks = std::min(n_pairs, c->sm_count * per_sm);
-    kern<<<blocks, RB_THREADS, smem, c->stream>>>(P, d_T, d_res);
-    c->launches += 1;
-    CK(cudaGetLastError());
-    return ICP4R_OK;
+    const bool svd = o->residual == ICP4R_P2P_SVD;
+    if (nt == 512) return svd ? launch_batch<ICP4R_P2P_SVD, 512>(c, P, smem, d_T, d_res) : launch_batch<ICP4R_P2P_GN, 512>(c, P, smem, d_T, d_res);
+    if (nt == 384) return svd ? launch_batch<ICP4R_P2P_SVD, 384>(c, P, smem, d_T, d_res) : launch_batch<ICP4R_P2P_GN, 384>(c, P, smem, d_T, d_res);
+    return svd ? launch_batch<ICP4R_P2P_SVD, 256>(c, P, smem, d_T, d_res) : launch_batch<ICP4R_P2P_GN, 256>(c, P, smem, d_T, d_res);
 }
 
 }  // namespace icp4r
