@@ -13,16 +13,18 @@
 //
 // How the exact 1-NN is kept cheap over the 30 iterations (all of it exact: the answer is always the one an exhaustive
 // search with the (d2, index) order would give):
-//   * every source point remembers its previous neighbour h and a lower bound LB on its distance to every OTHER target
-//     point. A pose update moves the point by delta, so the other points are now at least LB - delta away, and if
-//     |q - h| < LB - delta the old neighbour is still the unique nearest one: no search at all. One uniform pass over
-//     the cloud (32 of 32 lanes active, no loops) settles most points this way once the pose increments get small.
+//   * every source point remembers its two nearest target points h1, h2 of the last search and a lower bound LB on its
+//     distance to every OTHER target point. A pose update moves the point by delta, so the other points are now at
+//     least LB - delta away, and if min(|q - h1|, |q - h2|) < LB - delta the nearer of the two is the unique nearest
+//     point: no search at all. One uniform pass over the cloud (32 of 32 lanes active, no loops) settles most points
+//     this way once the pose increments get small; keeping two candidates instead of one matters because the usual
+//     reason for a failed test is the runner-up coming closer, not a third point.
 //   * the points that fail the test are compacted, in order, into a per-warp list and searched: all cells that the box
-//     [q - |q - h|, q + |q - h|] touches (it contains the ball in which a better neighbour would have to lie). The same
-//     pass yields the new LB = min(distance of the runner-up, distance from q to the nearest face of that cell box that
-//     has unvisited cells behind it).
-//   * without a previous neighbour (first iteration, or nothing inside the gate last time): cube-shell expansion around
-//     the query's cell with the running best pruning rows and x-extents.
+//     around q with the radius of the farther remembered point touches (it contains the ball in which a better
+//     neighbour would have to lie). The same pass yields the new h1, h2 and LB = min(distance of the third nearest
+//     point seen, distance from q to the nearest face of that cell box that has unvisited cells behind it).
+//   * without a remembered point (first iteration, or nothing inside the gate last time) the radius comes from the
+//     nearest point of the query's own cell, or, if that cell is empty, from a cube-shell expansion around it.
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -46,7 +48,7 @@ struct BatchParams {
     float cell_pts;  // target points per cell (by volume) of the per-pair grid
     float slack;     // extra radius of the bounded search, in cells (a wider box costs candidates and buys a larger LB)
     int reproducible;  // place the source in index order (bit-reproducible sums) instead of with atomics (2.4 % faster)
-    int use_hints;  // previous-iteration neighbour kept per source point (16-bit slot: needs max_m < 65535)
+    int use_hints;  // previous-iteration neighbours kept per source point (16-bit slots: needs max_m < 65535)
     float gate_f, gate_r;
     double rot_eps, trans_eps, mse_abs_eps;
     double T0[16];
@@ -63,20 +65,28 @@ __device__ __forceinline__ int cell_of_s(float v, float o, float inv, int dim) {
     return (int)f;
 }
 
-// Bounded exact 1-NN: `hd` = squared distance of a known target point (the previous neighbour, at slot hint_pos), so
-// the nearest point lies in the closed ball of that radius. Every point of every cell the enclosing box touches is
-// looked at — no pruning, the loop body is load / distance / compare — and the second smallest distance seen plus the
-// distance to the faces of the visited cell box bound every other target point from below (`lb`, metres).
-__device__ __forceinline__ uint64_t thread_box_nn(const PairGrid& g, const float4* __restrict__ s_tgt, const uint32_t* __restrict__ cs,
-                                                  float qx, float qy, float qz, float gate_f, float margin, float hd, float slack,
-                                                  int& best_pos, float& lb) {
+struct BoxHit {
+    float d1, d2;  // squared distances of the nearest and second nearest point (INFINITY: none)
+    int p1, p2;    // their slots (-1: none)
+    float lb;      // every other target point is at least this far away (metres)
+};
+
+// Bounded exact search: the caller knows that the nearest point lies in the closed ball of squared radius `hd` around
+// q. Every point of every cell the enclosing box touches is looked at — no pruning, the loop body is load / distance /
+// a 3-deep insertion — and the third smallest distance seen plus the distance to the faces of the visited cell box
+// bound every target point other than the two winners from below.
+// EXACT = false orders by distance only (the earlier slot wins a tie); the caller re-runs with EXACT = true, which
+// orders by (distance, original index), when the two best distances come out equal — the only case where the
+// difference can show.
+template <bool EXACT>
+__device__ __forceinline__ void box_scan(const PairGrid& g, const float4* __restrict__ s_tgt, const uint32_t* __restrict__ cs, float qx,
+                                         float qy, float qz, float margin, float hd, float slack, BoxHit& out) {
     const float r = sqrtf(hd) * 1.000001f + margin + slack;
     const int xa = cell_of_s(qx - r, g.ox, g.inv_cell, g.nx), xb = cell_of_s(qx + r, g.ox, g.inv_cell, g.nx);
     const int y0 = cell_of_s(qy - r, g.oy, g.inv_cell, g.ny), y1 = cell_of_s(qy + r, g.oy, g.inv_cell, g.ny);
     const int z0 = cell_of_s(qz - r, g.oz, g.inv_cell, g.nz), z1 = cell_of_s(qz + r, g.oz, g.inv_cell, g.nz);
-    float best_d = INFINITY, second = INFINITY;
-    int best_i = 0x7fffffff;
-    best_pos = -1;
+    float b1 = INFINITY, b2 = INFINITY, b3 = INFINITY;
+    int p1 = -1, p2 = -1, i1 = 0x7fffffff, i2 = 0x7fffffff;
     for (int z = z0; z <= z1; ++z) {
         int rowbase = (z * g.ny + y0) * g.nx;
         for (int y = y0; y <= y1; ++y, rowbase += g.nx) {
@@ -84,13 +94,23 @@ __device__ __forceinline__ uint64_t thread_box_nn(const PairGrid& g, const float
             for (uint32_t j = s; j < e; ++j) {
                 const float4 c = s_tgt[j];
                 const float d = dist2_exact(qx, qy, qz, c.x, c.y, c.z);
-                const int ci = __float_as_int(c.w);
-                // the loser of (running best, candidate) competes for second place; fminf drops a NaN
-                const bool better = d <= gate_f && (d < best_d || (d == best_d && ci < best_i));  // false for NaN
-                second = fminf(second, better ? best_d : d);
-                best_d = better ? d : best_d;
-                best_i = better ? ci : best_i;
-                best_pos = better ? (int)j : best_pos;
+                // insertion into (b1, b2, b3) written as selects: every comparison is false for a NaN, fminf drops it
+                bool lt1, lt2;
+                if (EXACT) {
+                    const int ci = __float_as_int(c.w);
+                    lt1 = d < b1 || (d == b1 && ci < i1);
+                    lt2 = d < b2 || (d == b2 && ci < i2);
+                    i2 = lt1 ? i1 : (lt2 ? ci : i2);
+                    i1 = lt1 ? ci : i1;
+                } else {
+                    lt1 = d < b1;
+                    lt2 = d < b2;
+                }
+                b3 = fminf(b3, lt2 ? b2 : d);
+                p2 = lt1 ? p1 : (lt2 ? (int)j : p2);
+                b2 = lt1 ? b1 : (lt2 ? d : b2);
+                p1 = lt1 ? (int)j : p1;
+                b1 = lt1 ? d : b1;
             }
         }
     }
@@ -102,25 +122,34 @@ __device__ __forceinline__ uint64_t thread_box_nn(const PairGrid& g, const float
     if (y1 < g.ny - 1) bd = fminf(bd, (g.oy + (float)(y1 + 1) * g.cell) - qy);
     if (z0 > 0) bd = fminf(bd, qz - (g.oz + (float)z0 * g.cell));
     if (z1 < g.nz - 1) bd = fminf(bd, (g.oz + (float)(z1 + 1) * g.cell) - qz);
-    lb = fmaxf(fminf(sqrtf(second) * 0.999999f, bd - 2.0f * margin), 0.0f);
-#ifdef ICP4R_RB_VERIFY
-    {
-        float sd = INFINITY;
-        int sp = -1;
-        const int mv = (int)cs[g.ncells];
-        for (int j = 0; j < mv; ++j) {
-            if (j == best_pos) continue;
-            const float4 c = s_tgt[j];
-            const float d = dist2_exact(qx, qy, qz, c.x, c.y, c.z);
-            if (d < sd) sd = d, sp = j;
-        }
-        if (lb > sqrtf(sd))
-            printf("RB_BOX block=%d best=%d second=%g bd=%g lb=%g true2=%g at %d | hd=%g r=%g box x %d..%d y %d..%d z %d..%d | dims %d %d %d cell %g o %g %g %g | cs[row y0]=%u..%u\n",
-                   blockIdx.x, best_pos, second, bd, lb, sd, sp, hd, r, xa, xb, y0, y1, z0, z1, g.nx, g.ny, g.nz, g.cell, g.ox, g.oy, g.oz,
-                   cs[(z0 * g.ny + y0) * g.nx + xa], cs[(z0 * g.ny + y0) * g.nx + xb + 1]);
+    out.d1 = b1;
+    out.d2 = b2;
+    out.p1 = p1;
+    out.p2 = p2;
+    out.lb = fmaxf(fminf(sqrtf(b3) * 0.999999f, bd - 2.0f * margin), 0.0f);
+}
+static __device__ __noinline__ void box_scan_exact(const PairGrid& g, const float4* __restrict__ s_tgt, const uint32_t* __restrict__ cs,
+                                                   float qx, float qy, float qz, float margin, float hd, float slack, BoxHit& out) {
+    box_scan<true>(g, s_tgt, cs, qx, qy, qz, margin, hd, slack, out);
+}
+__device__ __forceinline__ void thread_box_nn(const PairGrid& g, const float4* __restrict__ s_tgt, const uint32_t* __restrict__ cs, float qx,
+                                              float qy, float qz, float margin, float hd, float slack, BoxHit& out) {
+    box_scan<false>(g, s_tgt, cs, qx, qy, qz, margin, hd, slack, out);
+    if (out.p2 >= 0 && out.d1 == out.d2) box_scan_exact(g, s_tgt, cs, qx, qy, qz, margin, hd, slack, out);  // a tie for first place
+}
+
+// squared distance of the nearest point of the query's own cell (INFINITY if it is empty): a cheap radius for the
+// bounded search when nothing is remembered
+__device__ __forceinline__ float own_cell_seed(const PairGrid& g, const float4* __restrict__ s_tgt, const uint32_t* __restrict__ cs, float qx,
+                                               float qy, float qz) {
+    const int c = (cell_of_s(qz, g.oz, g.inv_cell, g.nz) * g.ny + cell_of_s(qy, g.oy, g.inv_cell, g.ny)) * g.nx +
+                  cell_of_s(qx, g.ox, g.inv_cell, g.nx);
+    float best = INFINITY;
+    for (uint32_t j = cs[c], e = cs[c + 1]; j < e; ++j) {
+        const float4 t = s_tgt[j];
+        best = fminf(best, dist2_exact(qx, qy, qz, t.x, t.y, t.z));
     }
-#endif
-    return best_pos >= 0 ? pack_key(best_d, best_i) : KEY_EMPTY;
+    return best;
 }
 
 // exact 1-NN of (qx,qy,qz) over the shared-memory grid without prior knowledge; returns the packed key and the slot
@@ -227,19 +256,19 @@ __device__ __noinline__ void rb_verify(const float4* s_tgt, int max_m, int mvali
             bp = j;
         }
     }
-    if (how == 2) {  // is lb really a lower bound on every other point?
-        float sd = INFINITY;
-        int sp = -1;
-        for (int j = 0; j < mvalid; ++j) {
-            if (j == bp) continue;
-            const float4 c = s_tgt[j];
-            const float d = dist2_exact(qx, qy, qz, c.x, c.y, c.z);
-            if (d < sd) sd = d, sp = j;
-        }
-        if (lb > sqrtf(sd)) printf("RB_VERIFY bad lb block=%d i=%d best=%d (r %g) runner-up=%d at %g but lb=%g q=(%g %g %g)\n", blockIdx.x, i, bp, sqrtf(bd), sp, sqrtf(sd), lb, qx, qy, qz);
-    }
     if (bp != pos) printf("RB_VERIFY mismatch how=%d block=%d i=%d got=%d want=%d (d2 want %g) lb=%g delta=%g\n", how, blockIdx.x, i, pos, bp, bd, lb, delta);
 }
+#endif
+
+#ifdef ICP4R_RB_TIMING
+// debug build only: cycles summed over warps (0 phase 1, 1 phase 2, 2 reduce incl. waiting, 3 solve (warp 0), 4 setup (warp 0),
+// 5 fitness pass, 6 points searched, 7 passes)
+__device__ unsigned long long rb_prof[12];
+#define RB_T(var) const long long var = clock64()
+#define RB_ADD(slot, v) do { if ((threadIdx.x & 31) == 0) atomicAdd(&rb_prof[slot], (unsigned long long)(v)); } while (0)
+#else
+#define RB_T(var)
+#define RB_ADD(slot, v)
 #endif
 
 template <int NV, int NW>
@@ -285,33 +314,39 @@ __device__ __forceinline__ void add_corr(double (&acc)[NV], int& cnt, const doub
 
 // One pass over the source cloud of the pair (an iteration, or the fitness pass): warp w owns the contiguous slice
 // [w * chunk, (w + 1) * chunk) of the cell-sorted source, so there is no block barrier between the two phases.
+// Per source point: s_h1 / s_h2 = slots of the two nearest target points of its last search (0xFFFF: none),
+// s_src[].w = LB (see the file header).
 template <int KIND, bool FIT, int NV>
 __device__ __forceinline__ void pair_pass(const PairGrid& g, const float4* __restrict__ s_tgt, float4* __restrict__ s_src,
-                                          const uint32_t* __restrict__ s_cs, unsigned short* __restrict__ s_prev,
-                                          unsigned short* __restrict__ s_list, const double* __restrict__ s_T, const float* __restrict__ s_dA,
-                                          const BatchParams& P, int n, int chunk, bool have_prev, double (&acc)[NV], int lane, int w) {
+                                          const uint32_t* __restrict__ s_cs, unsigned short* __restrict__ s_h1,
+                                          unsigned short* __restrict__ s_h2, unsigned short* __restrict__ s_list,
+                                          const double* __restrict__ s_T, const float* __restrict__ s_dA, const BatchParams& P, int n,
+                                          int chunk, bool have_prev, double (&acc)[NV], int lane, int w) {
+    constexpr int NONE = 0xFFFF;
     const int beg = min(n, w * chunk), end = min(n, beg + chunk);
     unsigned short* list = s_list + beg;
     int nl = 0, cnt = 0;
-    double T[12];
-#pragma unroll
-    for (int i = 0; i < 12; ++i) T[i] = s_T[i];
     const unsigned lt = (1u << lane) - 1u;
     const float slack = P.slack * g.cell;
-    // ---- phase 1: is the previous neighbour provably still the nearest one? ------------------------------------
+    RB_T(t_p1);
+    // ---- phase 1: is one of the two remembered points provably still the nearest one? ------------------------------
     for (int i0 = beg; i0 < end; i0 += 32) {
         const int i = i0 + lane;
         bool need = i < end;
         if (need && have_prev) {
-            const int hp = (int)s_prev[i];
-            if (hp != 0xFFFF) {
+            const int hp1 = (int)s_h1[i], hp2 = (int)s_h2[i];
+            if (hp1 != NONE) {
                 const float4 p = s_src[i];
                 double pw[3];
-                xform_point(T, p.x, p.y, p.z, pw);
+                xform_point(s_T, p.x, p.y, p.z, pw);
                 const float qx = (float)pw[0], qy = (float)pw[1], qz = (float)pw[2];
                 const float margin = fmaxf(g.margin, 9.5367431640625e-7f * fmaxf(fabsf(qx), fmaxf(fabsf(qy), fabsf(qz))));
-                const float4 h = s_tgt[hp];
-                const float d = dist2_exact(qx, qy, qz, h.x, h.y, h.z);
+                const float4 h1 = s_tgt[hp1];
+                const float4 h2 = s_tgt[hp2 != NONE ? hp2 : hp1];
+                const float d1 = dist2_exact(qx, qy, qz, h1.x, h1.y, h1.z);
+                const float d2 = hp2 != NONE ? dist2_exact(qx, qy, qz, h2.x, h2.y, h2.z) : INFINITY;
+                const bool second_wins = d2 < d1;
+                const float dm = second_wins ? d2 : d1;
                 // how far the last pose increment D moved this point: q - D^-1 q = (I - R^T) q + R^T t
                 const float ex = __fmaf_rn(s_dA[0], qx, __fmaf_rn(s_dA[1], qy, __fmaf_rn(s_dA[2], qz, s_dA[3])));
                 const float ey = __fmaf_rn(s_dA[4], qx, __fmaf_rn(s_dA[5], qy, __fmaf_rn(s_dA[6], qz, s_dA[7])));
@@ -319,11 +354,16 @@ __device__ __forceinline__ void pair_pass(const PairGrid& g, const float4* __res
                 const float delta = sqrtf(__fmaf_rn(ex, ex, __fmaf_rn(ey, ey, ez * ez))) * 1.0001f + 2.0f * margin;
                 const float lb = p.w - delta;  // every other target point is at least this far away now
                 s_src[i].w = lb;
-                if (d <= P.gate_f && sqrtf(d) * 1.000001f + margin < lb) {  // false for NaN
+                // (a tie between the two goes to the search, which orders by index)
+                if (dm <= P.gate_f && d1 != d2 && sqrtf(dm) * 1.000001f + margin < lb) {  // false for NaN
                     need = false;
-                    add_corr<KIND, FIT, NV>(acc, cnt, pw, h, d);
+                    if (second_wins) {
+                        s_h1[i] = (unsigned short)hp2;
+                        s_h2[i] = (unsigned short)hp1;
+                    }
+                    add_corr<KIND, FIT, NV>(acc, cnt, pw, second_wins ? h2 : h1, dm);
 #ifdef ICP4R_RB_VERIFY
-                    rb_verify(s_tgt, P.max_m, s_cs[g.ncells], qx, qy, qz, P.gate_f, hp, 1, i, lb, delta);
+                    rb_verify(s_tgt, P.max_m, s_cs[g.ncells], qx, qy, qz, P.gate_f, second_wins ? hp2 : hp1, 1, i, lb, delta);
 #endif
                 }
             }
@@ -333,6 +373,10 @@ __device__ __forceinline__ void pair_pass(const PairGrid& g, const float4* __res
         nl += __popc(mask);
     }
     __syncwarp();
+    RB_T(t_p2);
+    RB_ADD(0, t_p2 - t_p1);
+    RB_ADD(6, nl);
+    RB_ADD(7, 1);
     // ---- phase 2: search the rest --------------------------------------------------------------------------------
     for (int j0 = 0; j0 < nl; j0 += 32) {
         const int j = j0 + lane;
@@ -340,36 +384,58 @@ __device__ __forceinline__ void pair_pass(const PairGrid& g, const float4* __res
             const int i = (int)list[j];
             const float4 p = s_src[i];
             double pw[3];
-            xform_point(T, p.x, p.y, p.z, pw);
+            xform_point(s_T, p.x, p.y, p.z, pw);
             const float qx = (float)pw[0], qy = (float)pw[1], qz = (float)pw[2];
             const float margin = fmaxf(g.margin, 9.5367431640625e-7f * fmaxf(fabsf(qx), fmaxf(fabsf(qy), fabsf(qz))));
-            int pos = -1;
-            float lb = 0.0f;
-            uint64_t key = KEY_EMPTY;
-            bool bounded = false;
-            if (have_prev) {
-                const int hp = (int)s_prev[i];
-                if (hp != 0xFFFF) {
-                    const float4 h = s_tgt[hp];
-                    const float hd = dist2_exact(qx, qy, qz, h.x, h.y, h.z);
-                    if (hd <= P.gate_f) {  // false for NaN; a previous neighbour outside the gate is no bound
-                        key = thread_box_nn(g, s_tgt, s_cs, qx, qy, qz, P.gate_f, margin, hd, slack, pos, lb);
-                        bounded = true;
+            // a radius that is known to hold the nearest point
+            float hd = INFINITY;
+            if (P.use_hints) {
+                if (have_prev && (int)s_h1[i] != NONE) {
+                    const int hp1 = (int)s_h1[i], hp2 = (int)s_h2[i];
+                    const float4 h1 = s_tgt[hp1];
+                    const float d1 = dist2_exact(qx, qy, qz, h1.x, h1.y, h1.z);
+                    float d2 = d1;
+                    if (hp2 != NONE) {
+                        const float4 h2 = s_tgt[hp2];
+                        d2 = dist2_exact(qx, qy, qz, h2.x, h2.y, h2.z);
                     }
+                    // the farther of the two keeps both inside the box; beyond the gate only the nearer one is a bound
+                    const float dmax = fmaxf(d1, d2), dmin = fminf(d1, d2);
+                    hd = dmax <= P.gate_f ? dmax : dmin;
+                } else {
+                    hd = own_cell_seed(g, s_tgt, s_cs, qx, qy, qz);
                 }
             }
-            if (!bounded) key = thread_shell_nn(g, s_tgt, s_cs, qx, qy, qz, P.gate_f, P.gate_r, margin, pos);
-#ifdef ICP4R_RB_VERIFY
-            rb_verify(s_tgt, P.max_m, s_cs[g.ncells], qx, qy, qz, P.gate_f, pos, bounded ? 2 : 3, i, lb, 0.f);
-#endif
-            if (P.use_hints) {
-                s_prev[i] = pos >= 0 ? (unsigned short)pos : (unsigned short)0xFFFFu;
-                s_src[i].w = lb;
+            int pos = -1;
+            float dbest = 0.0f;
+            const bool bounded = hd <= fminf(P.gate_f, 3.0e38f);  // false for NaN and for "nothing known" (INFINITY)
+            if (bounded) {
+                BoxHit hit;
+                thread_box_nn(g, s_tgt, s_cs, qx, qy, qz, margin, hd, slack, hit);
+                if (hit.d1 <= P.gate_f) {
+                    pos = hit.p1;
+                    dbest = hit.d1;
+                }
+                s_h1[i] = pos >= 0 ? (unsigned short)pos : (unsigned short)NONE;
+                s_h2[i] = (pos >= 0 && hit.p2 >= 0) ? (unsigned short)hit.p2 : (unsigned short)NONE;
+                s_src[i].w = hit.lb;
+            } else {
+                const uint64_t key = thread_shell_nn(g, s_tgt, s_cs, qx, qy, qz, P.gate_f, P.gate_r, margin, pos);
+                dbest = key_d2(key);
+                if (P.use_hints) {  // the next pass starts from this point (one remembered point, no bound on the others yet)
+                    s_h1[i] = pos >= 0 ? (unsigned short)pos : (unsigned short)NONE;
+                    s_h2[i] = (unsigned short)NONE;
+                    s_src[i].w = 0.0f;
+                }
             }
-            if (key != KEY_EMPTY) add_corr<KIND, FIT, NV>(acc, cnt, pw, s_tgt[pos], key_d2(key));
+#ifdef ICP4R_RB_VERIFY
+            rb_verify(s_tgt, P.max_m, s_cs[g.ncells], qx, qy, qz, P.gate_f, pos, bounded ? 2 : 3, i, s_src[i].w, 0.f);
+#endif
+            if (pos >= 0) add_corr<KIND, FIT, NV>(acc, cnt, pw, s_tgt[pos], dbest);
         }
     }
     if (FIT || KIND == ICP4R_P2P_SVD) acc[0] = (double)cnt;
+    RB_ADD(1, clock64() - t_p2);
 }
 
 template <int KIND, int NT>
@@ -383,7 +449,8 @@ __global__ void __launch_bounds__(NT, 2) reg_batch_kernel(const __grid_constant_
     uint32_t* s_cq = s_cs + (RB_MAXC + 2);                          // [RB_MAXC + 2] source cell cursors (spatial sort) ...
     unsigned short* s_list = reinterpret_cast<unsigned short*>(s_cq);  // ... later the per-warp lists of points to search
     const size_t cq_bytes = max((size_t)(RB_MAXC + 2) * 4, ((size_t)(P.max_n + NT) * 2 + 15) & ~(size_t)15);
-    unsigned short* s_prev = reinterpret_cast<unsigned short*>(reinterpret_cast<unsigned char*>(s_cq) + cq_bytes);  // [max_n] slot of the last neighbour
+    unsigned short* s_prev = reinterpret_cast<unsigned short*>(reinterpret_cast<unsigned char*>(s_cq) + cq_bytes);  // [max_n] slot of the nearest point of the last search
+    unsigned short* s_prev2 = s_prev + ((P.max_n + 7) & ~7);                                                         // [max_n] slot of the runner-up
     __shared__ double s_red[NW * 32];
     __shared__ double s_tot[32];
     __shared__ double s_T[16];
@@ -403,6 +470,7 @@ __global__ void __launch_bounds__(NT, 2) reg_batch_kernel(const __grid_constant_
         const float4* __restrict__ gsrc = P.src + so;
         const float4* __restrict__ gtgt = P.tgt + to;
         __syncthreads();  // previous pair fully consumed
+        RB_T(t_s0);
 
         // ---- bounding box of the target ------------------------------------------------------------------
         float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -572,20 +640,22 @@ __global__ void __launch_bounds__(NT, 2) reg_batch_kernel(const __grid_constant_
         __syncthreads();
         // now s_cs[c] = start of target cell c, s_cs[c+1] = its end; s_cq is free: it holds the search lists from here on
         const int chunk = ((n + NT - 1) / NT) * 32;  // source points per warp
+        if (w == 0) RB_ADD(4, clock64() - t_s0);
 
         // ---- iterations ---------------------------------------------------------------------------------
         for (int it = 0; it < P.max_iterations; ++it) {
             double acc[NV];
 #pragma unroll
             for (int v = 0; v < NV; ++v) acc[v] = 0.0;
-            pair_pass<KIND, false, NV>(g, s_tgt, s_src, s_cs, s_prev, s_list, s_T, s_dA, P, n, chunk, P.use_hints && it > 0, acc, lane, w);
+            pair_pass<KIND, false, NV>(g, s_tgt, s_src, s_cs, s_prev, s_prev2, s_list, s_T, s_dA, P, n, chunk, P.use_hints && it > 0, acc, lane, w);
+            RB_T(t_r0);
             block_reduce<NV, NW>(acc, s_red, s_tot, tid);
+            RB_T(t_r1);
+            RB_ADD(2, t_r1 - t_r0);
             if (KIND == ICP4R_P2P_SVD && w == 0) {
-                // Kabsch step by one WARP (one matrix row per lane, solve_warp.cuh) instead of one thread: the other
-                // warps wait at the barrier below for this, every iteration
+                // Kabsch step: the other warps wait at the barrier below for this, every iteration
                 const bool last = (it == P.max_iterations - 1);
                 const double cnt = s_tot[0];
-                double* aux = s_red;       // [9] cross-covariance
                 double* Ds = s_red + 16;   // [12] increment, 3x4 row-major
                 if (cnt < 3.0) {
                     if (lane == 0) {
@@ -595,16 +665,25 @@ __global__ void __launch_bounds__(NT, 2) reg_batch_kernel(const __grid_constant_
                         s_flags[2] = it;
                     }
                 } else {
-                    const double pm0 = s_tot[1] / cnt, pm1 = s_tot[2] / cnt, pm2 = s_tot[3] / cnt;
-                    if (lane < 9) aux[lane] = s_tot[7 + lane] / cnt - (s_tot[1 + lane / 3] / cnt) * (s_tot[4 + lane % 3] / cnt);
-                    __syncwarp();
-                    double R0, R1, R2;
-                    warp_kabsch(aux, lane, R0, R1, R2);
-                    if (lane < 3) {
-                        Ds[4 * lane + 0] = R0;
-                        Ds[4 * lane + 1] = R1;
-                        Ds[4 * lane + 2] = R2;
-                        Ds[4 * lane + 3] = s_tot[4 + lane] / cnt - ((R0 * pm0 + R1 * pm1) + R2 * pm2);
+                    // every lane solves the 3x3 problem redundantly in its own registers (solve_warp.cuh: thread_kabsch);
+                    // this is the serial tail of the iteration: latency is all that counts
+                    const double inv = 1.0 / cnt;
+                    const double pm[3] = {s_tot[1] * inv, s_tot[2] * inv, s_tot[3] * inv};
+                    const double qm[3] = {s_tot[4] * inv, s_tot[5] * inv, s_tot[6] * inv};
+                    double Hc[9], Rk[9];
+#pragma unroll
+                    for (int e = 0; e < 9; ++e) Hc[e] = s_tot[7 + e] * inv - pm[e / 3] * qm[e % 3];
+                    RB_T(t_k0);
+                    thread_kabsch(Hc, Rk);
+                    RB_ADD(5, clock64() - t_k0);
+                    if (lane == 0) {
+#pragma unroll
+                        for (int r = 0; r < 3; ++r) {
+                            Ds[4 * r + 0] = Rk[3 * r + 0];
+                            Ds[4 * r + 1] = Rk[3 * r + 1];
+                            Ds[4 * r + 2] = Rk[3 * r + 2];
+                            Ds[4 * r + 3] = qm[r] - ((Rk[3 * r + 0] * pm[0] + Rk[3 * r + 1] * pm[1]) + Rk[3 * r + 2] * pm[2]);
+                        }
                     }
                     __syncwarp();
                     const double tn = warp_compose_entry(Ds, s_T, lane);
@@ -673,6 +752,7 @@ __global__ void __launch_bounds__(NT, 2) reg_batch_kernel(const __grid_constant_
                     s_flags[2] = P.max_iterations;
                 }
             }
+            if (w == 0) RB_ADD(3, clock64() - t_r1);
             __syncthreads();
             if (s_flags[0]) break;
         }
@@ -680,7 +760,7 @@ __global__ void __launch_bounds__(NT, 2) reg_batch_kernel(const __grid_constant_
         // ---- fitness pass: mean squared 1-NN distance under the final pose --------------------------
         {
             double fa[2] = {0.0, 0.0};
-            pair_pass<KIND, true, 2>(g, s_tgt, s_src, s_cs, s_prev, s_list, s_T, s_dA, P, n, chunk, P.use_hints && P.max_iterations > 0, fa, lane, w);
+            pair_pass<KIND, true, 2>(g, s_tgt, s_src, s_cs, s_prev, s_prev2, s_list, s_T, s_dA, P, n, chunk, P.use_hints && P.max_iterations > 0, fa, lane, w);
             block_reduce<2, NW>(fa, s_red, s_tot, tid);
         }
         if (tid < 16) T_out[(size_t)pair * 16 + tid] = s_T[tid];
@@ -708,6 +788,17 @@ static int launch_batch(Ctx* c, const BatchParams& P, size_t smem, double* d_T, 
     kern<<<blocks, NT, smem, c->stream>>>(P, d_T, d_res);
     c->launches += 1;
     CK(cudaGetLastError());
+#ifdef ICP4R_RB_TIMING
+    {
+        unsigned long long h[12], z[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        cudaStreamSynchronize(c->stream);
+        cudaMemcpyFromSymbol(h, rb_prof, sizeof(h));
+        cudaMemcpyToSymbol(rb_prof, z, sizeof(z));
+        const double np = (double)P.n_pairs, nw = NT / 32;
+        fprintf(stderr, "[rb timing] per pair, cycles averaged over warps: phase1 %.0f  phase2 %.0f  reduce+wait %.0f | warp 0: solve %.0f setup %.0f | searched points per pair %.0f, passes %.1f | kabsch %.0f cycles per pair\n",
+                h[0] / np / nw, h[1] / np / nw, h[2] / np / nw, h[3] / np, h[4] / np, h[6] / np, h[7] / np / nw, h[5] / np);
+    }
+#endif
     return ICP4R_OK;
 }
 
@@ -721,7 +812,7 @@ int register_batch(Ctx* c, const float4* d_src, const int32_t* d_soff, const flo
     if (nt != 256 && nt != 384 && nt != 512) nt = 256;
     const size_t cq_bytes = std::max((size_t)(RB_MAXC + 2) * 4, ((size_t)(std::max(max_n, 1) + nt) * 2 + 15) & ~(size_t)15);
     const size_t smem = (size_t)(std::max(max_m, 1) + std::max(max_n, 1)) * sizeof(float4) + (RB_MAXC + 2) * sizeof(uint32_t) + cq_bytes +
-                        (((size_t)std::max(max_n, 1) * sizeof(unsigned short) + 15) & ~(size_t)15);
+                        2 * (size_t)((std::max(max_n, 1) + 7) & ~7) * sizeof(unsigned short);
     if (smem > 200 * 1024)
         return fail(c, ICP4R_ERR_UNSUPPORTED, "pair too large for the shared-memory resident kernel (%zu B); use icp4r_register", smem);
     BatchParams P;

@@ -51,19 +51,23 @@ __device__ __forceinline__ void warp_solve_and_update(int residual, const RegPar
             }
             return;
         }
-        const double pm0 = tot[1] / cnt, pm1 = tot[2] / cnt, pm2 = tot[3] / cnt;
-        if (lane < 9) {
-            const int r = lane / 3, c = lane % 3;
-            aux[lane] = tot[7 + lane] / cnt - (tot[1 + r] / cnt) * (tot[4 + c] / cnt);
-        }
-        __syncwarp();
-        double R0, R1, R2;
-        warp_kabsch(aux, lane, R0, R1, R2);
-        if (lane < 3) {
-            Ds[4 * lane + 0] = R0;
-            Ds[4 * lane + 1] = R1;
-            Ds[4 * lane + 2] = R2;
-            Ds[4 * lane + 3] = tot[4 + lane] / cnt - ((R0 * pm0 + R1 * pm1) + R2 * pm2);
+        // every lane solves the 3x3 problem redundantly in its own registers (thread_kabsch): no lane-to-lane exchange
+        // on this serial tail of the iteration
+        const double inv = 1.0 / cnt;
+        const double pm[3] = {tot[1] * inv, tot[2] * inv, tot[3] * inv};
+        const double qm[3] = {tot[4] * inv, tot[5] * inv, tot[6] * inv};
+        double Hc[9], Rk[9];
+#pragma unroll
+        for (int e = 0; e < 9; ++e) Hc[e] = tot[7 + e] * inv - pm[e / 3] * qm[e % 3];
+        thread_kabsch(Hc, Rk);
+        if (lane == 0) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                Ds[4 * r + 0] = Rk[3 * r + 0];
+                Ds[4 * r + 1] = Rk[3 * r + 1];
+                Ds[4 * r + 2] = Rk[3 * r + 2];
+                Ds[4 * r + 3] = qm[r] - ((Rk[3 * r + 0] * pm[0] + Rk[3 * r + 1] * pm[1]) + Rk[3 * r + 2] * pm[2]);
+            }
         }
         __syncwarp();
         const double tn = warp_compose_entry(Ds, Ts, lane);

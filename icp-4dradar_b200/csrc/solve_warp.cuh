@@ -118,15 +118,31 @@ __device__ __forceinline__ double sum3(double v) {  // sum over lanes 0..3 (lane
 // lane i < 3 holding row i of the working matrix A and of V (H V = U S). R = V U^T with the column of the smallest
 // singular value rebuilt by cross products so det R = +1 (Umeyama's reflection fix). Row i of R is returned in
 // lane i (R0, R1, R2).
-__device__ __forceinline__ void warp_kabsch(const double* __restrict__ Hs, int lane, double& R0, double& R1, double& R2) {
+//
+// Vw (optional, 9 doubles in shared memory, row-major): warm start. The batched-pairs loop solves 30 nearly identical
+// problems in a row; starting from the V of the previous one (A = H V, already almost column-orthogonal) the sweeps end
+// after one or two instead of six to eight. V is written back. The rotation returned is the same (V U^T does not
+// depend on the order or sign of the singular vectors).
+__device__ __forceinline__ void warp_kabsch(const double* __restrict__ Hs, int lane, double& R0, double& R1, double& R2,
+                                            double* __restrict__ Vw = nullptr, int* sweeps_out = nullptr) {
     // every group of 4 lanes holds the same 3 rows (+ a zero lane), so the whole warp stays converged
     const int i = lane & 3;
     const bool rowlane = i < 3;
     double a[3], v[3];
+    if (Vw == nullptr) {
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        a[j] = rowlane ? Hs[3 * (rowlane ? i : 0) + j] : 0.0;
-        v[j] = (rowlane && i == j) ? 1.0 : 0.0;
+        for (int j = 0; j < 3; ++j) {
+            a[j] = rowlane ? Hs[3 * (rowlane ? i : 0) + j] : 0.0;
+            v[j] = (rowlane && i == j) ? 1.0 : 0.0;
+        }
+    } else {
+        const int r = rowlane ? i : 0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            a[j] = rowlane ? (Hs[3 * r + 0] * Vw[j] + Hs[3 * r + 1] * Vw[3 + j]) + Hs[3 * r + 2] * Vw[6 + j] : 0.0;
+            v[j] = rowlane ? Vw[3 * r + j] : 0.0;
+        }
+        __syncwarp();
     }
     for (int sweep = 0; sweep < 30; ++sweep) {
         double off = 0.0;
@@ -150,7 +166,12 @@ __device__ __forceinline__ void warp_kabsch(const double* __restrict__ Hs, int l
             v[p] = c * vp - s * vq;
             v[q] = s * vp + c * vq;
         }
+        if (sweeps_out) *sweeps_out = sweep + 1;
         if (off == 0.0) break;
+    }
+    if (Vw != nullptr && lane < 3) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) Vw[3 * lane + j] = v[j];
     }
     double sg[3];
 #pragma unroll
@@ -195,6 +216,90 @@ __device__ __forceinline__ void warp_kabsch(const double* __restrict__ Hs, int l
     R0 = vai * ua[0] + vbi * ub[0] + vci * uc[0];
     R1 = vai * ua[1] + vbi * ub[1] + vci * uc[1];
     R2 = vai * ua[2] + vbi * ub[2] + vci * uc[2];
+}
+
+// The same Kabsch rotation computed by ONE thread with the whole 3x3 problem in registers: no shuffles on the critical
+// path (each of the ~30 lane-to-lane exchanges of the warp version costs more than the arithmetic between them), no
+// divisions or square roots (reciprocal square roots only), the convergence test without a square root.
+// H row-major; R row-major. Every thread of a warp may call it redundantly (warp-uniform control flow).
+__device__ __forceinline__ void thread_kabsch(const double* __restrict__ H, double R[9]) {
+    double a[3][3], v[3][3];  // columns: a[j] = j-th column of A = H V, v[j] = j-th column of V
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            a[j][i] = H[3 * i + j];
+            v[j][i] = i == j ? 1.0 : 0.0;
+        }
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        bool rotated = false;
+#pragma unroll
+        for (int pq = 0; pq < 3; ++pq) {
+            const int p = pq == 2 ? 1 : 0, q = pq == 0 ? 1 : 2;  // (0,1), (0,2), (1,2)
+            const double al = (a[p][0] * a[p][0] + a[p][1] * a[p][1]) + a[p][2] * a[p][2];
+            const double be = (a[q][0] * a[q][0] + a[q][1] * a[q][1]) + a[q][2] * a[q][2];
+            const double ga = (a[p][0] * a[q][0] + a[p][1] * a[q][1]) + a[p][2] * a[q][2];
+            if (fabs(ga) <= 1e-300 || ga * ga <= 1e-32 * (al * be)) continue;
+            rotated = true;
+            // rotation that zeroes a_p . a_q: tan 2t = 2 ga / (be - al), |t| <= pi/4
+            const double dd = be - al, g2 = 2.0 * ga;
+            const double invh = rsqrt(dd * dd + g2 * g2);      // 1 / hypot(dd, g2)
+            const double c2 = 0.5 + 0.5 * fabs(dd) * invh;     // cos^2 t
+            const double invc = rsqrt(c2);
+            const double c = c2 * invc;
+            const double s = (dd >= 0 ? 0.5 : -0.5) * g2 * invh * invc;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const double ap = a[p][i], aq = a[q][i], vp = v[p][i], vq = v[q][i];
+                a[p][i] = c * ap - s * aq;
+                a[q][i] = s * ap + c * aq;
+                v[p][i] = c * vp - s * vq;
+                v[q][i] = s * vp + c * vq;
+            }
+        }
+        if (!rotated) break;
+    }
+    double n2[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) n2[j] = (a[j][0] * a[j][0] + a[j][1] * a[j][1]) + a[j][2] * a[j][2];
+    int cc = 0;
+    if (n2[1] < n2[cc]) cc = 1;
+    if (n2[2] < n2[cc]) cc = 2;
+    // the two dominant columns, selected without dynamic register indexing
+    double ua[3], ub[3], va[3], vb[3], na, nb;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        ua[i] = cc == 0 ? a[1][i] : (cc == 1 ? a[2][i] : a[0][i]);
+        ub[i] = cc == 0 ? a[2][i] : (cc == 1 ? a[0][i] : a[1][i]);
+        va[i] = cc == 0 ? v[1][i] : (cc == 1 ? v[2][i] : v[0][i]);
+        vb[i] = cc == 0 ? v[2][i] : (cc == 1 ? v[0][i] : v[1][i]);
+    }
+    na = cc == 0 ? n2[1] : (cc == 1 ? n2[2] : n2[0]);
+    nb = cc == 0 ? n2[2] : (cc == 1 ? n2[0] : n2[1]);
+    if (!(na > 0.0) || !(nb > 0.0)) {  // rank < 2: rotation undefined -> identity
+#pragma unroll
+        for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+        return;
+    }
+    const double ia = rsqrt(na), ib = rsqrt(nb);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        ua[i] *= ia;
+        ub[i] *= ib;
+    }
+    const double dab = (ua[0] * ub[0] + ua[1] * ub[1]) + ua[2] * ub[2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) ub[i] -= dab * ua[i];
+    const double inb = rsqrt((ub[0] * ub[0] + ub[1] * ub[1]) + ub[2] * ub[2]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) ub[i] *= inb;
+    double uc[3], vc[3];
+    cross3(ua, ub, uc);  // the third pair rebuilt by cross products: det R = +1 (Umeyama's reflection fix)
+    cross3(va, vb, vc);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) R[3 * i + j] = (va[i] * ua[j] + vb[i] * ub[j]) + vc[i] * uc[j];
 }
 
 }  // namespace icp4r

@@ -32,3 +32,11 @@ def handle(pkg):
     h = pkg.Icp4r(0)
     yield h
     h.close()
+
+
+def rot_angle(R):
+    """rotation angle of a 3x3 rotation matrix, accurate for tiny angles (arccos of the trace has a 1.5e-8 noise floor)"""
+    import numpy as np
+    R = np.asarray(R, np.float64)
+    s = 0.5 * np.sqrt((R[2, 1] - R[1, 2]) ** 2 + (R[0, 2] - R[2, 0]) ** 2 + (R[1, 0] - R[0, 1]) ** 2)
+    return float(np.arctan2(s, (np.trace(R) - 1) / 2))

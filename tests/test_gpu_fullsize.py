@@ -5,15 +5,12 @@ import os
 import sys
 
 import numpy as np
+from conftest import rot_angle
 import pytest
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-
-
-def rot_angle(R):
-    return float(np.arccos(np.clip((np.trace(R) - 1) / 2, -1, 1)))
 
 
 def test_c5_full_size_properties(pkg, handle):

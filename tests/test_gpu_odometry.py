@@ -1,6 +1,7 @@
 """GPU parity: the scan-to-map odometry loop (BASELINE config 3, scaled down) — register against the growing map,
 transform, Add_Points(false) — against the same loop on the CPU oracle with the reference's ikd-Tree as the map."""
 import numpy as np
+from conftest import rot_angle
 import pytest
 
 pytestmark = pytest.mark.gpu
@@ -39,7 +40,7 @@ def test_odometry_sequence_matches_oracle(pkg, O, handle):
     assert handle.map_size() == (total, total)
     for f, (a, b) in enumerate(zip(got, want)):
         D = a @ np.linalg.inv(b)
-        ang = np.arccos(np.clip((np.trace(D[:3, :3]) - 1) / 2, -1, 1))
+        ang = rot_angle(D[:3, :3])
         assert np.linalg.norm(D[:3, 3]) <= 1e-4 and ang <= 1e-4, (f, np.linalg.norm(D[:3, 3]), ang)
     # and the loop really tracks the trajectory (sanity of the synthetic sequence, not a parity bar)
     drift = np.linalg.norm(got[-1][:3, 3] - (np.linalg.inv(gt[0]) @ gt[-1])[:3, 3])
@@ -87,7 +88,7 @@ def test_scan_to_scan_node_matches_oracle(pkg, O, handle):
         assert np.allclose(vel_b[f], vel_o[f], rtol=1e-9, atol=1e-12)
         for got in (poses_b[f], poses_s[f]):
             D = got @ np.linalg.inv(poses_o[f])
-            ang = np.arccos(np.clip((np.trace(D[:3, :3]) - 1) / 2, -1, 1))
+            ang = rot_angle(D[:3, :3])
             assert np.linalg.norm(D[:3, 3]) <= 1e-4 and ang <= 1e-4, f
     # the least-squares velocity is that of the static world relative to the sensor (the reference solves K v = v_r
     # with v_r = -u . v_ego): opposite to the motion along +x, ~0.4 m per 0.1 s frame

@@ -4,6 +4,7 @@ Bars (north_star): correspondence indices bit-exact; per-iteration J^T J / J^T r
 final pose within 1e-4 m / 1e-4 rad after the fixed iteration count.
 """
 import numpy as np
+from conftest import rot_angle
 import pytest
 
 pytestmark = pytest.mark.gpu
@@ -15,7 +16,7 @@ ACC_RTOL = 1e-5
 
 def pose_err(A, B):
     D = A @ np.linalg.inv(B)
-    ang = np.arccos(np.clip((np.trace(D[:3, :3]) - 1) / 2, -1, 1))
+    ang = rot_angle(D[:3, :3])
     return np.linalg.norm(D[:3, 3]), ang
 
 
