@@ -2,20 +2,23 @@
 """bench.py — registrations/s and NN queries/s of the registration hot path on B200, with the reference's
 CPU path timed beside it.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload all|c1|c2|c2single|c3|c4|c5|gicp]
 
-Workload (default, BASELINE.json configs[1] = "C2"): one step = ONE scan-to-map registration, a 4,096-point
-synthetic 4D-radar scan against a resident 200,000-point map, point-to-plane with k = 5 neighbours
-(LidarPlaneNormFactor), 20 iterations, 2.0 m gate.  The map is built once and stays resident in HBM like the
-reference's ikd-Tree stays resident in RAM; scans rotate through a pool of 8 different scans.
-  value : registrations/s with the scan already in HBM (device pointer through the C ABI)
-  e2e   : the same through the C ABI with a HOST scan buffer: pinned host -> device copy of the scan, the
-          registration, device -> host copy of the pose/result, all inside the timed region
-N > 1 (torchrun): every rank registers its own stream of scans against its own replica of the map — independent
-units, no collective on the data path ("scaling": "weak"); value = all ranks' registrations / max-over-ranks time.
-`--workload c4` times BASELINE.json configs[3] instead (batched frame pairs, one CTA per pair).
-`--impl reference` times the reference's own CPU implementation of the path: its ikd-Tree (compiled unmodified,
-oracle/_ref) for the neighbour search + the restated Gauss-Newton loop, on all host cores, same workload.
+Default (`--workload all`): the headline line is BASELINE.json configs[3] ("C4", the config the metric "at 1/2/4/8
+B200" is quoted on and that fits one GPU): ONE fixed job of 65,536 independent frame pairs (2,048 + 2,048 points,
+point-to-point ICP, 30 iterations, ungated) split by pair range across the ranks, no collective ("scaling":
+"strong"). One step = the whole job.
+  value : registrations/s with the clouds already in HBM (device pointers through the C ABI)
+  e2e   : the same through the C ABI with pinned HOST clouds: host->device copy of both clouds (4.3 GB per step,
+          chunked on a second stream ahead of the kernels), the registrations, device->host copy of poses/results
+At N = 1 the same JSON line carries `configs`: one sub-record per other BASELINE config — c1 (single 1,024-pt pair),
+c2_single / c2_batch16 (4,096-pt scan vs resident 200 k-pt map, one scan per call / 16 scans per call), c3 (2,000-frame
+odometry sequence), c5 (16,384-pt scan vs 20 M-pt map) and gicp — each with value, e2e, roofline and cpu_baseline.
+At N > 1 `configs` carries c5 sharded in N x-slabs with the cross-rank sum inside the iteration kernel over NVLink
+peer memory (`--exchange nccl` for the NCCL all-reduce flavour).
+`--workload <one>` makes that config the headline line instead (c2: N > 1 = replicas, weak scaling).
+`--impl reference` times the reference's own CPU implementation of the headline path: its ikd-Tree (compiled
+unmodified, oracle/_ref) for the neighbour search + the restated Kabsch / Gauss-Newton loop, on all host cores.
 """
 import argparse
 import json
@@ -23,8 +26,8 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -32,8 +35,19 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_SCAN, N_MAP, K_NN, ITERS, GATE = 4096, 200000, 5, 20, 2.0
-C4_N, C4_ITERS = 2048, 30
-POOL = 16   # distinct scans; one C2 step registers all of them against the resident map in ONE call
+C1_N, C1_ITERS = 1024, 30
+C4_N, C4_ITERS, C4_PAIRS = 2048, 30, 65536
+C5_N, C5_ITERS = 16384, 20
+POOL = 16   # distinct scans; one c2_batch16 step registers all of them against the resident map in ONE call
+FP32_LANES_PER_S = 148 * 128 * 1.965e9   # fp32 lane-instructions per second of one B200 at the maximum SM clock
+DIST_EVAL_FP32 = 8                       # sub x3, mul x3, add x2 per squared distance (no FMA: bit-exact with the reference)
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
 
 
 def peaks():
@@ -43,6 +57,37 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_facts(kernel_key):
+    """per-launch DRAM traffic and issue statistics of a kernel from this round's ncu --set full capture
+    (profiles/r2_ncu_facts.json, written by scripts/ncu_facts.py from the .ncu-rep; None if not captured)"""
+    p = os.path.join(ROOT, "profiles", "r2_ncu_facts.json")
+    if not os.path.exists(p):
+        return None
+    return json.load(open(p)).get(kernel_key)
+
+
+def roofline(kernel, kernel_key, alg_bytes, kernel_ms, note, dist_evals=None, extra=None):
+    peak, peak_src = peaks()
+    ach = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    facts = ncu_facts(kernel_key)
+    r = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+         "traffic": (facts["dram_bytes_read"] + facts["dram_bytes_write"]) if facts else None,
+         "kernel": kernel, "kernel_ms": kernel_ms, "algorithmic_bytes": int(alg_bytes), "peak_source": peak_src, "note": note}
+    if facts:
+        r["ncu"] = {k: facts[k] for k in facts if k not in ("dram_bytes_read", "dram_bytes_write")}
+    if dist_evals is not None:
+        # compute-side bound for a cache-resident kernel (SURVEY.md §8(d)): squared-distance evaluations per second
+        # against what the fp32 pipes could issue if they did nothing else
+        ceil = FP32_LANES_PER_S / DIST_EVAL_FP32
+        rate = dist_evals / (kernel_ms * 1e-3)
+        r["compute"] = {"dist_evals_per_launch": int(dist_evals), "dist_evals_per_s": rate, "fp32_ceiling_evals_per_s": ceil,
+                        "frac": rate / ceil}
+    if extra:
+        r.update(extra)
+    return r
+
+
+# --------------------------------------------------------------------------------------------------- generators
 def make_c2(seed=1002):
     from icp4r_loader import pkg
     s = pkg.synth
@@ -57,12 +102,8 @@ def make_c2(seed=1002):
     return mp, scans
 
 
-NCU_TRAFFIC_BYTES = 7_582_208 + 537_600  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r1_c2_reg_iter_kernel_ncu.txt (cold-cache replay)
-C5_N, C5_ITERS = 16384, 20
-
-
 def make_c5(m, seed=1005):
-    """C5: dense map, uniform volume density over 400 x 400 x 20 m (6.25 pts/m^3 at 20 M), and a 16,384-pt scan drawn
+    """C5: dense map, uniform volume density over 400 x 400 x 20 m (6.25 pts/m^3 at 20 M), and 16,384-pt scans drawn
     from the map's own surfaces (a random subset + 2 cm noise) moved by a small rigid transform."""
     from icp4r_loader import pkg
     s = pkg.synth
@@ -77,27 +118,28 @@ def make_c5(m, seed=1005):
     return mp, scans
 
 
-def make_c4(n_pairs, seed=1004, with_offsets=False):
-    """n_pairs frame pairs of 2,048 points: 64 distinct scenes, each re-used with a different rigid offset of the
-    source (generating 65,536 scenes on the host would dominate the run). with_offsets: also return those offsets
-    [n_pairs,4,4] (identity for the first 64 pairs)."""
+def make_c4(n_pairs, seed=1004, with_offsets=False, first=0):
+    """frame pairs [first, first + n_pairs) of the C4 job, 2,048 points per cloud: 64 distinct scenes, each re-used with
+    a different rigid offset of the source (generating 65,536 scenes on the host would dominate the run); pair p
+    depends on (seed, p) only, so every rank generates exactly its own range. with_offsets: also return those offsets
+    [n_pairs,4,4] (identity for the pairs 0..63)."""
     from icp4r_loader import pkg
     s = pkg.synth
     base = [s.frame_pair(seed + i, C4_N) for i in range(64)]
-    rng = np.random.default_rng(seed)
     src = np.empty((n_pairs * C4_N, 4), np.float32)
     tgt = np.empty((n_pairs * C4_N, 4), np.float32)
     D = np.tile(np.eye(4), (n_pairs, 1, 1)) if with_offsets else None
-    for p in range(n_pairs):
+    for j in range(n_pairs):
+        p = first + j
         a, b, _ = base[p % 64]
         if p >= 64:
-            Dp = s.random_small_se3(rng, 0.3, 2.0)
-            src[p * C4_N:(p + 1) * C4_N] = s.apply(Dp, a)
+            Dp = s.random_small_se3(np.random.default_rng((seed, p)), 0.3, 2.0)
+            src[j * C4_N:(j + 1) * C4_N] = s.apply(Dp, a)
             if with_offsets:
-                D[p] = Dp
+                D[j] = Dp
         else:
-            src[p * C4_N:(p + 1) * C4_N] = a
-        tgt[p * C4_N:(p + 1) * C4_N] = b
+            src[j * C4_N:(j + 1) * C4_N] = a
+        tgt[j * C4_N:(j + 1) * C4_N] = b
     off = (np.arange(n_pairs + 1) * C4_N).astype(np.int32)
     return (src, tgt, off, D) if with_offsets else (src, tgt, off)
 
@@ -165,80 +207,586 @@ class quiet_c_stdout:
         os.close(self.saved)
 
 
-def cpu_reference_c2(mp, scans, budget_s, max_regs, threads):
-    with quiet_c_stdout():
-        return _cpu_reference_c2(mp, scans, budget_s, max_regs, threads)
+# --------------------------------------------------------------------------------------------------- CPU legs
+# Every CPU leg runs the reference's own ikd-Tree (compiled unmodified, oracle/_ref: kind "reference") for Build /
+# Add_Points / Nearest_Search when it travelled with the repo, else the oracle's exhaustive search (kind "port"),
+# plus the restated solve loop of oracle/oracle.c. PCL, FLANN and fast_gicp are absent from the image.
 
-
-def _cpu_reference_c2(mp, scans, budget_s, max_regs, threads):
-    """The reference's CPU path for this workload: ikd-Tree Build once (resident map), then per registration
-    20 x { 4,096 Nearest_Search(k=5, 2.0 m) on `threads` threads + plane fit + 6x6 Gauss-Newton }."""
+def cpu_c2(mp, scans, budget_s, max_regs, threads, residual=None, k=K_NN, iters=ITERS, gate=GATE, early_exit=0):
+    """ikd-Tree Build once (resident map), then per registration iters x { Nearest_Search on `threads` threads + solve }"""
     import oracle as O
-    oo = O.default_opts(residual=O.P2PLANE_KNN, k=K_NN, max_iterations=ITERS, max_corr_dist=GATE)
-    if O.have_ref():
-        kind, searcher = "reference", O.IkdTree(nthreads=threads)
-        searcher.build(mp)
-    else:
-        kind, searcher = "port", O.BruteSearcher(mp)
-        threads = O.num_threads()
-    times = []
-    t_all = time.perf_counter()
-    i = 0
-    while i < max_regs and (time.perf_counter() - t_all) < budget_s:
-        t0 = time.perf_counter()
-        O.register(scans[i % len(scans)], mp, oo, searcher=searcher)
-        times.append(time.perf_counter() - t0)
-        i += 1
-    if hasattr(searcher, "close"):
-        searcher.close()
+    with quiet_c_stdout():
+        oo = O.default_opts(residual=O.P2PLANE_KNN if residual is None else residual, k=k, max_iterations=iters, max_corr_dist=gate,
+                            early_exit=early_exit)
+        if O.have_ref():
+            kind, searcher = "reference", O.IkdTree(nthreads=threads)
+            searcher.build(mp)
+        else:
+            kind, searcher = "port", O.BruteSearcher(mp)
+            threads = O.num_threads()
+        times = []
+        t_all = time.perf_counter()
+        i = 0
+        while i < max_regs and (time.perf_counter() - t_all) < budget_s:
+            t0 = time.perf_counter()
+            O.register(scans[i % len(scans)], mp, oo, searcher=searcher)
+            times.append(time.perf_counter() - t0)
+            i += 1
+        if hasattr(searcher, "close"):
+            searcher.close()
     return kind, threads, times
 
 
+def cpu_pairs(src, tgt, n_pts, iters, budget_s, threads, max_pairs=1 << 30):
+    """frame pairs one after the other on each of `threads` host threads: ikd-Tree Build + iters x 1-NN + Kabsch per pair.
+    Returns (kind, pairs done, seconds)."""
+    import oracle as O
+    oo = O.default_opts(residual=O.P2P_SVD, max_iterations=iters)
+    n_avail = min(len(src) // n_pts, max_pairs)
+    use_ref = O.have_ref()
+    t0 = time.perf_counter()
+
+    def one(p):
+        if time.perf_counter() - t0 > budget_s:
+            return 0
+        a, b = src[p * n_pts:(p + 1) * n_pts], tgt[p * n_pts:(p + 1) * n_pts]
+        s = None
+        if use_ref:
+            s = O.IkdTree(nthreads=1)
+            s.build(b)
+        O.register(a, b, oo, searcher=s)   # ctypes releases the GIL for the duration of the call
+        if s is not None:
+            s.close()
+        return 1
+
+    with quiet_c_stdout():
+        if threads == 1:
+            done = 0
+            for p in range(n_avail):
+                r = one(p)
+                if not r:
+                    break
+                done += r
+        else:
+            with ThreadPoolExecutor(threads) as ex:
+                done = sum(ex.map(one, range(n_avail)))
+    return ("reference" if use_ref else "port"), done, time.perf_counter() - t0
+
+
+def cpu_c3(seq, budget_s, threads):
+    """the odometry loop on the host: ikd-Tree Build, then per frame register (Nearest_Search on all threads + the
+    Gauss-Newton loop), transform, Add_Points(.., false). Every frame is timed until a quarter of the budget is gone, then
+    every stride-th frame — with the frames in between inserted untimed at the last estimated pose — so that the sample
+    spreads over the whole sequence with the tree grown to each timed frame's size instead of stopping while it is small.
+    Returns (kind, frames timed, seconds timed, last frame reached)."""
+    import oracle as O
+    oo = O.default_opts(residual=O.P2PLANE_KNN, k=K_NN, max_iterations=ITERS, max_corr_dist=GATE)
+    use_ref = O.have_ref()
+    buf = np.empty((int(sum(len(s) for s in seq)), 4), np.float32)   # the map in insertion order (neighbour indices refer to it)
+    with quiet_c_stdout():
+        T = np.eye(4)
+        w0, _ = O.transform(T, seq[0])
+        n = len(w0)
+        buf[:n] = w0
+        tree = None
+        if use_ref:
+            tree = O.IkdTree(nthreads=threads)
+            tree.build(w0)
+        t0 = time.perf_counter()
+        timed_s, cnt, stride, f = 0.0, 0, 1, 0
+        for f, scan in enumerate(seq[1:], 1):
+            if f % stride == 0:
+                ta = time.perf_counter()
+                for i in range(16):
+                    oo.T0[i] = float(T.reshape(16)[i])
+                T, _r, _ = O.register(scan, buf[:n], oo, searcher=tree)
+                wv, _ = O.transform(T, scan)
+                if tree is not None:
+                    tree.add_points(wv, False)
+                timed_s += time.perf_counter() - ta
+                cnt += 1
+            else:
+                wv, _ = O.transform(T, scan)
+                if tree is not None:
+                    tree.add_points(wv, False)
+            buf[n:n + len(wv)] = wv
+            n += len(wv)
+            el = time.perf_counter() - t0
+            if stride == 1 and el > budget_s * 0.25:
+                left = len(seq) - 1 - f
+                per = timed_s / max(cnt, 1)
+                stride = max(1, int(np.ceil(left * per / max(budget_s * 0.6, 1e-3))))
+            if el > budget_s * 1.5:
+                break
+        if tree is not None:
+            tree.close()
+    return ("reference" if use_ref else "port"), cnt, timed_s, f
+
+
 def run_reference(args, rank, world):
+    """the reference arm: the headline workload on the host cores (rank 0 only)"""
     if rank != 0:
         return
+    threads = host_threads()
+    wl = "c4" if args.workload == "all" else args.workload
+    if wl == "c4":
+        # each step = a bounded sample of the 65,536-pair job: `threads` pairs in flight, ~20 s per step
+        n_sample = max(threads * 4, 64)
+        src, tgt, off = make_c4(n_sample)
+        kind, done, secs = cpu_pairs(src, tgt, C4_N, C4_ITERS, 20.0 * max(args.warmup, 1), threads, n_sample)   # warm-up
+        tot_done, tot_secs = 0, 0.0
+        for _ in range(args.steps):
+            kind, done, secs = cpu_pairs(src, tgt, C4_N, C4_ITERS, 20.0, threads, n_sample)
+            tot_done += done
+            tot_secs += secs
+            if tot_secs > 120.0:
+                break
+        v = tot_done / tot_secs
+        line = {"impl": "reference", "metric": "registrations/s", "value": v, "unit": "registrations/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * C4_PAIRS / v, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "nn_queries_per_s": v * C4_ITERS * C4_N,
+                "config": c4_config(args.pairs, 1),
+                "cpu_baseline": {"value": v, "unit": "registrations/s", "cores": threads, "kind": kind,
+                                 "sample": f"{tot_done} pairs of the job ({n_sample} distinct), one pair per host thread at a time: ikd-Tree Build + "
+                                           "30 x 1-NN + Kabsch each; ms_per_step extrapolates to the 65,536-pair job; PCL/FLANN absent from the image"},
+                "e2e": {"value": v, "unit": "registrations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+    # C2 (and the other scan-to-map shapes): one registration after the other, Nearest_Search on all host threads
     mp, scans = make_c2()
-    threads = os.cpu_count() or 1
-    try:
-        threads = len(os.sched_getaffinity(0))
-    except Exception:
-        pass
-    # warm-up + timed steps, bounded to a few minutes in total
-    # one step = POOL registrations (the scans of one batch of our arm), run one after the other on all host threads;
-    # warm-up + timed steps bounded to a few minutes in total
-    kind, threads, _ = cpu_reference_c2(mp, scans, 30.0, max(args.warmup, 1), threads)
-    kind, threads, times = cpu_reference_c2(mp, scans, 150.0, args.steps * POOL, threads)
+    cpu_c2(mp, scans, 30.0, max(args.warmup, 1), threads)
+    kind, threads, times = cpu_c2(mp, scans, 150.0, args.steps * POOL, threads)
     total = float(np.sum(times))
     v = len(times) / total
-    nsteps = max(len(times) // POOL, 1)
-    line = {
-        "impl": "reference", "metric": "registrations/s", "value": v, "unit": "registrations/s", "n_gpus": args.gpus,
-        "steps": nsteps, "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * total / len(times) * POOL, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "nn_queries_per_s": v * ITERS * N_SCAN,
-        "config": {"workload": "C2 scan-to-map: 4096-pt scans vs resident 200000-pt map, P2PLANE k=5, 20 iters, gate 2.0 m",
-                   "n": N_SCAN, "m": N_MAP, "k": K_NN, "iterations": ITERS, "max_corr_dist": GATE, "batch_scans": POOL,
-                   "step": f"{POOL} registrations, one after the other, each on all host threads"},
-        "cpu_baseline": {"value": v, "unit": "registrations/s", "cores": threads, "kind": kind,
-                         "sample": f"{len(times)} registrations; ikd-Tree Build excluded (resident map); PCL/fast_gicp absent from the image"},
-        "e2e": {"value": v, "unit": "registrations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }
+    line = {"impl": "reference", "metric": "registrations/s", "value": v, "unit": "registrations/s", "n_gpus": args.gpus,
+            "steps": max(len(times) // POOL, 1), "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * total / len(times) * POOL,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "nn_queries_per_s": v * ITERS * N_SCAN, "config": c2_config(1, True),
+            "cpu_baseline": {"value": v, "unit": "registrations/s", "cores": threads, "kind": kind,
+                             "sample": f"{len(times)} registrations; ikd-Tree Build excluded (resident map); PCL/fast_gicp absent from the image"},
+            "e2e": {"value": v, "unit": "registrations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def c4_config(pairs, world):
+    return {"workload": f"C4 batched registration: ONE job of {pairs} independent frame pairs, 2048 + 2048 pts each, P2P_SVD, 30 iterations, "
+                        f"ungated, split by pair range across {world} GPU(s), no collective",
+            "pairs": pairs, "n": C4_N, "m": C4_N, "iterations": C4_ITERS, "step": "the whole job",
+            "l2": "inputs (%.0f MB per step and GPU) exceed L2; flushed anyway" % (2 * pairs / world * C4_N * 16 / 1e6)}
+
+
+def c2_config(world, batch):
+    c = {"workload": "C2 scan-to-map: 4096-pt scans vs resident 200000-pt map, P2PLANE k=5, 20 iters, gate 2.0 m",
+         "n": N_SCAN, "m": N_MAP, "k": K_NN, "iterations": ITERS, "max_corr_dist": GATE,
+         "l2": "flushed before every timed step (256 MiB fill, untimed)", "replicas": world}
+    if batch:
+        c.update(batch_scans=POOL, step=f"{POOL} independent scans registered in one icp4r_register_map_batch call")
+    else:
+        c.update(step="one scan per icp4r_register_map call")
+    return c
+
+
+# --------------------------------------------------------------------------------------------------- GPU legs
+class Bench:
+    def __init__(self, args, rank, world, local):
+        import torch
+        import torch.distributed as dist
+        from icp4r_loader import pkg
+        self.torch, self.dist, self.pkg = torch, dist, pkg
+        self.args, self.rank, self.world, self.local = args, rank, world, local
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: libicp4r_cuda has no CPU fallback")
+        torch.cuda.set_device(local)
+        self.dev = torch.device("cuda", local)
+        if world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.h = pkg.Icp4r(local)
+        self.stream = torch.cuda.Stream(device=self.dev)
+        self.h.set_stream(self.stream.cuda_stream)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)  # > 126 MB L2
+        self.threads = host_threads()
+
+    def barrier(self):
+        self.torch.cuda.synchronize(self.dev)
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def timed(self, fn, steps):
+        """per-step device times (CUDA events on the launching stream); L2 flushed, untimed, before each"""
+        torch = self.torch
+        evs = []
+        with torch.cuda.stream(self.stream):
+            for i in range(steps):
+                self.flush.fill_(i & 0xff)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(self.stream)
+                fn(i)
+                e1.record(self.stream)
+                evs.append((e0, e1))
+        torch.cuda.synchronize(self.dev)
+        return [a.elapsed_time(b) for a, b in evs]
+
+    def max_over_ranks(self, x):
+        if self.world == 1:
+            return float(x)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def measure(self, step_dev, step_e2e, steps, warmup, units_total, sample_clocks=False):
+        """warm-up, K timed device-resident steps, then the same through host buffers. units_total = units of work the
+        WHOLE job (all ranks) completes per step. Returns a dict with value / e2e / launches / clocks."""
+        self.timed(step_dev, warmup)
+        self.barrier()
+        sampler = ClockSampler(self.local) if (sample_clocks and self.rank == 0) else None
+        l0 = self.h.launch_count()
+        wall0 = time.perf_counter()
+        ms = self.timed(step_dev, steps)
+        self.barrier()
+        wall = time.perf_counter() - wall0
+        launches = self.h.launch_count() - l0
+        clocks = sampler.stop() if sampler else None
+        total_ms = self.max_over_ranks(sum(ms))
+        self.timed(step_e2e, 3)
+        self.barrier()
+        ms_e2e = self.timed(step_e2e, steps)
+        self.barrier()
+        total_e2e = self.max_over_ranks(sum(ms_e2e))
+        return {"value": steps * units_total / (total_ms * 1e-3), "ms_per_step": total_ms / steps,
+                "e2e_value": steps * units_total / (total_e2e * 1e-3), "e2e_ms_per_step": total_e2e / steps,
+                "launches": int(launches), "clocks": clocks, "wall": wall, "p50_ms": float(np.median(ms)), "p99_ms": float(np.percentile(ms, 99)),
+                "steps": steps, "warmup": warmup}
+
+    def record(self, m, queries_per_unit, h2d, d2h, cfg):
+        r = {"metric": "registrations/s", "value": m["value"], "unit": "registrations/s", "steps": m["steps"], "warmup": m["warmup"],
+             "ms_per_step": m["ms_per_step"], "nn_queries_per_s": m["value"] * queries_per_unit, "config": cfg,
+             "e2e": {"value": m["e2e_value"], "unit": "registrations/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                     "ms_per_step": m["e2e_ms_per_step"], "nn_queries_per_s": m["e2e_value"] * queries_per_unit},
+             "gpu_launches": m["launches"], "p50_ms": m["p50_ms"], "p99_ms": m["p99_ms"]}
+        return r
+
+    def iter_kernel_ms(self, call):
+        """device time of one iteration launch, from the per-launch CUDA events of the handle's profiling mode"""
+        self.h.set_profiling(True)
+        ts = []
+        for i in range(5):
+            self.flush.fill_(i)
+            call(i)
+            p = self.h.last_profile()
+            if i >= 2 and len(p) > 1:
+                ts.append(float(np.mean(p[:-1])))   # the last entry is the fitness pass
+        self.h.set_profiling(False)
+        return float(np.mean(ts)) if ts else None
+
+    def stats_of(self, call):
+        """(queries searched, squared-distance evaluations, queries settled without a search) of one call"""
+        if not hasattr(self.h, "set_stats"):
+            return None
+        self.h.set_stats(True)
+        call(0)
+        s = self.h.get_stats()
+        self.h.set_stats(False)
+        return s
+
+    def m_r(self, map_pts_dev, m, scan):
+        """map points within the gate of >= 1 point of `scan` (the M_r of SURVEY.md §8(d)), counted on the device:
+        1-NN of every map point in the scan with the gate as max_dist"""
+        h2 = self.pkg.Icp4r(self.local)
+        h2.map_build(scan)
+        total = 0
+        step = 4 << 20
+        for a in range(0, m, step):
+            _i, _d, found = h2.map_knn(map_pts_dev[a:min(a + step, m)], 1, GATE)
+            total += int((found > 0).sum().item())
+        h2.close()
+        return total
+
+    # ---- C4 -------------------------------------------------------------------------------------------------------
+    def run_c4(self, steps, warmup, main):
+        torch, pkg, h = self.torch, self.pkg, self.h
+        pairs = self.args.pairs
+        lo, hi = pkg.shard.pair_range(pairs, self.rank, self.world)
+        mine = hi - lo
+        src, tgt, off = make_c4(mine, first=lo)
+        o = pkg.default_opts(residual=pkg.P2P_SVD, max_iterations=C4_ITERS)
+        d_src, d_tgt, d_off = torch.from_numpy(src).to(self.dev), torch.from_numpy(tgt).to(self.dev), torch.from_numpy(off).to(self.dev)
+        outT = torch.zeros((mine, 16), dtype=torch.float64, device=self.dev)
+        outR = torch.zeros((mine, 32), dtype=torch.uint8, device=self.dev)
+        p_src, p_tgt = torch.from_numpy(src).pin_memory(), torch.from_numpy(tgt).pin_memory()
+        step_dev = lambda i: h.register_batch(d_src, d_off, d_tgt, d_off, o, out=(outT, outR))
+        step_e2e = lambda i: h.register_batch(p_src.numpy(), off, p_tgt.numpy(), off, o)
+        m = self.measure(step_dev, step_e2e, steps, warmup, pairs, sample_clocks=main)
+        rec = self.record(m, C4_ITERS * C4_N, 2 * mine * C4_N * 16 + 2 * (mine + 1) * 4, mine * (128 + 32), c4_config(pairs, self.world))
+        rec["scaling"] = "strong"
+        rec["_m"] = m
+        if self.rank == 0:
+            st = self.stats_of(lambda i: h.register_batch(d_src[:1024 * C4_N], d_off[:1025], d_tgt[:1024 * C4_N], d_off[:1025], o))
+            evals = st[1] / 1024 * mine if st else None
+            alg = mine * (16 * 2 * C4_N + 64 + 160)
+            extra = None
+            if st:
+                extra = {"searches_per_registration": st[0] / 1024, "settled_without_search_per_registration": st[2] / 1024,
+                         "candidates_per_search": st[1] / max(st[0], 1)}
+            rec["roofline"] = roofline("reg_batch_kernel<P2P_SVD,256>", "reg_batch_kernel", alg, m["ms_per_step"],
+                                       "resident design: each pair is read from HBM once (65.8 KB) and iterated 31 times in shared memory; "
+                                       "the kernel is bound by instruction issue and the per-iteration barrier/solve chain, see DESIGN.md",
+                                       dist_evals=evals, extra=extra)
+            if self.world == 1 and not self.args.no_cpu_baseline:
+                k1, d1, s1 = cpu_pairs(src, tgt, C4_N, C4_ITERS, 10.0, 1)
+                kN, dN, sN = cpu_pairs(src, tgt, C4_N, C4_ITERS, 12.0, self.threads, max_pairs=max(self.threads * 4, 64))
+                rec["cpu_baseline"] = {"value": dN / sN, "unit": "registrations/s", "cores": self.threads, "kind": kN,
+                                       "sample": f"{dN} pairs of the job, one pair per host thread at a time (ikd-Tree Build + 30 x 1-NN + Kabsch each); "
+                                                 "PCL/FLANN absent from the image",
+                                       "single_thread": {"value": d1 / s1, "cores": 1, "sample": f"{d1} pairs on one thread"}}
+        del d_src, d_tgt, p_src, p_tgt
+        return rec
+
+    # ---- C1 -------------------------------------------------------------------------------------------------------
+    def run_c1(self, steps, warmup, main=False):
+        torch, pkg, h = self.torch, self.pkg, self.h
+        pool = [pkg.synth.frame_pair(1001 + i, C1_N) for i in range(8)]
+        o = pkg.default_opts(residual=pkg.P2P_SVD, max_iterations=C1_ITERS)
+        d = [(torch.from_numpy(a).to(self.dev), torch.from_numpy(b).to(self.dev)) for a, b, _ in pool]
+        pin = [(torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()) for a, b, _ in pool]
+        step_dev = lambda i: h.register(d[i % 8][0], d[i % 8][1], o)
+        step_e2e = lambda i: h.register(pin[i % 8][0].numpy(), pin[i % 8][1].numpy(), o)
+        m = self.measure(step_dev, step_e2e, steps, warmup, 1, sample_clocks=main)
+        rec = self.record(m, C1_ITERS * C1_N, 2 * C1_N * 16, 16 * 8 + 32,
+                          {"workload": "C1 single frame pair: 1024 + 1024 pts, P2P_SVD (Kabsch), 30 iterations, ungated (PCL defaults otherwise); "
+                                       "one icp4r_register call = target grid build + 30 iteration kernels + fitness pass",
+                           "n": C1_N, "m": C1_N, "iterations": C1_ITERS, "l2": "flushed before every timed step"})
+        rec["_m"] = m
+        k_ms = self.iter_kernel_ms(step_dev)
+        st = self.stats_of(step_dev)
+        rec["us_per_iteration"] = 1e3 * k_ms if k_ms else None
+        rec["roofline"] = roofline("reg_iter_kernel<P2P_SVD,1>", "reg_iter_kernel_c1", 16 * (C1_N + C1_N) + 232, k_ms,
+                                   "32 KB working set: one iteration is a latency chain (search, block reduce, last-block solve), not a stream",
+                                   dist_evals=(st[1] / (C1_ITERS + 1)) if st else None)
+        if not self.args.no_cpu_baseline:
+            src = np.concatenate([a for a, _, _ in pool])
+            tgt = np.concatenate([b for _, b, _ in pool])
+            kind, done, secs = cpu_pairs(np.tile(src, (8, 1)), np.tile(tgt, (8, 1)), C1_N, C1_ITERS, 5.0, 1)
+            rec["cpu_baseline"] = {"value": done / secs, "unit": "registrations/s", "cores": 1, "kind": kind,
+                                   "sample": f"{done} pairs on one thread (the reference node is single-threaded): ikd-Tree Build + 30 x 1-NN + Kabsch"}
+        return rec
+
+    # ---- C2 -------------------------------------------------------------------------------------------------------
+    def run_c2(self, steps, warmup, batch, main=False, with_cpu=True):
+        torch, pkg, h = self.torch, self.pkg, self.h
+        from scipy.spatial import cKDTree
+        mp, scans = make_c2(1002)
+        h.map_build(mp)
+        o = pkg.default_opts(residual=pkg.P2PLANE_KNN, k=K_NN, max_iterations=ITERS, max_corr_dist=GATE)
+        off = (np.arange(POOL + 1) * N_SCAN).astype(np.int32)
+        cat = np.ascontiguousarray(np.concatenate(scans))
+        d_cat = torch.from_numpy(cat).to(self.dev)
+        pin_cat = torch.from_numpy(cat).pin_memory()
+        d_scans = [torch.from_numpy(s).to(self.dev) for s in scans]
+        pin = [torch.from_numpy(s).pin_memory() for s in scans]
+        if batch:
+            step_dev = lambda i: h.register_map_batch(d_cat, off, o)
+            step_e2e = lambda i: h.register_map_batch(pin_cat.numpy(), off, o)
+            units, h2d, d2h = POOL, POOL * N_SCAN * 16, POOL * (16 * 8 + 32)
+        else:
+            step_dev = lambda i: h.register_map(d_scans[i % POOL], o)
+            step_e2e = lambda i: h.register_map(pin[i % POOL].numpy(), o)
+            units, h2d, d2h = 1, N_SCAN * 16, 16 * 8 + 32
+        m = self.measure(step_dev, step_e2e, steps, warmup, units * self.world, sample_clocks=main)
+        rec = self.record(m, ITERS * N_SCAN, h2d, d2h, c2_config(self.world, batch))
+        rec["scaling"] = "weak"
+        rec["_m"] = m
+        if self.rank == 0:
+            if batch:
+                d, _ = cKDTree(cat[:, :3]).query(mp[:, :3], distance_upper_bound=GATE)
+                o10 = pkg.default_opts(residual=pkg.P2PLANE_KNN, k=K_NN, max_iterations=ITERS // 2, max_corr_dist=GATE)
+                t20 = np.mean(self.timed(step_dev, 10))
+                t10 = np.mean(self.timed(lambda i: h.register_map_batch(d_cat, off, o10), 10))
+                k_ms = float(t20 - t10) / (ITERS - ITERS // 2)
+                nsc, key = POOL, "reg_iter_kernel_c2_batch16"
+            else:
+                d, _ = cKDTree(scans[0][:, :3]).query(mp[:, :3], distance_upper_bound=GATE)
+                k_ms = self.iter_kernel_ms(step_dev)
+                nsc, key = 1, "reg_iter_kernel_c2_single"
+            m_r = int(np.isfinite(d).sum())
+            st = self.stats_of(step_dev)
+            rec["us_per_iteration"] = 1e3 * k_ms
+            rec["roofline"] = roofline(f"reg_iter_kernel<P2PLANE_KNN,5> (gridDim.y = {nsc} scan(s))", key, 16 * (nsc * N_SCAN + m_r) + 232 * nsc, k_ms,
+                                       "working set (3.3 MB map + scans) is L2-resident: issue/latency-bound, see DESIGN.md",
+                                       dist_evals=(st[1] / (ITERS + 1)) if st else None, extra={"m_r": m_r})
+            if with_cpu and self.world == 1 and not self.args.no_cpu_baseline:
+                kind, threads, times = cpu_c2(mp, scans, 12.0, 200, self.threads)
+                rec["cpu_baseline"] = {"value": len(times) / float(np.sum(times)), "unit": "registrations/s", "cores": threads, "kind": kind,
+                                       "sample": f"{len(times)} registrations of the same workload, one after the other, Nearest_Search on all host threads; "
+                                                 "ikd-Tree Build excluded (resident map)"}
+        return rec
+
+    # ---- GICP -----------------------------------------------------------------------------------------------------
+    def run_gicp(self, steps, warmup, main=False):
+        torch, pkg, h = self.torch, self.pkg, self.h
+        mp, scans = make_c2(1002)
+        h.map_build(mp)
+        o = pkg.default_opts(residual=pkg.GICP, k=K_NN, max_iterations=64, early_exit=1, max_corr_dist=0.0)
+        d_scans = [torch.from_numpy(s).to(self.dev) for s in scans]
+        pin = [torch.from_numpy(s).pin_memory() for s in scans]
+        its = []
+
+        def step_dev(i):
+            T, r, _ = h.register_map(d_scans[i % POOL], o)
+            its.append(r.iterations)
+        step_e2e = lambda i: h.register_map(pin[i % POOL].numpy(), o)
+        m = self.measure(step_dev, step_e2e, steps, warmup, 1, sample_clocks=main)
+        n_it = float(np.mean(its[-steps:])) if its else 8.0
+        rec = self.record(m, n_it * N_SCAN, N_SCAN * 16, 16 * 8 + 32,
+                          {"workload": "GICP scan-to-map (what radar_odometry.cpp:399-411 runs): 4096-pt scan vs resident 200000-pt map, fast_gicp cost "
+                                       "(k=5 covariances, LM), early exit, ungated", "n": N_SCAN, "m": N_MAP, "k": K_NN, "max_iterations": 64,
+                           "mean_iterations": n_it, "l2": "flushed before every timed step"})
+        rec["_m"] = m
+        # the registration as a whole against its compulsory traffic: scan + its normals once, then per linearisation the
+        # scan (16 B) + per correspondence the target point and its normal (16 + 24 B) + the correspondence record (56 B)
+        alg = N_SCAN * (16 + 24) + n_it * N_SCAN * (16 + 16 + 24 + 56)
+        rec["roofline"] = roofline("reg_iter_kernel<GICP,1> + gicp_lm_step, whole registration", "gicp_registration", alg, m["ms_per_step"],
+                                   "latency-bound: ~8 linearisations x (grid-wide kernel + single-block LM step) on an L2-resident working set")
+        if not self.args.no_cpu_baseline:
+            import oracle as O
+            kind, threads, times = cpu_c2(mp, scans, 10.0, 50, self.threads, residual=O.GICP, iters=64, gate=0.0, early_exit=1)
+            rec["cpu_baseline"] = {"value": len(times) / float(np.sum(times)), "unit": "registrations/s", "cores": threads, "kind": kind,
+                                   "sample": f"{len(times)} registrations, restated fast_gicp loop with the reference's ikd-Tree for the neighbour searches "
+                                             "(target covariances recomputed per call like fast_gicp's setInputTarget); fast_gicp itself is absent from the image"}
+        return rec
+
+    # ---- C3 -------------------------------------------------------------------------------------------------------
+    def run_c3(self, steps, warmup, main=False):
+        torch, pkg, h = self.torch, self.pkg, self.h
+        frames = self.args.frames
+        seq, _gt = pkg.pipeline.synth_sequence(1003 + self.rank, frames)
+        o = pkg.default_opts(residual=pkg.P2PLANE_KNN, k=K_NN, max_iterations=ITERS, max_corr_dist=GATE)
+        d_seq = [torch.from_numpy(s).to(self.dev) for s in seq]
+        pin_seq = [torch.from_numpy(s).pin_memory() for s in seq]
+        h_seq = [p.numpy() for p in pin_seq]
+        step_dev = lambda i: pkg.pipeline.run_odometry(h, d_seq, o)
+        step_e2e = lambda i: pkg.pipeline.run_odometry(h, h_seq, o)
+        m = self.measure(step_dev, step_e2e, steps, warmup, frames, sample_clocks=main)
+        npts = int(sum(len(s) for s in seq))
+        rec = self.record(m, ITERS * int(np.mean([len(s) for s in seq])), npts * 16, frames * (16 * 8 + 32),
+                          {"workload": f"C3 odometry sequence: {frames} frames (~3000 static pts each), per frame register vs the growing map (P2PLANE k=5, "
+                                       "20 iters, gate 2.0 m) + transform + Add_Points(false), one icp4r_odometry_step call per frame; one step = the whole sequence",
+                           "frames": frames, "k": K_NN, "iterations": ITERS, "max_corr_dist": GATE, "final_map_points": npts,
+                           "l2": "flushed before every timed step; the map outgrows L2 during the sequence"})
+        rec["_m"] = m
+        rec["unit_note"] = "registrations/s = frames/s (one registration per frame)"
+        # dominant kernel: the iteration kernel against the FINAL map (state left behind by the last timed sequence)
+        last = d_seq[-1]
+        k_ms = self.iter_kernel_ms(lambda i: h.register_map(last, o))
+        mpts = h.map_points_dev() if hasattr(h, "map_points_dev") else None
+        m_r = self.m_r(mpts, npts, seq[-1]) if mpts is not None else None
+        st = self.stats_of(lambda i: h.register_map(last, o))
+        n_last = len(seq[-1])
+        rec["roofline"] = roofline("reg_iter_kernel<P2PLANE_KNN,5> at the final map", "reg_iter_kernel_c3", 16 * (n_last + (m_r or 0)) + 232, k_ms,
+                                   "per frame: 20 iteration kernels (latency chain on an L2-resident neighbourhood of the map) + incremental Add_Points",
+                                   dist_evals=(st[1] / (ITERS + 1)) if st else None, extra={"m_r": m_r})
+        if not self.args.no_cpu_baseline:
+            kind, cnt, secs, upto = cpu_c3(seq, 20.0, self.threads)
+            rec["cpu_baseline"] = {"value": cnt / secs, "unit": "registrations/s", "cores": self.threads if kind == "reference" else 1, "kind": kind,
+                                   "sample": f"{cnt} frames timed out of the first {upto}, spread over the sequence with the tree grown to each frame's size "
+                                             "(frames in between inserted untimed)"}
+        return rec
+
+    # ---- C5 -------------------------------------------------------------------------------------------------------
+    def run_c5(self, steps, warmup, main=False):
+        torch, pkg, h, dist = self.torch, self.pkg, self.h, self.dist
+        world, rank = self.world, self.rank
+        mpts = self.args.map_points
+        mp, scans = make_c5(mpts)
+        o = pkg.default_opts(residual=pkg.P2PLANE_KNN, k=K_NN, max_iterations=C5_ITERS, max_corr_dist=GATE)
+        d_scans = [torch.from_numpy(s).to(self.dev) for s in scans]
+        pin = [torch.from_numpy(s).pin_memory() for s in scans]
+        if world > 1:
+            bounds = pkg.shard.slab_bounds(mp[:, 0], world)
+            mine, lo, hi, _ = pkg.shard.slab_of_rank(mp, rank, world, axis=0, halo=GATE, bounds=bounds)
+            uid = [pkg.Icp4r.shard_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            h.shard_init(uid[0], rank, world)
+            if self.args.exchange == "peer":
+                hs = [None] * world
+                dist.all_gather_object(hs, h.shard_ipc_export())
+                h.shard_ipc_import(hs, rank, world)
+            d_map = torch.from_numpy(mine).to(self.dev)
+            h.map_build(d_map)
+            step_dev = lambda i: h.register_sharded(d_scans[i % 4], o, 0, lo, hi)
+            step_e2e = lambda i: h.register_sharded(pin[i % 4].numpy(), o, 0, lo, hi)
+            m_local = len(mine)
+        else:
+            d_map = torch.from_numpy(mp).to(self.dev)
+            h.map_build(d_map)
+            step_dev = lambda i: h.register_map(d_scans[i % 4], o)
+            step_e2e = lambda i: h.register_map(pin[i % 4].numpy(), o)
+            m_local = mpts
+        m = self.measure(step_dev, step_e2e, steps, warmup, 1, sample_clocks=main)
+        coll = ("none" if world == 1 else "29 fp64 sums exchanged inside the iteration kernel over NVLink peer memory" if self.args.exchange == "peer"
+                else "29-double NCCL all-reduce per iteration")
+        rec = self.record(m, C5_ITERS * C5_N, C5_N * 16, 16 * 8 + 32,
+                          {"workload": f"C5 large-map registration: 16384-pt scan vs {mpts}-pt dense map in {world} x-slab(s), P2PLANE k=5, 20 iters, gate 2.0 m",
+                           "n": C5_N, "m": mpts, "k": K_NN, "iterations": C5_ITERS, "max_corr_dist": GATE, "slabs": world, "collective": coll,
+                           "l2": "flushed before every timed step (256 MiB fill, untimed)"})
+        rec["scaling"] = "strong"
+        rec["_m"] = m
+        if rank == 0:
+            if world == 1:
+                k_ms = self.iter_kernel_ms(step_dev)
+                st = self.stats_of(step_dev)
+            else:
+                k_ms, st = m["ms_per_step"] / (C5_ITERS + 1), None
+            m_r = self.m_r(d_map, m_local, scans[0])
+            rec["us_per_iteration"] = 1e3 * k_ms
+            rec["roofline"] = roofline("reg_iter_kernel<P2PLANE_KNN,5>" + ("" if world == 1 else " (rank 0's slab, cross-rank sum fused in)"),
+                                       "reg_iter_kernel_c5", 16 * (C5_N + m_r) + 232, k_ms,
+                                       "gather-bound: 16,384 queries touch ~1 % of the 320 MB map per iteration; a launch is a latency chain, not a stream",
+                                       dist_evals=(st[1] / (C5_ITERS + 1)) if st else None, extra={"m_r": m_r})
+            if world == 1:
+                t0 = time.perf_counter()
+                h.map_build(d_map)
+                h.synchronize()
+                rec["map_build_ms"] = 1e3 * (time.perf_counter() - t0)
+            if world == 1 and not self.args.no_cpu_baseline:
+                # bounded sample: the same registrations against the 2 M map points of the central 126 x 126 x 20 m block
+                # (same density, 1/10 of the points: a 20 M-point ikd-Tree Build alone takes minutes) with the scan points
+                # that fall inside it
+                c = np.abs(mp[:, 0]) < 63.25
+                c &= np.abs(mp[:, 1]) < 63.25
+                sub = np.ascontiguousarray(mp[c])
+                sscans = []
+                for s in scans:
+                    k = (np.abs(s[:, 0]) < 60.0) & (np.abs(s[:, 1]) < 60.0)
+                    sscans.append(np.ascontiguousarray(s[k]))
+                kind, threads, times = cpu_c2(sub, sscans, 10.0, 50, self.threads, iters=C5_ITERS)
+                nq = float(np.mean([len(s) for s in sscans]))
+                per_reg = float(np.mean(times)) * (C5_N / nq)   # scaled to the full 16,384-pt scan (cost is per query)
+                rec["cpu_baseline"] = {"value": 1.0 / per_reg, "unit": "registrations/s", "cores": threads, "kind": kind,
+                                       "sample": f"{len(times)} registrations of the ~{int(nq)} scan points inside the central block against its {len(sub)} map points "
+                                                 f"(same density), scaled by 16384/{int(nq)} queries; Build excluded; a 20 M-point ikd-Tree is ~10 % deeper"}
+        return rec
+
+
+def strip(rec):
+    rec.pop("_m", None)
+    return rec
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5", "gicp"])
+    ap.add_argument("--workload", default="all", choices=["all", "c1", "c2", "c2single", "c3", "c4", "c5", "gicp"])
     ap.add_argument("--frames", type=int, default=2000, help="c3: frames of the odometry sequence (one step = the whole sequence)")
     ap.add_argument("--map-points", type=int, default=20_000_000, help="c5: points of the dense map (whole job)")
-    ap.add_argument("--pairs", type=int, default=65536, help="c4: frame pairs per GPU per step")
+    ap.add_argument("--pairs", type=int, default=C4_PAIRS, help="c4: frame pairs of the WHOLE job (split across the GPUs)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="c5, N > 1: cross-rank sum inside the iteration kernel over NVLink peer memory, or one NCCL all-reduce per iteration")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="workload all: skip the per-config sub-records")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -247,280 +795,50 @@ def main():
         run_reference(args, rank, world)
         return
     args.warmup = max(args.warmup, 3)
-
-    import torch
-    import torch.distributed as dist
-    from icp4r_loader import pkg
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: libicp4r_cuda has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    h = pkg.Icp4r(local)
-    stream = torch.cuda.Stream(device=dev)
-    h.set_stream(stream.cuda_stream)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    peak, peak_src = peaks()
-
-    def barrier():
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    def timed(fn, steps):
-        """sum of per-step device times (CUDA events on the launching stream); L2 flushed, untimed, before each"""
-        evs = []
-        with torch.cuda.stream(stream):
-            for i in range(steps):
-                flush.fill_(i & 0xff)
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(stream)
-                fn(i)
-                e1.record(stream)
-                evs.append((e0, e1))
-        torch.cuda.synchronize(dev)
-        return [a.elapsed_time(b) for a, b in evs]
-
-    if args.workload == "c2":
-        mp, scans = make_c2(1002 + rank * 0)
-        h.map_build(mp)
-        o = pkg.default_opts(residual=pkg.P2PLANE_KNN, k=K_NN, max_iterations=ITERS, max_corr_dist=GATE)
-        off = (np.arange(POOL + 1) * N_SCAN).astype(np.int32)
-        cat = np.ascontiguousarray(np.concatenate(scans))
-        d_cat = torch.from_numpy(cat).to(dev)
-        pin_cat = torch.from_numpy(cat).pin_memory()
-        h_cat = pin_cat.numpy()
-        d_scans = [torch.from_numpy(s).to(dev) for s in scans]
-        units_per_step = POOL
-        queries_per_unit = ITERS * N_SCAN
-        step_dev = lambda i: h.register_map_batch(d_cat, off, o)
-        step_e2e = lambda i: h.register_map_batch(h_cat, off, o)
-        h2d, d2h = POOL * N_SCAN * 16, POOL * (16 * 8 + 32)
-        cfg = {"workload": "C2 scan-to-map: 4096-pt scans vs resident 200000-pt map, P2PLANE k=5, 20 iters, gate 2.0 m",
-               "n": N_SCAN, "m": N_MAP, "k": K_NN, "iterations": ITERS, "max_corr_dist": GATE,
-               "batch_scans": POOL, "step": f"{POOL} independent scans registered in one icp4r_register_map_batch call "
-               "(one scan alone is latency-bound and leaves most SMs idle; single-scan latency is in latency_ms_single)",
-               "l2": "flushed before every timed step (256 MiB fill, untimed)", "replicas": world}
-    elif args.workload == "gicp":
-        # what radar_odometry.cpp:399-411 runs per frame: fast_gicp's cost (k = 5 covariances, LM, early exit, <= 64 iterations)
-        # for one 4,096-pt scan against the resident 200 k-pt map (target normals cached in the handle)
-        mp, scans = make_c2(1002)
-        h.map_build(mp)
-        o = pkg.default_opts(residual=pkg.GICP, k=K_NN, max_iterations=64, early_exit=1, max_corr_dist=0.0)
-        d_scans = [torch.from_numpy(s).to(dev) for s in scans]
-        pinned = [torch.from_numpy(s).pin_memory() for s in scans]
-        h_scans = [p.numpy() for p in pinned]
-        units_per_step = 1
-        queries_per_unit = 8 * N_SCAN   # ~8 outer iterations until the reference's convergence test fires
-        step_dev = lambda i: h.register_map(d_scans[i % POOL], o)
-        step_e2e = lambda i: h.register_map(h_scans[i % POOL], o)
-        h2d, d2h = N_SCAN * 16, 16 * 8 + 32
-        cfg = {"workload": "GICP scan-to-map: 4096-pt scan vs resident 200000-pt map, fast_gicp cost (k=5 covariances, LM), early exit, ungated",
-               "n": N_SCAN, "m": N_MAP, "k": K_NN, "max_iterations": 64, "l2": "flushed before every timed step (256 MiB fill, untimed)"}
-    elif args.workload == "c3":
-        # one step = the whole odometry sequence: Build on frame 0, then per frame register against the growing map,
-        # transform with the estimated pose, Add_Points(false). value = frames/s (each frame is one registration).
-        seq, _gt = pkg.pipeline.synth_sequence(1003 + rank, args.frames)
-        o = pkg.default_opts(residual=pkg.P2PLANE_KNN, k=K_NN, max_iterations=ITERS, max_corr_dist=GATE)
-        d_seq = [torch.from_numpy(s).to(dev) for s in seq]
-        pin_seq = [torch.from_numpy(s).pin_memory() for s in seq]
-        h_seq = [p.numpy() for p in pin_seq]
-        units_per_step = args.frames
-        queries_per_unit = ITERS * int(np.mean([len(s) for s in seq]))
-        step_dev = lambda i: pkg.pipeline.run_odometry(h, d_seq, o)
-        step_e2e = lambda i: pkg.pipeline.run_odometry(h, h_seq, o)
-        h2d, d2h = int(sum(len(s) for s in seq)) * 16, args.frames * (16 * 8 + 32)  # one icp4r_odometry_step per frame: the scan crosses once
-        cfg = {"workload": f"C3 odometry sequence: {args.frames} frames (~3000 static pts each), register vs growing map (P2PLANE k=5, 20 iters, gate 2.0 m) + transform + Add_Points(false) per frame (one icp4r_odometry_step call)",
-               "frames": args.frames, "k": K_NN, "iterations": ITERS, "max_corr_dist": GATE,
-               "final_map_points": int(sum(len(s) for s in seq)), "l2": "flushed before every timed step; the map outgrows L2 during the sequence"}
-    elif args.workload == "c5":
-        # one map split in spatial slabs along x (halo = gate) across the ranks; every rank gets the same scan; the 29
-        # accumulators are summed across ranks every iteration (in-kernel over peer memory, or NCCL). N = 1: the whole map on one GPU.
-        mp, scans = make_c5(args.map_points)
-        o = pkg.default_opts(residual=pkg.P2PLANE_KNN, k=K_NN, max_iterations=C5_ITERS, max_corr_dist=GATE)
-        if world > 1:
-            bounds = pkg.shard.slab_bounds(mp[:, 0], world)
-            mine, lo, hi, _ = pkg.shard.slab_of_rank(mp, rank, world, axis=0, halo=GATE, bounds=bounds)
-            uid = [pkg.Icp4r.shard_unique_id() if rank == 0 else None]
-            dist.broadcast_object_list(uid, src=0)
-            h.shard_init(uid[0], rank, world)
-            if args.exchange == "peer":
-                hs = [None] * world
-                dist.all_gather_object(hs, h.shard_ipc_export())
-                h.shard_ipc_import(hs, rank, world)
-            h.map_build(torch.from_numpy(mine).to(dev))
-            step_dev = lambda i: h.register_sharded(d_scans[i % 4], o, 0, lo, hi)
-            step_e2e = lambda i: h.register_sharded(h_scans[i % 4], o, 0, lo, hi)
-        else:
-            h.map_build(torch.from_numpy(mp).to(dev))
-            step_dev = lambda i: h.register_map(d_scans[i % 4], o)
-            step_e2e = lambda i: h.register_map(h_scans[i % 4], o)
-        d_scans = [torch.from_numpy(s).to(dev) for s in scans]
-        pinned = [torch.from_numpy(s).pin_memory() for s in scans]
-        h_scans = [p.numpy() for p in pinned]
-        units_per_step = 1.0 / world   # ONE registration per step for the whole job (strong scaling)
-        queries_per_unit = C5_ITERS * C5_N
-        h2d, d2h = C5_N * 16, 16 * 8 + 32
-        cfg = {"workload": f"C5 large-map registration: 16384-pt scan vs {args.map_points}-pt dense map in {world} x-slab(s), P2PLANE k=5, 20 iters, gate 2.0 m",
-               "n": C5_N, "m": args.map_points, "k": K_NN, "iterations": C5_ITERS, "max_corr_dist": GATE, "slabs": world,
-               "collective": ("none" if world == 1 else "29 fp64 sums exchanged inside the iteration kernel over NVLink peer memory" if args.exchange == "peer"
-                              else "29-double NCCL all-reduce per iteration"),
-               "l2": "flushed before every timed step (256 MiB fill, untimed)"}
+    B = Bench(args, rank, world, local)
+    wl = args.workload
+    K, W = args.steps, args.warmup
+    configs = None
+    if wl in ("all", "c4"):
+        rec = B.run_c4(K, W, True)
+        if wl == "all" and not args.no_configs:
+            configs = {}
+            if world == 1:
+                configs["c1"] = strip(B.run_c1(max(20 * K, 100), 10))
+                configs["c2_single"] = strip(B.run_c2(max(10 * K, 50), 10, batch=False, with_cpu=False))
+                configs["c2_batch16"] = strip(B.run_c2(max(10 * K, 50), 10, batch=True))
+                configs["gicp"] = strip(B.run_gicp(max(10 * K, 50), 5))
+                configs["c3"] = strip(B.run_c3(2, 3))
+                configs["c5"] = strip(B.run_c5(max(5 * K, 30), 5))
+            else:
+                configs["c5_sharded"] = strip(B.run_c5(max(5 * K, 30), 5))
+    elif wl == "c1":
+        rec = B.run_c1(K, W, main=True)
+    elif wl in ("c2", "c2single"):
+        rec = B.run_c2(K, W, batch=(wl == "c2"), main=True)
+    elif wl == "gicp":
+        rec = B.run_gicp(K, W, main=True)
+    elif wl == "c3":
+        rec = B.run_c3(K, W, main=True)
     else:
-        src, tgt, off = make_c4(args.pairs)
-        o = pkg.default_opts(residual=pkg.P2P_SVD, max_iterations=C4_ITERS)
-        d_src, d_tgt, d_off = torch.from_numpy(src).to(dev), torch.from_numpy(tgt).to(dev), torch.from_numpy(off).to(dev)
-        outT = torch.zeros((args.pairs, 16), dtype=torch.float64, device=dev)
-        outR = torch.zeros((args.pairs, 32), dtype=torch.uint8, device=dev)
-        p_src, p_tgt = torch.from_numpy(src).pin_memory(), torch.from_numpy(tgt).pin_memory()
-        units_per_step = args.pairs
-        queries_per_unit = C4_ITERS * C4_N
-        step_dev = lambda i: h.register_batch(d_src, d_off, d_tgt, d_off, o, out=(outT, outR))
-        step_e2e = lambda i: h.register_batch(p_src.numpy(), off, p_tgt.numpy(), off, o)
-        h2d, d2h = 2 * args.pairs * C4_N * 16 + 2 * (args.pairs + 1) * 4, args.pairs * (128 + 32)
-        cfg = {"workload": f"C4 batched registration: {args.pairs} frame pairs per GPU, 2048 pts each, P2P_SVD, 30 iters, ungated",
-               "pairs_per_gpu": args.pairs, "n": C4_N, "m": C4_N, "iterations": C4_ITERS,
-               "l2": "inputs (%.0f MB per step) exceed L2; flushed anyway" % (2 * args.pairs * C4_N * 16 / 1e6)}
-
-    # ---- warm-up, then the timed device-resident steps ----------------------------------------------------
-    timed(step_dev, args.warmup)
-    barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
-    l0 = h.launch_count()
-    wall0 = time.perf_counter()
-    ms = timed(step_dev, args.steps)
-    barrier()
-    wall = time.perf_counter() - wall0
-    launches = h.launch_count() - l0
-    clocks = sampler.stop() if sampler else None
-    t_dev = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
-    # ---- end-to-end through the C ABI with host buffers ------------------------------------------------------
-    timed(step_e2e, 3)
-    barrier()
-    ms_e2e = timed(step_e2e, args.steps)
-    barrier()
-    t_e2e = torch.tensor([sum(ms_e2e)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    total_ms, total_e2e_ms = float(t_dev.item()), float(t_e2e.item())
-    value = world * args.steps * units_per_step / (total_ms * 1e-3)
-    e2e_value = world * args.steps * units_per_step / (total_e2e_ms * 1e-3)
-
+        rec = B.run_c5(K, W, main=True)
     if rank == 0:
-        line = {
-            "metric": "registrations/s", "value": value, "unit": "registrations/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "strong" if args.workload == "c5" else "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
-            "nn_queries_per_s": value * queries_per_unit,
-            "e2e": {"value": e2e_value, "unit": "registrations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": total_e2e_ms / args.steps, "nn_queries_per_s": e2e_value * queries_per_unit},
-            "gpu_launches": int(launches), "wall_s_incl_flush": wall, "clocks": clocks,
-            "p50_ms": float(np.median(ms)), "p99_ms": float(np.percentile(ms, 99)),
-        }
-        # ---- roofline of the dominant kernel -------------------------------------------------------------------
-        if args.workload == "c2":
-            from scipy.spatial import cKDTree
-            # single-scan latency through icp4r_register_map (what a sequential odometry loop sees)
-            ms1 = timed(lambda i: h.register_map(d_scans[i % POOL], o), max(args.steps // 2, 10))
-            line["latency_ms_single"] = float(np.median(ms1))
-            line["single_scan_registrations_per_s"] = 1e3 / float(np.mean(ms1))
-            # algorithmic bytes of one fused iteration launch over the whole batch (SURVEY.md §8(d), kNN row without the
-            # index output the fused kernel never writes): 16*(B*N + M_r) + 232*B, M_r = map points within the gate of
-            # >= 1 query of any scan of the batch
-            d, _ = cKDTree(cat[:, :3]).query(mp[:, :3], distance_upper_bound=GATE)
-            m_r = int(np.isfinite(d).sum())
-            alg = 16 * (POOL * N_SCAN + m_r) + 232 * POOL
-            # device time of one iteration launch = (t(20 iterations) - t(10 iterations)) / 10, CUDA events, L2 flushed
-            o10 = pkg.default_opts(residual=pkg.P2PLANE_KNN, k=K_NN, max_iterations=ITERS // 2, max_corr_dist=GATE)
-            t20 = np.mean(timed(step_dev, 10))
-            t10 = np.mean(timed(lambda i: h.register_map_batch(d_cat, off, o10), 10))
-            k_ms = float(t20 - t10) / (ITERS - ITERS // 2)
-            ach = alg / (k_ms * 1e-3) / 1e9
-            # traffic: dram__bytes_read.sum + dram__bytes_write.sum of one launch from the ncu --set full capture summarised
-            # in profiles/ (ncu flushes caches between replays: the COLD figure; warm launches are served from L2)
-            line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": NCU_TRAFFIC_BYTES,
-                                "kernel": "reg_iter_kernel<P2PLANE_KNN,5> (gridDim.y = 16 scans)", "kernel_ms": k_ms, "algorithmic_bytes": alg, "m_r": m_r,
-                                "peak_source": peak_src,
-                                "note": "working set (3.3 MB map + 1 MB scans) is L2-resident: issue/latency-bound, see DESIGN.md"}
-        elif args.workload in ("c5", "c3", "gicp"):
-            line["roofline"] = None
-        else:
-            alg = args.pairs * (16 * 2 * C4_N + 64 + 160)
-            k_ms = total_ms / args.steps
-            ach = alg / (k_ms * 1e-3) / 1e9
-            line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                                "kernel": "reg_batch_kernel<P2P_SVD>", "kernel_ms": k_ms, "algorithmic_bytes": alg,
-                                "peak_source": peak_src,
-                                "note": "resident design: each pair is read once; the kernel is issue-bound, see DESIGN.md"}
-        # ---- CPU baseline beside it (rank 0, N = 1 only, bounded sample) --------------------------------------
-        if world == 1 and not args.no_cpu_baseline and args.workload == "c2":
-            threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-            kind, threads, times = cpu_reference_c2(mp, scans, 15.0, 200, threads)
-            v = len(times) / float(np.sum(times))
-            line["cpu_baseline"] = {"value": v, "unit": "registrations/s", "cores": threads, "kind": kind,
-                                    "sample": f"{len(times)} registrations of the same workload (~15 s); ikd-Tree Build excluded"}
-        elif world == 1 and not args.no_cpu_baseline and args.workload == "c4":
-            import oracle as O
-            oo = O.default_opts(residual=O.P2P_SVD, max_iterations=C4_ITERS)
-            t0 = time.perf_counter()
-            cnt = 0
-            with quiet_c_stdout():
-                while time.perf_counter() - t0 < 15.0:
-                    a, b = src[cnt * C4_N:(cnt + 1) * C4_N], tgt[cnt * C4_N:(cnt + 1) * C4_N]
-                    if O.have_ref():
-                        s = O.IkdTree(nthreads=1)
-                        s.build(b)
-                    else:
-                        s = None
-                    O.register(a, b, oo, searcher=s)
-                    if s is not None:
-                        s.close()
-                    cnt += 1
-            line["cpu_baseline"] = {"value": cnt / (time.perf_counter() - t0), "unit": "registrations/s", "cores": 1,
-                                    "kind": "reference" if O.have_ref() else "port",
-                                    "sample": f"{cnt} pairs, ikd-Tree Build + 30 x 1-NN + Kabsch each, one thread"}
-        elif world == 1 and not args.no_cpu_baseline and args.workload == "c3":
-            # the same loop on the host: the reference's ikd-Tree (Build, Add_Points(.., false), Nearest_Search on all
-            # threads) + the restated Gauss-Newton loop, on the first frames of the sequence (~20 s)
-            import oracle as O
-            threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-            oo = O.default_opts(residual=O.P2PLANE_KNN, k=K_NN, max_iterations=ITERS, max_corr_dist=GATE)
-            with quiet_c_stdout():
-                use_ref = O.have_ref()
-                T = np.eye(4)
-                w0, _ = O.transform(T, seq[0])
-                pts = [w0]
-                tree = None
-                if use_ref:
-                    tree = O.IkdTree(nthreads=threads)
-                    tree.build(w0)
-                t0 = time.perf_counter()
-                cnt = 0
-                for scan in seq[1:]:
-                    for i in range(16):
-                        oo.T0[i] = float(T.reshape(16)[i])
-                    T, _r, _ = O.register(scan, np.concatenate(pts), oo, searcher=tree)
-                    wv, _ = O.transform(T, scan)
-                    pts.append(wv)
-                    if tree is not None:
-                        tree.add_points(wv, False)
-                    cnt += 1
-                    if time.perf_counter() - t0 > 20.0:
-                        break
-                dt = time.perf_counter() - t0
-                if tree is not None:
-                    tree.close()
-            line["cpu_baseline"] = {"value": cnt / dt, "unit": "registrations/s", "cores": threads if use_ref else 1,
-                                    "kind": "reference" if use_ref else "port",
-                                    "sample": f"first {cnt} frames of the sequence (map still small: the reference slows down as the tree grows)"}
+        m = rec.pop("_m", None)
+        line = {"metric": rec["metric"], "value": rec["value"], "unit": rec["unit"], "n_gpus": world, "steps": rec["steps"], "warmup": rec["warmup"],
+                "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": rec.get("scaling", "weak"), "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic"}
+        for k, v in rec.items():
+            if k not in line:
+                line[k] = v
+        if m is not None:
+            line["clocks"] = m["clocks"]
+            line["wall_s_incl_flush"] = m["wall"]
+        if configs is not None:
+            line["configs"] = configs
         print(json.dumps(line), flush=True)
-    h.close()
+    B.h.close()
     if world > 1:
-        dist.destroy_process_group()
+        B.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -19,7 +19,7 @@ MAX_K = 16
 
 EXPORTS = [
     "icp4r_create", "icp4r_destroy", "icp4r_last_error", "icp4r_version", "icp4r_default_opts", "icp4r_set_stream",
-    "icp4r_synchronize", "icp4r_launch_count", "icp4r_set_profiling", "icp4r_last_profile", "icp4r_map_build", "icp4r_map_set_downsample", "icp4r_map_add_points",
+    "icp4r_synchronize", "icp4r_launch_count", "icp4r_set_profiling", "icp4r_last_profile", "icp4r_set_stats", "icp4r_get_stats", "icp4r_map_build", "icp4r_map_set_downsample", "icp4r_map_add_points",
     "icp4r_map_size", "icp4r_map_range", "icp4r_map_knn", "icp4r_map_knn_brute", "icp4r_map_sector", "icp4r_map_points",
     "icp4r_register", "icp4r_register_map", "icp4r_register_map_batch", "icp4r_register_batch", "icp4r_shard_unique_id", "icp4r_shard_init", "icp4r_shard_ipc_export", "icp4r_shard_ipc_import",
     "icp4r_register_sharded", "icp4r_transform_points", "icp4r_voxel_grid", "icp4r_odometry_step", "icp4r_map_box_search",
@@ -185,6 +185,15 @@ class Icp4r:
         self._ck(self.lib.icp4r_last_profile(self.h, C.c_void_p(buf.ctypes.data), C.c_int32(buf.shape[0]), C.byref(n)))
         return buf[:n.value].copy()
 
+    def set_stats(self, on: bool):
+        self._ck(self.lib.icp4r_set_stats(self.h, C.c_int(int(on))))
+
+    def get_stats(self):
+        """[searches, squared-distance evaluations, points settled without a search, ...] since the last call"""
+        out = (C.c_int64 * 8)()
+        self._ck(self.lib.icp4r_get_stats(self.h, out))
+        return [int(v) for v in out]
+
     # ---- map
     def map_build(self, pts, cell_size: float = 0.0):
         pts = _f4(pts)
@@ -245,6 +254,15 @@ class Icp4r:
         self._ck(self.lib.icp4r_map_points(self.h, C.c_int(HOST), C.c_void_p(pts.ctypes.data), C.c_void_p(valid.ctypes.data),
                                            C.c_int32(n)))
         return pts, valid
+
+    def map_points_dev(self):
+        """the stored points in insertion order as a torch tensor on the handle's device"""
+        import torch
+        n, _ = self.map_size()
+        pts = torch.zeros((max(n, 1), 4), dtype=torch.float32, device=torch.device("cuda", self.device))
+        self._ck(self.lib.icp4r_map_points(self.h, C.c_int(DEVICE), C.c_void_p(pts.data_ptr()), None, C.c_int32(n)))
+        self.synchronize()
+        return pts[:n]
 
     def map_sector(self, centre, radius, heading_deg):
         n, _ = self.map_size()

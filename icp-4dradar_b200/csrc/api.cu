@@ -266,6 +266,28 @@ int icp4r_last_profile(icp4r_handle h, float* ms_out, int32_t cap, int32_t* n_ou
     return ICP4R_OK;
 }
 
+int icp4r_set_stats(icp4r_handle h, int on) {
+    HCHECK(h);
+    if (on) {
+        CKS(reserve(c, c->d_stats, 8 * sizeof(unsigned long long)));
+        CK(cudaMemsetAsync(c->d_stats.p, 0, 8 * sizeof(unsigned long long), c->stream));
+    }
+    c->stats = on != 0;
+    // captured loops bake the per-call parameter block's address, not its content: nothing to invalidate
+    return ICP4R_OK;
+}
+
+int icp4r_get_stats(icp4r_handle h, int64_t out[8]) {
+    HCHECK(h);
+    if (!out) return fail(c, ICP4R_ERR_INVALID, "icp4r_get_stats: null output");
+    for (int i = 0; i < 8; ++i) out[i] = 0;
+    if (!c->d_stats.p) return ICP4R_OK;
+    CK(cudaMemcpyAsync(out, c->d_stats.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemsetAsync(c->d_stats.p, 0, 8 * sizeof(unsigned long long), c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return ICP4R_OK;
+}
+
 // ---- map ------------------------------------------------------------------------------------------------
 
 int icp4r_map_build(icp4r_handle h, const float* xyzw, int32_t n, int mem, float cell_size) {

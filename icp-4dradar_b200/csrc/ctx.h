@@ -153,6 +153,8 @@ struct RegParams {  // kernel parameters that change per call; lives in device m
     int map_m;
     // neighbours found at the previous iteration, K per source point (NULL: hints switched off)
     int32_t* nb_prev;
+    // work counters (NULL: off), see icp4r_set_stats
+    unsigned long long* stats;
 };
 
 struct GraphKey {
@@ -195,6 +197,8 @@ struct Ctx {
     GridDesc graph_grid_copy{};
     bool use_graph = true;
     bool profiling = false;
+    DevBuf d_stats;  // 8 x uint64 work counters, allocated by icp4r_set_stats
+    bool stats = false;
     std::vector<cudaEvent_t> prof_events;
     std::vector<float> prof_ms;
 

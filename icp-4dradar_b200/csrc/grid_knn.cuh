@@ -65,7 +65,7 @@ __device__ __forceinline__ void consider(float qx, float qy, float qz, const flo
 template <int K>
 __device__ __forceinline__ void scan_segments(const float4* __restrict__ sorted, SegAddr sg, uint32_t s0, uint32_t e0, uint32_t s1,
                                               uint32_t e1, int lane, float qx, float qy, float qz, float gate_f, uint64_t kth,
-                                              TopK<K>& list) {
+                                              TopK<K>& list, unsigned* cand = nullptr) {
     const uint32_t l0 = e0 - s0, l1 = e1 - s1;
     uint32_t inc = l0 + l1;
 #pragma unroll
@@ -75,6 +75,7 @@ __device__ __forceinline__ void scan_segments(const float4* __restrict__ sorted,
     }
     const uint32_t total = __shfl_sync(FULL, inc, 31);
     if (total == 0) return;
+    if (cand) *cand += total;  // work counter (icp4r_set_stats); the pointer is a compile-time null elsewhere
     const uint32_t exc = inc - (l0 + l1);
     // compact the non-empty ranges (in lane order) so the per-lane walk below only steps over real ones
     const unsigned b0 = __ballot_sync(FULL, l0 > 0), b1 = __ballot_sync(FULL, l1 > 0);
@@ -208,7 +209,8 @@ static __device__ __noinline__ uint64_t wide_ball_knn(const GridDesc& g, const f
 template <int K, bool WIDE = true>
 __device__ __forceinline__ uint64_t warp_grid_knn(const GridDesc& g, const float4* __restrict__ sorted, const uint32_t* __restrict__ cs,
                                                   const uint32_t* __restrict__ coarse, int m_sorted, SegAddr sg, float qx, float qy,
-                                                  float qz, float gate_f, float gate_r, int lane, float hint = -1.0f) {
+                                                  float qz, float gate_f, float gate_r, int lane, float hint = -1.0f,
+                                                  unsigned* cand = nullptr) {
     const float qmax = fmaxf(fabsf(qx), fmaxf(fabsf(qy), fabsf(qz)));
     const float margin = fmaxf(g.margin, 9.5367431640625e-7f * qmax);  // 2^-20 * magnitude
 
@@ -305,7 +307,7 @@ __device__ __forceinline__ uint64_t warp_grid_knn(const GridDesc& g, const float
                     }
                 }
             }
-            scan_segments<K>(sorted, sg, s0, e0, s1, e1, lane, qx, qy, qz, gate_f, hinted ? hint_key : kth, list);
+            scan_segments<K>(sorted, sg, s0, e0, s1, e1, lane, qx, qy, qz, gate_f, hinted ? hint_key : kth, list, cand);
         }
         prev = R;
         if (mine != KEY_EMPTY) list.insert(mine);  // carry the previous shells' winners (lanes < K)
@@ -352,7 +354,7 @@ __device__ __forceinline__ uint64_t warp_grid_knn(const GridDesc& g, const float
     if (!done && rneed > 0 && prev < rneed) {
         // no usable bound (tiny map, fewer than K points, or a ball that would cover most of the map): exhaustive scan
         list.clear();
-        scan_segments<K>(sorted, sg, 0u, lane == 0 ? (uint32_t)m_sorted : 0u, 0u, 0u, lane, qx, qy, qz, gate_f, KEY_EMPTY, list);
+        scan_segments<K>(sorted, sg, 0u, lane == 0 ? (uint32_t)m_sorted : 0u, 0u, 0u, lane, qx, qy, qz, gate_f, KEY_EMPTY, list, cand);
         mine = warp_merge_topk<K>(list, lane);
     }
     return mine;

@@ -198,6 +198,7 @@ __global__ void __launch_bounds__(RM_THREADS, 1)
         else if (lane == 28) ia = 7, ib = 7;
     }
     double acc = 0.0;  // this lane's running sum
+    unsigned st_cand = 0, st_q = 0;  // work counters of this warp (icp4r_set_stats)
 #ifdef ICP4R_PHASE_TIMING
     const long long tp0 = clock64();
 #endif
@@ -332,7 +333,8 @@ __global__ void __launch_bounds__(RM_THREADS, 1)
 #ifdef ICP4R_KNN_TIMING
         const long long tq0 = clock64();
 #endif
-        uint64_t mine = warp_grid_knn<KK, false>(g, P.map_sorted, P.map_cell_start, nullptr, P.map_m, sgaddr, qx, qy, qz, P.gate_f, P.gate_r, lane, hint);
+        uint64_t mine = warp_grid_knn<KK, false>(g, P.map_sorted, P.map_cell_start, nullptr, P.map_m, sgaddr, qx, qy, qz, P.gate_f, P.gate_r, lane, hint, &st_cand);
+        ++st_q;
 #ifdef ICP4R_KNN_TIMING
         const int tq_cycles = (int)(clock64() - tq0);
 #endif
@@ -542,6 +544,10 @@ __global__ void __launch_bounds__(RM_THREADS, 1)
     }
 
     flush_parked();
+    if (P.stats != nullptr && lane == 0) {
+        atomicAdd(P.stats + 0, (unsigned long long)st_q);
+        atomicAdd(P.stats + 1, (unsigned long long)st_cand);
+    }
     // block partial in a fixed order: value v = sum over warps 0..7 of lane v's accumulator
 #ifdef ICP4R_PHASE_TIMING
     const long long tp1 = clock64();
@@ -845,6 +851,7 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
     if (fused_shard) {
         P.xt = c->d_xt.as<XchTable>();
     }
+    P.stats = c->stats ? c->d_stats.as<unsigned long long>() : nullptr;
     const bool gicp = o->residual == ICP4R_GICP;
     if (c->use_hints) {
         CKS(reserve_grow(c, c->d_nbprev, (size_t)n * ICP4R_MAX_K * sizeof(int32_t)));
@@ -1111,6 +1118,7 @@ int register_scans_against_map(Ctx* c, Map& mp, const float4* d_src, const int32
             P.map_pts = mp.pts.as<float4>();
             P.map_m = mp.grid.m;
             P.shard_axis = -1;
+            P.stats = c->stats ? c->d_stats.as<unsigned long long>() : nullptr;
             P.nb_prev = c->use_hints ? c->d_nbprev.as<int32_t>() + (size_t)off_host[s0 + b] * ICP4R_MAX_K : nullptr;
             std::memcpy(hs[b].T0, T0s_host ? T0s_host + 16 * (size_t)(s0 + b) : o->T0, sizeof(hs[b].T0));
         }

@@ -120,6 +120,12 @@ int icp4r_launch_count(icp4r_handle h, int64_t* out);
  * time of each launch in milliseconds: max_iterations iteration kernels followed by the fitness pass. */
 int icp4r_set_profiling(icp4r_handle h, int on);
 int icp4r_last_profile(icp4r_handle h, float* ms_out, int32_t cap, int32_t* n_out);
+/* measurement aid: work counters of the registration kernels (icp4r_register*, all flavours), summed over the calls
+ * since the last icp4r_get_stats: out[0] = neighbour searches run, out[1] = squared-distance evaluations (candidates
+ * looked at), out[2] = source points whose previous neighbours were proven still nearest without a search (batched
+ * pairs), out[3..7] reserved. Counting costs a few instructions per search; it is off by default. */
+int icp4r_set_stats(icp4r_handle h, int on);
+int icp4r_get_stats(icp4r_handle h, int64_t out[8]);
 
 /* ---- map: replaces KD_TREE<PointType> (ikd_Tree.h:227-251) ---------------------------------------- */
 /* Build (ikd_Tree.cpp:354-365): discards any previous map. cell_size <= 0 picks one from the density. */

@@ -54,6 +54,6 @@ for p in (0, 1, 63, 64, 65, pairs - 1):
     worst = max(worst, float(np.abs(np.asarray(To).reshape(4, 4) - T0[p]).max()))
     assert abs(ro.fitness - R0["fitness"][p]) <= 1e-9 * max(1.0, ro.fitness), (p, ro.fitness, R0["fitness"][p])
 print("vs oracle (6 pairs): max |dT| = %.3e" % worst)
-for env in ({"ICP4R_RB_THREADS": "384"}, {"ICP4R_RB_THREADS": "512"}, {"ICP4R_RB_SLACK": "0.15"}, {"ICP4R_RB_SLACK": "0.3"},
-            {"ICP4R_RB_CELL_PTS": "1.0"}, {"ICP4R_RB_CELL_PTS": "3.0"}, {"ICP4R_RB_CELL_PTS": "1.0", "ICP4R_RB_SLACK": "0.15"}):
+for env in ({"ICP4R_RB_CELL_PTS": "3.0"}, {"ICP4R_RB_CELL_PTS": "4.0"}, {"ICP4R_RB_CELL_PTS": "5.0"}, {"ICP4R_RB_CELL_PTS": "6.0"},
+            {"ICP4R_RB_CELL_PTS": "8.0"}, {"ICP4R_RB_CELL_PTS": "12.0"}, {"ICP4R_RB_CELL_PTS": "4.0", "ICP4R_RB_SLACK": "0.1"}):
     run(env)
