@@ -225,11 +225,21 @@ def cpu_c2(mp, scans, budget_s, max_regs, threads, residual=None, k=K_NN, iters=
             kind, searcher = "port", O.BruteSearcher(mp)
             threads = O.num_threads()
         times = []
+        tn = None
         t_all = time.perf_counter()
         i = 0
         while i < max_regs and (time.perf_counter() - t_all) < budget_s:
             t0 = time.perf_counter()
-            O.register(scans[i % len(scans)], mp, oo, searcher=searcher)
+            if oo.residual == O.GICP:
+                # the map's covariances are computed once, outside the timed calls (our arm caches them in the handle too;
+                # fast_gicp itself recomputes them on every setInputTarget): the generous baseline
+                if tn is None:
+                    tn = O.gicp_normals(mp, k, searcher)
+                    t0 = time.perf_counter()
+                sc = scans[i % len(scans)]
+                O.gicp_register(sc, mp, oo, searcher=searcher, normals=(O.gicp_normals(sc, k), tn))
+            else:
+                O.register(scans[i % len(scans)], mp, oo, searcher=searcher)
             times.append(time.perf_counter() - t0)
             i += 1
         if hasattr(searcher, "close"):
@@ -498,6 +508,7 @@ class Bench:
         step = 4 << 20
         for a in range(0, m, step):
             _i, _d, found = h2.map_knn(map_pts_dev[a:min(a + step, m)], 1, GATE)
+            h2.synchronize()   # device outputs are ordered on the handle's own stream
             total += int((found > 0).sum().item())
         h2.close()
         return total
@@ -651,8 +662,9 @@ class Bench:
             import oracle as O
             kind, threads, times = cpu_c2(mp, scans, 10.0, 50, self.threads, residual=O.GICP, iters=64, gate=0.0, early_exit=1)
             rec["cpu_baseline"] = {"value": len(times) / float(np.sum(times)), "unit": "registrations/s", "cores": threads, "kind": kind,
-                                   "sample": f"{len(times)} registrations, restated fast_gicp loop with the reference's ikd-Tree for the neighbour searches "
-                                             "(target covariances recomputed per call like fast_gicp's setInputTarget); fast_gicp itself is absent from the image"}
+                                   "sample": f"{len(times)} registrations, restated fast_gicp loop with the reference's ikd-Tree for the neighbour searches; the map's "
+                                             "covariances computed once outside the timed calls (cached, like our arm; fast_gicp recomputes them per call); "
+                                             "fast_gicp itself is absent from the image"}
         return rec
 
     # ---- C3 -------------------------------------------------------------------------------------------------------

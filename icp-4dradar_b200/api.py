@@ -22,7 +22,7 @@ EXPORTS = [
     "icp4r_synchronize", "icp4r_launch_count", "icp4r_set_profiling", "icp4r_last_profile", "icp4r_set_stats", "icp4r_get_stats", "icp4r_map_build", "icp4r_map_set_downsample", "icp4r_map_add_points",
     "icp4r_map_size", "icp4r_map_range", "icp4r_map_knn", "icp4r_map_knn_brute", "icp4r_map_sector", "icp4r_map_points",
     "icp4r_register", "icp4r_register_map", "icp4r_register_map_batch", "icp4r_register_batch", "icp4r_shard_unique_id", "icp4r_shard_init", "icp4r_shard_ipc_export", "icp4r_shard_ipc_import",
-    "icp4r_register_sharded", "icp4r_transform_points", "icp4r_voxel_grid", "icp4r_odometry_step", "icp4r_map_box_search",
+    "icp4r_register_sharded", "icp4r_accumulate_slab", "icp4r_transform_points", "icp4r_voxel_grid", "icp4r_odometry_step", "icp4r_map_box_search",
     "icp4r_map_radius_search", "icp4r_map_delete_boxes", "icp4r_map_add_boxes", "icp4r_map_delete_points", "icp4r_doppler_filter",
 ]
 
@@ -423,6 +423,16 @@ class Icp4r:
         return T.reshape(4, 4), res
 
     # ---- Doppler filter
+    def accumulate_slab(self, src, opts: Opts, T, axis: int = -1, slab_lo: float = 0.0, slab_hi: float = 0.0):
+        """this slab's partial accumulators [ACC_LEN] at pose T (no cross-rank sum, no solve)"""
+        src = _f4(src)
+        ps, mem = _ptr(src)
+        Tm = np.ascontiguousarray(T, np.float64).reshape(16)
+        acc = np.zeros(ACC_LEN, np.float64)
+        self._ck(self.lib.icp4r_accumulate_slab(self.h, ps, C.c_int32(src.shape[0]), C.c_int(mem), C.byref(opts), C.c_void_p(Tm.ctypes.data),
+                                                C.c_int(axis), C.c_float(slab_lo), C.c_float(slab_hi), C.c_void_p(acc.ctypes.data)))
+        return acc
+
     def doppler_filter(self, records, iterations: int = 0, seed: int = 1, sigma: float = 0.5, split: float = 0.2):
         """records: [n,5] x,y,z,intensity,v_r (numpy or CUDA tensor). Returns (static_mask uint8 [n], DopplerResult)."""
         if isinstance(records, np.ndarray):

@@ -777,6 +777,16 @@ int icp4r_register_sharded(icp4r_handle h, const float* src, int32_t n, int mem,
     return register_against_map(c, c->map, static_cast<const float4*>(dsrc), n, opts, axis, slab_lo, slab_hi, T_out, res, nullptr);
 }
 
+int icp4r_accumulate_slab(icp4r_handle h, const float* src, int32_t n, int mem, const icp4r_opts* opts, const double T[16], int axis,
+                          float slab_lo, float slab_hi, double acc_out[ICP4R_ACC_LEN]) {
+    HCHECK(h);
+    if (!opts || !T || !acc_out || n < 0 || (n > 0 && !src) || bad_mem(mem) || axis < -1 || axis > 2)
+        return fail(c, ICP4R_ERR_INVALID, "icp4r_accumulate_slab: bad arguments");
+    const void* dsrc = nullptr;
+    CKS(stage_in(c, c->d_src, src, (size_t)n * sizeof(float4), mem, &dsrc));
+    return accumulate_slab(c, c->map, static_cast<const float4*>(dsrc), n, opts, T, axis, slab_lo, slab_hi, acc_out);
+}
+
 // ---- Doppler filter ---------------------------------------------------------------------------------------------
 
 int icp4r_doppler_filter(icp4r_handle h, const float* xyziv, int32_t n, int mem, const icp4r_doppler_opts* opts, uint8_t* static_mask,

@@ -249,6 +249,9 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
                          float slab_lo, float slab_hi, double* T_out_host, icp4r_result* res_host,
                          const icp4r_dump* dump_dev);
 
+int accumulate_slab(Ctx* c, Map& mp, const float4* d_src, int n, const icp4r_opts* o, const double* T_host, int shard_axis, float slab_lo,
+                    float slab_hi, double* acc_out_host);
+
 int register_scans_against_map(Ctx* c, Map& mp, const float4* d_src, const int32_t* off_host, int nscan, const icp4r_opts* o,
                                const double* T0s_host, double* T_out_host, icp4r_result* res_host);
 

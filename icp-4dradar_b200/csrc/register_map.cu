@@ -1055,6 +1055,73 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
     return ICP4R_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ one slab pass
+// One linearisation of slab-sharded registration at a given pose: the accumulators of the source points this slab owns,
+// without the cross-rank sum and without the solve (MODE_ITER_NOSOLVE of the same kernel the sharded loop runs).
+int accumulate_slab(Ctx* c, Map& mp, const float4* d_src, int n, const icp4r_opts* o, const double* T_host, int shard_axis, float slab_lo,
+                    float slab_hi, double* acc_out_host) {
+    if (!mp.built) return fail(c, ICP4R_ERR_STATE, "registration target has no built map");
+    if (o->residual < 0 || o->residual > ICP4R_P2PLANE_3PT) return fail(c, ICP4R_ERR_INVALID, "bad residual kind %d", o->residual);
+    if (o->residual == ICP4R_GICP) return fail(c, ICP4R_ERR_UNSUPPORTED, "icp4r_accumulate_slab does not support ICP4R_GICP");
+    const int k = knn_k_for(o);
+    if (k > ICP4R_MAX_K) return fail(c, ICP4R_ERR_INVALID, "k=%d exceeds ICP4R_MAX_K", k);
+    if (o->residual == ICP4R_P2PLANE_KNN && k < 3) return fail(c, ICP4R_ERR_INVALID, "P2PLANE_KNN needs k >= 3");
+    const bool sharded = shard_axis >= 0;
+    if (sharded && !(o->max_corr_dist > 0.0 && std::isfinite(o->max_corr_dist)))
+        return fail(c, ICP4R_ERR_INVALID, "a slab pass needs a finite max_corr_dist (halo guarantee)");
+    CKS(reserve(c, c->d_params, sizeof(RegParams)));
+    CKS(reserve(c, c->d_state, sizeof(RegState)));
+    CKS(reserve(c, c->d_T, 16 * sizeof(double)));
+    CKS(reserve(c, c->d_res, sizeof(ResultBlock)));
+    CKS(reserve(c, c->d_partials, (size_t)c->sm_count * 4 * ICP4R_ACC_LEN * sizeof(double) + 1024));
+    int wpb = (n + c->sm_count - 1) / c->sm_count;
+    wpb = std::min(std::max(wpb, 4), RM_WARPS);
+    const int threads = wpb * 32;
+    const int blocks = std::min(std::max(1, (n + wpb - 1) / wpb), c->sm_count);
+    struct Stage {
+        RegParams prm;
+        double T0[16];
+        double acc[ICP4R_ACC_LEN];
+    };
+    Stage* hs = static_cast<Stage*>(c->h_pinned);
+    RegParams& P = hs->prm;
+    std::memset(&P, 0, sizeof(P));
+    P.src = d_src;
+    P.n = n;
+    P.residual = o->residual;
+    P.k = k;
+    P.max_iterations = 1;
+    gate_params(o->max_corr_dist, &P.gate_f, &P.gate_r);
+    P.plane_thresh = o->plane_thresh;
+    P.map_sorted = mp.grid.sorted;
+    P.map_cell_start = mp.grid.cell_start;
+    P.map_coarse = mp.grid.coarse;
+    P.map_pts = mp.pts.as<float4>();
+    P.map_m = mp.grid.m;
+    P.shard_axis = sharded ? shard_axis : -1;
+    P.slab_lo = slab_lo;
+    P.slab_hi = slab_hi;
+    P.stats = c->stats ? c->d_stats.as<unsigned long long>() : nullptr;
+    std::memcpy(hs->T0, T_host, sizeof(hs->T0));
+    RegParams* d_prm = c->d_params.as<RegParams>();
+    RegState* d_st = c->d_state.as<RegState>();
+    CK(cudaMemcpyAsync(d_prm, &hs->prm, sizeof(RegParams), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_T.p, hs->T0, sizeof(hs->T0), cudaMemcpyHostToDevice, c->stream));
+    init_state_kernel<<<1, 32, 0, c->stream>>>(d_st, c->d_T.as<double>());
+    c->launches += 1;
+    GridDesc g = mp.grid;
+    g.sorted = nullptr;
+    g.cell_start = nullptr;
+    g.coarse = nullptr;
+    g.m = 0;
+    if (n > 0) dispatch_iter(c, o->residual, k, MODE_ITER_NOSOLVE, blocks, threads, 1, g, d_prm, d_st, c->d_partials.as<double>(), c->d_res.as<ResultBlock>(), 0);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(hs->acc, reinterpret_cast<const char*>(d_st) + offsetof(RegState, acc), sizeof(hs->acc), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    std::memcpy(acc_out_host, hs->acc, sizeof(hs->acc));
+    return ICP4R_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ batched scans
 // nscan independent scans against the same map in ONE sequence of launches (gridDim.y = scan): a single scan of a
 // few thousand points cannot fill the GPU (the iteration kernel is latency-bound, profiles/), several can.

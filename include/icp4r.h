@@ -190,6 +190,14 @@ int icp4r_shard_ipc_import(icp4r_handle h, const unsigned char* handles, int ran
 int icp4r_register_sharded(icp4r_handle h, const float* src_xyzw, int32_t n, int mem, const icp4r_opts* opts,
                            int axis, float slab_lo, float slab_hi, double T_out[16], icp4r_result* res);
 
+/* One linearisation of a slab-sharded registration at the pose T, WITHOUT the cross-rank sum and the solve: acc_out
+ * receives this slab's partial accumulators (layout of icp4r_dump.acc) over the source points whose transformed
+ * position falls in [slab_lo, slab_hi) along `axis` (axis = -1: every point, the whole map). For host programs that
+ * bring their own collective (MPI, gloo, ...) and for checking the ownership / halo rule on a single GPU. acc_out is
+ * HOST memory. All residual kinds except ICP4R_GICP. */
+int icp4r_accumulate_slab(icp4r_handle h, const float* src_xyzw, int32_t n, int mem, const icp4r_opts* opts, const double T[16],
+                          int axis, float slab_lo, float slab_hi, double acc_out[ICP4R_ACC_LEN]);
+
 /* ---- Doppler static-point filter (next to the path: the step before registration in icp4radar) -------------------- */
 /* records: n x 5 floats x, y, z, intensity, v_r (the reference's .bin layout, iterative_closest_point.cpp:373-377).
  * Two-point sine-model RANSAC (fitSineRansac, :85-128), static/dynamic split by the signed residual (:392-403) and

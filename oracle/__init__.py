@@ -388,6 +388,14 @@ def se3_exp(xi):
     return T.reshape(4, 4)
 
 
+def gn_update(acc, T):
+    """one Gauss-Newton pose update from summed accumulators (H upper triangle [21], g [6]): T <- exp(x^) T with H x = -g"""
+    acc = np.asarray(acc, np.float64)
+    rc, x = chol6_solve(acc[:21], acc[21:27])
+    assert rc == 0
+    return se3_exp(x) @ np.asarray(T, np.float64).reshape(4, 4)
+
+
 def plane_fit(P):
     P = np.ascontiguousarray(P, np.float64)
     n = np.zeros(3, np.float64)

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def test_c5_full_size_properties(pkg, handle):
+def test_c5_full_size_properties(pkg, O, handle):
     """C5: 16,384-pt scan vs a 20 M-point map"""
     import torch
     import bench
@@ -38,6 +38,11 @@ def test_c5_full_size_properties(pkg, handle):
     # the grid search equals the exhaustive search (same kernel family, no grid) on a sample of queries
     bi, bd, bf = handle.map_knn_brute(q[:128], 5, 2.0)
     assert (bi == idx[:128]).all() and (bd.view(np.int32) == d2[:128].view(np.int32)).all() and (bf == found[:128]).all()
+    # ... and the ORACLE's exhaustive exact kNN over all 20 M points (OpenMP over queries, ~5e9 distance evaluations),
+    # bit for bit: indices, float distances, counts
+    sel = np.concatenate([np.arange(128), np.arange(128, len(q), len(q) // 128)[:128]])
+    oi, od, of_ = O.knn(mp, q[sel], 5, 2.0)
+    assert (oi == idx[sel]).all() and (od.view(np.int32) == d2[sel].view(np.int32)).all() and (of_ == found[sel]).all()
     # registration: deterministic, and the scan (drawn from the map, moved by a small rigid transform) snaps back
     o = pkg.default_opts(residual=pkg.P2PLANE_KNN, k=5, max_iterations=20, max_corr_dist=2.0)
     T1, r1, _ = handle.register_map(q, o)
@@ -51,12 +56,23 @@ def test_c5_full_size_properties(pkg, handle):
     # and the loop did not make things worse than the identity pose
     i0, dd0, f0 = handle.map_knn(q, 1, 2.0)
     assert r1.fitness <= float(dd0[f0 == 1, 0].astype(np.float64).mean()) * 1.05
+    # one linearisation of the full-size problem against the oracle: the accumulators of a 1,024-point slice of the scan
+    # at the returned pose (oracle: exhaustive kNN over the 20 M points), J^T J / J^T r to 1e-9
+    oo = O.default_opts(residual=O.P2PLANE_KNN, k=5, max_iterations=20, max_corr_dist=2.0)
+    part = np.ascontiguousarray(q[:1024])
+    got = handle.accumulate_slab(part, o, T1, -1)
+    want, _idx, used = O.accumulate(part, mp, oo, T1)
+    assert int(got[28]) == used
+    assert np.linalg.norm(got[:21] - want[:21]) <= 1e-9 * np.linalg.norm(want[:21])
+    g_scale = max(np.linalg.norm(want[21:27]), np.sqrt(want[[0, 6, 11, 15, 18, 20]].sum() * want[27]))
+    assert np.linalg.norm(got[21:27] - want[21:27]) <= 1e-9 * g_scale
 
 
-def test_c4_full_size_properties(pkg, handle):
+def test_c4_full_size_properties(pkg, O, handle):
     """C4: 65,536 frame pairs of 2,048 + 2,048 points in one call. Every pair converges by iteration count, matches
-    every point (ungated), and a sample of pairs agrees with the same pair registered alone through the other
-    implementation of the loop (icp4r_register: grid in global memory, warp per query) to 1e-8."""
+    every point (ungated), and a sample of 24 pairs agrees with the ORACLE's registration of the same pair (exhaustive
+    exact 1-NN + fp64 Kabsch, 30 iterations) within the stated pose tolerance, and with the same pair registered alone
+    through the other implementation of the loop (icp4r_register: grid in global memory, warp per query) to 1e-8."""
     import bench
     src, tgt, so = bench.make_c4(65536)
     o = pkg.default_opts(residual=pkg.P2P_SVD, max_iterations=30)
@@ -64,10 +80,16 @@ def test_c4_full_size_properties(pkg, handle):
     assert np.isfinite(T).all() and (res["converged"] == 1).all() and (res["iterations"] == 30).all()
     assert (res["n_corr"] == 2048).all() and (res["n_fitness"] == 2048).all()          # ungated: every point matches
     rng = np.random.default_rng(0)
+    oo = O.default_opts(residual=O.P2P_SVD, max_iterations=30)
     single = pkg.Icp4r(0)
     try:
         for p in rng.choice(65536, 24, replace=False):
             a, b = src[so[p]:so[p + 1]], tgt[so[p]:so[p + 1]]
+            To, ro, _ = O.register(a, b, oo)
+            D = T[p] @ np.linalg.inv(To)
+            assert np.linalg.norm(D[:3, 3]) <= 1e-4 and rot_angle(D[:3, :3]) <= 1e-4, (p, np.linalg.norm(D[:3, 3]), rot_angle(D[:3, :3]))
+            assert ro.n_corr == res["n_corr"][p] and ro.iterations == res["iterations"][p]
+            assert abs(ro.fitness - res["fitness"][p]) <= 1e-6 * max(ro.fitness, 1e-12)
             T1, r1, _ = single.register(a, b, o)
             assert np.abs(T1 - T[p]).max() < 1e-8, (p, np.abs(T1 - T[p]).max())
             assert abs(r1.fitness - res["fitness"][p]) <= 1e-9 * max(r1.fitness, 1e-12) and r1.n_corr == res["n_corr"][p]
