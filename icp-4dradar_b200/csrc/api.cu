@@ -182,6 +182,10 @@ int icp4r_create(int device, icp4r_handle* out) {
     c->use_graph = !(ng && ng[0] == '1');
     const char* nh = std::getenv("ICP4R_NO_HINTS");
     c->use_hints = !(nh && nh[0] == '1');
+    {
+        const char* nl = std::getenv("ICP4R_NO_LB");
+        c->use_lb = !(nl && nl[0] == '1');
+    }
     const char* br = std::getenv("ICP4R_BATCH_REPRODUCIBLE");
     c->batch_reproducible = br && br[0] == '1';
     *out = c;
@@ -206,6 +210,7 @@ int icp4r_destroy(icp4r_handle h) {
     release(c->d_xch);
     release(c->d_xt);
     release(c->d_nbprev);
+    release(c->d_nbstate);
     release(c->bf_part);
     release(c->gs_pts);
     release(c->gs_idx);

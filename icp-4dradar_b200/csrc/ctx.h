@@ -120,6 +120,16 @@ struct RegState {
     unsigned ticket;
     unsigned ticket_fit;
     int pad;
+    // the last pose increment D as the displacement map q -> q - D^-1 q = (I - R^T) q + R^T t (row-major 3x4) and the
+    // iteration whose solve produced it (-1: none yet): a source point moved by |dA q| between that pass and the next
+    float dA[12];
+    int last_pass;
+    int pad3;
+};
+
+struct NbState {   // per source point, next to nb_prev
+    float lb;      // every map point other than the k remembered neighbours was at least this far away (metres) ...
+    int tag;       // ... at the pass with this tag (call epoch * 4096 + iteration)
 };
 
 struct RegParams {  // kernel parameters that change per call; lives in device memory so graphs stay valid
@@ -155,6 +165,10 @@ struct RegParams {  // kernel parameters that change per call; lives in device m
     int32_t* nb_prev;
     // work counters (NULL: off), see icp4r_set_stats
     unsigned long long* stats;
+    // per-point bound that lets a point keep its neighbours without a search (NULL: off), and this call's epoch
+    NbState* nb_state;
+    int epoch;
+    int pad_epoch;
 };
 
 struct GraphKey {
@@ -205,11 +219,13 @@ struct Ctx {
     // sharding (NCCL loaded lazily with dlopen)
     void* nccl_comm = nullptr;
     int rank = 0, world = 1;
-    DevBuf d_xch, d_xt, d_nbprev;
+    DevBuf d_xch, d_xt, d_nbprev, d_nbstate;
+    int reg_epoch = 0;  // bumped per registration call: NbState entries of earlier calls never match
     DevBuf bf_part;                           // exhaustive k-NN: per-split partial lists
     DevBuf gs_pts, gs_idx, gs_d2, gs_found;  // GICP: exhaustive k-NN scratch for the scan's own normals
     DevBuf vg_keys, vg_vals, vg_sort, vg_tiles, vg_out;  // voxel-grid centroid filter
     bool batch_reproducible = false;  // ICP4R_BATCH_REPRODUCIBLE=1 (see register_batch.cu)
+    bool use_lb = true;     // ICP4R_NO_LB=1 turns the keep-the-neighbours-without-a-search proof off (A/B measurements)
     bool use_hints = true;  // ICP4R_NO_HINTS=1 turns the previous-iteration search bound off (A/B measurements)            // local exchange buffer and the peer table
     void* xch_peers[XCH_MAXW] = {nullptr};  // peer mappings opened with cudaIpcOpenMemHandle
     bool xch_ready = false;

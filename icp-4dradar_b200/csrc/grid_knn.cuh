@@ -210,7 +210,9 @@ template <int K, bool WIDE = true>
 __device__ __forceinline__ uint64_t warp_grid_knn(const GridDesc& g, const float4* __restrict__ sorted, const uint32_t* __restrict__ cs,
                                                   const uint32_t* __restrict__ coarse, int m_sorted, SegAddr sg, float qx, float qy,
                                                   float qz, float gate_f, float gate_r, int lane, float hint = -1.0f,
-                                                  unsigned* cand = nullptr) {
+                                                  unsigned* cand = nullptr, float* cover2 = nullptr) {
+    // *cover2 (optional): every valid point with d2 below this value (and inside the gate) has been ranked by the search,
+    // i.e. a point that is not among the returned ones is at least that far away (squared) or beyond the gate
     const float qmax = fmaxf(fabsf(qx), fmaxf(fabsf(qy), fabsf(qz)));
     const float margin = fmaxf(g.margin, 9.5367431640625e-7f * qmax);  // 2^-20 * magnitude
 
@@ -245,6 +247,7 @@ __device__ __forceinline__ uint64_t warp_grid_knn(const GridDesc& g, const float
     TopK<K> list;
     list.clear();
     uint64_t mine = KEY_EMPTY, kth = KEY_EMPTY;
+    if (cover2) *cover2 = 0.0f;  // unknown until one of the proven exits below sets it
     int prev = -1;  // radius already scanned
     bool done = false;
     // Dense neighbourhoods (walls): look at the query's own cell first. Its k-th distance then prunes the rows and
@@ -316,6 +319,7 @@ __device__ __forceinline__ uint64_t warp_grid_knn(const GridDesc& g, const float
         kth = __shfl_sync(FULL, mine, K - 1);
         if (hinted) {  // the pass covered the whole hint box
             done = true;
+            if (cover2) *cover2 = hint * 0.999999f;
             break;
         }
 
@@ -328,11 +332,13 @@ __device__ __forceinline__ uint64_t warp_grid_knn(const GridDesc& g, const float
         if (cz + R < hiz) bound = fminf(bound, (g.oz + (float)(cz + R + 1) * g.cell) - qz);
         if (bound > 3.0e38f) {
             done = true;  // cube covers the gate box
+            if (cover2) *cover2 = INFINITY;
             break;
         }
         const float b = bound - margin;
         if (b > 0.0f && kth != KEY_EMPTY && key_d2(kth) < b * b * 0.99999905f) {
             done = true;
+            if (cover2) *cover2 = b * b * 0.99999905f;
             break;
         }
     }
@@ -356,6 +362,7 @@ __device__ __forceinline__ uint64_t warp_grid_knn(const GridDesc& g, const float
         list.clear();
         scan_segments<K>(sorted, sg, 0u, lane == 0 ? (uint32_t)m_sorted : 0u, 0u, 0u, lane, qx, qy, qz, gate_f, KEY_EMPTY, list, cand);
         mine = warp_merge_topk<K>(list, lane);
+        if (cover2) *cover2 = INFINITY;
     }
     return mine;
 }

@@ -19,8 +19,10 @@
 
 namespace icp4r {
 
-constexpr int RM_WARPS = 28;  // upper bound (28 x 32 threads x 72 registers fill one SM); the launch picks warps per block so that every SM gets one block
+constexpr int RM_WARPS = 28;
+constexpr int RM_BLOCKS_PER_SM = 1;  // measured: two 14-warp blocks per SM are no faster in batch mode (1.88 vs 1.85 ms) and slower for one scan (0.54 vs 0.46 ms)
 constexpr int RM_THREADS = RM_WARPS * 32;
+constexpr int RM_PARK = 32;    // plane fits parked per warp (P2PLANE_KNN)
 
 enum { MODE_ITER = 0, MODE_ITER_NOSOLVE = 1, MODE_FITNESS = 2, MODE_FITNESS_NOFINAL = 3 };
 
@@ -30,6 +32,15 @@ struct ResultBlock {  // what travels back to the host in one copy
     int xch_timeout;
     int pad;
 };
+
+// The pose increment D (3x4 in shared memory) as the map q -> q - D^-1 q: how far a point at q moved with this update.
+__device__ __forceinline__ void publish_increment(RegState* st, const double* Ds, int iter, int lane) {
+    if (lane < 12) {
+        const int r = lane >> 2, cc = lane & 3;
+        st->dA[lane] = cc < 3 ? (float)((r == cc ? 1.0 : 0.0) - Ds[4 * cc + r]) : (float)((Ds[r] * Ds[3] + Ds[4 + r] * Ds[7]) + Ds[8 + r] * Ds[11]);
+    }
+    if (lane == 0) st->last_pass = iter;
+}
 
 // Pose update from the reduced accumulators, run by one full warp (see solve_warp.cuh). `tot`, `Ts` and `ws`
 // (>= 32 doubles of scratch) are shared memory; every branch is warp-uniform.
@@ -72,6 +83,7 @@ __device__ __forceinline__ void warp_solve_and_update(int residual, const RegPar
         __syncwarp();
         const double tn = warp_compose_entry(Ds, Ts, lane);
         if (lane < 12) st->T[lane] = tn;
+        publish_increment(st, Ds, iter, lane);
         const double mse = tot[16] / cnt;
         if (lane == 0) st->last_cost = mse;
         if (P.early_exit) {
@@ -103,6 +115,7 @@ __device__ __forceinline__ void warp_solve_and_update(int residual, const RegPar
         __syncwarp();
         const double tn = warp_compose_entry(Ds, Ts, lane);
         if (lane < 12) st->T[lane] = tn;
+        publish_increment(st, Ds, iter, lane);
         if (lane == 0) st->last_cost = tot[27];
         if (P.early_exit) {
             const double wn = sqrt(aux[0] * aux[0] + aux[1] * aux[1] + aux[2] * aux[2]);
@@ -143,12 +156,15 @@ __device__ void write_result(const RegState* st, ResultBlock* out) {
 //   the normal equations live one per lane, in one register, for the whole kernel.
 // No block barrier on the per-point path. At the end the 8 warps' lanes are summed in a fixed order into the
 // block partial, and the last block to finish sums the partials in a fixed order and solves.
-template <int KIND, int K, int MODE>
-__global__ void __launch_bounds__(RM_THREADS, 1)
+// LB = false compiles the kernel without the keep-the-neighbours proof (exactly k neighbours ranked, no per-point state):
+// the flavour for a single small scan, where the proof cannot shorten the iteration's latency chain (one point per warp:
+// the slowest point sets the time) and its extra registers only cost.
+template <int KIND, int K, int MODE, bool LB>
+__global__ void __launch_bounds__(RM_THREADS, RM_BLOCKS_PER_SM)
     reg_iter_kernel(GridDesc g, const RegParams* __restrict__ prm, RegState* __restrict__ st,
                     double* __restrict__ partials, ResultBlock* __restrict__ out, int iter) {
     constexpr bool FIT = (MODE == MODE_FITNESS || MODE == MODE_FITNESS_NOFINAL);
-    constexpr int KK = FIT ? 1 : K;
+    (void)0;
     constexpr int RK = FIT ? ICP4R_P2P_SVD : KIND;  // residual actually accumulated
     // blockIdx.y selects one of the independent scans of a batched call (each has its own parameters, state,
     // partials and result); single registrations launch with gridDim.y == 1
@@ -160,9 +176,12 @@ __global__ void __launch_bounds__(RM_THREADS, 1)
 
     __shared__ WarpSegs segs[RM_WARPS];
     __shared__ double scr[RM_WARPS][3][12];  // per-warp operands of the lane products (up to 3 residual rows)
-    constexpr bool PARKED = (!FIT && KIND == ICP4R_P2PLANE_KNN && K <= 8);  // plane fits done 8 points at a time, one per lane
-    constexpr int PARK = 8;
-    __shared__ double scrq[PARKED ? RM_WARPS : 1][PARK][8];
+    constexpr bool PARKED = (!FIT && KIND == ICP4R_P2PLANE_KNN && K <= 8);  // plane fits done up to 32 points at a time, one per lane
+    constexpr int PARK = RM_PARK;
+    // per warp: PARK rows of 8 doubles (the residual row of a parked point) + PARK x (K + 1) ints (its neighbours + itself)
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    double (*scrq)[PARK][8] = reinterpret_cast<double (*)[PARK][8]>(dyn_smem);
+    int (*nbq)[PARK][K + 1] = reinterpret_cast<int (*)[PARK][K + 1]>(dyn_smem + (size_t)(blockDim.x >> 5) * PARK * 8 * sizeof(double));
     __shared__ double red[RM_WARPS][ICP4R_ACC_LEN];
     __shared__ double tot[ICP4R_ACC_LEN];
     __shared__ double Ts[16];
@@ -170,8 +189,12 @@ __global__ void __launch_bounds__(RM_THREADS, 1)
     __shared__ int own_list[RM_THREADS], own_cnt[RM_WARPS], own_n;  // sharded maps: this block's owned source points
 
     __shared__ RegParams P;  // per-call parameters: one copy per block instead of ~25 registers per thread
+    __shared__ float s_dA[12];  // displacement map of the last pose increment and the pass it belongs to (publish_increment)
+    __shared__ int s_last_pass;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     if (tid < 16) Ts[tid] = st->T[tid];
+    if (tid >= 16 && tid < 28) s_dA[tid - 16] = st->dA[tid - 16];
+    if (tid == 28) s_last_pass = st->last_pass;
     if (tid >= 32 && tid < 32 + (int)(sizeof(RegParams) / 4)) reinterpret_cast<uint32_t*>(&P)[tid - 32] = reinterpret_cast<const uint32_t*>(prm)[tid - 32];
     __syncthreads();
 
@@ -198,7 +221,7 @@ __global__ void __launch_bounds__(RM_THREADS, 1)
         else if (lane == 28) ia = 7, ib = 7;
     }
     double acc = 0.0;  // this lane's running sum
-    unsigned st_cand = 0, st_q = 0;  // work counters of this warp (icp4r_set_stats)
+    unsigned st_cand = 0, st_q = 0, st_settled = 0;  // work counters of this warp (icp4r_set_stats)
 #ifdef ICP4R_PHASE_TIMING
     const long long tp0 = clock64();
 #endif
@@ -207,7 +230,6 @@ __global__ void __launch_bounds__(RM_THREADS, 1)
     // points at once, one point per lane (the fit is ~400 fp64 instructions that every lane would otherwise execute
     // redundantly for every single point); lane q keeps point q's neighbour indices until the flush
     int parked = 0;
-    __shared__ int nbq[PARKED ? RM_WARPS : 1][PARK][K + 1];  // parked neighbour indices (+ the source index in slot K)
     auto flush_parked = [&]() {
         if (PARKED) {
             __syncwarp();  // the parked indices were written by other lanes
@@ -264,66 +286,210 @@ __global__ void __launch_bounds__(RM_THREADS, 1)
     const int n = P.n;
     const int kq = FIT ? 1 : P.k;
     const int nwb = blockDim.x >> 5;  // warps in this block (<= RM_WARPS)
-    const int gw = blockIdx.x * nwb + w, nw = gridDim.x * nwb;
+
     // Sharded map: the rank whose slab holds the transformed point owns it. Ownership changes with the pose, and a
     // warp that strides over ALL points would find a random share of its points owned (the slowest warp sets the
     // kernel time), so each block first compacts the owned points of its contiguous chunk into an ordered list
     // (ballot + prefix: deterministic) and its warps stride over that list.
+    // Work distribution. Every block owns a contiguous chunk of the source points and walks it blockDim.x points at a time:
+    //   phase A  one point per THREAD: is the point this block's business at all (slab-sharded maps: the rank whose slab
+    //            holds the transformed point owns it), and — P2PLANE_KNN after the first iteration — are its remembered
+    //            neighbours provably still the k nearest (see the per-point path below)? Such points skip the search;
+    //            their planes are fitted up to 32 at a time, one per lane, by their own warp.
+    //   phase B  the remaining points are compacted, in order (ballot + prefix: deterministic), into a block-wide list
+    //            and the warps stride over it one point per WARP: search, plane fit (parked), accumulation.
+    // A static split of ALL points over the warps made the slowest warp (the one with the most searches) set the kernel
+    // time: 30 % of the warp time of the batched C2 launch was spent at the block barrier (profiles/).
     const bool sharded = P.shard_axis >= 0;
-    const int per = sharded ? (n + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-    const int cbeg = sharded ? min(n, (int)blockIdx.x * per) : 0, cend = sharded ? min(n, cbeg + per) : 1;
+    const int per = (n + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int cbeg = min(n, (int)blockIdx.x * per), cend = min(n, cbeg + per);
+    // with only a point or two per warp (a single scan spread over the whole GPU) the lane-parallel phase would be one
+    // more serial step on the iteration's latency chain: the per-point path does the same test inline then
+    const bool lane_phase = LB && PARKED && P.nb_state != nullptr && iter > 0 && per >= 2 * nwb;
     for (int c0 = cbeg; c0 < cend; c0 += (int)blockDim.x) {
-    if (sharded) {
-        const int i = c0 + tid;
-        bool own = false;
-        if (i < cend) {
-            const float4 p = __ldg(P.src + i);
-            double pw[3];
-            xform_point(Ts, p.x, p.y, p.z, pw);
-            const float v = P.shard_axis == 0 ? (float)pw[0] : (P.shard_axis == 1 ? (float)pw[1] : (float)pw[2]);
-            own = (v >= P.slab_lo) && (v < P.slab_hi);
+        const int my_i = (c0 + tid < cend) ? c0 + tid : -1;
+        bool need = my_i >= 0;
+        if (lane_phase || sharded) {
+            const int kp = P.k;
+            bool ok = false;
+            int nbv[K];
+            float lb_new = 0.0f;
+            if (need) {
+                const float4 p = __ldg(P.src + my_i);
+                double pw[3];
+                xform_point(Ts, p.x, p.y, p.z, pw);
+                const float qx = (float)pw[0], qy = (float)pw[1], qz = (float)pw[2];
+                if (sharded) {
+                    const float v = P.shard_axis == 0 ? qx : (P.shard_axis == 1 ? qy : qz);
+                    need = (v >= P.slab_lo) && (v < P.slab_hi);
+                }
+                if (need && lane_phase) {
+                    const float margin_q = fmaxf(g.margin, 9.5367431640625e-7f * fmaxf(fabsf(qx), fmaxf(fabsf(qy), fabsf(qz))));
+                    const int32_t* nbp = P.nb_prev + (size_t)my_i * K;
+                    uint64_t key[K];
+                    bool all_valid = true;
+                    float hmax = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        key[j] = KEY_EMPTY;
+                        if (j < kp) {
+                            const int pj = __ldcg(nbp + j);
+                            if (pj < 0) {
+                                all_valid = false;
+                            } else {
+                                const float4 c = __ldg(pts + pj);
+                                const float d = dist2_exact(qx, qy, qz, c.x, c.y, c.z);
+                                hmax = fmaxf(hmax, d);
+                                if (!(d <= P.gate_f)) all_valid = false;  // also catches NaN
+                                key[j] = pack_key(d, pj);
+                            }
+                        }
+                    }
+                    if (all_valid) {
+                        const float2 sv = __ldcg(reinterpret_cast<const float2*>(P.nb_state + my_i));
+                        if (__float_as_int(sv.y) == P.epoch * 4096 + s_last_pass) {
+                            const float ex = __fmaf_rn(s_dA[0], qx, __fmaf_rn(s_dA[1], qy, __fmaf_rn(s_dA[2], qz, s_dA[3])));
+                            const float ey = __fmaf_rn(s_dA[4], qx, __fmaf_rn(s_dA[5], qy, __fmaf_rn(s_dA[6], qz, s_dA[7])));
+                            const float ez = __fmaf_rn(s_dA[8], qx, __fmaf_rn(s_dA[9], qy, __fmaf_rn(s_dA[10], qz, s_dA[11])));
+                            const float delta = sqrtf(__fmaf_rn(ex, ex, __fmaf_rn(ey, ey, ez * ez))) * 1.0001f + 2.0f * margin_q;
+                            lb_new = sv.x - delta;
+                            ok = sqrtf(hmax) * 1.000001f + margin_q < lb_new;
+                        }
+                    }
+                    if (ok) {
+                        // ascending (d2, index): insertion network over the K packed keys in registers
+#pragma unroll
+                        for (int a2 = 1; a2 < K; ++a2)
+#pragma unroll
+                            for (int b2 = a2; b2 > 0; --b2) {
+                                const uint64_t lo = key[b2 - 1] < key[b2] ? key[b2 - 1] : key[b2];
+                                const uint64_t hi = key[b2 - 1] < key[b2] ? key[b2] : key[b2 - 1];
+                                key[b2 - 1] = lo;
+                                key[b2] = hi;
+                            }
+#pragma unroll
+                        for (int j = 0; j < K; ++j) nbv[j] = j < kp ? key_idx(key[j]) : -1;
+                        need = false;
+                    }
+                }
+            }
+            if (PARKED) {
+                const unsigned okm = __ballot_sync(FULL, ok);
+                if (okm != 0u) {
+                    if (ok) {
+                        const int slot = __popc(okm & ((1u << lane) - 1u));  // parked == 0 here: phase B flushes before it ends
+                        int32_t* nbp = P.nb_prev + (size_t)my_i * K;
+#pragma unroll
+                        for (int j = 0; j < K; ++j)
+                            if (j < kp) {
+                                nbq[w][slot][j] = nbv[j];
+                                nbp[j] = nbv[j];
+                                if (P.dump_idx) P.dump_idx[((size_t)iter * n + my_i) * kp + j] = nbv[j];
+                            }
+                        nbq[w][slot][K] = my_i;
+                        __stcg(reinterpret_cast<float2*>(P.nb_state + my_i), make_float2(lb_new, __int_as_float(P.epoch * 4096 + iter)));
+                    }
+                    parked = __popc(okm);
+                    st_settled += (lane == 0) ? __popc(okm) : 0;
+                    flush_parked();
+                }
+            }
         }
-        const unsigned bal = __ballot_sync(FULL, own);
-        __syncthreads();  // the previous chunk's list is no longer read
-        if (lane == 0) own_cnt[w] = __popc(bal);
-        __syncthreads();
-        int before = 0;
-        for (int j = 0; j < w; ++j) before += own_cnt[j];
-        if (own) own_list[before + __popc(bal & ((1u << lane) - 1u))] = i;
-        if (tid == 0) {
-            int t = 0;
-            for (int j = 0; j < nwb; ++j) t += own_cnt[j];
-            own_n = t;
+        const bool direct = !(lane_phase || sharded);  // every point of the round takes the per-point path: no list needed
+        if (!direct) {   // the block's list of points that need the per-point path, in point order
+            const unsigned bal = __ballot_sync(FULL, need);
+            __syncthreads();  // the previous round's list is no longer read
+            if (lane == 0) own_cnt[w] = __popc(bal);
+            __syncthreads();
+            int before = 0;
+            for (int j = 0; j < w; ++j) before += own_cnt[j];
+            if (need) own_list[before + __popc(bal & ((1u << lane) - 1u))] = my_i;
+            if (tid == 0) {
+                int t = 0;
+                for (int j = 0; j < nwb; ++j) t += own_cnt[j];
+                own_n = t;
+            }
+            __syncthreads();
         }
-        __syncthreads();
-    }
-    for (int jj = 0;; ++jj) {
-        int i;
-        if (sharded) {
-            const int sl = w + jj * nwb;
-            if (sl >= own_n) break;
-            i = own_list[sl];
-        } else {
-            i = gw + jj * nw;
-            if (i >= n) break;
-        }
+    const int list_n = direct ? min((int)blockDim.x, cend - c0) : own_n;
+    for (int sl = w; sl < list_n; sl += nwb) {
+        const int i = direct ? c0 + sl : own_list[sl];
         const float4 p = __ldg(P.src + i);
         double pw[3];
         xform_point(Ts, p.x, p.y, p.z, pw);
         const float qx = (float)pw[0], qy = (float)pw[1], qz = (float)pw[2];
-        // the neighbours of the previous iteration bound this iteration's k-th distance (see warp_grid_knn)
+        // What is remembered per source point from the previous pass: its k neighbours (nb_prev) and a lower bound LB on the
+        // distance to every OTHER map point (nb_state). The pose update moved the point by delta, so the others are now at
+        // least LB - delta away: if the farthest remembered neighbour is closer than that, the k nearest neighbours are
+        // exactly the remembered ones — no search, only a re-ranking by (d2, index). Otherwise the remembered neighbours
+        // still bound the k-th distance (hint): one pass over the ball of that radius, widened a little so that the
+        // search also yields a useful new LB (the (k+1)-th distance, or the radius up to which it ranked every point).
+        constexpr int KS = FIT ? 1 : (LB ? K + 1 : K);
         float hint = -1.0f;
         int32_t* nbp = P.nb_prev ? P.nb_prev + (size_t)i * K : nullptr;
+        NbState* nbs = (LB && P.nb_state) ? P.nb_state + i : nullptr;
+        const float margin_q = fmaxf(g.margin, 9.5367431640625e-7f * fmaxf(fabsf(qx), fmaxf(fabsf(qy), fabsf(qz))));
+        uint64_t mine = KEY_EMPTY;
+        bool settled = false;
+        float lb_now = 0.0f;
         if (nbp != nullptr && (FIT ? P.max_iterations > 0 : iter > 0)) {
-            const int pj = lane < kq ? __ldcg(nbp + lane) : 0;
+            const int kp = P.k;
+            const int pj = lane < kp ? __ldcg(nbp + lane) : 0;
             float dh = 0.0f;
-            if (lane < kq && pj >= 0) {
+            if (lane < kp && pj >= 0) {
                 const float4 c = __ldg(pts + pj);
                 dh = dist2_exact(qx, qy, qz, c.x, c.y, c.z);
             }
+            const bool all_valid = !__any_sync(FULL, pj < 0);
             const unsigned hb = __reduce_max_sync(FULL, __float_as_uint(dh));  // d2 >= 0: bit order == value order; NaN sorts last
-            if (!__any_sync(FULL, pj < 0)) {
-                if (hb < 0x7f800000u) hint = __uint_as_float(hb);
+            const float hbf = __uint_as_float(hb);
+            // how far this point moved with the last pose increment (see publish_increment)
+            const float ex = __fmaf_rn(s_dA[0], qx, __fmaf_rn(s_dA[1], qy, __fmaf_rn(s_dA[2], qz, s_dA[3])));
+            const float ey = __fmaf_rn(s_dA[4], qx, __fmaf_rn(s_dA[5], qy, __fmaf_rn(s_dA[6], qz, s_dA[7])));
+            const float ez = __fmaf_rn(s_dA[8], qx, __fmaf_rn(s_dA[9], qy, __fmaf_rn(s_dA[10], qz, s_dA[11])));
+            const float delta = sqrtf(__fmaf_rn(ex, ex, __fmaf_rn(ey, ey, ez * ez))) * 1.0001f + 2.0f * margin_q;
+            if (!lane_phase && all_valid && nbs != nullptr && hb < 0x7f800000u && (FIT || hbf <= P.gate_f)) {
+                const float2 sv = __ldcg(reinterpret_cast<const float2*>(nbs));
+                if (__float_as_int(sv.y) == P.epoch * 4096 + s_last_pass) {
+                    lb_now = sv.x - delta;
+                    settled = sqrtf(hbf) * 1.000001f + margin_q < lb_now;  // false for NaN
+                }
+            }
+            if (settled) {
+                const uint64_t key = (lane < kp) ? pack_key(dh, pj) : KEY_EMPTY;
+                if (FIT) {
+                    const uint64_t m1 = warp_min_u64(key);
+                    if (lane == 0 && key_d2(m1) <= P.gate_f) mine = m1;
+                } else {
+                    int rank = 0;  // keys are unique (index in the low word): the ranks are a permutation
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        const uint64_t kj = __shfl_sync(FULL, key, j);
+                        if (j < kp && kj < key) ++rank;
+                    }
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        const uint64_t kj = __shfl_sync(FULL, key, j);
+                        const int rj = __shfl_sync(FULL, rank, j);
+                        if (j < kp && rj == lane) mine = kj;
+                    }
+                }
+                ++st_settled;
+            } else if (FIT) {
+                // any remembered neighbour bounds the nearest distance: take the closest of them
+                const unsigned hm = __reduce_min_sync(FULL, (lane < kp && pj >= 0) ? __float_as_uint(dh) : 0x7f800000u);
+                if (hm < 0x7f800000u) hint = __uint_as_float(hm);
+            } else if (all_valid) {
+                if (hb < 0x7f800000u) {
+                    hint = hbf;
+                    if (nbs != nullptr) {
+                        // widen the ball by a few times the last displacement (what is left of a converging loop's motion)
+                        const float r = sqrtf(hbf);
+                        const float slack = fminf(fmaxf(4.0f * delta, 0.05f * r), 0.5f * r);
+                        const float wide = (r + slack) * (r + slack);
+                        hint = (hbf <= P.gate_f) ? fminf(wide, fmaxf(P.gate_f, hbf)) : wide;
+                    }
+                }
             } else if (P.gate_r < 3.0e38f) {
                 // fewer than k neighbours inside the gate last time: most likely still so. The gate itself is the
                 // bound then: one pass over the gate ball instead of growing shell by shell up to it.
@@ -333,8 +499,21 @@ __global__ void __launch_bounds__(RM_THREADS, 1)
 #ifdef ICP4R_KNN_TIMING
         const long long tq0 = clock64();
 #endif
-        uint64_t mine = warp_grid_knn<KK, false>(g, P.map_sorted, P.map_cell_start, nullptr, P.map_m, sgaddr, qx, qy, qz, P.gate_f, P.gate_r, lane, hint, &st_cand);
-        ++st_q;
+        if (!settled) {
+            float cover2 = 0.0f;
+            mine = warp_grid_knn<KS, false>(g, P.map_sorted, P.map_cell_start, nullptr, P.map_m, sgaddr, qx, qy, qz, P.gate_f, P.gate_r, lane, hint, &st_cand,
+                                            &cover2);
+            ++st_q;
+            if (!FIT && nbs != nullptr) {
+                // every map point that is not one of the kq nearest is at least this far away
+                const uint64_t nxt = __shfl_sync(FULL, mine, kq < KS ? kq : KS - 1);
+                const bool full = __shfl_sync(FULL, mine, kq - 1) != KEY_EMPTY;
+                const float d_next = (kq < KS && nxt != KEY_EMPTY) ? key_d2(nxt) : INFINITY;
+                const float lb2 = fminf(fminf(d_next, cover2), P.gate_f);
+                lb_now = full ? fmaxf(sqrtf(lb2) * 0.999999f - margin_q, 0.0f) : 0.0f;
+            }
+        }
+        if (!FIT && nbs != nullptr && lane == 0) __stcg(reinterpret_cast<float2*>(nbs), make_float2(lb_now, __int_as_float(P.epoch * 4096 + iter)));
 #ifdef ICP4R_KNN_TIMING
         const int tq_cycles = (int)(clock64() - tq0);
 #endif
@@ -384,8 +563,8 @@ __global__ void __launch_bounds__(RM_THREADS, 1)
             }
         } else if (RK == ICP4R_P2PLANE_KNN && PARKED) {
             if (found == kq && kq >= 3) {  // park the neighbours in lane `parked`; the fit happens in flush_parked()
-                if (lane < kq) nbq[PARKED ? w : 0][parked][lane] = key_idx(mine);
-                if (lane == K) nbq[PARKED ? w : 0][parked][K] = i;
+                if (lane < kq) nbq[w][parked][lane] = key_idx(mine);
+                if (lane == K) nbq[w][parked][K] = i;
                 if (++parked == PARK) flush_parked();
             }
         } else if (RK == ICP4R_P2PLANE_KNN) {
@@ -541,12 +720,14 @@ __global__ void __launch_bounds__(RM_THREADS, 1)
             __syncwarp();
         }
     }
+    flush_parked();  // phase A of the next round parks from slot 0
     }
 
     flush_parked();
     if (P.stats != nullptr && lane == 0) {
         atomicAdd(P.stats + 0, (unsigned long long)st_q);
         atomicAdd(P.stats + 1, (unsigned long long)st_cand);
+        atomicAdd(P.stats + 2, (unsigned long long)st_settled);
     }
     // block partial in a fixed order: value v = sum over warps 0..7 of lane v's accumulator
 #ifdef ICP4R_PHASE_TIMING
@@ -726,51 +907,73 @@ __global__ void init_state_kernel(RegState* st, const double* T0) {
         st->n_corr = 0;
         st->ticket = 0;
         st->ticket_fit = 0;
+        st->last_pass = -1;
     }
+}
+
+template <int KIND, int K, int MODE, bool LB>
+static void launch_iter_mode(Ctx* c, int blocks, int threads, int nscan, const GridDesc& g, const RegParams* prm, RegState* st, double* partials,
+                             ResultBlock* out, int iter) {
+    constexpr bool FIT = (MODE == MODE_FITNESS || MODE == MODE_FITNESS_NOFINAL);
+    constexpr bool PARKED = (!FIT && KIND == ICP4R_P2PLANE_KNN && K <= 8);
+    // dynamic shared memory: the parked plane-fit rows (see reg_iter_kernel); sized for the largest block
+    constexpr size_t per_warp = PARKED ? (size_t)RM_PARK * (8 * sizeof(double) + (K + 1) * sizeof(int)) : 0;
+    static bool attr_set = false;
+    if (!attr_set && per_warp > 0) {
+        cudaFuncSetAttribute(reg_iter_kernel<KIND, K, MODE, LB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * RM_WARPS));
+        attr_set = true;
+    }
+    reg_iter_kernel<KIND, K, MODE, LB><<<dim3(blocks, nscan), threads, per_warp * (threads / 32), c->stream>>>(g, prm, st, partials, out, iter);
 }
 
 template <int KIND, int K>
 static void launch_iter(Ctx* c, int mode, int blocks, int threads, int nscan, const GridDesc& g, const RegParams* prm, RegState* st,
-                        double* partials, ResultBlock* out, int iter) {
+                        double* partials, ResultBlock* out, int iter, bool lb) {
+    // the proof only exists for the kinds whose loop keeps per-point state (see register_against_map); GICP never does
+    constexpr bool CAN_LB = KIND != ICP4R_GICP;
     switch (mode) {
         case MODE_ITER:
-            reg_iter_kernel<KIND, K, MODE_ITER><<<dim3(blocks, nscan), threads, 0, c->stream>>>(g, prm, st, partials, out, iter);
+            if (CAN_LB && lb) launch_iter_mode<KIND, K, MODE_ITER, CAN_LB>(c, blocks, threads, nscan, g, prm, st, partials, out, iter);
+            else launch_iter_mode<KIND, K, MODE_ITER, false>(c, blocks, threads, nscan, g, prm, st, partials, out, iter);
             break;
         case MODE_ITER_NOSOLVE:
-            reg_iter_kernel<KIND, K, MODE_ITER_NOSOLVE><<<dim3(blocks, nscan), threads, 0, c->stream>>>(g, prm, st, partials, out, iter);
+            if (CAN_LB && lb) launch_iter_mode<KIND, K, MODE_ITER_NOSOLVE, CAN_LB>(c, blocks, threads, nscan, g, prm, st, partials, out, iter);
+            else launch_iter_mode<KIND, K, MODE_ITER_NOSOLVE, false>(c, blocks, threads, nscan, g, prm, st, partials, out, iter);
             break;
         case MODE_FITNESS:
-            reg_iter_kernel<KIND, K, MODE_FITNESS><<<dim3(blocks, nscan), threads, 0, c->stream>>>(g, prm, st, partials, out, iter);
+            if (CAN_LB && lb) launch_iter_mode<KIND, K, MODE_FITNESS, CAN_LB>(c, blocks, threads, nscan, g, prm, st, partials, out, iter);
+            else launch_iter_mode<KIND, K, MODE_FITNESS, false>(c, blocks, threads, nscan, g, prm, st, partials, out, iter);
             break;
         default:
-            reg_iter_kernel<KIND, K, MODE_FITNESS_NOFINAL><<<dim3(blocks, nscan), threads, 0, c->stream>>>(g, prm, st, partials, out, iter);
+            if (CAN_LB && lb) launch_iter_mode<KIND, K, MODE_FITNESS_NOFINAL, CAN_LB>(c, blocks, threads, nscan, g, prm, st, partials, out, iter);
+            else launch_iter_mode<KIND, K, MODE_FITNESS_NOFINAL, false>(c, blocks, threads, nscan, g, prm, st, partials, out, iter);
             break;
     }
     c->launches += 1;
 }
 
 static void dispatch_iter(Ctx* c, int kind, int K, int mode, int blocks, int threads, int nscan, const GridDesc& g,
-                          const RegParams* prm, RegState* st, double* partials, ResultBlock* out, int iter) {
+                          const RegParams* prm, RegState* st, double* partials, ResultBlock* out, int iter, bool lb = false) {
     switch (kind) {
         case ICP4R_P2P_SVD:
-            launch_iter<ICP4R_P2P_SVD, 1>(c, mode, blocks, threads, nscan, g, prm, st, partials, out, iter);
+            launch_iter<ICP4R_P2P_SVD, 1>(c, mode, blocks, threads, nscan, g, prm, st, partials, out, iter, lb);
             break;
         case ICP4R_P2P_GN:
-            launch_iter<ICP4R_P2P_GN, 1>(c, mode, blocks, threads, nscan, g, prm, st, partials, out, iter);
+            launch_iter<ICP4R_P2P_GN, 1>(c, mode, blocks, threads, nscan, g, prm, st, partials, out, iter, lb);
             break;
         case ICP4R_P2LINE:
-            launch_iter<ICP4R_P2LINE, 2>(c, mode, blocks, threads, nscan, g, prm, st, partials, out, iter);
+            launch_iter<ICP4R_P2LINE, 2>(c, mode, blocks, threads, nscan, g, prm, st, partials, out, iter, lb);
             break;
         case ICP4R_GICP:
-            launch_iter<ICP4R_GICP, 1>(c, mode, blocks, threads, nscan, g, prm, st, partials, out, iter);
+            launch_iter<ICP4R_GICP, 1>(c, mode, blocks, threads, nscan, g, prm, st, partials, out, iter, lb);
             break;
         case ICP4R_P2PLANE_3PT:
-            launch_iter<ICP4R_P2PLANE_3PT, 5>(c, mode, blocks, threads, nscan, g, prm, st, partials, out, iter);
+            launch_iter<ICP4R_P2PLANE_3PT, 5>(c, mode, blocks, threads, nscan, g, prm, st, partials, out, iter, lb);
             break;
         default:
-            if (K <= 5) launch_iter<ICP4R_P2PLANE_KNN, 5>(c, mode, blocks, threads, nscan, g, prm, st, partials, out, iter);
-            else if (K <= 8) launch_iter<ICP4R_P2PLANE_KNN, 8>(c, mode, blocks, threads, nscan, g, prm, st, partials, out, iter);
-            else launch_iter<ICP4R_P2PLANE_KNN, 16>(c, mode, blocks, threads, nscan, g, prm, st, partials, out, iter);
+            if (K <= 5) launch_iter<ICP4R_P2PLANE_KNN, 5>(c, mode, blocks, threads, nscan, g, prm, st, partials, out, iter, lb);
+            else if (K <= 8) launch_iter<ICP4R_P2PLANE_KNN, 8>(c, mode, blocks, threads, nscan, g, prm, st, partials, out, iter, lb);
+            else launch_iter<ICP4R_P2PLANE_KNN, 16>(c, mode, blocks, threads, nscan, g, prm, st, partials, out, iter, lb);
             break;
     }
 }
@@ -809,10 +1012,11 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
     CKS(reserve(c, c->d_res, sizeof(ResultBlock)));
     // one source point per warp at a time; warps per block chosen so that the points spread over all SMs
     // (one block per SM keeps the number of partials the last block has to sum at <= sm_count)
-    int wpb = (n + c->sm_count - 1) / c->sm_count;
+    const int max_blocks = c->sm_count * RM_BLOCKS_PER_SM;
+    int wpb = (n + max_blocks - 1) / max_blocks;
     wpb = std::min(std::max(wpb, 4), RM_WARPS);
     const int threads = wpb * 32;
-    int blocks = std::min(std::max(1, (n + wpb - 1) / wpb), c->sm_count);
+    int blocks = std::min(std::max(1, (n + wpb - 1) / wpb), max_blocks);
     // sized once for the largest grid so the pointer baked into captured graphs never moves
     CKS(reserve(c, c->d_partials, (size_t)c->sm_count * 4 * ICP4R_ACC_LEN * sizeof(double) + 1024));
 
@@ -856,6 +1060,15 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
     if (c->use_hints) {
         CKS(reserve_grow(c, c->d_nbprev, (size_t)n * ICP4R_MAX_K * sizeof(int32_t)));
         P.nb_prev = c->d_nbprev.as<int32_t>();
+        if (c->use_lb && !gicp && o->max_iterations < 4096) {
+            const void* before = c->d_nbstate.p;
+            CKS(reserve_grow(c, c->d_nbstate, (size_t)std::max(n, 1) * sizeof(NbState)));
+            if (c->d_nbstate.p != before) CK(cudaMemsetAsync(c->d_nbstate.p, 0xFF, c->d_nbstate.cap, c->stream));
+            P.nb_state = c->d_nbstate.as<NbState>();
+            P.epoch = (++c->reg_epoch) & 0x3FFFF;
+        }
+        // worth it only with a few points per warp (see reg_iter_kernel): a single small scan runs the lean flavour
+        if ((n + blocks - 1) / blocks < 2 * wpb) P.nb_state = nullptr;
         // Sharded maps: a rank only refreshes the entries of the points it owns, so a point that changes owner finds
         // an older entry — still k valid points of this rank's slab, hence still a bound — or none (-1). Entries of
         // an earlier CALL must not survive (the map may have changed since): clear them.
@@ -890,6 +1103,7 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
         P.corr = c->d_gicp_corr.as<GicpCorr>();
     }
     std::memcpy(hs->T0, o->T0, sizeof(hs->T0));
+    const bool lb = P.nb_state != nullptr;  // which flavour of the iteration kernel runs (see reg_iter_kernel)
 
     RegParams* d_prm = c->d_params.as<RegParams>();
     RegState* d_st = c->d_state.as<RegState>();
@@ -921,28 +1135,28 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
         if (gicp) {
             // linearise (grid-wide, accumulators left in st->acc) then one single-block Levenberg-Marquardt step
             for (int it = it0; it < it1; ++it) {
-                dispatch_iter(c, o->residual, k, MODE_ITER_NOSOLVE, blocks, threads, 1, g, d_prm, d_st, d_part, d_out, it);
+                dispatch_iter(c, o->residual, k, MODE_ITER_NOSOLVE, blocks, threads, 1, g, d_prm, d_st, d_part, d_out, it, lb);
                 gicp_lm_step(c, d_prm, d_st, it);
             }
-            if (fit) dispatch_iter(c, o->residual, k, MODE_FITNESS, blocks, threads, 1, g, d_prm, d_st, d_part, d_out, 0);
+            if (fit) dispatch_iter(c, o->residual, k, MODE_FITNESS, blocks, threads, 1, g, d_prm, d_st, d_part, d_out, 0, lb);
         } else if (sharded && !fused_shard) {
             for (int it = 0; it < iters; ++it) {
-                dispatch_iter(c, o->residual, k, MODE_ITER_NOSOLVE, blocks, threads, 1, g, d_prm, d_st, d_part, d_out, it);
+                dispatch_iter(c, o->residual, k, MODE_ITER_NOSOLVE, blocks, threads, 1, g, d_prm, d_st, d_part, d_out, it, lb);
                 if (shard_allreduce(c, acc_ptr, ICP4R_ACC_LEN) != ICP4R_OK) enqueue_status = ICP4R_ERR_NCCL;
                 solve_kernel<<<1, 32, 0, c->stream>>>(o->residual, d_prm, d_st, it);
                 c->launches += 1;
             }
-            dispatch_iter(c, o->residual, k, MODE_FITNESS_NOFINAL, blocks, threads, 1, g, d_prm, d_st, d_part, d_out, 0);
+            dispatch_iter(c, o->residual, k, MODE_FITNESS_NOFINAL, blocks, threads, 1, g, d_prm, d_st, d_part, d_out, 0, lb);
             if (shard_allreduce(c, acc_ptr, 2) != ICP4R_OK) enqueue_status = ICP4R_ERR_NCCL;
             fitness_final_kernel<<<1, 32, 0, c->stream>>>(d_st, d_out);
             c->launches += 1;
         } else {
             if (prof) cudaEventRecord(c->prof_events[0], c->stream);
             for (int it = it0; it < it1; ++it) {
-                dispatch_iter(c, o->residual, k, MODE_ITER, blocks, threads, 1, g, d_prm, d_st, d_part, d_out, it);
+                dispatch_iter(c, o->residual, k, MODE_ITER, blocks, threads, 1, g, d_prm, d_st, d_part, d_out, it, lb);
                 if (prof) cudaEventRecord(c->prof_events[it + 1], c->stream);
             }
-            if (fit) dispatch_iter(c, o->residual, k, MODE_FITNESS, blocks, threads, 1, g, d_prm, d_st, d_part, d_out, 0);
+            if (fit) dispatch_iter(c, o->residual, k, MODE_FITNESS, blocks, threads, 1, g, d_prm, d_st, d_part, d_out, 0, lb);
             if (prof) cudaEventRecord(c->prof_events[iters + 1], c->stream);
         }
     };
@@ -965,7 +1179,7 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
     }
     auto run_range = [&](int it0, int it1, bool fit) -> int {
         GraphKey key{o->residual, k, blocks, it0 + 4096 * it1,
-                     threads | (sharded ? 1 << 16 : 0) | (gicp ? 1 << 17 : 0) | (fused_shard ? 1 << 19 : 0) | (fit ? 1 << 21 : 0)};
+                     threads | (sharded ? 1 << 16 : 0) | (gicp ? 1 << 17 : 0) | (fused_shard ? 1 << 19 : 0) | (fit ? 1 << 21 : 0) | (lb ? 1 << 22 : 0)};
         cudaGraphExec_t exec = nullptr;
         if (want_graph) {
             auto it = c->graphs.find(key);
@@ -1074,10 +1288,11 @@ int accumulate_slab(Ctx* c, Map& mp, const float4* d_src, int n, const icp4r_opt
     CKS(reserve(c, c->d_T, 16 * sizeof(double)));
     CKS(reserve(c, c->d_res, sizeof(ResultBlock)));
     CKS(reserve(c, c->d_partials, (size_t)c->sm_count * 4 * ICP4R_ACC_LEN * sizeof(double) + 1024));
-    int wpb = (n + c->sm_count - 1) / c->sm_count;
+    const int max_blocks = c->sm_count * RM_BLOCKS_PER_SM;
+    int wpb = (n + max_blocks - 1) / max_blocks;
     wpb = std::min(std::max(wpb, 4), RM_WARPS);
     const int threads = wpb * 32;
-    const int blocks = std::min(std::max(1, (n + wpb - 1) / wpb), c->sm_count);
+    const int blocks = std::min(std::max(1, (n + wpb - 1) / wpb), max_blocks);
     struct Stage {
         RegParams prm;
         double T0[16];
@@ -1150,7 +1365,7 @@ int register_scans_against_map(Ctx* c, Map& mp, const float4* d_src, const int32
         const int B = std::min(CH, nscan - s0);
         int nmax = 0;
         for (int b = 0; b < B; ++b) nmax = std::max(nmax, off_host[s0 + b + 1] - off_host[s0 + b]);
-        const int bps = std::max(1, c->sm_count / B);  // blocks per scan: the whole batch is one wave
+        const int bps = std::max(1, c->sm_count * RM_BLOCKS_PER_SM / B);  // blocks per scan: the whole batch is one wave
         int wpb = (nmax + bps - 1) / std::max(bps, 1);
         wpb = std::min(std::max(wpb, 4), RM_WARPS);
         const int threads = wpb * 32;
@@ -1162,6 +1377,13 @@ int register_scans_against_map(Ctx* c, Map& mp, const float4* d_src, const int32
         CKS(reserve_grow(c, c->bm_res, (size_t)B * sizeof(ResultBlock)));
         CKS(reserve_grow(c, c->bm_partials, (size_t)B * blocks * ICP4R_ACC_LEN * sizeof(double)));
         CKS(reserve_grow(c, c->d_nbprev, (size_t)off_host[s0 + B] * ICP4R_MAX_K * sizeof(int32_t)));
+        const bool use_lb = c->use_hints && c->use_lb && o->max_iterations < 4096 && (nmax + blocks - 1) / blocks >= 2 * wpb;
+        if (use_lb) {
+            const void* before = c->d_nbstate.p;
+            CKS(reserve_grow(c, c->d_nbstate, (size_t)std::max(off_host[s0 + B], 1) * sizeof(NbState)));
+            if (c->d_nbstate.p != before) CK(cudaMemsetAsync(c->d_nbstate.p, 0xFF, c->d_nbstate.cap, c->stream));
+            ++c->reg_epoch;
+        }
         const bool moved = old_ptrs[0] != c->bm_params.p || old_ptrs[1] != c->bm_state.p || old_ptrs[2] != c->bm_res.p ||
                            old_ptrs[3] != c->bm_partials.p;
         Stage* hs = static_cast<Stage*>(c->h_pinned);
@@ -1187,6 +1409,8 @@ int register_scans_against_map(Ctx* c, Map& mp, const float4* d_src, const int32
             P.shard_axis = -1;
             P.stats = c->stats ? c->d_stats.as<unsigned long long>() : nullptr;
             P.nb_prev = c->use_hints ? c->d_nbprev.as<int32_t>() + (size_t)off_host[s0 + b] * ICP4R_MAX_K : nullptr;
+            P.nb_state = use_lb ? c->d_nbstate.as<NbState>() + off_host[s0 + b] : nullptr;
+            P.epoch = c->reg_epoch & 0x3FFFF;
             std::memcpy(hs[b].T0, T0s_host ? T0s_host + 16 * (size_t)(s0 + b) : o->T0, sizeof(hs[b].T0));
         }
         RegParams* d_prm = c->bm_params.as<RegParams>();
@@ -1199,11 +1423,11 @@ int register_scans_against_map(Ctx* c, Map& mp, const float4* d_src, const int32
         init_state_kernel<<<B, 32, 0, c->stream>>>(d_st, c->bm_T0.as<double>());
         c->launches += 1;
         auto enqueue = [&]() {
-            for (int it = 0; it < iters; ++it) dispatch_iter(c, o->residual, k, MODE_ITER, blocks, threads, B, g, d_prm, d_st, d_part, d_out, it);
-            dispatch_iter(c, o->residual, k, MODE_FITNESS, blocks, threads, B, g, d_prm, d_st, d_part, d_out, 0);
+            for (int it = 0; it < iters; ++it) dispatch_iter(c, o->residual, k, MODE_ITER, blocks, threads, B, g, d_prm, d_st, d_part, d_out, it, use_lb);
+            dispatch_iter(c, o->residual, k, MODE_FITNESS, blocks, threads, B, g, d_prm, d_st, d_part, d_out, 0, use_lb);
         };
         const bool want_graph = c->use_graph && !c->profiling;
-        GraphKey key{o->residual, k, blocks, iters, threads | (1 << 18) | (B << 20)};
+        GraphKey key{o->residual, k, blocks, iters + (use_lb ? 8192 : 0), threads | (1 << 18) | (B << 20)};
         cudaGraphExec_t exec = nullptr;
         if (want_graph) {
             if (moved || c->graph_grid_owner != &mp.grid || std::memcmp(&c->graph_grid_copy, &g, sizeof(GridDesc)) != 0) {
