@@ -636,6 +636,37 @@ int icp4r_register(icp4r_handle h, const float* src, int32_t n, const float* tgt
     HCHECK(h);
     if (!opts || n < 0 || m < 0 || (n > 0 && !src) || (m > 0 && !tgt) || bad_mem(mem))
         return fail(c, ICP4R_ERR_INVALID, "icp4r_register: bad arguments");
+    // Point-to-point kinds on clouds that fit one SM's shared memory: the whole registration — target grid, every
+    // iteration, the solve, the fitness pass — runs as ONE launch of the resident kernel of icp4r_register_batch (a batch
+    // of one pair): no per-iteration launch, no grid in global memory, no cross-block reduction.
+    {
+        const char* e = std::getenv("ICP4R_REGISTER_VIA_MAP");
+        const bool kind_ok = opts->residual == ICP4R_P2P_SVD || opts->residual == ICP4R_P2P_GN;
+        if (kind_ok && !dump && !c->profiling && !(e && e[0] == '1') && register_batch_fits(n, m) && opts->max_iterations >= 0) {
+            struct Stage {
+                int32_t soff[2], toff[2];
+                double T[16];
+                icp4r_result res;
+            };
+            Stage* hs = static_cast<Stage*>(c->h_pinned);
+            hs->soff[0] = 0, hs->soff[1] = n, hs->toff[0] = 0, hs->toff[1] = m;
+            const void *dsrc = nullptr, *dtgt = nullptr;
+            CKS(stage_in(c, c->b_src, src, (size_t)n * sizeof(float4), mem, &dsrc));
+            CKS(stage_in(c, c->b_tgt, tgt, (size_t)m * sizeof(float4), mem, &dtgt));
+            CKS(reserve(c, c->b_soff, 4 * sizeof(int32_t)));
+            CKS(reserve(c, c->b_T, 16 * sizeof(double)));
+            CKS(reserve(c, c->b_res, sizeof(icp4r_result)));
+            CK(cudaMemcpyAsync(c->b_soff.p, hs->soff, 4 * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+            CKS(register_batch(c, static_cast<const float4*>(dsrc), c->b_soff.as<int32_t>(), static_cast<const float4*>(dtgt),
+                               c->b_soff.as<int32_t>() + 2, 1, n, m, opts, c->b_T.as<double>(), c->b_res.as<icp4r_result>()));
+            CK(cudaMemcpyAsync(hs->T, c->b_T.p, 16 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaMemcpyAsync(&hs->res, c->b_res.p, sizeof(icp4r_result), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            if (T_out) std::memcpy(T_out, hs->T, sizeof(hs->T));
+            if (res) *res = hs->res;
+            return ICP4R_OK;
+        }
+    }
     // transient index over the target, rebuilt per call like PCL's setInputTarget kd-tree
     Map& mp = c->tmp;
     mp.m = 0;

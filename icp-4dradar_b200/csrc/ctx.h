@@ -272,6 +272,7 @@ int register_scans_against_map(Ctx* c, Map& mp, const float4* d_src, const int32
                                const double* T0s_host, double* T_out_host, icp4r_result* res_host);
 
 // register_batch.cu
+bool register_batch_fits(int max_n, int max_m);  // does a pair of these sizes fit the shared-memory resident kernel?
 int register_batch(Ctx* c, const float4* d_src, const int32_t* d_soff, const float4* d_tgt, const int32_t* d_toff,
                    int n_pairs, int max_n, int max_m, const icp4r_opts* o, double* d_T, icp4r_result* d_res);
 
