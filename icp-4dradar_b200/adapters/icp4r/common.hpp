@@ -36,11 +36,16 @@ inline std::vector<float> pack_xyzw(It first, It last) {
     return out;
 }
 
-// One process-wide handle per device for objects that the reference constructs per frame on the stack
-// (pcl::IterativeClosestPoint at iterative_closest_point.cpp:510, FastGICP at radar_odometry.cpp:399):
-// creating a CUDA stream and buffers per frame would be wasted work.
+// One handle per THREAD and device for objects that the reference constructs per frame on the stack
+// (pcl::IterativeClosestPoint at iterative_closest_point.cpp:510, FastGICP at radar_odometry.cpp:399): creating a CUDA
+// stream and buffers per frame would be wasted work. An icp4r handle is stateful (staging buffers, transient target map,
+// error text, captured launch graphs) and serves one caller thread at a time (include/icp4r.h), so the shared one is
+// thread_local: registration objects used from different threads (a ROS callback thread and a processing thread) get
+// different handles and are as independent as the reference's objects; objects of one thread share one.
+// The handles live until the thread ends (they are deliberately not destroyed during static destruction, when the CUDA
+// runtime may already be gone).
 inline icp4r_handle shared_handle(int device = 0) {
-    static icp4r_handle h[16] = {nullptr};
+    static thread_local icp4r_handle h[16] = {nullptr};
     if (device < 0 || device >= 16) throw std::runtime_error("icp4r: bad device");
     if (!h[device]) {
         if (icp4r_create(device, &h[device]) != ICP4R_OK)

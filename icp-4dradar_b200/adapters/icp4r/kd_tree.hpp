@@ -8,6 +8,10 @@
 //
 // Differences a caller can observe:
 //   * exact ties in distance go to the lowest insertion index (the reference: traversal order);
+//   * Nearest_Search ranks at most ICP4R_MAX_K (16) neighbours per query: a larger k_nearest is clamped to 16
+//     (the reference accepts any k; its call sites use 5);
+//   * failures of the CUDA runtime surface as std::runtime_error (the reference never throws from these calls);
+//     a query before Build returns empty vectors like the reference does;
 //   * Nearest_Search is also offered for a whole batch of queries (one launch instead of N calls).
 #pragma once
 #include <cmath>
@@ -83,13 +87,18 @@ class KD_TREE {
                         double max_dist = INFINITY) {
         PointVector().swap(Nearest_Points);
         std::vector<float>().swap(Point_Distance);
-        if (k_nearest <= 0) return;
+        if (k_nearest <= 0 || mirror_.empty()) return;  // before Build: empty result, like the reference (ikd_Tree.cpp:370-371)
+        // the reference accepts any k; the library ranks up to ICP4R_MAX_K per query: larger requests are clamped (a radar
+        // map query for more than 16 neighbours does not occur in the reference, radar_odometry.cpp uses 5)
+        const int k = k_nearest < ICP4R_MAX_K ? k_nearest : ICP4R_MAX_K;
+        // max_dist: +inf = ungated. The library encodes "ungated" as <= 0, the reference treats 0 as "exact hits only"
+        // (dist <= 0): map it to the smallest positive gate so that only exact hits pass
+        const double gate = std::isinf(max_dist) ? 0.0 : (max_dist > 0.0 ? max_dist : 1e-30);
         const float q[4] = {point.x, point.y, point.z, 0.f};
-        std::vector<int32_t> idx(k_nearest);
-        std::vector<float> d2(k_nearest);
+        std::vector<int32_t> idx(k);
+        std::vector<float> d2(k);
         int32_t found = 0;
-        check(h_, icp4r_map_knn(h_, q, 1, ICP4R_HOST, k_nearest, std::isinf(max_dist) ? 0.0 : max_dist, idx.data(), d2.data(), &found),
-              "Nearest_Search");
+        check(h_, icp4r_map_knn(h_, q, 1, ICP4R_HOST, k, gate, idx.data(), d2.data(), &found), "Nearest_Search");
         for (int i = 0; i < found; ++i) {  // ascending, like ikd_Tree.cpp:392-396
             Nearest_Points.push_back(mirror_[idx[i]]);
             Point_Distance.push_back(d2[i]);

@@ -34,14 +34,29 @@ __global__ void __launch_bounds__(256) bbox_kernel(const float4* __restrict__ pt
                                                    int* __restrict__ bb) {
     float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
     int cnt = 0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
-        if (!valid[i]) continue;
-        const float4 p = pts[i];
-        if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) continue;
-        mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x);
-        mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
-        mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z);
-        ++cnt;
+    const int stride = gridDim.x * blockDim.x;
+    // four independent loads in flight per thread (one dependent load per trip left the kernel at a fifth of the HBM rate)
+    for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < m; i0 += 4 * stride) {
+        float4 p[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * stride;
+            ok[u] = i < m;
+            if (ok[u]) {
+                p[u] = pts[i];
+                ok[u] = valid[i] != 0;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (ok[u] && isfinite(p[u].x) && isfinite(p[u].y) && isfinite(p[u].z)) {
+                mn[0] = fminf(mn[0], p[u].x); mx[0] = fmaxf(mx[0], p[u].x);
+                mn[1] = fminf(mn[1], p[u].y); mx[1] = fmaxf(mx[1], p[u].y);
+                mn[2] = fminf(mn[2], p[u].z); mx[2] = fmaxf(mx[2], p[u].z);
+                ++cnt;
+            }
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -133,6 +148,207 @@ static int build_coarse(Ctx* c, Map& mp, GridDesc& g) {
     coarse_count_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, c->stream>>>(mp.cell_start.as<uint32_t>(), g, mp.coarse.as<uint32_t>());
     c->launches += 1;
     g.coarse = mp.coarse.as<uint32_t>();
+    return ICP4R_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ bucket build
+// Large maps: instead of an LSB radix sort of (key, index) pairs (3-4 passes of 20 B per point and pass, then a random
+// 16-byte gather per point) the points themselves are moved twice:
+//   1. scatter (x, y, z, index) into the fixed-capacity slot range of the point's BUCKET = 2^S consecutive cell keys
+//      (one returning atomic per point on a few thousand cursors; arrival order), then scan the bucket counts;
+//   2. one block per bucket loads its ~0.8 k points into shared memory, counting-sorts them by cell, orders every
+//      cell's points by index (the order the stable radix sort would give: the result is bit-identical), writes them
+//      out coalesced and fills the bucket's slice of the cell table — no binary search, no gather.
+// 80 B of traffic per point instead of ~125 B, none of it a per-point random read. Falls back to the radix path when a
+// bucket would not fit shared memory (strongly non-uniform maps).
+constexpr int BK_THREADS = 256;
+constexpr int BK_CAP = 2048;      // slots per bucket (scratch array and the sorting block's shared memory)
+constexpr int BK_MAX_S = 12;      // at most 4096 cell keys per bucket
+
+__device__ __forceinline__ uint32_t key_of_point(const GridDesc& g, const float4& p) {
+    const int cx = cell_of(p.x, g.ox, g.inv_cell, g.nx);
+    const int cy = cell_of(p.y, g.oy, g.inv_cell, g.ny);
+    const int cz = cell_of(p.z, g.oz, g.inv_cell, g.nz);
+    return (uint32_t)(cz * g.ny + cy) * (uint32_t)g.nx + (uint32_t)cx;
+}
+
+// one block: exclusive scan of the bucket counts (base[nb] = total), cursors zeroed, info = {largest bucket}
+__global__ void __launch_bounds__(1024) bk_scan_kernel(const uint32_t* __restrict__ cnt, int nb, uint32_t* __restrict__ base,
+                                                       uint32_t* __restrict__ info) {
+    __shared__ uint32_t wsum[32];
+    __shared__ uint32_t carry_s, max_s;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid == 0) carry_s = 0, max_s = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < nb; b0 += 1024) {
+        const int i = b0 + tid;
+        const uint32_t v = i < nb ? cnt[i] : 0u;
+        uint32_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(FULL, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) wsum[w] = x;
+        const uint32_t vmax = __reduce_max_sync(FULL, v);
+        if (lane == 0) atomicMax(&max_s, vmax);
+        __syncthreads();
+        uint32_t woff = 0;
+        for (int j = 0; j < w; ++j) woff += wsum[j];
+        const uint32_t carry = carry_s;
+        if (i < nb) base[i] = carry + woff + x - v;
+        __syncthreads();
+        if (tid == 1023) carry_s = carry + woff + x;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        base[nb] = carry_s;
+        info[0] = max_s;
+    }
+}
+
+__global__ void __launch_bounds__(256) bk_scatter_kernel(const float4* __restrict__ pts, const uint8_t* __restrict__ valid, int m, GridDesc g,
+                                                         int S, uint32_t* __restrict__ cursor, float4* __restrict__ tmp) {
+    const int stride = gridDim.x * blockDim.x;
+    for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < m; i0 += 4 * stride) {
+        float4 p[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * stride;
+            ok[u] = i < m;
+            if (ok[u]) {
+                p[u] = pts[i];
+                ok[u] = valid[i] != 0;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (ok[u] && isfinite(p[u].x) && isfinite(p[u].y) && isfinite(p[u].z)) {
+                const uint32_t b = key_of_point(g, p[u]) >> S;
+                const uint32_t slot = atomicAdd(cursor + b, 1u);  // a bucket that overflows is detected by the scan: radix path
+                if (slot < (uint32_t)BK_CAP)
+                    tmp[(size_t)b * BK_CAP + slot] = make_float4(p[u].x, p[u].y, p[u].z, __uint_as_float((uint32_t)(i0 + u * stride)));
+            }
+    }
+}
+
+// block b sorts bucket b: keys [b << S, (b + 1) << S)
+__global__ void __launch_bounds__(BK_THREADS) bk_sort_kernel(const float4* __restrict__ tmp, const uint32_t* __restrict__ base, GridDesc g, int S,
+                                                            float4* __restrict__ sorted, uint32_t* __restrict__ cell_start) {
+    extern __shared__ __align__(16) unsigned char bk_smem[];
+    float4* s_pts = reinterpret_cast<float4*>(bk_smem);                        // [BK_CAP]
+    unsigned short* s_fk = reinterpret_cast<unsigned short*>(s_pts + BK_CAP);  // [BK_CAP] cell of a point, relative to the bucket
+    unsigned short* s_perm = s_fk + BK_CAP;                                    // [BK_CAP] point at a sorted slot
+    uint32_t* s_start = reinterpret_cast<uint32_t*>(s_perm + BK_CAP);          // [2^S + 1]
+    uint32_t* s_cur = s_start + ((1 << S) + 1);                                // [2^S]
+    __shared__ uint32_t wsum[BK_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const uint32_t b = blockIdx.x;
+    const uint32_t off = base[b], nbk = base[b + 1] - off;
+    const int ncell = 1 << S;
+    for (int c = tid; c <= ncell; c += BK_THREADS) s_start[c] = 0;
+    for (int c = tid; c < ncell; c += BK_THREADS) s_cur[c] = 0;
+    __syncthreads();
+    for (uint32_t j = tid; j < nbk; j += BK_THREADS) {
+        const float4 p = tmp[(size_t)b * BK_CAP + j];
+        s_pts[j] = p;
+        const uint32_t fk = key_of_point(g, p) - (b << S);
+        s_fk[j] = (unsigned short)fk;
+        atomicAdd(&s_start[fk + 1], 1u);
+    }
+    __syncthreads();
+    {   // s_start[c + 1] <- inclusive prefix of the counts, i.e. s_start[c] = first slot of cell c
+        const int per = (ncell + BK_THREADS - 1) / BK_THREADS;
+        uint32_t sum = 0;
+        for (int t = 0; t < per; ++t) {
+            const int c = tid * per + t;
+            if (c < ncell) sum += s_start[c + 1];
+        }
+        uint32_t x = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(FULL, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) wsum[w] = x;
+        __syncthreads();
+        uint32_t run = x - sum;
+        for (int j = 0; j < w; ++j) run += wsum[j];
+        for (int t = 0; t < per; ++t) {
+            const int c = tid * per + t;
+            if (c < ncell) {
+                run += s_start[c + 1];
+                s_start[c + 1] = run;
+            }
+        }
+    }
+    __syncthreads();
+    for (uint32_t j = tid; j < nbk; j += BK_THREADS) {
+        const uint32_t fk = s_fk[j];
+        s_perm[s_start[fk] + atomicAdd(&s_cur[fk], 1u)] = (unsigned short)j;
+    }
+    __syncthreads();
+    // ascending index inside every cell (what the stable sort of the radix path produces): insertion sort, cells are small
+    for (int c = tid; c < ncell; c += BK_THREADS) {
+        const uint32_t s0 = s_start[c], e0 = s_start[c + 1];
+        for (uint32_t a = s0 + 1; a < e0; ++a) {
+            const unsigned short pj = s_perm[a];
+            const uint32_t idx = __float_as_uint(s_pts[pj].w);
+            uint32_t q = a;
+            while (q > s0 && __float_as_uint(s_pts[s_perm[q - 1]].w) > idx) {
+                s_perm[q] = s_perm[q - 1];
+                --q;
+            }
+            s_perm[q] = pj;
+        }
+    }
+    __syncthreads();
+    for (uint32_t j = tid; j < nbk; j += BK_THREADS) sorted[off + j] = s_pts[s_perm[j]];
+    for (int c = tid; c < ncell; c += BK_THREADS) {
+        const uint32_t key = (b << S) + (uint32_t)c;
+        if (key <= (uint32_t)g.ncells) cell_start[key] = off + s_start[c];
+    }
+}
+
+// *built = true if the grid (sorted points + cell table) was built, false if the caller must take the radix path
+static int bucket_build(Ctx* c, Map& mp, const GridDesc& g, int m, int nvalid, bool* built) {
+    *built = false;
+    const char* e = std::getenv("ICP4R_BUCKET_MIN");
+    const int min_pts = e ? std::atoi(e) : 262144;
+    if (nvalid < min_pts || min_pts < 0) return ICP4R_OK;
+    // about 0.8 k points per bucket by volume (slots: BK_CAP)
+    const double ppc = (double)nvalid / std::max(g.ncells, 1);
+    int S = (int)std::lround(std::log2(std::max(800.0 / std::max(ppc, 1e-9), 1.0)));
+    S = std::min(std::max(S, 2), BK_MAX_S);
+    const long long nb_ll = ((long long)g.ncells + 1 + (1ll << S) - 1) >> S;
+    if (nb_ll * BK_CAP > 4ll * std::max(m, 1) + (1 << 20)) return ICP4R_OK;  // mostly empty buckets (surfaces in a big volume): not worth the scratch
+    const int nb = (int)nb_ll;
+    CKS(reserve(c, c->d_scratch, ((size_t)2 * nb + 16) * sizeof(uint32_t)));
+    uint32_t* cursor = c->d_scratch.as<uint32_t>();   // [nb] points per bucket
+    uint32_t* base = cursor + nb;                     // [nb + 1]
+    uint32_t* info = base + nb + 1;                   // [1]
+    CKS(reserve_grow(c, mp.sorted_alt, (size_t)nb * BK_CAP * sizeof(float4)));
+    CK(cudaMemsetAsync(cursor, 0, (size_t)nb * sizeof(uint32_t), c->stream));
+    const int blocks = std::min((m + 1023) / 1024, c->sm_count * 8);
+    bk_scatter_kernel<<<blocks, 256, 0, c->stream>>>(mp.pts.as<float4>(), mp.valid.as<uint8_t>(), m, g, S, cursor, mp.sorted_alt.as<float4>());
+    bk_scan_kernel<<<1, 1024, 0, c->stream>>>(cursor, nb, base, info);
+    c->launches += 2;
+    uint32_t h_max = 0;
+    CK(cudaMemcpyAsync(&h_max, info, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (h_max > (uint32_t)BK_CAP) return ICP4R_OK;
+    const size_t smem = (size_t)BK_CAP * (sizeof(float4) + 2 * sizeof(unsigned short)) + ((size_t)2 * (1 << S) + 1) * sizeof(uint32_t);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CK(cudaFuncSetAttribute(bk_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)((size_t)BK_CAP * (sizeof(float4) + 2 * sizeof(unsigned short)) + ((size_t)2 * (1 << BK_MAX_S) + 1) * sizeof(uint32_t))));
+        attr_set = true;
+    }
+    bk_sort_kernel<<<nb, BK_THREADS, smem, c->stream>>>(mp.sorted_alt.as<float4>(), base, g, S, mp.sorted.as<float4>(), mp.cell_start.as<uint32_t>());
+    c->launches += 1;
+    CK(cudaGetLastError());
+    *built = true;
     return ICP4R_OK;
 }
 
@@ -292,20 +508,26 @@ int map_rebuild_grid(Ctx* c, Map& mp) {
         CKS(reserve_grow(c, mp.sorted, (size_t)std::max(m, 1) * sizeof(float4)));
         CKS(reserve_grow(c, mp.cell_start, ((size_t)g.ncells + 2) * sizeof(uint32_t)));
         tr.mark("reserve");
-        key_kernel<<<(m + 255) / 256, 256, 0, c->stream>>>(mp.pts.as<float4>(), mp.valid.as<uint8_t>(), m, g,
-                                                             mp.keys_a.as<uint32_t>(), mp.vals_a.as<uint32_t>());
-        c->launches += 1;
-        tr.mark("keys");
-        int bits = 1;
-        while ((1ll << bits) <= (long long)g.ncells) ++bits;  // key == ncells must be representable
-        uint32_t *ks, *vs;
-        CKS(radix_sort_pairs(c, mp.keys_a.as<uint32_t>(), mp.keys_b.as<uint32_t>(), mp.vals_a.as<uint32_t>(),
-                             mp.vals_b.as<uint32_t>(), m, bits, c->d_scratch, &ks, &vs));
-        tr.mark("radix sort");
-        // 4. cell table by binary search over the sorted keys
-        cell_start_kernel<<<(g.ncells + 1 + 255) / 256, 256, 0, c->stream>>>(ks, m, g.ncells, mp.cell_start.as<uint32_t>());
-        c->launches += 1;
-        tr.mark("cell table");
+        uint32_t *ks = nullptr, *vs = nullptr;
+        bool bucketed = false;
+        CKS(bucket_build(c, mp, g, m, nvalid, &bucketed));  // large maps: two moves of the points, no radix sort
+        if (bucketed) {
+            tr.mark("bucket build");
+        } else {
+            key_kernel<<<(m + 255) / 256, 256, 0, c->stream>>>(mp.pts.as<float4>(), mp.valid.as<uint8_t>(), m, g,
+                                                                 mp.keys_a.as<uint32_t>(), mp.vals_a.as<uint32_t>());
+            c->launches += 1;
+            tr.mark("keys");
+            int bits = 1;
+            while ((1ll << bits) <= (long long)g.ncells) ++bits;  // key == ncells must be representable
+            CKS(radix_sort_pairs(c, mp.keys_a.as<uint32_t>(), mp.keys_b.as<uint32_t>(), mp.vals_a.as<uint32_t>(),
+                                 mp.vals_b.as<uint32_t>(), m, bits, c->d_scratch, &ks, &vs));
+            tr.mark("radix sort");
+            // 4. cell table by binary search over the sorted keys
+            cell_start_kernel<<<(g.ncells + 1 + 255) / 256, 256, 0, c->stream>>>(ks, m, g.ncells, mp.cell_start.as<uint32_t>());
+            c->launches += 1;
+            tr.mark("cell table");
+        }
         bool again = false;
         if (!(mp.user_cell > 0.f) && !mp.quick_build && pass < 2 && nvalid >= 64) {
             int* d_occ = c->d_scratch.as<int>();
@@ -331,7 +553,7 @@ int map_rebuild_grid(Ctx* c, Map& mp) {
         }
         if (again) continue;
         // 5. points into sorted order (valid ones come first)
-        if (nvalid > 0) {
+        if (nvalid > 0 && !bucketed) {
             gather_kernel<<<(nvalid + 255) / 256, 256, 0, c->stream>>>(mp.pts.as<float4>(), vs, nvalid, mp.sorted.as<float4>());
             c->launches += 1;
         }

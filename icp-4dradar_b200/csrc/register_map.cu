@@ -173,6 +173,10 @@ __global__ void __launch_bounds__(RM_THREADS, RM_BLOCKS_PER_SM)
     partials += (size_t)blockIdx.y * gridDim.x * ICP4R_ACC_LEN;
     out += blockIdx.y;
     if (!FIT && st->done) return;
+    if (FIT && st->xch_timeout) {  // a sharded loop that lost a peer: nothing to measure, hand the flag to the host
+        if (MODE == MODE_FITNESS && blockIdx.x == 0 && threadIdx.x == 0) write_result(st, out);
+        return;
+    }
 
     __shared__ WarpSegs segs[RM_WARPS];
     __shared__ double scr[RM_WARPS][3][12];  // per-warp operands of the lane products (up to 3 residual rows)
@@ -830,11 +834,23 @@ __global__ void __launch_bounds__(RM_THREADS, RM_BLOCKS_PER_SM)
                 }
                 sum += __longlong_as_double((long long)((a & 0xFFFFFFFFull) | (b << 32)));
             }
-            if (late) st->xch_timeout = 1;
+            // a peer that never published: the sums are incomplete. Stop the loop right here — no solve on garbage, the
+            // remaining iteration launches and the fitness pass become no-ops instead of spinning 10 s each — and report
+            late = __any_sync(FULL, late);
+            if (late && lane == 0) {
+                st->xch_timeout = 1;
+                st->done = 1;
+                st->converged = 0;
+                st->iterations = iter;
+            }
             tot[lane] = sum;
             if (lane == 0) mine->seq = epoch;
         }
         __syncthreads();
+        if (*reinterpret_cast<volatile int*>(&st->xch_timeout)) {
+            if (MODE == MODE_FITNESS && tid == 0) write_result(st, out);
+            return;
+        }
     }
     if (FIT) {
         if (tid == 0) {
@@ -1191,21 +1207,25 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
             // cannot be captured); the instantiated graph is then launched on c->stream
             cudaStream_t run_stream = c->stream;
             c->stream = c->own_stream;
-            CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-            const int64_t before = c->launches;
-            enqueue_loop(it0, it1, fit);
-            c->graph_launches = c->launches - before;
-            c->launches = before;  // counted at replay time below
-            cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
-            c->stream = run_stream;
+            cudaError_t ce = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
+            if (ce == cudaSuccess) {
+                const int64_t before = c->launches;
+                enqueue_loop(it0, it1, fit);
+                c->graph_launches = c->launches - before;
+                c->launches = before;  // counted at replay time below
+                ce = cudaStreamEndCapture(c->stream, &graph);
+            }
+            c->stream = run_stream;  // restored on every path: later calls must stay ordered on the caller's stream
             if (ce == cudaSuccess && enqueue_status == ICP4R_OK) ce = cudaGraphInstantiate(&exec, graph, 0);
             if (graph) cudaGraphDestroy(graph);
             if (ce != cudaSuccess || enqueue_status != ICP4R_OK) {
+                // capture is an optimisation: whatever went wrong (an NCCL build that cannot be captured, a stream in a
+                // state that refuses capture), the loop still runs as direct launches below
                 cudaGetLastError();
                 exec = nullptr;
                 enqueue_status = ICP4R_OK;
-                if (sharded) c->no_graph_sharded = true;  // this NCCL build can not be captured: launch directly from now on
-                else return fail(c, ICP4R_ERR_CUDA, "graph capture of the registration loop failed: %s", cudaGetErrorString(ce));
+                if (sharded) c->no_graph_sharded = true;
+                else c->use_graph = false;
             } else {
                 c->graphs[key] = exec;
                 c->graph_launch_counts[key] = c->graph_launches;
@@ -1442,18 +1462,25 @@ int register_scans_against_map(Ctx* c, Map& mp, const float4* d_src, const int32
                 cudaGraph_t graph = nullptr;
                 cudaStream_t run_stream = c->stream;
                 c->stream = c->own_stream;
-                CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-                const int64_t before = c->launches;
-                enqueue();
-                c->graph_launches = c->launches - before;
-                c->launches = before;
-                cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
-                c->stream = run_stream;
-                CK(ce);
-                CK(cudaGraphInstantiate(&exec, graph, 0));
-                cudaGraphDestroy(graph);
-                c->graphs[key] = exec;
-                c->graph_launch_counts[key] = c->graph_launches;
+                cudaError_t ce = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
+                if (ce == cudaSuccess) {
+                    const int64_t before = c->launches;
+                    enqueue();
+                    c->graph_launches = c->launches - before;
+                    c->launches = before;
+                    ce = cudaStreamEndCapture(c->stream, &graph);
+                }
+                c->stream = run_stream;  // restored on every path
+                if (ce == cudaSuccess) ce = cudaGraphInstantiate(&exec, graph, 0);
+                if (graph) cudaGraphDestroy(graph);
+                if (ce != cudaSuccess) {  // capture is an optimisation: run the loop as direct launches instead
+                    cudaGetLastError();
+                    exec = nullptr;
+                    c->use_graph = false;
+                } else {
+                    c->graphs[key] = exec;
+                    c->graph_launch_counts[key] = c->graph_launches;
+                }
             }
         }
         if (exec) {

@@ -77,6 +77,10 @@ void shard_destroy(Ctx* c) {
 // ---- peer-memory flavour: exchange buffers mapped across processes with CUDA IPC ------------------------------------
 int shard_ipc_export(Ctx* c, unsigned char out[64]) {
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+    // the exchange counts its rounds on every rank (Xch.seq); exporting again would zero this rank's count while the
+    // peers keep theirs and every later exchange would time out: one export per handle
+    if (c->d_xch.p != nullptr)
+        return fail(c, ICP4R_ERR_STATE, "icp4r_shard_ipc_export was already called on this handle (create a new handle to re-join)");
     CKS(reserve(c, c->d_xch, sizeof(Xch)));
     CK(cudaMemsetAsync(c->d_xch.p, 0, sizeof(Xch), c->stream));
     CK(cudaStreamSynchronize(c->stream));

@@ -14,7 +14,10 @@
  * Conventions
  *   - every function returns an icp4r_status (0 = ok); nothing throws or calls back across the boundary;
  *     icp4r_last_error(h) describes the last failure on that handle.
- *   - one handle = one CUDA device + one stream + one caller thread at a time; handles are independent.
+ *   - one handle = one CUDA device + one stream + one caller thread at a time: a handle is stateful (staging buffers,
+ *     the transient target of icp4r_register, the error text, captured launch graphs) and is NOT thread-safe; calls on
+ *     one handle from several threads must be serialised by the caller. Distinct handles are independent and may be used
+ *     concurrently (that is how multi-GPU batches run; the C++ adapters keep one handle per thread).
  *   - points are packed float rows  x, y, z, w  (w = intensity, carried not used); `mem` says whether the
  *     caller's pointers (inputs AND outputs of that call) are host (ICP4R_HOST) or device (ICP4R_DEVICE).
  *   - poses are row-major double[16]; the update convention is the left perturbation T <- exp(xi^) T with
