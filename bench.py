@@ -2,7 +2,7 @@
 """bench.py — registrations/s and NN queries/s of the registration hot path on B200, with the reference's
 CPU path timed beside it.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload all|c1|c2|c2single|c3|c4|c5|gicp]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload all|c1|c2|c2single|c3|c3ref|c4|c5|gicp]
 
 Default (`--workload all`): the headline line is BASELINE.json configs[3] ("C4", the config the metric "at 1/2/4/8
 B200" is quoted on and that fits one GPU): ONE fixed job of 65,536 independent frame pairs (2,048 + 2,048 points,
@@ -13,7 +13,9 @@ point-to-point ICP, 30 iterations, ungated) split by pair range across the ranks
           chunked on a second stream ahead of the kernels), the registrations, device->host copy of poses/results
 At N = 1 the same JSON line carries `configs`: one sub-record per other BASELINE config — c1 (single 1,024-pt pair),
 c2_single / c2_batch16 (4,096-pt scan vs resident 200 k-pt map, one scan per call / 16 scans per call), c3 (2,000-frame
-odometry sequence), c5 (16,384-pt scan vs 20 M-pt map) and gicp — each with value, e2e, roofline and cpu_baseline.
+odometry sequence: register + transform + Add_Points per frame), c3ref (the scan-to-map node's own per-frame flow from raw
+radar frames: Doppler filter, Add_Points, Sector_Search, GICP against the sub-map, VoxelGrid), c5 (16,384-pt scan vs
+20 M-pt map) and gicp — each with value, e2e, roofline and cpu_baseline.
 At N > 1 `configs` carries c5 sharded in N x-slabs with the cross-rank sum inside the iteration kernel over NVLink
 peer memory (`--exchange nccl` for the NCCL all-reduce flavour).
 `--workload <one>` makes that config the headline line instead (c2: N > 1 = replicas, weak scaling).
@@ -283,19 +285,24 @@ def cpu_pairs(src, tgt, n_pts, iters, budget_s, threads, max_pairs=1 << 30):
     return ("reference" if use_ref else "port"), done, time.perf_counter() - t0
 
 
-def cpu_c3(seq, budget_s, threads):
-    """the odometry loop on the host: ikd-Tree Build, then per frame register (Nearest_Search on all threads + the
-    Gauss-Newton loop), transform, Add_Points(.., false). Every frame is timed until a quarter of the budget is gone, then
-    every stride-th frame — with the frames in between inserted untimed at the last estimated pose — so that the sample
-    spreads over the whole sequence with the tree grown to each timed frame's size instead of stopping while it is small.
-    Returns (kind, frames timed, seconds timed, last frame reached)."""
+def cpu_c3(raw, budget_s, threads, seed=1):
+    """the odometry loop on the host from raw radar frames: per frame the Doppler filter, then register against the
+    ikd-Tree map (Nearest_Search on all threads + the Gauss-Newton loop), transform, Add_Points(.., false). Every frame is
+    timed until a quarter of the budget is gone, then every stride-th frame — with the frames in between inserted untimed
+    at the last estimated pose — so that the sample spreads over the whole sequence with the tree grown to each timed
+    frame's size instead of stopping while it is small. Returns (kind, frames timed, seconds timed, last frame reached)."""
     import oracle as O
     oo = O.default_opts(residual=O.P2PLANE_KNN, k=K_NN, max_iterations=ITERS, max_corr_dist=GATE)
     use_ref = O.have_ref()
-    buf = np.empty((int(sum(len(s) for s in seq)), 4), np.float32)   # the map in insertion order (neighbour indices refer to it)
+    buf = np.empty((int(sum(len(s) for s in raw)), 4), np.float32)   # the map in insertion order (neighbour indices refer to it)
+
+    def static_of(f):
+        mask, _ = O.doppler_filter(raw[f], 0, seed + f)
+        return np.ascontiguousarray(raw[f][mask.astype(bool)][:, :4])
+
     with quiet_c_stdout():
         T = np.eye(4)
-        w0, _ = O.transform(T, seq[0])
+        w0, _ = O.transform(T, static_of(0))
         n = len(w0)
         buf[:n] = w0
         tree = None
@@ -304,9 +311,10 @@ def cpu_c3(seq, budget_s, threads):
             tree.build(w0)
         t0 = time.perf_counter()
         timed_s, cnt, stride, f = 0.0, 0, 1, 0
-        for f, scan in enumerate(seq[1:], 1):
+        for f in range(1, len(raw)):
             if f % stride == 0:
                 ta = time.perf_counter()
+                scan = static_of(f)
                 for i in range(16):
                     oo.T0[i] = float(T.reshape(16)[i])
                 T, _r, _ = O.register(scan, buf[:n], oo, searcher=tree)
@@ -316,14 +324,14 @@ def cpu_c3(seq, budget_s, threads):
                 timed_s += time.perf_counter() - ta
                 cnt += 1
             else:
-                wv, _ = O.transform(T, scan)
+                wv, _ = O.transform(T, static_of(f))
                 if tree is not None:
                     tree.add_points(wv, False)
             buf[n:n + len(wv)] = wv
             n += len(wv)
             el = time.perf_counter() - t0
             if stride == 1 and el > budget_s * 0.25:
-                left = len(seq) - 1 - f
+                left = len(raw) - 1 - f
                 per = timed_s / max(cnt, 1)
                 stride = max(1, int(np.ceil(left * per / max(budget_s * 0.6, 1e-3))))
             if el > budget_s * 1.5:
@@ -331,6 +339,56 @@ def cpu_c3(seq, budget_s, threads):
         if tree is not None:
             tree.close()
     return ("reference" if use_ref else "port"), cnt, timed_s, f
+
+
+def cpu_c3ref(frames, poses, budget_s, threads, radius=80.0, leaf=0.5, seed=1):
+    """the node's own per-frame flow on the host (Doppler filter, transform, ikd-Tree Add_Points, Sector_Search, GICP with
+    the reference's ikd-Tree for the searches, voxel grid over the whole map), timed on a few frames spread over the
+    sequence; every frame is placed with the same prior poses as in the GPU arm, the frames in between untimed, so that the tree and the map
+    have the right size at every timed frame. Returns (kind, frames timed, seconds, list of timed frame numbers)."""
+    import oracle as O
+    oo = O.default_opts(residual=O.GICP, k=K_NN, max_iterations=64, early_exit=1, max_corr_dist=0.0)
+    use_ref = O.have_ref()
+    total = sum(len(f) for f in frames)
+    buf = np.empty((total, 4), np.float32)
+    n = 0
+    nf = len(frames)
+    picks = sorted(set(int(round(x)) for x in np.linspace(nf * 0.1, nf - 1, 6)))
+    timed_s, done, t_all = 0.0, [], time.perf_counter()
+    with quiet_c_stdout():
+        tree = O.IkdTree(nthreads=threads) if use_ref else None
+        om = O.OracleMap(total) if tree is None else None
+        for f, rec in enumerate(frames):
+            T = np.asarray(poses[f])   # the prior pose the node places the scan with
+            timed = f in picks and (time.perf_counter() - t_all) < budget_s
+            t0 = time.perf_counter()
+            mask, _ = O.doppler_filter(rec, 0, seed + f)
+            static = np.ascontiguousarray(rec[mask.astype(bool)][:, :4])
+            scan_w, _ = O.transform(T, static)
+            buf[n:n + len(scan_w)] = scan_w
+            if f == 0:
+                tree.build(scan_w) if tree is not None else om.add_points(scan_w, False)
+                n += len(scan_w)
+                continue
+            tree.add_points(scan_w, False) if tree is not None else om.add_points(scan_w, False)
+            n += len(scan_w)
+            if timed:
+                yaw = float(np.degrees(np.arctan2(T[1, 0], T[0, 0])))
+                idx = tree.sector(T[:3, 3], radius, yaw) if tree is not None else om.sector(T[:3, 3], radius, yaw)
+                sub = np.ascontiguousarray(buf[idx])
+                s2 = None
+                if use_ref:   # fast_gicp builds a kd-tree over the sub-map on every setInputTarget
+                    s2 = O.IkdTree(nthreads=threads)
+                    s2.build(sub)
+                O.gicp_register(scan_w, sub, oo, searcher=s2)
+                if s2 is not None:
+                    s2.close()
+                O.voxel_grid(buf[:n], leaf)
+                timed_s += time.perf_counter() - t0
+                done.append(f)
+        if tree is not None:
+            tree.close()
+    return ("reference" if use_ref else "port"), len(done), timed_s, done
 
 
 def run_reference(args, rank, world):
@@ -671,37 +729,89 @@ class Bench:
     def run_c3(self, steps, warmup, main=False):
         torch, pkg, h = self.torch, self.pkg, self.h
         frames = self.args.frames
-        seq, _gt = pkg.pipeline.synth_sequence(1003 + self.rank, frames)
+        raw, _gt = pkg.pipeline.synth_radar_sequence(1003 + self.rank, frames, pts_per_frame=4000, extent=400.0, scan_radius=60.0)
         o = pkg.default_opts(residual=pkg.P2PLANE_KNN, k=K_NN, max_iterations=ITERS, max_corr_dist=GATE)
-        d_seq = [torch.from_numpy(s).to(self.dev) for s in seq]
-        pin_seq = [torch.from_numpy(s).pin_memory() for s in seq]
-        h_seq = [p.numpy() for p in pin_seq]
-        step_dev = lambda i: pkg.pipeline.run_odometry(h, d_seq, o)
-        step_e2e = lambda i: pkg.pipeline.run_odometry(h, h_seq, o)
+        d_raw = [torch.from_numpy(f).to(self.dev) for f in raw]
+        pin = [torch.from_numpy(f).pin_memory() for f in raw]
+        step_dev = lambda i: pkg.pipeline.run_odometry_raw(h, d_raw, o)
+        step_e2e = lambda i: pkg.pipeline.run_odometry_raw(h, pin, o, on_device=lambda r: r.to(self.dev, non_blocking=True))
         m = self.measure(step_dev, step_e2e, steps, warmup, frames, sample_clocks=main)
-        npts = int(sum(len(s) for s in seq))
-        rec = self.record(m, ITERS * int(np.mean([len(s) for s in seq])), npts * 16, frames * (16 * 8 + 32),
-                          {"workload": f"C3 odometry sequence: {frames} frames (~3000 static pts each), per frame register vs the growing map (P2PLANE k=5, "
-                                       "20 iters, gate 2.0 m) + transform + Add_Points(false), one icp4r_odometry_step call per frame; one step = the whole sequence",
-                           "frames": frames, "k": K_NN, "iterations": ITERS, "max_corr_dist": GATE, "final_map_points": npts,
+        npts, _ = h.map_size()
+        n_static = npts / frames
+        rec = self.record(m, ITERS * int(n_static), int(sum(len(f) for f in raw)) * 20, frames * (16 * 8 + 32),
+                          {"workload": f"C3 odometry sequence: {frames} raw radar frames of 4000 records; per frame the Doppler static-point filter (~{int(n_static)} static "
+                                       "points), then register vs the growing map (P2PLANE k=5, 20 iters, gate 2.0 m) + transform + Add_Points(false) "
+                                       "(icp4r_doppler_static_points + icp4r_odometry_step); one step = the whole sequence",
+                           "frames": frames, "k": K_NN, "iterations": ITERS, "max_corr_dist": GATE, "final_map_points": int(npts),
                            "l2": "flushed before every timed step; the map outgrows L2 during the sequence"})
         rec["_m"] = m
         rec["unit_note"] = "registrations/s = frames/s (one registration per frame)"
+        rec["ms_per_frame"] = m["ms_per_step"] / frames
         # dominant kernel: the iteration kernel against the FINAL map (state left behind by the last timed sequence)
-        last = d_seq[-1]
+        last, _ = h.doppler_static_points(d_raw[-1], 0, seed=1 + frames - 1)
         k_ms = self.iter_kernel_ms(lambda i: h.register_map(last, o))
-        mpts = h.map_points_dev() if hasattr(h, "map_points_dev") else None
-        m_r = self.m_r(mpts, npts, seq[-1]) if mpts is not None else None
+        mpts = h.map_points_dev()
+        m_r = self.m_r(mpts, int(npts), last.cpu().numpy())
         st = self.stats_of(lambda i: h.register_map(last, o))
-        n_last = len(seq[-1])
-        rec["roofline"] = roofline("reg_iter_kernel<P2PLANE_KNN,5> at the final map", "reg_iter_kernel_c3", 16 * (n_last + (m_r or 0)) + 232, k_ms,
-                                   "per frame: 20 iteration kernels (latency chain on an L2-resident neighbourhood of the map) + incremental Add_Points",
+        rec["us_per_iteration"] = 1e3 * k_ms if k_ms else None
+        rec["roofline"] = roofline("reg_iter_kernel<P2PLANE_KNN,5> at the final map", "reg_iter_kernel_c3", 16 * (int(last.shape[0]) + m_r) + 232, k_ms,
+                                   "per frame: Doppler filter, 20 iteration kernels (latency chain on an L2-resident neighbourhood of the map), incremental Add_Points",
                                    dist_evals=(st[1] / (ITERS + 1)) if st else None, extra={"m_r": m_r})
         if not self.args.no_cpu_baseline:
-            kind, cnt, secs, upto = cpu_c3(seq, 20.0, self.threads)
+            kind, cnt, secs, upto = cpu_c3(raw, 20.0, self.threads)
             rec["cpu_baseline"] = {"value": cnt / secs, "unit": "registrations/s", "cores": self.threads if kind == "reference" else 1, "kind": kind,
                                    "sample": f"{cnt} frames timed out of the first {upto}, spread over the sequence with the tree grown to each frame's size "
-                                             "(frames in between inserted untimed)"}
+                                             "(frames in between inserted untimed); per frame Doppler filter + registration + transform + Add_Points"}
+        return rec
+
+    # ---- the node's own per-frame flow ------------------------------------------------------------------------------------
+    def run_c3ref(self, steps, warmup, main=False):
+        torch, pkg, h = self.torch, self.pkg, self.h
+        nf = self.args.frames_ref
+        # a forward-looking radar: returns within 80 m and +-60 degrees (the sector the node searches its map with)
+        frames, gt = pkg.pipeline.synth_radar_sequence(1003 + self.rank, nf, pts_per_frame=4000, extent=400.0, scan_radius=90.0, fov_deg=55.0, max_range=78.0, forward="y")
+        o = pkg.default_opts(residual=pkg.GICP, k=K_NN, max_iterations=64, early_exit=1, max_corr_dist=0.0)
+        d_frames = [torch.from_numpy(f).to(self.dev) for f in frames]
+        pin = [torch.from_numpy(f).pin_memory() for f in frames]
+        total = int(sum(len(f) for f in frames))
+        vg_out = torch.empty((total, 4), dtype=torch.float32, device=self.dev)
+        last = {}
+
+        def step_dev(i):
+            last["poses"], last["n_ds"] = pkg.pipeline.run_reference_flow(h, d_frames, o, vg_out=vg_out, priors=gt)
+        step_e2e = lambda i: pkg.pipeline.run_reference_flow(h, pin, o, vg_out=vg_out, on_device=lambda r: r.to(self.dev, non_blocking=True), priors=gt)
+        m = self.measure(step_dev, step_e2e, steps, warmup, nf, sample_clocks=main)
+        n_map, _ = h.map_size()
+        rec = self.record(m, 8 * 3000, total * 20, nf * (16 * 8 + 32),
+                          {"workload": f"the scan-to-map node's own per-frame flow (radar_odometry.cpp:328,380-429), {nf} raw radar frames of 4000 records: Doppler "
+                                       "static-point filter, pointAssociateToMap, Add_Points(false), Sector_Search 80 m, GICP (k=5, LM, early exit) against the sector "
+                                       "sub-map, pose chained by left multiplication, VoxelGrid 0.5 m over the whole map; one step = the whole sequence",
+                           "frames": nf, "final_map_points": int(n_map), "final_downsampled_points": int(last.get("n_ds", 0)),
+                           "l2": "flushed before every timed step"})
+        rec["_m"] = m
+        rec["unit_note"] = "registrations/s = frames/s (one registration per frame)"
+        rec["ms_per_frame"] = m["ms_per_step"] / nf
+        # roofline of the step that streams: the voxel grid over the whole map (16 B read per map point, 16 B written per leaf)
+        evs = []
+        with torch.cuda.stream(self.stream):
+            for i in range(5):
+                self.flush.fill_(i)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(self.stream)
+                ds = h.voxel_grid(None, 0.5, out=vg_out)
+                e1.record(self.stream)
+                evs.append((e0, e1))
+        torch.cuda.synchronize(self.dev)
+        vg_ms = float(np.median([a.elapsed_time(b) for a, b in evs[1:]]))
+        rec["roofline"] = roofline("icp4r_voxel_grid over the final map (key + sort + segmented mean kernels)", "voxel_grid_c3ref",
+                                   17 * int(n_map) + 16 * int(ds.shape[0]), vg_ms,
+                                   "the per-frame flow is a chain of small launches (filter, sector, sub-map grid + covariances, ~8 GICP linearisations) around "
+                                   "two streaming passes over the growing map (sector filter, voxel grid); the voxel grid is the larger one")
+        if not self.args.no_cpu_baseline:
+            kind, cnt, secs, which = cpu_c3ref(frames, gt, 25.0, self.threads)
+            rec["cpu_baseline"] = {"value": cnt / max(secs, 1e-9), "unit": "registrations/s", "cores": self.threads if kind == "reference" else 1, "kind": kind,
+                                   "sample": f"frames {which} of the sequence timed whole (filter, transform, Add_Points, Sector_Search, kd-tree over the sub-map, GICP, "
+                                             "voxel grid) with the tree grown to that frame; frames in between inserted untimed; fast_gicp / PCL absent from the image"}
         return rec
 
     # ---- C5 -------------------------------------------------------------------------------------------------------
@@ -791,7 +901,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="all", choices=["all", "c1", "c2", "c2single", "c3", "c4", "c5", "gicp"])
+    ap.add_argument("--workload", default="all", choices=["all", "c1", "c2", "c2single", "c3", "c3ref", "c4", "c5", "gicp"])
+    ap.add_argument("--frames-ref", type=int, default=400, help="c3ref: raw radar frames of the node's own per-frame flow")
     ap.add_argument("--frames", type=int, default=2000, help="c3: frames of the odometry sequence (one step = the whole sequence)")
     ap.add_argument("--map-points", type=int, default=20_000_000, help="c5: points of the dense map (whole job)")
     ap.add_argument("--pairs", type=int, default=C4_PAIRS, help="c4: frame pairs of the WHOLE job (split across the GPUs)")
@@ -821,6 +932,7 @@ def main():
                 configs["c2_batch16"] = strip(B.run_c2(max(10 * K, 50), 10, batch=True))
                 configs["gicp"] = strip(B.run_gicp(max(10 * K, 50), 5))
                 configs["c3"] = strip(B.run_c3(2, 3))
+                configs["c3ref"] = strip(B.run_c3ref(2, 3))
                 configs["c5"] = strip(B.run_c5(max(5 * K, 30), 5))
             else:
                 configs["c5_sharded"] = strip(B.run_c5(max(5 * K, 30), 5))
@@ -832,6 +944,8 @@ def main():
         rec = B.run_gicp(K, W, main=True)
     elif wl == "c3":
         rec = B.run_c3(K, W, main=True)
+    elif wl == "c3ref":
+        rec = B.run_c3ref(K, W, main=True)
     else:
         rec = B.run_c5(K, W, main=True)
     if rank == 0:

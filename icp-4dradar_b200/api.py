@@ -22,7 +22,7 @@ EXPORTS = [
     "icp4r_synchronize", "icp4r_launch_count", "icp4r_set_profiling", "icp4r_last_profile", "icp4r_set_stats", "icp4r_get_stats", "icp4r_map_build", "icp4r_map_set_downsample", "icp4r_map_add_points",
     "icp4r_map_size", "icp4r_map_range", "icp4r_map_knn", "icp4r_map_knn_brute", "icp4r_map_sector", "icp4r_map_points",
     "icp4r_register", "icp4r_register_map", "icp4r_register_map_batch", "icp4r_register_batch", "icp4r_shard_unique_id", "icp4r_shard_init", "icp4r_shard_ipc_export", "icp4r_shard_ipc_import",
-    "icp4r_register_sharded", "icp4r_accumulate_slab", "icp4r_transform_points", "icp4r_voxel_grid", "icp4r_odometry_step", "icp4r_map_box_search",
+    "icp4r_register_sharded", "icp4r_accumulate_slab", "icp4r_register_submap", "icp4r_doppler_static_points", "icp4r_transform_points", "icp4r_voxel_grid", "icp4r_odometry_step", "icp4r_map_box_search",
     "icp4r_map_radius_search", "icp4r_map_delete_boxes", "icp4r_map_add_boxes", "icp4r_map_delete_points", "icp4r_doppler_filter",
 ]
 
@@ -423,6 +423,48 @@ class Icp4r:
         return T.reshape(4, 4), res
 
     # ---- Doppler filter
+    def register_submap(self, src, idx, opts: Opts):
+        """source vs the map points idx (numpy int32 or a torch int32 tensor on the device, like src). Returns (T, result)."""
+        src = _f4(src)
+        ps, mem = _ptr(src)
+        pi, mem_i = _ptr(idx)
+        assert mem == mem_i, "src and idx must live in the same memory space"
+        T = np.zeros(16, np.float64)
+        res = Result()
+        self._ck(self.lib.icp4r_register_submap(self.h, ps, C.c_int32(src.shape[0]), pi, C.c_int32(int(idx.shape[0])), C.c_int(mem), C.byref(opts),
+                                                C.c_void_p(T.ctypes.data), C.byref(res)))
+        return T.reshape(4, 4), res
+
+    def map_sector_dev(self, centre, radius, heading_deg):
+        """Sector_Search with the indices left on the device (torch int32 tensor)"""
+        import torch
+        n, _ = self.map_size()
+        c = np.asarray(centre, np.float32)
+        out = torch.empty(max(n, 1), dtype=torch.int32, device=torch.device("cuda", self.device))
+        cnt = C.c_int32(0)
+        self._ck(self.lib.icp4r_map_sector(self.h, C.c_void_p(c.ctypes.data), C.c_float(radius), C.c_float(heading_deg),
+                                           C.c_int(DEVICE), C.c_void_p(out.data_ptr()), C.c_int32(out.shape[0]), C.byref(cnt)))
+        return out[:min(cnt.value, out.shape[0])]
+
+    def doppler_static_points(self, records, iterations: int = 0, seed: int = 1, sigma: float = 0.5, split: float = 0.2):
+        """(static points [ns,4] in the memory space of `records`, DopplerResult)"""
+        o = DopplerOpts(iterations, 0, seed, sigma, split)
+        res = DopplerResult()
+        pr, mem = _ptr(records)
+        n = int(records.shape[0])
+        cnt = C.c_int32(0)
+        if mem == HOST:
+            rec = np.ascontiguousarray(records, np.float32)
+            out = np.empty((max(n, 1), 4), np.float32)
+            self._ck(self.lib.icp4r_doppler_static_points(self.h, C.c_void_p(rec.ctypes.data), C.c_int32(n), C.c_int(HOST), C.byref(o),
+                                                          C.c_void_p(out.ctypes.data), C.c_int32(n), C.byref(cnt), C.byref(res)))
+            return out[:cnt.value].copy(), res
+        import torch
+        out = torch.empty((max(n, 1), 4), dtype=torch.float32, device=records.device)
+        self._ck(self.lib.icp4r_doppler_static_points(self.h, pr, C.c_int32(n), C.c_int(DEVICE), C.byref(o), C.c_void_p(out.data_ptr()),
+                                                      C.c_int32(n), C.byref(cnt), C.byref(res)))
+        return out[:cnt.value], res
+
     def accumulate_slab(self, src, opts: Opts, T, axis: int = -1, slab_lo: float = 0.0, slab_hi: float = 0.0):
         """this slab's partial accumulators [ACC_LEN] at pose T (no cross-rank sum, no solve)"""
         src = _f4(src)
@@ -458,9 +500,14 @@ class Icp4r:
                                               C.c_void_p(T.ctypes.data), C.byref(res)))
         return T.reshape(4, 4), res
 
-    def voxel_grid(self, pts, leaf: float):
-        """pcl::VoxelGrid centroid filter. pts None: the handle's map (returns numpy); numpy -> numpy; torch CUDA -> torch."""
+    def voxel_grid(self, pts, leaf: float, out=None):
+        """pcl::VoxelGrid centroid filter. pts None: the handle's map (returns numpy, or — with `out`, a torch CUDA float32
+        [cap,4] tensor — the filled part of `out`); numpy -> numpy; torch CUDA -> torch."""
         cnt = C.c_int32(0)
+        if pts is None and out is not None:
+            self._ck(self.lib.icp4r_voxel_grid(self.h, None, C.c_int32(0), C.c_int(DEVICE), C.c_float(leaf), C.c_void_p(out.data_ptr()),
+                                               C.c_int32(out.shape[0]), C.byref(cnt)))
+            return out[:min(cnt.value, out.shape[0])]
         if pts is None:
             n, _ = self.map_size()
             out = np.empty((max(n, 1), 4), np.float32)

@@ -52,6 +52,47 @@ void release(DevBuf& b) {
     b.cap = 0;
 }
 
+// order-preserving compaction of the radar records the Doppler filter kept, as x, y, z, intensity rows (one block)
+__global__ void __launch_bounds__(1024) compact_static_kernel(const float* __restrict__ rec, const uint8_t* __restrict__ mask, int n,
+                                                             float4* __restrict__ out, int cap, int* __restrict__ n_out) {
+    __shared__ int wcnt[32];
+    __shared__ int carry_s;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < n; b0 += 1024) {
+        const int i = b0 + tid;
+        const bool keep = i < n && mask[i] != 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) wcnt[w] = __popc(bal);
+        __syncthreads();
+        int before = carry_s;
+        for (int j = 0; j < w; ++j) before += wcnt[j];
+        if (keep) {
+            const int pos = before + __popc(bal & ((1u << lane) - 1u));
+            if (pos < cap) out[pos] = make_float4(rec[5 * (size_t)i], rec[5 * (size_t)i + 1], rec[5 * (size_t)i + 2], rec[5 * (size_t)i + 3]);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int t = 0;
+            for (int j = 0; j < 32; ++j) t += wcnt[j];
+            carry_s += t;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) *n_out = carry_s;
+}
+
+// target of a sub-map registration: the map's points at the given indices (out-of-range indices give a NaN row, which
+// every search ignores)
+__global__ void __launch_bounds__(256) gather_subset_kernel(const float4* __restrict__ pts, int m, const int32_t* __restrict__ idx, int n_idx,
+                                                           float4* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_idx) return;
+    const int j = idx[i];
+    out[i] = (j >= 0 && j < m) ? pts[j] : make_float4(NAN, NAN, NAN, 0.f);
+}
+
 int shard_unique_id(char id_out[128]);
 int shard_init(Ctx* c, const char id_in[128], int rank, int world);
 void shard_destroy(Ctx* c);
@@ -127,6 +168,7 @@ using namespace icp4r;
     Ctx* c = (h);                       \
     c->err.clear();                     \
     if (cudaSetDevice(c->device) != cudaSuccess) return fail(c, ICP4R_ERR_CUDA, "cudaSetDevice(%d) failed", c->device)
+
 
 extern "C" {
 
@@ -631,6 +673,46 @@ int icp4r_register_map_batch(icp4r_handle h, const float* src, const int32_t* of
     return register_scans_against_map(c, c->map, static_cast<const float4*>(dsrc), off, n_scans, opts, T0s, T_out, res);
 }
 
+// registration against a transient target (the handle's c->tmp map): an explicit cloud (tgt, m) or, with idx != nullptr,
+// the subset idx[0..n_idx) of the handle's persistent map gathered on the device
+static int register_transient(Ctx* c, const float* src, int32_t n, const float* tgt, int32_t m, int mem, const int32_t* idx, int32_t n_idx,
+                              const icp4r_opts* opts, double T_out[16], icp4r_result* res, const icp4r_dump* dump) {
+    // transient index over the target, rebuilt per call like PCL's setInputTarget kd-tree
+    Map& mp = c->tmp;
+    mp.m = 0;
+    mp.built = false;
+    mp.user_cell = 0.f;
+    mp.hint_cell = 0.f;
+    if (idx != nullptr) m = n_idx;
+    {   // a small target that serves one registration: the volume-estimated cell is good enough, the occupancy-based
+        // refinement (a device round trip and up to two more sorts) costs more than it saves
+        const char* e = std::getenv("ICP4R_TMP_REFINE");
+        mp.quick_build = m <= 16384 && !(e && e[0] == '1');
+    }
+    if (idx == nullptr) {
+        CKS(set_points(c, mp, tgt, m, mem, 0));
+    } else {
+        CKS(map_reserve(c, mp, m));
+        const void* didx = nullptr;
+        CKS(stage_in(c, c->d_idx, idx, (size_t)m * sizeof(int32_t), mem, &didx));
+        if (m > 0) {
+            gather_subset_kernel<<<(m + 255) / 256, 256, 0, c->stream>>>(c->map.pts.as<float4>(), c->map.m, static_cast<const int32_t*>(didx), m,
+                                                                        mp.pts.as<float4>());
+            c->launches += 1;
+            CK(cudaMemsetAsync(mp.valid.p, 1, (size_t)m, c->stream));
+            CK(cudaMemsetAsync(mp.userdel.p, 0, (size_t)m, c->stream));
+        }
+    }
+    mp.m = m;
+    CKS(map_rebuild_grid(c, mp));
+    const void* dsrc = nullptr;
+    CKS(stage_in(c, c->d_src, src, (size_t)n * sizeof(float4), mem, &dsrc));
+    DumpStage ds;
+    CKS(dump_prepare(c, dump, mem, n, opts, ds));
+    CKS(register_against_map(c, mp, static_cast<const float4*>(dsrc), n, opts, -1, 0.f, 0.f, T_out, res, dump ? &ds.dev : nullptr));
+    return dump_finish(c, ds);
+}
+
 int icp4r_register(icp4r_handle h, const float* src, int32_t n, const float* tgt, int32_t m, int mem, const icp4r_opts* opts,
                    double T_out[16], icp4r_result* res, const icp4r_dump* dump) {
     HCHECK(h);
@@ -667,26 +749,17 @@ int icp4r_register(icp4r_handle h, const float* src, int32_t n, const float* tgt
             return ICP4R_OK;
         }
     }
-    // transient index over the target, rebuilt per call like PCL's setInputTarget kd-tree
-    Map& mp = c->tmp;
-    mp.m = 0;
-    mp.built = false;
-    mp.user_cell = 0.f;
-    mp.hint_cell = 0.f;
-    {   // a small target that serves one registration: the volume-estimated cell is good enough, the occupancy-based
-        // refinement (a device round trip and up to two more sorts) costs more than it saves
-        const char* e = std::getenv("ICP4R_TMP_REFINE");
-        mp.quick_build = m <= 16384 && !(e && e[0] == '1');
-    }
-    CKS(set_points(c, mp, tgt, m, mem, 0));
-    mp.m = m;
-    CKS(map_rebuild_grid(c, mp));
-    const void* dsrc = nullptr;
-    CKS(stage_in(c, c->d_src, src, (size_t)n * sizeof(float4), mem, &dsrc));
-    DumpStage ds;
-    CKS(dump_prepare(c, dump, mem, n, opts, ds));
-    CKS(register_against_map(c, mp, static_cast<const float4*>(dsrc), n, opts, -1, 0.f, 0.f, T_out, res, dump ? &ds.dev : nullptr));
-    return dump_finish(c, ds);
+    return register_transient(c, src, n, tgt, m, mem, nullptr, 0, opts, T_out, res, dump);
+}
+
+int icp4r_register_submap(icp4r_handle h, const float* src, int32_t n, const int32_t* idx, int32_t n_idx, int mem, const icp4r_opts* opts,
+                          double T_out[16], icp4r_result* res) {
+    HCHECK(h);
+    if (!opts || n < 0 || n_idx < 0 || (n > 0 && !src) || (n_idx > 0 && !idx) || bad_mem(mem))
+        return fail(c, ICP4R_ERR_INVALID, "icp4r_register_submap: bad arguments");
+    if (!c->map.built) return fail(c, ICP4R_ERR_STATE, "icp4r_register_submap: the handle has no map");
+    static const int32_t none = 0;
+    return register_transient(c, src, n, nullptr, 0, mem, n_idx > 0 ? idx : &none, n_idx, opts, T_out, res, nullptr);
 }
 
 int icp4r_register_batch(icp4r_handle h, const float* src, const int32_t* src_off, const float* tgt, const int32_t* tgt_off,
@@ -841,6 +914,37 @@ int icp4r_doppler_filter(icp4r_handle h, const float* xyziv, int32_t n, int mem,
     std::memcpy(res, c->h_pinned, sizeof(icp4r_doppler_result));
     if (mem == ICP4R_HOST && static_mask && n > 0) {
         CK(cudaMemcpyAsync(static_mask, dmask, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return ICP4R_OK;
+}
+
+int icp4r_doppler_static_points(icp4r_handle h, const float* xyziv, int32_t n, int mem, const icp4r_doppler_opts* opts, float* xyzw_out,
+                                int32_t cap, int32_t* n_out, icp4r_doppler_result* res) {
+    HCHECK(h);
+    if (!opts || !res || !n_out || n < 0 || cap < 0 || (n > 0 && !xyziv) || (cap > 0 && !xyzw_out) || bad_mem(mem))
+        return fail(c, ICP4R_ERR_INVALID, "icp4r_doppler_static_points: bad arguments");
+    const void* drec = nullptr;
+    CKS(stage_in(c, c->d_src, xyziv, (size_t)n * 5 * sizeof(float), mem, &drec));
+    CKS(reserve(c, c->d_found, (size_t)std::max(n, 1)));
+    uint8_t* dmask = c->d_found.as<uint8_t>();
+    CKS(doppler_filter(c, static_cast<const float*>(drec), n, opts->iterations, opts->seed, opts->sigma, opts->split, dmask, c->h_pinned));
+    std::memcpy(res, c->h_pinned, sizeof(icp4r_doppler_result));
+    float4* dout = reinterpret_cast<float4*>(xyzw_out);
+    if (mem == ICP4R_HOST) {
+        CKS(reserve(c, c->gs_pts, (size_t)std::max(cap, 1) * sizeof(float4)));
+        dout = c->gs_pts.as<float4>();
+    }
+    CKS(reserve(c, c->d_scratch, 4096));
+    int* d_n = c->d_scratch.as<int>();
+    compact_static_kernel<<<1, 1024, 0, c->stream>>>(static_cast<const float*>(drec), dmask, n, dout, cap, d_n);
+    c->launches += 1;
+    int* h_n = reinterpret_cast<int*>(static_cast<char*>(c->h_pinned) + 256);
+    CK(cudaMemcpyAsync(h_n, d_n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    *n_out = *h_n;
+    if (mem == ICP4R_HOST && std::min(*n_out, cap) > 0) {
+        CK(cudaMemcpyAsync(xyzw_out, dout, (size_t)std::min(*n_out, cap) * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
     }
     return ICP4R_OK;

@@ -324,7 +324,7 @@ static int bucket_build(Ctx* c, Map& mp, const GridDesc& g, int m, int nvalid, b
     const long long nb_ll = ((long long)g.ncells + 1 + (1ll << S) - 1) >> S;
     if (nb_ll * BK_CAP > 4ll * std::max(m, 1) + (1 << 20)) return ICP4R_OK;  // mostly empty buckets (surfaces in a big volume): not worth the scratch
     const int nb = (int)nb_ll;
-    CKS(reserve(c, c->d_scratch, ((size_t)2 * nb + 16) * sizeof(uint32_t)));
+    CKS(reserve_grow(c, c->d_scratch, ((size_t)2 * nb + 16) * sizeof(uint32_t)));
     uint32_t* cursor = c->d_scratch.as<uint32_t>();   // [nb] points per bucket
     uint32_t* base = cursor + nb;                     // [nb + 1]
     uint32_t* info = base + nb + 1;                   // [1]

@@ -167,7 +167,7 @@ int radix_sort_pairs(Ctx* c, uint32_t* keys_a, uint32_t* keys_b, uint32_t* vals_
     *vals_out = vals_a;
     if (n <= 0) return ICP4R_OK;
     const int tiles = (n + RS_TILE - 1) / RS_TILE;
-    CKS(reserve(c, scratch, ((size_t)256 * tiles + 256) * sizeof(uint32_t)));
+    CKS(reserve_grow(c, scratch, ((size_t)256 * tiles + 256) * sizeof(uint32_t)));  // callers sort growing maps frame after frame
     uint32_t* counts = scratch.as<uint32_t>();
     uint32_t* totals = counts + (size_t)256 * tiles;
     if (bits < 1) bits = 1;

@@ -243,8 +243,8 @@ int voxel_grid(Ctx* c, const float4* d_pts, const uint8_t* d_valid, int n, float
     int bits = 1;
     while (bits < 32 && (1ull << bits) <= (unsigned long long)d.invalid) ++bits;
 
-    CKS(reserve(c, c->vg_keys, (size_t)n * 2 * sizeof(uint32_t)));
-    CKS(reserve(c, c->vg_vals, (size_t)n * 2 * sizeof(uint32_t)));
+    CKS(reserve_grow(c, c->vg_keys, (size_t)n * 2 * sizeof(uint32_t)));  // the map this runs over grows every frame: geometric growth, not a cudaMalloc per call
+    CKS(reserve_grow(c, c->vg_vals, (size_t)n * 2 * sizeof(uint32_t)));
     uint32_t *ka = c->vg_keys.as<uint32_t>(), *kb = ka + n, *va = c->vg_vals.as<uint32_t>(), *vb = va + n;
     vg_key_kernel<<<(n + VG_THREADS - 1) / VG_THREADS, VG_THREADS, 0, c->stream>>>(d_pts, d_valid, n, d, ka, va);
     c->launches += 1;
@@ -252,7 +252,7 @@ int voxel_grid(Ctx* c, const float4* d_pts, const uint8_t* d_valid, int n, float
     CKS(radix_sort_pairs(c, ka, kb, va, vb, n, bits, c->vg_sort, &ks, &vs));
     const int nv = nfinite;  // skipped points carry the largest key and sit behind the finite ones
     const int tiles = (nv + VG_TILE - 1) / VG_TILE;
-    CKS(reserve(c, c->vg_tiles, (size_t)(tiles + 1) * sizeof(int)));
+    CKS(reserve_grow(c, c->vg_tiles, (size_t)(tiles + 1) * sizeof(int)));
     int* d_tiles = c->vg_tiles.as<int>();
     vg_count_kernel<<<tiles, VG_THREADS, 0, c->stream>>>(ks, nv, d_tiles);
     vg_scan_kernel<<<1, 1024, 0, c->stream>>>(d_tiles, tiles);

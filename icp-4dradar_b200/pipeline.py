@@ -55,17 +55,52 @@ def run_odometry(h: api.Icp4r, scans, opts: api.Opts, T_first=None, fused: bool 
     return poses
 
 
+def run_odometry_raw(h: api.Icp4r, frames, opts: api.Opts, seed: int = 1, on_device=None):
+    """BASELINE config 3 from RAW radar frames [n,5]: per frame the Doppler static-point filter
+    (icp4r_doppler_static_points), then one icp4r_odometry_step (register against the growing map, transform, Add_Points).
+    on_device: callable that moves one frame to the device (host-buffer flavour). Returns the estimated poses."""
+    T = np.eye(4)
+    poses = []
+    h.map_build(np.zeros((0, 4), np.float32))
+    for f, rec in enumerate(frames):
+        if on_device is not None:
+            rec = on_device(rec)
+        static, _ = h.doppler_static_points(rec, 0, seed=seed + f)
+        if f == 0:
+            h.odometry_step(static, opts, T)
+        else:
+            T, _res = h.odometry_step(static, opts, T)
+        poses.append(T.copy())
+    return poses
+
+
 # ---- scan-to-scan node ---------------------------------------------------------------------------------------------
 def synth_radar_sequence(seed: int, frames: int, pts_per_frame: int = 1200, extent: float = 120.0, scan_radius: float = 50.0,
-                         dynamic_frac: float = 0.1):
-    """(list of raw radar frames [n,5] x,y,z,intensity,doppler in the sensor frame, list of ground-truth poses)."""
+                         dynamic_frac: float = 0.1, fov_deg: float | None = None, max_range: float | None = None, forward: str = "x"):
+    """(list of raw radar frames [n,5] x,y,z,intensity,doppler in the sensor frame, list of ground-truth poses).
+    fov_deg / max_range: keep only the returns inside the sensor's field of view (|azimuth| <= fov_deg, range <=
+    max_range in the sensor frame) like a forward-looking radar (the reference's sub-map is the same sector: 80 m,
+    RADAR_RADIUS at radar_odometry.cpp:36); the scene is over-sampled so that about pts_per_frame returns remain.
+    forward: the sensor axis the field of view is centred on. The scan-to-map node passes its yaw as the sector heading
+    (radar_odometry.cpp:379,396) and KD_TREE::calc_heading measures headings from the +y axis (ikd_Tree.cpp:1434-1448:
+    heading 0 = +y, -90 = +x), i.e. that node's sector looks along the body's +y axis: use forward="y" for its flow."""
     rng = np.random.default_rng(seed)
     scene = synth.Scene(seed, extent=extent, n_walls=int(12 * (extent / 80.0) ** 2))
     poses = synth.trajectory(seed, frames)
     out = []
+    crop = fov_deg is not None or max_range is not None
     for f, T in enumerate(poses):
-        w = scene.sample(rng, pts_per_frame, centre=(T[0, 3], T[1, 3]), radius=scan_radius)
+        n_draw = pts_per_frame * (6 if crop else 1)
+        w = scene.sample(rng, n_draw, centre=(T[0, 3], T[1, 3]), radius=scan_radius)
         s = synth.apply(np.linalg.inv(T), w)
+        if crop:
+            keep = np.ones(len(s), bool)
+            if max_range is not None:
+                keep &= np.linalg.norm(s[:, :3], axis=1) <= max_range
+            if fov_deg is not None:
+                az = np.arctan2(s[:, 1], s[:, 0]) if forward == "x" else np.arctan2(-s[:, 0], s[:, 1])
+                keep &= np.abs(np.degrees(az)) <= fov_deg
+            s = np.ascontiguousarray(s[keep][:pts_per_frame])
         nxt = poses[min(f + 1, frames - 1)]
         prv = poses[max(f - 1, 0)]
         v_world = (nxt[:3, 3] - prv[:3, 3]) / (0.1 * max(1, min(f + 1, frames - 1) - max(f - 1, 0)))   # 10 Hz frames
@@ -108,3 +143,53 @@ def run_scan_to_scan(h: api.Icp4r, frames, opts: api.Opts, batched: bool = True,
         cur = cur @ np.asarray(T, np.float64).reshape(4, 4)
         poses.append(cur.copy())
     return poses, vel, res
+
+
+# ---- the scan-to-map node's own per-frame flow ---------------------------------------------------------------------
+def yaw_deg(T) -> float:
+    """heading as the reference computes it: R2rpy(R)(2) in degrees (/root/reference/src/radar_odometry.cpp:120-135,379)"""
+    return float(np.degrees(np.arctan2(T[1, 0], T[0, 0])))
+
+
+def run_reference_flow(h: api.Icp4r, frames, opts: api.Opts, radius: float = 80.0, leaf: float = 0.5, seed: int = 1, vg_out=None,
+                       on_device=None, priors=None):
+    """What /root/reference/src/radar_odometry.cpp:328,380-429 does per radar frame, with every step on the device:
+
+      static points of the raw frame (ego-velocity / Doppler filter, :328)   -> icp4r_doppler_static_points
+      pointAssociateToMap with the current pose (:384-389)                    -> icp4r_transform_points
+      ikd_Tree.Add_Points(scan_map, false) (:390; Build on the first frame)   -> icp4r_map_add_points / icp4r_map_build
+      ikd_Tree.Sector_Search(p_now, 80 m, heading) (:392-396)                 -> icp4r_map_sector (indices stay on the device)
+      FastGICP align of the scan against the sub-map (:399-405)               -> icp4r_register_submap (ICP4R_GICP)
+      currOdom = icp_result * currOdom (:412)
+      VoxelGrid 0.5 m over the whole accumulated map (:426-429)               -> icp4r_voxel_grid(NULL)
+
+    frames: raw radar records [n,5] (x, y, z, intensity, doppler), numpy or torch CUDA tensors; on_device: callable that
+    moves one frame to the device (the bench's host-buffer flavour passes a pinned-memory copy here so that the raw frame
+    is the only thing that crosses the bus). priors: the pose q_w_curr / t_w_curr the node places every scan with before
+    aligning it — in the reference it comes from the odometry / ground-truth queue (radar_odometry.cpp:352-379); None: the
+    chained estimate itself. Returns (currOdom per frame, points of the last down-sampled map)."""
+    odom = np.eye(4)
+    poses = []
+    n_ds = 0
+    for f, rec in enumerate(frames):
+        if on_device is not None:
+            rec = on_device(rec)
+        T = odom if priors is None else np.asarray(priors[f], np.float64)
+        static, _dres = h.doppler_static_points(rec, 0, seed=seed + f)
+        scan_w = h.transform_points(T, static)
+        if f == 0:
+            h.map_build(scan_w)
+            if priors is not None:
+                odom = T.copy()
+        else:
+            h.map_add_points(scan_w, False)
+            if isinstance(scan_w, np.ndarray):
+                idx = h.map_sector(T[:3, 3], radius, yaw_deg(T))
+            else:
+                idx = h.map_sector_dev(T[:3, 3], radius, yaw_deg(T))
+            D, _res = h.register_submap(scan_w, idx, opts)
+            odom = D @ (odom if priors is None else T)
+        poses.append(odom.copy())
+        ds = h.voxel_grid(None, leaf, out=vg_out)
+        n_ds = int(ds.shape[0])
+    return poses, n_ds

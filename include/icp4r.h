@@ -162,6 +162,11 @@ int icp4r_register(icp4r_handle h, const float* src_xyzw, int32_t n, const float
 /* source vs the handle's map (radar_odometry.cpp:390-411 with the ikd-Tree map as the target) */
 int icp4r_register_map(icp4r_handle h, const float* src_xyzw, int32_t n, int mem, const icp4r_opts* opts,
                        double T_out[16], icp4r_result* res, const icp4r_dump* dump);
+/* source vs a SUBSET of the handle's map given by point indices (icp4r_map_sector's output; same memory space as the
+ * call): what radar_odometry.cpp:396-405 does with SubMap. The subset is gathered on the device into the handle's
+ * transient target, indexed and registered like icp4r_register — the sub-map never crosses the bus. */
+int icp4r_register_submap(icp4r_handle h, const float* src_xyzw, int32_t n, const int32_t* idx, int32_t n_idx, int mem,
+                          const icp4r_opts* opts, double T_out[16], icp4r_result* res);
 /* n_scans independent scans against the handle's map in ONE sequence of launches (throughput mode: one scan of a
  * few thousand points leaves most of the GPU idle). src_xyzw holds the scans back to back (memory space `mem`);
  * off [n_scans+1] (points), T0s ([n_scans][16] initial guesses, or NULL = opts->T0 for all), T_out [n_scans][16]
@@ -220,6 +225,12 @@ typedef struct icp4r_doppler_result {
 } icp4r_doppler_result;
 int icp4r_doppler_filter(icp4r_handle h, const float* xyziv, int32_t n, int mem, const icp4r_doppler_opts* opts,
                          uint8_t* static_mask, icp4r_doppler_result* res);
+
+/* The static points of a radar frame: icp4r_doppler_filter followed by an order-preserving compaction of the records the
+ * filter keeps, as packed x, y, z, intensity rows — the cloud the reference hands to its registration
+ * (iterative_closest_point.cpp:392-407). At most `cap` rows are written; *n_out = number of static points. */
+int icp4r_doppler_static_points(icp4r_handle h, const float* xyziv, int32_t n, int mem, const icp4r_doppler_opts* opts,
+                                float* xyzw_out, int32_t cap, int32_t* n_out, icp4r_doppler_result* res);
 
 /* ---- helpers on the path ----------------------------------------------------------------------------- */
 /* p' = R p + t in double, written back as float (pointAssociateToMap, radar_odometry.cpp:137-145) */
