@@ -187,6 +187,7 @@ int icp4r_default_opts(icp4r_opts* o) {
     o->mse_abs_eps = 1e-12;
     o->plane_thresh = 0.2;
     for (int i = 0; i < 16; ++i) o->T0[i] = (i % 5 == 0) ? 1.0 : 0.0;
+    o->interp_s = 1.0;
     return ICP4R_OK;
 }
 
@@ -787,6 +788,28 @@ int icp4r_register_batch(icp4r_handle h, const float* src, const int32_t* src_of
     }
     const size_t ns = (size_t)so[n_pairs], nt = (size_t)to[n_pairs];
     if ((ns > 0 && !src) || (nt > 0 && !tgt)) return fail(c, ICP4R_ERR_INVALID, "null cloud pointer");
+    if (!register_batch_fits(max_n, max_m)) {
+        // A pair that does not fit one SM's shared memory (n + m above ~12 k points): every pair of the batch goes through
+        // the map path instead — target grid in global memory, one launch per iteration — one after the other. Same
+        // results (both loops are checked against the same oracle), lower throughput; the resident kernel is the fast
+        // path for radar-sized clouds.
+        if (opts->residual != ICP4R_P2P_SVD && opts->residual != ICP4R_P2P_GN)
+            return fail(c, ICP4R_ERR_UNSUPPORTED, "batched registration supports P2P_SVD and P2P_GN (got %d)", opts->residual);
+        std::vector<double> Th((size_t)n_pairs * 16);
+        std::vector<icp4r_result> Rh(n_pairs);
+        for (int i = 0; i < n_pairs; ++i)
+            CKS(register_transient(c, src + 4 * (size_t)so[i], so[i + 1] - so[i], tgt + 4 * (size_t)to[i], to[i + 1] - to[i], mem, nullptr, 0, opts,
+                                   Th.data() + 16 * (size_t)i, &Rh[i], nullptr));
+        if (mem == ICP4R_DEVICE) {
+            CK(cudaMemcpyAsync(T_out, Th.data(), Th.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+            CK(cudaMemcpyAsync(res, Rh.data(), Rh.size() * sizeof(icp4r_result), cudaMemcpyHostToDevice, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+        } else {
+            std::memcpy(T_out, Th.data(), Th.size() * sizeof(double));
+            std::memcpy(res, Rh.data(), Rh.size() * sizeof(icp4r_result));
+        }
+        return ICP4R_OK;
+    }
     // Large host-resident batches: copy the clouds in chunks on a second stream that runs ahead of the kernels, so the
     // bus transfer of chunk k+1 overlaps the registration of chunk k (the clouds of a pair range are contiguous).
     constexpr int NCHUNK = 8;

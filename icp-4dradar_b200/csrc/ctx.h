@@ -142,6 +142,7 @@ struct RegParams {  // kernel parameters that change per call; lives in device m
     float gate_f;        // largest float whose double is <= max_dist^2 (+inf when ungated)
     float gate_r;        // search radius in metres incl. rounding slack (+inf when ungated)
     double rot_eps, trans_eps, mse_abs_eps, plane_thresh;
+    double interp_s;     // P2LINE / P2PLANE_3PT: interpolation ratio of the functors (1 = full pose)
     double* dump_pose;
     double* dump_acc;
     int32_t* dump_idx;

@@ -42,6 +42,72 @@ __device__ __forceinline__ void publish_increment(RegState* st, const double* Ds
     if (lane == 0) st->last_pass = iter;
 }
 
+// T_s = (exp(s log R), s t) and M = s J_l(s phi) J_l(phi)^-1 for the interpolated functors (see reg_iter_kernel)
+__device__ __noinline__ void interp_pose(const double* T, double s, double* Tss, double* M) {
+    const double R[9] = {T[0], T[1], T[2], T[4], T[5], T[6], T[8], T[9], T[10]};
+    // phi = log R
+    const double w[3] = {0.5 * (R[7] - R[5]), 0.5 * (R[2] - R[6]), 0.5 * (R[3] - R[1])};  // sin(theta) * axis
+    const double sn = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+    const double cs = 0.5 * ((R[0] + R[4] + R[8]) - 1.0);
+    const double th = atan2(sn, cs);
+    const double f = th < 1e-8 ? 1.0 + th * th / 6.0 : th / sn;
+    const double phi[3] = {f * w[0], f * w[1], f * w[2]};
+    auto skew = [](const double* v, double* K) {
+        K[0] = 0; K[1] = -v[2]; K[2] = v[1];
+        K[3] = v[2]; K[4] = 0; K[5] = -v[0];
+        K[6] = -v[1]; K[7] = v[0]; K[8] = 0;
+    };
+    auto mul3 = [](const double* A, const double* B, double* C) {
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) C[3 * i + j] = (A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j]) + A[3 * i + 2] * B[6 + j];
+    };
+    double K[9], K2[9];
+    skew(phi, K);
+    mul3(K, K, K2);
+    const double th2 = th * th;
+    // J_l(phi)^-1 = I - K/2 + (1/th^2 - (1 + cos)/(2 th sin)) K^2
+    const double ci = th < 1e-4 ? 1.0 / 12.0 + th2 / 720.0 : 1.0 / th2 - (1.0 + cos(th)) / (2.0 * th * sin(th));
+    double Jinv[9];
+    for (int e = 0; e < 9; ++e) Jinv[e] = (e % 4 == 0 ? 1.0 : 0.0) - 0.5 * K[e] + ci * K2[e];
+    // exp(s phi) and J_l(s phi): angle a = s th, generator Ks = s K
+    const double a = s * th, a2 = a * a;
+    const double A1 = a < 1e-4 ? 1.0 - a2 / 6.0 : sin(a) / a;
+    const double B1 = a < 1e-4 ? 0.5 - a2 / 24.0 : (1.0 - cos(a)) / a2;
+    const double C1 = a < 1e-4 ? 1.0 / 6.0 - a2 / 120.0 : (a - sin(a)) / (a2 * a);
+    double Rs[9], Jl[9];
+    for (int e = 0; e < 9; ++e) {
+        const double I = e % 4 == 0 ? 1.0 : 0.0;
+        Rs[e] = I + A1 * (s * K[e]) + B1 * (s * s * K2[e]);
+        Jl[e] = I + B1 * (s * K[e]) + C1 * (s * s * K2[e]);
+    }
+    double JJ[9];
+    mul3(Jl, Jinv, JJ);
+    for (int e = 0; e < 9; ++e) M[e] = s * JJ[e];
+    for (int r = 0; r < 3; ++r) {
+        Tss[4 * r + 0] = Rs[3 * r + 0];
+        Tss[4 * r + 1] = Rs[3 * r + 1];
+        Tss[4 * r + 2] = Rs[3 * r + 2];
+        Tss[4 * r + 3] = s * T[4 * r + 3];
+    }
+    Tss[12] = Tss[13] = Tss[14] = 0.0;
+    Tss[15] = 1.0;
+}
+
+// Jacobian row of a residual with gradient g at the placed point lp (see reg_iter_kernel): out[0..2] = d/d omega, out[3..5] = d/d v
+__device__ __forceinline__ void interp_row(const double g[3], const double lp[3], const double* T, const double* Tss, const double* M, double s,
+                                           double* out) {
+    const double u[3] = {lp[0] - Tss[3], lp[1] - Tss[7], lp[2] - Tss[11]};  // R_s p
+    const double t[3] = {T[3], T[7], T[11]};
+    double a[3], b[3];
+    cross3(u, g, a);
+    cross3(t, g, b);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        out[j] = ((a[0] * M[j] + a[1] * M[3 + j]) + a[2] * M[6 + j]) + s * b[j];
+        out[3 + j] = s * g[j];
+    }
+}
+
 // Pose update from the reduced accumulators, run by one full warp (see solve_warp.cuh). `tot`, `Ts` and `ws`
 // (>= 32 doubles of scratch) are shared memory; every branch is warp-uniform.
 __device__ __forceinline__ void warp_solve_and_update(int residual, const RegParams& P, RegState* st, const double* tot, const double* Ts,
@@ -201,6 +267,19 @@ __global__ void __launch_bounds__(RM_THREADS, RM_BLOCKS_PER_SM)
     if (tid == 28) s_last_pass = st->last_pass;
     if (tid >= 32 && tid < 32 + (int)(sizeof(RegParams) / 4)) reinterpret_cast<uint32_t*>(&P)[tid - 32] = reinterpret_cast<const uint32_t*>(prm)[tid - 32];
     __syncthreads();
+    // RadarEdgeFactor / LidarPlaneFactor with an interpolation ratio s != 1 (radarFactor.hpp:26-32,78-84): the point is
+    // placed with T_s = (slerp(I, q, s), s t) instead of T, for the search and for the residual alike. Under the left
+    // perturbation T <- exp(xi^) T the placed point moves as
+    //     d lp = -[R_s p]x M d omega - s [t]x d omega + s d v,      M = s J_l(s phi) J_l(phi)^-1,  phi = log R
+    // (J_l = left Jacobian of SO(3)), so a residual row with gradient g has J = [ (R_s p x g)^T M + s (t x g)^T | s g^T ].
+    constexpr bool CAN_INTERP = !FIT && (KIND == ICP4R_P2LINE || KIND == ICP4R_P2PLANE_3PT);
+    __shared__ double Tss[CAN_INTERP ? 16 : 1], Ms[CAN_INTERP ? 9 : 1];
+    const bool interp = CAN_INTERP && P.interp_s != 1.0;
+    if (CAN_INTERP && interp) {
+        if (tid == 0) interp_pose(Ts, P.interp_s, Tss, Ms);
+        __syncthreads();
+    }
+    const double* Tx = (CAN_INTERP && interp) ? Tss : Ts;  // the pose source points are placed with
 
     const float4* __restrict__ pts = P.map_pts;  // map points by insertion index
     const SegAddr sgaddr = seg_addr(&segs[w]);
@@ -321,7 +400,7 @@ __global__ void __launch_bounds__(RM_THREADS, RM_BLOCKS_PER_SM)
             if (need) {
                 const float4 p = __ldg(P.src + my_i);
                 double pw[3];
-                xform_point(Ts, p.x, p.y, p.z, pw);
+                xform_point(Tx, p.x, p.y, p.z, pw);
                 const float qx = (float)pw[0], qy = (float)pw[1], qz = (float)pw[2];
                 if (sharded) {
                     const float v = P.shard_axis == 0 ? qx : (P.shard_axis == 1 ? qy : qz);
@@ -420,7 +499,7 @@ __global__ void __launch_bounds__(RM_THREADS, RM_BLOCKS_PER_SM)
         const int i = direct ? c0 + sl : own_list[sl];
         const float4 p = __ldg(P.src + i);
         double pw[3];
-        xform_point(Ts, p.x, p.y, p.z, pw);
+        xform_point(Tx, p.x, p.y, p.z, pw);
         const float qx = (float)pw[0], qy = (float)pw[1], qz = (float)pw[2];
         // What is remembered per source point from the previous pass: its k neighbours (nb_prev) and a lower bound LB on the
         // distance to every OTHER map point (nb_state). The pose update moved the point by delta, so the others are now at
@@ -673,10 +752,14 @@ __global__ void __launch_bounds__(RM_THREADS, RM_BLOCKS_PER_SM)
                     nrm[2] /= len;
                     if (lane == 0) {
                         double* s = scr[w][0];
-                        double pxn[3];
-                        cross3(pw, nrm, pxn);
-                        s[0] = pxn[0]; s[1] = pxn[1]; s[2] = pxn[2];
-                        s[3] = nrm[0]; s[4] = nrm[1]; s[5] = nrm[2];
+                        if (CAN_INTERP && interp) {
+                            interp_row(nrm, pw, Ts, Tss, Ms, P.interp_s, s);
+                        } else {
+                            double pxn[3];
+                            cross3(pw, nrm, pxn);
+                            s[0] = pxn[0]; s[1] = pxn[1]; s[2] = pxn[2];
+                            s[3] = nrm[0]; s[4] = nrm[1]; s[5] = nrm[2];
+                        }
                         s[6] = ((pw[0] - j3[0]) * nrm[0] + (pw[1] - j3[1]) * nrm[1]) + (pw[2] - j3[2]) * nrm[2];
                         s[7] = 1.0; s[8] = 0.0;
                     }
@@ -710,6 +793,7 @@ __global__ void __launch_bounds__(RM_THREADS, RM_BLOCKS_PER_SM)
                             s[j] = (Dr[0] * Px[j] + Dr[1] * Px[3 + j]) + Dr[2] * Px[6 + j];
                             s[3 + j] = Dr[j];
                             s[6] = nuj / L;
+                            if (CAN_INTERP && interp && j == 2) interp_row(Dr, pw, Ts, Tss, Ms, P.interp_s, s);  // overwrites s[0..5]
                         }
                         s[7] = lane == 0 ? 1.0 : 0.0;
                         s[8] = 0.0;
@@ -1056,6 +1140,7 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
     P.trans_eps = o->trans_eps;
     P.mse_abs_eps = o->mse_abs_eps;
     P.plane_thresh = o->plane_thresh;
+    P.interp_s = (o->interp_s > 0.0 && (o->residual == ICP4R_P2LINE || o->residual == ICP4R_P2PLANE_3PT)) ? o->interp_s : 1.0;
     P.dump_pose = dump ? dump->pose : nullptr;
     P.dump_acc = dump ? dump->acc : nullptr;
     P.dump_idx = dump ? dump->idx : nullptr;
@@ -1076,7 +1161,7 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
     if (c->use_hints) {
         CKS(reserve_grow(c, c->d_nbprev, (size_t)n * ICP4R_MAX_K * sizeof(int32_t)));
         P.nb_prev = c->d_nbprev.as<int32_t>();
-        if (c->use_lb && !gicp && o->max_iterations < 4096) {
+        if (c->use_lb && !gicp && o->max_iterations < 4096 && P.interp_s == 1.0) {
             const void* before = c->d_nbstate.p;
             CKS(reserve_grow(c, c->d_nbstate, (size_t)std::max(n, 1) * sizeof(NbState)));
             if (c->d_nbstate.p != before) CK(cudaMemsetAsync(c->d_nbstate.p, 0xFF, c->d_nbstate.cap, c->stream));
@@ -1328,6 +1413,7 @@ int accumulate_slab(Ctx* c, Map& mp, const float4* d_src, int n, const icp4r_opt
     P.max_iterations = 1;
     gate_params(o->max_corr_dist, &P.gate_f, &P.gate_r);
     P.plane_thresh = o->plane_thresh;
+    P.interp_s = (o->interp_s > 0.0 && (o->residual == ICP4R_P2LINE || o->residual == ICP4R_P2PLANE_3PT)) ? o->interp_s : 1.0;
     P.map_sorted = mp.grid.sorted;
     P.map_cell_start = mp.grid.cell_start;
     P.map_coarse = mp.grid.coarse;
@@ -1397,7 +1483,8 @@ int register_scans_against_map(Ctx* c, Map& mp, const float4* d_src, const int32
         CKS(reserve_grow(c, c->bm_res, (size_t)B * sizeof(ResultBlock)));
         CKS(reserve_grow(c, c->bm_partials, (size_t)B * blocks * ICP4R_ACC_LEN * sizeof(double)));
         CKS(reserve_grow(c, c->d_nbprev, (size_t)off_host[s0 + B] * ICP4R_MAX_K * sizeof(int32_t)));
-        const bool use_lb = c->use_hints && c->use_lb && o->max_iterations < 4096 && (nmax + blocks - 1) / blocks >= 2 * wpb;
+        const bool interp = o->interp_s > 0.0 && o->interp_s != 1.0 && (o->residual == ICP4R_P2LINE || o->residual == ICP4R_P2PLANE_3PT);
+        const bool use_lb = c->use_hints && c->use_lb && !interp && o->max_iterations < 4096 && (nmax + blocks - 1) / blocks >= 2 * wpb;
         if (use_lb) {
             const void* before = c->d_nbstate.p;
             CKS(reserve_grow(c, c->d_nbstate, (size_t)std::max(off_host[s0 + B], 1) * sizeof(NbState)));
@@ -1421,6 +1508,8 @@ int register_scans_against_map(Ctx* c, Map& mp, const float4* d_src, const int32
             P.trans_eps = o->trans_eps;
             P.mse_abs_eps = o->mse_abs_eps;
             P.plane_thresh = o->plane_thresh;
+            P.interp_s = (o->interp_s > 0.0 && (o->residual == ICP4R_P2LINE || o->residual == ICP4R_P2PLANE_3PT)) ? o->interp_s : 1.0;
+    P.interp_s = (o->interp_s > 0.0 && (o->residual == ICP4R_P2LINE || o->residual == ICP4R_P2PLANE_3PT)) ? o->interp_s : 1.0;
             P.map_sorted = mp.grid.sorted;
             P.map_cell_start = mp.grid.cell_start;
             P.map_coarse = mp.grid.coarse;

@@ -63,8 +63,8 @@ typedef enum icp4r_residual {
                               pcl::IterativeClosestPoint does at iterative_closest_point.cpp:510-514     */
     ICP4R_P2P_GN = 1,      /* LidarDistanceFactor (radarFactor.hpp:140-171), Gauss-Newton 6x6           */
     ICP4R_P2PLANE_KNN = 2, /* LidarPlaneNormFactor (radarFactor.hpp:105-137), plane from the k neighbours */
-    ICP4R_P2LINE = 3,      /* RadarEdgeFactor (radarFactor.hpp:11-54), line through the 2 nearest, s = 1  */
-    ICP4R_P2PLANE_3PT = 5, /* LidarPlaneFactor (radarFactor.hpp:56-103), plane through the 3 nearest points, s = 1 */
+    ICP4R_P2LINE = 3,      /* RadarEdgeFactor (radarFactor.hpp:11-54), line through the 2 nearest, s = opts.interp_s */
+    ICP4R_P2PLANE_3PT = 5, /* LidarPlaneFactor (radarFactor.hpp:56-103), plane through the 3 nearest points, s = opts.interp_s */
     ICP4R_GICP = 4         /* fast_gicp cost (radar_odometry.cpp:399-405): k-NN plane-regularised covariances of both
                               clouds, 1-NN Mahalanobis residual, Levenberg-Marquardt; opts.k = CorrespondenceRandomness */
 } icp4r_residual;
@@ -80,6 +80,10 @@ typedef struct icp4r_opts {
     double mse_abs_eps;      /* early exit (P2P_SVD): |mse_i - mse_{i-1}| < mse_abs_eps (PCL 1e-12) */
     double plane_thresh;     /* P2PLANE_KNN: all k neighbours within this distance of the plane (0.2) */
     double T0[16];           /* initial guess, row-major */
+    double interp_s;         /* P2LINE / P2PLANE_3PT: the interpolation ratio s of RadarEdgeFactor / LidarPlaneFactor
+                                (radarFactor.hpp:26-32,78-84): the residual is evaluated at slerp(I, q, s) p + s t instead of
+                                q p + t (A-LOAM's motion-distortion model; one s per call). 1 (default) = the full pose;
+                                values <= 0 are treated as 1. Ignored by the other kinds. */
 } icp4r_opts;
 
 typedef struct icp4r_result {

@@ -31,6 +31,7 @@ class OrcOpts(C.Structure):
         ("mse_abs_eps", C.c_double),
         ("plane_thresh", C.c_double),
         ("T0", C.c_double * 16),
+        ("interp_s", C.c_double),
     ]
 
 

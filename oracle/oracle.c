@@ -34,6 +34,7 @@ void orc_default_opts(orc_opts* o) {
     o->mse_abs_eps = 1e-12;
     o->plane_thresh = 0.2;
     for (int i = 0; i < 16; ++i) o->T0[i] = (i % 5 == 0) ? 1.0 : 0.0;
+    o->interp_s = 1.0;
 }
 
 /* ------------------------------------------------------------------ kNN ---------------------------- */
@@ -519,6 +520,124 @@ static int contribute(int residual, int k, double plane_thresh, const double pw[
     return 0;
 }
 
+/* ---- RadarEdgeFactor / LidarPlaneFactor with an interpolation ratio s != 1 (radarFactor.hpp:26-32,78-84) ------------
+ * The functors place the point with slerp(I, q, s) p + s t. The loop here follows them literally: the pose is converted to
+ * the functor's (q = x,y,z,w ; t) parameters, the RESIDUAL is the functor restatement above (orc_res_edge /
+ * orc_res_plane), and the JACOBIAN with respect to the left perturbation T <- exp(xi^) T is taken by central differences
+ * of that functor (h = 1e-6: error ~1e-10 relative) — deliberately not the closed form the device kernel uses. */
+static void pose_to_qt(const double T[16], double q[4], double t[3]) {
+    const double m00 = T[0], m01 = T[1], m02 = T[2], m10 = T[4], m11 = T[5], m12 = T[6], m20 = T[8], m21 = T[9], m22 = T[10];
+    const double tr = m00 + m11 + m22;
+    double x, y, z, w;
+    if (tr > 0.0) {
+        const double S = sqrt(tr + 1.0) * 2.0;
+        w = 0.25 * S;
+        x = (m21 - m12) / S;
+        y = (m02 - m20) / S;
+        z = (m10 - m01) / S;
+    } else if (m00 > m11 && m00 > m22) {
+        const double S = sqrt(1.0 + m00 - m11 - m22) * 2.0;
+        w = (m21 - m12) / S;
+        x = 0.25 * S;
+        y = (m01 + m10) / S;
+        z = (m02 + m20) / S;
+    } else if (m11 > m22) {
+        const double S = sqrt(1.0 + m11 - m00 - m22) * 2.0;
+        w = (m02 - m20) / S;
+        x = (m01 + m10) / S;
+        y = 0.25 * S;
+        z = (m12 + m21) / S;
+    } else {
+        const double S = sqrt(1.0 + m22 - m00 - m11) * 2.0;
+        w = (m10 - m01) / S;
+        x = (m02 + m20) / S;
+        y = (m12 + m21) / S;
+        z = 0.25 * S;
+    }
+    const double nq = sqrt(x * x + y * y + z * z + w * w);
+    q[0] = x / nq;
+    q[1] = y / nq;
+    q[2] = z / nq;
+    q[3] = w / nq;
+    t[0] = T[3];
+    t[1] = T[7];
+    t[2] = T[11];
+}
+
+/* the pose the functors place a point with: (slerp(I, q, s), s t) as a 4x4 matrix */
+void orc_interp_pose(const double T[16], double s, double Ts[16]) {
+    double q[4], t[3], qs[4];
+    pose_to_qt(T, q, t);
+    slerp_from_identity(s, q, qs);
+    const double e[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int c = 0; c < 3; ++c) {
+        double col[3];
+        quat_rotate(qs, e[c], col);
+        Ts[0 + c] = col[0];
+        Ts[4 + c] = col[1];
+        Ts[8 + c] = col[2];
+    }
+    Ts[3] = s * t[0];
+    Ts[7] = s * t[1];
+    Ts[11] = s * t[2];
+    Ts[12] = Ts[13] = Ts[14] = 0.0;
+    Ts[15] = 1.0;
+}
+
+/* residual rows (1 for the plane, 3 for the edge) of source point p under pose T */
+static int interp_residual(int residual, const double T[16], double s, const double p[3], const float* tgt, const int32_t* nn, double r[3]) {
+    double q[4], t[3];
+    pose_to_qt(T, q, t);
+    if (residual == ORC_P2PLANE_3PT) {
+        const float *fj = tgt + 4 * (size_t)nn[0], *fl = tgt + 4 * (size_t)nn[1], *fm = tgt + 4 * (size_t)nn[2];
+        const double j[3] = {fj[0], fj[1], fj[2]}, l[3] = {fl[0], fl[1], fl[2]}, m[3] = {fm[0], fm[1], fm[2]};
+        orc_res_plane(q, t, p, j, l, m, s, r);
+        return 1;
+    }
+    const float *fa = tgt + 4 * (size_t)nn[0], *fb = tgt + 4 * (size_t)nn[1];
+    const double a[3] = {fa[0], fa[1], fa[2]}, b[3] = {fb[0], fb[1], fb[2]};
+    orc_res_edge(q, t, p, a, b, s, r);
+    return 3;
+}
+
+static int contribute_interp(int residual, const double T[16], double s, const float* psrc, const float* tgt, const int32_t* nn, int found,
+                             double* acc) {
+    const int need = residual == ORC_P2PLANE_3PT ? 3 : 2;
+    if (found < need) return 0;
+    if (residual == ORC_P2PLANE_3PT) { /* degenerate plane: the three points are collinear */
+        const float *fj = tgt + 4 * (size_t)nn[0], *fl = tgt + 4 * (size_t)nn[1], *fm = tgt + 4 * (size_t)nn[2];
+        const double jl[3] = {(double)fj[0] - fl[0], (double)fj[1] - fl[1], (double)fj[2] - fl[2]};
+        const double jm[3] = {(double)fj[0] - fm[0], (double)fj[1] - fm[1], (double)fj[2] - fm[2]};
+        double n[3];
+        cross3(jl, jm, n);
+        if (!(sqrt((n[0] * n[0] + n[1] * n[1]) + n[2] * n[2]) > 0.0)) return 0;
+    } else {
+        const float *fa = tgt + 4 * (size_t)nn[0], *fb = tgt + 4 * (size_t)nn[1];
+        const double ba[3] = {(double)fb[0] - fa[0], (double)fb[1] - fa[1], (double)fb[2] - fa[2]};
+        if (!(sqrt((ba[0] * ba[0] + ba[1] * ba[1]) + ba[2] * ba[2]) > 0.0)) return 0;
+    }
+    const double p[3] = {psrc[0], psrc[1], psrc[2]};
+    double r0[3];
+    const int rows = interp_residual(residual, T, s, p, tgt, nn, r0);
+    double J[3][6];
+    const double h = 1e-6;
+    for (int i = 0; i < 6; ++i) {
+        double xi[6] = {0, 0, 0, 0, 0, 0}, D[16], Tp[16], Tm[16], rp[3], rm[3];
+        xi[i] = h;
+        orc_se3_exp(xi, D);
+        orc_mat4_mul(D, T, Tp);
+        xi[i] = -h;
+        orc_se3_exp(xi, D);
+        orc_mat4_mul(D, T, Tm);
+        interp_residual(residual, Tp, s, p, tgt, nn, rp);
+        interp_residual(residual, Tm, s, p, tgt, nn, rm);
+        for (int k = 0; k < rows; ++k) J[k][i] = (rp[k] - rm[k]) / (2.0 * h);
+    }
+    for (int k = 0; k < rows; ++k) acc_gn(acc, J[k], r0[k]);
+    acc[28] += 1.0;
+    return 1;
+}
+
 static int knn_k_for(const orc_opts* o) {
     switch (o->residual) {
         case ORC_P2P_SVD:
@@ -543,13 +662,21 @@ int orc_accumulate(const float* src, int n, const float* tgt, int m, orc_knn_fn 
     int32_t* idx = (int32_t*)malloc(sizeof(int32_t) * (size_t)n * k);
     float* d2 = (float*)malloc(sizeof(float) * (size_t)n * k);
     int32_t* fnd = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
-    orc_transform(T, src, n, q, pw);
+    const int interp = (o->residual == ORC_P2LINE || o->residual == ORC_P2PLANE_3PT) && o->interp_s > 0.0 && o->interp_s != 1.0;
+    double Tplace[16];
+    if (interp) orc_interp_pose(T, o->interp_s, Tplace);
+    else memcpy(Tplace, T, sizeof(Tplace));
+    orc_transform(Tplace, src, n, q, pw);
     knn(ctx, q, n, k, o->max_corr_dist, idx, d2, fnd);
     memset(acc, 0, sizeof(double) * ORC_ACC_LEN);
     int used = 0;
-    for (int i = 0; i < n; ++i)
-        used += contribute(o->residual, k, o->plane_thresh, pw + 3 * (size_t)i, tgt, idx + (size_t)i * k,
-                           d2 + (size_t)i * k, fnd[i], acc);
+    for (int i = 0; i < n; ++i) {
+        if (interp)
+            used += contribute_interp(o->residual, T, o->interp_s, src + 4 * (size_t)i, tgt, idx + (size_t)i * k, fnd[i], acc);
+        else
+            used += contribute(o->residual, k, o->plane_thresh, pw + 3 * (size_t)i, tgt, idx + (size_t)i * k,
+                               d2 + (size_t)i * k, fnd[i], acc);
+    }
     if (idx_out) memcpy(idx_out, idx, sizeof(int32_t) * (size_t)n * k);
     free(q);
     free(pw);

@@ -62,6 +62,34 @@ def test_register_pair_matches_oracle(pkg, O, handle, name, k, gate):
     assert abs(res.fitness - ro.fitness) <= 1e-6 * max(ro.fitness, 1e-12)
 
 
+@pytest.mark.parametrize("name,k,gate,s", [("P2LINE", 2, 3.0, 0.5), ("P2PLANE_3PT", 3, 2.0, 0.5), ("P2PLANE_3PT", 3, 2.5, 0.25), ("P2LINE", 2, 3.0, 1.0)])
+def test_interpolated_functors_match_oracle(pkg, O, handle, name, k, gate, s):
+    """RadarEdgeFactor / LidarPlaneFactor with their interpolation ratio s (radarFactor.hpp:26-32,78-84): the point is placed
+    with slerp(I, q, s) p + s t. Device: closed-form Jacobian (left Jacobians of SO(3)); oracle: the functor restated
+    literally and differentiated numerically. Correspondences bit-exact, J^T J / J^T r to 1e-5, final pose to 1e-4."""
+    kind = getattr(pkg, name)
+    src, tgt, _ = pkg.synth.frame_pair(1001, 1024, 4000, extent=40.0)
+    T0 = pkg.synth.se3(0.02, 0.004, -0.003, (0.1, -0.05, 0.02))
+    iters = 8
+    o = pkg.default_opts(residual=kind, k=k, max_iterations=iters, max_corr_dist=gate, interp_s=s, T0=T0)
+    oo = O.default_opts(residual=kind, k=k, max_iterations=iters, max_corr_dist=gate, interp_s=s, T0=T0)
+    T, res, bufs = handle.register(src, tgt, o, dump=True)
+    To, ro, _ = O.register(src, tgt, oo)
+    assert res.iterations == ro.iterations == iters
+    check_dumps(O, kind, k, src, tgt, oo, bufs, res.iterations)
+    et, er = pose_err(T, To)
+    assert et <= POSE_TOL_T and er <= POSE_TOL_R, (et, er)
+    assert res.n_corr == ro.n_corr
+    # the map-resident and batched-scan entry points take the same option
+    handle.map_build(tgt)
+    T2, r2, _ = handle.register_map(src, o)
+    assert np.abs(T2 - T).max() <= 1e-9 and r2.n_corr == res.n_corr
+    if s != 1.0:
+        o1 = pkg.default_opts(residual=kind, k=k, max_iterations=iters, max_corr_dist=gate, T0=T0)
+        T1, _r1, _ = handle.register_map(src, o1)
+        assert np.abs(T1 - T).max() > 1e-4   # s really changes the problem
+
+
 def test_c1_config(pkg, O, handle):
     """BASELINE config 1: 1,024-pt frame pair, point-to-point, 30 iterations, ungated"""
     src, tgt, _ = pkg.synth.frame_pair(1001, 1024)
@@ -162,6 +190,30 @@ def test_batch_ragged(pkg, O, handle):
             assert et <= POSE_TOL_T and er <= POSE_TOL_R, (i, et, er)
             if ro.n_fitness:
                 assert abs(rb["fitness"][i] - ro.fitness) <= 1e-6 * ro.fitness
+
+
+def test_batch_pairs_larger_than_shared_memory(pkg, O, handle):
+    """pairs above one SM's shared memory (here 9,000 + 9,000 points) take the map path pair by pair instead of failing"""
+    import torch
+    srcs, tgts = [], []
+    for i in range(3):
+        s, t, _ = pkg.synth.frame_pair(300 + i, 9000 if i == 1 else 500, 9000 if i == 1 else 700, extent=60.0)
+        srcs.append(s)
+        tgts.append(t)
+    soff = np.concatenate([[0], np.cumsum([len(s) for s in srcs])]).astype(np.int32)
+    toff = np.concatenate([[0], np.cumsum([len(t) for t in tgts])]).astype(np.int32)
+    S, Tg = np.concatenate(srcs), np.concatenate(tgts)
+    o = pkg.default_opts(residual=pkg.P2P_SVD, max_iterations=6)
+    oo = O.default_opts(residual=O.P2P_SVD, max_iterations=6)
+    Tb, rb = handle.register_batch(S, soff, Tg, toff, o)
+    Td, rd = handle.register_batch(torch.from_numpy(S).cuda(), torch.from_numpy(soff).cuda(), torch.from_numpy(Tg).cuda(),
+                                   torch.from_numpy(toff).cuda(), o)
+    assert np.array_equal(Td.cpu().numpy().reshape(-1, 4, 4), Tb)
+    for i in range(3):
+        To, ro, _ = O.register(srcs[i], tgts[i], oo)
+        et, er = pose_err(Tb[i], To)
+        assert et <= POSE_TOL_T and er <= POSE_TOL_R, (i, et, er)
+        assert rb["n_corr"][i] == ro.n_corr and rb["iterations"][i] == ro.iterations
 
 
 def test_transform_points(pkg, O, handle):
