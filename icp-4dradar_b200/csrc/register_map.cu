@@ -247,11 +247,16 @@ __global__ void __launch_bounds__(RM_THREADS, RM_BLOCKS_PER_SM)
     __shared__ WarpSegs segs[RM_WARPS];
     __shared__ double scr[RM_WARPS][3][12];  // per-warp operands of the lane products (up to 3 residual rows)
     constexpr bool PARKED = (!FIT && KIND == ICP4R_P2PLANE_KNN && K <= 8);  // plane fits done up to 32 points at a time, one per lane
-    constexpr int PARK = RM_PARK;
-    // per warp: PARK rows of 8 doubles (the residual row of a parked point) + PARK x (K + 1) ints (its neighbours + itself)
+    // per warp: PARK rows of 8 doubles (the residual row of a parked point) + PARK x (K + 1) ints (its neighbours + itself).
+    // The flavour with the lane-parallel phase parks up to 32 points per warp in dynamic shared memory; the lean flavour
+    // parks 8 in static arrays (constant addresses: the two base pointers cost it four registers it does not have).
+    constexpr int PARK = LB ? RM_PARK : 8;
     extern __shared__ __align__(16) unsigned char dyn_smem[];
-    double (*scrq)[PARK][8] = reinterpret_cast<double (*)[PARK][8]>(dyn_smem);
-    int (*nbq)[PARK][K + 1] = reinterpret_cast<int (*)[PARK][K + 1]>(dyn_smem + (size_t)(blockDim.x >> 5) * PARK * 8 * sizeof(double));
+    __shared__ double scrq_s[(PARKED && !LB) ? RM_WARPS : 1][8][8];
+    __shared__ int nbq_s[(PARKED && !LB) ? RM_WARPS : 1][8][K + 1];
+    double (*scrq)[PARK][8] = LB ? reinterpret_cast<double (*)[PARK][8]>(dyn_smem) : reinterpret_cast<double (*)[PARK][8]>(&scrq_s[0][0][0]);
+    int (*nbq)[PARK][K + 1] = LB ? reinterpret_cast<int (*)[PARK][K + 1]>(dyn_smem + (size_t)(blockDim.x >> 5) * PARK * 8 * sizeof(double))
+                                 : reinterpret_cast<int (*)[PARK][K + 1]>(&nbq_s[0][0][0]);
     __shared__ double red[RM_WARPS][ICP4R_ACC_LEN];
     __shared__ double tot[ICP4R_ACC_LEN];
     __shared__ double Ts[16];
@@ -374,129 +379,11 @@ __global__ void __launch_bounds__(RM_THREADS, RM_BLOCKS_PER_SM)
     // warp that strides over ALL points would find a random share of its points owned (the slowest warp sets the
     // kernel time), so each block first compacts the owned points of its contiguous chunk into an ordered list
     // (ballot + prefix: deterministic) and its warps stride over that list.
-    // Work distribution. Every block owns a contiguous chunk of the source points and walks it blockDim.x points at a time:
-    //   phase A  one point per THREAD: is the point this block's business at all (slab-sharded maps: the rank whose slab
-    //            holds the transformed point owns it), and — P2PLANE_KNN after the first iteration — are its remembered
-    //            neighbours provably still the k nearest (see the per-point path below)? Such points skip the search;
-    //            their planes are fitted up to 32 at a time, one per lane, by their own warp.
-    //   phase B  the remaining points are compacted, in order (ballot + prefix: deterministic), into a block-wide list
-    //            and the warps stride over it one point per WARP: search, plane fit (parked), accumulation.
-    // A static split of ALL points over the warps made the slowest warp (the one with the most searches) set the kernel
-    // time: 30 % of the warp time of the batched C2 launch was spent at the block barrier (profiles/).
-    const bool sharded = P.shard_axis >= 0;
-    const int per = (n + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int cbeg = min(n, (int)blockIdx.x * per), cend = min(n, cbeg + per);
-    // with only a point or two per warp (a single scan spread over the whole GPU) the lane-parallel phase would be one
-    // more serial step on the iteration's latency chain: the per-point path does the same test inline then
-    const bool lane_phase = LB && PARKED && P.nb_state != nullptr && iter > 0 && per >= 2 * nwb;
-    for (int c0 = cbeg; c0 < cend; c0 += (int)blockDim.x) {
-        const int my_i = (c0 + tid < cend) ? c0 + tid : -1;
-        bool need = my_i >= 0;
-        if (lane_phase || sharded) {
-            const int kp = P.k;
-            bool ok = false;
-            int nbv[K];
-            float lb_new = 0.0f;
-            if (need) {
-                const float4 p = __ldg(P.src + my_i);
-                double pw[3];
-                xform_point(Tx, p.x, p.y, p.z, pw);
-                const float qx = (float)pw[0], qy = (float)pw[1], qz = (float)pw[2];
-                if (sharded) {
-                    const float v = P.shard_axis == 0 ? qx : (P.shard_axis == 1 ? qy : qz);
-                    need = (v >= P.slab_lo) && (v < P.slab_hi);
-                }
-                if (need && lane_phase) {
-                    const float margin_q = fmaxf(g.margin, 9.5367431640625e-7f * fmaxf(fabsf(qx), fmaxf(fabsf(qy), fabsf(qz))));
-                    const int32_t* nbp = P.nb_prev + (size_t)my_i * K;
-                    uint64_t key[K];
-                    bool all_valid = true;
-                    float hmax = 0.0f;
-#pragma unroll
-                    for (int j = 0; j < K; ++j) {
-                        key[j] = KEY_EMPTY;
-                        if (j < kp) {
-                            const int pj = __ldcg(nbp + j);
-                            if (pj < 0) {
-                                all_valid = false;
-                            } else {
-                                const float4 c = __ldg(pts + pj);
-                                const float d = dist2_exact(qx, qy, qz, c.x, c.y, c.z);
-                                hmax = fmaxf(hmax, d);
-                                if (!(d <= P.gate_f)) all_valid = false;  // also catches NaN
-                                key[j] = pack_key(d, pj);
-                            }
-                        }
-                    }
-                    if (all_valid) {
-                        const float2 sv = __ldcg(reinterpret_cast<const float2*>(P.nb_state + my_i));
-                        if (__float_as_int(sv.y) == P.epoch * 4096 + s_last_pass) {
-                            const float ex = __fmaf_rn(s_dA[0], qx, __fmaf_rn(s_dA[1], qy, __fmaf_rn(s_dA[2], qz, s_dA[3])));
-                            const float ey = __fmaf_rn(s_dA[4], qx, __fmaf_rn(s_dA[5], qy, __fmaf_rn(s_dA[6], qz, s_dA[7])));
-                            const float ez = __fmaf_rn(s_dA[8], qx, __fmaf_rn(s_dA[9], qy, __fmaf_rn(s_dA[10], qz, s_dA[11])));
-                            const float delta = sqrtf(__fmaf_rn(ex, ex, __fmaf_rn(ey, ey, ez * ez))) * 1.0001f + 2.0f * margin_q;
-                            lb_new = sv.x - delta;
-                            ok = sqrtf(hmax) * 1.000001f + margin_q < lb_new;
-                        }
-                    }
-                    if (ok) {
-                        // ascending (d2, index): insertion network over the K packed keys in registers
-#pragma unroll
-                        for (int a2 = 1; a2 < K; ++a2)
-#pragma unroll
-                            for (int b2 = a2; b2 > 0; --b2) {
-                                const uint64_t lo = key[b2 - 1] < key[b2] ? key[b2 - 1] : key[b2];
-                                const uint64_t hi = key[b2 - 1] < key[b2] ? key[b2] : key[b2 - 1];
-                                key[b2 - 1] = lo;
-                                key[b2] = hi;
-                            }
-#pragma unroll
-                        for (int j = 0; j < K; ++j) nbv[j] = j < kp ? key_idx(key[j]) : -1;
-                        need = false;
-                    }
-                }
-            }
-            if (PARKED) {
-                const unsigned okm = __ballot_sync(FULL, ok);
-                if (okm != 0u) {
-                    if (ok) {
-                        const int slot = __popc(okm & ((1u << lane) - 1u));  // parked == 0 here: phase B flushes before it ends
-                        int32_t* nbp = P.nb_prev + (size_t)my_i * K;
-#pragma unroll
-                        for (int j = 0; j < K; ++j)
-                            if (j < kp) {
-                                nbq[w][slot][j] = nbv[j];
-                                nbp[j] = nbv[j];
-                                if (P.dump_idx) P.dump_idx[((size_t)iter * n + my_i) * kp + j] = nbv[j];
-                            }
-                        nbq[w][slot][K] = my_i;
-                        __stcg(reinterpret_cast<float2*>(P.nb_state + my_i), make_float2(lb_new, __int_as_float(P.epoch * 4096 + iter)));
-                    }
-                    parked = __popc(okm);
-                    st_settled += (lane == 0) ? __popc(okm) : 0;
-                    flush_parked();
-                }
-            }
-        }
-        const bool direct = !(lane_phase || sharded);  // every point of the round takes the per-point path: no list needed
-        if (!direct) {   // the block's list of points that need the per-point path, in point order
-            const unsigned bal = __ballot_sync(FULL, need);
-            __syncthreads();  // the previous round's list is no longer read
-            if (lane == 0) own_cnt[w] = __popc(bal);
-            __syncthreads();
-            int before = 0;
-            for (int j = 0; j < w; ++j) before += own_cnt[j];
-            if (need) own_list[before + __popc(bal & ((1u << lane) - 1u))] = my_i;
-            if (tid == 0) {
-                int t = 0;
-                for (int j = 0; j < nwb; ++j) t += own_cnt[j];
-                own_n = t;
-            }
-            __syncthreads();
-        }
-    const int list_n = direct ? min((int)blockDim.x, cend - c0) : own_n;
-    for (int sl = w; sl < list_n; sl += nwb) {
-        const int i = direct ? c0 + sl : own_list[sl];
+    // with only a point or two per warp the lane-parallel phase would be one more serial step on the iteration's latency
+    // chain: the per-point path does the same test inline then
+    const bool lane_phase = LB && PARKED && P.nb_state != nullptr && iter > 0 && (n + (int)gridDim.x - 1) / (int)gridDim.x >= 2 * nwb;
+    // ---- one source point, start to finish, by one warp ---------------------------------------------------------------
+    auto per_point = [&](const int i) {
         const float4 p = __ldg(P.src + i);
         double pw[3];
         xform_point(Tx, p.x, p.y, p.z, pw);
@@ -807,8 +694,133 @@ __global__ void __launch_bounds__(RM_THREADS, RM_BLOCKS_PER_SM)
             for (int r3 = 0; r3 < rows; ++r3) acc += scr[w][r3][ia] * scr[w][r3][ib];
             __syncwarp();
         }
-    }
+    };
+
+    if constexpr (!LB) {
+        // lean flavour (a single small scan, never sharded): the warps stride over the points, nothing else
+        for (int i = blockIdx.x * nwb + w; i < n; i += (int)gridDim.x * nwb) per_point(i);
+    } else {
+    // Work distribution. Every block owns a contiguous chunk of the source points and walks it blockDim.x points at a time:
+    //   phase A  one point per THREAD: is the point this block's business at all (slab-sharded maps: the rank whose slab
+    //            holds the transformed point owns it), and — P2PLANE_KNN after the first iteration — are its remembered
+    //            neighbours provably still the k nearest (see the per-point path below)? Such points skip the search;
+    //            their planes are fitted up to 32 at a time, one per lane, by their own warp.
+    //   phase B  the remaining points are compacted, in order (ballot + prefix: deterministic), into a block-wide list
+    //            and the warps stride over it one point per WARP: search, plane fit (parked), accumulation.
+    // A static split of ALL points over the warps made the slowest warp (the one with the most searches) set the kernel
+    // time: 30 % of the warp time of the batched C2 launch was spent at the block barrier (profiles/).
+    const bool sharded = P.shard_axis >= 0;
+    const int per = (n + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int cbeg = min(n, (int)blockIdx.x * per), cend = min(n, cbeg + per);
+    for (int c0 = cbeg; c0 < cend; c0 += (int)blockDim.x) {
+        const int my_i = (c0 + tid < cend) ? c0 + tid : -1;
+        bool need = my_i >= 0;
+        if (lane_phase || sharded) {
+            const int kp = P.k;
+            bool ok = false;
+            int nbv[K];
+            float lb_new = 0.0f;
+            if (need) {
+                const float4 p = __ldg(P.src + my_i);
+                double pw[3];
+                xform_point(Tx, p.x, p.y, p.z, pw);
+                const float qx = (float)pw[0], qy = (float)pw[1], qz = (float)pw[2];
+                if (sharded) {
+                    const float v = P.shard_axis == 0 ? qx : (P.shard_axis == 1 ? qy : qz);
+                    need = (v >= P.slab_lo) && (v < P.slab_hi);
+                }
+                if (need && lane_phase) {
+                    const float margin_q = fmaxf(g.margin, 9.5367431640625e-7f * fmaxf(fabsf(qx), fmaxf(fabsf(qy), fabsf(qz))));
+                    const int32_t* nbp = P.nb_prev + (size_t)my_i * K;
+                    uint64_t key[K];
+                    bool all_valid = true;
+                    float hmax = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        key[j] = KEY_EMPTY;
+                        if (j < kp) {
+                            const int pj = __ldcg(nbp + j);
+                            if (pj < 0) {
+                                all_valid = false;
+                            } else {
+                                const float4 c = __ldg(pts + pj);
+                                const float d = dist2_exact(qx, qy, qz, c.x, c.y, c.z);
+                                hmax = fmaxf(hmax, d);
+                                if (!(d <= P.gate_f)) all_valid = false;  // also catches NaN
+                                key[j] = pack_key(d, pj);
+                            }
+                        }
+                    }
+                    if (all_valid) {
+                        const float2 sv = __ldcg(reinterpret_cast<const float2*>(P.nb_state + my_i));
+                        if (__float_as_int(sv.y) == P.epoch * 4096 + s_last_pass) {
+                            const float ex = __fmaf_rn(s_dA[0], qx, __fmaf_rn(s_dA[1], qy, __fmaf_rn(s_dA[2], qz, s_dA[3])));
+                            const float ey = __fmaf_rn(s_dA[4], qx, __fmaf_rn(s_dA[5], qy, __fmaf_rn(s_dA[6], qz, s_dA[7])));
+                            const float ez = __fmaf_rn(s_dA[8], qx, __fmaf_rn(s_dA[9], qy, __fmaf_rn(s_dA[10], qz, s_dA[11])));
+                            const float delta = sqrtf(__fmaf_rn(ex, ex, __fmaf_rn(ey, ey, ez * ez))) * 1.0001f + 2.0f * margin_q;
+                            lb_new = sv.x - delta;
+                            ok = sqrtf(hmax) * 1.000001f + margin_q < lb_new;
+                        }
+                    }
+                    if (ok) {
+                        // ascending (d2, index): insertion network over the K packed keys in registers
+#pragma unroll
+                        for (int a2 = 1; a2 < K; ++a2)
+#pragma unroll
+                            for (int b2 = a2; b2 > 0; --b2) {
+                                const uint64_t lo = key[b2 - 1] < key[b2] ? key[b2 - 1] : key[b2];
+                                const uint64_t hi = key[b2 - 1] < key[b2] ? key[b2] : key[b2 - 1];
+                                key[b2 - 1] = lo;
+                                key[b2] = hi;
+                            }
+#pragma unroll
+                        for (int j = 0; j < K; ++j) nbv[j] = j < kp ? key_idx(key[j]) : -1;
+                        need = false;
+                    }
+                }
+            }
+            if (PARKED) {
+                const unsigned okm = __ballot_sync(FULL, ok);
+                if (okm != 0u) {
+                    if (ok) {
+                        const int slot = __popc(okm & ((1u << lane) - 1u));  // parked == 0 here: phase B flushes before it ends
+                        int32_t* nbp = P.nb_prev + (size_t)my_i * K;
+#pragma unroll
+                        for (int j = 0; j < K; ++j)
+                            if (j < kp) {
+                                nbq[w][slot][j] = nbv[j];
+                                nbp[j] = nbv[j];
+                                if (P.dump_idx) P.dump_idx[((size_t)iter * n + my_i) * kp + j] = nbv[j];
+                            }
+                        nbq[w][slot][K] = my_i;
+                        __stcg(reinterpret_cast<float2*>(P.nb_state + my_i), make_float2(lb_new, __int_as_float(P.epoch * 4096 + iter)));
+                    }
+                    parked = __popc(okm);
+                    st_settled += (lane == 0) ? __popc(okm) : 0;
+                    flush_parked();
+                }
+            }
+        }
+        const bool direct = !(lane_phase || sharded);  // every point of the round takes the per-point path: no list needed
+        if (!direct) {   // the block's list of points that need the per-point path, in point order
+            const unsigned bal = __ballot_sync(FULL, need);
+            __syncthreads();  // the previous round's list is no longer read
+            if (lane == 0) own_cnt[w] = __popc(bal);
+            __syncthreads();
+            int before = 0;
+            for (int j = 0; j < w; ++j) before += own_cnt[j];
+            if (need) own_list[before + __popc(bal & ((1u << lane) - 1u))] = my_i;
+            if (tid == 0) {
+                int t = 0;
+                for (int j = 0; j < nwb; ++j) t += own_cnt[j];
+                own_n = t;
+            }
+            __syncthreads();
+        }
+    const int list_n = direct ? min((int)blockDim.x, cend - c0) : own_n;
+    for (int sl = w; sl < list_n; sl += nwb) per_point(direct ? c0 + sl : own_list[sl]);
     flush_parked();  // phase A of the next round parks from slot 0
+    }
     }
 
     flush_parked();
@@ -1017,7 +1029,7 @@ static void launch_iter_mode(Ctx* c, int blocks, int threads, int nscan, const G
     constexpr bool FIT = (MODE == MODE_FITNESS || MODE == MODE_FITNESS_NOFINAL);
     constexpr bool PARKED = (!FIT && KIND == ICP4R_P2PLANE_KNN && K <= 8);
     // dynamic shared memory: the parked plane-fit rows (see reg_iter_kernel); sized for the largest block
-    constexpr size_t per_warp = PARKED ? (size_t)RM_PARK * (8 * sizeof(double) + (K + 1) * sizeof(int)) : 0;
+    constexpr size_t per_warp = (PARKED && LB) ? (size_t)RM_PARK * (8 * sizeof(double) + (K + 1) * sizeof(int)) : 0;
     static bool attr_set = false;
     if (!attr_set && per_warp > 0) {
         cudaFuncSetAttribute(reg_iter_kernel<KIND, K, MODE, LB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * RM_WARPS));
@@ -1168,8 +1180,10 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
             P.nb_state = c->d_nbstate.as<NbState>();
             P.epoch = (++c->reg_epoch) & 0x3FFFF;
         }
-        // worth it only with a few points per warp (see reg_iter_kernel): a single small scan runs the lean flavour
-        if ((n + blocks - 1) / blocks < 2 * wpb) P.nb_state = nullptr;
+        // worth it only with many points per warp (see reg_iter_kernel), measured: 16 per warp (16 C2 scans per launch)
+        // 2.14 -> 1.91 ms, 4 per warp (C5, dense 3-D map) 0.705 -> 0.95 ms (the wider search balls cost more than the
+        // skipped searches save), 1 per warp (C2 single) no difference: the lean flavour below 8 per warp
+        if ((n + blocks - 1) / blocks < 8 * wpb) P.nb_state = nullptr;
         // Sharded maps: a rank only refreshes the entries of the points it owns, so a point that changes owner finds
         // an older entry — still k valid points of this rank's slab, hence still a bound — or none (-1). Entries of
         // an earlier CALL must not survive (the map may have changed since): clear them.
@@ -1204,7 +1218,7 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
         P.corr = c->d_gicp_corr.as<GicpCorr>();
     }
     std::memcpy(hs->T0, o->T0, sizeof(hs->T0));
-    const bool lb = P.nb_state != nullptr;  // which flavour of the iteration kernel runs (see reg_iter_kernel)
+    const bool lb = P.nb_state != nullptr || sharded;  // which flavour of the iteration kernel runs (the lean one has no slab ownership code)
 
     RegParams* d_prm = c->d_params.as<RegParams>();
     RegState* d_st = c->d_state.as<RegState>();
@@ -1435,7 +1449,7 @@ int accumulate_slab(Ctx* c, Map& mp, const float4* d_src, int n, const icp4r_opt
     g.cell_start = nullptr;
     g.coarse = nullptr;
     g.m = 0;
-    if (n > 0) dispatch_iter(c, o->residual, k, MODE_ITER_NOSOLVE, blocks, threads, 1, g, d_prm, d_st, c->d_partials.as<double>(), c->d_res.as<ResultBlock>(), 0);
+    if (n > 0) dispatch_iter(c, o->residual, k, MODE_ITER_NOSOLVE, blocks, threads, 1, g, d_prm, d_st, c->d_partials.as<double>(), c->d_res.as<ResultBlock>(), 0, sharded);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(hs->acc, reinterpret_cast<const char*>(d_st) + offsetof(RegState, acc), sizeof(hs->acc), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -1484,7 +1498,7 @@ int register_scans_against_map(Ctx* c, Map& mp, const float4* d_src, const int32
         CKS(reserve_grow(c, c->bm_partials, (size_t)B * blocks * ICP4R_ACC_LEN * sizeof(double)));
         CKS(reserve_grow(c, c->d_nbprev, (size_t)off_host[s0 + B] * ICP4R_MAX_K * sizeof(int32_t)));
         const bool interp = o->interp_s > 0.0 && o->interp_s != 1.0 && (o->residual == ICP4R_P2LINE || o->residual == ICP4R_P2PLANE_3PT);
-        const bool use_lb = c->use_hints && c->use_lb && !interp && o->max_iterations < 4096 && (nmax + blocks - 1) / blocks >= 2 * wpb;
+        const bool use_lb = c->use_hints && c->use_lb && !interp && o->max_iterations < 4096 && (nmax + blocks - 1) / blocks >= 8 * wpb;
         if (use_lb) {
             const void* before = c->d_nbstate.p;
             CKS(reserve_grow(c, c->d_nbstate, (size_t)std::max(off_host[s0 + B], 1) * sizeof(NbState)));
