@@ -225,12 +225,16 @@ __device__ void write_result(const RegState* st, ResultBlock* out) {
 // LB = false compiles the kernel without the keep-the-neighbours proof (exactly k neighbours ranked, no per-point state):
 // the flavour for a single small scan, where the proof cannot shorten the iteration's latency chain (one point per warp:
 // the slowest point sets the time) and its extra registers only cost.
-template <int KIND, int K, int MODE, bool LB>
+// FLAVOUR 0: lean, 1: with the keep-the-neighbours proof (LB), 2: block-chunked work distribution without the proof
+// (slab-sharded maps: the ownership test needs the per-block lists, the proof does not pay on the maps that get sharded)
+template <int KIND, int K, int MODE, int FLAVOUR>
 __global__ void __launch_bounds__(RM_THREADS, RM_BLOCKS_PER_SM)
     reg_iter_kernel(GridDesc g, const RegParams* __restrict__ prm, RegState* __restrict__ st,
                     double* __restrict__ partials, ResultBlock* __restrict__ out, int iter) {
     constexpr bool FIT = (MODE == MODE_FITNESS || MODE == MODE_FITNESS_NOFINAL);
-    (void)0;
+    constexpr bool LB = FLAVOUR == 1;
+    constexpr bool CHUNKED = FLAVOUR != 0;
+
     constexpr int RK = FIT ? ICP4R_P2P_SVD : KIND;  // residual actually accumulated
     // blockIdx.y selects one of the independent scans of a batched call (each has its own parameters, state,
     // partials and result); single registrations launch with gridDim.y == 1
@@ -696,7 +700,7 @@ __global__ void __launch_bounds__(RM_THREADS, RM_BLOCKS_PER_SM)
         }
     };
 
-    if constexpr (!LB) {
+    if constexpr (!CHUNKED) {
         // lean flavour (a single small scan, never sharded): the warps stride over the points, nothing else
         for (int i = blockIdx.x * nwb + w; i < n; i += (int)gridDim.x * nwb) per_point(i);
     } else {
@@ -1023,49 +1027,53 @@ __global__ void init_state_kernel(RegState* st, const double* T0) {
     }
 }
 
-template <int KIND, int K, int MODE, bool LB>
+template <int KIND, int K, int MODE, int FLAVOUR>
 static void launch_iter_mode(Ctx* c, int blocks, int threads, int nscan, const GridDesc& g, const RegParams* prm, RegState* st, double* partials,
                              ResultBlock* out, int iter) {
     constexpr bool FIT = (MODE == MODE_FITNESS || MODE == MODE_FITNESS_NOFINAL);
     constexpr bool PARKED = (!FIT && KIND == ICP4R_P2PLANE_KNN && K <= 8);
     // dynamic shared memory: the parked plane-fit rows (see reg_iter_kernel); sized for the largest block
+    constexpr bool LB = FLAVOUR == 1;
     constexpr size_t per_warp = (PARKED && LB) ? (size_t)RM_PARK * (8 * sizeof(double) + (K + 1) * sizeof(int)) : 0;
     static bool attr_set = false;
     if (!attr_set && per_warp > 0) {
-        cudaFuncSetAttribute(reg_iter_kernel<KIND, K, MODE, LB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * RM_WARPS));
+        cudaFuncSetAttribute(reg_iter_kernel<KIND, K, MODE, FLAVOUR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * RM_WARPS));
         attr_set = true;
     }
-    reg_iter_kernel<KIND, K, MODE, LB><<<dim3(blocks, nscan), threads, per_warp * (threads / 32), c->stream>>>(g, prm, st, partials, out, iter);
+    reg_iter_kernel<KIND, K, MODE, FLAVOUR><<<dim3(blocks, nscan), threads, per_warp * (threads / 32), c->stream>>>(g, prm, st, partials, out, iter);
+}
+
+template <int KIND, int K, int MODE>
+static void launch_iter_flavour(Ctx* c, int flavour, int blocks, int threads, int nscan, const GridDesc& g, const RegParams* prm, RegState* st,
+                                double* partials, ResultBlock* out, int iter) {
+    // GICP keeps no per-point state between iterations (its LM step moves the pose outside the kernel): no proof flavour
+    if (flavour == 1 && KIND != ICP4R_GICP) launch_iter_mode<KIND, K, MODE, (KIND != ICP4R_GICP ? 1 : 0)>(c, blocks, threads, nscan, g, prm, st, partials, out, iter);
+    else if (flavour == 2) launch_iter_mode<KIND, K, MODE, 2>(c, blocks, threads, nscan, g, prm, st, partials, out, iter);
+    else launch_iter_mode<KIND, K, MODE, 0>(c, blocks, threads, nscan, g, prm, st, partials, out, iter);
 }
 
 template <int KIND, int K>
 static void launch_iter(Ctx* c, int mode, int blocks, int threads, int nscan, const GridDesc& g, const RegParams* prm, RegState* st,
-                        double* partials, ResultBlock* out, int iter, bool lb) {
-    // the proof only exists for the kinds whose loop keeps per-point state (see register_against_map); GICP never does
-    constexpr bool CAN_LB = KIND != ICP4R_GICP;
+                        double* partials, ResultBlock* out, int iter, int flavour) {
     switch (mode) {
         case MODE_ITER:
-            if (CAN_LB && lb) launch_iter_mode<KIND, K, MODE_ITER, CAN_LB>(c, blocks, threads, nscan, g, prm, st, partials, out, iter);
-            else launch_iter_mode<KIND, K, MODE_ITER, false>(c, blocks, threads, nscan, g, prm, st, partials, out, iter);
+            launch_iter_flavour<KIND, K, MODE_ITER>(c, flavour, blocks, threads, nscan, g, prm, st, partials, out, iter);
             break;
         case MODE_ITER_NOSOLVE:
-            if (CAN_LB && lb) launch_iter_mode<KIND, K, MODE_ITER_NOSOLVE, CAN_LB>(c, blocks, threads, nscan, g, prm, st, partials, out, iter);
-            else launch_iter_mode<KIND, K, MODE_ITER_NOSOLVE, false>(c, blocks, threads, nscan, g, prm, st, partials, out, iter);
+            launch_iter_flavour<KIND, K, MODE_ITER_NOSOLVE>(c, flavour, blocks, threads, nscan, g, prm, st, partials, out, iter);
             break;
         case MODE_FITNESS:
-            if (CAN_LB && lb) launch_iter_mode<KIND, K, MODE_FITNESS, CAN_LB>(c, blocks, threads, nscan, g, prm, st, partials, out, iter);
-            else launch_iter_mode<KIND, K, MODE_FITNESS, false>(c, blocks, threads, nscan, g, prm, st, partials, out, iter);
+            launch_iter_flavour<KIND, K, MODE_FITNESS>(c, flavour, blocks, threads, nscan, g, prm, st, partials, out, iter);
             break;
         default:
-            if (CAN_LB && lb) launch_iter_mode<KIND, K, MODE_FITNESS_NOFINAL, CAN_LB>(c, blocks, threads, nscan, g, prm, st, partials, out, iter);
-            else launch_iter_mode<KIND, K, MODE_FITNESS_NOFINAL, false>(c, blocks, threads, nscan, g, prm, st, partials, out, iter);
+            launch_iter_flavour<KIND, K, MODE_FITNESS_NOFINAL>(c, flavour, blocks, threads, nscan, g, prm, st, partials, out, iter);
             break;
     }
     c->launches += 1;
 }
 
 static void dispatch_iter(Ctx* c, int kind, int K, int mode, int blocks, int threads, int nscan, const GridDesc& g,
-                          const RegParams* prm, RegState* st, double* partials, ResultBlock* out, int iter, bool lb = false) {
+                          const RegParams* prm, RegState* st, double* partials, ResultBlock* out, int iter, int lb = 0) {
     switch (kind) {
         case ICP4R_P2P_SVD:
             launch_iter<ICP4R_P2P_SVD, 1>(c, mode, blocks, threads, nscan, g, prm, st, partials, out, iter, lb);
@@ -1173,7 +1181,7 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
     if (c->use_hints) {
         CKS(reserve_grow(c, c->d_nbprev, (size_t)n * ICP4R_MAX_K * sizeof(int32_t)));
         P.nb_prev = c->d_nbprev.as<int32_t>();
-        if (c->use_lb && !gicp && o->max_iterations < 4096 && P.interp_s == 1.0) {
+        if (c->use_lb && !gicp && !sharded && o->max_iterations < 4096 && P.interp_s == 1.0) {
             const void* before = c->d_nbstate.p;
             CKS(reserve_grow(c, c->d_nbstate, (size_t)std::max(n, 1) * sizeof(NbState)));
             if (c->d_nbstate.p != before) CK(cudaMemsetAsync(c->d_nbstate.p, 0xFF, c->d_nbstate.cap, c->stream));
@@ -1218,7 +1226,7 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
         P.corr = c->d_gicp_corr.as<GicpCorr>();
     }
     std::memcpy(hs->T0, o->T0, sizeof(hs->T0));
-    const bool lb = P.nb_state != nullptr || sharded;  // which flavour of the iteration kernel runs (the lean one has no slab ownership code)
+    const int lb = sharded ? 2 : (P.nb_state != nullptr ? 1 : 0);  // flavour of the iteration kernel (see reg_iter_kernel)
 
     RegParams* d_prm = c->d_params.as<RegParams>();
     RegState* d_st = c->d_state.as<RegState>();
@@ -1294,7 +1302,7 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
     }
     auto run_range = [&](int it0, int it1, bool fit) -> int {
         GraphKey key{o->residual, k, blocks, it0 + 4096 * it1,
-                     threads | (sharded ? 1 << 16 : 0) | (gicp ? 1 << 17 : 0) | (fused_shard ? 1 << 19 : 0) | (fit ? 1 << 21 : 0) | (lb ? 1 << 22 : 0)};
+                     threads | (sharded ? 1 << 16 : 0) | (gicp ? 1 << 17 : 0) | (fused_shard ? 1 << 19 : 0) | (fit ? 1 << 21 : 0) | (lb << 22)};
         cudaGraphExec_t exec = nullptr;
         if (want_graph) {
             auto it = c->graphs.find(key);
@@ -1449,7 +1457,7 @@ int accumulate_slab(Ctx* c, Map& mp, const float4* d_src, int n, const icp4r_opt
     g.cell_start = nullptr;
     g.coarse = nullptr;
     g.m = 0;
-    if (n > 0) dispatch_iter(c, o->residual, k, MODE_ITER_NOSOLVE, blocks, threads, 1, g, d_prm, d_st, c->d_partials.as<double>(), c->d_res.as<ResultBlock>(), 0, sharded);
+    if (n > 0) dispatch_iter(c, o->residual, k, MODE_ITER_NOSOLVE, blocks, threads, 1, g, d_prm, d_st, c->d_partials.as<double>(), c->d_res.as<ResultBlock>(), 0, sharded ? 2 : 0);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(hs->acc, reinterpret_cast<const char*>(d_st) + offsetof(RegState, acc), sizeof(hs->acc), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -1546,8 +1554,8 @@ int register_scans_against_map(Ctx* c, Map& mp, const float4* d_src, const int32
         init_state_kernel<<<B, 32, 0, c->stream>>>(d_st, c->bm_T0.as<double>());
         c->launches += 1;
         auto enqueue = [&]() {
-            for (int it = 0; it < iters; ++it) dispatch_iter(c, o->residual, k, MODE_ITER, blocks, threads, B, g, d_prm, d_st, d_part, d_out, it, use_lb);
-            dispatch_iter(c, o->residual, k, MODE_FITNESS, blocks, threads, B, g, d_prm, d_st, d_part, d_out, 0, use_lb);
+            for (int it = 0; it < iters; ++it) dispatch_iter(c, o->residual, k, MODE_ITER, blocks, threads, B, g, d_prm, d_st, d_part, d_out, it, use_lb ? 1 : 0);
+            dispatch_iter(c, o->residual, k, MODE_FITNESS, blocks, threads, B, g, d_prm, d_st, d_part, d_out, 0, use_lb ? 1 : 0);
         };
         const bool want_graph = c->use_graph && !c->profiling;
         GraphKey key{o->residual, k, blocks, iters + (use_lb ? 8192 : 0), threads | (1 << 18) | (B << 20)};
