@@ -623,15 +623,18 @@ class Bench:
         m = self.measure(step_dev, step_e2e, steps, warmup, 1, sample_clocks=main)
         rec = self.record(m, C1_ITERS * C1_N, 2 * C1_N * 16, 16 * 8 + 32,
                           {"workload": "C1 single frame pair: 1024 + 1024 pts, P2P_SVD (Kabsch), 30 iterations, ungated (PCL defaults otherwise); "
-                                       "one icp4r_register call = target grid build + 30 iteration kernels + fitness pass",
+                                       "one icp4r_register call = ONE kernel launch (resident kernel: grid, 30 iterations, fitness pass in shared memory)",
                            "n": C1_N, "m": C1_N, "iterations": C1_ITERS, "l2": "flushed before every timed step"})
         rec["_m"] = m
-        k_ms = self.iter_kernel_ms(step_dev)
+        # the whole registration is ONE launch of the resident kernel (a batch of one pair: one CTA, one SM): target grid,
+        # 30 iterations, solves and the fitness pass in shared memory. Its time is the step time minus the result copy.
         st = self.stats_of(step_dev)
-        rec["us_per_iteration"] = 1e3 * k_ms if k_ms else None
-        rec["roofline"] = roofline("reg_iter_kernel<P2P_SVD,1>", "reg_iter_kernel_c1", 16 * (C1_N + C1_N) + 232, k_ms,
-                                   "32 KB working set: one iteration is a latency chain (search, block reduce, last-block solve), not a stream",
-                                   dist_evals=(st[1] / (C1_ITERS + 1)) if st else None)
+        rec["us_per_iteration"] = 1e3 * m["ms_per_step"] / (C1_ITERS + 1)
+        rec["roofline"] = roofline("reg_batch_kernel<P2P_SVD,256>, one pair (one CTA)", "reg_batch_kernel_c1", 16 * (C1_N + C1_N) + 64 + 160, m["ms_per_step"],
+                                   "one CTA on one SM iterates a 32 KB working set in shared memory: a latency chain (31 passes x {search, block "
+                                   "reduce, Kabsch}), not a stream; the HBM figure is the two clouds read once",
+                                   dist_evals=st[1] if st else None,
+                                   extra={"searches_per_registration": st[0], "settled_without_search_per_registration": st[2]} if st else None)
         if not self.args.no_cpu_baseline:
             src = np.concatenate([a for a, _, _ in pool])
             tgt = np.concatenate([b for _, b, _ in pool])

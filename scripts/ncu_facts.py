@@ -11,7 +11,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-OUT = os.path.join(ROOT, "profiles", "r2_ncu_facts.json")
+OUT = os.environ.get("NCU_FACTS_OUT", os.path.join(ROOT, "profiles", "r2_ncu_facts.json"))
 WANT = {
     "dram__bytes_read.sum": "dram_bytes_read", "dram__bytes_write.sum": "dram_bytes_write", "gpu__time_duration.sum": "ncu_duration_us",
     "smsp__inst_executed.sum": "warp_instructions", "smsp__thread_inst_executed_per_inst_executed.ratio": "lanes_per_instruction",
