@@ -399,7 +399,7 @@ def run_reference(args, rank, world):
     wl = "c4" if args.workload == "all" else args.workload
     if wl == "c4":
         # each step = a bounded sample of the 65,536-pair job: `threads` pairs in flight, ~20 s per step
-        n_sample = max(threads * 4, 64)
+        n_sample = max(threads * 64, 1024)
         src, tgt, off = make_c4(n_sample)
         kind, done, secs = cpu_pairs(src, tgt, C4_N, C4_ITERS, 20.0 * max(args.warmup, 1), threads, n_sample)   # warm-up
         tot_done, tot_secs = 0, 0.0
