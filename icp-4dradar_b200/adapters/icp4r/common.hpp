@@ -1,5 +1,6 @@
 // common.hpp — shared pieces of the header-only adapters over include/icp4r.h.
 #pragma once
+#include <cstddef>
 #include <cstdint>
 #include <stdexcept>
 #include <string>
@@ -22,19 +23,36 @@ inline float intensity_of(const P& p, std::true_type) { return p.intensity; }
 template <typename P>
 inline float intensity_of(const P&, std::false_type) { return 0.f; }
 
-template <typename It>
-inline std::vector<float> pack_xyzw(It first, It last) {
-    std::vector<float> out;
-    out.reserve(4 * static_cast<std::size_t>(last - first));
-    for (; first != last; ++first) {
-        using P = typename std::decay<decltype(*first)>::type;
-        out.push_back(first->x);
-        out.push_back(first->y);
-        out.push_back(first->z);
-        out.push_back(intensity_of(*first, has_intensity<P>()));
-    }
-    return out;
+// The reference's clouds go to the library AS THEY LIE IN MEMORY: a std::vector / pcl::PointCloud of PointType is an
+// array of sizeof(PointType)-byte rows with x, y, z in the first 12 bytes (every PCL point type starts with
+// PCL_ADD_POINT4D); RowLayout tells the handle that stride (and where the intensity sits) for the calls inside its
+// scope and restores the packed default afterwards. No host-side pack loop, no temporary vector: the rows are copied
+// to the device unmodified and repacked there (icp4r_set_point_layout).
+template <typename P>
+inline int32_t w_offset(std::true_type) {
+    static_assert(std::is_standard_layout<P>::value, "point type must be standard-layout");
+    return (int32_t)offsetof(P, intensity);
 }
+template <typename P>
+inline int32_t w_offset(std::false_type) { return -1; }
+
+template <typename P>
+class RowLayout {
+   public:
+    explicit RowLayout(icp4r_handle h) : h_(h) {
+        static_assert(sizeof(P) % 4 == 0 && sizeof(P) >= 12, "point rows must be whole floats");
+        static_assert(offsetof(P, x) == 0 && offsetof(P, y) == 4 && offsetof(P, z) == 8, "x, y, z must lead the point type");
+        icp4r_set_point_layout(h_, (int32_t)sizeof(P), w_offset<P>(has_intensity<P>()));
+    }
+    ~RowLayout() { icp4r_set_point_layout(h_, 16, 12); }
+    RowLayout(const RowLayout&) = delete;
+    RowLayout& operator=(const RowLayout&) = delete;
+
+   private:
+    icp4r_handle h_;
+};
+template <typename P>
+inline const float* rows(const P* first) { return reinterpret_cast<const float*>(first); }
 
 // One handle per THREAD and device for objects that the reference constructs per frame on the stack
 // (pcl::IterativeClosestPoint at iterative_closest_point.cpp:510, FastGICP at radar_odometry.cpp:399): creating a CUDA

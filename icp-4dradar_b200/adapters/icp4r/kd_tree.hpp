@@ -69,16 +69,20 @@ class KD_TREE {
 
     void Build(PointVector point_cloud) {  // by value, like the reference
         mirror_.assign(point_cloud.begin(), point_cloud.end());
-        const std::vector<float> xyzw = pack_xyzw(point_cloud.begin(), point_cloud.end());
-        check(h_, icp4r_map_build(h_, xyzw.data(), (int32_t)point_cloud.size(), ICP4R_HOST, 0.f), "Build");
+        {
+            RowLayout<PointType> lay(h_);
+            check(h_, icp4r_map_build(h_, rows(point_cloud.data()), (int32_t)point_cloud.size(), ICP4R_HOST, 0.f), "Build");
+        }
         check(h_, icp4r_map_set_downsample(h_, downsample_size_), "Build");
     }
 
     int Add_Points(PointVector& PointToAdd, bool downsample_on) {
-        const std::vector<float> xyzw = pack_xyzw(PointToAdd.begin(), PointToAdd.end());
         int32_t replaced = 0;
-        check(h_, icp4r_map_add_points(h_, xyzw.data(), (int32_t)PointToAdd.size(), ICP4R_HOST, downsample_on ? 1 : 0, &replaced),
-              "Add_Points");
+        {
+            RowLayout<PointType> lay(h_);
+            check(h_, icp4r_map_add_points(h_, rows(PointToAdd.data()), (int32_t)PointToAdd.size(), ICP4R_HOST, downsample_on ? 1 : 0, &replaced),
+                  "Add_Points");
+        }
         mirror_.insert(mirror_.end(), PointToAdd.begin(), PointToAdd.end());
         return replaced;
     }
@@ -108,11 +112,11 @@ class KD_TREE {
     // batch form: rows of k indices into insertion order (-1 = none) and squared distances
     void Nearest_Search_Batch(const PointVector& queries, int k_nearest, std::vector<int32_t>& indices, std::vector<float>& sq_dist,
                               std::vector<int32_t>& found, double max_dist = INFINITY) {
-        const std::vector<float> q = pack_xyzw(queries.begin(), queries.end());
+        RowLayout<PointType> lay(h_);
         indices.assign(queries.size() * k_nearest, -1);
         sq_dist.assign(queries.size() * k_nearest, INFINITY);
         found.assign(queries.size(), 0);
-        check(h_, icp4r_map_knn(h_, q.data(), (int32_t)queries.size(), ICP4R_HOST, k_nearest, std::isinf(max_dist) ? 0.0 : max_dist,
+        check(h_, icp4r_map_knn(h_, rows(queries.data()), (int32_t)queries.size(), ICP4R_HOST, k_nearest, std::isinf(max_dist) ? 0.0 : max_dist,
                                indices.data(), sq_dist.data(), found.data()),
               "Nearest_Search_Batch");
     }
@@ -159,8 +163,8 @@ class KD_TREE {
 
     void Delete_Points(PointVector& PointToDel) {
         if (PointToDel.empty()) return;
-        const std::vector<float> v = pack_xyzw(PointToDel.begin(), PointToDel.end());
-        check(h_, icp4r_map_delete_points(h_, v.data(), (int32_t)PointToDel.size(), ICP4R_HOST, nullptr), "Delete_Points");
+        RowLayout<PointType> lay(h_);
+        check(h_, icp4r_map_delete_points(h_, rows(PointToDel.data()), (int32_t)PointToDel.size(), ICP4R_HOST, nullptr), "Delete_Points");
     }
 
     BoxPointType tree_range() {

@@ -86,18 +86,23 @@ class RegistrationBase {
         from_matrix4f(guess, opts_.T0);
         std::memcpy(T_, opts_.T0, sizeof(T_));
         if (!src_ || !tgt_ || src_->points.empty() || tgt_->points.empty()) return;  // PCL prints and returns
-        const std::vector<float> s = pack_xyzw(src_->points.begin(), src_->points.end());
-        const std::vector<float> t = pack_xyzw(tgt_->points.begin(), tgt_->points.end());
-        const int rc = icp4r_register(h_, s.data(), (int32_t)src_->points.size(), t.data(), (int32_t)tgt_->points.size(), ICP4R_HOST,
-                                      &opts_, T_, &res_, nullptr);
+        static_assert(sizeof(PointSource) == sizeof(PointTarget), "source and target rows share one layout per call");
+        const int32_t n = (int32_t)src_->points.size();
+        std::vector<float> out(4 * (std::size_t)n);
+        int rc, rc_out;
+        {
+            RowLayout<PointSource> lay(h_);  // the clouds are read as they lie in memory
+            rc = icp4r_register(h_, rows(src_->points.data()), n, rows(tgt_->points.data()), (int32_t)tgt_->points.size(), ICP4R_HOST, &opts_, T_,
+                                &res_, nullptr);
+            // output = source transformed by the final pose (pcl::transformPointCloud at the end of align)
+            rc_out = rc == ICP4R_OK ? icp4r_transform_points(h_, T_, rows(src_->points.data()), n, ICP4R_HOST, out.data()) : rc;
+        }
         if (rc != ICP4R_OK) {
             last_error_ = icp4r_last_error(h_);
             return;
         }
         converged_ = res_.converged != 0;
-        // output = source transformed by the final pose (pcl::transformPointCloud at the end of align)
-        std::vector<float> out(s.size());
-        if (icp4r_transform_points(h_, T_, s.data(), (int32_t)src_->points.size(), ICP4R_HOST, out.data()) == ICP4R_OK) {
+        if (rc_out == ICP4R_OK) {
             output.points.assign(src_->points.begin(), src_->points.end());
             for (std::size_t i = 0; i < output.points.size(); ++i) {
                 output.points[i].x = out[4 * i];

@@ -37,11 +37,14 @@ class VoxelGrid {
             output.width = output.height = 0;
             return;
         }
-        const std::vector<float> in = pack_xyzw(input_->points.begin(), input_->points.end());
         const int32_t n = (int32_t)input_->points.size();
         std::vector<float> out(4 * (std::size_t)n);
         int32_t cnt = 0;
-        const int rc = icp4r_voxel_grid(h_, in.data(), n, ICP4R_HOST, leaf_, out.data(), n, &cnt);
+        int rc;
+        {
+            RowLayout<PointT> lay(h_);
+            rc = icp4r_voxel_grid(h_, rows(input_->points.data()), n, ICP4R_HOST, leaf_, out.data(), n, &cnt);
+        }
         if (rc == ICP4R_ERR_INVALID) {  // PCL: "Leaf size is too small for the input dataset" -> output = input
             output = *input_;
             return;

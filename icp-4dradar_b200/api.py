@@ -18,7 +18,7 @@ ACC_LEN = 32
 MAX_K = 16
 
 EXPORTS = [
-    "icp4r_create", "icp4r_destroy", "icp4r_last_error", "icp4r_version", "icp4r_default_opts", "icp4r_set_stream",
+    "icp4r_create", "icp4r_destroy", "icp4r_last_error", "icp4r_version", "icp4r_default_opts", "icp4r_set_stream", "icp4r_set_point_layout",
     "icp4r_synchronize", "icp4r_launch_count", "icp4r_set_profiling", "icp4r_last_profile", "icp4r_set_stats", "icp4r_get_stats", "icp4r_map_build", "icp4r_map_set_downsample", "icp4r_map_add_points",
     "icp4r_map_size", "icp4r_map_range", "icp4r_map_knn", "icp4r_map_knn_brute", "icp4r_map_sector", "icp4r_map_points",
     "icp4r_register", "icp4r_register_map", "icp4r_register_map_batch", "icp4r_register_batch", "icp4r_shard_unique_id", "icp4r_shard_init", "icp4r_shard_ipc_export", "icp4r_shard_ipc_import",
@@ -125,11 +125,12 @@ def _ptr(a):
 
 
 def _f4(a):
+    """point rows as float32: (n, 4) packed x y z w by default; wider (or 3-float) rows go with Icp4r.set_point_layout"""
     if isinstance(a, np.ndarray):
         a = np.ascontiguousarray(a, dtype=np.float32)
-        assert a.ndim == 2 and a.shape[1] == 4, a.shape
+        assert a.ndim == 2 and a.shape[1] >= 3, a.shape
         return a
-    assert a.dim() == 2 and a.shape[1] == 4 and a.is_contiguous() and a.dtype.is_floating_point and a.element_size() == 4
+    assert a.dim() == 2 and a.shape[1] >= 3 and a.is_contiguous() and a.dtype.is_floating_point and a.element_size() == 4
     return a
 
 
@@ -168,6 +169,10 @@ class Icp4r:
     # ---- lifecycle
     def set_stream(self, cuda_stream_ptr: int):
         self._ck(self.lib.icp4r_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def set_point_layout(self, stride_bytes: int = 16, w_offset_bytes: int = 12):
+        """layout of the point INPUT rows of later calls (pcl::PointXYZI: 32, 16); outputs stay packed (n, 4)"""
+        self._ck(self.lib.icp4r_set_point_layout(self.h, C.c_int32(stride_bytes), C.c_int32(w_offset_bytes)))
 
     def synchronize(self):
         self._ck(self.lib.icp4r_synchronize(self.h))
@@ -531,10 +536,10 @@ class Icp4r:
         p, mem = _ptr(pts)
         T = np.ascontiguousarray(T, np.float64).reshape(16)
         if mem == HOST:
-            out = np.empty_like(pts)
+            out = np.empty((pts.shape[0], 4), np.float32)  # outputs are always packed x, y, z, w
         else:
             import torch
-            out = torch.empty_like(pts)
+            out = torch.empty((pts.shape[0], 4), dtype=torch.float32, device=pts.device)
         self._ck(self.lib.icp4r_transform_points(self.h, C.c_void_p(T.ctypes.data), p, C.c_int32(pts.shape[0]), C.c_int(mem),
                                                  _ptr(out)[0]))
         return out

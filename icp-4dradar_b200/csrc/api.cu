@@ -146,11 +146,60 @@ static int stage_in(Ctx* c, DevBuf& b, const void* user, size_t bytes, int mem, 
     return ICP4R_OK;
 }
 
+// rows of `stride` bytes (x, y, z at byte 0, 4, 8; w at byte `woff`, or none) -> packed x, y, z, w
+__global__ void __launch_bounds__(256) repack_rows_kernel(const unsigned char* __restrict__ raw, size_t n, int stride, int woff,
+                                                          float4* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* row = reinterpret_cast<const float*>(raw + i * (size_t)stride);
+    float4 p;
+    if ((stride & 15) == 0) {  // 16-byte aligned rows (pcl::PointXYZI: 32 bytes): one vector load for x, y, z
+        const float4 v = *reinterpret_cast<const float4*>(row);
+        p = make_float4(v.x, v.y, v.z, woff == 12 ? v.w : 0.f);
+    } else {
+        p = make_float4(row[0], row[1], row[2], 0.f);
+    }
+    if (woff >= 0 && !((stride & 15) == 0 && woff == 12)) p.w = row[woff >> 2];
+    out[i] = p;
+}
+
+static bool packed_layout(const Ctx* c) { return c->pt_stride == 16 && c->pt_woff == 12; }
+static const float* row_at(const Ctx* c, const float* base, size_t i) {
+    return reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(base) + i * (size_t)c->pt_stride);
+}
+
+// the caller's rows [0, n) as packed float4 at `dst` (device memory), whatever their layout and memory space
+static int unpack_points_to(Ctx* c, const float* user, size_t n, int mem, float4* dst) {
+    if (n == 0) return ICP4R_OK;
+    if (packed_layout(c)) {
+        CK(cudaMemcpyAsync(dst, user, n * sizeof(float4), mem == ICP4R_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+        return ICP4R_OK;
+    }
+    const unsigned char* raw = reinterpret_cast<const unsigned char*>(user);
+    if (mem == ICP4R_HOST) {  // the raw rows cross the bus as they are (no host-side pack loop), the device repacks them
+        CKS(reserve_grow(c, c->d_raw, n * (size_t)c->pt_stride));
+        CK(cudaMemcpyAsync(c->d_raw.p, user, n * (size_t)c->pt_stride, cudaMemcpyHostToDevice, c->stream));
+        raw = static_cast<const unsigned char*>(c->d_raw.p);
+    }
+    repack_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(raw, n, c->pt_stride, c->pt_woff, dst);
+    c->launches += 1;
+    CK(cudaGetLastError());
+    return ICP4R_OK;
+}
+
+// a point-cloud input of a call: packed float4 on the device (aliased when it already is exactly that)
+static int stage_points(Ctx* c, DevBuf& b, const float* user, size_t n, int mem, const void** dev) {
+    if (packed_layout(c)) return stage_in(c, b, user, n * sizeof(float4), mem, dev);
+    CKS(reserve(c, b, std::max<size_t>(n, 16) * sizeof(float4)));
+    CKS(unpack_points_to(c, user, n, mem, static_cast<float4*>(b.p)));
+    *dev = b.p;
+    return ICP4R_OK;
+}
+
 static int set_points(Ctx* c, Map& mp, const float* xyzw, int n, int mem, int offset) {
     CKS(map_reserve(c, mp, offset + n));
     if (n > 0) {
-        CK(cudaMemcpyAsync(mp.pts.as<float4>() + offset, xyzw, (size_t)n * sizeof(float4),
-                           mem == ICP4R_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+        CKS(unpack_points_to(c, xyzw, (size_t)n, mem, mp.pts.as<float4>() + offset));
         CK(cudaMemsetAsync(mp.valid.as<uint8_t>() + offset, 1, (size_t)n, c->stream));
         CK(cudaMemsetAsync(mp.userdel.as<uint8_t>() + offset, 0, (size_t)n, c->stream));
     }
@@ -228,6 +277,11 @@ int icp4r_create(int device, icp4r_handle* out) {
     {
         const char* nl = std::getenv("ICP4R_NO_LB");
         c->use_lb = !(nl && nl[0] == '1');
+        // measured on B200 (scripts/probe_map_kernels.py): the persistent loop is bit-identical but SLOWER than the captured
+        // graph of per-iteration launches (C2 single 0.485 vs 0.436 ms, C5 0.762 vs 0.695 ms) — a kernel boundary inside a
+        // graph costs ~1 us here, the in-kernel hand-over a release + an acquire round trip + the pose reload — so it is opt-in
+        const char* np_ = std::getenv("ICP4R_PERSIST");
+        c->use_persist = np_ && np_[0] == '1';
     }
     const char* br = std::getenv("ICP4R_BATCH_REPRODUCIBLE");
     c->batch_reproducible = br && br[0] == '1';
@@ -253,6 +307,7 @@ int icp4r_destroy(icp4r_handle h) {
     release(c->d_xch);
     release(c->d_xt);
     release(c->d_nbprev);
+    release(c->d_raw);
     release(c->d_nbstate);
     release(c->bf_part);
     release(c->gs_pts);
@@ -285,6 +340,15 @@ int icp4r_set_stream(icp4r_handle h, void* s) {
     HCHECK(h);
     cudaStreamSynchronize(c->stream);
     c->stream = s ? static_cast<cudaStream_t>(s) : c->own_stream;
+    return ICP4R_OK;
+}
+
+int icp4r_set_point_layout(icp4r_handle h, int32_t stride_bytes, int32_t w_offset_bytes) {
+    HCHECK(h);
+    if (stride_bytes < 12 || (stride_bytes & 3) != 0 || stride_bytes > 4096 || (w_offset_bytes >= 0 && ((w_offset_bytes & 3) != 0 || w_offset_bytes + 4 > stride_bytes)))
+        return fail(c, ICP4R_ERR_INVALID, "icp4r_set_point_layout: stride %d / w offset %d (rows are 4-byte aligned, x y z first)", stride_bytes, w_offset_bytes);
+    c->pt_stride = stride_bytes;
+    c->pt_woff = w_offset_bytes < 0 ? -1 : w_offset_bytes;
     return ICP4R_OK;
 }
 
@@ -384,7 +448,7 @@ int icp4r_map_add_points(icp4r_handle h, const float* xyzw, int32_t n, int mem, 
     int total = 0;
     for (int off = 0; off < n; off += CH) {
         const int cn = std::min(CH, n - off);
-        CKS(set_points(c, mp, xyzw + 4 * (size_t)off, cn, mem, mp.m));
+        CKS(set_points(c, mp, row_at(c, xyzw, (size_t)off), cn, mem, mp.m));
         CK(cudaMemsetAsync(mp.valid.as<uint8_t>() + mp.m, 0, (size_t)cn, c->stream));  // not inserted yet
         int rep = 0;
         CKS(map_downsample_add(c, mp, cn, &rep, force_seq));
@@ -421,7 +485,7 @@ static int map_knn_common(Ctx* c, bool brute, const float* q, int32_t nq, int me
     if (!c->map.built) return fail(c, ICP4R_ERR_STATE, "icp4r_map_knn before icp4r_map_build");
     if (nq == 0) return ICP4R_OK;
     const void* dq = nullptr;
-    CKS(stage_in(c, c->d_q, q, (size_t)nq * sizeof(float4), mem, &dq));
+    CKS(stage_points(c, c->d_q, q, (size_t)nq, mem, &dq));
     int32_t* di = idx;
     float* dd = d2;
     int32_t* df = found;
@@ -541,7 +605,7 @@ int icp4r_map_delete_points(icp4r_handle h, const float* xyzw, int32_t n, int me
     if (!mp.built) return fail(c, ICP4R_ERR_STATE, "icp4r_map_delete_points before icp4r_map_build");
     if (n == 0) return ICP4R_OK;
     const void* dreq = nullptr;
-    CKS(stage_in(c, c->d_q, xyzw, (size_t)n * sizeof(float4), mem, &dreq));
+    CKS(stage_points(c, c->d_q, xyzw, (size_t)n, mem, &dreq));
     int deleted = 0;
     CKS(map_delete_points(c, mp, static_cast<const float4*>(dreq), n, &deleted));
     if (deleted > 0) CKS(map_rebuild_grid(c, mp));
@@ -618,7 +682,7 @@ int icp4r_register_map(icp4r_handle h, const float* src, int32_t n, int mem, con
     HCHECK(h);
     if (!opts || n < 0 || (n > 0 && !src) || bad_mem(mem)) return fail(c, ICP4R_ERR_INVALID, "icp4r_register_map: bad arguments");
     const void* dsrc = nullptr;
-    CKS(stage_in(c, c->d_src, src, (size_t)n * sizeof(float4), mem, &dsrc));
+    CKS(stage_points(c, c->d_src, src, (size_t)n, mem, &dsrc));
     DumpStage ds;
     CKS(dump_prepare(c, dump, mem, n, opts, ds));
     CKS(register_against_map(c, c->map, static_cast<const float4*>(dsrc), n, opts, -1, 0.f, 0.f, T_out, res, dump ? &ds.dev : nullptr));
@@ -634,7 +698,7 @@ int icp4r_odometry_step(icp4r_handle h, const float* scan, int32_t n, int mem, c
     if (downsample_on) return fail(c, ICP4R_ERR_UNSUPPORTED, "icp4r_odometry_step: use icp4r_map_add_points for down-sampled insertion");
     Map& mp = c->map;
     const void* dsrc = nullptr;
-    CKS(stage_in(c, c->d_src, scan, (size_t)n * sizeof(float4), mem, &dsrc));
+    CKS(stage_points(c, c->d_src, scan, (size_t)n, mem, &dsrc));
     icp4r_result r;
     std::memset(&r, 0, sizeof(r));
     if (mp.built && mp.m > 0) {
@@ -670,7 +734,7 @@ int icp4r_register_map_batch(icp4r_handle h, const float* src, const int32_t* of
     const size_t total = (size_t)(off[n_scans] - off[0]);
     if (total > 0 && !src) return fail(c, ICP4R_ERR_INVALID, "null cloud pointer");
     const void* dsrc = nullptr;
-    CKS(stage_in(c, c->d_src, src, (size_t)off[n_scans] * sizeof(float4), mem, &dsrc));
+    CKS(stage_points(c, c->d_src, src, (size_t)off[n_scans], mem, &dsrc));
     return register_scans_against_map(c, c->map, static_cast<const float4*>(dsrc), off, n_scans, opts, T0s, T_out, res);
 }
 
@@ -707,7 +771,7 @@ static int register_transient(Ctx* c, const float* src, int32_t n, const float* 
     mp.m = m;
     CKS(map_rebuild_grid(c, mp));
     const void* dsrc = nullptr;
-    CKS(stage_in(c, c->d_src, src, (size_t)n * sizeof(float4), mem, &dsrc));
+    CKS(stage_points(c, c->d_src, src, (size_t)n, mem, &dsrc));
     DumpStage ds;
     CKS(dump_prepare(c, dump, mem, n, opts, ds));
     CKS(register_against_map(c, mp, static_cast<const float4*>(dsrc), n, opts, -1, 0.f, 0.f, T_out, res, dump ? &ds.dev : nullptr));
@@ -734,8 +798,8 @@ int icp4r_register(icp4r_handle h, const float* src, int32_t n, const float* tgt
             Stage* hs = static_cast<Stage*>(c->h_pinned);
             hs->soff[0] = 0, hs->soff[1] = n, hs->toff[0] = 0, hs->toff[1] = m;
             const void *dsrc = nullptr, *dtgt = nullptr;
-            CKS(stage_in(c, c->b_src, src, (size_t)n * sizeof(float4), mem, &dsrc));
-            CKS(stage_in(c, c->b_tgt, tgt, (size_t)m * sizeof(float4), mem, &dtgt));
+            CKS(stage_points(c, c->b_src, src, (size_t)n, mem, &dsrc));
+            CKS(stage_points(c, c->b_tgt, tgt, (size_t)m, mem, &dtgt));
             CKS(reserve(c, c->b_soff, 4 * sizeof(int32_t)));
             CKS(reserve(c, c->b_T, 16 * sizeof(double)));
             CKS(reserve(c, c->b_res, sizeof(icp4r_result)));
@@ -788,6 +852,17 @@ int icp4r_register_batch(icp4r_handle h, const float* src, const int32_t* src_of
     }
     const size_t ns = (size_t)so[n_pairs], nt = (size_t)to[n_pairs];
     if ((ns > 0 && !src) || (nt > 0 && !tgt)) return fail(c, ICP4R_ERR_INVALID, "null cloud pointer");
+    // a strided input layout (icp4r_set_point_layout): both clouds are repacked on the device first; from here on the
+    // POINTS are packed device rows (pmem), offsets and outputs keep following `mem`
+    int pmem = mem;
+    if (!packed_layout(c)) {
+        const void *ps = nullptr, *pt = nullptr;
+        CKS(stage_points(c, c->b_src, src, ns, mem, &ps));
+        CKS(stage_points(c, c->b_tgt, tgt, nt, mem, &pt));
+        src = static_cast<const float*>(ps);
+        tgt = static_cast<const float*>(pt);
+        pmem = ICP4R_DEVICE;
+    }
     if (!register_batch_fits(max_n, max_m)) {
         // A pair that does not fit one SM's shared memory (n + m above ~12 k points): every pair of the batch goes through
         // the map path instead — target grid in global memory, one launch per iteration — one after the other. Same
@@ -797,9 +872,14 @@ int icp4r_register_batch(icp4r_handle h, const float* src, const int32_t* src_of
             return fail(c, ICP4R_ERR_UNSUPPORTED, "batched registration supports P2P_SVD and P2P_GN (got %d)", opts->residual);
         std::vector<double> Th((size_t)n_pairs * 16);
         std::vector<icp4r_result> Rh(n_pairs);
-        for (int i = 0; i < n_pairs; ++i)
-            CKS(register_transient(c, src + 4 * (size_t)so[i], so[i + 1] - so[i], tgt + 4 * (size_t)to[i], to[i + 1] - to[i], mem, nullptr, 0, opts,
-                                   Th.data() + 16 * (size_t)i, &Rh[i], nullptr));
+        const int keep_stride = c->pt_stride, keep_woff = c->pt_woff;
+        if (pmem != mem) c->pt_stride = 16, c->pt_woff = 12;  // the rows are packed by now
+        int rc_pairs = ICP4R_OK;
+        for (int i = 0; i < n_pairs && rc_pairs == ICP4R_OK; ++i)
+            rc_pairs = register_transient(c, src + 4 * (size_t)so[i], so[i + 1] - so[i], tgt + 4 * (size_t)to[i], to[i + 1] - to[i], pmem, nullptr, 0, opts,
+                                          Th.data() + 16 * (size_t)i, &Rh[i], nullptr);
+        c->pt_stride = keep_stride, c->pt_woff = keep_woff;
+        CKS(rc_pairs);
         if (mem == ICP4R_DEVICE) {
             CK(cudaMemcpyAsync(T_out, Th.data(), Th.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
             CK(cudaMemcpyAsync(res, Rh.data(), Rh.size() * sizeof(icp4r_result), cudaMemcpyHostToDevice, c->stream));
@@ -813,7 +893,7 @@ int icp4r_register_batch(icp4r_handle h, const float* src, const int32_t* src_of
     // Large host-resident batches: copy the clouds in chunks on a second stream that runs ahead of the kernels, so the
     // bus transfer of chunk k+1 overlaps the registration of chunk k (the clouds of a pair range are contiguous).
     constexpr int NCHUNK = 8;
-    if (mem == ICP4R_HOST && n_pairs >= 64 * NCHUNK && (ns + nt) * sizeof(float4) >= ((size_t)32 << 20)) {
+    if (mem == ICP4R_HOST && pmem == ICP4R_HOST && n_pairs >= 64 * NCHUNK && (ns + nt) * sizeof(float4) >= ((size_t)32 << 20)) {
         if (!c->copy_stream) {
             CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
             for (auto& e : c->copy_events) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -852,8 +932,8 @@ int icp4r_register_batch(icp4r_handle h, const float* src, const int32_t* src_of
         return ICP4R_OK;
     }
     const void *dsrc = nullptr, *dtgt = nullptr, *dso = nullptr, *dto = nullptr;
-    CKS(stage_in(c, c->b_src, src, ns * sizeof(float4), mem, &dsrc));
-    CKS(stage_in(c, c->b_tgt, tgt, nt * sizeof(float4), mem, &dtgt));
+    CKS(stage_in(c, c->b_src, src, ns * sizeof(float4), pmem, &dsrc));
+    CKS(stage_in(c, c->b_tgt, tgt, nt * sizeof(float4), pmem, &dtgt));
     CKS(stage_in(c, c->b_soff, src_off, (size_t)(n_pairs + 1) * 4, mem, &dso));
     CKS(stage_in(c, c->b_toff, tgt_off, (size_t)(n_pairs + 1) * 4, mem, &dto));
     double* dT = T_out;
@@ -905,7 +985,7 @@ int icp4r_register_sharded(icp4r_handle h, const float* src, int32_t n, int mem,
     if (!opts || n < 0 || (n > 0 && !src) || bad_mem(mem) || axis < 0 || axis > 2)
         return fail(c, ICP4R_ERR_INVALID, "icp4r_register_sharded: bad arguments");
     const void* dsrc = nullptr;
-    CKS(stage_in(c, c->d_src, src, (size_t)n * sizeof(float4), mem, &dsrc));
+    CKS(stage_points(c, c->d_src, src, (size_t)n, mem, &dsrc));
     return register_against_map(c, c->map, static_cast<const float4*>(dsrc), n, opts, axis, slab_lo, slab_hi, T_out, res, nullptr);
 }
 
@@ -915,7 +995,7 @@ int icp4r_accumulate_slab(icp4r_handle h, const float* src, int32_t n, int mem, 
     if (!opts || !T || !acc_out || n < 0 || (n > 0 && !src) || bad_mem(mem) || axis < -1 || axis > 2)
         return fail(c, ICP4R_ERR_INVALID, "icp4r_accumulate_slab: bad arguments");
     const void* dsrc = nullptr;
-    CKS(stage_in(c, c->d_src, src, (size_t)n * sizeof(float4), mem, &dsrc));
+    CKS(stage_points(c, c->d_src, src, (size_t)n, mem, &dsrc));
     return accumulate_slab(c, c->map, static_cast<const float4*>(dsrc), n, opts, T, axis, slab_lo, slab_hi, acc_out);
 }
 
@@ -986,7 +1066,7 @@ extern "C" int icp4r_transform_points(icp4r_handle h, const double T[16], const 
     if (!T || n < 0 || (n > 0 && (!xyzw || !xyzw_out)) || bad_mem(mem)) return fail(c, ICP4R_ERR_INVALID, "icp4r_transform_points: bad arguments");
     if (n == 0) return ICP4R_OK;
     const void* din = nullptr;
-    CKS(stage_in(c, c->d_q, xyzw, (size_t)n * sizeof(float4), mem, &din));
+    CKS(stage_points(c, c->d_q, xyzw, (size_t)n, mem, &din));
     float4* dout = reinterpret_cast<float4*>(xyzw_out);
     if (mem == ICP4R_HOST) {
         CKS(reserve(c, c->d_src, (size_t)n * sizeof(float4)));
@@ -1007,7 +1087,7 @@ extern "C" int icp4r_voxel_grid(icp4r_handle h, const float* xyzw, int32_t n, in
     const uint8_t* dvalid = nullptr;
     if (xyzw) {
         const void* p;
-        CKS(stage_in(c, c->d_q, xyzw, (size_t)n * sizeof(float4), mem, &p));
+        CKS(stage_points(c, c->d_q, xyzw, (size_t)n, mem, &p));
         din = static_cast<const float4*>(p);
     } else {  // the handle's own map (deleted points skipped)
         if (!c->map.built) return fail(c, ICP4R_ERR_STATE, "icp4r_voxel_grid(NULL) before icp4r_map_build");

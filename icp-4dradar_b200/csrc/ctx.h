@@ -119,7 +119,7 @@ struct RegState {
     int n_corr;
     unsigned ticket;
     unsigned ticket_fit;
-    int pad;
+    int loop_epoch;      // persistent loop: iterations completed (published by the block that solved, see reg_loop_kernel)
     // the last pose increment D as the displacement map q -> q - D^-1 q = (I - R^T) q + R^T t (row-major 3x4) and the
     // iteration whose solve produced it (-1: none yet): a source point moved by |dA q| between that pass and the next
     float dA[12];
@@ -198,6 +198,9 @@ struct Ctx {
     DevBuf d_src_normals, d_gicp_corr;
 
     DevBuf d_src, d_q, d_idx, d_d2, d_found, d_scratch, d_partials, d_state, d_params, d_T, d_res;
+    // layout of the caller's point-cloud INPUT rows (icp4r_set_point_layout): byte stride and byte offset of w (< 0: none)
+    int pt_stride = 16, pt_woff = 12;
+    DevBuf d_raw;  // raw strided rows of a host cloud on their way to the device repack
     DevBuf d_dump_pose, d_dump_acc, d_dump_idx;
     DevBuf b_src, b_tgt, b_soff, b_toff, b_T, b_res;  // batched registration
     DevBuf bm_params, bm_state, bm_T0, bm_res, bm_partials;  // batched scans against the map
@@ -226,6 +229,8 @@ struct Ctx {
     DevBuf gs_pts, gs_idx, gs_d2, gs_found;  // GICP: exhaustive k-NN scratch for the scan's own normals
     DevBuf vg_keys, vg_vals, vg_sort, vg_tiles, vg_out;  // voxel-grid centroid filter
     bool batch_reproducible = false;  // ICP4R_BATCH_REPRODUCIBLE=1 (see register_batch.cu)
+    bool coop_ok = true;      // cleared when a cooperative launch was refused
+    bool use_persist = false;  // ICP4R_PERSIST=1: single-scan loops as ONE cooperative launch (reg_loop_kernel) instead of a graph of per-iteration launches
     bool use_lb = true;     // ICP4R_NO_LB=1 turns the keep-the-neighbours-without-a-search proof off (A/B measurements)
     bool use_hints = true;  // ICP4R_NO_HINTS=1 turns the previous-iteration search bound off (A/B measurements)            // local exchange buffer and the peer table
     void* xch_peers[XCH_MAXW] = {nullptr};  // peer mappings opened with cudaIpcOpenMemHandle
@@ -248,7 +253,8 @@ int grid_knn(Ctx* c, const Map& mp, const float4* q, int nq, int k, double max_d
              int32_t* found);
 int brute_knn_cloud(Ctx* c, const float4* cloud_xyzi, int m, const float4* q, int nq, int k, double max_dist, int32_t* idx, float* d2,
                     int32_t* found);
-int gicp_normals_small(Ctx* c, const float4* d_pts, int n, int k, DevBuf& normals);  // own-cloud k-NN normals without a grid
+int gicp_normals_small(Ctx* c, const float4* d_pts, int n, int k, DevBuf& normals);
+int gicp_normals_small_to(Ctx* c, const float4* d_pts, int n, int k, double* out);  // same, into a caller-sized device array  // own-cloud k-NN normals without a grid
 int brute_knn(Ctx* c, const Map& mp, const float4* q, int nq, int k, double max_dist, int32_t* idx, float* d2,
               int32_t* found);
 void gate_params(double max_dist, float* gate_f, float* gate_r);
@@ -279,7 +285,7 @@ int register_batch(Ctx* c, const float4* d_src, const int32_t* d_soff, const flo
 
 // gicp.cu
 int gicp_normals(Ctx* c, Map& mp, int k);  // fills mp.normals for every valid point of mp (cached per k)
-int gicp_lm_step(Ctx* c, const RegParams* d_prm, RegState* d_st, int iter);
+int gicp_lm_step(Ctx* c, const RegParams* d_prm, RegState* d_st, int iter, int nscan = 1);  // one block per scan
 
 // doppler.cu
 int doppler_filter(Ctx* c, const float* d_rec, int n, int iterations, uint64_t seed, double sigma, double split, uint8_t* d_mask,

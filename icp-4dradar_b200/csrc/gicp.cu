@@ -195,8 +195,8 @@ __global__ void __launch_bounds__(128) normals_from_idx_kernel(const float4* __r
     normals[3 * (size_t)i + 2] = nrm[2];
 }
 
-int gicp_normals_small(Ctx* c, const float4* d_pts, int n, int k, DevBuf& normals) {
-    CKS(reserve_grow(c, normals, (size_t)std::max(n, 1) * 3 * sizeof(double)));
+// normals of the n points at d_pts from their own k nearest neighbours, written to `out` (3 doubles per point, device)
+int gicp_normals_small_to(Ctx* c, const float4* d_pts, int n, int k, double* out) {
     if (n <= 0) return ICP4R_OK;
     CKS(reserve_grow(c, c->gs_pts, (size_t)n * sizeof(float4)));
     CKS(reserve_grow(c, c->gs_idx, (size_t)n * k * sizeof(int32_t)));
@@ -205,7 +205,6 @@ int gicp_normals_small(Ctx* c, const float4* d_pts, int n, int k, DevBuf& normal
     stamp_index_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(d_pts, n, c->gs_pts.as<float4>());
     c->launches += 1;
     CKS(brute_knn_cloud(c, c->gs_pts.as<float4>(), n, d_pts, n, k, 0.0, c->gs_idx.as<int32_t>(), c->gs_d2.as<float>(), c->gs_found.as<int32_t>()));
-    double* out = normals.as<double>();
     const int blocks = (n + 127) / 128;
     if (k <= 5) normals_from_idx_kernel<5><<<blocks, 128, 0, c->stream>>>(d_pts, c->gs_idx.as<int32_t>(), c->gs_found.as<int32_t>(), n, k, out);
     else if (k <= 8) normals_from_idx_kernel<8><<<blocks, 128, 0, c->stream>>>(d_pts, c->gs_idx.as<int32_t>(), c->gs_found.as<int32_t>(), n, k, out);
@@ -213,6 +212,11 @@ int gicp_normals_small(Ctx* c, const float4* d_pts, int n, int k, DevBuf& normal
     c->launches += 1;
     CK(cudaGetLastError());
     return ICP4R_OK;
+}
+
+int gicp_normals_small(Ctx* c, const float4* d_pts, int n, int k, DevBuf& normals) {
+    CKS(reserve_grow(c, normals, (size_t)std::max(n, 1) * 3 * sizeof(double)));
+    return gicp_normals_small_to(c, d_pts, n, k, normals.as<double>());
 }
 
 int gicp_normals(Ctx* c, Map& mp, int k) {
@@ -252,6 +256,8 @@ __device__ __forceinline__ bool delta_converged(const double* D /*3x4*/, double 
 // fast_gicp LsqRegistration::step_lm for one outer iteration: st->acc holds H (21), g (6), y0, count of the
 // linearisation at st->T; P.corr holds each source point's correspondence and L^-1.
 __global__ void __launch_bounds__(LM_THREADS) gicp_lm_kernel(const RegParams* __restrict__ prm, RegState* __restrict__ st, int iter) {
+    prm += blockIdx.x;  // one block per scan of a batched call
+    st += blockIdx.x;
     if (st->done) return;
     __shared__ double Hs[ICP4R_ACC_LEN], Hl[ICP4R_ACC_LEN], Ts[16], Xi[16], Ds[16], xi6[8], red[32];
     __shared__ double s_lambda, s_nu;
@@ -358,8 +364,8 @@ __global__ void __launch_bounds__(LM_THREADS) gicp_lm_kernel(const RegParams* __
     }
 }
 
-int gicp_lm_step(Ctx* c, const RegParams* d_prm, RegState* d_st, int iter) {
-    gicp_lm_kernel<<<1, LM_THREADS, 0, c->stream>>>(d_prm, d_st, iter);
+int gicp_lm_step(Ctx* c, const RegParams* d_prm, RegState* d_st, int iter, int nscan) {
+    gicp_lm_kernel<<<nscan, LM_THREADS, 0, c->stream>>>(d_prm, d_st, iter);
     c->launches += 1;
     return ICP4R_OK;
 }

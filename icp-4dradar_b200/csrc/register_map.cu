@@ -153,7 +153,7 @@ __device__ __forceinline__ void warp_solve_and_update(int residual, const RegPar
         const double mse = tot[16] / cnt;
         if (lane == 0) st->last_cost = mse;
         if (P.early_exit) {
-            if (fabs(mse - st->mse_prev) < P.mse_abs_eps) {
+            if (fabs(mse - __ldcg(&st->mse_prev)) < P.mse_abs_eps) {
                 stop = true;
                 conv = true;
             } else if (lane == 0) {
@@ -227,10 +227,12 @@ __device__ void write_result(const RegState* st, ResultBlock* out) {
 // the slowest point sets the time) and its extra registers only cost.
 // FLAVOUR 0: lean, 1: with the keep-the-neighbours proof (LB), 2: block-chunked work distribution without the proof
 // (slab-sharded maps: the ownership test needs the per-block lists, the proof does not pay on the maps that get sharded)
+// Returns true in the block that finished last (the one that reduced and solved). `load_p`: (re)load the per-call
+// parameter block into shared memory — the persistent loop below does it once, not every iteration.
 template <int KIND, int K, int MODE, int FLAVOUR>
-__global__ void __launch_bounds__(RM_THREADS, RM_BLOCKS_PER_SM)
-    reg_iter_kernel(GridDesc g, const RegParams* __restrict__ prm, RegState* __restrict__ st,
-                    double* __restrict__ partials, ResultBlock* __restrict__ out, int iter) {
+__device__ __forceinline__ bool reg_iter_body(const GridDesc& g, const RegParams* __restrict__ prm, RegState* __restrict__ st,
+                                              double* __restrict__ partials, ResultBlock* __restrict__ out, const int iter, const bool load_p,
+                                              const bool check_done = true) {
     constexpr bool FIT = (MODE == MODE_FITNESS || MODE == MODE_FITNESS_NOFINAL);
     constexpr bool LB = FLAVOUR == 1;
     constexpr bool CHUNKED = FLAVOUR != 0;
@@ -242,10 +244,12 @@ __global__ void __launch_bounds__(RM_THREADS, RM_BLOCKS_PER_SM)
     st += blockIdx.y;
     partials += (size_t)blockIdx.y * gridDim.x * ICP4R_ACC_LEN;
     out += blockIdx.y;
-    if (!FIT && st->done) return;
+    // (state another block wrote during an earlier iteration of the SAME launch — the persistent loop — must not come
+    // out of this SM's L1: volatile / ld.cg)
+    if (!FIT && check_done && *reinterpret_cast<volatile int*>(&st->done)) return false;  // (the persistent loop looks once per block)
     if (FIT && st->xch_timeout) {  // a sharded loop that lost a peer: nothing to measure, hand the flag to the host
         if (MODE == MODE_FITNESS && blockIdx.x == 0 && threadIdx.x == 0) write_result(st, out);
-        return;
+        return false;
     }
 
     __shared__ WarpSegs segs[RM_WARPS];
@@ -271,10 +275,10 @@ __global__ void __launch_bounds__(RM_THREADS, RM_BLOCKS_PER_SM)
     __shared__ float s_dA[12];  // displacement map of the last pose increment and the pass it belongs to (publish_increment)
     __shared__ int s_last_pass;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    if (tid < 16) Ts[tid] = st->T[tid];
-    if (tid >= 16 && tid < 28) s_dA[tid - 16] = st->dA[tid - 16];
-    if (tid == 28) s_last_pass = st->last_pass;
-    if (tid >= 32 && tid < 32 + (int)(sizeof(RegParams) / 4)) reinterpret_cast<uint32_t*>(&P)[tid - 32] = reinterpret_cast<const uint32_t*>(prm)[tid - 32];
+    if (tid < 16) Ts[tid] = __ldcg(&st->T[tid]);
+    if (tid >= 16 && tid < 28) s_dA[tid - 16] = __ldcg(&st->dA[tid - 16]);
+    if (tid == 28) s_last_pass = __ldcg(&st->last_pass);
+    if (load_p && tid >= 32 && tid < 32 + (int)(sizeof(RegParams) / 4)) reinterpret_cast<uint32_t*>(&P)[tid - 32] = reinterpret_cast<const uint32_t*>(prm)[tid - 32];
     __syncthreads();
     // RadarEdgeFactor / LidarPlaneFactor with an interpolation ratio s != 1 (radarFactor.hpp:26-32,78-84): the point is
     // placed with T_s = (slerp(I, q, s), s t) instead of T, for the search and for the residual alike. Under the left
@@ -863,7 +867,7 @@ __global__ void __launch_bounds__(RM_THREADS, RM_BLOCKS_PER_SM)
         }
     }
     __syncthreads();
-    if (!is_last) return;
+    if (!is_last) return false;
 #ifdef ICP4R_PHASE_TIMING
     const long long tp3 = clock64();
 #endif
@@ -949,7 +953,7 @@ __global__ void __launch_bounds__(RM_THREADS, RM_BLOCKS_PER_SM)
         __syncthreads();
         if (*reinterpret_cast<volatile int*>(&st->xch_timeout)) {
             if (MODE == MODE_FITNESS && tid == 0) write_result(st, out);
-            return;
+            return true;
         }
     }
     if (FIT) {
@@ -963,7 +967,7 @@ __global__ void __launch_bounds__(RM_THREADS, RM_BLOCKS_PER_SM)
                 st->acc[1] = tot[16];
             }
         }
-        return;
+        return true;
     }
     if (tid < ICP4R_ACC_LEN) {
         if (P.dump_acc) P.dump_acc[(size_t)iter * ICP4R_ACC_LEN + tid] = tot[tid];
@@ -982,6 +986,49 @@ __global__ void __launch_bounds__(RM_THREADS, RM_BLOCKS_PER_SM)
         dbg[2] = (unsigned long long)(clock64() - tp4);  // solve
     }
 #endif
+    return true;
+}
+
+template <int KIND, int K, int MODE, int FLAVOUR>
+__global__ void __launch_bounds__(RM_THREADS, RM_BLOCKS_PER_SM)
+    reg_iter_kernel(GridDesc g, const RegParams* __restrict__ prm, RegState* __restrict__ st,
+                    double* __restrict__ partials, ResultBlock* __restrict__ out, int iter) {
+    reg_iter_body<KIND, K, MODE, FLAVOUR>(g, prm, st, partials, out, iter, true);
+}
+
+// The whole iteration loop of ONE scan as ONE persistent launch (cooperative: every block is resident, one per SM).
+// Iterations [it0, it1) of the lean flavour run back to back inside the kernel; what separates two iterations is no
+// longer a kernel boundary (launch gap, parameter reload, cold L1) but a grid-wide hand-over built on the ticket the
+// iteration already takes: the block that finishes last reduces, solves, updates the pose and then publishes
+// st->loop_epoch = iteration + 1 (release); thread 0 of every other block spins on that word (acquire) and the block
+// moves on. Early exit leaves the loop on the device (st->done), so there is no look at a flag from the host either.
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+template <int KIND, int K>
+__global__ void __launch_bounds__(RM_THREADS, RM_BLOCKS_PER_SM)
+    reg_loop_kernel(GridDesc g, const RegParams* __restrict__ prm, RegState* __restrict__ st, double* __restrict__ partials,
+                    ResultBlock* __restrict__ out, int it0, int it1) {
+    __shared__ int s_done;  // one thread per block looks at the global flag: 130 k threads polling one L2 line would serialise
+    for (int it = it0; it < it1; ++it) {
+        const bool last = reg_iter_body<KIND, K, MODE_ITER, 0>(g, prm, st, partials, out, it, it == it0, false);
+        __syncthreads();  // the last block's warp 0 has written the new pose; everybody is done with the shared scratch
+        if (threadIdx.x == 0) {
+            if (last) {
+                st_release_gpu(&st->loop_epoch, it + 1);
+            } else {
+                while (ld_acquire_gpu(&st->loop_epoch) < it + 1) {
+                }
+            }
+            s_done = *reinterpret_cast<volatile int*>(&st->done);
+        }
+        __syncthreads();
+        if (s_done) break;
+    }
 }
 
 // sharded path: solve after the cross-rank sum of st->acc
@@ -1023,6 +1070,7 @@ __global__ void init_state_kernel(RegState* st, const double* T0) {
         st->n_corr = 0;
         st->ticket = 0;
         st->ticket_fit = 0;
+        st->loop_epoch = 0;
         st->last_pass = -1;
     }
 }
@@ -1095,6 +1143,28 @@ static void dispatch_iter(Ctx* c, int kind, int K, int mode, int blocks, int thr
             else if (K <= 8) launch_iter<ICP4R_P2PLANE_KNN, 8>(c, mode, blocks, threads, nscan, g, prm, st, partials, out, iter, lb);
             else launch_iter<ICP4R_P2PLANE_KNN, 16>(c, mode, blocks, threads, nscan, g, prm, st, partials, out, iter, lb);
             break;
+    }
+}
+
+// persistent loop (reg_loop_kernel): cooperative launch, lean flavour, one scan
+template <int KIND, int K>
+static cudaError_t launch_loop_kind(Ctx* c, int blocks, int threads, GridDesc g, const RegParams* prm, RegState* st, double* partials,
+                                    ResultBlock* out, int it0, int it1) {
+    void* args[] = {&g, &prm, &st, &partials, &out, &it0, &it1};
+    return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&reg_loop_kernel<KIND, K>), dim3(blocks), dim3(threads), args, 0, c->stream);
+}
+static cudaError_t launch_loop(Ctx* c, int kind, int K, int blocks, int threads, const GridDesc& g, const RegParams* prm, RegState* st,
+                               double* partials, ResultBlock* out, int it0, int it1) {
+    c->launches += 1;
+    switch (kind) {
+        case ICP4R_P2P_SVD: return launch_loop_kind<ICP4R_P2P_SVD, 1>(c, blocks, threads, g, prm, st, partials, out, it0, it1);
+        case ICP4R_P2P_GN: return launch_loop_kind<ICP4R_P2P_GN, 1>(c, blocks, threads, g, prm, st, partials, out, it0, it1);
+        case ICP4R_P2LINE: return launch_loop_kind<ICP4R_P2LINE, 2>(c, blocks, threads, g, prm, st, partials, out, it0, it1);
+        case ICP4R_P2PLANE_3PT: return launch_loop_kind<ICP4R_P2PLANE_3PT, 5>(c, blocks, threads, g, prm, st, partials, out, it0, it1);
+        default:
+            if (K <= 5) return launch_loop_kind<ICP4R_P2PLANE_KNN, 5>(c, blocks, threads, g, prm, st, partials, out, it0, it1);
+            if (K <= 8) return launch_loop_kind<ICP4R_P2PLANE_KNN, 8>(c, blocks, threads, g, prm, st, partials, out, it0, it1);
+            return launch_loop_kind<ICP4R_P2PLANE_KNN, 16>(c, blocks, threads, g, prm, st, partials, out, it0, it1);
     }
 }
 
@@ -1290,6 +1360,25 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
             c->prof_events.push_back(e);
         }
     }
+    // One scan, lean flavour, not sharded, not GICP: the whole loop is ONE cooperative launch (reg_loop_kernel) followed by
+    // the fitness launch — no graph, no chunks, no look at the done flag from the host. The grid is one block per SM
+    // at most, so all of it is resident, which is what the in-kernel hand-over between iterations needs.
+    if (c->use_persist && c->coop_ok && !sharded && !gicp && !prof && lb == 0 && n > 0 && iters > 0 && blocks <= c->sm_count * RM_BLOCKS_PER_SM) {
+        const cudaError_t le = launch_loop(c, o->residual, k, blocks, threads, g, d_prm, d_st, d_part, d_out, 0, iters);
+        if (le == cudaSuccess) {
+            dispatch_iter(c, o->residual, k, MODE_FITNESS, blocks, threads, 1, g, d_prm, d_st, d_part, d_out, 0, lb);
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(&hs->out, d_out, sizeof(ResultBlock), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            c->prof_ms.clear();
+            if (T_out_host) std::memcpy(T_out_host, hs->out.T, sizeof(hs->out.T));
+            if (res_host) *res_host = hs->out.res;
+            return ICP4R_OK;
+        }
+        cudaGetLastError();  // a device / driver that refuses the cooperative launch: the per-iteration path below
+        c->coop_ok = false;
+        c->launches -= 1;
+    }
     const bool want_graph = c->use_graph && n > 0 && !c->profiling && !(sharded && c->no_graph_sharded) && iters < 4096;
     if (want_graph) {
         // graphs bake the grid geometry by value: drop them when it changed
@@ -1471,8 +1560,26 @@ int accumulate_slab(Ctx* c, Map& mp, const float4* d_src, int n, const icp4r_opt
 int register_scans_against_map(Ctx* c, Map& mp, const float4* d_src, const int32_t* off_host, int nscan, const icp4r_opts* o,
                                const double* T0s_host, double* T_out_host, icp4r_result* res_host) {
     if (!mp.built) return fail(c, ICP4R_ERR_STATE, "registration target has no built map");
-    if (o->residual == ICP4R_GICP) return fail(c, ICP4R_ERR_UNSUPPORTED, "batched scans do not support ICP4R_GICP (per-scan covariances)");
     if (o->residual < 0 || o->residual > ICP4R_P2PLANE_3PT) return fail(c, ICP4R_ERR_INVALID, "bad residual kind %d", o->residual);
+    const bool gicp = o->residual == ICP4R_GICP;
+    const int kc = std::min(std::max(o->k > 0 ? o->k : 20, 3), ICP4R_MAX_K);  // GICP: neighbours per covariance
+    if (gicp) {
+        // fast_gicp per scan: the map's covariances are shared (cached per k), every scan gets its own (exhaustive k-NN
+        // inside the scan), its own correspondence table and its own Levenberg-Marquardt state; one linearisation launch
+        // (gridDim.y = scan) and one LM launch (one block per scan) per outer iteration serve the whole batch.
+        int nmax_all = 0;
+        for (int b = 0; b < nscan; ++b) nmax_all = std::max(nmax_all, off_host[b + 1] - off_host[b]);
+        if (nmax_all > 8192) {  // scans too large for the exhaustive covariance search: one after the other
+            for (int b = 0; b < nscan; ++b) {
+                icp4r_opts ob = *o;
+                if (T0s_host) std::memcpy(ob.T0, T0s_host + 16 * (size_t)b, sizeof(ob.T0));
+                CKS(register_against_map(c, mp, d_src + off_host[b], off_host[b + 1] - off_host[b], &ob, -1, 0.f, 0.f,
+                                         T_out_host ? T_out_host + 16 * (size_t)b : nullptr, res_host ? res_host + b : nullptr, nullptr));
+            }
+            return ICP4R_OK;
+        }
+        CKS(gicp_normals(c, mp, kc));
+    }
     const int k = knn_k_for(o);
     if (k > ICP4R_MAX_K) return fail(c, ICP4R_ERR_INVALID, "k=%d exceeds ICP4R_MAX_K", k);
     if (o->residual == ICP4R_P2PLANE_KNN && k < 3) return fail(c, ICP4R_ERR_INVALID, "P2PLANE_KNN needs k >= 3");
@@ -1506,7 +1613,15 @@ int register_scans_against_map(Ctx* c, Map& mp, const float4* d_src, const int32
         CKS(reserve_grow(c, c->bm_partials, (size_t)B * blocks * ICP4R_ACC_LEN * sizeof(double)));
         CKS(reserve_grow(c, c->d_nbprev, (size_t)off_host[s0 + B] * ICP4R_MAX_K * sizeof(int32_t)));
         const bool interp = o->interp_s > 0.0 && o->interp_s != 1.0 && (o->residual == ICP4R_P2LINE || o->residual == ICP4R_P2PLANE_3PT);
-        const bool use_lb = c->use_hints && c->use_lb && !interp && o->max_iterations < 4096 && (nmax + blocks - 1) / blocks >= 8 * wpb;
+        const bool use_lb = c->use_hints && c->use_lb && !interp && !gicp && o->max_iterations < 4096 && (nmax + blocks - 1) / blocks >= 8 * wpb;
+        if (gicp) {
+            const int base = off_host[s0], tot = off_host[s0 + B] - base;
+            CKS(reserve_grow(c, c->srcmap.normals, (size_t)std::max(tot, 1) * 3 * sizeof(double)));
+            CKS(reserve_grow(c, c->d_gicp_corr, (size_t)std::max(tot, 1) * sizeof(GicpCorr)));
+            for (int b = 0; b < B; ++b)
+                CKS(gicp_normals_small_to(c, d_src + off_host[s0 + b], off_host[s0 + b + 1] - off_host[s0 + b], kc,
+                                          c->srcmap.normals.as<double>() + 3 * (size_t)(off_host[s0 + b] - base)));
+        }
         if (use_lb) {
             const void* before = c->d_nbstate.p;
             CKS(reserve_grow(c, c->d_nbstate, (size_t)std::max(off_host[s0 + B], 1) * sizeof(NbState)));
@@ -1531,7 +1646,6 @@ int register_scans_against_map(Ctx* c, Map& mp, const float4* d_src, const int32
             P.mse_abs_eps = o->mse_abs_eps;
             P.plane_thresh = o->plane_thresh;
             P.interp_s = (o->interp_s > 0.0 && (o->residual == ICP4R_P2LINE || o->residual == ICP4R_P2PLANE_3PT)) ? o->interp_s : 1.0;
-    P.interp_s = (o->interp_s > 0.0 && (o->residual == ICP4R_P2LINE || o->residual == ICP4R_P2PLANE_3PT)) ? o->interp_s : 1.0;
             P.map_sorted = mp.grid.sorted;
             P.map_cell_start = mp.grid.cell_start;
             P.map_coarse = mp.grid.coarse;
@@ -1542,6 +1656,13 @@ int register_scans_against_map(Ctx* c, Map& mp, const float4* d_src, const int32
             P.nb_prev = c->use_hints ? c->d_nbprev.as<int32_t>() + (size_t)off_host[s0 + b] * ICP4R_MAX_K : nullptr;
             P.nb_state = use_lb ? c->d_nbstate.as<NbState>() + off_host[s0 + b] : nullptr;
             P.epoch = c->reg_epoch & 0x3FFFF;
+            if (gicp) {
+                const size_t rel = (size_t)(off_host[s0 + b] - off_host[s0]);
+                P.src_normals = c->srcmap.normals.as<double>() + 3 * rel;
+                P.tgt_normals = mp.normals.as<double>();
+                P.tgt_pts = mp.pts.as<float4>();
+                P.corr = c->d_gicp_corr.as<GicpCorr>() + rel;
+            }
             std::memcpy(hs[b].T0, T0s_host ? T0s_host + 16 * (size_t)(s0 + b) : o->T0, sizeof(hs[b].T0));
         }
         RegParams* d_prm = c->bm_params.as<RegParams>();
@@ -1553,52 +1674,82 @@ int register_scans_against_map(Ctx* c, Map& mp, const float4* d_src, const int32
         CK(cudaMemcpy2DAsync(c->bm_T0.p, 16 * sizeof(double), hs[0].T0, sizeof(Stage), 16 * sizeof(double), B, cudaMemcpyHostToDevice, c->stream));
         init_state_kernel<<<B, 32, 0, c->stream>>>(d_st, c->bm_T0.as<double>());
         c->launches += 1;
-        auto enqueue = [&]() {
-            for (int it = 0; it < iters; ++it) dispatch_iter(c, o->residual, k, MODE_ITER, blocks, threads, B, g, d_prm, d_st, d_part, d_out, it, use_lb ? 1 : 0);
-            dispatch_iter(c, o->residual, k, MODE_FITNESS, blocks, threads, B, g, d_prm, d_st, d_part, d_out, 0, use_lb ? 1 : 0);
-        };
-        const bool want_graph = c->use_graph && !c->profiling;
-        GraphKey key{o->residual, k, blocks, iters + (use_lb ? 8192 : 0), threads | (1 << 18) | (B << 20)};
-        cudaGraphExec_t exec = nullptr;
-        if (want_graph) {
-            if (moved || c->graph_grid_owner != &mp.grid || std::memcmp(&c->graph_grid_copy, &g, sizeof(GridDesc)) != 0) {
-                for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
-                c->graphs.clear();
-                c->graph_grid_owner = &mp.grid;
-                c->graph_grid_copy = g;
-            }
-            auto itg = c->graphs.find(key);
-            if (itg != c->graphs.end()) exec = itg->second;
-            if (!exec) {
-                cudaGraph_t graph = nullptr;
-                cudaStream_t run_stream = c->stream;
-                c->stream = c->own_stream;
-                cudaError_t ce = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
-                if (ce == cudaSuccess) {
-                    const int64_t before = c->launches;
-                    enqueue();
-                    c->graph_launches = c->launches - before;
-                    c->launches = before;
-                    ce = cudaStreamEndCapture(c->stream, &graph);
-                }
-                c->stream = run_stream;  // restored on every path
-                if (ce == cudaSuccess) ce = cudaGraphInstantiate(&exec, graph, 0);
-                if (graph) cudaGraphDestroy(graph);
-                if (ce != cudaSuccess) {  // capture is an optimisation: run the loop as direct launches instead
-                    cudaGetLastError();
-                    exec = nullptr;
-                    c->use_graph = false;
+        // iterations [it0, it1) of every scan and, if `fit`, the fitness pass
+        auto enqueue = [&](int it0, int it1, bool fit) {
+            for (int it = it0; it < it1; ++it) {
+                if (gicp) {  // linearise every scan (accumulators left in its st->acc), then one LM step per scan
+                    dispatch_iter(c, o->residual, k, MODE_ITER_NOSOLVE, blocks, threads, B, g, d_prm, d_st, d_part, d_out, it, 0);
+                    gicp_lm_step(c, d_prm, d_st, it, B);
                 } else {
-                    c->graphs[key] = exec;
-                    c->graph_launch_counts[key] = c->graph_launches;
+                    dispatch_iter(c, o->residual, k, MODE_ITER, blocks, threads, B, g, d_prm, d_st, d_part, d_out, it, use_lb ? 1 : 0);
                 }
             }
+            if (fit) dispatch_iter(c, o->residual, k, MODE_FITNESS, blocks, threads, B, g, d_prm, d_st, d_part, d_out, 0, use_lb ? 1 : 0);
+        };
+        const bool want_graph = c->use_graph && !c->profiling && iters < 4096;
+        if (want_graph && (moved || c->graph_grid_owner != &mp.grid || std::memcmp(&c->graph_grid_copy, &g, sizeof(GridDesc)) != 0)) {
+            for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+            c->graphs.clear();
+            c->graph_grid_owner = &mp.grid;
+            c->graph_grid_copy = g;
         }
-        if (exec) {
-            CK(cudaGraphLaunch(exec, c->stream));
-            c->launches += c->graph_launch_counts[key];
+        auto run_range = [&](int it0, int it1, bool fit) -> int {
+            GraphKey key{o->residual, k, blocks, it0 + 4096 * it1,
+                         threads | (use_lb ? 1 << 16 : 0) | (gicp ? 1 << 17 : 0) | (1 << 18) | (fit ? 1 << 19 : 0) | (B << 20)};
+            cudaGraphExec_t exec = nullptr;
+            if (want_graph && c->use_graph) {
+                auto itg = c->graphs.find(key);
+                if (itg != c->graphs.end()) exec = itg->second;
+                if (!exec) {
+                    cudaGraph_t graph = nullptr;
+                    cudaStream_t run_stream = c->stream;
+                    c->stream = c->own_stream;
+                    cudaError_t ce = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
+                    if (ce == cudaSuccess) {
+                        const int64_t before = c->launches;
+                        enqueue(it0, it1, fit);
+                        c->graph_launches = c->launches - before;
+                        c->launches = before;
+                        ce = cudaStreamEndCapture(c->stream, &graph);
+                    }
+                    c->stream = run_stream;  // restored on every path
+                    if (ce == cudaSuccess) ce = cudaGraphInstantiate(&exec, graph, 0);
+                    if (graph) cudaGraphDestroy(graph);
+                    if (ce != cudaSuccess) {  // capture is an optimisation: run the loop as direct launches instead
+                        cudaGetLastError();
+                        exec = nullptr;
+                        c->use_graph = false;
+                    } else {
+                        c->graphs[key] = exec;
+                        c->graph_launch_counts[key] = c->graph_launches;
+                    }
+                }
+            }
+            if (exec) {
+                CK(cudaGraphLaunch(exec, c->stream));
+                c->launches += c->graph_launch_counts[key];
+            } else {
+                enqueue(it0, it1, fit);
+            }
+            return ICP4R_OK;
+        };
+        // loops with early exit and a long budget (fast_gicp: 64) run in chunks with a look at the scans' `done` flags in
+        // between, like the single-scan path: the launches after convergence are no-ops but not free
+        constexpr int CHUNK = 8;
+        if (!(o->early_exit && iters > CHUNK + CHUNK / 2)) {
+            CKS(run_range(0, iters, true));
         } else {
-            enqueue();
+            std::vector<int> done(B);
+            for (int it0 = 0; it0 < iters; it0 += CHUNK) {
+                CKS(run_range(it0, std::min(it0 + CHUNK, iters), false));
+                CK(cudaMemcpy2DAsync(done.data(), sizeof(int), reinterpret_cast<const char*>(d_st) + offsetof(RegState, done), sizeof(RegState),
+                                     sizeof(int), B, cudaMemcpyDeviceToHost, c->stream));
+                CK(cudaStreamSynchronize(c->stream));
+                bool all = true;
+                for (int b = 0; b < B; ++b) all = all && done[b] != 0;
+                if (all) break;
+            }
+            CKS(run_range(0, 0, true));
         }
         CK(cudaGetLastError());
         CK(cudaMemcpy2DAsync(&hs[0].out, sizeof(Stage), d_out, sizeof(ResultBlock), sizeof(ResultBlock), B, cudaMemcpyDeviceToHost, c->stream));

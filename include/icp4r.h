@@ -115,6 +115,14 @@ const char* icp4r_version(void);
 int icp4r_default_opts(icp4r_opts* o);
 /* run on an existing cudaStream_t (e.g. the harness' current stream) instead of the handle's own */
 int icp4r_set_stream(icp4r_handle h, void* cuda_stream);
+/* Layout of the point-cloud INPUT rows (every `*_xyzw` input parameter) of the calls that follow, host or device:
+ * row i starts at byte i * stride_bytes and holds x, y, z as floats at bytes 0, 4, 8 and w at byte w_offset_bytes
+ * (< 0: no w, 0 is stored). Default (16, 12) = packed x, y, z, w. pcl::PointXYZI, the reference's PointType
+ * (/root/reference/include/radar_odometry.h typedef, 32-byte rows, intensity at byte 16), is (32, 16): the adapters pass
+ * the reference's clouds as they lie in memory — the rows cross the bus unmodified and one device kernel repacks them,
+ * no host-side pack loop. stride_bytes: multiple of 4 in [12, 4096]. Point OUTPUTS are always packed x, y, z, w;
+ * the 5-float Doppler records (icp4r_doppler_*) have their own fixed layout. */
+int icp4r_set_point_layout(icp4r_handle h, int32_t stride_bytes, int32_t w_offset_bytes);
 /* Completion: every call that returns something in HOST memory (poses, results, counts, host output arrays) has
  * finished when it returns. Outputs the caller asked for in DEVICE memory (mem = ICP4R_DEVICE: neighbour tables,
  * transformed points, batched poses/results, dumps, filtered clouds) are ordered on the handle's stream: use them on

@@ -32,7 +32,7 @@ def test_only_sm100a_code(pkg):
 
 
 def test_struct_layouts(pkg, O):
-    assert C.sizeof(pkg.Opts) == C.sizeof(O.OrcOpts) == 4 * 4 + 5 * 8 + 16 * 8
+    assert C.sizeof(pkg.Opts) == C.sizeof(O.OrcOpts) == 4 * 4 + 5 * 8 + 16 * 8 + 8  # ... + interp_s
     assert C.sizeof(pkg.Result) == C.sizeof(O.OrcResult) == 32
     o = pkg.default_opts()
     assert (o.residual, o.k, o.max_iterations, o.early_exit) == (pkg.P2P_SVD, 5, 10, 0)

@@ -342,3 +342,38 @@ def test_large_host_batch_is_pipelined_and_equal(pkg, monkeypatch):
     fast.close()
     rdn = rd.cpu().numpy().view(pkg.api.RESULT_DTYPE).reshape(-1)
     assert (rh["n_corr"] == rdn["n_corr"]).all() and (rh["iterations"] == rdn["iterations"]).all()
+
+
+def test_persistent_loop_equals_per_iteration_launches(pkg):
+    """ICP4R_PERSIST=1: single-scan loops run as ONE cooperative launch (reg_loop_kernel: grid-wide hand-over between
+    iterations inside the kernel); the result must be bit-identical to the default one-launch-per-iteration graph, with
+    and without early exit, for every residual kind of the scan-to-map call"""
+    import os
+    import bench
+    mp, scans = bench.make_c2()
+    scan = scans[0][:3000]
+    out = {}
+    for mode in ("persist", "launches"):
+        if mode == "persist":
+            os.environ["ICP4R_PERSIST"] = "1"
+        try:
+            h = pkg.Icp4r(0)
+        finally:
+            os.environ.pop("ICP4R_PERSIST", None)
+        h.map_build(mp)
+        rows = []
+        for kind, k in ((pkg.P2PLANE_KNN, 5), (pkg.P2PLANE_KNN, 8), (pkg.P2P_SVD, 1), (pkg.P2P_GN, 1), (pkg.P2LINE, 2), (pkg.P2PLANE_3PT, 3)):
+            for early, iters in ((0, 12), (1, 40)):
+                o = pkg.default_opts(residual=kind, k=k, max_iterations=iters, early_exit=early, max_corr_dist=2.0,
+                                     rot_eps=1e-5, trans_eps=1e-5, mse_abs_eps=1e-9)
+                n0 = h.launch_count()
+                T, r, _ = h.register_map(scan, o)
+                T2, r2, _ = h.register_map(scan, o)   # and again: the hand-over word starts from zero every call
+                assert np.array_equal(T, T2)
+                rows.append((T, r.converged, r.iterations, r.n_corr, r.fitness, h.launch_count() - n0))
+        out[mode] = rows
+        h.close()
+    for a, b in zip(out["persist"], out["launches"]):
+        assert np.array_equal(a[0], b[0]) and a[1:5] == b[1:5], (a, b)
+        assert a[5] == 2 * 3, a[5]          # init + loop + fitness, twice
+        assert b[5] > a[5]
