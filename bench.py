@@ -68,12 +68,14 @@ def ncu_facts(kernel_key):
     return json.load(open(p)).get(kernel_key)
 
 
-def roofline(kernel, kernel_key, alg_bytes, kernel_ms, note, dist_evals=None, extra=None):
+def roofline(kernel, kernel_key, alg_bytes, kernel_ms, note, dist_evals=None, extra=None, traffic_scale=1.0):
+    """traffic_scale: the ncu capture processed fewer units than one bench launch does (e.g. 2,048 of the 65,536 pairs):
+    its DRAM bytes are scaled to the launch `achieved` is quoted on"""
     peak, peak_src = peaks()
     ach = alg_bytes / (kernel_ms * 1e-3) / 1e9
     facts = ncu_facts(kernel_key)
     r = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-         "traffic": (facts["dram_bytes_read"] + facts["dram_bytes_write"]) if facts else None,
+         "traffic": (facts["dram_bytes_read"] + facts["dram_bytes_write"]) * traffic_scale if facts else None,
          "kernel": kernel, "kernel_ms": kernel_ms, "algorithmic_bytes": int(alg_bytes), "peak_source": peak_src, "note": note}
     if facts:
         r["ncu"] = {k: facts[k] for k in facts if k not in ("dram_bytes_read", "dram_bytes_write")}
@@ -600,7 +602,7 @@ class Bench:
             rec["roofline"] = roofline("reg_batch_kernel<P2P_SVD,256>", "reg_batch_kernel", alg, m["ms_per_step"],
                                        "resident design: each pair is read from HBM once (65.8 KB) and iterated 31 times in shared memory; "
                                        "the kernel is bound by instruction issue and the per-iteration barrier/solve chain, see DESIGN.md",
-                                       dist_evals=evals, extra=extra)
+                                       dist_evals=evals, extra=extra, traffic_scale=mine / 2048.0)   # the capture ran 2,048 pairs
             if self.world == 1 and not self.args.no_cpu_baseline:
                 k1, d1, s1 = cpu_pairs(src, tgt, C4_N, C4_ITERS, 10.0, 1)
                 kN, dN, sN = cpu_pairs(src, tgt, C4_N, C4_ITERS, 12.0, self.threads, max_pairs=max(self.threads * 4, 64))
@@ -893,6 +895,113 @@ class Bench:
         return rec
 
 
+    # ---- streaming kernels (HBM-bound by nature: where a roofline fraction means something) ------------------------
+    def run_streams(self):
+        """Build (KD_TREE::Build, ikd_Tree.cpp:354-365) of the 20 M-point C5 map, VoxelGrid over 20 M points
+        (radar_odometry.cpp:426-429) and Add_Points(false) of one 3,000-point scan into a 3 M-point map (radar_odometry.cpp:390):
+        device-resident input, CUDA events on the handle's stream around 5 calls each, points/s and the HBM roofline of the
+        whole call (all its kernels, host round trips for the grid geometry included)."""
+        torch, pkg, h = self.torch, self.pkg, self.h
+        peak, peak_src = peaks()
+
+        def timed_call(fn, reps=5, warm=2):
+            for _ in range(warm):
+                fn()
+            ts = []
+            for _ in range(reps):
+                self.flush.fill_(1)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                h.synchronize()
+                e0.record(self.stream)
+                fn()
+                h.synchronize()
+                e1.record(self.stream)
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            return float(np.median(ts))
+
+        def rec(name, what, n_pts, ms, alg_bytes, key, note):
+            facts = ncu_facts(key)
+            ach = alg_bytes / (ms * 1e-3) / 1e9
+            return {"metric": "points/s", "value": n_pts / (ms * 1e-3), "unit": "points/s", "ms_per_step": ms, "config": {"workload": what},
+                    "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                 "traffic": facts.get("dram_bytes") if facts else None, "kernel": name, "kernel_ms": ms,
+                                 "algorithmic_bytes": int(alg_bytes), "peak_source": peak_src, "note": note,
+                                 **({"ncu_kernels_us": facts.get("kernels_us")} if facts else {})}}
+
+        out = {}
+        m = self.args.map_points
+        with torch.cuda.stream(self.stream):
+            mp = torch.from_numpy(pkg.synth.dense_map(1005, m)).to(self.dev)
+            ms = timed_call(lambda: h.map_build(mp))
+            ncell = max(m // 8, 1)
+            out["build"] = rec("map build: bbox + bucket scatter + per-bucket shared-memory sort + coarse table", f"KD_TREE::Build of a {m}-point dense map (C5's map), device-resident points",
+                               m, ms, 32.0 * m + 4.0 * ncell, "stream_build",
+                               "algorithmic = 16 B read + 16 B written per point + the cell table; the build moves every point twice (bucket scatter, in-bucket sort) "
+                               "after a bounding-box pass: ~80 B of traffic per point, two host round trips for the grid geometry")
+            g = torch.Generator(device=self.dev).manual_seed(7)
+            p = torch.rand((m, 4), generator=g, device=self.dev)
+            p[:, 0] = (p[:, 0] - 0.5) * 400
+            p[:, 1] = (p[:, 1] - 0.5) * 400
+            p[:, 2] = (p[:, 2] - 0.5) * 20
+            vg_out = torch.empty((m, 4), dtype=torch.float32, device=self.dev)
+            leaves = [0]
+
+            def vg():
+                leaves[0] = int(h.voxel_grid_into(p, 0.5, vg_out))
+            ms = timed_call(vg)
+            out["voxel_grid"] = rec("icp4r_voxel_grid: min/max + leaf keys + radix sort + segmented mean", f"pcl::VoxelGrid 0.5 m over {m} points in a 400 x 400 x 20 m volume -> {leaves[0]} leaves",
+                                    m, ms, 16.0 * m + 16.0 * leaves[0], "stream_voxel_grid",
+                                    "algorithmic = 16 B read per point + 16 B written per leaf; the sort of (leaf key, index) pairs and the per-leaf gather of 16-byte "
+                                    "points from 32-byte sectors are what the traffic above that is")
+            del p, vg_out, mp
+            s_ = pkg.synth
+            rng = np.random.default_rng(1003)
+            sc = s_.Scene(1003, extent=400.0, n_walls=200)
+            h2 = pkg.Icp4r(self.local)
+            h2.set_stream(self.stream.cuda_stream)
+            m3 = 3_000_000
+            h2.map_build(torch.from_numpy(sc.sample(rng, m3)).to(self.dev))
+            ts = []
+            for f in range(12):
+                w = torch.from_numpy(sc.sample(rng, 3000, centre=(10.0 + f, 5.0), radius=80.0)).to(self.dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                h2.synchronize()
+                e0.record(self.stream)
+                h2.map_add_points(w, False)
+                h2.synchronize()
+                e1.record(self.stream)
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            ms = float(np.median(ts[2:]))
+            out["add_points"] = rec("incremental Add_Points: sort of the new keys + merge into the sorted map + cell-table shift",
+                                    f"KD_TREE::Add_Points(3,000 points, false) into a {m3}-point map (C3 per-frame shape)", 3000, ms, 32.0 * m3 + 4.0 * (m3 // 4),
+                                    "stream_add_points",
+                                    "algorithmic = the merge rewrites the sorted map (16 B read + 16 B written per MAP point) + the cell table; work is O(map), "
+                                    "not O(batch): a two-level table would change that (DESIGN.md §9)")
+            h2.close()
+        return out
+
+    # ---- the adapter boundary --------------------------------------------------------------------------------------
+    def run_adapters(self):
+        """end-to-end timings through the C++ adapters a maintainer of the reference would compile against (pageable
+        pcl::PointCloud<pcl::PointXYZI> clouds, every copy and allocation inside): adapters/bench_adapters.cpp"""
+        import subprocess
+        exe = os.path.join(ROOT, "icp-4dradar_b200", "adapters", "bench_adapters")
+        if not os.path.exists(exe):
+            return {"unavailable": "adapters/bench_adapters not built (make -C icp-4dradar_b200/adapters)"}
+        r = subprocess.run([exe], capture_output=True, text=True, timeout=300, env=dict(os.environ, CUDA_VISIBLE_DEVICES=str(self.local)))
+        if r.returncode != 0:
+            return {"unavailable": f"bench_adapters exited {r.returncode}: {r.stderr[-200:]}"}
+        d = json.loads(r.stdout.strip().splitlines()[-1])
+        return {"metric": "registrations/s", "value": d["c1_registrations_per_s"], "unit": "registrations/s",
+                "config": {"workload": "icp4r::IterativeClosestPoint<PointXYZI>::align on 1,024 + 1,024-point pageable PCL clouds, object constructed per frame "
+                                       "(iterative_closest_point.cpp:510-521), wall clock around the call; the other figures time KD_TREE::Build / "
+                                       "Nearest_Search / Sector_Search / Add_Points, FastGICPSingleThread::align and VoxelGrid::filter the same way"},
+                "e2e": {"value": d["c1_registrations_per_s"], "unit": "registrations/s", "h2d_bytes_per_step": 2 * 1024 * 32 * 2, "d2h_bytes_per_step": 1024 * 16 + 160},
+                "wall_ms": d}
+
+
 def strip(rec):
     rec.pop("_m", None)
     return rec
@@ -904,7 +1013,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="all", choices=["all", "c1", "c2", "c2single", "c3", "c3ref", "c4", "c5", "gicp"])
+    ap.add_argument("--workload", default="all", choices=["all", "c1", "c2", "c2single", "c3", "c3ref", "c4", "c5", "gicp", "streams"])
     ap.add_argument("--frames-ref", type=int, default=400, help="c3ref: raw radar frames of the node's own per-frame flow")
     ap.add_argument("--frames", type=int, default=2000, help="c3: frames of the odometry sequence (one step = the whole sequence)")
     ap.add_argument("--map-points", type=int, default=20_000_000, help="c5: points of the dense map (whole job)")
@@ -937,8 +1046,15 @@ def main():
                 configs["c3"] = strip(B.run_c3(2, 3))
                 configs["c3ref"] = strip(B.run_c3ref(2, 3))
                 configs["c5"] = strip(B.run_c5(max(5 * K, 30), 5))
+                configs["streams"] = B.run_streams()
+                configs["adapters"] = B.run_adapters()
             else:
                 configs["c5_sharded"] = strip(B.run_c5(max(5 * K, 30), 5))
+    elif wl == "streams":
+        if rank == 0:
+            print(json.dumps({"streams": B.run_streams(), "adapters": B.run_adapters()}), flush=True)
+        B.h.close()
+        return
     elif wl == "c1":
         rec = B.run_c1(K, W, main=True)
     elif wl in ("c2", "c2single"):

@@ -531,6 +531,14 @@ class Icp4r:
                                            C.c_int32(out.shape[0]), C.byref(cnt)))
         return out[:cnt.value].copy() if mem == HOST else out[:cnt.value]
 
+    def voxel_grid_into(self, pts, leaf: float, out) -> int:
+        """voxel_grid of a CUDA tensor into a caller-provided CUDA float32 [cap, 4] tensor; returns the number of leaves"""
+        pts = _f4(pts)
+        cnt = C.c_int32(0)
+        self._ck(self.lib.icp4r_voxel_grid(self.h, C.c_void_p(pts.data_ptr()), C.c_int32(pts.shape[0]), C.c_int(DEVICE), C.c_float(leaf),
+                                           C.c_void_p(out.data_ptr()), C.c_int32(out.shape[0]), C.byref(cnt)))
+        return cnt.value
+
     def transform_points(self, T, pts):
         pts = _f4(pts)
         p, mem = _ptr(pts)

@@ -757,6 +757,12 @@ static int register_transient(Ctx* c, const float* src, int32_t n, const float* 
     if (idx == nullptr) {
         CKS(set_points(c, mp, tgt, m, mem, 0));
     } else {
+        // a subset of the handle's map has the map's local density: its (occupancy-refined) cell size serves the sub-map
+        // as it is — one sort instead of up to three and no look at the occupancy from the host
+        if (c->map.built && c->map.grid.cell > 0.f) {
+            mp.hint_cell = c->map.grid.cell;
+            mp.quick_build = true;
+        }
         CKS(map_reserve(c, mp, m));
         const void* didx = nullptr;
         CKS(stage_in(c, c->d_idx, idx, (size_t)m * sizeof(int32_t), mem, &didx));

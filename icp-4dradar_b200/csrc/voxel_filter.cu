@@ -67,13 +67,36 @@ __global__ void __launch_bounds__(VG_THREADS) vg_minmax_kernel(const float4* __r
         }
         cnt += __shfl_xor_sync(FULL, cnt, o);
     }
-    if ((threadIdx.x & 31) == 0 && cnt > 0) {
+    // one set of atomics per block, not per warp (they serialise on seven words)
+    __shared__ float s_mn[VG_THREADS / 32][3], s_mx[VG_THREADS / 32][3];
+    __shared__ int s_cnt[VG_THREADS / 32];
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            atomicMin(bb + a, vg_f2ord(mn[a]));
-            atomicMax(bb + 3 + a, vg_f2ord(mx[a]));
+            s_mn[w][a] = mn[a];
+            s_mx[w][a] = mx[a];
         }
-        atomicAdd(bb + 6, cnt);
+        s_cnt[w] = cnt;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int j = 1; j < VG_THREADS / 32; ++j) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                mn[a] = fminf(mn[a], s_mn[j][a]);
+                mx[a] = fmaxf(mx[a], s_mx[j][a]);
+            }
+            cnt += s_cnt[j];
+        }
+        if (cnt > 0) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                atomicMin(bb + a, vg_f2ord(mn[a]));
+                atomicMax(bb + 3 + a, vg_f2ord(mx[a]));
+            }
+            atomicAdd(bb + 6, cnt);
+        }
     }
 }
 
@@ -215,7 +238,7 @@ int voxel_grid(Ctx* c, const float4* d_pts, const uint8_t* d_valid, int n, float
     CKS(reserve(c, c->d_scratch, 64));
     int* d_bb = c->d_scratch.as<int>();
     vg_minmax_init<<<1, 32, 0, c->stream>>>(d_bb);
-    vg_minmax_kernel<<<std::min((n + VG_THREADS - 1) / VG_THREADS, c->sm_count * 8), VG_THREADS, 0, c->stream>>>(d_pts, d_valid, n, d_bb);
+    vg_minmax_kernel<<<std::max(1, std::min((n + 8 * VG_THREADS - 1) / (8 * VG_THREADS), c->sm_count * 8)), VG_THREADS, 0, c->stream>>>(d_pts, d_valid, n, d_bb);
     c->launches += 2;
     int bb[7];
     CK(cudaMemcpyAsync(bb, d_bb, sizeof(bb), cudaMemcpyDeviceToHost, c->stream));
