@@ -6,6 +6,7 @@
 //     gain ratio, accept / re-damp — one single-block kernel per outer iteration.
 // [UPSTREAM, unpinned]: fast_gicp is not vendored by the reference; restated from its published algorithm.
 #include <cmath>
+#include <cstdlib>
 
 #include "ctx.h"
 #include "device_math.cuh"
@@ -64,13 +65,139 @@ __device__ __forceinline__ void smallest_eigvec3(const double C[9], double n[3])
     n[2] = v2 / len;
 }
 
+// covariance of `found` neighbour positions about their mean, divided by k (fast_gicp divides by k_correspondences_), and its
+// smallest eigenvector: the one arithmetic, in one order, behind every normals kernel of this file
+template <int K, typename NB>
+__device__ __forceinline__ void normal_of_neighbours(const NB& nb /* [K][3] floats */, int found, int k, double n[3]) {
+    double mean[3] = {0, 0, 0}, C[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        if (j < found) {
+            mean[0] += (double)nb[j][0];
+            mean[1] += (double)nb[j][1];
+            mean[2] += (double)nb[j][2];
+        }
+    }
+    const double fdiv = (double)(found > 0 ? found : 1);
+    mean[0] /= fdiv;
+    mean[1] /= fdiv;
+    mean[2] /= fdiv;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        if (j < found) {
+            const double d[3] = {(double)nb[j][0] - mean[0], (double)nb[j][1] - mean[1], (double)nb[j][2] - mean[2]};
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = 0; b < 3; ++b) C[3 * a + b] += d[a] * d[b];
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 9; ++a) C[a] /= (double)k;
+    smallest_eigvec3(C, n);
+}
+
+// Self k-NN of a whole cloud, ONE THREAD PER POINT in cell order (k <= 5, the reference's setCorrespondenceRandomness(5)).
+// The queries ARE the grid's points, so neighbouring threads sit in the same or adjacent cells and read the same few
+// rows of the sorted array (L1 hits); each thread ranks every point of the 3 x 3 x 3 cells around its own cell by
+// (d2, index) in registers. The answer is exact when the k-th distance found is smaller than the distance to the nearest
+// face of that cell block that has cells behind it; the points where it is not (sparse surroundings: a few per cent) go
+// to a list that the warp-per-query kernel below finishes. Same neighbours in the same order -> same normals, bit for bit,
+// as the warp-per-query kernel alone (4 x fewer executed instructions per point, no idle lanes).
+template <int K>
+__global__ void __launch_bounds__(128) normals_brick_kernel(GridDesc g, int k, double* __restrict__ normals, int* __restrict__ todo,
+                                                            int* __restrict__ todo_n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.m) return;
+    const float4 p = __ldg(g.sorted + i);
+    const int cx = cell_of(p.x, g.ox, g.inv_cell, g.nx), cy = cell_of(p.y, g.oy, g.inv_cell, g.ny), cz = cell_of(p.z, g.oz, g.inv_cell, g.nz);
+    const int xa = max(cx - 1, 0), xb = min(cx + 1, g.nx - 1);
+    const int y0 = max(cy - 1, 0), y1 = min(cy + 1, g.ny - 1);
+    const int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.nz - 1);
+    uint64_t key[K];
+    int slot[K];
+#pragma unroll
+    for (int t = 0; t < K; ++t) {
+        key[t] = KEY_EMPTY;
+        slot[t] = 0;
+    }
+    for (int z = z0; z <= z1; ++z)
+        for (int y = y0; y <= y1; ++y) {
+            const uint32_t rowbase = (uint32_t)(z * g.ny + y) * (uint32_t)g.nx;
+            const uint32_t s = __ldg(g.cell_start + rowbase + xa), e = __ldg(g.cell_start + rowbase + xb + 1);
+            for (uint32_t j = s; j < e; ++j) {
+                const float4 c = __ldg(g.sorted + j);
+                const float d = dist2_exact(p.x, p.y, p.z, c.x, c.y, c.z);
+                uint64_t cur = pack_key(d, __float_as_int(c.w));
+                if (cur < key[K - 1]) {  // ascending insertion, a chain of selects
+                    int cs_ = (int)j;
+#pragma unroll
+                    for (int t = 0; t < K; ++t) {
+                        const bool lt = cur < key[t];
+                        const uint64_t tk = lt ? key[t] : cur;
+                        const int ts = lt ? slot[t] : cs_;
+                        key[t] = lt ? cur : key[t];
+                        slot[t] = lt ? cs_ : slot[t];
+                        cur = tk;
+                        cs_ = ts;
+                    }
+                }
+            }
+        }
+    // faces of the visited block with cells behind them (the grid spans the cloud's bounding box: nothing lies outside it)
+    float bd = 3.4e38f;
+    if (xa > 0) bd = fminf(bd, p.x - (g.ox + (float)xa * g.cell));
+    if (xb < g.nx - 1) bd = fminf(bd, (g.ox + (float)(xb + 1) * g.cell) - p.x);
+    if (y0 > 0) bd = fminf(bd, p.y - (g.oy + (float)y0 * g.cell));
+    if (y1 < g.ny - 1) bd = fminf(bd, (g.oy + (float)(y1 + 1) * g.cell) - p.y);
+    if (z0 > 0) bd = fminf(bd, p.z - (g.oz + (float)z0 * g.cell));
+    if (z1 < g.nz - 1) bd = fminf(bd, (g.oz + (float)(z1 + 1) * g.cell) - p.z);
+    const int kk = min(k, K);
+    int found = 0;
+#pragma unroll
+    for (int t = 0; t < K; ++t) found += (t < kk && key[t] != KEY_EMPTY) ? 1 : 0;
+    bool exact = bd > 3.0e38f;  // the block is the whole grid
+    if (!exact && found == kk) {
+        const float margin = fmaxf(g.margin, 9.5367431640625e-7f * fmaxf(fabsf(p.x), fmaxf(fabsf(p.y), fabsf(p.z))));
+        const float b = bd - 2.0f * margin;
+        float dk = 0.0f;
+#pragma unroll
+        for (int t = 0; t < K; ++t)
+            if (t == kk - 1) dk = key_d2(key[t]);
+        exact = b > 0.0f && dk < b * b * 0.999999f;  // every unvisited point is strictly farther than the k-th found
+    }
+    if (!exact) {
+        todo[atomicAdd(todo_n, 1)] = i;
+        return;
+    }
+    float nb[K][3];
+#pragma unroll
+    for (int t = 0; t < K; ++t) {
+        if (t < found) {
+            const float4 c = __ldg(g.sorted + slot[t]);
+            nb[t][0] = c.x;
+            nb[t][1] = c.y;
+            nb[t][2] = c.z;
+        } else {
+            nb[t][0] = nb[t][1] = nb[t][2] = 0.f;
+        }
+    }
+    double n[3];
+    normal_of_neighbours<K>(nb, found, k, n);
+    const size_t o = 3 * (size_t)__float_as_int(p.w);
+    normals[o] = n[0];
+    normals[o + 1] = n[1];
+    normals[o + 2] = n[2];
+}
+
 // k-NN among the grid's own cloud (the point itself included), covariance about the neighbours' mean divided by k,
 // smallest eigenvector -> normals[3 * original_index]. A warp searches the neighbours of PARK consecutive points one
 // after the other (all lanes cooperate on one query) and parks their coordinates in shared memory; the covariance
 // and the Jacobi eigen-solver (a few thousand fp64 instructions) then run with ONE POINT PER LANE instead of
 // redundantly on all 32 lanes for every single point.
 template <int K>
-__global__ void __launch_bounds__(256) normals_kernel(GridDesc g, const float4* __restrict__ pts, int k, int chunk, double* __restrict__ normals) {
+__global__ void __launch_bounds__(256) normals_kernel(GridDesc g, const float4* __restrict__ pts, int k, int chunk, double* __restrict__ normals,
+                                                      const int* __restrict__ list, const int* __restrict__ list_n) {
     constexpr int PARK = K <= 5 ? 32 : (K <= 8 ? 16 : 8);  // upper bound of `chunk` (points a warp parks per round)
     __shared__ WarpSegs segs[8];
     __shared__ float nbuf[8][PARK][K][3];
@@ -78,10 +205,11 @@ __global__ void __launch_bounds__(256) normals_kernel(GridDesc g, const float4* 
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int base = warp * chunk; base < g.m; base += nwarps * chunk) {
-        const int cnt = min(chunk, g.m - base);
+    const int total = list ? *list_n : g.m;  // `list`: only the sorted positions named there (what normals_brick_kernel left over)
+    for (int base = warp * chunk; base < total; base += nwarps * chunk) {
+        const int cnt = min(chunk, total - base);
         for (int j = 0; j < cnt; ++j) {
-            const float4 p = __ldg(g.sorted + base + j);
+            const float4 p = __ldg(g.sorted + (list ? list[base + j] : base + j));
             const uint64_t mine = warp_grid_knn<K>(g, seg_addr(&segs[w]), p.x, p.y, p.z, INFINITY, INFINITY, lane);
             const bool have = (lane < k) && (mine != KEY_EMPTY);
             const int found = __popc(__ballot_sync(FULL, have));
@@ -99,34 +227,8 @@ __global__ void __launch_bounds__(256) normals_kernel(GridDesc g, const float4* 
         __syncwarp();
         if (lane < cnt) {
             const int found = nfound[w][lane];
-            double mean[3] = {0, 0, 0}, C[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-            for (int j = 0; j < K; ++j) {
-                if (j < found) {
-                    mean[0] += (double)nbuf[w][lane][j][0];
-                    mean[1] += (double)nbuf[w][lane][j][1];
-                    mean[2] += (double)nbuf[w][lane][j][2];
-                }
-            }
-            const double fdiv = (double)(found > 0 ? found : 1);
-            mean[0] /= fdiv;
-            mean[1] /= fdiv;
-            mean[2] /= fdiv;
-#pragma unroll
-            for (int j = 0; j < K; ++j) {
-                if (j < found) {
-                    const double d[3] = {(double)nbuf[w][lane][j][0] - mean[0], (double)nbuf[w][lane][j][1] - mean[1],
-                                         (double)nbuf[w][lane][j][2] - mean[2]};
-#pragma unroll
-                    for (int a = 0; a < 3; ++a)
-#pragma unroll
-                        for (int b = 0; b < 3; ++b) C[3 * a + b] += d[a] * d[b];
-                }
-            }
-#pragma unroll
-            for (int a = 0; a < 9; ++a) C[a] /= (double)k;  // fast_gicp divides by k_correspondences_
             double n[3];
-            smallest_eigvec3(C, n);
+            normal_of_neighbours<K>(nbuf[w][lane], found, k, n);
             const size_t o = 3 * (size_t)nidx[w][lane];
             normals[o] = n[0];
             normals[o + 1] = n[1];
@@ -229,10 +331,24 @@ int gicp_normals(Ctx* c, Map& mp, int k) {
         const int chunk = std::min(park, std::max(1, (mp.grid.m + warps_avail - 1) / warps_avail));
         const int blocks = std::min((mp.grid.m + 8 * chunk - 1) / (8 * chunk), c->sm_count * 8);
         double* out = mp.normals.as<double>();
-        if (k <= 5) normals_kernel<5><<<blocks, 256, 0, c->stream>>>(mp.grid, mp.pts.as<float4>(), k, chunk, out);
-        else if (k <= 8) normals_kernel<8><<<blocks, 256, 0, c->stream>>>(mp.grid, mp.pts.as<float4>(), k, chunk, out);
-        else normals_kernel<16><<<blocks, 256, 0, c->stream>>>(mp.grid, mp.pts.as<float4>(), k, chunk, out);
-        c->launches += 1;
+        const char* nb_env = std::getenv("ICP4R_NO_BRICK_NORMALS");
+        if (k <= 5 && mp.grid.m >= 4096 && !(nb_env && nb_env[0] == '1')) {
+            // thread-per-point pass over the 3 x 3 x 3 cell blocks, then the warp-per-query kernel on what it could not prove
+            CKS(reserve_grow(c, c->gs_idx, ((size_t)mp.grid.m + 4) * sizeof(int32_t)));
+            int* todo_n = c->gs_idx.as<int>();
+            int* todo = todo_n + 4;
+            CK(cudaMemsetAsync(todo_n, 0, sizeof(int), c->stream));
+            normals_brick_kernel<5><<<(mp.grid.m + 127) / 128, 128, 0, c->stream>>>(mp.grid, k, out, todo, todo_n);
+            const int fb_chunk = 4;
+            const int fb_blocks = std::max(1, std::min((mp.grid.m / 8 + 8 * fb_chunk - 1) / (8 * fb_chunk), c->sm_count * 8));
+            normals_kernel<5><<<fb_blocks, 256, 0, c->stream>>>(mp.grid, mp.pts.as<float4>(), k, fb_chunk, out, todo, todo_n);
+            c->launches += 2;
+        } else {
+            if (k <= 5) normals_kernel<5><<<blocks, 256, 0, c->stream>>>(mp.grid, mp.pts.as<float4>(), k, chunk, out, nullptr, nullptr);
+            else if (k <= 8) normals_kernel<8><<<blocks, 256, 0, c->stream>>>(mp.grid, mp.pts.as<float4>(), k, chunk, out, nullptr, nullptr);
+            else normals_kernel<16><<<blocks, 256, 0, c->stream>>>(mp.grid, mp.pts.as<float4>(), k, chunk, out, nullptr, nullptr);
+            c->launches += 1;
+        }
         CK(cudaGetLastError());
     }
     mp.normals_k = k;

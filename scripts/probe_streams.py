@@ -15,18 +15,27 @@ h = pkg.Icp4r(0)
 d = torch.from_numpy(pkg.synth.dense_map(1005, m)).to(dev)
 
 
+FLUSH = os.environ.get("PROBE_FLUSH") == "1"   # write a 256 MiB buffer (> L2) before every timed call, like bench.py does
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if FLUSH else None
+
+
 def ev(fn, reps=5):
     fn()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    h.synchronize()
-    e0.record()
+    tot = 0.0
     for _ in range(reps):
+        if FLUSH:
+            flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        h.synchronize()
+        e0.record()
         fn()
-    h.synchronize()
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / reps
+        h.synchronize()
+        e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / reps
 
 
 print(f"map_build({m}): {ev(lambda: h.map_build(d)):.3f} ms", flush=True)

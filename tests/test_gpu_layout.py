@@ -100,3 +100,34 @@ def test_gicp_batched_scans_equal_single(pkg, handle):
             assert (rb[i]["converged"], rb[i]["iterations"], rb[i]["n_corr"]) == (ri.converged, ri.iterations, ri.n_corr), i
             assert np.abs(Tb[i] - Ti).max() < 1e-9, (i, np.abs(Tb[i] - Ti).max())
             assert abs(rb[i]["fitness"] - ri.fitness) <= 1e-9 * max(ri.fitness, 1e-12)
+
+
+def test_brick_normals_equal_warp_per_query_normals(pkg):
+    """GICP target covariances: the thread-per-point pass over 3 x 3 x 3 cell blocks (+ the warp-per-query kernel on the
+    points it cannot prove) must pick the same neighbours in the same order as the warp-per-query kernel alone — the
+    registration that consumes the normals is then bit-identical. Dense map (most points proven) and a sparse cloud
+    (most points fall through to the list)."""
+    import os
+    import bench
+    mp, scans = bench.make_c2()
+    rng = np.random.default_rng(5)
+    sparse = np.zeros((6000, 4), np.float32)
+    sparse[:, :3] = rng.uniform(-200, 200, (6000, 3)).astype(np.float32)
+    sparse[:40] = sparse[40:80]  # exact duplicates: ties go to the lower index in both kernels
+    o = pkg.default_opts(residual=pkg.GICP, k=5, max_iterations=6, early_exit=0)
+    out = {}
+    for mode in ("brick", "warp"):
+        if mode == "warp":
+            os.environ["ICP4R_NO_BRICK_NORMALS"] = "1"
+        try:
+            h = pkg.Icp4r(0)
+            h.map_build(mp)
+            a = h.register_map(scans[0], o)
+            h.map_build(sparse)
+            b = h.register_map(sparse[:500] + np.float32(0.01), o)
+            out[mode] = (a[0], a[1].n_corr, a[1].fitness, b[0], b[1].n_corr, b[1].fitness)
+            h.close()
+        finally:
+            os.environ.pop("ICP4R_NO_BRICK_NORMALS", None)
+    for x, y in zip(out["brick"], out["warp"]):
+        assert np.array_equal(np.asarray(x), np.asarray(y))
