@@ -411,6 +411,7 @@ int icp4r_map_build(icp4r_handle h, const float* xyzw, int32_t n, int mem, float
     mp.built = false;
     mp.user_cell = cell_size;
     mp.hint_cell = 0.f;
+    mp.no_bucket = false;
     mp.padded = false;  // Build discards the previous map, its growth history included (a padded grid has ~2x the cells)
     CKS(set_points(c, mp, xyzw, n, mem, 0));
     mp.m = n;

@@ -79,6 +79,7 @@ struct Map {
     DevBuf inc_bnd;                  // per-block search bounds of the merge passes
     int valid_at_build = 0;          // valid points at the last full build (density drift -> full rebuild)
     bool quick_build = false;        // skip the occupancy-based cell refinement (short-lived clouds: GICP source)
+    bool no_bucket = false;          // the bucket build overflowed on this map once: radix path from then on (reset by Build)
     bool padded = false;             // grid built with slack around the bounding box (set once an append fell outside)
 };
 

@@ -121,29 +121,52 @@ __global__ void __launch_bounds__(128) normals_brick_kernel(GridDesc g, int k, d
         key[t] = KEY_EMPTY;
         slot[t] = 0;
     }
-    for (int z = z0; z <= z1; ++z)
-        for (int y = y0; y <= y1; ++y) {
-            const uint32_t rowbase = (uint32_t)(z * g.ny + y) * (uint32_t)g.nx;
-            const uint32_t s = __ldg(g.cell_start + rowbase + xa), e = __ldg(g.cell_start + rowbase + xb + 1);
-            for (uint32_t j = s; j < e; ++j) {
-                const float4 c = __ldg(g.sorted + j);
-                const float d = dist2_exact(p.x, p.y, p.z, c.x, c.y, c.z);
-                uint64_t cur = pack_key(d, __float_as_int(c.w));
-                if (cur < key[K - 1]) {  // ascending insertion, a chain of selects
-                    int cs_ = (int)j;
+    const int kk = min(k, K);
+    const float margin = fmaxf(g.margin, 9.5367431640625e-7f * fmaxf(fabsf(p.x), fmaxf(fabsf(p.y), fabsf(p.z))));
+    // own cell first: where the cloud is dense it already holds k points and their k-th distance prunes most of the other
+    // 26 cells (a cell is skipped only when even its nearest corner is strictly farther than the k-th distance so far:
+    // nothing in it could enter the list, ties included)
+    for (int pass = 0; pass < 2; ++pass)
+        for (int z = z0; z <= z1; ++z)
+            for (int y = y0; y <= y1; ++y) {
+                const bool own_row = (y == cy && z == cz);
+                if (pass == 0 && !own_row) continue;
+                float ddy = y > cy ? (g.oy + (float)y * g.cell) - p.y : (y < cy ? p.y - (g.oy + (float)(y + 1) * g.cell) : 0.0f);
+                float ddz = z > cz ? (g.oz + (float)z * g.cell) - p.z : (z < cz ? p.z - (g.oz + (float)(z + 1) * g.cell) : 0.0f);
+                ddy = fmaxf(ddy - margin, 0.0f);
+                ddz = fmaxf(ddz - margin, 0.0f);
+                const float dyz2 = (ddy * ddy + ddz * ddz) * 0.999999f;
+                const uint32_t rowbase = (uint32_t)(z * g.ny + y) * (uint32_t)g.nx;
+                for (int x = xa; x <= xb; ++x) {
+                    if ((pass == 0) != (x == cx && own_row)) continue;  // pass 0: the own cell only; pass 1: the other 26
+                    float kd = 3.4e38f;
 #pragma unroll
-                    for (int t = 0; t < K; ++t) {
-                        const bool lt = cur < key[t];
-                        const uint64_t tk = lt ? key[t] : cur;
-                        const int ts = lt ? slot[t] : cs_;
-                        key[t] = lt ? cur : key[t];
-                        slot[t] = lt ? cs_ : slot[t];
-                        cur = tk;
-                        cs_ = ts;
+                    for (int t = 0; t < K; ++t)
+                        if (t == kk - 1 && key[t] != KEY_EMPTY) kd = key_d2(key[t]) * 1.000001f;
+                    float ddx = x > cx ? (g.ox + (float)x * g.cell) - p.x : (x < cx ? p.x - (g.ox + (float)(x + 1) * g.cell) : 0.0f);
+                    ddx = fmaxf(ddx - margin, 0.0f);
+                    if (dyz2 + ddx * ddx * 0.999999f > kd) continue;
+                    const uint32_t s = __ldg(g.cell_start + rowbase + x), e = __ldg(g.cell_start + rowbase + x + 1);
+                    for (uint32_t j = s; j < e; ++j) {
+                        const float4 c = __ldg(g.sorted + j);
+                        const float d = dist2_exact(p.x, p.y, p.z, c.x, c.y, c.z);
+                        uint64_t cur = pack_key(d, __float_as_int(c.w));
+                        if (cur < key[K - 1]) {  // ascending insertion, a chain of selects
+                            int cs_ = (int)j;
+#pragma unroll
+                            for (int t = 0; t < K; ++t) {
+                                const bool lt = cur < key[t];
+                                const uint64_t tk = lt ? key[t] : cur;
+                                const int ts = lt ? slot[t] : cs_;
+                                key[t] = lt ? cur : key[t];
+                                slot[t] = lt ? cs_ : slot[t];
+                                cur = tk;
+                                cs_ = ts;
+                            }
+                        }
                     }
                 }
             }
-        }
     // faces of the visited block with cells behind them (the grid spans the cloud's bounding box: nothing lies outside it)
     float bd = 3.4e38f;
     if (xa > 0) bd = fminf(bd, p.x - (g.ox + (float)xa * g.cell));
@@ -152,13 +175,11 @@ __global__ void __launch_bounds__(128) normals_brick_kernel(GridDesc g, int k, d
     if (y1 < g.ny - 1) bd = fminf(bd, (g.oy + (float)(y1 + 1) * g.cell) - p.y);
     if (z0 > 0) bd = fminf(bd, p.z - (g.oz + (float)z0 * g.cell));
     if (z1 < g.nz - 1) bd = fminf(bd, (g.oz + (float)(z1 + 1) * g.cell) - p.z);
-    const int kk = min(k, K);
     int found = 0;
 #pragma unroll
     for (int t = 0; t < K; ++t) found += (t < kk && key[t] != KEY_EMPTY) ? 1 : 0;
     bool exact = bd > 3.0e38f;  // the block is the whole grid
     if (!exact && found == kk) {
-        const float margin = fmaxf(g.margin, 9.5367431640625e-7f * fmaxf(fabsf(p.x), fmaxf(fabsf(p.y), fabsf(p.z))));
         const float b = bd - 2.0f * margin;
         float dk = 0.0f;
 #pragma unroll

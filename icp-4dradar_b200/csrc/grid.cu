@@ -344,8 +344,11 @@ __global__ void __launch_bounds__(BK_THREADS) bk_sort_kernel(const float4* __res
 static int bucket_build(Ctx* c, Map& mp, const GridDesc& g, int m, int nvalid, bool* built) {
     *built = false;
     const char* e = std::getenv("ICP4R_BUCKET_MIN");
-    const int min_pts = e ? std::atoi(e) : 262144;
-    if (nvalid < min_pts || min_pts < 0) return ICP4R_OK;
+    // worth it for large maps only: below a few million points the radix path is faster (a 290 k-point sector sub-map spent
+    // 136 us in the scatter alone — few buckets, contended cursors — against ~75 us for the whole radix sort), and a map
+    // whose buckets overflowed once (surfaces: strongly non-uniform occupancy) is not tried again until it is rebuilt from scratch
+    const int min_pts = e ? std::atoi(e) : 4000000;
+    if (nvalid < min_pts || min_pts < 0 || mp.no_bucket) return ICP4R_OK;
     // about 0.8 k points per bucket by volume (slots: BK_CAP)
     const double ppc = (double)nvalid / std::max(g.ncells, 1);
     int S = (int)std::lround(std::log2(std::max(800.0 / std::max(ppc, 1e-9), 1.0)));
@@ -366,7 +369,10 @@ static int bucket_build(Ctx* c, Map& mp, const GridDesc& g, int m, int nvalid, b
     uint32_t h_max = 0;
     CK(cudaMemcpyAsync(&h_max, info, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    if (h_max > (uint32_t)BK_CAP) return ICP4R_OK;
+    if (h_max > (uint32_t)BK_CAP) {
+        mp.no_bucket = true;
+        return ICP4R_OK;
+    }
     const size_t smem = (size_t)BK_CAP * (sizeof(float4) + 2 * sizeof(unsigned short)) + ((size_t)2 * (1 << S) + 1) * sizeof(uint32_t);
     static bool attr_set = false;
     if (!attr_set) {

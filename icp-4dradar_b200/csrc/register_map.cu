@@ -1439,13 +1439,15 @@ int register_against_map(Ctx* c, Map& mp, const float4* d_src, int n, const icp4
     // With early exit the iterations after convergence are no-op launches (~2 us each): a 64-iteration budget that
     // converges after 8 would spend more time skipping than iterating. Run such loops in chunks and look at the
     // device's `done` flag in between (one 4-byte copy + sync per chunk).
-    constexpr int CHUNK = 8;
+    // The first chunk is short: a tracker that starts from a good prior (the odometry node: the previous pose) converges in
+    // two or three outer iterations, and a chunk of 8 then spends more launches skipping than working.
+    constexpr int CHUNK = 8, CHUNK0 = 4;
     const bool chunked = o->early_exit && iters > CHUNK + CHUNK / 2 && !sharded && !prof;
     if (!chunked) {
         CKS(run_range(0, iters, true));
     } else {
-        for (int it0 = 0; it0 < iters; it0 += CHUNK) {
-            CKS(run_range(it0, std::min(it0 + CHUNK, iters), false));
+        for (int it0 = 0, step = CHUNK0; it0 < iters; it0 += step, step = CHUNK) {
+            CKS(run_range(it0, std::min(it0 + step, iters), false));
             CK(cudaMemcpyAsync(&hs->done_flag, reinterpret_cast<const char*>(d_st) + offsetof(RegState, done), sizeof(int),
                                cudaMemcpyDeviceToHost, c->stream));
             CK(cudaStreamSynchronize(c->stream));
