@@ -189,7 +189,10 @@ struct Ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr, own_stream = nullptr;
     cudaStream_t copy_stream = nullptr;  // host->device copies of large batched calls run ahead of the compute stream
-    cudaEvent_t copy_events[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    DevBuf d_pairctr;                    // pair counters of the batched kernel's dynamic scheduling (one per launch in flight)
+    unsigned pairctr_slot = 0;
+    cudaStream_t aux_stream = nullptr;   // second compute stream of those calls: consecutive chunk kernels overlap their tails
+    cudaEvent_t copy_events[36] = {};   // [chunk] copy done, [32] start, [33] aux stream done
     std::string err;
     int64_t launches = 0;
 

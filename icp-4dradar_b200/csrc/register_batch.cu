@@ -53,6 +53,7 @@ struct BatchParams {
     double rot_eps, trans_eps, mse_abs_eps;
     double T0[16];
     unsigned long long* stats;  // work counters (NULL: off), see icp4r_set_stats
+    int* next_pair;  // NULL: pair = blockIdx.x + i * gridDim.x; else the CTAs draw pairs from this counter (zeroed before the launch)
 };
 
 struct PairGrid {
@@ -478,7 +479,17 @@ __global__ void __launch_bounds__(NT, 2) reg_batch_kernel(const __grid_constant_
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     constexpr int NV = (KIND == ICP4R_P2P_SVD) ? 17 : 29;
 
-    for (int pair = blockIdx.x; pair < P.n_pairs; pair += gridDim.x) {
+    // Pairs differ in cost (searches depend on the geometry), so a static pair -> CTA assignment leaves the SMs of the
+    // cheap pairs idle at the end of a launch: with more pairs than CTAs every CTA draws its next pair from a counter.
+    __shared__ int s_pair;
+    for (int pair = blockIdx.x;; pair += gridDim.x) {
+        if (P.next_pair != nullptr) {
+            __syncthreads();  // everybody has read s_pair of the previous round
+            if (tid == 0) s_pair = atomicAdd(P.next_pair, 1);
+            __syncthreads();
+            pair = s_pair;
+        }
+        if (pair >= P.n_pairs) break;
         const int so = P.soff[pair], n = P.soff[pair + 1] - so;
         const int to = P.toff[pair], m = P.toff[pair + 1] - to;
         const float4* __restrict__ gsrc = P.src + so;
@@ -807,7 +818,13 @@ static int launch_batch(Ctx* c, const BatchParams& P, size_t smem, double* d_T, 
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
     per_sm = std::max(per_sm, 1);
     const int blocks = std::min(P.n_pairs, c->sm_count * per_sm);
-    kern<<<blocks, NT, smem, c->stream>>>(P, d_T, d_res);
+    BatchParams Q = P;
+    if (P.n_pairs > blocks) {  // dynamic pair scheduling; each launch gets a counter of its own (launches on two streams overlap)
+        CKS(reserve(c, c->d_pairctr, 64 * sizeof(int)));
+        Q.next_pair = c->d_pairctr.as<int>() + (c->pairctr_slot++ & 63);
+        CK(cudaMemsetAsync(Q.next_pair, 0, sizeof(int), c->stream));
+    }
+    kern<<<blocks, NT, smem, c->stream>>>(Q, d_T, d_res);
     c->launches += 1;
     CK(cudaGetLastError());
 #ifdef ICP4R_RB_TIMING
