@@ -25,13 +25,18 @@ seq = list(L.values())
 
 
 def last_run(first, last):
-    """the last complete launch sequence first ... last"""
+    """the complete launch sequence first ... last that moved the most bytes (the probe also builds smaller maps)"""
+    best, best_b = [], -1.0
     ends = [i for i, d in enumerate(seq) if d["k"] == last]
-    for e in reversed(ends):
+    for e in ends:
         for b in range(e, -1, -1):
             if seq[b]["k"] == first:
-                return seq[b:e + 1]
-    return []
+                run = seq[b:e + 1]
+                tot = sum(d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0) for d in run)
+                if tot >= best_b:
+                    best, best_b = run, tot
+                break
+    return best
 
 
 out_txt = [f"# one call each, from `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none python scripts/probe_streams.py`",
