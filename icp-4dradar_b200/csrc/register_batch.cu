@@ -322,10 +322,10 @@ __device__ __forceinline__ void add_corr(double (&acc)[NV], int& cnt, const doub
 // [w * chunk, (w + 1) * chunk) of the cell-sorted source, so there is no block barrier between the two phases.
 // Per source point: s_h1 / s_h2 = slots of the two nearest target points of its last search (0xFFFF: none),
 // s_src[].w = LB (see the file header).
-template <int KIND, bool FIT, int NV>
+template <int KIND, bool FIT, int NV, int NW>
 __device__ __forceinline__ void pair_pass(const PairGrid& g, const float4* __restrict__ s_tgt, float4* __restrict__ s_src,
                                           const uint32_t* __restrict__ s_cs, unsigned short* __restrict__ s_h1,
-                                          unsigned short* __restrict__ s_h2, unsigned short* __restrict__ s_list,
+                                          unsigned short* __restrict__ s_h2, unsigned short* __restrict__ s_list, int* __restrict__ s_wcnt,
                                           const double* __restrict__ s_T, const float* __restrict__ s_dA, const BatchParams& P, int n,
                                           int chunk, bool have_prev, double (&acc)[NV], int lane, int w) {
     constexpr int NONE = 0xFFFF;
@@ -385,10 +385,25 @@ __device__ __forceinline__ void pair_pass(const PairGrid& g, const float4* __res
     RB_ADD(6, nl);
     RB_ADD(7, 1);
     // ---- phase 2: search the rest --------------------------------------------------------------------------------
-    for (int j0 = 0; j0 < nl; j0 += 32) {
-        const int j = j0 + lane;
-        if (j < nl) {
-            const int i = (int)list[j];
+    // The points that need a search cluster in space, i.e. in a few warps' slices (the source is in cell order): the
+    // warps' lists are pooled and the BLOCK's threads take one entry each, so a pass costs one search round (< 256 entries
+    // per pair and pass on C4) instead of as many rounds as the fullest warp list needs.
+    if (lane == 0) s_wcnt[w] = nl;
+    __syncthreads();
+    int pre[NW + 1];
+    pre[0] = 0;
+#pragma unroll
+    for (int j = 0; j < NW; ++j) pre[j + 1] = pre[j] + s_wcnt[j];
+    const int pooled = pre[NW];
+    for (int j = (w << 5) + lane; j < pooled; j += NW * 32) {
+        {
+            int ww = 0;
+#pragma unroll
+            for (int t = 1; t < NW; ++t) ww += (j >= pre[t]) ? 1 : 0;
+            int off_in = j;
+#pragma unroll
+            for (int t = 0; t < NW; ++t) off_in = (t == ww) ? j - pre[t] : off_in;
+            const int i = (int)s_list[min(n, ww * chunk) + off_in];
             const float4 p = s_src[i];
             double pw[3];
             xform_point(s_T, p.x, p.y, p.z, pw);
@@ -473,6 +488,7 @@ __global__ void __launch_bounds__(NT, 2) reg_batch_kernel(const __grid_constant_
     __shared__ float s_bb[NW][6];
     __shared__ PairGrid s_g;
     __shared__ uint32_t s_wsum[NW];
+    __shared__ int s_wcnt[NW];  // entries of every warp's search list (pair_pass)
     __shared__ int s_flags[4];  // done, converged, iterations, n_corr
     __shared__ double s_misc[2];  // mse_prev, last_cost
 
@@ -672,7 +688,7 @@ __global__ void __launch_bounds__(NT, 2) reg_batch_kernel(const __grid_constant_
             double acc[NV];
 #pragma unroll
             for (int v = 0; v < NV; ++v) acc[v] = 0.0;
-            pair_pass<KIND, false, NV>(g, s_tgt, s_src, s_cs, s_prev, s_prev2, s_list, s_T, s_dA, P, n, chunk, P.use_hints && it > 0, acc, lane, w);
+            pair_pass<KIND, false, NV, NW>(g, s_tgt, s_src, s_cs, s_prev, s_prev2, s_list, s_wcnt, s_T, s_dA, P, n, chunk, P.use_hints && it > 0, acc, lane, w);
             RB_T(t_r0);
             block_reduce<NV, NW>(acc, s_red, s_tot, tid);
             RB_T(t_r1);
@@ -785,7 +801,7 @@ __global__ void __launch_bounds__(NT, 2) reg_batch_kernel(const __grid_constant_
         // ---- fitness pass: mean squared 1-NN distance under the final pose --------------------------
         {
             double fa[2] = {0.0, 0.0};
-            pair_pass<KIND, true, 2>(g, s_tgt, s_src, s_cs, s_prev, s_prev2, s_list, s_T, s_dA, P, n, chunk, P.use_hints && P.max_iterations > 0, fa, lane, w);
+            pair_pass<KIND, true, 2, NW>(g, s_tgt, s_src, s_cs, s_prev, s_prev2, s_list, s_wcnt, s_T, s_dA, P, n, chunk, P.use_hints && P.max_iterations > 0, fa, lane, w);
             block_reduce<2, NW>(fa, s_red, s_tot, tid);
         }
         if (tid < 16) T_out[(size_t)pair * 16 + tid] = s_T[tid];
