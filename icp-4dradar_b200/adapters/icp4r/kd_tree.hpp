@@ -150,21 +150,53 @@ class KD_TREE {
     }
 
     int Delete_Point_Boxes(std::vector<BoxPointType>& BoxPoints) {
+        const std::vector<uint8_t> before = valid_mask();
         int32_t n = 0;
         check(h_, icp4r_map_delete_boxes(h_, BoxPoints.empty() ? nullptr : BoxPoints[0].vertex_min, (int32_t)BoxPoints.size(), &n),
               "Delete_Point_Boxes");
+        if (n > 0) note_removed(before);
         return n;
     }
 
     void Add_Point_Boxes(std::vector<BoxPointType>& BoxPoints) {
         check(h_, icp4r_map_add_boxes(h_, BoxPoints.empty() ? nullptr : BoxPoints[0].vertex_min, (int32_t)BoxPoints.size(), nullptr),
               "Add_Point_Boxes");
+        if (!removed_pending_.empty()) {  // a revived point was never "removed"
+            const std::vector<uint8_t> now = valid_mask();
+            std::vector<int32_t> keep;
+            for (int32_t i : removed_pending_)
+                if (!now[(std::size_t)i]) keep.push_back(i);
+            removed_pending_.swap(keep);
+        }
     }
 
     void Delete_Points(PointVector& PointToDel) {
         if (PointToDel.empty()) return;
-        RowLayout<PointType> lay(h_);
-        check(h_, icp4r_map_delete_points(h_, rows(PointToDel.data()), (int32_t)PointToDel.size(), ICP4R_HOST, nullptr), "Delete_Points");
+        const std::vector<uint8_t> before = valid_mask();
+        int32_t n = 0;
+        {
+            RowLayout<PointType> lay(h_);
+            check(h_, icp4r_map_delete_points(h_, rows(PointToDel.data()), (int32_t)PointToDel.size(), ICP4R_HOST, &n), "Delete_Points");
+        }
+        if (n > 0) note_removed(before);
+    }
+
+    // ikd_Tree.h:246 — flatten(root, Storage, NOT_RECORD) appends every non-deleted point of the subtree; there are no tree
+    // nodes here, so the adapter's form takes no node and appends every valid point of the map (insertion order; the
+    // reference: traversal order).
+    void flatten(PointVector& Storage) {
+        const std::vector<uint8_t> v = valid_mask();
+        for (std::size_t i = 0; i < v.size(); ++i)
+            if (v[i]) Storage.push_back(mirror_[i]);
+    }
+
+    // ikd_Tree.h:247, ikd_Tree.cpp:567-579 — appends the points that Delete_Points / Delete_Point_Boxes removed since the
+    // last call (not the ones down-sampling replaced, ikd_Tree.cpp:1393) and forgets them. The reference reports a deleted
+    // point only once a rebuild has purged its node (timing dependent); here it is reported right after the delete call —
+    // the same set once the reference's rebuilds have caught up.
+    void acquire_removed_points(PointVector& removed_points) {
+        for (int32_t i : removed_pending_) removed_points.push_back(mirror_[(std::size_t)i]);
+        removed_pending_.clear();
     }
 
     BoxPointType tree_range() {
@@ -182,8 +214,20 @@ class KD_TREE {
     icp4r_handle native_handle() { return h_; }
 
    private:
+    std::vector<uint8_t> valid_mask() {
+        std::vector<uint8_t> v(mirror_.size());
+        if (!v.empty()) check(h_, icp4r_map_points(h_, ICP4R_HOST, nullptr, v.data(), (int32_t)v.size()), "valid mask");
+        return v;
+    }
+    void note_removed(const std::vector<uint8_t>& before) {
+        const std::vector<uint8_t> now = valid_mask();
+        for (std::size_t i = 0; i < now.size() && i < before.size(); ++i)
+            if (before[i] && !now[i]) removed_pending_.push_back((int32_t)i);
+    }
+
     icp4r_handle h_ = nullptr;
     float downsample_size_;
+    std::vector<int32_t> removed_pending_;  // removed by a delete call, not yet handed out by acquire_removed_points
     std::vector<PointType, Eigen::aligned_allocator<PointType>> mirror_;  // host copies, returned by value like the reference
 };
 

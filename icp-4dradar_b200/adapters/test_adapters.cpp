@@ -136,9 +136,19 @@ int main() {
         REQUIRE(in_ball.empty());
         ikd_Tree.Add_Point_Boxes(boxes);
         REQUIRE(ikd_Tree.validnum() == before);
+        icp4r::KD_TREE<PointType>::PointVector removed, flat;
+        ikd_Tree.acquire_removed_points(removed);  // ikd_Tree.h:247: the box's points came back before anybody asked
+        REQUIRE(removed.empty());
         icp4r::KD_TREE<PointType>::PointVector victims(all.begin(), all.begin() + 7);
         ikd_Tree.Delete_Points(victims);
         REQUIRE(ikd_Tree.validnum() == before - 7);
+        ikd_Tree.acquire_removed_points(removed);
+        REQUIRE(removed.size() == 7);
+        for (int i = 0; i < 7; ++i) REQUIRE(removed[i].x == all[i].x && removed[i].intensity == all[i].intensity);
+        ikd_Tree.acquire_removed_points(removed);  // appends, and hands every point out once
+        REQUIRE(removed.size() == 7);
+        ikd_Tree.flatten(flat);                    // ikd_Tree.h:246: every non-deleted point
+        REQUIRE((int)flat.size() == before - 7 && flat[0].intensity == all[7].intensity);
         std::printf("box/radius/delete shapes: %zu in box, %d deleted and restored, 7 points deleted\n", in_box.size(), deleted);
     }
     // ---- the pcl::VoxelGrid shape, as radar_odometry.cpp:426-429 uses it

@@ -233,6 +233,8 @@ struct Ctx {
     DevBuf gs_pts, gs_idx, gs_d2, gs_found;  // GICP: exhaustive k-NN scratch for the scan's own normals
     DevBuf vg_keys, vg_vals, vg_sort, vg_tiles, vg_out;  // voxel-grid centroid filter
     bool batch_reproducible = false;  // ICP4R_BATCH_REPRODUCIBLE=1 (see register_batch.cu)
+    float submap_cell = 0.f;  // icp4r_register_submap: occupancy-refined cell size of the last refined sub-map (0: none yet)
+    int submap_m = 0, submap_uses = 0;
     bool coop_ok = true;      // cleared when a cooperative launch was refused
     bool use_persist = false;  // ICP4R_PERSIST=1: single-scan loops as ONE cooperative launch (reg_loop_kernel) instead of a graph of per-iteration launches
     bool use_lb = true;     // ICP4R_NO_LB=1 turns the keep-the-neighbours-without-a-search proof off (A/B measurements)

@@ -105,7 +105,7 @@ __device__ __forceinline__ void normal_of_neighbours(const NB& nb /* [K][3] floa
 // to a list that the warp-per-query kernel below finishes. Same neighbours in the same order -> same normals, bit for bit,
 // as the warp-per-query kernel alone (4 x fewer executed instructions per point, no idle lanes).
 template <int K>
-__global__ void __launch_bounds__(128) normals_brick_kernel(GridDesc g, int k, double* __restrict__ normals, int* __restrict__ todo,
+__global__ void __launch_bounds__(128) normals_brick_kernel(GridDesc g, int k, int* __restrict__ nbslot, int* __restrict__ todo,
                                                             int* __restrict__ todo_n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= g.m) return;
@@ -114,12 +114,16 @@ __global__ void __launch_bounds__(128) normals_brick_kernel(GridDesc g, int k, d
     const int xa = max(cx - 1, 0), xb = min(cx + 1, g.nx - 1);
     const int y0 = max(cy - 1, 0), y1 = min(cy + 1, g.ny - 1);
     const int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.nz - 1);
-    uint64_t key[K];
-    int slot[K];
+    // the k best so far, ascending by (d2, original index): distances, indices and sorted slots in registers. Every
+    // candidate runs the same K-step chain of selects — no branch, so the 32 lanes of a warp stay together (a guarded
+    // insertion made the warp execute the chain whenever ANY lane inserted: 47 % of the executed instructions).
+    float kd[K];
+    int ki[K], slot[K];
 #pragma unroll
     for (int t = 0; t < K; ++t) {
-        key[t] = KEY_EMPTY;
-        slot[t] = 0;
+        kd[t] = INFINITY;
+        ki[t] = 0x7fffffff;
+        slot[t] = -1;
     }
     const int kk = min(k, K);
     const float margin = fmaxf(g.margin, 9.5367431640625e-7f * fmaxf(fabsf(p.x), fmaxf(fabsf(p.y), fabsf(p.z))));
@@ -139,30 +143,30 @@ __global__ void __launch_bounds__(128) normals_brick_kernel(GridDesc g, int k, d
                 const uint32_t rowbase = (uint32_t)(z * g.ny + y) * (uint32_t)g.nx;
                 for (int x = xa; x <= xb; ++x) {
                     if ((pass == 0) != (x == cx && own_row)) continue;  // pass 0: the own cell only; pass 1: the other 26
-                    float kd = 3.4e38f;
+                    float kth = INFINITY;
 #pragma unroll
                     for (int t = 0; t < K; ++t)
-                        if (t == kk - 1 && key[t] != KEY_EMPTY) kd = key_d2(key[t]) * 1.000001f;
+                        if (t == kk - 1) kth = kd[t];
                     float ddx = x > cx ? (g.ox + (float)x * g.cell) - p.x : (x < cx ? p.x - (g.ox + (float)(x + 1) * g.cell) : 0.0f);
                     ddx = fmaxf(ddx - margin, 0.0f);
-                    if (dyz2 + ddx * ddx * 0.999999f > kd) continue;
+                    if (dyz2 + ddx * ddx * 0.999999f > kth * 1.000001f) continue;  // false while the list is not full (inf)
                     const uint32_t s = __ldg(g.cell_start + rowbase + x), e = __ldg(g.cell_start + rowbase + x + 1);
                     for (uint32_t j = s; j < e; ++j) {
                         const float4 c = __ldg(g.sorted + j);
-                        const float d = dist2_exact(p.x, p.y, p.z, c.x, c.y, c.z);
-                        uint64_t cur = pack_key(d, __float_as_int(c.w));
-                        if (cur < key[K - 1]) {  // ascending insertion, a chain of selects
-                            int cs_ = (int)j;
+                        float cd = dist2_exact(p.x, p.y, p.z, c.x, c.y, c.z);
+                        int ci = __float_as_int(c.w), cs_ = (int)j;
 #pragma unroll
-                            for (int t = 0; t < K; ++t) {
-                                const bool lt = cur < key[t];
-                                const uint64_t tk = lt ? key[t] : cur;
-                                const int ts = lt ? slot[t] : cs_;
-                                key[t] = lt ? cur : key[t];
-                                slot[t] = lt ? cs_ : slot[t];
-                                cur = tk;
-                                cs_ = ts;
-                            }
+                        for (int t = 0; t < K; ++t) {
+                            const bool lt = cd < kd[t] || (cd == kd[t] && ci < ki[t]);
+                            const float td = lt ? kd[t] : cd;
+                            const int ti = lt ? ki[t] : ci;
+                            const int ts = lt ? slot[t] : cs_;
+                            kd[t] = lt ? cd : kd[t];
+                            ki[t] = lt ? ci : ki[t];
+                            slot[t] = lt ? cs_ : slot[t];
+                            cd = td;
+                            ci = ti;
+                            cs_ = ts;
                         }
                     }
                 }
@@ -176,36 +180,51 @@ __global__ void __launch_bounds__(128) normals_brick_kernel(GridDesc g, int k, d
     if (z0 > 0) bd = fminf(bd, p.z - (g.oz + (float)z0 * g.cell));
     if (z1 < g.nz - 1) bd = fminf(bd, (g.oz + (float)(z1 + 1) * g.cell) - p.z);
     int found = 0;
+    float dk = 0.0f;
 #pragma unroll
-    for (int t = 0; t < K; ++t) found += (t < kk && key[t] != KEY_EMPTY) ? 1 : 0;
+    for (int t = 0; t < K; ++t) {
+        found += (t < kk && slot[t] >= 0) ? 1 : 0;
+        if (t == kk - 1) dk = kd[t];
+    }
     bool exact = bd > 3.0e38f;  // the block is the whole grid
     if (!exact && found == kk) {
         const float b = bd - 2.0f * margin;
-        float dk = 0.0f;
-#pragma unroll
-        for (int t = 0; t < K; ++t)
-            if (t == kk - 1) dk = key_d2(key[t]);
         exact = b > 0.0f && dk < b * b * 0.999999f;  // every unvisited point is strictly farther than the k-th found
     }
-    if (!exact) {
-        todo[atomicAdd(todo_n, 1)] = i;
-        return;
-    }
+    // the neighbours' sorted slots (or "not proven": the warp-per-query kernel does that point) go to global memory; the
+    // covariances and eigenvectors are a second, register-hungry kernel of their own (normals_from_slots_kernel)
+#pragma unroll
+    for (int t = 0; t < K; ++t) nbslot[(size_t)i * K + t] = (exact && t < found) ? slot[t] : -1;
+    if (!exact) todo[atomicAdd(todo_n, 1)] = i;
+}
+
+// second half of the brick path: neighbour slots -> covariance -> smallest eigenvector, one thread per point; points the
+// brick pass could not prove (first slot -1) are left to the warp-per-query kernel
+template <int K>
+__global__ void __launch_bounds__(128) normals_from_slots_kernel(GridDesc g, int k, const int* __restrict__ nbslot, double* __restrict__ normals) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.m) return;
+    int sl[K];
+#pragma unroll
+    for (int t = 0; t < K; ++t) sl[t] = __ldg(nbslot + (size_t)i * K + t);
+    if (sl[0] < 0) return;
     float nb[K][3];
+    int found = 0;
 #pragma unroll
     for (int t = 0; t < K; ++t) {
-        if (t < found) {
-            const float4 c = __ldg(g.sorted + slot[t]);
+        if (sl[t] >= 0) {
+            const float4 c = __ldg(g.sorted + sl[t]);
             nb[t][0] = c.x;
             nb[t][1] = c.y;
             nb[t][2] = c.z;
+            ++found;
         } else {
             nb[t][0] = nb[t][1] = nb[t][2] = 0.f;
         }
     }
     double n[3];
     normal_of_neighbours<K>(nb, found, k, n);
-    const size_t o = 3 * (size_t)__float_as_int(p.w);
+    const size_t o = 3 * (size_t)__float_as_int(__ldg(g.sorted + i).w);
     normals[o] = n[0];
     normals[o + 1] = n[1];
     normals[o + 2] = n[2];
@@ -355,11 +374,14 @@ int gicp_normals(Ctx* c, Map& mp, int k) {
         const char* nb_env = std::getenv("ICP4R_NO_BRICK_NORMALS");
         if (k <= 5 && mp.grid.m >= 4096 && !(nb_env && nb_env[0] == '1')) {
             // thread-per-point pass over the 3 x 3 x 3 cell blocks, then the warp-per-query kernel on what it could not prove
-            CKS(reserve_grow(c, c->gs_idx, ((size_t)mp.grid.m + 4) * sizeof(int32_t)));
+            CKS(reserve_grow(c, c->gs_idx, ((size_t)mp.grid.m * 6 + 4) * sizeof(int32_t)));
             int* todo_n = c->gs_idx.as<int>();
             int* todo = todo_n + 4;
+            int* nbslot = todo + mp.grid.m;
             CK(cudaMemsetAsync(todo_n, 0, sizeof(int), c->stream));
-            normals_brick_kernel<5><<<(mp.grid.m + 127) / 128, 128, 0, c->stream>>>(mp.grid, k, out, todo, todo_n);
+            normals_brick_kernel<5><<<(mp.grid.m + 127) / 128, 128, 0, c->stream>>>(mp.grid, k, nbslot, todo, todo_n);
+            normals_from_slots_kernel<5><<<(mp.grid.m + 127) / 128, 128, 0, c->stream>>>(mp.grid, k, nbslot, out);
+            c->launches += 1;
             const int fb_chunk = 4;
             const int fb_blocks = std::max(1, std::min((mp.grid.m / 8 + 8 * fb_chunk - 1) / (8 * fb_chunk), c->sm_count * 8));
             normals_kernel<5><<<fb_blocks, 256, 0, c->stream>>>(mp.grid, mp.pts.as<float4>(), k, fb_chunk, out, todo, todo_n);
