@@ -980,6 +980,37 @@ class Bench:
                                     "algorithmic = the merge rewrites the sorted map (16 B read + 16 B written per MAP point) + the cell table; work is O(map), "
                                     "not O(batch): a two-level table would change that (DESIGN.md §9)")
             h2.close()
+        if self.world == 1 and not self.args.no_cpu_baseline:
+            # the reference's CPU path beside each, on a bounded sample of the same kind of input (points/s, one host thread:
+            # ikd-Tree's Build / Add_Points and PCL's VoxelGrid are single-threaded)
+            import oracle as O
+            import time
+            have = O.have_ref()
+            nb = 2_000_000
+            sample = pkg.synth.dense_map(1005, nb)
+            if have:
+                t = O.IkdTree()
+                t0 = time.perf_counter()
+                t.build(sample)
+                dt = time.perf_counter() - t0
+                out["build"]["cpu_baseline"] = {"value": nb / dt, "unit": "points/s", "cores": 1, "kind": "reference",
+                                                "sample": f"KD_TREE::Build of {nb} points of the same dense map (the reference's ikd-Tree compiled unmodified)"}
+                w = sc.sample(rng, 3000, centre=(20.0, 5.0), radius=80.0)
+                t0 = time.perf_counter()
+                t.add_points(w, False)
+                dt = time.perf_counter() - t0
+                out["add_points"]["cpu_baseline"] = {"value": 3000 / dt, "unit": "points/s", "cores": 1, "kind": "reference",
+                                                     "sample": f"KD_TREE::Add_Points(3,000 points, false) into that {nb}-point ikd-Tree"}
+                t.close()
+            vs = np.random.default_rng(7).random((nb, 4), dtype=np.float32)
+            vs[:, 0] = (vs[:, 0] - 0.5) * 400
+            vs[:, 1] = (vs[:, 1] - 0.5) * 400
+            vs[:, 2] = (vs[:, 2] - 0.5) * 20
+            t0 = time.perf_counter()
+            O.voxel_grid(vs, 0.5)
+            dt = time.perf_counter() - t0
+            out["voxel_grid"]["cpu_baseline"] = {"value": nb / dt, "unit": "points/s", "cores": 1, "kind": "port",
+                                                 "sample": f"pcl::VoxelGrid restated in C (oracle.c) on {nb} points of the same distribution; PCL itself is absent from the image"}
         return out
 
     # ---- the adapter boundary --------------------------------------------------------------------------------------
@@ -1042,6 +1073,8 @@ def main():
                 configs["c1"] = strip(B.run_c1(max(20 * K, 100), 10))
                 configs["c2_single"] = strip(B.run_c2(max(10 * K, 50), 10, batch=False, with_cpu=False))
                 configs["c2_batch16"] = strip(B.run_c2(max(10 * K, 50), 10, batch=True))
+                if configs["c2_batch16"].get("cpu_baseline"):  # the same registrations on the host: one CPU figure serves both records
+                    configs["c2_single"]["cpu_baseline"] = dict(configs["c2_batch16"]["cpu_baseline"])
                 configs["gicp"] = strip(B.run_gicp(max(10 * K, 50), 5))
                 configs["c3"] = strip(B.run_c3(2, 3))
                 configs["c3ref"] = strip(B.run_c3ref(2, 3))

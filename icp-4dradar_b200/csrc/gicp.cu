@@ -111,9 +111,6 @@ __global__ void __launch_bounds__(128) normals_brick_kernel(GridDesc g, int k, i
     if (i >= g.m) return;
     const float4 p = __ldg(g.sorted + i);
     const int cx = cell_of(p.x, g.ox, g.inv_cell, g.nx), cy = cell_of(p.y, g.oy, g.inv_cell, g.ny), cz = cell_of(p.z, g.oz, g.inv_cell, g.nz);
-    const int xa = max(cx - 1, 0), xb = min(cx + 1, g.nx - 1);
-    const int y0 = max(cy - 1, 0), y1 = min(cy + 1, g.ny - 1);
-    const int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.nz - 1);
     // the k best so far, ascending by (d2, original index): distances, indices and sorted slots in registers. Every
     // candidate runs the same K-step chain of selects — no branch, so the 32 lanes of a warp stay together (a guarded
     // insertion made the warp execute the chain whenever ANY lane inserted: 47 % of the executed instructions).
@@ -127,29 +124,39 @@ __global__ void __launch_bounds__(128) normals_brick_kernel(GridDesc g, int k, i
     }
     const int kk = min(k, K);
     const float margin = fmaxf(g.margin, 9.5367431640625e-7f * fmaxf(fabsf(p.x), fmaxf(fabsf(p.y), fabsf(p.z))));
-    // own cell first: where the cloud is dense it already holds k points and their k-th distance prunes most of the other
-    // 26 cells (a cell is skipped only when even its nearest corner is strictly farther than the k-th distance so far:
-    // nothing in it could enter the list, ties included)
-    for (int pass = 0; pass < 2; ++pass)
+    // Own cell first — where the cloud is dense it already holds k points and their k-th distance prunes most other
+    // cells (a cell is skipped only when even its nearest corner is strictly farther than the k-th distance so far: nothing
+    // in it could enter the list, ties included) — then the shell of cells at Chebyshev distance 1, and, if the k-th
+    // distance is still not proven smaller than the distance to the block's faces, the shell at distance 2.
+    constexpr int RMAX = 2;
+    bool exact = false;
+    int found = 0;
+    for (int R = 0; R <= RMAX && !exact; ++R) {
+        const int xa = max(cx - R, 0), xb = min(cx + R, g.nx - 1);
+        const int y0 = max(cy - R, 0), y1 = min(cy + R, g.ny - 1);
+        const int z0 = max(cz - R, 0), z1 = min(cz + R, g.nz - 1);
         for (int z = z0; z <= z1; ++z)
             for (int y = y0; y <= y1; ++y) {
-                const bool own_row = (y == cy && z == cz);
-                if (pass == 0 && !own_row) continue;
                 float ddy = y > cy ? (g.oy + (float)y * g.cell) - p.y : (y < cy ? p.y - (g.oy + (float)(y + 1) * g.cell) : 0.0f);
                 float ddz = z > cz ? (g.oz + (float)z * g.cell) - p.z : (z < cz ? p.z - (g.oz + (float)(z + 1) * g.cell) : 0.0f);
                 ddy = fmaxf(ddy - margin, 0.0f);
                 ddz = fmaxf(ddz - margin, 0.0f);
                 const float dyz2 = (ddy * ddy + ddz * ddz) * 0.999999f;
+                float kth = INFINITY;
+#pragma unroll
+                for (int t = 0; t < K; ++t)
+                    if (t == kk - 1) kth = kd[t];
+                if (dyz2 > kth * 1.000001f) continue;  // the whole row is too far (never while the list is not full: inf)
+                const bool inner_row = max(abs(y - cy), abs(z - cz)) < R;  // only its two end cells belong to this shell
                 const uint32_t rowbase = (uint32_t)(z * g.ny + y) * (uint32_t)g.nx;
                 for (int x = xa; x <= xb; ++x) {
-                    if ((pass == 0) != (x == cx && own_row)) continue;  // pass 0: the own cell only; pass 1: the other 26
-                    float kth = INFINITY;
+                    if (inner_row && abs(x - cx) < R) continue;  // visited by an earlier shell
 #pragma unroll
                     for (int t = 0; t < K; ++t)
                         if (t == kk - 1) kth = kd[t];
                     float ddx = x > cx ? (g.ox + (float)x * g.cell) - p.x : (x < cx ? p.x - (g.ox + (float)(x + 1) * g.cell) : 0.0f);
                     ddx = fmaxf(ddx - margin, 0.0f);
-                    if (dyz2 + ddx * ddx * 0.999999f > kth * 1.000001f) continue;  // false while the list is not full (inf)
+                    if (dyz2 + ddx * ddx * 0.999999f > kth * 1.000001f) continue;
                     const uint32_t s = __ldg(g.cell_start + rowbase + x), e = __ldg(g.cell_start + rowbase + x + 1);
                     for (uint32_t j = s; j < e; ++j) {
                         const float4 c = __ldg(g.sorted + j);
@@ -171,25 +178,27 @@ __global__ void __launch_bounds__(128) normals_brick_kernel(GridDesc g, int k, i
                     }
                 }
             }
-    // faces of the visited block with cells behind them (the grid spans the cloud's bounding box: nothing lies outside it)
-    float bd = 3.4e38f;
-    if (xa > 0) bd = fminf(bd, p.x - (g.ox + (float)xa * g.cell));
-    if (xb < g.nx - 1) bd = fminf(bd, (g.ox + (float)(xb + 1) * g.cell) - p.x);
-    if (y0 > 0) bd = fminf(bd, p.y - (g.oy + (float)y0 * g.cell));
-    if (y1 < g.ny - 1) bd = fminf(bd, (g.oy + (float)(y1 + 1) * g.cell) - p.y);
-    if (z0 > 0) bd = fminf(bd, p.z - (g.oz + (float)z0 * g.cell));
-    if (z1 < g.nz - 1) bd = fminf(bd, (g.oz + (float)(z1 + 1) * g.cell) - p.z);
-    int found = 0;
-    float dk = 0.0f;
+        if (R == 0) continue;
+        // faces of the visited block with cells behind them (the grid spans the cloud's bounding box: nothing lies outside it)
+        float bd = 3.4e38f;
+        if (xa > 0) bd = fminf(bd, p.x - (g.ox + (float)xa * g.cell));
+        if (xb < g.nx - 1) bd = fminf(bd, (g.ox + (float)(xb + 1) * g.cell) - p.x);
+        if (y0 > 0) bd = fminf(bd, p.y - (g.oy + (float)y0 * g.cell));
+        if (y1 < g.ny - 1) bd = fminf(bd, (g.oy + (float)(y1 + 1) * g.cell) - p.y);
+        if (z0 > 0) bd = fminf(bd, p.z - (g.oz + (float)z0 * g.cell));
+        if (z1 < g.nz - 1) bd = fminf(bd, (g.oz + (float)(z1 + 1) * g.cell) - p.z);
+        found = 0;
+        float dk = 0.0f;
 #pragma unroll
-    for (int t = 0; t < K; ++t) {
-        found += (t < kk && slot[t] >= 0) ? 1 : 0;
-        if (t == kk - 1) dk = kd[t];
-    }
-    bool exact = bd > 3.0e38f;  // the block is the whole grid
-    if (!exact && found == kk) {
-        const float b = bd - 2.0f * margin;
-        exact = b > 0.0f && dk < b * b * 0.999999f;  // every unvisited point is strictly farther than the k-th found
+        for (int t = 0; t < K; ++t) {
+            found += (t < kk && slot[t] >= 0) ? 1 : 0;
+            if (t == kk - 1) dk = kd[t];
+        }
+        exact = bd > 3.0e38f;  // the block is the whole grid
+        if (!exact && found == kk) {
+            const float b = bd - 2.0f * margin;
+            exact = b > 0.0f && dk < b * b * 0.999999f;  // every unvisited point is strictly farther than the k-th found
+        }
     }
     // the neighbours' sorted slots (or "not proven": the warp-per-query kernel does that point) go to global memory; the
     // covariances and eigenvectors are a second, register-hungry kernel of their own (normals_from_slots_kernel)
