@@ -147,19 +147,19 @@ static int stage_in(Ctx* c, DevBuf& b, const void* user, size_t bytes, int mem, 
 }
 
 // rows of `stride` bytes (x, y, z at byte 0, 4, 8; w at byte `woff`, or none) -> packed x, y, z, w
-__global__ void __launch_bounds__(256) repack_rows_kernel(const unsigned char* __restrict__ raw, size_t n, int stride, int woff,
+__global__ void __launch_bounds__(256) repack_rows_kernel(const unsigned char* __restrict__ raw, size_t n, int stride, int woff, int vec,
                                                           float4* __restrict__ out) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float* row = reinterpret_cast<const float*>(raw + i * (size_t)stride);
     float4 p;
-    if ((stride & 15) == 0) {  // 16-byte aligned rows (pcl::PointXYZI: 32 bytes): one vector load for x, y, z
+    if (vec) {  // 16-byte aligned rows (pcl::PointXYZI: 32 bytes, aligned base): one vector load for x, y, z
         const float4 v = *reinterpret_cast<const float4*>(row);
         p = make_float4(v.x, v.y, v.z, woff == 12 ? v.w : 0.f);
     } else {
         p = make_float4(row[0], row[1], row[2], 0.f);
     }
-    if (woff >= 0 && !((stride & 15) == 0 && woff == 12)) p.w = row[woff >> 2];
+    if (woff >= 0 && !(vec && woff == 12)) p.w = row[woff >> 2];
     out[i] = p;
 }
 
@@ -181,7 +181,10 @@ static int unpack_points_to(Ctx* c, const float* user, size_t n, int mem, float4
         CK(cudaMemcpyAsync(c->d_raw.p, user, n * (size_t)c->pt_stride, cudaMemcpyHostToDevice, c->stream));
         raw = static_cast<const unsigned char*>(c->d_raw.p);
     }
-    repack_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(raw, n, c->pt_stride, c->pt_woff, dst);
+    // vector loads need 16-byte aligned rows: the stride AND the caller's base pointer (a device pointer may be anything)
+    const int vec = ((c->pt_stride & 15) == 0 && (reinterpret_cast<uintptr_t>(raw) & 15) == 0) ? 1 : 0;
+    if ((reinterpret_cast<uintptr_t>(raw) & 3) != 0) return fail(c, ICP4R_ERR_INVALID, "point rows must be 4-byte aligned");
+    repack_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(raw, n, c->pt_stride, c->pt_woff, vec, dst);
     c->launches += 1;
     CK(cudaGetLastError());
     return ICP4R_OK;

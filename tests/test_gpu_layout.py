@@ -74,6 +74,28 @@ def test_point_layout_equals_packed(pkg, handle, where):
     assert np.abs(bare["reg"] - ref["reg"]).max() < 1e-11 and np.array_equal(bare["reg_map"], ref["reg_map"])
 
 
+def test_point_layout_unaligned_device_rows(pkg, handle):
+    """32-byte rows in device memory whose base is only 4-byte aligned (a view into a larger buffer): same answers"""
+    import torch
+    src, tgt, _ = pkg.synth.frame_pair(22, 700, 900, extent=25.0)
+    buf = torch.zeros(8 * len(tgt) + 1, dtype=torch.float32, device="cuda")
+    buf[1:] = torch.from_numpy(xyzi_rows(tgt)).reshape(-1).cuda()
+    view = buf[1:].reshape(len(tgt), 8)          # data_ptr is base + 4 bytes
+    assert view.data_ptr() % 16 != 0 and view.is_contiguous()
+    handle.map_build(tgt)
+    ref = handle.map_knn(src, 5, 2.0)
+    handle.set_point_layout(32, 16)
+    try:
+        handle.map_build(view)
+    finally:
+        handle.set_point_layout(16, 12)
+    got = handle.map_knn(src, 5, 2.0)
+    for a, b in zip(ref, got):
+        assert np.array_equal(a, b)
+    mp, _ = handle.map_points()
+    assert np.array_equal(mp, tgt)
+
+
 def test_point_layout_rejects_bad_arguments(pkg, handle):
     for stride, woff in ((8, -1), (18, -1), (32, 30), (32, 32), (16, 14), (8192, 0)):
         with pytest.raises(pkg.Icp4rError):
