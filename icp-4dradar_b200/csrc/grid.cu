@@ -193,6 +193,11 @@ static int build_coarse(Ctx* c, Map& mp, GridDesc& g) {
 constexpr int BK_THREADS = 256;
 constexpr int BK_CAP = 2048;      // slots per bucket (scratch array and the sorting block's shared memory)
 constexpr int BK_MAX_S = 12;      // at most 4096 cell keys per bucket
+// The scatter is bound by the L2's atomic throughput, not by bandwidth and not by the SMs (ncu: issue slots 7 % busy,
+// long-scoreboard stall 129 per issued instruction, DRAM at 19 %): 20 M returning atomics in ~0.4 ms = ~25 per clock over
+// the whole L2. Spreading the cursors over separate 128-byte lines (stride 64 words) changed nothing (418 vs 410 us), so
+// it is the read-modify-write rate of the slices, not same-line serialisation: packed cursors stay.
+constexpr int BK_CSTRIDE = 1;     // uint32 words between two cursors
 
 __device__ __forceinline__ uint32_t key_of_point(const GridDesc& g, const float4& p) {
     const int cx = cell_of(p.x, g.ox, g.inv_cell, g.nx);
@@ -211,7 +216,7 @@ __global__ void __launch_bounds__(1024) bk_scan_kernel(const uint32_t* __restric
     __syncthreads();
     for (int b0 = 0; b0 < nb; b0 += 1024) {
         const int i = b0 + tid;
-        const uint32_t v = i < nb ? cnt[i] : 0u;
+        const uint32_t v = i < nb ? cnt[(size_t)i * BK_CSTRIDE] : 0u;
         uint32_t x = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -255,7 +260,7 @@ __global__ void __launch_bounds__(256) bk_scatter_kernel(const float4* __restric
         for (int u = 0; u < 4; ++u)
             if (ok[u] && isfinite(p[u].x) && isfinite(p[u].y) && isfinite(p[u].z)) {
                 const uint32_t b = key_of_point(g, p[u]) >> S;
-                const uint32_t slot = atomicAdd(cursor + b, 1u);  // a bucket that overflows is detected by the scan: radix path
+                const uint32_t slot = atomicAdd(cursor + (size_t)b * BK_CSTRIDE, 1u);  // a bucket that overflows is detected by the scan: radix path
                 if (slot < (uint32_t)BK_CAP)
                     tmp[(size_t)b * BK_CAP + slot] = make_float4(p[u].x, p[u].y, p[u].z, __uint_as_float((uint32_t)(i0 + u * stride)));
             }
@@ -318,22 +323,19 @@ __global__ void __launch_bounds__(BK_THREADS) bk_sort_kernel(const float4* __res
         s_perm[s_start[fk] + atomicAdd(&s_cur[fk], 1u)] = (unsigned short)j;
     }
     __syncthreads();
-    // ascending index inside every cell (what the stable sort of the radix path produces): insertion sort, cells are small
-    for (int c = tid; c < ncell; c += BK_THREADS) {
-        const uint32_t s0 = s_start[c], e0 = s_start[c + 1];
-        for (uint32_t a = s0 + 1; a < e0; ++a) {
-            const unsigned short pj = s_perm[a];
-            const uint32_t idx = __float_as_uint(s_pts[pj].w);
-            uint32_t q = a;
-            while (q > s0 && __float_as_uint(s_pts[s_perm[q - 1]].w) > idx) {
-                s_perm[q] = s_perm[q - 1];
-                --q;
-            }
-            s_perm[q] = pj;
-        }
+    // ascending index inside every cell (what the stable sort of the radix path produces): every point counts the points
+    // of its cell with a smaller index — its rank — and goes straight to its final position. (One thread insertion-sorting
+    // a whole cell left the block waiting at the barrier for the thread with the fullest cell: barrier stall 10.9 per issue.)
+    for (uint32_t a = tid; a < nbk; a += BK_THREADS) {
+        const unsigned short pj = s_perm[a];
+        const uint32_t fk = s_fk[pj];
+        const uint32_t s0 = s_start[fk], e0 = s_start[fk + 1];
+        const float4 me = s_pts[pj];
+        const uint32_t idx = __float_as_uint(me.w);
+        uint32_t rank = 0;
+        for (uint32_t q = s0; q < e0; ++q) rank += __float_as_uint(s_pts[s_perm[q]].w) < idx ? 1u : 0u;
+        sorted[off + s0 + rank] = me;
     }
-    __syncthreads();
-    for (uint32_t j = tid; j < nbk; j += BK_THREADS) sorted[off + j] = s_pts[s_perm[j]];
     for (int c = tid; c < ncell; c += BK_THREADS) {
         const uint32_t key = (b << S) + (uint32_t)c;
         if (key <= (uint32_t)g.ncells) cell_start[key] = off + s_start[c];
@@ -356,12 +358,12 @@ static int bucket_build(Ctx* c, Map& mp, const GridDesc& g, int m, int nvalid, b
     const long long nb_ll = ((long long)g.ncells + 1 + (1ll << S) - 1) >> S;
     if (nb_ll * BK_CAP > 4ll * std::max(m, 1) + (1 << 20)) return ICP4R_OK;  // mostly empty buckets (surfaces in a big volume): not worth the scratch
     const int nb = (int)nb_ll;
-    CKS(reserve_grow(c, c->d_scratch, ((size_t)2 * nb + 16) * sizeof(uint32_t)));
-    uint32_t* cursor = c->d_scratch.as<uint32_t>();   // [nb] points per bucket
-    uint32_t* base = cursor + nb;                     // [nb + 1]
+    CKS(reserve_grow(c, c->d_scratch, ((size_t)nb * BK_CSTRIDE + nb + 16) * sizeof(uint32_t)));
+    uint32_t* cursor = c->d_scratch.as<uint32_t>();   // [nb * BK_CSTRIDE] points per bucket, one cursor per 256 bytes
+    uint32_t* base = cursor + (size_t)nb * BK_CSTRIDE;  // [nb + 1]
     uint32_t* info = base + nb + 1;                   // [1]
     CKS(reserve_grow(c, mp.sorted_alt, (size_t)nb * BK_CAP * sizeof(float4)));
-    CK(cudaMemsetAsync(cursor, 0, (size_t)nb * sizeof(uint32_t), c->stream));
+    CK(cudaMemsetAsync(cursor, 0, (size_t)nb * BK_CSTRIDE * sizeof(uint32_t), c->stream));
     const int blocks = std::min((m + 1023) / 1024, c->sm_count * 8);
     bk_scatter_kernel<<<blocks, 256, 0, c->stream>>>(mp.pts.as<float4>(), mp.valid.as<uint8_t>(), m, g, S, cursor, mp.sorted_alt.as<float4>());
     bk_scan_kernel<<<1, 1024, 0, c->stream>>>(cursor, nb, base, info);

@@ -214,3 +214,34 @@ def test_region_search_matches_oracle_large(handle, O):
         lo = c - rng.uniform(0.5, 20, 3).astype(np.float32)
         hi = c + rng.uniform(0.5, 20, 3).astype(np.float32)
         assert (np.sort(handle.map_box_search(lo, hi)) == O.map_box_search(pts, valid, lo, hi)).all()
+
+
+def test_bucket_build_equals_radix_build(pkg, monkeypatch):
+    """large maps are built through fixed-capacity buckets (scatter + in-bucket shared-memory sort with every point ranked
+    by index inside its cell) instead of the radix sort: the sorted map must be the same — k-NN over both is bit-identical
+    and equals the exhaustive search"""
+    import torch
+    m = 1_200_000
+    mp = torch.from_numpy(pkg.synth.dense_map(1005, m)).cuda()
+    q = mp[torch.randperm(m, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))[:50000]].clone()
+    q[:, :3] += 0.01
+    res = {}
+    for mode in ("bucket", "radix"):
+        monkeypatch.setenv("ICP4R_BUCKET_MIN", "500000" if mode == "bucket" else "-1")
+        h = pkg.Icp4r(0)
+        n0 = h.launch_count()
+        h.map_build(mp)
+        launches = h.launch_count() - n0
+        idx, d2, found = h.map_knn(q, 5, 2.0)
+        h.synchronize()
+        res[mode] = (idx.cpu().numpy(), d2.cpu().numpy().view(np.int32), found.cpu().numpy(), launches)
+        if mode == "radix":
+            bi, bd, bf = h.map_knn_brute(q[:1000], 5, 2.0)
+            h.synchronize()
+            brute = (bi.cpu().numpy(), bd.cpu().numpy().view(np.int32), bf.cpu().numpy())
+        h.close()
+    assert res["bucket"][3] < res["radix"][3]          # really two different build paths
+    for a, b in zip(res["bucket"][:3], res["radix"][:3]):
+        assert np.array_equal(a, b)
+    for a, b in zip(res["radix"][:3], brute):
+        assert np.array_equal(a[:1000], b)
