@@ -401,12 +401,13 @@ def run_reference(args, rank, world):
     wl = "c4" if args.workload == "all" else args.workload
     if wl == "c4":
         # each step = a bounded sample of the 65,536-pair job: `threads` pairs in flight, ~20 s per step
-        n_sample = max(threads * 64, 1024)
+        step_s = float(os.environ.get("ICP4R_REF_STEP_S", "20"))   # seconds of CPU work per step (tests shrink it)
+        n_sample = max(threads * 64, 1024) if step_s >= 5 else max(threads * 2, 32)
         src, tgt, off = make_c4(n_sample)
-        kind, done, secs = cpu_pairs(src, tgt, C4_N, C4_ITERS, 20.0 * max(args.warmup, 1), threads, n_sample)   # warm-up
+        kind, done, secs = cpu_pairs(src, tgt, C4_N, C4_ITERS, step_s * max(args.warmup, 1), threads, n_sample)   # warm-up
         tot_done, tot_secs = 0, 0.0
         for _ in range(args.steps):
-            kind, done, secs = cpu_pairs(src, tgt, C4_N, C4_ITERS, 20.0, threads, n_sample)
+            kind, done, secs = cpu_pairs(src, tgt, C4_N, C4_ITERS, step_s, threads, n_sample)
             tot_done += done
             tot_secs += secs
             if tot_secs > 120.0:
