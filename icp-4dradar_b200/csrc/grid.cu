@@ -759,24 +759,25 @@ constexpr int INC_THREADS = 256;
 // search bounds of every block of the two merge passes below, so that the passes themselves start with a
 // (usually empty) range instead of a chain of dependent loads: bnd[b] = lower_bound(first key of block b); the entry
 // behind the last block is nf
-__global__ void __launch_bounds__(256) inc_bounds_old_kernel(const float4* __restrict__ sorted_old, int m_old, GridDesc g,
-                                                            const uint32_t* __restrict__ nkeys, int nf, int nblocks, int* __restrict__ bnd) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b > nblocks) return;
-    if (b == nblocks) {
-        bnd[b] = nf;
-        return;
+// both tables in ONE launch (they are independent: blocks [0, gb_old) fill the old-point bounds, the rest the cell bounds)
+__global__ void __launch_bounds__(256) inc_bounds_kernel(const float4* __restrict__ sorted_old, int m_old, GridDesc g, const uint32_t* __restrict__ nkeys,
+                                                        int nf, int ob, int* __restrict__ bnd_old, int gb_old, int cb, int* __restrict__ bnd_cell) {
+    if ((int)blockIdx.x < gb_old) {
+        const int b = blockIdx.x * blockDim.x + threadIdx.x;
+        if (b > ob) return;
+        if (b == ob) {
+            bnd_old[b] = nf;
+            return;
+        }
+        const float4 p = sorted_old[(size_t)b * INC_THREADS];
+        const uint32_t key = (uint32_t)(cell_of(p.z, g.oz, g.inv_cell, g.nz) * g.ny + cell_of(p.y, g.oy, g.inv_cell, g.ny)) * (uint32_t)g.nx +
+                             (uint32_t)cell_of(p.x, g.ox, g.inv_cell, g.nx);
+        bnd_old[b] = lower_bound_u32(nkeys, 0, nf, key);
+    } else {
+        const int b = ((int)blockIdx.x - gb_old) * blockDim.x + threadIdx.x;
+        if (b > cb) return;
+        bnd_cell[b] = b == cb ? nf : lower_bound_u32(nkeys, 0, nf, (uint32_t)b * INC_THREADS);
     }
-    const float4 p = sorted_old[(size_t)b * INC_THREADS];
-    const uint32_t key = (uint32_t)(cell_of(p.z, g.oz, g.inv_cell, g.nz) * g.ny + cell_of(p.y, g.oy, g.inv_cell, g.ny)) * (uint32_t)g.nx +
-                         (uint32_t)cell_of(p.x, g.ox, g.inv_cell, g.nx);
-    bnd[b] = lower_bound_u32(nkeys, 0, nf, key);
-}
-__global__ void __launch_bounds__(256) inc_bounds_cell_kernel(int ncells, const uint32_t* __restrict__ nkeys, int nf, int nblocks,
-                                                             int* __restrict__ bnd) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b > nblocks) return;
-    bnd[b] = b == nblocks ? nf : lower_bound_u32(nkeys, 0, nf, (uint32_t)b * INC_THREADS);
 }
 // old sorted point j moves to j + (new points in lower cells)
 __global__ void __launch_bounds__(INC_THREADS) inc_merge_old_kernel(const float4* __restrict__ sorted_old, int m_old, GridDesc g,
@@ -874,12 +875,12 @@ int map_append_incremental(Ctx* c, Map& mp, int n_new, bool* merged) {
         CKS(reserve_grow(c, mp.inc_bnd, ((size_t)(ob + 1) + (size_t)(cb + 1)) * sizeof(int)));
         int* bnd_old = mp.inc_bnd.as<int>();
         int* bnd_cell = bnd_old + (ob + 1);
-        inc_bounds_old_kernel<<<(ob + 1 + 255) / 256, 256, 0, c->stream>>>(g.sorted, m_old, g, ks, nf, ob, bnd_old);
-        inc_bounds_cell_kernel<<<(cb + 1 + 255) / 256, 256, 0, c->stream>>>(g.ncells, ks, nf, cb, bnd_cell);
+        const int gb_old = (ob + 1 + 255) / 256, gb_cell = (cb + 1 + 255) / 256;
+        inc_bounds_kernel<<<gb_old + gb_cell, 256, 0, c->stream>>>(g.sorted, m_old, g, ks, nf, ob, bnd_old, gb_old, cb, bnd_cell);
         inc_merge_old_kernel<<<ob, INC_THREADS, 0, c->stream>>>(g.sorted, m_old, g, ks, bnd_old, s_new);
         inc_merge_new_kernel<<<(nf + 255) / 256, 256, 0, c->stream>>>(mp.pts.as<float4>(), ks, vs, nf, g.cell_start, s_new, g, mp.coarse.as<uint32_t>());
         inc_cell_kernel<<<cb, INC_THREADS, 0, c->stream>>>(mp.cell_start.as<uint32_t>(), g.ncells, ks, bnd_cell);
-        c->launches += 5;
+        c->launches += 4;
         CK(cudaGetLastError());
         tr.mark("inc merge");
         std::swap(mp.sorted, mp.sorted_alt);
