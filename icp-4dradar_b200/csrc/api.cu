@@ -1076,8 +1076,8 @@ int icp4r_doppler_static_points(icp4r_handle h, const float* xyziv, int32_t n, i
     CKS(stage_in(c, c->d_src, xyziv, (size_t)n * 5 * sizeof(float), mem, &drec));
     CKS(reserve(c, c->d_found, (size_t)std::max(n, 1)));
     uint8_t* dmask = c->d_found.as<uint8_t>();
-    CKS(doppler_filter(c, static_cast<const float*>(drec), n, opts->iterations, opts->seed, opts->sigma, opts->split, dmask, c->h_pinned));
-    std::memcpy(res, c->h_pinned, sizeof(icp4r_doppler_result));
+    // the filter's result, the compaction and the count of static points are enqueued back to back: ONE host round trip
+    CKS(doppler_filter(c, static_cast<const float*>(drec), n, opts->iterations, opts->seed, opts->sigma, opts->split, dmask, c->h_pinned, false));
     float4* dout = reinterpret_cast<float4*>(xyzw_out);
     if (mem == ICP4R_HOST) {
         CKS(reserve(c, c->gs_pts, (size_t)std::max(cap, 1) * sizeof(float4)));
@@ -1090,6 +1090,7 @@ int icp4r_doppler_static_points(icp4r_handle h, const float* xyziv, int32_t n, i
     int* h_n = reinterpret_cast<int*>(static_cast<char*>(c->h_pinned) + 256);
     CK(cudaMemcpyAsync(h_n, d_n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    std::memcpy(res, c->h_pinned, sizeof(icp4r_doppler_result));
     *n_out = *h_n;
     if (mem == ICP4R_HOST && std::min(*n_out, cap) > 0) {
         CK(cudaMemcpyAsync(xyzw_out, dout, (size_t)std::min(*n_out, cap) * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));

@@ -295,7 +295,7 @@ int gicp_lm_step(Ctx* c, const RegParams* d_prm, RegState* d_st, int iter, int n
 
 // doppler.cu
 int doppler_filter(Ctx* c, const float* d_rec, int n, int iterations, uint64_t seed, double sigma, double split, uint8_t* d_mask,
-                   void* out_host);
+                   void* out_host, bool sync_now = true);
 
 // shard.cu
 int shard_allreduce(Ctx* c, double* d_buf, int count);

@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(1024) doppler_final_kernel(const float* __rest
 }
 
 int doppler_filter(Ctx* c, const float* d_rec, int n, int iterations, uint64_t seed, double sigma, double split, uint8_t* d_mask,
-                   void* out_host /* DopplerOut, pinned */) {
+                   void* out_host /* DopplerOut, pinned */, bool sync_now) {
     if (iterations <= 0) iterations = (int)(n * 0.2);  // fitSineRansac(..., PointsNum * 0.2), :389
     CKS(reserve_grow(c, c->d_q, (size_t)std::max(n, 1) * sizeof(DopplerPoint)));
     CKS(reserve_grow(c, c->d_partials, std::max((size_t)std::max(iterations, 1) * 24 + 256, (size_t)c->sm_count * 4 * ICP4R_ACC_LEN * sizeof(double) + 1024)));
@@ -195,7 +195,7 @@ int doppler_filter(Ctx* c, const float* d_rec, int n, int iterations, uint64_t s
     c->launches += 1;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out_host, d_out, sizeof(DopplerOut), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    if (sync_now) CK(cudaStreamSynchronize(c->stream));  // (a caller with more work to enqueue synchronises once, later)
     return ICP4R_OK;
 }
 
