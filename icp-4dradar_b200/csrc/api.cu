@@ -283,6 +283,8 @@ int icp4r_create(int device, icp4r_handle* out) {
         // measured on B200 (scripts/probe_map_kernels.py): the persistent loop is bit-identical but SLOWER than the captured
         // graph of per-iteration launches (C2 single 0.485 vs 0.436 ms, C5 0.762 vs 0.695 ms) — a kernel boundary inside a
         // graph costs ~1 us here, the in-kernel hand-over a release + an acquire round trip + the pose reload — so it is opt-in
+        if (const char* e = std::getenv("ICP4R_LB_SLACK_A")) c->slack_a = (float)std::atof(e);
+        if (const char* e = std::getenv("ICP4R_LB_SLACK_B")) c->slack_b = (float)std::atof(e);
         const char* np_ = std::getenv("ICP4R_PERSIST");
         c->use_persist = np_ && np_[0] == '1';
     }

@@ -171,6 +171,7 @@ struct RegParams {  // kernel parameters that change per call; lives in device m
     NbState* nb_state;
     int epoch;
     int pad_epoch;
+    float slack_a, slack_b;  // proof flavour: the search ball is widened by slack_a x (last displacement) unless that exceeds slack_b x r
 };
 
 struct GraphKey {
@@ -235,6 +236,7 @@ struct Ctx {
     bool batch_reproducible = false;  // ICP4R_BATCH_REPRODUCIBLE=1 (see register_batch.cu)
     float submap_cell = 0.f;  // icp4r_register_submap: occupancy-refined cell size of the last refined sub-map (0: none yet)
     int submap_m = 0, submap_uses = 0;
+    float slack_a = 4.0f, slack_b = 0.5f;  // ICP4R_LB_SLACK_A / ICP4R_LB_SLACK_B (A/B measurements)
     bool coop_ok = true;      // cleared when a cooperative launch was refused
     bool use_persist = false;  // ICP4R_PERSIST=1: single-scan loops as ONE cooperative launch (reg_loop_kernel) instead of a graph of per-iteration launches
     bool use_lb = true;     // ICP4R_NO_LB=1 turns the keep-the-neighbours-without-a-search proof off (A/B measurements)
